@@ -1,0 +1,749 @@
+// Non-GEMM kernels of the FB-DDPG step: replay gather, input staging, device RNG, LayerNorm+tanh,
+// L2 projection, action sampling, batch x batch loss, Q loss, bias column sums, Adam + soft update.
+#pragma once
+#include "common.cuh"
+
+#define FB_LN_EPS 1e-5f
+#define FB_NORMALIZE_EPS 1e-12f
+#define FB_CLAMP_EPS 1e-6f
+#define FB_MAX_LN_DIM 2048
+
+// ---- device-resident per-step scalars -------------------------------------------------------------
+struct DevScalars {
+  float stddev, stddev_clip, lr_forward, lr_backward, lr_actor, tau, replay_discount, replay_future, grad_scale;
+  float bc1_fb, bc2s_fb, bc1_actor, bc2s_actor;  // Adam bias corrections: 1-beta1^t, sqrt(1-beta2^t)
+  long long step_fb, step_actor;                 // 1-based Adam step counts
+  unsigned long long rng_counter;                // bumped once per FB_PHASE_SAMPLE
+};
+
+struct HostScalars {  // mirrors fb_step_scalars (fb_b200.h)
+  float stddev, stddev_clip, lr_forward, lr_backward, lr_actor, tau, replay_discount, replay_future, grad_scale;
+};
+
+__global__ void k_set_scalars(DevScalars* s, HostScalars h) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    s->stddev = h.stddev; s->stddev_clip = h.stddev_clip; s->lr_forward = h.lr_forward;
+    s->lr_backward = h.lr_backward; s->lr_actor = h.lr_actor; s->tau = h.tau;
+    s->replay_discount = h.replay_discount; s->replay_future = h.replay_future; s->grad_scale = h.grad_scale;
+  }
+}
+
+__global__ void k_set_adam_steps(DevScalars* s, long long fb, long long actor) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { s->step_fb = fb; s->step_actor = actor; }
+}
+
+// which: 0 = fb optimizer, 1 = actor optimizer, 2 = rng counter
+__global__ void k_tick(DevScalars* s, int which, float beta1, float beta2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (which == 2) { s->rng_counter += 1ull; return; }
+  long long t = (which == 0 ? s->step_fb : s->step_actor) + 1;
+  const double bc1 = 1.0 - pow((double)beta1, (double)t);
+  const double bc2 = 1.0 - pow((double)beta2, (double)t);
+  if (which == 0) { s->step_fb = t; s->bc1_fb = (float)bc1; s->bc2s_fb = (float)sqrt(bc2); }
+  else { s->step_actor = t; s->bc1_actor = (float)bc1; s->bc2s_actor = (float)sqrt(bc2); }
+}
+
+// ---- replay gather ----------------------------------------------------------------------------------
+// Packed storage row (fp32, every field starts on a 16-byte boundary):
+//   [observation(O) pad | action(A) pad | reward discount 0 0 | goal(G) pad]
+// Packed batch row produced by the gather:
+//   [obs | action | reward discount*gamma 0 0 | next_obs | goal | next_goal | future_obs | future_goal]
+// (in_memory_replay_buffer.py:162-183).  One warp handles one sampled transition; lane l moves the l-th,
+// (l+32)-th ... 128-bit chunk of the output row, so a warp reads the two adjacent storage rows (t-1, t)
+// as contiguous coalesced 16-byte loads.
+struct GatherSlot {   // one 16-byte chunk of the output row
+  short src_row;      // 0: row t-1, 1: row t, 2: row future-1, -1: zero fill
+  short special;      // 1: the [reward, discount, 0, 0] chunk (discount is scaled)
+  int src_f4;         // float4 index inside the storage row
+};
+#define FB_MAX_GATHER_SLOTS 192
+
+struct GatherParams {
+  const float* rows; const int* ep_len;
+  int rows_per_episode, row_stride;  // row_stride in floats (multiple of 4)
+  int n_slots, out_ld;               // out_ld in floats (multiple of 4)
+  GatherSlot slots[FB_MAX_GATHER_SLOTS];
+};
+
+__global__ void __launch_bounds__(256) k_gather_rows(const __grid_constant__ GatherParams gpv, const int* __restrict__ ep_idx,
+                                                     const int* __restrict__ step_idx, const int* __restrict__ future_idx,
+                                                     int batch, const float* __restrict__ discount_scale_dev,
+                                                     float discount_scale_host, float* __restrict__ out) {
+  const GatherParams* gp = &gpv;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= batch) return;
+  const float gamma = discount_scale_dev ? *discount_scale_dev : discount_scale_host;
+  const int ep = ep_idx[warp], t = step_idx[warp];
+  const int fut = future_idx ? future_idx[warp] : t;
+  const int stride4 = gp->row_stride >> 2;
+  const float4* base = reinterpret_cast<const float4*>(gp->rows) + (size_t)ep * gp->rows_per_episode * stride4;
+  const float4* r_prev = base + (size_t)(t - 1) * stride4;
+  const float4* r_cur = base + (size_t)t * stride4;
+  const float4* r_fut = base + (size_t)(fut - 1) * stride4;
+  float4* o = reinterpret_cast<float4*>(out + (size_t)warp * gp->out_ld);
+  const int n = gp->n_slots;
+  for (int s = lane; s < n; s += 32) {
+    const GatherSlot sl = gp->slots[s];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sl.src_row == 0) v = ld_stream_f4(r_prev + sl.src_f4);
+    else if (sl.src_row == 1) v = ld_stream_f4(r_cur + sl.src_f4);
+    else if (sl.src_row == 2) { if (future_idx) v = ld_stream_f4(r_fut + sl.src_f4); else continue; }
+    if (sl.special) { v.y *= gamma; v.z = 0.f; v.w = 0.f; }
+    o[s] = v;
+  }
+}
+
+// write one finished episode into packed storage (device-side repack of [rows, dim] field arrays)
+__global__ void k_pack_episode(float* __restrict__ dst_rows, int row_stride, int rows, int O, int A, int G, int off_action,
+                               int off_reward, int off_goal, const float* __restrict__ obs, const float* __restrict__ act,
+                               const float* __restrict__ rew, const float* __restrict__ disc, const float* __restrict__ goal) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  float* d = dst_rows + (size_t)r * row_stride;
+  for (int c = threadIdx.x; c < row_stride; c += blockDim.x) {
+    float v = 0.f;
+    if (c < O) v = obs[(size_t)r * O + c];
+    else if (c >= off_action && c < off_action + A) v = act[(size_t)r * A + (c - off_action)];
+    else if (c == off_reward) v = rew[r];
+    else if (c == off_reward + 1) v = disc[r];
+    else if (G > 0 && c >= off_goal && c < off_goal + G) v = goal[(size_t)r * G + (c - off_goal)];
+    d[c] = v;
+  }
+}
+
+// layout of the packed batch row (floats)
+struct BatchLayout {
+  int O, A, G;          // G == 0: no goal columns
+  int off_obs, off_action, off_rd, off_next_obs, off_goal, off_next_goal, off_future_obs, off_future_goal, pitch;
+};
+
+// tight user arrays -> packed batch rows (explicit-input path; fb_set_batch)
+__global__ void k_pack_batch(BatchLayout L, int batch, const float* __restrict__ obs, const float* __restrict__ action,
+                             const float* __restrict__ discount, const float* __restrict__ next_obs,
+                             const float* __restrict__ next_goal, float* __restrict__ out) {
+  const int r = blockIdx.x;
+  if (r >= batch) return;
+  float* o = out + (size_t)r * L.pitch;
+  for (int c = threadIdx.x; c < L.O; c += blockDim.x) {
+    o[L.off_obs + c] = obs[(size_t)r * L.O + c];
+    o[L.off_next_obs + c] = next_obs[(size_t)r * L.O + c];
+  }
+  for (int c = threadIdx.x; c < L.A; c += blockDim.x) o[L.off_action + c] = action[(size_t)r * L.A + c];
+  if (L.G > 0 && next_goal)
+    for (int c = threadIdx.x; c < L.G; c += blockDim.x) o[L.off_next_goal + c] = next_goal[(size_t)r * L.G + c];
+  if (threadIdx.x == 0) { o[L.off_rd] = 0.f; o[L.off_rd + 1] = discount[r]; }
+}
+
+// packed batch rows -> the concatenated network inputs of the step.
+//   actor_in_o  [2B, ldO ] = [next_obs ; obs]          actor_in_oz [2B, ldOZ] = [next_obs|. ; obs|.]  (z filled later)
+//   in_oa [B, ldOA] = [obs|action]   in_noa/in_oa2 [B, ldOA] = [next_obs|.] / [obs|.] (actions filled later)
+//   goal_next [B, ldG] = next_goal (or next_obs)        mix_in [B, ldG] = (goal or obs)[perm]   (fb_ddpg.py:460-468)
+//   disc -> column `disc_col` of the gather block
+struct StageParams {
+  BatchLayout L;
+  int batch, use_goal;
+  float* actor_in_o; int ldO;
+  float* actor_in_oz; int ldOZ;
+  float* in_oa; float* in_noa; float* in_oa2; int ldOA;
+  float* goal_next; float* mix_in; int ldG;
+  float* blk; int blk_pitch, disc_col;
+  const int* perm;            // null: identity (mix_in then holds un-permuted rows)
+  const float* mix_override;  // tight [B, G]: explicit backward_input[perm] from fb_set_batch, or null
+};
+
+__global__ void __launch_bounds__(128) k_stage_inputs(StageParams P, const float* __restrict__ packed) {
+  const int r = blockIdx.x;
+  if (r >= P.batch) return;
+  const BatchLayout& L = P.L;
+  const float* row = packed + (size_t)r * L.pitch;
+  const int B = P.batch;
+  for (int c = threadIdx.x; c < L.O; c += blockDim.x) {
+    const float o = row[L.off_obs + c], no = row[L.off_next_obs + c];
+    P.actor_in_o[(size_t)r * P.ldO + c] = no;
+    P.actor_in_o[(size_t)(B + r) * P.ldO + c] = o;
+    P.actor_in_oz[(size_t)r * P.ldOZ + c] = no;
+    P.actor_in_oz[(size_t)(B + r) * P.ldOZ + c] = o;
+    P.in_oa[(size_t)r * P.ldOA + c] = o;
+    P.in_oa2[(size_t)r * P.ldOA + c] = o;
+    P.in_noa[(size_t)r * P.ldOA + c] = no;
+  }
+  for (int c = threadIdx.x; c < L.A; c += blockDim.x) P.in_oa[(size_t)r * P.ldOA + L.O + c] = row[L.off_action + c];
+  const int G = P.use_goal ? L.G : L.O;
+  const int src = P.perm ? P.perm[r] : r;
+  const float* prow = packed + (size_t)src * L.pitch;
+  for (int c = threadIdx.x; c < G; c += blockDim.x) {
+    P.goal_next[(size_t)r * P.ldG + c] = P.use_goal ? row[L.off_next_goal + c] : row[L.off_next_obs + c];
+    float m;
+    if (P.mix_override) m = P.mix_override[(size_t)r * G + c];
+    else m = P.use_goal ? prow[L.off_goal + c] : prow[L.off_obs + c];
+    P.mix_in[(size_t)r * P.ldG + c] = m;
+  }
+  if (threadIdx.x == 0) P.blk[(size_t)r * P.blk_pitch + P.disc_col] = row[L.off_rd + 1];
+}
+
+// ---- device RNG (rng_device = 1) ----------------------------------------------------------------------
+// One warp per sampled transition: episode / step / future indices (in_memory_replay_buffer.py:147-161
+// semantics: uniform episode, uniform step in [1, len], future = step + Geometric(1-future) clipped),
+// the mix mask (fb_ddpg.py:471), z ~ sqrt(Z) * normalize(N(0,I)) (fb_ddpg.py:224-232) and both action-noise rows.
+struct RngParams {
+  unsigned long long seed;
+  int batch, rows_per_episode, Z, A, ldZ, ldA;
+  float mix_ratio;
+  const int* n_episodes;  // device scalar: len(buffer)
+  const int* ep_len;
+  int* ep_idx; int* step_idx; int* future_idx; int* mix_mask; unsigned int* perm_keys;
+  float* z_rand; float* noise_fb; float* noise_actor;
+};
+
+__global__ void __launch_bounds__(256) k_rng_draw(RngParams P, const DevScalars* __restrict__ sc) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= P.batch) return;
+  Philox ph(P.seed);
+  const unsigned long long ctr = sc->rng_counter;
+  if (lane == 0) {
+    // uniform over the valid transitions (ep, t), t in [1, len(ep)]: draw a padded slot and reject the
+    // padding.  Equals "uniform episode, uniform step" for fixed-length buffers and the length-weighted
+    // episode draw of in_memory_replay_buffer.py:149-151 for ragged ones.
+    const int n_ep = max(*P.n_episodes, 1);
+    const int tmax = max(P.rows_per_episode - 1, 1);
+    int ep = 0, t = 1, len = 1;
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t attempt = 0; attempt < 64u; ++attempt) {
+      r = ph(ctr, (uint32_t)warp, 8u + attempt);
+      ep = (int)(((unsigned long long)r.x * (unsigned long long)n_ep) >> 32);
+      t = 1 + (int)(((unsigned long long)r.y * (unsigned long long)tmax) >> 32);
+      len = P.ep_len[ep];
+      if (t <= len) break;
+      t = max(len, 1);  // only reached if all 64 attempts hit padding
+    }
+    int fut = t;
+    const float future = sc->replay_future;
+    if (future < 1.f) {
+      // Geometric(p = 1-future) on {1,2,...} by inversion
+      const float u = u01(r.z);
+      const float g = (future <= 0.f) ? 1.f : ceilf(logf(u) / logf(future));
+      fut = t + (int)fminf(fmaxf(g, 1.f), 1.0e9f);
+      fut = min(fut, len);
+    }
+    P.ep_idx[warp] = ep; P.step_idx[warp] = t; P.future_idx[warp] = fut;
+    P.mix_mask[warp] = (u01(r.w) - (1.0f / 16777216.0f) < P.mix_ratio) ? 1 : 0;
+    const uint4 q = ph(ctr, (uint32_t)warp, 1u);
+    P.perm_keys[warp] = q.x;
+  }
+  // z: Z normals, 4 per lane per pass
+  float ss = 0.f;
+  float zv[4];
+  for (int base = 0; base < P.Z; base += 128) {
+    const uint4 r = ph(ctr, (uint32_t)warp, 1024u + (uint32_t)(base / 128) * 32u + lane);
+    const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
+    zv[0] = n0.x; zv[1] = n0.y; zv[2] = n1.x; zv[3] = n1.y;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = base + lane * 4 + j;
+      if (c < P.Z) { ss += zv[j] * zv[j]; P.z_rand[(size_t)warp * P.ldZ + c] = zv[j]; }
+    }
+  }
+  ss = warp_sum(ss);
+  const float scale = sqrtf((float)P.Z) / fmaxf(sqrtf(ss), FB_NORMALIZE_EPS);
+  __syncwarp();
+  for (int c = lane; c < P.Z; c += 32) P.z_rand[(size_t)warp * P.ldZ + c] *= scale;
+  // action noise rows
+  for (int base = 0; base < P.A; base += 64) {
+    const uint4 r = ph(ctr, (uint32_t)warp, 4096u + (uint32_t)(base / 64) * 32u + lane);
+    const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
+    const int c = base + lane * 2;
+    if (c < P.A) { P.noise_fb[(size_t)warp * P.ldA + c] = n0.x; P.noise_actor[(size_t)warp * P.ldA + c] = n1.x; }
+    if (c + 1 < P.A) { P.noise_fb[(size_t)warp * P.ldA + c + 1] = n0.y; P.noise_actor[(size_t)warp * P.ldA + c + 1] = n1.y; }
+  }
+}
+
+// random permutation of [0, n): bitonic sort of (key, index) pairs in one CTA (torch.randperm, fb_ddpg.py:467)
+__global__ void __launch_bounds__(1024) k_randperm(const unsigned int* __restrict__ keys, int n, int npow2, int* __restrict__ perm) {
+  extern __shared__ unsigned long long sp[];
+  for (int i = threadIdx.x; i < npow2; i += blockDim.x)
+    sp[i] = (i < n) ? (((unsigned long long)keys[i] << 32) | (unsigned int)i) : 0xffffffffffffffffull;
+  __syncthreads();
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = sp[i], b = sp[ixj];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { sp[i] = b; sp[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = (int)(sp[i] & 0xffffffffull);
+}
+
+// ---- LayerNorm + tanh ("ntanh", fb_modules.py:49-50) ------------------------------------------------
+struct LnDesc {
+  const float* x; float* y; const float* gamma; const float* beta; float* mean; float* rstd;
+  int rows, D, ld, row_begin;  // row_begin: first global warp index of this problem
+};
+
+__global__ void __launch_bounds__(256) k_ln_tanh_fwd(const LnDesc* __restrict__ descs, int nprob, int total_rows) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= total_rows) return;
+  int p = 0;
+  while (p + 1 < nprob && descs[p + 1].row_begin <= gw) ++p;
+  const LnDesc d = descs[p];
+  const int r = gw - d.row_begin;
+  const float* x = d.x + (size_t)r * d.ld;
+  float s = 0.f;
+  for (int c = lane; c < d.D; c += 32) s += x[c];
+  const float mean = warp_sum(s) / (float)d.D;
+  float v = 0.f;
+  for (int c = lane; c < d.D; c += 32) { const float t = x[c] - mean; v += t * t; }
+  const float var = warp_sum(v) / (float)d.D;
+  const float rstd = 1.0f / sqrtf(var + FB_LN_EPS);
+  float* y = d.y + (size_t)r * d.ld;
+  for (int c = lane; c < d.D; c += 32) y[c] = tanhf((x[c] - mean) * rstd * __ldg(d.gamma + c) + __ldg(d.beta + c));
+  if (lane == 0) { d.mean[r] = mean; d.rstd[r] = rstd; }
+}
+
+struct LnBwdDesc {
+  const float* dy;   // grad w.r.t. the tanh output, [rows, ld_dy]
+  const float* y;    // saved tanh output
+  const float* x;    // saved pre-LayerNorm activations
+  const float* gamma; const float* mean; const float* rstd;
+  float* dx;         // grad w.r.t. x (may alias dy), [rows, ld_dy]
+  float* dgamma; float* dbeta;  // accumulated (atomics); both null when the affine grads are not needed
+  int rows, D, ld, ld_dy, cta_begin, cta_count;
+};
+#define FB_LN_BWD_ROWS_PER_CTA 16
+
+__global__ void __launch_bounds__(256) k_ln_tanh_bwd(const LnBwdDesc* __restrict__ descs, int nprob) {
+  __shared__ float s_dg[FB_MAX_LN_DIM];
+  __shared__ float s_db[FB_MAX_LN_DIM];
+  int p = 0;
+  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;
+  const LnBwdDesc d = descs[p];
+  const int cta = blockIdx.x - d.cta_begin;
+  const bool affine = d.dgamma != nullptr;
+  if (affine) {
+    for (int c = threadIdx.x; c < d.D; c += blockDim.x) { s_dg[c] = 0.f; s_db[c] = 0.f; }
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = cta * FB_LN_BWD_ROWS_PER_CTA;
+  const float invD = 1.0f / (float)d.D;
+  for (int rr = warp; rr < FB_LN_BWD_ROWS_PER_CTA; rr += 8) {
+    const int r = r0 + rr;
+    if (r >= d.rows) break;
+    const float* dy = d.dy + (size_t)r * d.ld_dy;
+    const float* y = d.y + (size_t)r * d.ld;
+    const float* x = d.x + (size_t)r * d.ld;
+    const float mean = d.mean[r], rstd = d.rstd[r];
+    float a = 0.f, b = 0.f;
+    for (int c = lane; c < d.D; c += 32) {
+      const float yy = y[c];
+      const float g = dy[c] * (1.f - yy * yy);
+      const float gg = g * __ldg(d.gamma + c);
+      const float xh = (x[c] - mean) * rstd;
+      a += gg; b += gg * xh;
+    }
+    a = warp_sum(a) * invD; b = warp_sum(b) * invD;
+    float* dx = d.dx + (size_t)r * d.ld_dy;
+    for (int c = lane; c < d.D; c += 32) {
+      const float yy = y[c];
+      const float g = dy[c] * (1.f - yy * yy);
+      const float gg = g * __ldg(d.gamma + c);
+      const float xh = (x[c] - mean) * rstd;
+      dx[c] = rstd * (gg - a - xh * b);
+      if (affine) { atomicAdd(&s_dg[c], g * xh); atomicAdd(&s_db[c], g); }
+    }
+  }
+  if (affine) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < d.D; c += blockDim.x) { atomicAdd(d.dgamma + c, s_dg[c]); atomicAdd(d.dbeta + c, s_db[c]); }
+  }
+}
+
+// ---- sqrt(Z) * F.normalize (fb_modules.py:33-40, 227-229) ------------------------------------------
+struct L2Desc { const float* x; float* y; float* nrm; int rows, Z, ldx, ldy, row_begin; };
+
+__global__ void __launch_bounds__(256) k_l2norm_fwd(const L2Desc* __restrict__ descs, int nprob, int total_rows) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= total_rows) return;
+  int p = 0;
+  while (p + 1 < nprob && descs[p + 1].row_begin <= gw) ++p;
+  const L2Desc d = descs[p];
+  const int r = gw - d.row_begin;
+  const float* x = d.x + (size_t)r * d.ldx;
+  float s = 0.f;
+  for (int c = lane; c < d.Z; c += 32) s += x[c] * x[c];
+  const float nrm = fmaxf(sqrtf(warp_sum(s)), FB_NORMALIZE_EPS);
+  const float sq = sqrtf((float)d.Z);
+  float* y = d.y + (size_t)r * d.ldy;
+  for (int c = lane; c < d.Z; c += 32) y[c] = sq * (x[c] / nrm);
+  if (lane == 0 && d.nrm) d.nrm[r] = nrm;
+}
+
+// dx = (sqrt(Z)/nrm) * (dy - xh * (xh . dy)),  xh = y / sqrt(Z)
+__global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
+                                                    const float* __restrict__ nrm, float* __restrict__ dx, int lddx, int rows, int Z) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float sq = sqrtf((float)Z), isq = 1.0f / sq;
+  float dot = 0.f;
+  for (int c = lane; c < Z; c += 32) dot += y[(size_t)r * ldy + c] * isq * dy[(size_t)r * lddy + c];
+  dot = warp_sum(dot);
+  const float k = sq / nrm[r];
+  for (int c = lane; c < Z; c += 32) {
+    const float xh = y[(size_t)r * ldy + c] * isq;
+    dx[(size_t)r * lddx + c] = k * (dy[(size_t)r * lddy + c] - xh * dot);
+  }
+}
+
+// ---- z finalisation (fb_ddpg.py:470-485): z[mix] = sqrt(Z) normalize(B(backward_input[perm])[mix]) ----
+struct ZFinalParams {
+  int batch, Z, O;
+  const float* z_rand; int ldZ;
+  const float* b_mix; int ld_bmix;      // already sqrt(Z)-normalised by BackwardMap; the reference renormalises
+  const int* mix_mask;                  // null: no mixing
+  float* z; float* actor_in_oz; int ldOZ;
+};
+
+__global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= P.batch) return;
+  const bool mix = P.mix_mask && P.mix_mask[r] != 0;
+  const float sq = sqrtf((float)P.Z);
+  const float* src = mix ? (P.b_mix + (size_t)r * P.ld_bmix) : (P.z_rand + (size_t)r * P.ldZ);
+  float nrm = 1.f;
+  if (mix) {
+    float s = 0.f;
+    for (int c = lane; c < P.Z; c += 32) s += src[c] * src[c];
+    nrm = fmaxf(sqrtf(warp_sum(s)), FB_NORMALIZE_EPS);
+  }
+  for (int c = lane; c < P.Z; c += 32) {
+    const float v = mix ? sq * (src[c] / nrm) : src[c];
+    P.z[(size_t)r * P.ldZ + c] = v;
+    P.actor_in_oz[(size_t)r * P.ldOZ + P.O + c] = v;
+    P.actor_in_oz[(size_t)(P.batch + r) * P.ldOZ + P.O + c] = v;
+  }
+}
+
+// ---- action sampling: mu = tanh(pre); TruncatedNormal.sample(clip) (utils.py:164-185) ---------------
+// rows [0,B): next_obs side with update_fb's noise -> next_action into in_noa[:, O:]
+// rows [B,2B): obs side with update_actor's noise  -> action into in_oa2[:, O:], log-prob metric
+struct ActorOutParams {
+  int batch, A, O;
+  const float* pre; float* mu; int ldA;
+  const float* noise_fb; const float* noise_actor; int ldN;
+  float* in_noa; float* in_oa2; int ldOA;
+  float* next_action; float* action_new;  // tight-ish copies [B, ldA] for inspection
+  double* acc;  // acc[ACC_LOGPROB]
+};
+
+// ---- accumulators (doubles) ------------------------------------------------------------------------
+enum {
+  // zeroed at the start of FB_PHASE_FB_FWD
+  ACC_OFFDIAG_SQ = 0,  // sum_{s!=t} sum_k (M_k - g*tM)^2
+  ACC_DIAG,            // sum_s sum_k M_k[s,s]
+  ACC_COV_OFF_SQ,      // sum_{s!=t} Cov^2
+  ACC_COV_DIAG,        // sum_s Cov[s,s]
+  ACC_TARGET_M,        // sum_{s,t} tM
+  ACC_M1,              // sum_{s,t} M1
+  ACC_LOGPROB,         // sum_s log N(a; mu, std)
+  ACC_PAD0,
+  // zeroed at the start of FB_PHASE_ACTOR_FWD
+  ACC_Q,               // sum_s min_k Q_k
+  ACC_PAD1,
+  // zeroed at the start of FB_PHASE_METRICS
+  ACC_F1, ACC_B, ACC_B_NORM, ACC_Z_NORM, ACC_ORTH_SQ, ACC_LINF_BITS,
+  ACC_COUNT = 16
+};
+
+__global__ void __launch_bounds__(256) k_actor_out(ActorOutParams P, const DevScalars* __restrict__ sc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = 2 * P.batch * P.A;
+  double lp = 0.0;
+  if (idx < total) {
+    const int r = idx / P.A, a = idx - r * P.A;
+    const float std = sc->stddev, clip = sc->stddev_clip;
+    const float mu = tanhf(P.pre[(size_t)r * P.ldA + a]);
+    P.mu[(size_t)r * P.ldA + a] = mu;
+    const bool fb_side = r < P.batch;
+    const int rb = fb_side ? r : r - P.batch;
+    const float nz = fb_side ? P.noise_fb[(size_t)rb * P.ldN + a] : P.noise_actor[(size_t)rb * P.ldN + a];
+    float eps = nz * std;
+    eps = fminf(fmaxf(eps, -clip), clip);
+    const float x = mu + eps;
+    const float act = fminf(fmaxf(x, -1.0f + FB_CLAMP_EPS), 1.0f - FB_CLAMP_EPS);
+    if (fb_side) {
+      P.in_noa[(size_t)rb * P.ldOA + P.O + a] = act;
+      P.next_action[(size_t)rb * P.ldA + a] = act;
+    } else {
+      P.in_oa2[(size_t)rb * P.ldOA + P.O + a] = act;
+      P.action_new[(size_t)rb * P.ldA + a] = act;
+      const float dlt = act - mu;
+      lp = (double)(-(dlt * dlt) / (2.f * std * std) - logf(std) - 0.91893853320467274178f);
+    }
+  }
+  lp = warp_sum_d(lp);
+  if ((threadIdx.x & 31) == 0 && lp != 0.0) atomicAdd(P.acc + ACC_LOGPROB, lp);
+}
+
+// ---- batch x batch loss, elementwise stage ----------------------------------------------------------
+// In:  M1,M2 = F_k . B^T; T1,T2 = tF_k . tB^T; Cov = B . B^T for a block of `nr` rows (global row index
+//      row0 + i) by `nc` columns (global).  Out (in place): G1,G2 = dL/dM_k, Gc = ortho_coef * dL_orth/dCov
+//      restricted to off-diagonal entries (the diagonal -2 mean(Cov_ss) term is added by k_loss_init_db).
+// fb_ddpg.py:320-326,344-347; gradient identities in SURVEY.md section 8a.
+struct LossElemParams {
+  float* M1; float* M2; const float* T1; const float* T2; float* Cov;
+  int nr, nc, ld, row0;
+  const float* disc; int disc_stride;  // discount of local row i at disc[i*disc_stride]
+  float inv_noff, inv_n, ortho_coef;
+  double* acc;
+};
+
+__global__ void __launch_bounds__(256) k_fb_loss_elem(LossElemParams P) {
+  double a_off = 0.0, a_diag = 0.0, a_cov = 0.0, a_covd = 0.0, a_tm = 0.0, a_m1 = 0.0;
+  for (int row = blockIdx.y; row < P.nr; row += gridDim.y) {
+  const float g = P.disc[(size_t)row * P.disc_stride];
+  const int diag_col = P.row0 + row;
+  const size_t base = (size_t)row * P.ld;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < P.nc; c += gridDim.x * blockDim.x) {
+    const float m1 = P.M1[base + c], m2 = P.M2[base + c];
+    const float tm = fminf(P.T1[base + c], P.T2[base + c]);
+    const float cv = P.Cov[base + c];
+    a_tm += tm; a_m1 += m1;
+    if (c != diag_col) {
+      const float d1 = m1 - g * tm, d2 = m2 - g * tm;
+      a_off += (double)d1 * d1 + (double)d2 * d2;
+      a_cov += (double)cv * cv;
+      P.M1[base + c] = d1 * P.inv_noff;
+      P.M2[base + c] = d2 * P.inv_noff;
+      P.Cov[base + c] = P.ortho_coef * 4.f * P.inv_noff * cv;
+    } else {
+      a_diag += (double)m1 + (double)m2;
+      a_covd += cv;
+      P.M1[base + c] = -P.inv_n;
+      P.M2[base + c] = -P.inv_n;
+      P.Cov[base + c] = 0.f;
+    }
+  }
+  }
+  __shared__ double red[6][8];
+  double vals[6] = {a_off, a_diag, a_cov, a_covd, a_tm, a_m1};
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const double v = warp_sum_d(vals[i]);
+    if (lane == 0) red[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
+    const int slot[6] = {ACC_OFFDIAG_SQ, ACC_DIAG, ACC_COV_OFF_SQ, ACC_COV_DIAG, ACC_TARGET_M, ACC_M1};
+    atomicAdd(P.acc + slot[threadIdx.x], s);
+  }
+}
+
+// Column-block twin of k_fb_loss_elem: rows are the LOCAL columns t of the loss matrices, columns run over
+// all global rows s:  Mt_k[t,s] = B_t . F_k[s],  Tt_k[t,s] = tB_t . tF_k[s].  Out (in place): Gt_k = dL/dM_k[s,t].
+// The discount now belongs to the column (s).  No accumulators (the row-block pass owns the loss sums).
+struct LossElemTParams {
+  float* M1; float* M2; const float* T1; const float* T2;
+  int nr, nc, ld, row0;
+  const float* disc; int disc_stride;  // discount of GLOBAL row s at disc[s*disc_stride]
+  float inv_noff, inv_n;
+};
+
+__global__ void __launch_bounds__(256) k_fb_loss_elem_t(LossElemTParams P) {
+  for (int row = blockIdx.y; row < P.nr; row += gridDim.y) {
+    const int diag_col = P.row0 + row;
+    const size_t base = (size_t)row * P.ld;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < P.nc; c += gridDim.x * blockDim.x) {
+      if (c != diag_col) {
+        const float g = __ldg(P.disc + (size_t)c * P.disc_stride);
+        const float tm = fminf(P.T1[base + c], P.T2[base + c]);
+        P.M1[base + c] = (P.M1[base + c] - g * tm) * P.inv_noff;
+        P.M2[base + c] = (P.M2[base + c] - g * tm) * P.inv_noff;
+      } else {
+        P.M1[base + c] = -P.inv_n;
+        P.M2[base + c] = -P.inv_n;
+      }
+    }
+  }
+}
+
+// dB starts from the diagonal term of the orthonormality loss: d(-2 c mean_s Cov_ss)/dB_s = -(4c/n) B_s
+__global__ void k_loss_init_db(float* __restrict__ dB, int lddb, const float* __restrict__ Bm, int ldb, int rows, int Z, float coef) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Z) return;
+  const int r = idx / Z, c = idx - r * Z;
+  dB[(size_t)r * lddb + c] = coef * Bm[(size_t)r * ldb + c];
+}
+
+// ---- actor Q loss (fb_ddpg.py:400-406): Q = min_k F_k . z, loss = -mean Q ------------------------
+__global__ void __launch_bounds__(256) k_actor_q(const float* __restrict__ F1, const float* __restrict__ F2, int ldf,
+                                                 const float* __restrict__ z, int ldz, float* __restrict__ dF1,
+                                                 float* __restrict__ dF2, int lddf, int rows, int Z, float inv_n, double* acc) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float q1 = 0.f, q2 = 0.f;
+  for (int c = lane; c < Z; c += 32) {
+    const float zz = z[(size_t)r * ldz + c];
+    q1 += F1[(size_t)r * ldf + c] * zz;
+    q2 += F2[(size_t)r * ldf + c] * zz;
+  }
+  q1 = warp_sum(q1); q2 = warp_sum(q2);
+  // torch.min(Q1, Q2) routes the gradient to the smaller entry (ties: split evenly)
+  const float w1 = (q1 < q2) ? 1.f : ((q1 == q2) ? 0.5f : 0.f);
+  const float w2 = 1.f - w1;
+  for (int c = lane; c < Z; c += 32) {
+    const float gz = -z[(size_t)r * ldz + c] * inv_n;
+    dF1[(size_t)r * lddf + c] = w1 * gz;
+    dF2[(size_t)r * lddf + c] = w2 * gz;
+  }
+  if (lane == 0) atomicAdd(acc + ACC_Q, (double)fminf(q1, q2));
+}
+
+// ---- bias gradients: column sums over the batch ----------------------------------------------------
+struct ColsumDesc { const float* src; float* dst; int rows, N, ld, cta_begin, ctas_n, ctas_r; };
+#define FB_COLSUM_ROWS_PER_CTA 128
+
+__global__ void __launch_bounds__(256) k_colsum(const ColsumDesc* __restrict__ descs, int nprob) {
+  int p = 0;
+  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;
+  const ColsumDesc d = descs[p];
+  const int local = blockIdx.x - d.cta_begin;
+  const int cn = local % d.ctas_n, cr = local / d.ctas_n;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = cn * 32 + tx;
+  const int r0 = cr * FB_COLSUM_ROWS_PER_CTA;
+  const int r1 = min(d.rows, r0 + FB_COLSUM_ROWS_PER_CTA);
+  float s = 0.f;
+  if (col < d.N)
+    for (int r = r0 + ty; r < r1; r += 8) s += d.src[(size_t)r * d.ld + col];
+  __shared__ float red[8][33];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && col < d.N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    atomicAdd(d.dst + col, t);
+  }
+}
+
+// ---- Adam (torch.optim.Adam defaults, fb_ddpg.py:146-151) + target soft update (utils.py:66-69) -------
+// p,g,m,v are flat fp32 segments of n floats (multiple of 4).  Elements [0, split) use lr_a, the rest lr_b
+// (the fb optimizer's two param groups).  `target` (nullable) is lerped towards the NEW parameters.
+// Gradients are cleared after use so the next step's atomically-accumulated dW start from zero.
+__global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                                              float4* __restrict__ v, float4* __restrict__ target, size_t n4, size_t split4,
+                                              const DevScalars* __restrict__ sc, int which, float beta1, float beta2, float eps) {
+  const float bc1 = which == 0 ? sc->bc1_fb : sc->bc1_actor;
+  const float bc2s = which == 0 ? sc->bc2s_fb : sc->bc2s_actor;
+  const float lr_a = which == 0 ? sc->lr_forward : sc->lr_actor;
+  const float lr_b = which == 0 ? sc->lr_backward : sc->lr_actor;
+  const float tau = sc->tau, gs = sc->grad_scale;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float step_size = (i < split4 ? lr_a : lr_b) / bc1;
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    float* pa = reinterpret_cast<float*>(&pp); float* ga = reinterpret_cast<float*>(&gg);
+    float* ma = reinterpret_cast<float*>(&mm); float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = ga[j] * gs;
+      ma[j] = ma[j] * beta1 + gr * (1.f - beta1);
+      va[j] = va[j] * beta2 + (gr * gr) * (1.f - beta2);
+      const float denom = sqrtf(va[j]) / bc2s + eps;
+      pa[j] = pa[j] - step_size * (ma[j] / denom);
+    }
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (target) {
+      float4 tt = target[i];
+      tt.x = tau * pp.x + (1.f - tau) * tt.x; tt.y = tau * pp.y + (1.f - tau) * tt.y;
+      tt.z = tau * pp.z + (1.f - tau) * tt.z; tt.w = tau * pp.w + (1.f - tau) * tt.w;
+      target[i] = tt;
+    }
+  }
+}
+
+// ---- metrics (fb_ddpg.py:356-377, 413-418) -----------------------------------------------------------
+// sums over the local rows of F1, B, |B_s|, |z_s|
+__global__ void __launch_bounds__(256) k_metric_rows(const float* __restrict__ F1, int ldf, const float* __restrict__ Bm, int ldb,
+                                                     const float* __restrict__ z, int ldz, int rows, int Z, double* acc) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float f = 0.f, b = 0.f, bb = 0.f, zz = 0.f;
+  for (int c = lane; c < Z; c += 32) {
+    const float bv = Bm[(size_t)r * ldb + c], zv = z[(size_t)r * ldz + c];
+    f += F1[(size_t)r * ldf + c]; b += bv; bb += bv * bv; zz += zv * zv;
+  }
+  f = warp_sum(f); b = warp_sum(b); bb = warp_sum(bb); zz = warp_sum(zz);
+  if (lane == 0) {
+    atomicAdd(acc + ACC_F1, (double)f); atomicAdd(acc + ACC_B, (double)b);
+    atomicAdd(acc + ACC_B_NORM, (double)sqrtf(bb)); atomicAdd(acc + ACC_Z_NORM, (double)sqrtf(zz));
+  }
+}
+
+// eye_diff = B^T B / n - I  (Z x Z): block a computes row a; linf via atomicMax on the float bits (values >= 0)
+__global__ void __launch_bounds__(128) k_metric_cov(const float* __restrict__ Bm, int ldb, int rows, int Z, double* acc,
+                                                    unsigned int* linf_bits) {
+  const int a = blockIdx.x;
+  float mx = 0.f, sq = 0.f;
+  for (int b = threadIdx.x; b < Z; b += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += Bm[(size_t)r * ldb + a] * Bm[(size_t)r * ldb + b];
+    const float e = s / (float)rows - (a == b ? 1.f : 0.f);
+    mx = fmaxf(mx, fabsf(e)); sq += e * e;
+  }
+  mx = warp_max(mx); sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) { atomicMax(linf_bits, __float_as_uint(mx)); atomicAdd(acc + ACC_ORTH_SQ, (double)sq); }
+}
+
+struct MetricFinalParams {
+  const double* acc; const unsigned int* linf_bits; float* out;
+  int n_local, n_global, Z; float ortho_coef;
+};
+// indices must match FB_M_* in fb_b200.h
+__global__ void k_metric_final(MetricFinalParams P) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double n = (double)P.n_global, nl = (double)P.n_local;
+  const double noff = n * (n - 1.0);
+  const double fb_off = 0.5 * P.acc[ACC_OFFDIAG_SQ] / noff;
+  const double fb_diag = -P.acc[ACC_DIAG] / n;
+  const double orth_off = P.acc[ACC_COV_OFF_SQ] / noff;
+  const double orth_diag = -2.0 * P.acc[ACC_COV_DIAG] / n;
+  const double orth = orth_off + orth_diag;
+  float* o = P.out;
+  o[0] = (float)(P.acc[ACC_TARGET_M] / (nl * n));
+  o[1] = (float)(P.acc[ACC_M1] / (nl * n));
+  o[2] = (float)(P.acc[ACC_F1] / (nl * P.Z));
+  o[3] = (float)(P.acc[ACC_B] / (nl * P.Z));
+  o[4] = (float)(P.acc[ACC_B_NORM] / nl);
+  o[5] = (float)(P.acc[ACC_Z_NORM] / nl);
+  o[6] = (float)(fb_off + fb_diag + (double)P.ortho_coef * orth);
+  o[7] = (float)fb_diag;
+  o[8] = (float)fb_off;
+  o[9] = (float)orth;
+  o[10] = (float)orth_diag;
+  o[11] = (float)orth_off;
+  o[12] = __uint_as_float(*P.linf_bits);
+  o[13] = (float)(sqrt(P.acc[ACC_ORTH_SQ]) / sqrt((double)P.Z));
+  o[14] = (float)(-P.acc[ACC_Q] / n);
+  o[15] = (float)(P.acc[ACC_Q] / n);
+  o[16] = (float)(P.acc[ACC_LOGPROB] / n);
+}
+
+// ---- fp32 FMA-chain microbenchmark (roofline denominator for the CUDA-core GEMMs) ---------------------
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float b = 1.000001f, c = 1e-7f;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+    a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;
+}

@@ -1,0 +1,203 @@
+/*
+ * fb_b200.h — C ABI of libfb_b200.so: the FB-DDPG gradient step on one B200 (sm_100a).
+ *
+ * The reference (facebookresearch/controllable_agent) is pure Python/PyTorch and has no FFI; its
+ * seam for this path is the Python method surface of FBDDPGAgent / ReplayBuffer.  This header is
+ * the boundary a maintainer would bind (ctypes stub in INTEGRATION.md) to replace, per entry point:
+ *
+ *   fb_replay_*           url_benchmark/in_memory_replay_buffer.py:104-133 (add), :139-190 (sample)
+ *                         url_benchmark/replay_buffer.py:50-63 (EpisodeBatch.to)
+ *   fb_set_batch/z/noise  explicit-input form of fb_ddpg.py:433-468 (used by parity tests and by a
+ *                         host-resident replay buffer feeding the device step)
+ *   FB_PHASE_SAMPLE       fb_ddpg.py:433-434,451,467,471 + utils.py:178 (index/z/noise draws + gather)
+ *   FB_PHASE_MIX          fb_ddpg.py:470-485 (z mixing through backward_net)
+ *   FB_PHASE_FB_FWD/LOSS/BWD   fb_ddpg.py:303-348,380-383 (update_fb forward, loss, backward)
+ *   FB_PHASE_FB_ADAM      fb_ddpg.py:384 (fb_opt.step) fused with utils.py:66-69 soft_update_params
+ *                         (fb_ddpg.py:500-503; legal because update_actor never writes F/B)
+ *   FB_PHASE_ACTOR_FWD/BWD     fb_ddpg.py:389-410 (update_actor forward, Q loss, backward)
+ *   FB_PHASE_ACTOR_ADAM   fb_ddpg.py:411 (actor_opt.step)
+ *
+ * Conventions: every pointer argument named d_* is a DEVICE pointer into caller-owned fp32 (or
+ * int32 where stated) contiguous memory; h_* is a HOST pointer.  The library never allocates
+ * parameter/optimizer/replay memory and never takes ownership.  Calls enqueue work on `stream`
+ * (a cudaStream_t passed as void*) and do not synchronise unless documented.  Return value:
+ * 0 = ok, negative = argument/state error (FB_E_*), positive = cudaError_t.  A handle may be used
+ * from one host thread at a time.  No global state.
+ */
+#ifndef FB_B200_H
+#define FB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_ABI_VERSION 1
+
+enum {
+  FB_OK = 0,
+  FB_E_ARG = -1,        /* bad argument */
+  FB_E_STATE = -2,      /* called before fb_bind / unsupported in this state */
+  FB_E_UNSUPPORTED = -3 /* configuration branch the kernels do not implement */
+};
+
+/* nets, in the order their flat segments are described */
+enum { FB_NET_FORWARD = 0, FB_NET_BACKWARD = 1, FB_NET_ACTOR = 2 };
+
+/* phases of one gradient step; OR them into fb_run's mask */
+enum {
+  FB_PHASE_SAMPLE = 1 << 0,     /* device RNG draws (if rng_device) + replay gather into the step inputs */
+  FB_PHASE_MIX = 1 << 1,        /* B(backward_input[perm]) on mix rows -> z */
+  FB_PHASE_FB_FWD = 1 << 2,     /* actor(next_obs,z), actor(obs,z), F_tgt, B_tgt, F, B forwards */
+  FB_PHASE_FB_LOSS = 1 << 3,    /* batch x batch contraction, fb/orth losses, dF1 dF2 dB */
+  FB_PHASE_FB_BWD = 1 << 4,     /* backward through forward_net / backward_net -> grad_fb */
+  FB_PHASE_FB_ADAM = 1 << 5,    /* Adam on F,B + target soft update + grad clear */
+  FB_PHASE_ACTOR_FWD = 1 << 6,  /* F(obs,z,a) with updated F, Q = min_k F_k.z, actor loss */
+  FB_PHASE_ACTOR_BWD = 1 << 7,  /* dQ -> dF -> da -> backward through actor -> grad_actor */
+  FB_PHASE_ACTOR_ADAM = 1 << 8, /* Adam on actor + grad clear */
+  FB_PHASE_METRICS = 1 << 9,    /* finalise the metrics block (means, orth_linf, orth_l2) */
+  FB_PHASE_ALL = (1 << 10) - 1
+};
+
+/* index of each scalar in the metrics block (float[FB_METRIC_COUNT]) — keys of the dict returned
+ * by FBDDPGAgent.update, fb_ddpg.py:357-377,414-418 */
+enum {
+  FB_M_TARGET_M = 0, FB_M_M1, FB_M_F1, FB_M_B, FB_M_B_NORM, FB_M_Z_NORM, FB_M_FB_LOSS, FB_M_FB_DIAG,
+  FB_M_FB_OFFDIAG, FB_M_ORTH_LOSS, FB_M_ORTH_LOSS_DIAG, FB_M_ORTH_LOSS_OFFDIAG, FB_M_ORTH_LINF, FB_M_ORTH_L2,
+  FB_M_ACTOR_LOSS, FB_M_Q, FB_M_ACTOR_LOGPROB, FB_M_COUNT_USED,
+  FB_METRIC_COUNT = 32
+};
+
+typedef struct fb_config {
+  int32_t abi_version;         /* FB_ABI_VERSION */
+  int32_t batch;               /* rows this process handles per step (B, or B/world for sharded runs) */
+  int32_t global_batch;        /* n in the loss normalisation (1/n, 1/(n(n-1))); == batch on one GPU */
+  int32_t row_offset;          /* global row index of local row 0 (diagonal position); 0 on one GPU */
+  int32_t obs_dim, action_dim, z_dim, goal_dim; /* goal_dim == obs_dim when use_goal == 0 */
+  int32_t hidden_dim, feature_dim, backward_hidden_dim;
+  int32_t use_goal;            /* goal_space is not None: B reads goal / next_goal instead of obs */
+  int32_t rng_device;          /* 1: indices, perm, mix mask, z and action noise are drawn on the device
+                                  (Philox) inside FB_PHASE_SAMPLE; 0: the caller provides them */
+  float ortho_coef, mix_ratio;
+  float beta1, beta2, adam_eps; /* torch.optim.Adam defaults 0.9 / 0.999 / 1e-8 */
+  uint64_t seed;               /* Philox seed for rng_device */
+} fb_config;
+
+/* per-step scalars (host values; copied to the device by fb_set_step_scalars) */
+typedef struct fb_step_scalars {
+  float stddev, stddev_clip;   /* utils.schedule(stddev_schedule, step), cfg.stddev_clip */
+  float lr_forward, lr_backward, lr_actor; /* lr, lr_coef*lr, lr (fb_ddpg.py:146-151) */
+  float tau;                   /* fb_target_tau */
+  float replay_discount;       /* ReplayBuffer._discount */
+  float replay_future;         /* ReplayBuffer._future (only read by rng_device draws) */
+  float grad_scale;            /* multiplies gradients inside Adam (1 on one GPU) */
+} fb_step_scalars;
+
+/* caller-owned device memory the handle works on */
+typedef struct fb_buffers {
+  /* flat fp32 segments; sizes from fb_flat_size().  fb = [forward_net | backward_net] */
+  float* d_param_fb; float* d_grad_fb; float* d_m_fb; float* d_v_fb; float* d_target_fb;
+  float* d_param_actor; float* d_grad_actor; float* d_m_actor; float* d_v_actor;
+  void* d_workspace; size_t workspace_bytes;  /* >= fb_workspace_bytes(), zero-initialised by fb_bind */
+} fb_buffers;
+
+/* replay storage resident in HBM: one packed fp32 row per (episode, time) of
+ * [observation | action | reward | discount | goal], row stride `row_stride` floats (multiple of 4) */
+typedef struct fb_replay_view {
+  const float* d_rows;          /* [max_episodes, rows_per_episode, row_stride] */
+  const int32_t* d_episode_len; /* [max_episodes] transitions per episode (rows-1) */
+  int32_t max_episodes, rows_per_episode, row_stride;
+  int32_t n_episodes;           /* len(buffer): episodes currently sampleable */
+  int32_t off_obs, off_action, off_reward, off_discount, off_goal; /* column offsets; off_goal<0 if absent */
+} fb_replay_view;
+
+typedef struct fb_handle fb_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int fb_abi_version(void);
+const char* fb_error_string(int code);
+int fb_create(const fb_config* cfg, fb_handle** out);
+void fb_destroy(fb_handle* h);
+
+/* ---- layout queries (valid right after fb_create) ------------------------------------------ */
+/* total floats of the fb flat segment (forward_net then backward_net) / of the actor segment */
+size_t fb_flat_size(const fb_handle* h, int actor /*0: fb, 1: actor*/);
+/* number of parameter tensors of a net, in nn.Module registration order */
+int fb_num_tensors(const fb_handle* h, int net);
+/* tensor `index` of `net`: offset (floats) inside its flat segment (fb for FORWARD/BACKWARD, actor
+ * for ACTOR), shape rows x cols (cols == 0 for 1-D tensors); name is written NUL-terminated */
+int fb_tensor_info(const fb_handle* h, int net, int index, size_t* offset, int* rows, int* cols,
+                   char* name, size_t name_cap);
+size_t fb_workspace_bytes(const fb_handle* h);
+
+/* ---- binding --------------------------------------------------------------------------------- */
+/* record the caller's buffers, zero the workspace, build the launch plan (synchronises once) */
+int fb_bind(fb_handle* h, const fb_buffers* bufs, void* stream);
+int fb_bind_replay(fb_handle* h, const fb_replay_view* view);
+
+/* ---- per-step inputs --------------------------------------------------------------------------- */
+int fb_set_step_scalars(fb_handle* h, const fb_step_scalars* s, void* stream);
+/* rng_device == 0: int32 draws made by the caller exactly as the reference makes them
+ * (in_memory_replay_buffer.py:147-161, fb_ddpg.py:467,471): ep_idx, step_idx, future_idx (may be
+ * NULL), perm, mix_mask (0/1).  Device pointers, length batch each. */
+int fb_set_indices(fb_handle* h, const int32_t* d_ep_idx, const int32_t* d_step_idx, const int32_t* d_future_idx,
+                   const int32_t* d_perm, const int32_t* d_mix_mask, void* stream);
+/* explicit transitions instead of FB_PHASE_SAMPLE's gather (row-major [batch, dim], tight; what
+ * EpisodeBatch.to(device) yields, replay_buffer.py:50-63).  d_goal / d_next_goal may be NULL when
+ * use_goal == 0 (obs / next_obs are used).  d_goal is NOT permuted: the library applies `perm` from
+ * fb_set_indices when it builds backward_input (fb_ddpg.py:460-468).  d_discount is [batch], already
+ * multiplied by the replay discount. */
+int fb_set_batch(fb_handle* h, const float* d_obs, const float* d_action, const float* d_discount,
+                 const float* d_next_obs, const float* d_goal, const float* d_next_goal, void* stream);
+/* rng_device == 0: the random z of fb_ddpg.py:451 ([batch, z_dim], rows of norm sqrt(z_dim)) */
+int fb_set_z(fb_handle* h, const float* d_z, void* stream);
+/* rng_device == 0: the two N(0,1) draws of utils.py:178 ([batch, action_dim] each): update_fb's
+ * next-action noise and update_actor's action noise */
+int fb_set_noise(fb_handle* h, const float* d_noise_fb, const float* d_noise_actor, void* stream);
+
+/* ---- the step -------------------------------------------------------------------------------- */
+/* enqueue the phases in `phase_mask` in step order.  use_graph != 0 replays a CUDA graph captured
+ * (once per mask) from the same launch sequence. */
+int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream);
+/* number of kernel launches (graph nodes) fb_run(mask) issues */
+int fb_launch_count(fb_handle* h, uint32_t phase_mask);
+/* device pointer to the metrics block, float[FB_METRIC_COUNT], indices FB_M_* */
+const float* fb_metrics_ptr(const fb_handle* h);
+/* 1-based Adam step counters live on the device; these set them (checkpoint restore) */
+int fb_set_adam_steps(fb_handle* h, int64_t fb_step, int64_t actor_step, void* stream);
+int fb_get_adam_steps(fb_handle* h, int64_t* fb_step, int64_t* actor_step, void* stream); /* synchronises */
+
+/* ---- multi-GPU hooks (exact global-batch loss; see DESIGN.md "Multi-GPU") --------------------- */
+/* packed per-row block [F1|F2|tF1|tF2|B|tB|discount] each rank contributes to the all-gather that
+ * sits between FB_PHASE_FB_FWD and FB_PHASE_FB_LOSS; floats per row / local + gathered pointers */
+int fb_gather_block(fb_handle* h, int* floats_per_row, float** d_local, float** d_global);
+
+/* ---- introspection for tests: named views into the workspace --------------------------------- */
+/* names: "obs","next_obs","action","discount","z","next_action","action_new","F1","F2","tF1","tF2",
+ * "B","tB","dF1","dF2","dB","mu","mix_input","next_goal", ... returns rows, cols, leading dim */
+int fb_workspace_view(fb_handle* h, const char* name, float** d_ptr, int* rows, int* cols, int* ld);
+
+/* ---- stand-alone operators (tests, microbenchmarks) ------------------------------------------- */
+/* the replay gather alone: out rows [batch, out_ld] = [obs|action|reward|discount|next_obs|goal|next_goal|
+ * future_obs|future_goal] (goal parts only if the view has goals), discount multiplied by
+ * replay_discount.  future_idx may be NULL (those columns are then left untouched). */
+int fb_replay_gather(const fb_replay_view* view, const int32_t* d_ep_idx, const int32_t* d_step_idx,
+                     const int32_t* d_future_idx, int batch, float replay_discount, float* d_out, int out_ld,
+                     void* stream);
+/* write one finished episode ([rows, dim] host-or-device fp32 arrays already on the device) into the
+ * packed storage: dst row block = rows of episode `slot` */
+int fb_replay_pack_episode(const fb_replay_view* view, float* d_rows_mut, int slot, int rows, const float* d_obs,
+                           const float* d_action, const float* d_reward, const float* d_discount,
+                           const float* d_goal, void* stream);
+/* C[M,N] (+)= op(A)·op(B)^T with the grouped SIMT SGEMM used by the plan (single problem) */
+int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, int M, int N, int K, int lda, int ldb,
+             int ldc, int a_kmajor, int b_kmajor, int relu, int splitk, void* stream);
+/* FMA-chain microbenchmark: returns measured fp32 TFLOP/s of the CUDA cores (synchronises) */
+int fb_fp32_peak_tflops(double* out_tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FB_B200_H */
