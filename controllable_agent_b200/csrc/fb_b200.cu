@@ -1,0 +1,935 @@
+// libfb_b200.so — the FB-DDPG gradient step (url_benchmark/agent/fb_ddpg.py:427-520) on one B200, C ABI of
+// include/fb_b200.h.  sm_100a only; no CPU route.
+#include "plan.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+#define CKE(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+static int phase_index(uint32_t bit) { int i = 0; while ((1u << i) != bit) ++i; return i; }
+
+// ------------------------------------------------------------------------------------------------
+// op recorders
+// ------------------------------------------------------------------------------------------------
+struct Builder {
+  fb_handle* h;
+  char* d_arena;
+  int phase = 0;
+  void set_phase(uint32_t bit) { phase = phase_index(bit); }
+  void push(Op op) { h->ops[phase].push_back(std::move(op)); }
+
+  void gemm(std::vector<GemmDesc> g) {
+    if (g.empty()) return;
+    GroupLaunch gl = finalize_group(h, std::move(g), d_arena);
+    push([gl](cudaStream_t s) {
+      k_gemm_grouped<<<gl.ctas, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(gl.d_descs, gl.nprob);
+      return cudaGetLastError();
+    });
+  }
+  void ln_fwd(std::vector<LnDesc> v) {
+    int rows = 0;
+    for (auto& d : v) { d.row_begin = rows; rows += d.rows; }
+    const LnDesc* dd = arena_put(h, v, d_arena);
+    const int n = (int)v.size();
+    push([dd, n, rows](cudaStream_t s) {
+      k_ln_tanh_fwd<<<fb_ceil_div(rows, 8), 256, 0, s>>>(dd, n, rows);
+      return cudaGetLastError();
+    });
+  }
+  void ln_bwd(std::vector<LnBwdDesc> v) {
+    int ctas = 0;
+    for (auto& d : v) { d.cta_begin = ctas; d.cta_count = fb_ceil_div(d.rows, FB_LN_BWD_ROWS_PER_CTA); ctas += d.cta_count; }
+    const LnBwdDesc* dd = arena_put(h, v, d_arena);
+    const int n = (int)v.size();
+    push([dd, n, ctas](cudaStream_t s) {
+      k_ln_tanh_bwd<<<ctas, 256, 0, s>>>(dd, n);
+      return cudaGetLastError();
+    });
+  }
+  void l2_fwd(std::vector<L2Desc> v) {
+    int rows = 0;
+    for (auto& d : v) { d.row_begin = rows; rows += d.rows; }
+    const L2Desc* dd = arena_put(h, v, d_arena);
+    const int n = (int)v.size();
+    push([dd, n, rows](cudaStream_t s) {
+      k_l2norm_fwd<<<fb_ceil_div(rows, 8), 256, 0, s>>>(dd, n, rows);
+      return cudaGetLastError();
+    });
+  }
+  void colsum(std::vector<ColsumDesc> v) {
+    int ctas = 0;
+    for (auto& d : v) {
+      d.cta_begin = ctas; d.ctas_n = fb_ceil_div(d.N, 32); d.ctas_r = fb_ceil_div(d.rows, FB_COLSUM_ROWS_PER_CTA);
+      ctas += d.ctas_n * d.ctas_r;
+    }
+    const ColsumDesc* dd = arena_put(h, v, d_arena);
+    const int n = (int)v.size();
+    push([dd, n, ctas](cudaStream_t s) {
+      k_colsum<<<ctas, 256, 0, s>>>(dd, n);
+      return cudaGetLastError();
+    });
+  }
+  void memset0(void* p, size_t bytes) {
+    push([p, bytes](cudaStream_t s) { return cudaMemsetAsync(p, 0, bytes, s); });
+  }
+};
+
+static ColsumDesc mk_colsum(const Mat& src, float* dst) {
+  ColsumDesc d; memset(&d, 0, sizeof(d));
+  d.src = src.p; d.dst = dst; d.rows = src.rows; d.N = src.cols; d.ld = src.ld;
+  return d;
+}
+
+// activations of one "embed" block: Linear -> LayerNorm -> Tanh -> Linear -> ReLU  (fb_modules.py:60-78)
+struct EmbedAct { Mat x, pre, y, out; float* mean; float* rstd; };
+static EmbedAct embed_alloc(fb_handle* h, const Mat& x, const Mat& out, int H, const std::string& name) {
+  EmbedAct e; e.x = x; e.out = out;
+  e.pre = ws_mat(h, x.rows, H, (name + ".pre").c_str());
+  e.y = ws_mat(h, x.rows, H, (name + ".y").c_str());
+  e.mean = (float*)ws_alloc(h, x.rows * sizeof(float));
+  e.rstd = (float*)ws_alloc(h, x.rows * sizeof(float));
+  return e;
+}
+static LnDesc embed_ln(const EmbedAct& e, const PSet& p) {
+  LnDesc d; memset(&d, 0, sizeof(d));
+  d.x = e.pre.p; d.y = e.y.p; d.gamma = p.v(2); d.beta = p.v(3); d.mean = e.mean; d.rstd = e.rstd;
+  d.rows = e.pre.rows; d.D = e.pre.cols; d.ld = e.pre.ld;
+  return d;
+}
+// backward of LN+tanh for rows [r0, r0+n) of an embed block: dy (grad wrt tanh output) -> dx in place
+static LnBwdDesc embed_ln_bwd(const EmbedAct& e, const PSet& p, const Mat& dy, int r0, bool affine) {
+  LnBwdDesc d; memset(&d, 0, sizeof(d));
+  d.dy = dy.p; d.dx = dy.p; d.y = e.y.p + (size_t)r0 * e.y.ld; d.x = e.pre.p + (size_t)r0 * e.pre.ld;
+  d.gamma = p.v(2); d.mean = e.mean + r0; d.rstd = e.rstd + r0;
+  d.dgamma = affine ? p.gv(2) : nullptr; d.dbeta = affine ? p.gv(3) : nullptr;
+  d.rows = dy.rows; d.D = dy.cols; d.ld = e.y.ld; d.ld_dy = dy.ld;
+  return d;
+}
+
+// activations of one BackwardMap instance: Linear -> LN -> Tanh -> Linear -> ReLU -> Linear -> sqrt(Z) normalize
+struct BAct { Mat x, pre, y, h2, raw, out; float* mean; float* rstd; float* nrm; };
+static BAct b_alloc(fb_handle* h, const Mat& x, const Mat& out, const std::string& name) {
+  const fb_config& c = h->cfg;
+  BAct b; b.x = x; b.out = out;
+  b.pre = ws_mat(h, x.rows, c.backward_hidden_dim, (name + ".pre").c_str());
+  b.y = ws_mat(h, x.rows, c.backward_hidden_dim, (name + ".y").c_str());
+  b.h2 = ws_mat(h, x.rows, c.backward_hidden_dim, (name + ".h2").c_str());
+  b.raw = ws_mat(h, x.rows, c.z_dim, (name + ".raw").c_str());
+  b.mean = (float*)ws_alloc(h, x.rows * sizeof(float));
+  b.rstd = (float*)ws_alloc(h, x.rows * sizeof(float));
+  b.nrm = (float*)ws_alloc(h, x.rows * sizeof(float));
+  return b;
+}
+static LnDesc b_ln(const BAct& b, const PSet& p) {
+  LnDesc d; memset(&d, 0, sizeof(d));
+  d.x = b.pre.p; d.y = b.y.p; d.gamma = p.v(2); d.beta = p.v(3); d.mean = b.mean; d.rstd = b.rstd;
+  d.rows = b.pre.rows; d.D = b.pre.cols; d.ld = b.pre.ld;
+  return d;
+}
+static L2Desc b_l2(const BAct& b, int Z) {
+  L2Desc d; memset(&d, 0, sizeof(d));
+  d.x = b.raw.p; d.y = b.out.p; d.nrm = b.nrm; d.rows = b.raw.rows; d.Z = Z; d.ldx = b.raw.ld; d.ldy = b.out.ld;
+  return d;
+}
+
+// head: Linear(2Fd -> H) -> ReLU -> Linear(H -> out)
+struct HeadAct { Mat h1, out; };
+
+// ------------------------------------------------------------------------------------------------
+// the plan
+// ------------------------------------------------------------------------------------------------
+static int build_gather_params(const fb_replay_view& v, GatherParams& gp, const BatchLayout& L, int out_ld);
+static void make_batch_layout(BatchLayout& L, int O, int A, int G, int X, int with_future);
+
+static int build_plan(fb_handle* h) {
+  const fb_config& c = h->cfg;
+  const int B = c.batch, n = c.global_batch, O = c.obs_dim, A = c.action_dim, Z = c.z_dim, H = c.hidden_dim, Fd = c.feature_dim;
+  const int G = c.goal_dim;
+  const bool use_goal = c.use_goal != 0;
+  for (auto& v : h->ops) v.clear();
+  h->views.clear();
+  h->arena.clear();
+  h->ws_off = 0;
+
+  char* d_arena = (char*)ws_alloc(h, FB_DESC_ARENA_BYTES);
+  h->d_sc = (DevScalars*)ws_alloc(h, sizeof(DevScalars));
+  h->d_acc = (double*)ws_alloc(h, ACC_COUNT * sizeof(double));
+  h->d_linf = (unsigned int*)ws_alloc(h, 16);
+  h->d_metrics = (float*)ws_alloc(h, FB_METRIC_COUNT * sizeof(float));
+  h->d_n_episodes = (int*)ws_alloc(h, 16);
+  h->d_ep_idx = (int*)ws_alloc(h, B * sizeof(int));
+  h->d_step_idx = (int*)ws_alloc(h, B * sizeof(int));
+  h->d_future_idx = (int*)ws_alloc(h, B * sizeof(int));
+  h->d_perm = (int*)ws_alloc(h, B * sizeof(int));
+  h->d_identity_perm = (int*)ws_alloc(h, B * sizeof(int));
+  h->d_mix_mask = (int*)ws_alloc(h, B * sizeof(int));
+  h->d_perm_keys = (unsigned int*)ws_alloc(h, B * sizeof(int));
+
+  // ---- packed batch rows ---------------------------------------------------------------------
+  BatchLayout& L = h->bl;
+  make_batch_layout(L, O, A, use_goal ? G : 0, 0, 0);  // the step does not read meta / hindsight fields (future_ratio = 0)
+  h->packed = ws_mat(h, B, L.pitch, "packed");
+
+  // ---- step inputs ---------------------------------------------------------------------------
+  Mat actor_in_o = ws_mat(h, 2 * B, O, "actor_in_o");
+  Mat actor_in_oz = ws_mat(h, 2 * B, O + Z, "actor_in_oz");
+  Mat in_oa = ws_mat(h, B, O + A, "in_oa");
+  Mat in_noa = ws_mat(h, B, O + A, "in_noa");
+  Mat in_oa2 = ws_mat(h, B, O + A, "in_oa2");
+  Mat goal_next = ws_mat(h, B, G, "next_goal");
+  Mat mix_in = ws_mat(h, B, G, "mix_input");
+  h->z_rand = ws_mat(h, B, Z, "z_rand");
+  Mat z = ws_mat(h, B, Z, "z");
+  h->noise_fb = ws_mat(h, B, A, "noise_fb");
+  h->noise_actor = ws_mat(h, B, A, "noise_actor");
+  Mat mu = ws_mat(h, 2 * B, A, "mu_all");
+  h->views["mu"] = mu.rs(B, B);
+  Mat next_action = ws_mat(h, B, A, "next_action");
+  Mat action_new = ws_mat(h, B, A, "action_new");
+
+  // gather block [F1|F2|tF1|tF2|B|tB|discount ...] : what a rank contributes to the all-gather
+  const int ldZ = fb_round_up(Z, 4);
+  const int blk_pitch = 6 * ldZ + 4;
+  h->blk_local = ws_mat(h, B, blk_pitch, "blk_local");
+  if (n != B) h->blk_global = ws_mat(h, n, blk_pitch, "blk_global");
+  else h->blk_global = h->blk_local;
+  const Mat& bl = h->blk_local; const Mat& bg = h->blk_global;
+  auto blkcol = [&](const Mat& m, int i) { Mat r = m; r.p = m.p + i * ldZ; r.cols = Z; return r; };
+  Mat F1 = blkcol(bl, 0), F2 = blkcol(bl, 1), tF1 = blkcol(bl, 2), tF2 = blkcol(bl, 3), Bm = blkcol(bl, 4), tB = blkcol(bl, 5);
+  Mat F1g = blkcol(bg, 0), F2g = blkcol(bg, 1), tF1g = blkcol(bg, 2), tF2g = blkcol(bg, 3), Bg = blkcol(bg, 4), tBg = blkcol(bg, 5);
+  const int disc_col = 6 * ldZ;
+  h->views["F1"] = F1; h->views["F2"] = F2; h->views["tF1"] = tF1; h->views["tF2"] = tF2; h->views["B"] = Bm; h->views["tB"] = tB;
+  { Mat d = bl; d.p = bl.p + disc_col; d.cols = 1; h->views["discount"] = d; }
+
+  // ---- parameter sets ------------------------------------------------------------------------
+  const fb_buffers& bf = h->bufs;
+  PSet pF{&h->seg_fb, h->fwd_first, bf.d_param_fb, bf.d_grad_fb};
+  PSet pFt{&h->seg_fb, h->fwd_first, bf.d_target_fb, nullptr};
+  PSet pB{&h->seg_fb, h->bwd_first, bf.d_param_fb, bf.d_grad_fb};
+  PSet pBt{&h->seg_fb, h->bwd_first, bf.d_target_fb, nullptr};
+  PSet pA{&h->seg_actor, 0, bf.d_param_actor, bf.d_grad_actor};
+  // sub-blocks: embed = 6 tensors (W0 b0 gamma beta W3 b3), head = 4 tensors (W1 b1 W2 b2)
+  const int E_OA = 0, E_OZ = 6, HD_1 = 12, HD_2 = 16;   // forward net
+  const int A_O = 0, A_OZ = 6, A_POL = 12;              // actor
+
+  // ---- activations ---------------------------------------------------------------------------
+  Mat hA = ws_mat(h, 2 * B, 2 * Fd, "hA");
+  Mat hFt = ws_mat(h, B, 2 * Fd, "hFt");
+  Mat hF = ws_mat(h, B, 2 * Fd, "hF");
+  Mat hF2 = ws_mat(h, B, 2 * Fd, "hF2");
+  EmbedAct eAo = embed_alloc(h, actor_in_o, hA.cs(0, Fd), H, "actor.obs_net");
+  EmbedAct eAoz = embed_alloc(h, actor_in_oz, hA.cs(Fd, Fd), H, "actor.obs_z_net");
+  EmbedAct eFtoa = embed_alloc(h, in_noa, hFt.cs(0, Fd), H, "Ft.obs_action_net");
+  EmbedAct eFtoz = embed_alloc(h, actor_in_oz.rs(0, B), hFt.cs(Fd, Fd), H, "Ft.obs_z_net");
+  EmbedAct eFoa = embed_alloc(h, in_oa, hF.cs(0, Fd), H, "F.obs_action_net");
+  EmbedAct eFoz = embed_alloc(h, actor_in_oz.rs(B, B), hF.cs(Fd, Fd), H, "F.obs_z_net");
+  EmbedAct eF2oa = embed_alloc(h, in_oa2, hF2.cs(0, Fd), H, "F2.obs_action_net");
+  EmbedAct eF2oz = embed_alloc(h, actor_in_oz.rs(B, B), hF2.cs(Fd, Fd), H, "F2.obs_z_net");
+  Mat h1A = ws_mat(h, 2 * B, H, "actor.policy.h1");
+  Mat preA = ws_mat(h, 2 * B, A, "actor.policy.out");
+  Mat h1Ft1 = ws_mat(h, B, H, "Ft.F1.h1"), h1Ft2 = ws_mat(h, B, H, "Ft.F2.h1");
+  Mat h1F1 = ws_mat(h, B, H, "F.F1.h1"), h1F2 = ws_mat(h, B, H, "F.F2.h1");
+  Mat h1Fa1 = ws_mat(h, B, H, "F2.F1.h1"), h1Fa2 = ws_mat(h, B, H, "F2.F2.h1");
+  Mat Fa = ws_mat(h, B, 2 * ldZ, "Fa");
+  Mat Fa1 = Fa.cs(0, Z), Fa2 = Fa.cs(ldZ, Z);
+  h->views["F1a"] = Fa1; h->views["F2a"] = Fa2;
+  Mat b_mix_out = ws_mat(h, B, Z, "B_mix");
+  BAct bMix = b_alloc(h, mix_in, b_mix_out, "Bmix");
+  BAct bT = b_alloc(h, goal_next, tB, "Bt");
+  BAct bO = b_alloc(h, goal_next, Bm, "Bo");
+
+  // loss matrices (row block and column block); Mat cols = n
+  Mat M1 = ws_mat(h, B, n, "M1"), M2 = ws_mat(h, B, n, "M2"), T1 = ws_mat(h, B, n, "T1"), T2 = ws_mat(h, B, n, "T2");
+  Mat Cov = ws_mat(h, B, n, "Cov");
+  Mat Mt1 = ws_mat(h, B, n, "Mt1"), Mt2 = ws_mat(h, B, n, "Mt2"), Tt1 = ws_mat(h, B, n, "Tt1"), Tt2 = ws_mat(h, B, n, "Tt2");
+  Mat dblk = ws_mat(h, B, 3 * ldZ, "dblk");
+  Mat dF1 = dblk.cs(0, Z), dF2 = dblk.cs(ldZ, Z), dB = dblk.cs(2 * ldZ, Z);
+  h->views["dF1"] = dF1; h->views["dF2"] = dF2; h->views["dB"] = dB;
+  Mat draw = ws_mat(h, B, Z, "dBraw");
+  // backward scratch
+  Mat dh1 = ws_mat(h, B, 2 * H, "dh1");          // [dh1_F1 | dh1_F2]
+  Mat dh1_1 = dh1.cs(0, H), dh1_2 = dh1.cs(H, H);
+  Mat dhF = ws_mat(h, B, 2 * Fd, "dhF");
+  Mat dy_oa = ws_mat(h, B, H, "dy_oa"), dy_oz = ws_mat(h, B, H, "dy_oz");
+  Mat dh2 = ws_mat(h, B, c.backward_hidden_dim, "dh2"), dy1 = ws_mat(h, B, c.backward_hidden_dim, "dy1");
+  Mat dFa = ws_mat(h, B, 2 * ldZ, "dFa");
+  Mat dFa1 = dFa.cs(0, Z), dFa2 = dFa.cs(ldZ, Z);
+  Mat dhoa = ws_mat(h, B, Fd, "dhoa");
+  Mat dpreA = ws_mat(h, B, A, "dpreA");
+  Mat dh1A = ws_mat(h, B, H, "dh1A");
+  Mat dhA = ws_mat(h, B, 2 * Fd, "dhA");
+  Mat dy_o = ws_mat(h, B, H, "dy_o"), dy_aoz = ws_mat(h, B, H, "dy_aoz");
+
+  Builder b{h, d_arena};
+  DevScalars* sc = h->d_sc;
+  double* acc = h->d_acc;
+
+  // =========================== FB_PHASE_SAMPLE ===================================================
+  b.set_phase(FB_PHASE_SAMPLE);
+  if (c.rng_device) {
+    RngParams rp; memset(&rp, 0, sizeof(rp));
+    rp.seed = c.seed; rp.batch = B; rp.Z = Z; rp.A = A; rp.ldZ = h->z_rand.ld; rp.ldA = h->noise_fb.ld; rp.mix_ratio = c.mix_ratio;
+    rp.n_episodes = h->d_n_episodes; rp.ep_idx = h->d_ep_idx; rp.step_idx = h->d_step_idx; rp.future_idx = h->d_future_idx;
+    rp.mix_mask = h->d_mix_mask; rp.perm_keys = h->d_perm_keys; rp.z_rand = h->z_rand.p; rp.noise_fb = h->noise_fb.p;
+    rp.noise_actor = h->noise_actor.p;
+    fb_handle* hh = h;
+    b.push([rp, sc, hh](cudaStream_t s) mutable {
+      rp.ep_len = hh->replay.d_episode_len; rp.rows_per_episode = hh->replay.rows_per_episode;
+      k_rng_draw<<<fb_ceil_div(rp.batch, 8), 256, 0, s>>>(rp, sc);
+      return cudaGetLastError();
+    });
+    int npow2 = 1; while (npow2 < B) npow2 <<= 1;
+    unsigned int* keys = h->d_perm_keys; int* perm = h->d_perm;
+    b.push([keys, perm, B, npow2](cudaStream_t s) {
+      k_randperm<<<1, 1024, npow2 * sizeof(unsigned long long), s>>>(keys, B, npow2, perm);
+      return cudaGetLastError();
+    });
+    b.push([sc](cudaStream_t s) { k_tick<<<1, 32, 0, s>>>(sc, 2, 0.f, 0.f); return cudaGetLastError(); });
+  }
+  {
+    fb_handle* hh = h;
+    b.push([hh, sc](cudaStream_t s) {
+      if (!hh->replay_bound) return cudaErrorInvalidValue;
+      GatherParams gp;
+      if (build_gather_params(hh->replay, gp, hh->bl, hh->packed.ld) != FB_OK) return cudaErrorInvalidValue;
+      k_gather_rows<<<fb_ceil_div(hh->cfg.batch, 8), 256, 0, s>>>(gp, hh->d_ep_idx, hh->d_step_idx, nullptr, hh->cfg.batch,
+                                                                 &sc->replay_discount, 0.f, hh->packed.p);
+      return cudaGetLastError();
+    });
+  }
+
+  // =========================== FB_PHASE_MIX =====================================================
+  b.set_phase(FB_PHASE_MIX);
+  {
+    StageParams sp; memset(&sp, 0, sizeof(sp));
+    sp.L = L; sp.batch = B; sp.use_goal = use_goal ? 1 : 0;
+    sp.actor_in_o = actor_in_o.p; sp.ldO = actor_in_o.ld; sp.actor_in_oz = actor_in_oz.p; sp.ldOZ = actor_in_oz.ld;
+    sp.in_oa = in_oa.p; sp.in_noa = in_noa.p; sp.in_oa2 = in_oa2.p; sp.ldOA = in_oa.ld;
+    sp.goal_next = goal_next.p; sp.mix_in = mix_in.p; sp.ldG = goal_next.ld;
+    sp.blk = bl.p; sp.blk_pitch = bl.ld; sp.disc_col = disc_col;
+    sp.perm = h->d_perm; sp.mix_override = nullptr;
+    const float* packed = h->packed.p;
+    b.push([sp, packed](cudaStream_t s) { k_stage_inputs<<<sp.batch, 128, 0, s>>>(sp, packed); return cudaGetLastError(); });
+  }
+  const bool do_mix = c.mix_ratio > 0.f;
+  if (do_mix) {  // mix_z = backward_net(backward_input[perm]) on every row; rows outside the mask are ignored
+    b.gemm({lin_fwd(bMix.x, pB.w(0), pB.v(1), bMix.pre, 0)});
+    b.ln_fwd({b_ln(bMix, pB)});
+    b.gemm({lin_fwd(bMix.y, pB.w(4), pB.v(5), bMix.h2, GF_RELU)});
+    b.gemm({lin_fwd(bMix.h2, pB.w(6), pB.v(7), bMix.raw, 0)});
+    b.l2_fwd({b_l2(bMix, Z)});
+  }
+  {
+    ZFinalParams zp; memset(&zp, 0, sizeof(zp));
+    zp.batch = B; zp.Z = Z; zp.O = O; zp.z_rand = h->z_rand.p; zp.ldZ = z.ld; zp.b_mix = b_mix_out.p; zp.ld_bmix = b_mix_out.ld;
+    zp.mix_mask = do_mix ? h->d_mix_mask : nullptr; zp.z = z.p; zp.actor_in_oz = actor_in_oz.p; zp.ldOZ = actor_in_oz.ld;
+    b.push([zp](cudaStream_t s) { k_z_final<<<fb_ceil_div(zp.batch, 8), 256, 0, s>>>(zp); return cudaGetLastError(); });
+  }
+
+  // =========================== FB_PHASE_FB_FWD ==================================================
+  b.set_phase(FB_PHASE_FB_FWD);
+  b.memset0(acc, 8 * sizeof(double));
+  b.gemm({lin_fwd(eAo.x, pA.w(A_O + 0), pA.v(A_O + 1), eAo.pre, 0), lin_fwd(eAoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eAoz.pre, 0),
+          lin_fwd(eFoa.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eFoa.pre, 0), lin_fwd(eFoz.x, pF.w(E_OZ + 0), pF.v(E_OZ + 1), eFoz.pre, 0),
+          lin_fwd(eFtoz.x, pFt.w(E_OZ + 0), pFt.v(E_OZ + 1), eFtoz.pre, 0),
+          lin_fwd(bO.x, pB.w(0), pB.v(1), bO.pre, 0), lin_fwd(bT.x, pBt.w(0), pBt.v(1), bT.pre, 0)});
+  b.ln_fwd({embed_ln(eAo, pA.sub(A_O)), embed_ln(eAoz, pA.sub(A_OZ)), embed_ln(eFoa, pF.sub(E_OA)), embed_ln(eFoz, pF.sub(E_OZ)),
+            embed_ln(eFtoz, pFt.sub(E_OZ)), b_ln(bO, pB), b_ln(bT, pBt)});
+  b.gemm({lin_fwd(eAo.y, pA.w(A_O + 4), pA.v(A_O + 5), eAo.out, GF_RELU), lin_fwd(eAoz.y, pA.w(A_OZ + 4), pA.v(A_OZ + 5), eAoz.out, GF_RELU),
+          lin_fwd(eFoa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eFoa.out, GF_RELU), lin_fwd(eFoz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eFoz.out, GF_RELU),
+          lin_fwd(eFtoz.y, pFt.w(E_OZ + 4), pFt.v(E_OZ + 5), eFtoz.out, GF_RELU),
+          lin_fwd(bO.y, pB.w(4), pB.v(5), bO.h2, GF_RELU), lin_fwd(bT.y, pBt.w(4), pBt.v(5), bT.h2, GF_RELU)});
+  b.gemm({lin_fwd(hA, pA.w(A_POL + 0), pA.v(A_POL + 1), h1A, GF_RELU),
+          lin_fwd(bO.h2, pB.w(6), pB.v(7), bO.raw, 0), lin_fwd(bT.h2, pBt.w(6), pBt.v(7), bT.raw, 0)});
+  b.gemm({lin_fwd(h1A, pA.w(A_POL + 2), pA.v(A_POL + 3), preA, 0)});
+  b.l2_fwd({b_l2(bO, Z), b_l2(bT, Z)});
+  {
+    ActorOutParams ap; memset(&ap, 0, sizeof(ap));
+    ap.batch = B; ap.A = A; ap.O = O; ap.pre = preA.p; ap.mu = mu.p; ap.ldA = preA.ld;
+    ap.noise_fb = h->noise_fb.p; ap.noise_actor = h->noise_actor.p; ap.ldN = h->noise_fb.ld;
+    ap.in_noa = in_noa.p; ap.in_oa2 = in_oa2.p; ap.ldOA = in_noa.ld; ap.next_action = next_action.p; ap.action_new = action_new.p;
+    ap.acc = acc;
+    b.push([ap, sc](cudaStream_t s) {
+      k_actor_out<<<fb_ceil_div(2 * ap.batch * ap.A, 256), 256, 0, s>>>(ap, sc);
+      return cudaGetLastError();
+    });
+  }
+  b.gemm({lin_fwd(eFtoa.x, pFt.w(E_OA + 0), pFt.v(E_OA + 1), eFtoa.pre, 0)});
+  b.ln_fwd({embed_ln(eFtoa, pFt.sub(E_OA))});
+  b.gemm({lin_fwd(eFtoa.y, pFt.w(E_OA + 4), pFt.v(E_OA + 5), eFtoa.out, GF_RELU)});
+  b.gemm({lin_fwd(hFt, pFt.w(HD_1 + 0), pFt.v(HD_1 + 1), h1Ft1, GF_RELU), lin_fwd(hFt, pFt.w(HD_2 + 0), pFt.v(HD_2 + 1), h1Ft2, GF_RELU),
+          lin_fwd(hF, pF.w(HD_1 + 0), pF.v(HD_1 + 1), h1F1, GF_RELU), lin_fwd(hF, pF.w(HD_2 + 0), pF.v(HD_2 + 1), h1F2, GF_RELU)});
+  b.gemm({lin_fwd(h1Ft1, pFt.w(HD_1 + 2), pFt.v(HD_1 + 3), tF1, 0), lin_fwd(h1Ft2, pFt.w(HD_2 + 2), pFt.v(HD_2 + 3), tF2, 0),
+          lin_fwd(h1F1, pF.w(HD_1 + 2), pF.v(HD_1 + 3), F1, 0), lin_fwd(h1F2, pF.w(HD_2 + 2), pF.v(HD_2 + 3), F2, 0)});
+
+  // =========================== FB_PHASE_FB_LOSS =================================================
+  // (multi-GPU: the caller all-gathers blk_local -> blk_global between FB_FWD and FB_LOSS)
+  b.set_phase(FB_PHASE_FB_LOSS);
+  {
+    auto outer = [&](const Mat& X, const Mat& Yall, const Mat& C) {  // C[rows(X), n] = X . Yall^T  (K = Z)
+      return gemm_raw(X.p, X.ld, 1, Yall.p, Yall.ld, 1, C.p, C.ld, X.rows, Yall.rows, Z, nullptr, 0, nullptr, 0);
+    };
+    b.gemm({outer(F1, Bg, M1), outer(F2, Bg, M2), outer(tF1, tBg, T1), outer(tF2, tBg, T2), outer(Bm, Bg, Cov),
+            outer(Bm, F1g, Mt1), outer(Bm, F2g, Mt2), outer(tB, tF1g, Tt1), outer(tB, tF2g, Tt2)});
+    const float inv_noff = 1.0f / ((float)n * (float)(n - 1)), inv_n = 1.0f / (float)n;
+    LossElemParams lp; memset(&lp, 0, sizeof(lp));
+    lp.M1 = M1.p; lp.M2 = M2.p; lp.T1 = T1.p; lp.T2 = T2.p; lp.Cov = Cov.p; lp.nr = B; lp.nc = n; lp.ld = M1.ld; lp.row0 = c.row_offset;
+    lp.disc = bl.p + disc_col; lp.disc_stride = bl.ld; lp.inv_noff = inv_noff; lp.inv_n = inv_n; lp.ortho_coef = c.ortho_coef; lp.acc = acc;
+    b.push([lp](cudaStream_t s) {
+      dim3 grid(fb_ceil_div(lp.nc, 1024) > 0 ? fb_ceil_div(lp.nc, 1024) : 1, lp.nr < 592 ? lp.nr : 592);
+      k_fb_loss_elem<<<grid, 256, 0, s>>>(lp);
+      return cudaGetLastError();
+    });
+    LossElemTParams lt; memset(&lt, 0, sizeof(lt));
+    lt.M1 = Mt1.p; lt.M2 = Mt2.p; lt.T1 = Tt1.p; lt.T2 = Tt2.p; lt.nr = B; lt.nc = n; lt.ld = Mt1.ld; lt.row0 = c.row_offset;
+    lt.disc = bg.p + disc_col; lt.disc_stride = bg.ld; lt.inv_noff = inv_noff; lt.inv_n = inv_n;
+    b.push([lt](cudaStream_t s) {
+      dim3 grid(fb_ceil_div(lt.nc, 1024) > 0 ? fb_ceil_div(lt.nc, 1024) : 1, lt.nr < 592 ? lt.nr : 592);
+      k_fb_loss_elem_t<<<grid, 256, 0, s>>>(lt);
+      return cudaGetLastError();
+    });
+    b.memset0(dblk.p, (size_t)dblk.rows * dblk.ld * sizeof(float));
+    const float coef = -4.0f * c.ortho_coef * inv_n;
+    b.push([dB, Bm, B, Z, coef](cudaStream_t s) {
+      k_loss_init_db<<<fb_ceil_div(B * Z, 256), 256, 0, s>>>(dB.p, dB.ld, Bm.p, Bm.ld, B, Z, coef);
+      return cudaGetLastError();
+    });
+    auto inner = [&](const Mat& Gm, const Mat& Yall, const Mat& C) {  // C[B, Z] += Gm[B, n] . Yall[n, Z]
+      GemmDesc d = gemm_raw(Gm.p, Gm.ld, 1, Yall.p, Yall.ld, 0, C.p, C.ld, Gm.rows, Z, n, nullptr, GF_ATOMIC, nullptr, 0);
+      return d;
+    };
+    b.gemm({inner(M1, Bg, dF1), inner(M2, Bg, dF2), inner(Mt1, F1g, dB), inner(Mt2, F2g, dB), inner(Cov, Bg, dB)});
+  }
+
+  // =========================== FB_PHASE_FB_BWD ==================================================
+  b.set_phase(FB_PHASE_FB_BWD);
+  b.push([dB, Bm, bO, draw, B, Z](cudaStream_t s) {
+    k_l2norm_bwd<<<fb_ceil_div(B, 8), 256, 0, s>>>(dB.p, dB.ld, Bm.p, Bm.ld, bO.nrm, draw.p, draw.ld, B, Z);
+    return cudaGetLastError();
+  });
+  b.colsum({mk_colsum(dF1, pF.gv(HD_1 + 3)), mk_colsum(dF2, pF.gv(HD_2 + 3)), mk_colsum(draw, pB.gv(7))});
+  b.gemm({lin_dw(dF1, h1F1, pF.gw(HD_1 + 2)), lin_dw(dF2, h1F2, pF.gw(HD_2 + 2)), lin_dw(draw, bO.h2, pB.gw(6)),
+          lin_dx(dF1, pF.w(HD_1 + 2), dh1_1, GF_MASK_RELU, &h1F1), lin_dx(dF2, pF.w(HD_2 + 2), dh1_2, GF_MASK_RELU, &h1F2),
+          lin_dx(draw, pB.w(6), dh2, GF_MASK_RELU, &bO.h2)});
+  b.colsum({mk_colsum(dh1_1, pF.gv(HD_1 + 1)), mk_colsum(dh1_2, pF.gv(HD_2 + 1)), mk_colsum(dh2, pB.gv(5))});
+  {
+    GemmDesc d = lin_dx(dh1_1, pF.w(HD_1 + 0), dhF, GF_MASK_RELU, &hF);
+    Mat w2 = pF.w(HD_2 + 0);
+    d.A2 = dh1_2.p; d.B2 = w2.p; d.K2 = w2.rows;
+    b.gemm({lin_dw(dh1_1, hF, pF.gw(HD_1 + 0)), lin_dw(dh1_2, hF, pF.gw(HD_2 + 0)), d, lin_dw(dh2, bO.y, pB.gw(4)),
+            lin_dx(dh2, pB.w(4), dy1, 0, nullptr)});
+  }
+  Mat dhF_oa = dhF.cs(0, Fd), dhF_oz = dhF.cs(Fd, Fd);
+  b.colsum({mk_colsum(dhF_oa, pF.gv(E_OA + 5)), mk_colsum(dhF_oz, pF.gv(E_OZ + 5))});
+  {
+    LnBwdDesc d; memset(&d, 0, sizeof(d));
+    d.dy = dy1.p; d.dx = dy1.p; d.y = bO.y.p; d.x = bO.pre.p; d.gamma = pB.v(2); d.mean = bO.mean; d.rstd = bO.rstd;
+    d.dgamma = pB.gv(2); d.dbeta = pB.gv(3); d.rows = B; d.D = dy1.cols; d.ld = bO.y.ld; d.ld_dy = dy1.ld;
+    b.ln_bwd({d});
+  }
+  b.colsum({mk_colsum(dy1, pB.gv(1))});
+  b.gemm({lin_dw(dhF_oa, eFoa.y, pF.gw(E_OA + 4)), lin_dw(dhF_oz, eFoz.y, pF.gw(E_OZ + 4)),
+          lin_dx(dhF_oa, pF.w(E_OA + 4), dy_oa, 0, nullptr), lin_dx(dhF_oz, pF.w(E_OZ + 4), dy_oz, 0, nullptr),
+          lin_dw(dy1, bO.x, pB.gw(0))});
+  b.ln_bwd({embed_ln_bwd(eFoa, pF.sub(E_OA), dy_oa, 0, true), embed_ln_bwd(eFoz, pF.sub(E_OZ), dy_oz, 0, true)});
+  b.colsum({mk_colsum(dy_oa, pF.gv(E_OA + 1)), mk_colsum(dy_oz, pF.gv(E_OZ + 1))});
+  b.gemm({lin_dw(dy_oa, eFoa.x, pF.gw(E_OA + 0)), lin_dw(dy_oz, eFoz.x, pF.gw(E_OZ + 0))});
+
+  // =========================== FB_PHASE_FB_ADAM =================================================
+  b.set_phase(FB_PHASE_FB_ADAM);
+  {
+    const float b1 = c.beta1, b2 = c.beta2, eps = c.adam_eps;
+    b.push([sc, b1, b2](cudaStream_t s) { k_tick<<<1, 32, 0, s>>>(sc, 0, b1, b2); return cudaGetLastError(); });
+    float4 *p = (float4*)bf.d_param_fb, *g = (float4*)bf.d_grad_fb, *m = (float4*)bf.d_m_fb, *v = (float4*)bf.d_v_fb, *t = (float4*)bf.d_target_fb;
+    const size_t n4 = h->seg_fb.size / 4, split4 = h->bwd_offset / 4;
+    b.push([=](cudaStream_t s) {
+      k_adam<<<FB_SM_COUNT * 8, 256, 0, s>>>(p, g, m, v, t, n4, split4, sc, 0, b1, b2, eps);
+      return cudaGetLastError();
+    });
+  }
+
+  // =========================== FB_PHASE_ACTOR_FWD ===============================================
+  b.set_phase(FB_PHASE_ACTOR_FWD);
+  b.memset0(acc + ACC_Q, 2 * sizeof(double));
+  b.gemm({lin_fwd(eF2oa.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eF2oa.pre, 0), lin_fwd(eF2oz.x, pF.w(E_OZ + 0), pF.v(E_OZ + 1), eF2oz.pre, 0)});
+  b.ln_fwd({embed_ln(eF2oa, pF.sub(E_OA)), embed_ln(eF2oz, pF.sub(E_OZ))});
+  b.gemm({lin_fwd(eF2oa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eF2oa.out, GF_RELU), lin_fwd(eF2oz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eF2oz.out, GF_RELU)});
+  b.gemm({lin_fwd(hF2, pF.w(HD_1 + 0), pF.v(HD_1 + 1), h1Fa1, GF_RELU), lin_fwd(hF2, pF.w(HD_2 + 0), pF.v(HD_2 + 1), h1Fa2, GF_RELU)});
+  b.gemm({lin_fwd(h1Fa1, pF.w(HD_1 + 2), pF.v(HD_1 + 3), Fa1, 0), lin_fwd(h1Fa2, pF.w(HD_2 + 2), pF.v(HD_2 + 3), Fa2, 0)});
+  {
+    const float inv_n = 1.0f / (float)n;
+    b.push([Fa1, Fa2, z, dFa1, dFa2, B, Z, inv_n, acc](cudaStream_t s) {
+      k_actor_q<<<fb_ceil_div(B, 8), 256, 0, s>>>(Fa1.p, Fa2.p, Fa1.ld, z.p, z.ld, dFa1.p, dFa2.p, dFa1.ld, B, Z, inv_n, acc);
+      return cudaGetLastError();
+    });
+  }
+
+  // =========================== FB_PHASE_ACTOR_BWD ===============================================
+  b.set_phase(FB_PHASE_ACTOR_BWD);
+  b.gemm({lin_dx(dFa1, pF.w(HD_1 + 2), dh1_1, GF_MASK_RELU, &h1Fa1), lin_dx(dFa2, pF.w(HD_2 + 2), dh1_2, GF_MASK_RELU, &h1Fa2)});
+  {
+    Mat hF2oa = hF2.cs(0, Fd);
+    GemmDesc d = lin_dx(dh1_1, pF.w(HD_1 + 0).cs(0, Fd), dhoa, GF_MASK_RELU, &hF2oa);
+    Mat w2 = pF.w(HD_2 + 0).cs(0, Fd);
+    d.A2 = dh1_2.p; d.B2 = w2.p; d.K2 = w2.rows;
+    b.gemm({d});
+  }
+  b.gemm({lin_dx(dhoa, pF.w(E_OA + 4), dy_oa, 0, nullptr)});
+  b.ln_bwd({embed_ln_bwd(eF2oa, pF.sub(E_OA), dy_oa, 0, false)});
+  {
+    Mat muB = mu.rs(B, B);
+    b.gemm({lin_dx(dy_oa, pF.w(E_OA + 0).cs(O, A), dpreA, GF_MASK_TANH, &muB)});
+  }
+  Mat h1A_o = h1A.rs(B, B), hA_o = hA.rs(B, B);
+  b.colsum({mk_colsum(dpreA, pA.gv(A_POL + 3))});
+  b.gemm({lin_dw(dpreA, h1A_o, pA.gw(A_POL + 2)), lin_dx(dpreA, pA.w(A_POL + 2), dh1A, GF_MASK_RELU, &h1A_o)});
+  b.colsum({mk_colsum(dh1A, pA.gv(A_POL + 1))});
+  b.gemm({lin_dw(dh1A, hA_o, pA.gw(A_POL + 0)), lin_dx(dh1A, pA.w(A_POL + 0), dhA, GF_MASK_RELU, &hA_o)});
+  Mat dhA_o = dhA.cs(0, Fd), dhA_oz = dhA.cs(Fd, Fd);
+  b.colsum({mk_colsum(dhA_o, pA.gv(A_O + 5)), mk_colsum(dhA_oz, pA.gv(A_OZ + 5))});
+  b.gemm({lin_dw(dhA_o, eAo.y.rs(B, B), pA.gw(A_O + 4)), lin_dw(dhA_oz, eAoz.y.rs(B, B), pA.gw(A_OZ + 4)),
+          lin_dx(dhA_o, pA.w(A_O + 4), dy_o, 0, nullptr), lin_dx(dhA_oz, pA.w(A_OZ + 4), dy_aoz, 0, nullptr)});
+  b.ln_bwd({embed_ln_bwd(eAo, pA.sub(A_O), dy_o, B, true), embed_ln_bwd(eAoz, pA.sub(A_OZ), dy_aoz, B, true)});
+  b.colsum({mk_colsum(dy_o, pA.gv(A_O + 1)), mk_colsum(dy_aoz, pA.gv(A_OZ + 1))});
+  b.gemm({lin_dw(dy_o, eAo.x.rs(B, B), pA.gw(A_O + 0)), lin_dw(dy_aoz, eAoz.x.rs(B, B), pA.gw(A_OZ + 0))});
+
+  // =========================== FB_PHASE_ACTOR_ADAM ==============================================
+  b.set_phase(FB_PHASE_ACTOR_ADAM);
+  {
+    const float b1 = c.beta1, b2 = c.beta2, eps = c.adam_eps;
+    b.push([sc, b1, b2](cudaStream_t s) { k_tick<<<1, 32, 0, s>>>(sc, 1, b1, b2); return cudaGetLastError(); });
+    float4 *p = (float4*)bf.d_param_actor, *g = (float4*)bf.d_grad_actor, *m = (float4*)bf.d_m_actor, *v = (float4*)bf.d_v_actor;
+    const size_t n4 = h->seg_actor.size / 4;
+    b.push([=](cudaStream_t s) {
+      k_adam<<<FB_SM_COUNT * 8, 256, 0, s>>>(p, g, m, v, nullptr, n4, n4, sc, 1, b1, b2, eps);
+      return cudaGetLastError();
+    });
+  }
+
+  // =========================== FB_PHASE_METRICS =================================================
+  b.set_phase(FB_PHASE_METRICS);
+  b.memset0(acc + ACC_F1, 6 * sizeof(double));
+  b.memset0(h->d_linf, 16);
+  b.push([F1, Bm, z, B, Z, acc](cudaStream_t s) {
+    k_metric_rows<<<fb_ceil_div(B, 8), 256, 0, s>>>(F1.p, F1.ld, Bm.p, Bm.ld, z.p, z.ld, B, Z, acc);
+    return cudaGetLastError();
+  });
+  {
+    unsigned int* linf = h->d_linf;
+    b.push([Bg, n, Z, acc, linf](cudaStream_t s) {
+      k_metric_cov<<<Z, 128, 0, s>>>(Bg.p, Bg.ld, n, Z, acc, linf);
+      return cudaGetLastError();
+    });
+    MetricFinalParams mp; memset(&mp, 0, sizeof(mp));
+    mp.acc = acc; mp.linf_bits = linf; mp.out = h->d_metrics; mp.n_local = B; mp.n_global = n; mp.Z = Z; mp.ortho_coef = c.ortho_coef;
+    b.push([mp](cudaStream_t s) { k_metric_final<<<1, 32, 0, s>>>(mp); return cudaGetLastError(); });
+  }
+
+  if (h->arena.size() > FB_DESC_ARENA_BYTES) return FB_E_STATE;
+  h->ws_off = (h->ws_off + 255) / 256 * 256;
+  return FB_OK;
+}
+
+// gather slots: which 16-byte chunk of which storage row feeds each 16-byte chunk of the output row
+static int build_gather_params(const fb_replay_view& v, GatherParams& gp, const BatchLayout& L, int out_ld) {
+  memset(&gp, 0, sizeof(gp));
+  if (v.row_stride % 4 || out_ld % 4 || v.off_obs % 4 || v.off_action % 4 || v.off_reward % 4 || v.off_discount != v.off_reward + 1)
+    return FB_E_ARG;
+  if (L.G > 0 && (v.off_goal < 0 || v.off_goal % 4)) return FB_E_ARG;
+  if (L.X > 0 && (v.off_extra < 0 || v.off_extra % 4)) return FB_E_ARG;
+  gp.rows = v.d_rows; gp.ep_len = v.d_episode_len; gp.rows_per_episode = v.rows_per_episode; gp.row_stride = v.row_stride;
+  gp.out_ld = out_ld;
+  int n = 0;
+  auto field = [&](int dst_off, int src_row, int src_off, int dim, int special) {
+    for (int c = 0; c < fb_round_up(dim, 4); c += 4) {
+      if (n >= FB_MAX_GATHER_SLOTS) return;
+      GatherSlot& s = gp.slots[n];
+      s.dst_f4 = (dst_off + c) / 4; s.src_row = (short)src_row; s.special = (short)special; s.src_f4 = (src_off + c) / 4;
+      ++n;
+    }
+  };
+  field(L.off_obs, 0, v.off_obs, L.O, 0);
+  field(L.off_action, 1, v.off_action, L.A, 0);
+  field(L.off_rd, 1, v.off_reward, 4, 1);
+  field(L.off_next_obs, 1, v.off_obs, L.O, 0);
+  if (L.G > 0) { field(L.off_goal, 0, v.off_goal, L.G, 0); field(L.off_next_goal, 1, v.off_goal, L.G, 0); }
+  if (L.X > 0) field(L.off_extra, 0, v.off_extra, L.X, 0);
+  if (L.with_future) {
+    field(L.off_future_obs, 2, v.off_obs, L.O, 0);
+    if (L.G > 0) field(L.off_future_goal, 2, v.off_goal, L.G, 0);
+  }
+  if (n >= FB_MAX_GATHER_SLOTS) return FB_E_UNSUPPORTED;
+  gp.n_slots = n;
+  return FB_OK;
+}
+
+static void make_batch_layout(BatchLayout& L, int O, int A, int G, int X, int with_future) {
+  memset(&L, 0, sizeof(L));
+  L.O = O; L.A = A; L.G = G; L.X = X; L.with_future = with_future;
+  int off = 0;
+  L.off_obs = off; off += fb_round_up(O, 4);
+  L.off_action = off; off += fb_round_up(A, 4);
+  L.off_rd = off; off += 4;
+  L.off_next_obs = off; off += fb_round_up(O, 4);
+  L.off_goal = off; off += fb_round_up(G, 4);
+  L.off_next_goal = off; off += fb_round_up(G, 4);
+  L.off_extra = off; off += fb_round_up(X, 4);
+  L.off_future_obs = off; if (with_future) off += fb_round_up(O, 4);
+  L.off_future_goal = off; if (with_future) off += fb_round_up(G, 4);
+  L.pitch = off;
+}
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int fb_abi_version(void) { return FB_ABI_VERSION; }
+
+const char* fb_error_string(int code) {
+  switch (code) {
+    case FB_OK: return "ok";
+    case FB_E_ARG: return "bad argument";
+    case FB_E_STATE: return "bad state (fb_bind / fb_bind_replay not called, or descriptor arena overflow)";
+    case FB_E_UNSUPPORTED: return "unsupported configuration";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+  }
+}
+
+int fb_create(const fb_config* cfg, fb_handle** out) {
+  if (!cfg || !out) return FB_E_ARG;
+  if (cfg->abi_version != FB_ABI_VERSION) return FB_E_ARG;
+  if (cfg->batch < 2 || cfg->global_batch < cfg->batch || cfg->row_offset < 0 || cfg->row_offset + cfg->batch > cfg->global_batch)
+    return FB_E_ARG;
+  if (cfg->obs_dim < 1 || cfg->action_dim < 1 || cfg->z_dim < 1 || cfg->goal_dim < 1 || cfg->hidden_dim < 1 || cfg->feature_dim < 1 ||
+      cfg->backward_hidden_dim < 1)
+    return FB_E_ARG;
+  if (cfg->hidden_dim > FB_MAX_LN_DIM || cfg->backward_hidden_dim > FB_MAX_LN_DIM) return FB_E_UNSUPPORTED;
+  if (!cfg->use_goal && cfg->goal_dim != cfg->obs_dim) return FB_E_ARG;
+  fb_handle* h = new fb_handle();
+  h->cfg = *cfg;
+  memset(&h->bufs, 0, sizeof(h->bufs));
+  memset(&h->replay, 0, sizeof(h->replay));
+  build_layout(h);
+  // dry run of the plan against a null workspace to size it
+  h->ws_base = nullptr;
+  int rc = build_plan(h);
+  if (rc != FB_OK) { delete h; return rc; }
+  h->ws_bytes = h->ws_off;
+  for (auto& v : h->ops) v.clear();
+  *out = h;
+  return FB_OK;
+}
+
+void fb_destroy(fb_handle* h) {
+  if (!h) return;
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  delete h;
+}
+
+size_t fb_flat_size(const fb_handle* h, int actor) { return actor ? h->seg_actor.size : h->seg_fb.size; }
+
+static const SegmentLayout* net_tensors(const fb_handle* h, int net, int* first, int* count) {
+  switch (net) {
+    case FB_NET_FORWARD: *first = h->fwd_first; *count = h->bwd_first - h->fwd_first; return &h->seg_fb;
+    case FB_NET_BACKWARD: *first = h->bwd_first; *count = (int)h->seg_fb.t.size() - h->bwd_first; return &h->seg_fb;
+    case FB_NET_ACTOR: *first = 0; *count = (int)h->seg_actor.t.size(); return &h->seg_actor;
+    default: return nullptr;
+  }
+}
+
+int fb_num_tensors(const fb_handle* h, int net) {
+  int first, count;
+  return net_tensors(h, net, &first, &count) ? count : FB_E_ARG;
+}
+
+int fb_tensor_info(const fb_handle* h, int net, int index, size_t* offset, int* rows, int* cols, char* name, size_t name_cap) {
+  int first, count;
+  const SegmentLayout* L = net_tensors(h, net, &first, &count);
+  if (!L || index < 0 || index >= count) return FB_E_ARG;
+  const TensorInfo& t = L->t[first + index];
+  if (offset) *offset = t.off;
+  if (rows) *rows = t.rows;
+  if (cols) *cols = t.cols;
+  if (name && name_cap) { strncpy(name, t.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  return FB_OK;
+}
+
+size_t fb_workspace_bytes(const fb_handle* h) { return h->ws_bytes; }
+
+__global__ void k_iota(int* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+int fb_bind(fb_handle* h, const fb_buffers* bufs, void* stream) {
+  if (!h || !bufs) return FB_E_ARG;
+  if (!bufs->d_param_fb || !bufs->d_grad_fb || !bufs->d_m_fb || !bufs->d_v_fb || !bufs->d_target_fb || !bufs->d_param_actor ||
+      !bufs->d_grad_actor || !bufs->d_m_actor || !bufs->d_v_actor || !bufs->d_workspace)
+    return FB_E_ARG;
+  if (bufs->workspace_bytes < h->ws_bytes) return FB_E_ARG;
+  if (((uintptr_t)bufs->d_workspace & 255u) || ((uintptr_t)bufs->d_param_fb & 15u) || ((uintptr_t)bufs->d_param_actor & 15u) ||
+      ((uintptr_t)bufs->d_grad_fb & 15u) || ((uintptr_t)bufs->d_grad_actor & 15u) || ((uintptr_t)bufs->d_target_fb & 15u))
+    return FB_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  h->graphs.clear();
+  h->bufs = *bufs;
+  h->ws_base = (char*)bufs->d_workspace;
+  int rc = build_plan(h);
+  if (rc != FB_OK) return rc;
+  CK(cudaFuncSetAttribute(k_gemm_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  CK(cudaMemsetAsync(h->ws_base, 0, h->ws_bytes, s));
+  CK(cudaMemcpyAsync(h->ws_base, h->arena.data(), h->arena.size(), cudaMemcpyHostToDevice, s));
+  k_iota<<<fb_ceil_div(h->cfg.batch, 256), 256, 0, s>>>(h->d_perm, h->cfg.batch);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  h->bound = true;
+  return FB_OK;
+}
+
+int fb_bind_replay(fb_handle* h, const fb_replay_view* view, void* stream) {
+  if (!h || !view || !h->bound) return h && view ? FB_E_STATE : FB_E_ARG;
+  GatherParams gp;
+  int rc = build_gather_params(*view, gp, h->bl, h->packed.ld);
+  if (rc != FB_OK) return rc;
+  const bool same = h->replay_bound && h->replay.d_rows == view->d_rows && h->replay.d_episode_len == view->d_episode_len &&
+                    h->replay.rows_per_episode == view->rows_per_episode && h->replay.row_stride == view->row_stride;
+  if (!same) {  // graphs bake the storage pointers
+    for (auto it = h->graphs.begin(); it != h->graphs.end();) {
+      if (it->first & FB_PHASE_SAMPLE) { cudaGraphExecDestroy(it->second); it = h->graphs.erase(it); } else ++it;
+    }
+  }
+  h->replay = *view;
+  h->replay_bound = true;
+  CK(cudaMemcpyAsync(h->d_n_episodes, &h->replay.n_episodes, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return FB_OK;
+}
+
+int fb_set_step_scalars(fb_handle* h, const fb_step_scalars* sv, void* stream) {
+  if (!h || !sv || !h->bound) return FB_E_STATE;
+  HostScalars hs{sv->stddev, sv->stddev_clip, sv->lr_forward, sv->lr_backward, sv->lr_actor, sv->tau, sv->replay_discount,
+                 sv->replay_future, sv->grad_scale};
+  k_set_scalars<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_sc, hs);
+  CK(cudaGetLastError());
+  return FB_OK;
+}
+
+int fb_set_indices(fb_handle* h, const int32_t* d_ep_idx, const int32_t* d_step_idx, const int32_t* d_future_idx, const int32_t* d_perm,
+                   const int32_t* d_mix_mask, void* stream) {
+  if (!h || !h->bound) return FB_E_STATE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nb = (size_t)h->cfg.batch * sizeof(int32_t);
+  if (d_ep_idx) CK(cudaMemcpyAsync(h->d_ep_idx, d_ep_idx, nb, cudaMemcpyDeviceToDevice, s));
+  if (d_step_idx) CK(cudaMemcpyAsync(h->d_step_idx, d_step_idx, nb, cudaMemcpyDeviceToDevice, s));
+  if (d_future_idx) CK(cudaMemcpyAsync(h->d_future_idx, d_future_idx, nb, cudaMemcpyDeviceToDevice, s));
+  if (d_perm) CK(cudaMemcpyAsync(h->d_perm, d_perm, nb, cudaMemcpyDeviceToDevice, s));
+  if (d_mix_mask) CK(cudaMemcpyAsync(h->d_mix_mask, d_mix_mask, nb, cudaMemcpyDeviceToDevice, s));
+  return FB_OK;
+}
+
+int fb_set_batch(fb_handle* h, const float* d_obs, const float* d_action, const float* d_discount, const float* d_next_obs,
+                 const float* d_goal, const float* d_next_goal, void* stream) {
+  if (!h || !h->bound) return FB_E_STATE;
+  if (!d_obs || !d_action || !d_discount || !d_next_obs) return FB_E_ARG;
+  if (h->cfg.use_goal && (!d_goal || !d_next_goal)) return FB_E_ARG;
+  k_pack_batch<<<h->cfg.batch, 64, 0, (cudaStream_t)stream>>>(h->bl, h->cfg.batch, d_obs, d_action, d_discount, d_next_obs, d_goal,
+                                                             d_next_goal, h->packed.p);
+  CK(cudaGetLastError());
+  return FB_OK;
+}
+
+static int copy_rows(const Mat& dst, const float* src, cudaStream_t s) {
+  CK(cudaMemcpy2DAsync(dst.p, dst.ld * sizeof(float), src, dst.cols * sizeof(float), dst.cols * sizeof(float), dst.rows,
+                       cudaMemcpyDeviceToDevice, s));
+  return FB_OK;
+}
+
+int fb_set_z(fb_handle* h, const float* d_z, void* stream) {
+  if (!h || !h->bound) return FB_E_STATE;
+  if (!d_z) return FB_E_ARG;
+  return copy_rows(h->z_rand, d_z, (cudaStream_t)stream);
+}
+
+int fb_set_noise(fb_handle* h, const float* d_noise_fb, const float* d_noise_actor, void* stream) {
+  if (!h || !h->bound) return FB_E_STATE;
+  int rc = FB_OK;
+  if (d_noise_fb) rc = copy_rows(h->noise_fb, d_noise_fb, (cudaStream_t)stream);
+  if (rc == FB_OK && d_noise_actor) rc = copy_rows(h->noise_actor, d_noise_actor, (cudaStream_t)stream);
+  return rc;
+}
+
+static cudaError_t run_eager(fb_handle* h, uint32_t mask, cudaStream_t s) {
+  for (int ph = 0; ph < FB_NUM_PHASES; ++ph) {
+    if (!(mask & (1u << ph))) continue;
+    for (auto& op : h->ops[ph]) CKE(op(s));
+  }
+  return cudaSuccess;
+}
+
+int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream) {
+  if (!h || !h->bound) return FB_E_STATE;
+  if ((phase_mask & FB_PHASE_SAMPLE) && !h->replay_bound) return FB_E_STATE;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!use_graph) return (int)run_eager(h, phase_mask, s);
+  auto it = h->graphs.find(phase_mask);
+  if (it == h->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = run_eager(h, phase_mask, s);
+    cudaError_t e2 = cudaStreamEndCapture(s, &graph);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return (int)(e != cudaSuccess ? e : e2);
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return (int)e;
+    it = h->graphs.emplace(phase_mask, exec).first;
+  }
+  CK(cudaGraphLaunch(it->second, s));
+  return FB_OK;
+}
+
+int fb_launch_count(fb_handle* h, uint32_t phase_mask) {
+  if (!h || !h->bound) return FB_E_STATE;
+  int n = 0;
+  for (int ph = 0; ph < FB_NUM_PHASES; ++ph)
+    if (phase_mask & (1u << ph)) n += (int)h->ops[ph].size();
+  return n;
+}
+
+const float* fb_metrics_ptr(const fb_handle* h) { return h && h->bound ? h->d_metrics : nullptr; }
+
+int fb_set_adam_steps(fb_handle* h, int64_t fb_step, int64_t actor_step, void* stream) {
+  if (!h || !h->bound) return FB_E_STATE;
+  k_set_adam_steps<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_sc, (long long)fb_step, (long long)actor_step);
+  CK(cudaGetLastError());
+  return FB_OK;
+}
+
+int fb_get_adam_steps(fb_handle* h, int64_t* fb_step, int64_t* actor_step, void* stream) {
+  if (!h || !h->bound) return FB_E_STATE;
+  DevScalars hs;
+  CK(cudaMemcpyAsync(&hs, h->d_sc, sizeof(hs), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  if (fb_step) *fb_step = hs.step_fb;
+  if (actor_step) *actor_step = hs.step_actor;
+  return FB_OK;
+}
+
+int fb_gather_block(fb_handle* h, int* floats_per_row, float** d_local, float** d_global) {
+  if (!h || !h->bound) return FB_E_STATE;
+  if (floats_per_row) *floats_per_row = h->blk_local.ld;
+  if (d_local) *d_local = h->blk_local.p;
+  if (d_global) *d_global = h->blk_global.p;
+  return FB_OK;
+}
+
+int fb_workspace_view(fb_handle* h, const char* name, float** d_ptr, int* rows, int* cols, int* ld) {
+  if (!h || !h->bound || !name) return FB_E_STATE;
+  auto it = h->views.find(name);
+  if (it == h->views.end()) return FB_E_ARG;
+  if (d_ptr) *d_ptr = it->second.p;
+  if (rows) *rows = it->second.rows;
+  if (cols) *cols = it->second.cols;
+  if (ld) *ld = it->second.ld;
+  return FB_OK;
+}
+
+// ---- stand-alone operators -----------------------------------------------------------------------
+int fb_batch_row_layout(int obs_dim, int action_dim, int goal_dim, int extra_dim, int with_future, int32_t* offsets9, int32_t* pitch) {
+  BatchLayout L;
+  make_batch_layout(L, obs_dim, action_dim, goal_dim, extra_dim, with_future);
+  if (offsets9) {
+    offsets9[0] = L.off_obs; offsets9[1] = L.off_action; offsets9[2] = L.off_rd; offsets9[3] = L.off_next_obs; offsets9[4] = L.off_goal;
+    offsets9[5] = L.off_next_goal; offsets9[6] = L.off_extra; offsets9[7] = L.off_future_obs; offsets9[8] = L.off_future_goal;
+  }
+  if (pitch) *pitch = L.pitch;
+  return FB_OK;
+}
+
+int fb_replay_gather(const fb_replay_view* view, int obs_dim, int action_dim, const int32_t* d_ep_idx, const int32_t* d_step_idx,
+                     const int32_t* d_future_idx, int batch, float replay_discount, float* d_out, int out_ld, void* stream) {
+  if (!view || !d_ep_idx || !d_step_idx || !d_out || batch < 1) return FB_E_ARG;
+  BatchLayout L;
+  make_batch_layout(L, obs_dim, action_dim, view->off_goal >= 0 ? view->goal_dim : 0, view->off_extra >= 0 ? view->extra_dim : 0,
+                    d_future_idx != nullptr);
+  if (out_ld < L.pitch) return FB_E_ARG;
+  GatherParams gp;
+  int rc = build_gather_params(*view, gp, L, out_ld);
+  if (rc != FB_OK) return rc;
+  k_gather_rows<<<fb_ceil_div(batch, 8), 256, 0, (cudaStream_t)stream>>>(gp, d_ep_idx, d_step_idx, d_future_idx, batch, nullptr,
+                                                                        replay_discount, d_out);
+  CK(cudaGetLastError());
+  return FB_OK;
+}
+
+int fb_replay_pack_episode(const fb_replay_view* view, float* d_rows_mut, int slot, int rows, int obs_dim, int action_dim,
+                           const float* d_obs, const float* d_action, const float* d_reward, const float* d_discount, const float* d_goal,
+                           const float* d_extra, void* stream) {
+  if (!view || !d_rows_mut || slot < 0 || slot >= view->max_episodes || rows < 1 || rows > view->rows_per_episode) return FB_E_ARG;
+  if (!d_obs || !d_action || !d_reward || !d_discount) return FB_E_ARG;
+  PackEpisodeParams P; memset(&P, 0, sizeof(P));
+  P.row_stride = view->row_stride; P.rows = rows; P.O = obs_dim; P.A = action_dim;
+  P.G = (view->off_goal >= 0 && d_goal) ? view->goal_dim : 0; P.X = (view->off_extra >= 0 && d_extra) ? view->extra_dim : 0;
+  P.off_obs = view->off_obs; P.off_action = view->off_action; P.off_reward = view->off_reward; P.off_goal = view->off_goal;
+  P.off_extra = view->off_extra;
+  float* dst = d_rows_mut + (size_t)slot * view->rows_per_episode * view->row_stride;
+  k_pack_episode<<<rows, 64, 0, (cudaStream_t)stream>>>(dst, P, d_obs, d_action, d_reward, d_discount, d_goal, d_extra);
+  CK(cudaGetLastError());
+  return FB_OK;
+}
+
+int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, int M, int N, int K, int lda, int ldb, int ldc,
+             int a_kmajor, int b_kmajor, int relu, int splitk, void* stream) {
+  if (!dA || !dB || !dC || M < 1 || N < 1 || K < 1) return FB_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  GemmDesc d = gemm_raw(dA, lda, a_kmajor, dB, ldb, b_kmajor, dC, ldc, M, N, K, d_bias, relu ? GF_RELU : 0, nullptr, 0);
+  d.cfg = (M > 64 && N > 64) ? GEMM_CFG_BIG : GEMM_CFG_SMALL;
+  const int bm = d.cfg == GEMM_CFG_BIG ? 128 : 64;
+  d.tiles_m = fb_ceil_div(M, bm); d.tiles_n = fb_ceil_div(N, bm);
+  if (splitk < 1) splitk = 1;
+  if (splitk > 1) { if (relu) return FB_E_ARG; d.flags |= GF_ATOMIC; }
+  d.k_per_split = fb_round_up(fb_ceil_div(K, splitk), GEMM_BK);
+  d.splitk = fb_ceil_div(K, d.k_per_split);
+  d.a_vec = aligned16(dA) && lda % 4 == 0; d.b_vec = aligned16(dB) && ldb % 4 == 0; d.c_vec = aligned16(dC) && ldc % 4 == 0;
+  d.work_begin = 0; d.work_count = d.tiles_m * d.tiles_n * d.splitk;
+  GemmDesc* dd = nullptr;
+  CK(cudaMallocAsync(&dd, sizeof(GemmDesc), s));
+  CK(cudaMemcpyAsync(dd, &d, sizeof(GemmDesc), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));  // d is a stack object
+  CK(cudaFuncSetAttribute(k_gemm_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  k_gemm_grouped<<<d.work_count, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(dd, 1);
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(dd, s));
+  return FB_OK;
+}
+
+int fb_fp32_peak_tflops(double* out_tflops, void* stream) {
+  if (!out_tflops) return FB_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* d = nullptr;
+  CK(cudaMallocAsync(&d, 16, s));
+  const int iters = 1 << 15, blocks = FB_SM_COUNT * 8;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k_fma_peak<<<blocks, 256, 0, s>>>(d, 1 << 10);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(e0, s));
+    k_fma_peak<<<blocks, 256, 0, s>>>(d, iters);
+    CK(cudaEventRecord(e1, s));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CK(cudaFreeAsync(d, s));
+  *out_tflops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks / ((double)best * 1e-3) / 1e12;
+  return FB_OK;
+}
+
+}  // extern "C"

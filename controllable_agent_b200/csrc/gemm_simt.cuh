@@ -22,10 +22,12 @@ enum { GEMM_CFG_BIG = 0, GEMM_CFG_SMALL = 1 };  // 128x128 tile, 8x8 per thread 
 struct __align__(16) GemmDesc {
   const float* A;
   const float* B;
+  const float* A2;    // optional second K segment (same majors / leading dims): C = A.B^T + A2.B2^T
+  const float* B2;
   float* C;
   const float* bias;  // [N] or null; added once (by k-split 0)
   const float* mask;  // same indexing as C with ldmask, or null
-  int M, N, K;
+  int M, N, K, K2;
   int lda, ldb, ldc, ldmask;
   int a_kmajor, b_kmajor;
   int a_vec, b_vec, c_vec;  // 128-bit access legal (pointer and leading dimension 16-byte aligned)
@@ -91,8 +93,11 @@ __device__ __forceinline__ void gemm_store_slot(float* __restrict__ S, int slot,
   }
 }
 
+// accumulate op(A)[m0.., kbeg..kend) . op(B)[n0.., kbeg..kend)^T into acc (register-prefetch double buffering)
 template <int BM, int BN, int TM, int TN, bool AK, bool BKM>
-__device__ __forceinline__ void gemm_tile(const GemmDesc& d, int tm, int tn, int ks, float* __restrict__ smem) {
+__device__ __forceinline__ void gemm_accumulate(const float* __restrict__ A, const float* __restrict__ B, int lda, int ldb,
+                                                int M, int N, int m0, int n0, int kbeg, int kend, bool avec, bool bvec,
+                                                float* __restrict__ smem, float (&acc)[TM][TN]) {
   constexpr int BK = GEMM_BK;
   constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
   constexpr int A_SLOTS = BM * BK / 4 / GEMM_THREADS;
@@ -101,35 +106,20 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, int tm, int tn, int
   static_assert((BM / TM) * (BN / TN) == GEMM_THREADS, "thread tiling must cover the CTA tile");
   float* As = smem;                    // [2][BK][LDA_S]
   float* Bs = smem + 2 * BK * LDA_S;   // [2][BK][LDB_S]
-
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int m0 = tm * BM, n0 = tn * BN;
-  const int kbeg = ks * d.k_per_split;
-  const int kend = min(d.K, kbeg + d.k_per_split);
-  const float* __restrict__ A = d.A;
-  const float* __restrict__ B = d.B;
-  const int lda = d.lda, ldb = d.ldb, M = d.M, N = d.N;
-  const bool avec = d.a_vec != 0, bvec = d.b_vec != 0;
-
   float4 ra[A_SLOTS], rb[B_SLOTS];
-  float acc[TM][TN];
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   const int nk = (kend - kbeg + BK - 1) / BK;
-  if (nk > 0) {
+  if (nk <= 0) return;
 #pragma unroll
-    for (int i = 0; i < A_SLOTS; ++i) ra[i] = gemm_load_slot<BM, AK>(A, lda, M, m0, kbeg, kend, tid + i * GEMM_THREADS, avec);
+  for (int i = 0; i < A_SLOTS; ++i) ra[i] = gemm_load_slot<BM, AK>(A, lda, M, m0, kbeg, kend, tid + i * GEMM_THREADS, avec);
 #pragma unroll
-    for (int i = 0; i < B_SLOTS; ++i) rb[i] = gemm_load_slot<BN, BKM>(B, ldb, N, n0, kbeg, kend, tid + i * GEMM_THREADS, bvec);
+  for (int i = 0; i < B_SLOTS; ++i) rb[i] = gemm_load_slot<BN, BKM>(B, ldb, N, n0, kbeg, kend, tid + i * GEMM_THREADS, bvec);
 #pragma unroll
-    for (int i = 0; i < A_SLOTS; ++i) gemm_store_slot<BM, AK>(As, tid + i * GEMM_THREADS, ra[i]);
+  for (int i = 0; i < A_SLOTS; ++i) gemm_store_slot<BM, AK>(As, tid + i * GEMM_THREADS, ra[i]);
 #pragma unroll
-    for (int i = 0; i < B_SLOTS; ++i) gemm_store_slot<BN, BKM>(Bs, tid + i * GEMM_THREADS, rb[i]);
-  }
+  for (int i = 0; i < B_SLOTS; ++i) gemm_store_slot<BN, BKM>(Bs, tid + i * GEMM_THREADS, rb[i]);
   __syncthreads();
 
   for (int kt = 0; kt < nk; ++kt) {
@@ -178,6 +168,28 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, int tm, int tn, int
     }
     __syncthreads();
   }
+}
+
+template <int BM, int BN, int TM, int TN, bool AK, bool BKM>
+__device__ __forceinline__ void gemm_tile(const GemmDesc& d, int tm, int tn, int ks, float* __restrict__ smem) {
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = tm * BM, n0 = tn * BN;
+  const int M = d.M, N = d.N;
+  const bool avec = d.a_vec != 0, bvec = d.b_vec != 0;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  {
+    const int kbeg = ks * d.k_per_split;
+    const int kend = min(d.K, kbeg + d.k_per_split);
+    gemm_accumulate<BM, BN, TM, TN, AK, BKM>(d.A, d.B, d.lda, d.ldb, M, N, m0, n0, kbeg, kend, avec, bvec, smem, acc);
+  }
+  if (d.K2 > 0)  // second segment (never combined with split-K)
+    gemm_accumulate<BM, BN, TM, TN, AK, BKM>(d.A2, d.B2, d.lda, d.ldb, M, N, m0, n0, 0, d.K2, avec, bvec, smem, acc);
 
   // ---- epilogue ----
   const float alpha = d.alpha;

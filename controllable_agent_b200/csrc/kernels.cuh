@@ -52,9 +52,10 @@ __global__ void k_tick(DevScalars* s, int which, float beta1, float beta2) {
 // (l+32)-th ... 128-bit chunk of the output row, so a warp reads the two adjacent storage rows (t-1, t)
 // as contiguous coalesced 16-byte loads.
 struct GatherSlot {   // one 16-byte chunk of the output row
-  short src_row;      // 0: row t-1, 1: row t, 2: row future-1, -1: zero fill
+  short src_row;      // 0: row t-1, 1: row t, 2: row future-1
   short special;      // 1: the [reward, discount, 0, 0] chunk (discount is scaled)
   int src_f4;         // float4 index inside the storage row
+  int dst_f4;         // float4 index inside the output row
 };
 #define FB_MAX_GATHER_SLOTS 192
 
@@ -89,38 +90,42 @@ __global__ void __launch_bounds__(256) k_gather_rows(const __grid_constant__ Gat
     else if (sl.src_row == 1) v = ld_stream_f4(r_cur + sl.src_f4);
     else if (sl.src_row == 2) { if (future_idx) v = ld_stream_f4(r_fut + sl.src_f4); else continue; }
     if (sl.special) { v.y *= gamma; v.z = 0.f; v.w = 0.f; }
-    o[s] = v;
+    o[sl.dst_f4] = v;
   }
 }
 
-// write one finished episode into packed storage (device-side repack of [rows, dim] field arrays)
-__global__ void k_pack_episode(float* __restrict__ dst_rows, int row_stride, int rows, int O, int A, int G, int off_action,
-                               int off_reward, int off_goal, const float* __restrict__ obs, const float* __restrict__ act,
-                               const float* __restrict__ rew, const float* __restrict__ disc, const float* __restrict__ goal) {
+// write one finished episode into packed storage (device-side repack of tight [rows, dim] field arrays)
+struct PackEpisodeParams { int row_stride, rows, O, A, G, X, off_obs, off_action, off_reward, off_goal, off_extra; };
+
+__global__ void k_pack_episode(float* __restrict__ dst_rows, PackEpisodeParams P, const float* __restrict__ obs,
+                               const float* __restrict__ act, const float* __restrict__ rew, const float* __restrict__ disc,
+                               const float* __restrict__ goal, const float* __restrict__ extra) {
   const int r = blockIdx.x;
-  if (r >= rows) return;
-  float* d = dst_rows + (size_t)r * row_stride;
-  for (int c = threadIdx.x; c < row_stride; c += blockDim.x) {
+  if (r >= P.rows) return;
+  float* d = dst_rows + (size_t)r * P.row_stride;
+  for (int c = threadIdx.x; c < P.row_stride; c += blockDim.x) {
     float v = 0.f;
-    if (c < O) v = obs[(size_t)r * O + c];
-    else if (c >= off_action && c < off_action + A) v = act[(size_t)r * A + (c - off_action)];
-    else if (c == off_reward) v = rew[r];
-    else if (c == off_reward + 1) v = disc[r];
-    else if (G > 0 && c >= off_goal && c < off_goal + G) v = goal[(size_t)r * G + (c - off_goal)];
+    if (c >= P.off_obs && c < P.off_obs + P.O) v = obs[(size_t)r * P.O + (c - P.off_obs)];
+    else if (c >= P.off_action && c < P.off_action + P.A) v = act[(size_t)r * P.A + (c - P.off_action)];
+    else if (c == P.off_reward) v = rew[r];
+    else if (c == P.off_reward + 1) v = disc[r];
+    else if (P.G > 0 && c >= P.off_goal && c < P.off_goal + P.G) v = goal[(size_t)r * P.G + (c - P.off_goal)];
+    else if (P.X > 0 && c >= P.off_extra && c < P.off_extra + P.X) v = extra[(size_t)r * P.X + (c - P.off_extra)];
     d[c] = v;
   }
 }
 
 // layout of the packed batch row (floats)
 struct BatchLayout {
-  int O, A, G;          // G == 0: no goal columns
-  int off_obs, off_action, off_rd, off_next_obs, off_goal, off_next_goal, off_future_obs, off_future_goal, pitch;
+  int O, A, G, X;       // G == 0: no goal columns; X: extra (meta) columns, gathered at t-1
+  int with_future;
+  int off_obs, off_action, off_rd, off_next_obs, off_goal, off_next_goal, off_extra, off_future_obs, off_future_goal, pitch;
 };
 
 // tight user arrays -> packed batch rows (explicit-input path; fb_set_batch)
 __global__ void k_pack_batch(BatchLayout L, int batch, const float* __restrict__ obs, const float* __restrict__ action,
                              const float* __restrict__ discount, const float* __restrict__ next_obs,
-                             const float* __restrict__ next_goal, float* __restrict__ out) {
+                             const float* __restrict__ goal, const float* __restrict__ next_goal, float* __restrict__ out) {
   const int r = blockIdx.x;
   if (r >= batch) return;
   float* o = out + (size_t)r * L.pitch;
@@ -129,8 +134,11 @@ __global__ void k_pack_batch(BatchLayout L, int batch, const float* __restrict__
     o[L.off_next_obs + c] = next_obs[(size_t)r * L.O + c];
   }
   for (int c = threadIdx.x; c < L.A; c += blockDim.x) o[L.off_action + c] = action[(size_t)r * L.A + c];
-  if (L.G > 0 && next_goal)
-    for (int c = threadIdx.x; c < L.G; c += blockDim.x) o[L.off_next_goal + c] = next_goal[(size_t)r * L.G + c];
+  if (L.G > 0 && goal && next_goal)
+    for (int c = threadIdx.x; c < L.G; c += blockDim.x) {
+      o[L.off_goal + c] = goal[(size_t)r * L.G + c];
+      o[L.off_next_goal + c] = next_goal[(size_t)r * L.G + c];
+    }
   if (threadIdx.x == 0) { o[L.off_rd] = 0.f; o[L.off_rd + 1] = discount[r]; }
 }
 

@@ -1,0 +1,215 @@
+// Host-side launch plan of one FB-DDPG gradient step (fb_ddpg.py:427-520) on one B200.
+//
+// The plan is built once per handle (fb_bind): every activation lives at a fixed address inside the
+// caller's workspace, every kernel argument is a constant, so a phase is a fixed launch sequence that can
+// be replayed eagerly or as a CUDA graph.  Layers of different networks that sit at the same depth of the
+// step's dependency graph are issued as ONE grouped SGEMM launch (gemm_simt.cuh) so a launch fills 148 SMs.
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fb_b200.h"
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+
+#define FB_NUM_PHASES 10
+#define FB_DESC_ARENA_BYTES (1u << 20)
+#define FB_SM_COUNT 148
+
+struct Mat {
+  float* p = nullptr;
+  int rows = 0, cols = 0, ld = 0;
+  Mat rs(int r0, int n) const { Mat m = *this; m.p = p + (size_t)r0 * ld; m.rows = n; return m; }
+  Mat cs(int c0, int n) const { Mat m = *this; m.p = p + c0; m.cols = n; return m; }
+};
+
+struct TensorInfo { std::string name; size_t off; int rows, cols; size_t numel() const { return (size_t)rows * (cols ? cols : 1); } };
+
+struct SegmentLayout {
+  std::vector<TensorInfo> t;
+  size_t size = 0;
+  int add(const std::string& name, int rows, int cols) {
+    TensorInfo ti{name, size, rows, cols};
+    t.push_back(ti);
+    size += (ti.numel() + 31) / 32 * 32;  // every tensor starts on a 128-byte boundary
+    return (int)t.size() - 1;
+  }
+};
+
+typedef std::function<cudaError_t(cudaStream_t)> Op;
+
+struct fb_handle {
+  fb_config cfg;
+  // parameter layout: fb segment = forward_net tensors [0,20) then backward_net tensors [20,28); actor segment
+  SegmentLayout seg_fb, seg_actor;
+  int fwd_first = 0, bwd_first = 0;
+  size_t bwd_offset = 0;  // float offset of the first backward_net tensor inside the fb segment
+  fb_buffers bufs;
+  bool bound = false;
+  size_t ws_bytes = 0;
+  // workspace bump allocator
+  char* ws_base = nullptr;
+  size_t ws_off = 0;
+  // descriptor arena (host mirror, uploaded once at bind)
+  std::vector<char> arena;
+  // plan
+  std::vector<Op> ops[FB_NUM_PHASES];
+  std::map<std::string, Mat> views;
+  std::map<uint32_t, cudaGraphExec_t> graphs;
+  // fixed workspace objects
+  DevScalars* d_sc = nullptr;
+  double* d_acc = nullptr;
+  unsigned int* d_linf = nullptr;
+  float* d_metrics = nullptr;
+  int* d_n_episodes = nullptr;
+  int *d_ep_idx = nullptr, *d_step_idx = nullptr, *d_future_idx = nullptr, *d_perm = nullptr, *d_mix_mask = nullptr;
+  unsigned int* d_perm_keys = nullptr;
+  int* d_identity_perm = nullptr;
+  Mat packed, z_rand, noise_fb, noise_actor, blk_local, blk_global;
+  BatchLayout bl;
+  fb_replay_view replay;
+  bool replay_bound = false;
+  bool have_perm = false, have_mix_mask = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+// layout (registration order of fb_modules.py: Actor :81-108, ForwardMap :154-185, BackwardMap :211-221)
+// ------------------------------------------------------------------------------------------------
+static void add_embed(SegmentLayout& s, const std::string& p, int in_dim, int H, int Fd) {
+  s.add(p + ".0.weight", H, in_dim); s.add(p + ".0.bias", H, 0);
+  s.add(p + ".1.weight", H, 0); s.add(p + ".1.bias", H, 0);
+  s.add(p + ".3.weight", Fd, H); s.add(p + ".3.bias", Fd, 0);
+}
+static void add_head(SegmentLayout& s, const std::string& p, int Fd, int H, int out) {
+  s.add(p + ".0.weight", H, 2 * Fd); s.add(p + ".0.bias", H, 0);
+  s.add(p + ".2.weight", out, H); s.add(p + ".2.bias", out, 0);
+}
+static void build_layout(fb_handle* h) {
+  const fb_config& c = h->cfg;
+  const int O = c.obs_dim, A = c.action_dim, Z = c.z_dim, G = c.goal_dim, H = c.hidden_dim, Fd = c.feature_dim, Hb = c.backward_hidden_dim;
+  SegmentLayout& f = h->seg_fb;
+  h->fwd_first = 0;
+  add_embed(f, "obs_action_net", O + A, H, Fd);
+  add_embed(f, "obs_z_net", O + Z, H, Fd);
+  add_head(f, "F1", Fd, H, Z);
+  add_head(f, "F2", Fd, H, Z);
+  h->bwd_first = (int)f.t.size();
+  h->bwd_offset = f.size;
+  f.add("B.0.weight", Hb, G); f.add("B.0.bias", Hb, 0); f.add("B.1.weight", Hb, 0); f.add("B.1.bias", Hb, 0);
+  f.add("B.3.weight", Hb, Hb); f.add("B.3.bias", Hb, 0); f.add("B.5.weight", Z, Hb); f.add("B.5.bias", Z, 0);
+  SegmentLayout& a = h->seg_actor;
+  add_embed(a, "obs_net", O, H, Fd);
+  add_embed(a, "obs_z_net", O + Z, H, Fd);
+  add_head(a, "policy", Fd, H, A);
+}
+
+// a parameter set: values + (optional) gradient buffer sharing one layout
+struct PSet {
+  const SegmentLayout* L; int first; float* val; float* grad;
+  Mat w(int i) const { const TensorInfo& t = L->t[first + i]; Mat m; m.p = val + t.off; m.rows = t.rows; m.cols = t.cols ? t.cols : 1; m.ld = m.cols; return m; }
+  float* v(int i) const { return val + L->t[first + i].off; }
+  Mat gw(int i) const { Mat m = w(i); m.p = grad + L->t[first + i].off; return m; }
+  float* gv(int i) const { return grad ? grad + L->t[first + i].off : nullptr; }
+  PSet sub(int d) const { PSet p = *this; p.first += d; return p; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------------
+static void* ws_alloc(fb_handle* h, size_t bytes) {
+  h->ws_off = (h->ws_off + 255) / 256 * 256;
+  void* p = h->ws_base + h->ws_off;
+  h->ws_off += bytes;
+  return p;
+}
+static Mat ws_mat(fb_handle* h, int rows, int cols, const char* name = nullptr) {
+  Mat m; m.rows = rows; m.cols = cols; m.ld = fb_round_up(cols, 4);
+  m.p = (float*)ws_alloc(h, (size_t)rows * m.ld * sizeof(float));
+  if (name) h->views[name] = m;
+  return m;
+}
+template <typename T>
+static T* arena_put(fb_handle* h, const std::vector<T>& v, char* d_arena) {
+  size_t off = (h->arena.size() + 15) / 16 * 16;
+  h->arena.resize(off + v.size() * sizeof(T));
+  memcpy(h->arena.data() + off, v.data(), v.size() * sizeof(T));
+  return reinterpret_cast<T*>(d_arena + off);
+}
+
+// ------------------------------------------------------------------------------------------------
+// grouped GEMM construction
+// ------------------------------------------------------------------------------------------------
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+static GemmDesc gemm_raw(const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor, float* C, int ldc, int M, int N,
+                         int K, const float* bias, int flags, const float* mask, int ldmask) {
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.A = A; d.B = B; d.C = C; d.bias = bias; d.mask = mask;
+  d.M = M; d.N = N; d.K = K; d.K2 = 0;
+  d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.ldmask = ldmask;
+  d.a_kmajor = a_kmajor; d.b_kmajor = b_kmajor;
+  d.flags = flags; d.alpha = 1.f; d.splitk = 1;
+  return d;
+}
+// Y[rows, out] = X . W^T + b            (nn.Linear forward)
+static GemmDesc lin_fwd(const Mat& X, const Mat& W, const float* bias, const Mat& Y, int flags) {
+  return gemm_raw(X.p, X.ld, 1, W.p, W.ld, 1, Y.p, Y.ld, X.rows, W.rows, W.cols, bias, flags, nullptr, 0);
+}
+// dX[rows, in] = dY . W   (optionally masked by a saved activation)
+static GemmDesc lin_dx(const Mat& dY, const Mat& W, const Mat& dX, int flags, const Mat* mask) {
+  return gemm_raw(dY.p, dY.ld, 1, W.p, W.ld, 0, dX.p, dX.ld, dY.rows, W.cols, W.rows, nullptr, flags, mask ? mask->p : nullptr,
+                  mask ? mask->ld : 0);
+}
+// dW[out, in] += dY^T . X  (accumulates into the zeroed flat gradient; split-K over the batch)
+static GemmDesc lin_dw(const Mat& dY, const Mat& X, const Mat& dW) {
+  GemmDesc d = gemm_raw(dY.p, dY.ld, 0, X.p, X.ld, 0, dW.p, dW.ld, dW.rows, dW.cols, dY.rows, nullptr, GF_ATOMIC, nullptr, 0);
+  d.splitk = -1;  // let finalize choose
+  return d;
+}
+
+struct GroupLaunch { const GemmDesc* d_descs; int nprob, ctas; };
+
+static GroupLaunch finalize_group(fb_handle* h, std::vector<GemmDesc> g, char* d_arena) {
+  // tile configuration per problem
+  int big_tiles = 0;
+  for (auto& d : g) {
+    d.cfg = (d.M > 64 && d.N > 64) ? GEMM_CFG_BIG : GEMM_CFG_SMALL;
+    const int bm = d.cfg == GEMM_CFG_BIG ? 128 : 64;
+    d.tiles_m = fb_ceil_div(d.M, bm); d.tiles_n = fb_ceil_div(d.N, bm);
+    big_tiles += d.tiles_m * d.tiles_n;
+  }
+  int total = 0;
+  for (auto& d : g) total += d.tiles_m * d.tiles_n;
+  const int target = 2 * FB_SM_COUNT;
+  int work = 0;
+  for (auto& d : g) {
+    const int tiles = d.tiles_m * d.tiles_n;
+    int sk = 1;
+    const bool can_split = (d.flags & GF_ATOMIC) && d.K2 == 0 && !(d.flags & GF_RELU);
+    if (can_split && total < target) {
+      sk = fb_ceil_div(target, total);
+      const int max_sk = d.K / 128 > 0 ? d.K / 128 : 1;
+      if (sk > max_sk) sk = max_sk;
+      if (sk > 16) sk = 16;
+    }
+    int kps = fb_round_up(fb_ceil_div(d.K, sk), GEMM_BK);
+    sk = fb_ceil_div(d.K, kps);
+    d.splitk = sk; d.k_per_split = kps;
+    if (sk == 1 && (d.flags & GF_ATOMIC) == 0) d.k_per_split = fb_round_up(d.K, GEMM_BK);
+    d.a_vec = aligned16(d.A) && (d.lda % 4 == 0) && (d.K2 == 0 || aligned16(d.A2));
+    d.b_vec = aligned16(d.B) && (d.ldb % 4 == 0) && (d.K2 == 0 || aligned16(d.B2));
+    d.c_vec = aligned16(d.C) && (d.ldc % 4 == 0);
+    d.work_begin = work; d.work_count = tiles * sk;
+    work += d.work_count;
+  }
+  (void)big_tiles;
+  GroupLaunch gl;
+  gl.d_descs = arena_put(h, g, d_arena);
+  gl.nprob = (int)g.size(); gl.ctas = work;
+  return gl;
+}

@@ -1,0 +1,224 @@
+"""FBStepEngine — the Python owner of one libfb_b200 handle.
+
+PyTorch is used for device memory and streams only: the engine allocates the flat parameter / gradient /
+Adam-moment / target segments and the workspace as CUDA tensors, hands their raw pointers to the C ABI
+(include/fb_b200.h) and exposes named views on them.  All arithmetic of the gradient step
+(url_benchmark/agent/fb_ddpg.py:427-520) happens inside the library's sm_100a kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import typing as tp
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+@dataclasses.dataclass
+class EngineConfig:
+    batch: int
+    obs_dim: int
+    action_dim: int
+    z_dim: int
+    goal_dim: int
+    hidden_dim: int = 1024
+    feature_dim: int = 512
+    backward_hidden_dim: int = 526
+    use_goal: bool = False
+    rng_device: bool = False
+    ortho_coef: float = 1.0
+    mix_ratio: float = 0.5
+    beta1: float = 0.9
+    beta2: float = 0.999
+    adam_eps: float = 1e-8
+    seed: int = 0
+    global_batch: tp.Optional[int] = None   # multi-GPU: rows of all ranks; None = batch
+    row_offset: int = 0                     # multi-GPU: global index of local row 0
+
+
+def _ptr(t: tp.Optional[torch.Tensor]) -> tp.Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class FBStepEngine:
+    def __init__(self, cfg: EngineConfig, device: tp.Union[str, torch.device] = "cuda") -> None:
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("controllable_agent_b200 runs on CUDA (sm_100a) only; there is no CPU path "
+                               f"(got device={device!r})")
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA is not available: controllable_agent_b200 has no CPU fallback")
+        self.lib = L.load()
+        self.cfg = cfg
+        c = L.fb_config(abi_version=L.FB_ABI_VERSION, batch=cfg.batch, global_batch=cfg.global_batch or cfg.batch,
+                        row_offset=cfg.row_offset, obs_dim=cfg.obs_dim, action_dim=cfg.action_dim, z_dim=cfg.z_dim,
+                        goal_dim=cfg.goal_dim, hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim,
+                        backward_hidden_dim=cfg.backward_hidden_dim, use_goal=int(cfg.use_goal),
+                        rng_device=int(cfg.rng_device), ortho_coef=cfg.ortho_coef, mix_ratio=cfg.mix_ratio,
+                        beta1=cfg.beta1, beta2=cfg.beta2, adam_eps=cfg.adam_eps, seed=cfg.seed)
+        h = C.c_void_p()
+        L.check(self.lib.fb_create(C.byref(c), C.byref(h)), "fb_create")
+        self.h = h
+        with torch.cuda.device(self.device):
+            n_fb, n_actor = self.lib.fb_flat_size(h, 0), self.lib.fb_flat_size(h, 1)
+            z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)  # noqa: E731
+            self.param_fb, self.grad_fb, self.m_fb, self.v_fb, self.target_fb = z(n_fb), z(n_fb), z(n_fb), z(n_fb), z(n_fb)
+            self.param_actor, self.grad_actor, self.m_actor, self.v_actor = z(n_actor), z(n_actor), z(n_actor), z(n_actor)
+            ws_bytes = self.lib.fb_workspace_bytes(h)
+            self.workspace = torch.zeros(ws_bytes + 256, dtype=torch.uint8, device=self.device)
+            ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
+            self._ws_shift = ws_ptr - self.workspace.data_ptr()
+            bufs = L.fb_buffers(self.param_fb.data_ptr(), self.grad_fb.data_ptr(), self.m_fb.data_ptr(), self.v_fb.data_ptr(),
+                                self.target_fb.data_ptr(), self.param_actor.data_ptr(), self.grad_actor.data_ptr(),
+                                self.m_actor.data_ptr(), self.v_actor.data_ptr(), ws_ptr, ws_bytes)
+            L.check(self.lib.fb_bind(h, C.byref(bufs), self._stream()), "fb_bind")
+        self.layout = {net: self._tensor_table(net) for net in (L.NET_FORWARD, L.NET_BACKWARD, L.NET_ACTOR)}
+        self._scalars: tp.Optional[tp.Tuple[float, ...]] = None
+        self._keepalive: tp.List[tp.Any] = []
+        mp = self.lib.fb_metrics_ptr(h)
+        self._metrics = self._wrap(mp, L.METRIC_COUNT)
+        self._metrics_host = torch.zeros(L.METRIC_COUNT, dtype=torch.float32).pin_memory()
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self) -> None:
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.fb_destroy(self.h)
+            self.h = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _wrap(self, ptr: int, numel: int) -> torch.Tensor:
+        """fp32 tensor view of `numel` floats at device address `ptr` inside the workspace."""
+        off = ptr - self.workspace.data_ptr()
+        assert 0 <= off and off + 4 * numel <= self.workspace.numel(), "pointer outside the workspace"
+        return self.workspace[off:off + 4 * numel].view(torch.float32)
+
+    def _tensor_table(self, net: int) -> tp.List[tp.Tuple[str, int, tp.Tuple[int, ...]]]:
+        out = []
+        for i in range(self.lib.fb_num_tensors(self.h, net)):
+            off, rows, cols = C.c_size_t(), C.c_int(), C.c_int()
+            name = C.create_string_buffer(64)
+            L.check(self.lib.fb_tensor_info(self.h, net, i, C.byref(off), C.byref(rows), C.byref(cols), name, 64))
+            shape = (rows.value, cols.value) if cols.value else (rows.value,)
+            out.append((name.value.decode(), off.value, shape))
+        return out
+
+    def tensors(self, net: int, which: str = "param") -> "tp.OrderedDict[str, torch.Tensor]":
+        """Named views (nn.Module registration order) of one net inside a flat segment.
+        which: param | grad | m | v | target (target only for forward/backward nets)."""
+        import collections
+        seg = {"param": (self.param_fb, self.param_actor), "grad": (self.grad_fb, self.grad_actor),
+               "m": (self.m_fb, self.m_actor), "v": (self.v_fb, self.v_actor), "target": (self.target_fb, None)}[which]
+        flat = seg[1] if net == L.NET_ACTOR else seg[0]
+        if flat is None:
+            raise ValueError("the actor has no target network")
+        out = collections.OrderedDict()
+        for name, off, shape in self.layout[net]:
+            n = int(np.prod(shape))
+            out[name] = flat[off:off + n].view(*shape)
+        return out
+
+    def view(self, name: str) -> torch.Tensor:
+        """Strided view of a named workspace matrix (test introspection)."""
+        p, rows, cols, ld = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        L.check(self.lib.fb_workspace_view(self.h, name.encode(), C.byref(p), C.byref(rows), C.byref(cols), C.byref(ld)),
+                f"fb_workspace_view({name})")
+        flat = self._wrap(p.value, (rows.value - 1) * ld.value + cols.value)
+        return torch.as_strided(flat, (rows.value, cols.value), (ld.value, 1))
+
+    # -- per-step inputs -------------------------------------------------------------------------
+    def set_scalars(self, stddev: float, stddev_clip: float, lr_forward: float, lr_backward: float, lr_actor: float,
+                    tau: float, replay_discount: float = 1.0, replay_future: float = 1.0, grad_scale: float = 1.0) -> None:
+        key = (stddev, stddev_clip, lr_forward, lr_backward, lr_actor, tau, replay_discount, replay_future, grad_scale)
+        if key == self._scalars:
+            return
+        s = L.fb_step_scalars(*key)
+        L.check(self.lib.fb_set_step_scalars(self.h, C.byref(s), self._stream()), "fb_set_step_scalars")
+        self._scalars = key
+
+    def _dev_i32(self, x: tp.Any) -> tp.Optional[torch.Tensor]:
+        if x is None:
+            return None
+        t = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x)
+        t = t.to(device=self.device, dtype=torch.int32).contiguous()
+        assert t.numel() == self.cfg.batch
+        return t
+
+    def _dev_f32(self, x: tp.Any, cols: int) -> tp.Optional[torch.Tensor]:
+        if x is None:
+            return None
+        t = torch.as_tensor(x).to(device=self.device, dtype=torch.float32).contiguous()
+        assert t.numel() == self.cfg.batch * cols, (tuple(t.shape), self.cfg.batch, cols)
+        return t
+
+    def set_indices(self, ep_idx: tp.Any = None, step_idx: tp.Any = None, future_idx: tp.Any = None, perm: tp.Any = None,
+                    mix_mask: tp.Any = None) -> None:
+        ts = [self._dev_i32(x) for x in (ep_idx, step_idx, future_idx, perm, mix_mask)]
+        L.check(self.lib.fb_set_indices(self.h, *[_ptr(t) for t in ts], self._stream()), "fb_set_indices")
+        self._keepalive = ts  # copies are enqueued on the stream; keep the sources alive until the next call
+
+    def set_batch(self, obs: tp.Any, action: tp.Any, discount: tp.Any, next_obs: tp.Any, goal: tp.Any = None,
+                  next_goal: tp.Any = None) -> None:
+        c = self.cfg
+        ts = [self._dev_f32(obs, c.obs_dim), self._dev_f32(action, c.action_dim), self._dev_f32(discount, 1),
+              self._dev_f32(next_obs, c.obs_dim),
+              self._dev_f32(goal, c.goal_dim) if c.use_goal else None,
+              self._dev_f32(next_goal, c.goal_dim) if c.use_goal else None]
+        L.check(self.lib.fb_set_batch(self.h, *[_ptr(t) for t in ts], self._stream()), "fb_set_batch")
+        self._keepalive_batch = ts
+
+    def set_z(self, z: tp.Any) -> None:
+        t = self._dev_f32(z, self.cfg.z_dim)
+        L.check(self.lib.fb_set_z(self.h, _ptr(t), self._stream()), "fb_set_z")
+        self._keepalive_z = t
+
+    def set_noise(self, noise_fb: tp.Any = None, noise_actor: tp.Any = None) -> None:
+        a, b = self._dev_f32(noise_fb, self.cfg.action_dim), self._dev_f32(noise_actor, self.cfg.action_dim)
+        L.check(self.lib.fb_set_noise(self.h, _ptr(a), _ptr(b), self._stream()), "fb_set_noise")
+        self._keepalive_noise = (a, b)
+
+    def bind_replay(self, view: "L.fb_replay_view") -> None:
+        L.check(self.lib.fb_bind_replay(self.h, C.byref(view), self._stream()), "fb_bind_replay")
+
+    def set_adam_steps(self, fb_step: int, actor_step: int) -> None:
+        L.check(self.lib.fb_set_adam_steps(self.h, fb_step, actor_step, self._stream()), "fb_set_adam_steps")
+
+    def get_adam_steps(self) -> tp.Tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        L.check(self.lib.fb_get_adam_steps(self.h, C.byref(a), C.byref(b), self._stream()), "fb_get_adam_steps")
+        return a.value, b.value
+
+    # -- the step --------------------------------------------------------------------------------
+    def run(self, mask: int = L.PHASE_ALL, graph: bool = False) -> None:
+        L.check(self.lib.fb_run(self.h, mask, int(graph), self._stream()), f"fb_run(0x{mask:x})")
+
+    def launch_count(self, mask: int = L.PHASE_ALL) -> int:
+        return self.lib.fb_launch_count(self.h, mask)
+
+    def gather_block(self) -> tp.Tuple[torch.Tensor, torch.Tensor]:
+        """(local, global) packed [rows, pitch] blocks for the multi-GPU all-gather between FB_FWD and FB_LOSS."""
+        n, pl, pg = C.c_int(), C.c_void_p(), C.c_void_p()
+        L.check(self.lib.fb_gather_block(self.h, C.byref(n), C.byref(pl), C.byref(pg)), "fb_gather_block")
+        gb = self.cfg.global_batch or self.cfg.batch
+        return (self._wrap(pl.value, self.cfg.batch * n.value).view(self.cfg.batch, n.value),
+                self._wrap(pg.value, gb * n.value).view(gb, n.value))
+
+    def metrics_tensor(self) -> torch.Tensor:
+        return self._metrics
+
+    def read_metrics(self) -> tp.Dict[str, float]:
+        """One D2H copy of the metrics block (replaces the ~19 .item() syncs of fb_ddpg.py:357-377,414-418)."""
+        self._metrics_host.copy_(self._metrics, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        vals = self._metrics_host.tolist()
+        return {k: vals[i] for i, k in enumerate(L.METRIC_KEYS)}

@@ -110,7 +110,10 @@ typedef struct fb_replay_view {
   const int32_t* d_episode_len; /* [max_episodes] transitions per episode (rows-1) */
   int32_t max_episodes, rows_per_episode, row_stride;
   int32_t n_episodes;           /* len(buffer): episodes currently sampleable */
-  int32_t off_obs, off_action, off_reward, off_discount, off_goal; /* column offsets; off_goal<0 if absent */
+  /* column offsets (floats, each a multiple of 4; off_discount == off_reward + 1); off_goal / off_extra < 0 if absent.
+   * `extra` = the non-TimeStep (meta) keys concatenated, in_memory_replay_buffer.py:162 */
+  int32_t off_obs, off_action, off_reward, off_discount, off_goal, off_extra;
+  int32_t goal_dim, extra_dim;
 } fb_replay_view;
 
 typedef struct fb_handle fb_handle;
@@ -135,7 +138,9 @@ size_t fb_workspace_bytes(const fb_handle* h);
 /* ---- binding --------------------------------------------------------------------------------- */
 /* record the caller's buffers, zero the workspace, build the launch plan (synchronises once) */
 int fb_bind(fb_handle* h, const fb_buffers* bufs, void* stream);
-int fb_bind_replay(fb_handle* h, const fb_replay_view* view);
+/* (re)bind the HBM replay storage FB_PHASE_SAMPLE gathers from; copies n_episodes to the device.  Cheap when only
+ * n_episodes changed (online training, pretrain.py:649). */
+int fb_bind_replay(fb_handle* h, const fb_replay_view* view, void* stream);
 
 /* ---- per-step inputs --------------------------------------------------------------------------- */
 int fb_set_step_scalars(fb_handle* h, const fb_step_scalars* s, void* stream);
@@ -179,18 +184,22 @@ int fb_gather_block(fb_handle* h, int* floats_per_row, float** d_local, float** 
  * "B","tB","dF1","dF2","dB","mu","mix_input","next_goal", ... returns rows, cols, leading dim */
 int fb_workspace_view(fb_handle* h, const char* name, float** d_ptr, int* rows, int* cols, int* ld);
 
-/* ---- stand-alone operators (tests, microbenchmarks) ------------------------------------------- */
-/* the replay gather alone: out rows [batch, out_ld] = [obs|action|reward|discount|next_obs|goal|next_goal|
- * future_obs|future_goal] (goal parts only if the view has goals), discount multiplied by
- * replay_discount.  future_idx may be NULL (those columns are then left untouched). */
-int fb_replay_gather(const fb_replay_view* view, const int32_t* d_ep_idx, const int32_t* d_step_idx,
-                     const int32_t* d_future_idx, int batch, float replay_discount, float* d_out, int out_ld,
-                     void* stream);
-/* write one finished episode ([rows, dim] host-or-device fp32 arrays already on the device) into the
- * packed storage: dst row block = rows of episode `slot` */
-int fb_replay_pack_episode(const fb_replay_view* view, float* d_rows_mut, int slot, int rows, const float* d_obs,
-                           const float* d_action, const float* d_reward, const float* d_discount,
-                           const float* d_goal, void* stream);
+/* ---- stand-alone operators (ReplayBuffer.sample / add, tests, microbenchmarks) ------------------- */
+/* layout of a packed batch row: float offsets of [obs, action, (reward,discount,0,0), next_obs, goal, next_goal, extra,
+ * future_obs, future_goal] (every field padded to a multiple of 4 floats) and the row pitch */
+int fb_batch_row_layout(int obs_dim, int action_dim, int goal_dim, int extra_dim, int with_future, int32_t* offsets9,
+                        int32_t* pitch);
+/* the replay gather alone (in_memory_replay_buffer.py:162-183): out rows [batch, out_ld] in fb_batch_row_layout order
+ * (goal / extra parts only if the view has them, future parts only if d_future_idx != NULL), discount multiplied by
+ * replay_discount.  obs = row step-1, action/reward/discount/next_obs = row step, future_* = row future-1. */
+int fb_replay_gather(const fb_replay_view* view, int obs_dim, int action_dim, const int32_t* d_ep_idx,
+                     const int32_t* d_step_idx, const int32_t* d_future_idx, int batch, float replay_discount, float* d_out,
+                     int out_ld, void* stream);
+/* write one finished episode (tight [rows, dim] fp32 field arrays already on the device) into the packed storage rows of
+ * episode `slot` (in_memory_replay_buffer.py:114-133) */
+int fb_replay_pack_episode(const fb_replay_view* view, float* d_rows_mut, int slot, int rows, int obs_dim, int action_dim,
+                           const float* d_obs, const float* d_action, const float* d_reward, const float* d_discount,
+                           const float* d_goal, const float* d_extra, void* stream);
 /* C[M,N] (+)= op(A)·op(B)^T with the grouped SIMT SGEMM used by the plan (single problem) */
 int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, int M, int N, int K, int lda, int ldb,
              int ldc, int a_kmajor, int b_kmajor, int relu, int splitk, void* stream);

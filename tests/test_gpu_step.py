@@ -1,0 +1,187 @@
+"""GPU parity of the FB-DDPG gradient step (through the C ABI) against
+  (a) the golden fixtures produced by the UNMODIFIED reference (tests/golden/update_*.npz) and
+  (b) the oracle restatement on fresh seeded inputs, at the reference's default widths.
+Tolerance: 1e-3 relative (BASELINE.json north_star); typical observed error is ~1e-6."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, subtree
+from gpu_common import REL_TOL, dims_from_params, golden_params, load_params, make_engine, read_tensors, rel
+from oracle import fb_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _L():
+    from controllable_agent_b200 import _lib as L
+    return L
+
+
+@pytest.mark.parametrize("M,N,K,ak,bk,relu,splitk", [
+    (128, 128, 64, 1, 1, 0, 1), (200, 150, 70, 1, 1, 1, 1), (1024, 512, 74, 1, 1, 0, 1), (96, 50, 128, 1, 1, 0, 1),
+    (300, 526, 526, 1, 0, 0, 1), (526, 24, 1000, 0, 0, 0, 4), (50, 1024, 333, 0, 0, 0, 3), (130, 6, 48, 1, 0, 0, 1),
+    (64, 64, 16, 0, 1, 0, 1), (257, 129, 1025, 1, 1, 0, 2)])
+def test_sgemm_against_float64(M, N, K, ak, bk, relu, splitk):
+    L = _L()
+    lib = L.load()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((M, K) if ak else (K, M), generator=g)
+    Bm = torch.randn((N, K) if bk else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = (A.double() if ak else A.double().T) @ (Bm.double().T if bk else Bm.double()) + bias.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    dA, dB, dbias = A.cuda(), Bm.cuda(), bias.cuda()
+    dC = torch.zeros(M, N, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    L.check(lib.fb_sgemm(dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), dbias.data_ptr(), M, N, K, A.shape[1], Bm.shape[1], N,
+                         ak, bk, relu, splitk, s))
+    torch.cuda.synchronize()
+    assert rel(dC, ref) < 1e-5
+
+
+def _run_update_case(g, d, use_goal, graph):
+    L = _L()
+    t = {k: torch.from_numpy(np.array(v)) for k, v in subtree(g, "in").items()}
+    B = t["obs"].shape[0]
+    eng = make_engine(d, B, use_goal=use_goal, mix_ratio=0.5, ortho_coef=float(g["cfg/ortho_coef"]))
+    load_params(eng, fwd=subtree(g, "param0/forward_net"), bwd=subtree(g, "param0/backward_net"),
+                actor=subtree(g, "param0/actor"), fwd_tgt=subtree(g, "param0/forward_target_net"),
+                bwd_tgt=subtree(g, "param0/backward_target_net"))
+    lr, tau = float(g["cfg/lr"]), float(g["cfg/tau"])
+    eng.set_scalars(float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]), lr, lr, lr, tau)
+    eng.set_batch(t["obs"], t["action"], t["discount"], t["next_obs"], t["next_goal"] if use_goal else None,
+                  t["next_goal"] if use_goal else None)
+    eng.set_z(t["z"])
+    eng.set_noise(t["noise_fb"], t["noise_actor"])
+    return eng, t, L
+
+
+@pytest.mark.parametrize("case", ["small", "goal", "wide"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_update_matches_reference_golden(case, graph):
+    g = load_golden(f"update_{case}")
+    fwd, bwd, actor = (golden_params(g, f"param0/{n}") for n in ("forward_net", "backward_net", "actor"))
+    d = dims_from_params(fwd, bwd, actor)
+    use_goal = case == "goal"
+    eng, t, L = _run_update_case(g, d, use_goal, graph)
+
+    # ---- update_fb up to the gradients (fb_ddpg.py:303-383) ----
+    eng.run(L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD | L.PHASE_METRICS, graph=graph)
+    torch.cuda.synchronize()
+    assert rel(eng.view("z"), t["z"]) < 1e-6
+    ora = O.fb_loss_and_grads(fwd, bwd, golden_params(g, "param0/forward_target_net"), golden_params(g, "param0/backward_target_net"),
+                              actor, t["obs"], t["action"], t["discount"], t["next_obs"], t["next_goal"], t["z"], t["noise_fb"],
+                              float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]), float(g["cfg/ortho_coef"]), d.z_dim)
+    for name in ("next_action", "tF1", "tF2", "tB", "F1", "F2", "B", "dF1", "dF2", "dB"):
+        assert rel(eng.view(name), ora[name]) < REL_TOL, name
+    m = eng.read_metrics()
+    for k, v in subtree(g, "metric_fb").items():
+        if k == "fb_opt_lr":
+            continue
+        assert m[k] == pytest.approx(float(v), rel=REL_TOL, abs=1e-5), k
+    for net, key in ((L.NET_FORWARD, "forward_net"), (L.NET_BACKWARD, "backward_net")):
+        got = read_tensors(eng, net, "grad")
+        for name, ref in subtree(g, f"grad_fb/{key}").items():
+            assert rel(got[name], ref) < REL_TOL, (key, name, rel(got[name], ref))
+
+    # ---- fb_opt.step (Adam step 1) + both soft updates ----
+    eng.run(L.PHASE_FB_ADAM, graph=graph)
+    torch.cuda.synchronize()
+    for net, key in ((L.NET_FORWARD, "forward_net"), (L.NET_BACKWARD, "backward_net")):
+        got = read_tensors(eng, net, "param")
+        for name, ref in subtree(g, f"param1/{key}").items():
+            assert np.abs(got[name].numpy() - ref).max() < 2e-5, (key, name)   # |dp| = lr = 1e-4 on step 1
+        got = read_tensors(eng, net, "target")
+        for name, ref in subtree(g, f"param1/{key.replace('_net', '_target_net')}").items():
+            assert np.abs(got[name].numpy() - ref).max() < 1e-5, (key, name)
+        assert float(eng.tensors(net, "grad")[next(iter(got))].abs().max()) == 0.0   # grads cleared for the next step
+
+    # ---- update_actor with the just-updated forward_net (fb_ddpg.py:389-410) ----
+    # the oracle is evaluated on the engine's own post-Adam forward_net so that Adam's sign(g) amplification of
+    # ulp-level gradient noise does not leak into this comparison
+    fwd1 = read_tensors(eng, L.NET_FORWARD, "param")
+    eng.run(L.PHASE_ACTOR_FWD | L.PHASE_ACTOR_BWD | L.PHASE_METRICS, graph=graph)
+    torch.cuda.synchronize()
+    ora_a = O.actor_loss_and_grads(actor, fwd1, t["obs"], t["z"], t["noise_actor"], float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]))
+    assert rel(eng.view("action_new"), ora_a["action"]) < REL_TOL
+    assert rel(eng.view("mu"), ora_a["mu"]) < REL_TOL
+    m = eng.read_metrics()
+    assert m["actor_loss"] == pytest.approx(float(ora_a["actor_loss"]), rel=REL_TOL, abs=1e-5)
+    assert m["q"] == pytest.approx(float(ora_a["q"]), rel=REL_TOL, abs=1e-5)
+    assert m["actor_logprob"] == pytest.approx(float(ora_a["actor_logprob"]), rel=REL_TOL, abs=1e-5)
+    ref_m = subtree(g, "metric_actor")   # the reference's own numbers (its forward_net differs by Adam noise only)
+    assert m["actor_loss"] == pytest.approx(float(ref_m["actor_loss"]), rel=5e-3, abs=1e-4)
+    got = read_tensors(eng, L.NET_ACTOR, "grad")
+    for name, ref in ora_a["grads_actor"].items():
+        assert rel(got[name], ref) < REL_TOL, (name, rel(got[name], ref))
+    for name, ref in subtree(g, "grad_actor/actor").items():
+        assert rel(got[name], ref) < 2e-2, (name, rel(got[name], ref))
+    eng.run(L.PHASE_ACTOR_ADAM, graph=graph)
+    torch.cuda.synchronize()
+    got = read_tensors(eng, L.NET_ACTOR, "param")
+    for name, ref in subtree(g, "param1/actor").items():
+        assert np.abs(got[name].numpy() - ref).max() < 2.1e-4, name   # a sign flip of a ~0 gradient moves p by 2 lr
+    assert eng.get_adam_steps() == (1, 1)
+    eng.close()
+
+
+def test_full_width_step_against_oracle():
+    """Default widths of the reference config (hidden 1024, feature 512, backward hidden 526, z 50, obs 24, act 6) at
+    batch 256 (BASELINE.json configs[0]); oracle on CPU from the same seeded parameters and inputs."""
+    L = _L()
+    d = O.Dims()
+    B = 256
+    gen = torch.Generator().manual_seed(11)
+    actor = O.init_params(O.actor_spec(d), gen)
+    fwd = O.init_params(O.forward_map_spec(d), gen)
+    bwd = O.init_params(O.backward_map_spec(d), gen)
+    fwd_t = {k: v + 0.02 * torch.randn(v.shape, generator=gen) for k, v in fwd.items()}
+    bwd_t = {k: v + 0.02 * torch.randn(v.shape, generator=gen) for k, v in bwd.items()}
+    obs, next_obs = torch.randn(B, d.obs_dim, generator=gen), torch.randn(B, d.obs_dim, generator=gen)
+    action = torch.rand(B, d.action_dim, generator=gen) * 2 - 1
+    discount = torch.full((B, 1), 0.98)
+    z_rand = O.sample_z(B, d.z_dim, gen)
+    noise_fb, noise_actor = torch.randn(B, d.action_dim, generator=gen), torch.randn(B, d.action_dim, generator=gen)
+    perm = torch.randperm(B, generator=gen)
+    mix_mask = (torch.rand(B, generator=gen) < 0.5)
+    # oracle z mixing (fb_ddpg.py:460-485)
+    z = z_rand.clone()
+    idx = torch.where(mix_mask)[0]
+    with torch.no_grad():
+        z[idx] = O.l2_project(O.backward_map(bwd, obs[perm][idx], d.z_dim), d.z_dim)
+
+    eng = make_engine(d, B)
+    load_params(eng, fwd=fwd, bwd=bwd, actor=actor, fwd_tgt=fwd_t, bwd_tgt=bwd_t)
+    eng.set_scalars(0.2, 0.3, 1e-4, 1e-4, 1e-4, 0.01)
+    eng.set_indices(perm=perm, mix_mask=mix_mask.int())
+    eng.set_batch(obs, action, discount, next_obs)
+    eng.set_z(z_rand)
+    eng.set_noise(noise_fb, noise_actor)
+    eng.run(L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD | L.PHASE_METRICS)
+    torch.cuda.synchronize()
+    assert rel(eng.view("z"), z) < 1e-5
+    ora = O.fb_loss_and_grads(fwd, bwd, fwd_t, bwd_t, actor, obs, action, discount, next_obs, next_obs, z, noise_fb, 0.2, 0.3,
+                              1.0, d.z_dim)
+    m = eng.read_metrics()
+    for k, v in ora["metrics"].items():
+        assert m[k] == pytest.approx(v, rel=REL_TOL, abs=1e-5), k
+    worst = 0.0
+    for net, key in ((L.NET_FORWARD, "grads_forward"), (L.NET_BACKWARD, "grads_backward")):
+        got = read_tensors(eng, net, "grad")
+        for name, ref in ora[key].items():
+            worst = max(worst, rel(got[name], ref))
+            assert rel(got[name], ref) < REL_TOL, (key, name)
+    print("worst fb grad rel err", worst)
+    eng.run(L.PHASE_FB_ADAM)
+    fwd1 = read_tensors(eng, L.NET_FORWARD, "param")
+    eng.run(L.PHASE_ACTOR_FWD | L.PHASE_ACTOR_BWD | L.PHASE_METRICS)
+    torch.cuda.synchronize()
+    ora_a = O.actor_loss_and_grads(actor, fwd1, obs, z, noise_actor, 0.2, 0.3)
+    m = eng.read_metrics()
+    assert m["actor_loss"] == pytest.approx(float(ora_a["actor_loss"]), rel=REL_TOL, abs=1e-5)
+    got = read_tensors(eng, L.NET_ACTOR, "grad")
+    for name, ref in ora_a["grads_actor"].items():
+        assert rel(got[name], ref) < REL_TOL, (name, rel(got[name], ref))
+    eng.close()
