@@ -38,6 +38,7 @@ PHASE_ALL = (1 << 10) - 1
 METRIC_KEYS = ("target_M", "M1", "F1", "B", "B_norm", "z_norm", "fb_loss", "fb_diag", "fb_offdiag", "orth_loss",
                "orth_loss_diag", "orth_loss_offdiag", "orth_linf", "orth_l2", "actor_loss", "q", "actor_logprob")
 METRIC_COUNT = 32
+OP_KINDS = ("gemm", "layernorm", "elementwise", "colsum", "adam", "gather", "loss", "memset", "contract")
 
 
 class fb_config(C.Structure):
@@ -90,6 +91,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "fb_set_noise": (_i, [_vp, _vp, _vp, _vp]),
     "fb_run": (_i, [_vp, _u32, _i, _vp]),
     "fb_launch_count": (_i, [_vp, _u32]),
+    "fb_profile_ops": (_i, [_vp, _u32, _i, _vp, C.POINTER(C.c_float), _pi32, C.POINTER(C.c_double), C.POINTER(C.c_double), _i]),
     "fb_metrics_ptr": (_vp, [_vp]),
     "fb_set_adam_steps": (_i, [_vp, C.c_int64, C.c_int64, _vp]),
     "fb_get_adam_steps": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp]),

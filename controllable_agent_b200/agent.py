@@ -1,0 +1,494 @@
+"""FBDDPGAgent — the reference's agent API (url_benchmark/agent/fb_ddpg.py:37-520) over the B200 step engine.
+
+Same Hydra config surface (`agent=fb_ddpg`, every field of FBDDPGAgentConfig with the same default), same
+constructor (`FBDDPGAgent(**kwargs)`), same public methods and attributes the workspaces touch (SURVEY.md
+section 8b).  `update()` is one CUDA-graph launch of libfb_b200's step; the nn.Modules hanging off the agent
+(`actor`, `forward_net`, ...) are parameter *views* on the flat segments that step trains in place and are only
+evaluated by the per-environment-step helpers (`act`, `get_goal_meta`, `infer_meta*`, `compute_z_correl`).
+"""
+from __future__ import annotations
+
+import copy
+import dataclasses
+import logging
+import math
+import os
+import typing as tp
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.distributions.utils import _standard_normal
+
+from . import _lib as L
+from . import modules as M
+from .engine import EngineConfig, FBStepEngine
+from .replay import ReplayBuffer
+
+logger = logging.getLogger(__name__)
+MetaDict = tp.Mapping[str, np.ndarray]
+
+try:  # the Hydra surface, when hydra / omegaconf are installed (they are not in the build image)
+    import omegaconf
+    MISSING: tp.Any = omegaconf.MISSING
+    II = omegaconf.II
+except ImportError:  # pragma: no cover
+    MISSING = "???"
+
+    def II(key: str) -> tp.Any:  # noqa: N802
+        return "${" + key + "}"
+
+# goal-space widths (url_benchmark/goals.py:44-112 evaluated once; get_goal_space_dim builds a MuJoCo env, goals.py:218-221)
+GOAL_SPACE_DIMS = {"simplified_walker": 3, "walker_pos_speed": 4, "walker_pos_speed_z": 6, "simplified_quadruped": 2,
+                   "quad_pos_speed": 7, "simplified_jaco": 3, "simplified_point_mass_maze": 2}
+
+
+def get_goal_space_dim(name: str) -> int:
+    if name in GOAL_SPACE_DIMS:
+        return GOAL_SPACE_DIMS[name]
+    from url_benchmark import goals as _goals  # needs dm_control
+    return int(_goals.get_goal_space_dim(name))
+
+
+@dataclasses.dataclass
+class FBDDPGAgentConfig:
+    # @package agent  — field for field the reference's dataclass (fb_ddpg.py:37-82)
+    _target_: str = "controllable_agent_b200.agent.FBDDPGAgent"
+    name: str = "fb_ddpg"
+    obs_type: str = MISSING
+    obs_shape: tp.Tuple[int, ...] = MISSING
+    action_shape: tp.Tuple[int, ...] = MISSING
+    device: str = II("device")
+    lr: float = 1e-4
+    lr_coef: float = 1
+    fb_target_tau: float = 0.01
+    update_every_steps: int = 2
+    use_tb: bool = II("use_tb")
+    use_wandb: bool = II("use_wandb")
+    use_hiplog: bool = II("use_hiplog")
+    num_expl_steps: int = MISSING
+    num_inference_steps: int = 5120
+    hidden_dim: int = 1024
+    backward_hidden_dim: int = 526
+    feature_dim: int = 512
+    z_dim: int = 50
+    stddev_schedule: str = "0.2"
+    stddev_clip: float = 0.3
+    update_z_every_step: int = 300
+    update_z_proba: float = 1.0
+    nstep: int = 1
+    batch_size: int = 1024
+    init_fb: bool = True
+    update_encoder: bool = II("update_encoder")
+    goal_space: tp.Optional[str] = II("goal_space")
+    ortho_coef: float = 1.0
+    log_std_bounds: tp.Tuple[float, float] = (-5, 2)
+    temp: float = 1
+    boltzmann: bool = False
+    debug: bool = False
+    future_ratio: float = 0.0
+    mix_ratio: float = 0.5
+    rand_weight: bool = False
+    preprocess: bool = True
+    norm_z: bool = True
+    q_loss: bool = False
+    q_loss_coef: float = 0.01
+    additional_metric: bool = False
+    add_trunk: bool = False
+    # --- additions of this implementation (defaults keep the reference's semantics) ---
+    rng_mode: str = "device"     # "device": Philox draws inside the step graph; "reference": numpy/torch draws in the
+    #                              reference's order (Appendix B of SURVEY.md), uploaded per step
+    use_cuda_graph: bool = True
+
+
+def register_hydra() -> None:
+    """cs.store(group="agent", name="fb_ddpg", node=FBDDPGAgentConfig) as fb_ddpg.py:85-86 does (needs hydra)."""
+    from hydra.core.config_store import ConfigStore
+    ConfigStore.instance().store(group="agent", name="fb_ddpg", node=FBDDPGAgentConfig)
+
+
+_UNSUPPORTED = {"boltzmann": False, "debug": False, "q_loss": False, "rand_weight": False, "preprocess": True, "add_trunk": False,
+                "norm_z": True}
+
+
+class FBDDPGAgent:
+
+    def __init__(self, **kwargs: tp.Any) -> None:
+        cfg = FBDDPGAgentConfig(**kwargs)
+        self.cfg = cfg
+        assert len(cfg.action_shape) == 1
+        self.action_dim = cfg.action_shape[0]
+        self.solved_meta: tp.Any = None
+        if cfg.obs_type == "pixels":
+            raise NotImplementedError("controllable_agent_b200 implements the states-only FB-DDPG path (obs_type=pixels "
+                                      "needs the DDPG conv encoder, out of scope)")
+        for key, ok in _UNSUPPORTED.items():
+            if getattr(cfg, key) != ok:
+                raise NotImplementedError(f"agent.{key}={getattr(cfg, key)} is a non-default branch of fb_ddpg.py the CUDA step "
+                                          f"does not implement (supported: {key}={ok})")
+        if cfg.future_ratio > 0:
+            raise NotImplementedError("agent.future_ratio > 0 (hindsight z, fb_ddpg.py:488-491) is not implemented")
+        device = torch.device(cfg.device)
+        if device.type != "cuda":
+            raise RuntimeError(f"controllable_agent_b200.FBDDPGAgent needs device=cuda (got {cfg.device!r}); there is no "
+                               "CPU fallback — use the reference agent on CPU")
+        self.aug: nn.Module = nn.Identity()
+        self.encoder: nn.Module = nn.Identity()
+        self.obs_dim = cfg.obs_shape[0]
+        if cfg.feature_dim < self.obs_dim:
+            logger.warning(f"feature_dim {cfg.feature_dim} should not be smaller that obs_dim {self.obs_dim}")
+        goal_dim = self.obs_dim
+        if cfg.goal_space is not None:
+            goal_dim = get_goal_space_dim(cfg.goal_space)
+        if cfg.z_dim < goal_dim:
+            logger.warning(f"z_dim {cfg.z_dim} should not be smaller that goal_dim {goal_dim}")
+        self.goal_dim = goal_dim
+
+        # data-parallel layout: cfg.batch_size is the GLOBAL batch; each rank steps batch_size / world rows
+        self.world, self.rank = 1, 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world, self.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        if cfg.batch_size % self.world:
+            raise ValueError(f"batch_size {cfg.batch_size} must be divisible by the world size {self.world}")
+        local = cfg.batch_size // self.world
+
+        seed = int(torch.initial_seed() % (2 ** 63)) + 7919 * self.rank
+        self.engine = FBStepEngine(EngineConfig(
+            batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
+            hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
+            use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
+            mix_ratio=cfg.mix_ratio, seed=seed, global_batch=cfg.batch_size, row_offset=self.rank * local), device)
+
+        # networks: constructed on the CPU in the reference's order (Actor, ForwardMap, BackwardMap, BackwardMap target,
+        # ForwardMap target — fb_ddpg.py:117-139) so that the torch CPU generator is consumed identically, then moved
+        # onto the flat device segments
+        e = self.engine
+        self.actor = M.Actor(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim)
+        self.forward_net = M.ForwardMap(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim)
+        self.backward_net = M.BackwardMap(goal_dim, cfg.z_dim, cfg.backward_hidden_dim, norm_z=cfg.norm_z)
+        self.backward_target_net = M.BackwardMap(goal_dim, cfg.z_dim, cfg.backward_hidden_dim, norm_z=cfg.norm_z)
+        self.forward_target_net = M.ForwardMap(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim)
+        M.adopt_flat(self.actor, e.tensors(L.NET_ACTOR, "param"))
+        M.adopt_flat(self.forward_net, e.tensors(L.NET_FORWARD, "param"))
+        M.adopt_flat(self.backward_net, e.tensors(L.NET_BACKWARD, "param"))
+        M.adopt_flat(self.backward_target_net, e.tensors(L.NET_BACKWARD, "target"))
+        M.adopt_flat(self.forward_target_net, e.tensors(L.NET_FORWARD, "target"))
+        e.target_fb.copy_(e.param_fb)   # load_state_dict of the online nets into the targets (fb_ddpg.py:141-142)
+        if self.world > 1:  # replicas start from rank 0's parameters
+            for flat in (e.param_fb, e.target_fb, e.param_actor):
+                torch.distributed.broadcast(flat, src=0)
+
+        # real torch optimizers (init_from / checkpoints look for them in __dict__, fb_ddpg.py:173-175); their state
+        # tensors are views of the flat Adam moments the CUDA step updates
+        self.encoder_opt: tp.Optional[torch.optim.Adam] = None
+        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=cfg.lr)
+        self.fb_opt = torch.optim.Adam([{"params": self.forward_net.parameters()},
+                                        {"params": self.backward_net.parameters(), "lr": cfg.lr_coef * cfg.lr}], lr=cfg.lr)
+        self._link_optimizer_state()
+        self.train()
+        self.forward_target_net.train()
+        self.backward_target_net.train()
+        self.actor_success: tp.List[float] = []
+        self._replay_key: tp.Any = None
+        self.last_update_launches = 0
+        # where rng_mode="reference" makes its torch draws (z, action noise): the agent's device, like the reference run
+        # with device=cuda; tests point it at "cpu" to replay the CPU-generated golden trajectories
+        self.draw_device: tp.Union[str, torch.device] = device
+
+    # ------------------------------------------------------------------------------------------------
+    def _link_optimizer_state(self) -> None:
+        e = self.engine
+        fb_step, actor_step = e.get_adam_steps()
+        for opt, nets, step in ((self.actor_opt, [(self.actor, L.NET_ACTOR)], actor_step),
+                                (self.fb_opt, [(self.forward_net, L.NET_FORWARD), (self.backward_net, L.NET_BACKWARD)], fb_step)):
+            for net, net_id in nets:
+                m, v = e.tensors(net_id, "m"), e.tensors(net_id, "v")
+                for (name, p) in net.named_parameters():
+                    opt.state[p] = {"step": torch.tensor(float(step)), "exp_avg": m[name], "exp_avg_sq": v[name]}
+
+    def _sync_optimizer_steps(self) -> None:
+        fb_step, actor_step = self.engine.get_adam_steps()
+        for opt, step in ((self.actor_opt, actor_step), (self.fb_opt, fb_step)):
+            for st in opt.state.values():
+                st["step"] = torch.tensor(float(step))
+
+    def train(self, training: bool = True) -> None:
+        self.training = training
+        for net in [self.encoder, self.actor, self.forward_net, self.backward_net]:
+            net.train(training)
+
+    def init_from(self, other: tp.Any) -> None:
+        """fb_ddpg.py:166-175: copy parameters net by net, then the optimizers' state."""
+        names = ["encoder", "actor"]
+        if self.cfg.init_fb:
+            names += ["forward_net", "backward_net", "backward_target_net", "forward_target_net"]
+        for name in names:
+            M.hard_update_params(getattr(other, name), getattr(self, name))
+        if isinstance(other, FBDDPGAgent):
+            other._sync_optimizer_steps()
+        steps = {}
+        for key in ("actor_opt", "fb_opt"):
+            src = getattr(other, key).state_dict()
+            mine = getattr(self, key)
+            step = 0.0
+            for group_s, group_m in zip(src["param_groups"], mine.param_groups):
+                group_m["lr"] = group_s["lr"]
+                for idx_s, p in zip(group_s["params"], group_m["params"]):
+                    st = src["state"].get(idx_s)
+                    if st is None:
+                        continue
+                    mine.state[p]["exp_avg"].copy_(st["exp_avg"])
+                    mine.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
+                    step = float(st["step"])
+            steps[key] = int(step)
+        self.engine.set_adam_steps(steps["fb_opt"], steps["actor_opt"])
+        self._sync_optimizer_steps()
+
+    # -- pickling: pretrain.py:437-449 saves the whole agent object ---------------------------------
+    def __getstate__(self) -> tp.Dict[str, tp.Any]:
+        e = self.engine
+        fb_step, actor_step = e.get_adam_steps()
+        flats = {k: getattr(e, k).detach().cpu() for k in ("param_fb", "m_fb", "v_fb", "target_fb", "param_actor", "m_actor", "v_actor")}
+        return {"cfg": dataclasses.asdict(self.cfg), "flats": flats, "adam_steps": (fb_step, actor_step),
+                "solved_meta": self.solved_meta, "training": self.training,
+                "lrs": ([g["lr"] for g in self.fb_opt.param_groups], [g["lr"] for g in self.actor_opt.param_groups])}
+
+    def __setstate__(self, state: tp.Dict[str, tp.Any]) -> None:
+        cpu_rng = torch.get_rng_state()
+        self.__init__(**state["cfg"])  # type: ignore[misc]
+        torch.set_rng_state(cpu_rng)
+        for k, v in state["flats"].items():
+            getattr(self.engine, k).copy_(v)
+        self.engine.set_adam_steps(*state["adam_steps"])
+        self._sync_optimizer_steps()
+        for g, lr in zip(self.fb_opt.param_groups, state["lrs"][0]):
+            g["lr"] = lr
+        for g, lr in zip(self.actor_opt.param_groups, state["lrs"][1]):
+            g["lr"] = lr
+        self.solved_meta = state["solved_meta"]
+        self.train(state["training"])
+
+    # -- inference helpers (per environment step) --------------------------------------
+    def get_goal_meta(self, goal_array: np.ndarray) -> MetaDict:
+        desired_goal = torch.tensor(goal_array).unsqueeze(0).to(self.cfg.device)
+        with torch.no_grad():
+            z = self.backward_net(desired_goal)
+        if self.cfg.norm_z:
+            z = math.sqrt(self.cfg.z_dim) * F.normalize(z, dim=1)
+        meta = OrderedDict()
+        meta["z"] = z.squeeze(0).cpu().numpy()
+        return meta
+
+    def infer_meta(self, replay_loader: tp.Any) -> MetaDict:
+        obs_list, reward_list = [], []
+        batch_size = 0
+        while batch_size < self.cfg.num_inference_steps:
+            batch = replay_loader.sample(self.cfg.batch_size)
+            batch = batch.to(self.cfg.device)
+            obs_list.append(batch.next_goal if self.cfg.goal_space is not None else batch.next_obs)
+            reward_list.append(batch.reward)
+            batch_size += batch.next_obs.size(0)
+        obs, reward = torch.cat(obs_list, 0), torch.cat(reward_list, 0)
+        obs, reward = obs[:self.cfg.num_inference_steps], reward[:self.cfg.num_inference_steps]
+        return self.infer_meta_from_obs_and_rewards(obs, reward)
+
+    def infer_meta_from_obs_and_rewards(self, obs: torch.Tensor, reward: torch.Tensor) -> MetaDict:
+        with torch.no_grad():
+            b = self.backward_net(obs)
+        z = torch.matmul(reward.T, b) / reward.shape[0]
+        if self.cfg.norm_z:
+            z = math.sqrt(self.cfg.z_dim) * F.normalize(z, dim=1)
+        meta = OrderedDict()
+        meta["z"] = z.squeeze().cpu().numpy()
+        return meta
+
+    def sample_z(self, size: int, device: tp.Union[str, torch.device] = "cpu") -> torch.Tensor:
+        gaussian_rdv = torch.randn((size, self.cfg.z_dim), dtype=torch.float32, device=device)
+        gaussian_rdv = F.normalize(gaussian_rdv, dim=1)
+        return math.sqrt(self.cfg.z_dim) * gaussian_rdv
+
+    def init_meta(self) -> MetaDict:
+        if self.solved_meta is not None:
+            return self.solved_meta
+        meta = OrderedDict()
+        meta["z"] = self.sample_z(1).squeeze().numpy()
+        return meta
+
+    def update_meta(self, meta: MetaDict, global_step: int, time_step: tp.Any, finetune: bool = False,
+                    replay_loader: tp.Optional[tp.Any] = None) -> MetaDict:
+        if global_step % self.cfg.update_z_every_step == 0 and np.random.rand() < self.cfg.update_z_proba:
+            return self.init_meta()
+        return meta
+
+    def act(self, obs: tp.Any, meta: MetaDict, step: int, eval_mode: bool) -> tp.Any:
+        obs = torch.as_tensor(obs, device=self.cfg.device, dtype=torch.float32).unsqueeze(0)
+        h = self.encoder(obs)
+        z = torch.as_tensor(meta["z"], device=self.cfg.device).unsqueeze(0)
+        stddev = M.schedule(self.cfg.stddev_schedule, step)
+        dist = self.actor(h, z, stddev)
+        if eval_mode:
+            action = dist.mean
+            if self.cfg.additional_metric:
+                F_mean_s = self.forward_net(obs, z, action)
+                F_rand_s = self.forward_net(obs, z, torch.zeros_like(action).uniform_(-1.0, 1.0))
+                Qs = [torch.min(*(torch.einsum("sd, sd -> s", Fk, z) for Fk in Fs)) for Fs in [F_mean_s, F_rand_s]]
+                self.actor_success = (Qs[0] > Qs[1]).cpu().numpy().tolist()
+        else:
+            action = dist.sample()
+            if step < self.cfg.num_expl_steps:
+                action.uniform_(-1.0, 1.0)
+        return action.detach().cpu().numpy()[0]
+
+    def compute_z_correl(self, time_step: tp.Any, meta: MetaDict) -> float:
+        goal = time_step.goal if self.cfg.goal_space is not None else time_step.observation
+        with torch.no_grad():
+            zs = [torch.Tensor(x).unsqueeze(0).float().to(self.cfg.device) for x in [goal, meta["z"]]]
+            zs[0] = self.backward_net(zs[0])
+            zs = [F.normalize(z, 1) for z in zs]
+            return torch.matmul(zs[0], zs[1].T).item()
+
+    # -- the gradient step ---------------------------------------------------------------------------
+    def _metrics_enabled(self) -> bool:
+        c = self.cfg
+        return bool(c.use_tb) or bool(c.use_wandb) or bool(c.use_hiplog)
+
+    def _set_scalars(self, step: int, replay_discount: float = 1.0, replay_future: float = 1.0) -> None:
+        c = self.cfg
+        self.engine.set_scalars(M.schedule(c.stddev_schedule, step), c.stddev_clip, self.fb_opt.param_groups[0]["lr"],
+                                self.fb_opt.param_groups[1]["lr"], self.actor_opt.param_groups[0]["lr"], c.fb_target_tau,
+                                replay_discount, replay_future, 1.0)
+
+    def _run(self, mask: int) -> None:
+        """Enqueue the phases of `mask`; with >1 rank, split at the two exchange points (DESIGN.md "Multi-GPU")."""
+        e, g = self.engine, bool(self.cfg.use_cuda_graph)
+        if self.world == 1:
+            e.run(mask, graph=g)
+            self.last_update_launches = e.launch_count(mask)
+            return
+        import torch.distributed as dist
+        seg1 = mask & (L.PHASE_SAMPLE | L.PHASE_MIX | L.PHASE_FB_FWD)
+        seg2 = mask & (L.PHASE_FB_LOSS | L.PHASE_FB_BWD)
+        seg3 = mask & (L.PHASE_FB_ADAM | L.PHASE_ACTOR_FWD | L.PHASE_ACTOR_BWD)
+        seg4 = mask & (L.PHASE_ACTOR_ADAM | L.PHASE_METRICS)
+        local, glob = e.gather_block()
+        if seg1:
+            e.run(seg1, graph=g)
+        if seg2:
+            dist.all_gather_into_tensor(glob, local)   # [F1|F2|tF1|tF2|B|tB|discount] rows of every rank
+            e.run(seg2, graph=g)
+            dist.all_reduce(e.grad_fb)
+        if seg3:
+            e.run(seg3, graph=g)
+            dist.all_reduce(e.grad_actor)
+        if seg4:
+            e.run(seg4, graph=g)
+        self.last_update_launches = e.launch_count(mask)
+
+    def update_fb(self, obs: torch.Tensor, action: torch.Tensor, discount: torch.Tensor, next_obs: torch.Tensor,
+                  next_goal: torch.Tensor, z: torch.Tensor, step: int) -> tp.Dict[str, float]:
+        """fb_ddpg.py:291-387 on explicit tensors: targets, F/B forward, loss, backward, fb_opt.step().  `z` is used as
+        given (mixing belongs to update()); like the reference this does NOT move the target networks."""
+        e = self.engine
+        if self.world > 1:
+            raise NotImplementedError("update_fb on explicit tensors is single-GPU; use update()")
+        use_goal = self.cfg.goal_space is not None
+        e.set_batch(obs, action, discount, next_obs, next_goal if use_goal else None, next_goal if use_goal else None)
+        e.set_z(z)
+        e.set_indices(mix_mask=np.zeros(e.cfg.batch, np.int32))
+        shape = (e.cfg.batch, self.action_dim)
+        # update_fb's and update_actor's N(0,1) draws (utils.py:178), consumed from the device generator in that order
+        e.set_noise(_standard_normal(shape, dtype=torch.float32, device=e.device),
+                    _standard_normal(shape, dtype=torch.float32, device=e.device))
+        tau, self.cfg.fb_target_tau = self.cfg.fb_target_tau, 0.0   # Adam only: soft updates are update()'s job
+        try:
+            self._set_scalars(step)
+        finally:
+            self.cfg.fb_target_tau = tau
+        mask = L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD | L.PHASE_FB_ADAM
+        metrics: tp.Dict[str, float] = {}
+        if self._metrics_enabled():
+            self._run(mask | L.PHASE_METRICS)
+            m = e.read_metrics()
+            metrics = {k: m[k] for k in L.METRIC_KEYS[:14]}
+            metrics["fb_opt_lr"] = self.fb_opt.param_groups[0]["lr"]
+        else:
+            self._run(mask)
+        return metrics
+
+    def update_actor(self, obs: torch.Tensor, z: torch.Tensor, step: int) -> tp.Dict[str, float]:
+        """fb_ddpg.py:389-421.  Must follow update_fb() on the same (obs, z): the actor forward on `obs` was batched
+        with the one on `next_obs` there, and is reused here (the actor has not changed in between)."""
+        e = self.engine
+        self._run(L.PHASE_ACTOR_FWD | L.PHASE_ACTOR_BWD | L.PHASE_ACTOR_ADAM)
+        if self.cfg.use_tb or self.cfg.use_wandb:
+            e.run(L.PHASE_METRICS, graph=False)
+            m = e.read_metrics()
+            return {k: m[k] for k in L.METRIC_KEYS[14:]}
+        return {}
+
+    def update(self, replay_loader: tp.Any, step: int) -> tp.Dict[str, float]:
+        """fb_ddpg.py:427-520: sample, z draw + mixing, update_fb, update_actor, target soft updates."""
+        metrics: tp.Dict[str, float] = {}
+        c, e = self.cfg, self.engine
+        if step % c.update_every_steps != 0:
+            return metrics
+        B = e.cfg.batch
+        fused = isinstance(replay_loader, ReplayBuffer)
+        if fused:
+            self._set_scalars(step, float(replay_loader._discount), float(replay_loader._future))
+            key = (id(replay_loader), replay_loader._version, len(replay_loader))
+            if key != self._replay_key:
+                e.bind_replay(replay_loader.view())
+                self._replay_key = key
+        else:
+            self._set_scalars(step)
+        mask = L.PHASE_ALL & ~L.PHASE_METRICS
+        if fused and c.rng_mode == "device":
+            pass  # every draw happens inside FB_PHASE_SAMPLE
+        else:
+            # the reference's RNG streams in the reference's order
+            if fused:
+                ep_idx, step_idx, future_idx = replay_loader.draw_indices(B)
+            else:
+                batch = replay_loader.sample(B).to(c.device)
+                mask &= ~L.PHASE_SAMPLE
+            z = self.sample_z(B, device=self.draw_device)
+            perm = torch.randperm(B)
+            mix = (np.random.uniform(size=B) < c.mix_ratio).astype(np.int32) if c.mix_ratio > 0 else np.zeros(B, np.int32)
+            noise_fb = _standard_normal((B, self.action_dim), dtype=torch.float32, device=self.draw_device)
+            noise_actor = _standard_normal((B, self.action_dim), dtype=torch.float32, device=self.draw_device)
+            if fused:
+                e.set_indices(ep_idx, step_idx, future_idx, perm, mix)
+            else:
+                e.set_indices(perm=perm, mix_mask=mix)
+                use_goal = c.goal_space is not None
+                if use_goal:
+                    assert batch.goal is not None and batch.next_goal is not None
+                e.set_batch(batch.obs, batch.action, batch.discount, batch.next_obs, batch.goal if use_goal else None,
+                            batch.next_goal if use_goal else None)
+            e.set_z(z)
+            e.set_noise(noise_fb, noise_actor)
+        if self._metrics_enabled():
+            self._run(mask | L.PHASE_METRICS)
+            m = e.read_metrics()
+            if self.world > 1:
+                m = self._reduce_metrics(m)
+            metrics.update({k: m[k] for k in L.METRIC_KEYS[:14]})
+            metrics["fb_opt_lr"] = self.fb_opt.param_groups[0]["lr"]
+            if c.use_tb or c.use_wandb:   # the actor block logs under a narrower condition (fb_ddpg.py:413)
+                metrics.update({k: m[k] for k in L.METRIC_KEYS[14:]})
+        else:
+            self._run(mask)
+        return metrics
+
+    def _reduce_metrics(self, m: tp.Dict[str, float]) -> tp.Dict[str, float]:
+        """Per-rank metric blocks -> global values: loss-type entries are partial sums over the rank's rows, the
+        others are per-rank means (or replicated)."""
+        import torch.distributed as dist
+        mean_keys = {"target_M", "M1", "F1", "B", "B_norm", "z_norm", "orth_linf", "orth_l2"}
+        t = torch.tensor([m[k] / self.world if k in mean_keys else m[k] for k in L.METRIC_KEYS], dtype=torch.float64,
+                         device=self.engine.device)
+        dist.all_reduce(t)
+        return {k: float(v) for k, v in zip(L.METRIC_KEYS, t.tolist())}

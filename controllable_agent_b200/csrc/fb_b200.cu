@@ -15,7 +15,9 @@ struct Builder {
   char* d_arena;
   int phase = 0;
   void set_phase(uint32_t bit) { phase = phase_index(bit); }
-  void push(Op op) { h->ops[phase].push_back(std::move(op)); }
+  void push(OpFn fn, int kind = FB_OPK_ELEMENTWISE, double flops = 0.0, double bytes = 0.0) {
+    h->ops[phase].push_back(Op{std::move(fn), kind, flops, bytes});
+  }
 
   void gemm(std::vector<GemmDesc> g) {
     if (g.empty()) return;
@@ -23,27 +25,32 @@ struct Builder {
     push([gl](cudaStream_t s) {
       k_gemm_grouped<<<gl.ctas, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(gl.d_descs, gl.nprob);
       return cudaGetLastError();
-    });
+    }, FB_OPK_GEMM, gl.flops, gl.bytes);
   }
   void ln_fwd(std::vector<LnDesc> v) {
     int rows = 0;
-    for (auto& d : v) { d.row_begin = rows; rows += d.rows; }
+    double bytes = 0.0;
+    for (auto& d : v) { d.row_begin = rows; rows += d.rows; bytes += 8.0 * d.rows * (double)d.D; }
     const LnDesc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
     push([dd, n, rows](cudaStream_t s) {
       k_ln_tanh_fwd<<<fb_ceil_div(rows, 8), 256, 0, s>>>(dd, n, rows);
       return cudaGetLastError();
-    });
+    }, FB_OPK_LAYERNORM, 0.0, bytes);
   }
   void ln_bwd(std::vector<LnBwdDesc> v) {
     int ctas = 0;
-    for (auto& d : v) { d.cta_begin = ctas; d.cta_count = fb_ceil_div(d.rows, FB_LN_BWD_ROWS_PER_CTA); ctas += d.cta_count; }
+    double bytes = 0.0;
+    for (auto& d : v) {
+      d.cta_begin = ctas; d.cta_count = fb_ceil_div(d.rows, FB_LN_BWD_ROWS_PER_CTA); ctas += d.cta_count;
+      bytes += 16.0 * d.rows * (double)d.D;
+    }
     const LnBwdDesc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
     push([dd, n, ctas](cudaStream_t s) {
       k_ln_tanh_bwd<<<ctas, 256, 0, s>>>(dd, n);
       return cudaGetLastError();
-    });
+    }, FB_OPK_LAYERNORM, 0.0, bytes);
   }
   void l2_fwd(std::vector<L2Desc> v) {
     int rows = 0;
@@ -57,7 +64,9 @@ struct Builder {
   }
   void colsum(std::vector<ColsumDesc> v) {
     int ctas = 0;
+    double bytes = 0.0;
     for (auto& d : v) {
+      bytes += 4.0 * d.rows * (double)d.N;
       d.cta_begin = ctas; d.ctas_n = fb_ceil_div(d.N, 32); d.ctas_r = fb_ceil_div(d.rows, FB_COLSUM_ROWS_PER_CTA);
       ctas += d.ctas_n * d.ctas_r;
     }
@@ -66,10 +75,10 @@ struct Builder {
     push([dd, n, ctas](cudaStream_t s) {
       k_colsum<<<ctas, 256, 0, s>>>(dd, n);
       return cudaGetLastError();
-    });
+    }, FB_OPK_COLSUM, 0.0, bytes);
   }
   void memset0(void* p, size_t bytes) {
-    push([p, bytes](cudaStream_t s) { return cudaMemsetAsync(p, 0, bytes, s); });
+    push([p, bytes](cudaStream_t s) { return cudaMemsetAsync(p, 0, bytes, s); }, FB_OPK_MEMSET, 0.0, (double)bytes);
   }
 };
 
@@ -294,7 +303,7 @@ static int build_plan(fb_handle* h) {
       k_gather_rows<<<fb_ceil_div(hh->cfg.batch, 8), 256, 0, s>>>(gp, hh->d_ep_idx, hh->d_step_idx, nullptr, hh->cfg.batch,
                                                                  &sc->replay_discount, 0.f, hh->packed.p);
       return cudaGetLastError();
-    });
+    }, FB_OPK_GATHER, 0.0, 2.0 * 4.0 * (double)B * (double)h->bl.pitch);
   }
 
   // =========================== FB_PHASE_MIX =====================================================
@@ -378,7 +387,7 @@ static int build_plan(fb_handle* h) {
       dim3 grid(fb_ceil_div(lp.nc, 1024) > 0 ? fb_ceil_div(lp.nc, 1024) : 1, lp.nr < 592 ? lp.nr : 592);
       k_fb_loss_elem<<<grid, 256, 0, s>>>(lp);
       return cudaGetLastError();
-    });
+    }, FB_OPK_LOSS, 0.0, 4.0 * 8.0 * (double)B * (double)n);
     LossElemTParams lt; memset(&lt, 0, sizeof(lt));
     lt.M1 = Mt1.p; lt.M2 = Mt2.p; lt.T1 = Tt1.p; lt.T2 = Tt2.p; lt.nr = B; lt.nc = n; lt.ld = Mt1.ld; lt.row0 = c.row_offset;
     lt.disc = bg.p + disc_col; lt.disc_stride = bg.ld; lt.inv_noff = inv_noff; lt.inv_n = inv_n;
@@ -386,7 +395,7 @@ static int build_plan(fb_handle* h) {
       dim3 grid(fb_ceil_div(lt.nc, 1024) > 0 ? fb_ceil_div(lt.nc, 1024) : 1, lt.nr < 592 ? lt.nr : 592);
       k_fb_loss_elem_t<<<grid, 256, 0, s>>>(lt);
       return cudaGetLastError();
-    });
+    }, FB_OPK_LOSS, 0.0, 4.0 * 6.0 * (double)B * (double)n);
     b.memset0(dblk.p, (size_t)dblk.rows * dblk.ld * sizeof(float));
     const float coef = -4.0f * c.ortho_coef * inv_n;
     b.push([dB, Bm, B, Z, coef](cudaStream_t s) {
@@ -444,7 +453,7 @@ static int build_plan(fb_handle* h) {
     b.push([=](cudaStream_t s) {
       k_adam<<<FB_SM_COUNT * 8, 256, 0, s>>>(p, g, m, v, t, n4, split4, sc, 0, b1, b2, eps);
       return cudaGetLastError();
-    });
+    }, FB_OPK_ADAM, 0.0, 4.0 * 4.0 * (double)n4 * 10.0);  // r(p,g,m,v,target) + w(p,g,m,v,target)
   }
 
   // =========================== FB_PHASE_ACTOR_FWD ===============================================
@@ -502,7 +511,7 @@ static int build_plan(fb_handle* h) {
     b.push([=](cudaStream_t s) {
       k_adam<<<FB_SM_COUNT * 8, 256, 0, s>>>(p, g, m, v, nullptr, n4, n4, sc, 1, b1, b2, eps);
       return cudaGetLastError();
-    });
+    }, FB_OPK_ADAM, 0.0, 4.0 * 4.0 * (double)n4 * 8.0);
   }
 
   // =========================== FB_PHASE_METRICS =================================================
@@ -623,6 +632,7 @@ int fb_create(const fb_config* cfg, fb_handle** out) {
 void fb_destroy(fb_handle* h) {
   if (!h) return;
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   delete h;
 }
 
@@ -773,10 +783,14 @@ int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream) {
   if (!use_graph) return (int)run_eager(h, phase_mask, s);
   auto it = h->graphs.find(phase_mask);
   if (it == h->graphs.end()) {
+    // capture on a private stream (the caller's may be the legacy default stream, which cannot capture);
+    // nothing executes during capture, the instantiated graph is launched on the caller's stream
     cudaGraph_t graph = nullptr;
-    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    cudaError_t e = run_eager(h, phase_mask, s);
-    cudaError_t e2 = cudaStreamEndCapture(s, &graph);
+    if (!h->capture_stream) CK(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = h->capture_stream;
+    CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = run_eager(h, phase_mask, cs);
+    cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
     if (e != cudaSuccess || e2 != cudaSuccess) {
       if (graph) cudaGraphDestroy(graph);
       return (int)(e != cudaSuccess ? e : e2);
@@ -796,6 +810,43 @@ int fb_launch_count(fb_handle* h, uint32_t phase_mask) {
   int n = 0;
   for (int ph = 0; ph < FB_NUM_PHASES; ++ph)
     if (phase_mask & (1u << ph)) n += (int)h->ops[ph].size();
+  return n;
+}
+
+int fb_profile_ops(fb_handle* h, uint32_t phase_mask, int reps, void* stream, float* ms_out, int32_t* kind_out, double* flops_out,
+                   double* bytes_out, int cap) {
+  if (!h || !h->bound) return FB_E_STATE;
+  if (reps < 1 || cap < 1 || !ms_out) return FB_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<const Op*> ops;
+  for (int ph = 0; ph < FB_NUM_PHASES; ++ph)
+    if (phase_mask & (1u << ph))
+      for (auto& op : h->ops[ph]) ops.push_back(&op);
+  const int n = (int)ops.size();
+  if (n > cap) return FB_E_ARG;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  std::vector<double> acc(n, 0.0);
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(ev[0], s));
+    for (int i = 0; i < n; ++i) {
+      CK((*ops[i])(s));
+      CK(cudaEventRecord(ev[i + 1], s));
+    }
+    CK(cudaEventSynchronize(ev[n]));
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      acc[i] += ms;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  for (int i = 0; i < n; ++i) {
+    ms_out[i] = (float)(acc[i] / reps);
+    if (kind_out) kind_out[i] = ops[i]->kind;
+    if (flops_out) flops_out[i] = ops[i]->flops;
+    if (bytes_out) bytes_out[i] = ops[i]->bytes;
+  }
   return n;
 }
 

@@ -40,7 +40,15 @@ struct SegmentLayout {
   }
 };
 
-typedef std::function<cudaError_t(cudaStream_t)> Op;
+typedef std::function<cudaError_t(cudaStream_t)> OpFn;
+// kinds of launch, reported by fb_profile_ops (FB_OPK_* in fb_b200.h)
+struct Op {
+  OpFn fn;
+  int kind;
+  double flops;  // algorithmic FLOPs of this launch (2 x MACs for GEMM groups)
+  double bytes;  // algorithmic bytes read + written
+  cudaError_t operator()(cudaStream_t s) const { return fn(s); }
+};
 
 struct fb_handle {
   fb_config cfg;
@@ -60,6 +68,7 @@ struct fb_handle {
   std::vector<Op> ops[FB_NUM_PHASES];
   std::map<std::string, Mat> views;
   std::map<uint32_t, cudaGraphExec_t> graphs;
+  cudaStream_t capture_stream = nullptr;
   // fixed workspace objects
   DevScalars* d_sc = nullptr;
   double* d_acc = nullptr;
@@ -172,7 +181,7 @@ static GemmDesc lin_dw(const Mat& dY, const Mat& X, const Mat& dW) {
   return d;
 }
 
-struct GroupLaunch { const GemmDesc* d_descs; int nprob, ctas; };
+struct GroupLaunch { const GemmDesc* d_descs; int nprob, ctas; double flops, bytes; };
 
 static GroupLaunch finalize_group(fb_handle* h, std::vector<GemmDesc> g, char* d_arena) {
   // tile configuration per problem
@@ -209,6 +218,12 @@ static GroupLaunch finalize_group(fb_handle* h, std::vector<GemmDesc> g, char* d
   }
   (void)big_tiles;
   GroupLaunch gl;
+  gl.flops = 0.0; gl.bytes = 0.0;
+  for (auto& d : g) {
+    const double k = (double)d.K + (double)d.K2;
+    gl.flops += 2.0 * d.M * (double)d.N * k;
+    gl.bytes += 4.0 * ((double)d.M * k + (double)d.N * k + (double)d.M * d.N * ((d.flags & GF_ATOMIC) ? 2.0 : 1.0));
+  }
   gl.d_descs = arena_put(h, g, d_arena);
   gl.nprob = (int)g.size(); gl.ctas = work;
   return gl;

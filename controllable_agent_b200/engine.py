@@ -205,6 +205,16 @@ class FBStepEngine:
     def launch_count(self, mask: int = L.PHASE_ALL) -> int:
         return self.lib.fb_launch_count(self.h, mask)
 
+    def profile_ops(self, mask: int = L.PHASE_ALL, reps: int = 5) -> tp.List[tp.Dict[str, tp.Any]]:
+        """Per-launch CUDA-event timings of the phases in `mask` (runs the step `reps` times eagerly)."""
+        cap = self.launch_count(mask)
+        ms, kind = (C.c_float * cap)(), (C.c_int32 * cap)()
+        flops, nbytes = (C.c_double * cap)(), (C.c_double * cap)()
+        n = self.lib.fb_profile_ops(self.h, mask, reps, self._stream(), ms, kind, flops, nbytes, cap)
+        if n < 0:
+            L.check(n, "fb_profile_ops")
+        return [{"ms": ms[i], "kind": L.OP_KINDS[kind[i]], "flops": flops[i], "bytes": nbytes[i]} for i in range(n)]
+
     def gather_block(self) -> tp.Tuple[torch.Tensor, torch.Tensor]:
         """(local, global) packed [rows, pitch] blocks for the multi-GPU all-gather between FB_FWD and FB_LOSS."""
         n, pl, pg = C.c_int(), C.c_void_p(), C.c_void_p()

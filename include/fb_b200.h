@@ -168,6 +168,14 @@ int fb_set_noise(fb_handle* h, const float* d_noise_fb, const float* d_noise_act
 int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream);
 /* number of kernel launches (graph nodes) fb_run(mask) issues */
 int fb_launch_count(fb_handle* h, uint32_t phase_mask);
+/* kinds of launch reported by fb_profile_ops */
+enum { FB_OPK_GEMM = 0, FB_OPK_LAYERNORM, FB_OPK_ELEMENTWISE, FB_OPK_COLSUM, FB_OPK_ADAM, FB_OPK_GATHER, FB_OPK_LOSS,
+       FB_OPK_MEMSET, FB_OPK_CONTRACT };
+/* run the launches of `phase_mask` eagerly `reps` times with a CUDA event between consecutive launches (on `stream`) and
+ * report, per launch: mean duration (ms), kind (FB_OPK_*), algorithmic FLOPs and algorithmic bytes.  Returns the number
+ * of launches (<= cap) or a negative error.  Synchronises.  Executes the step for real (parameters move). */
+int fb_profile_ops(fb_handle* h, uint32_t phase_mask, int reps, void* stream, float* ms_out, int32_t* kind_out,
+                   double* flops_out, double* bytes_out, int cap);
 /* device pointer to the metrics block, float[FB_METRIC_COUNT], indices FB_M_* */
 const float* fb_metrics_ptr(const fb_handle* h);
 /* 1-based Adam step counters live on the device; these set them (checkpoint restore) */
