@@ -749,6 +749,7 @@ __global__ void k_metric_final(MetricFinalParams P) {
 __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters) {
   float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
   const float b = 1.000001f, c = 1e-7f;
+#pragma unroll 16
   for (int i = 0; i < iters; ++i) {
     a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
     a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
