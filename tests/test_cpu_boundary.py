@@ -1,0 +1,194 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol include/fb_b200.h declares, the
+parameter layout matches the reference's registration order and sizes, the config surface matches the reference's
+dataclass field for field, and the product refuses to run without CUDA (no CPU fallback)."""
+import ctypes as C
+import dataclasses
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden, subtree
+from oracle import fb_oracle as O
+
+
+def _lib():
+    from controllable_agent_b200 import _lib as L
+    return L, L.load()
+
+
+def test_library_exports_every_declared_symbol():
+    L, lib = _lib()
+    header = open(os.path.join(ROOT, "include", "fb_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(fb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 27
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/fb_b200.h but not exported"
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)   # the ctypes table binds exactly the header
+    assert lib.fb_abi_version() == L.FB_ABI_VERSION
+    assert lib.fb_error_string(-1) == b"bad argument"
+
+
+def _create(L, lib, d, batch=64, **kw):
+    c = L.fb_config(abi_version=L.FB_ABI_VERSION, batch=batch, global_batch=kw.get("global_batch", batch), row_offset=kw.get("row_offset", 0),
+                    obs_dim=d.obs_dim, action_dim=d.action_dim, z_dim=d.z_dim, goal_dim=d.goal_dim, hidden_dim=d.hidden_dim,
+                    feature_dim=d.feature_dim, backward_hidden_dim=d.backward_hidden_dim, use_goal=kw.get("use_goal", 0), rng_device=0,
+                    ortho_coef=1.0, mix_ratio=0.5, beta1=0.9, beta2=0.999, adam_eps=1e-8, seed=0)
+    h = C.c_void_p()
+    return lib.fb_create(C.byref(c), C.byref(h)), h
+
+
+def _table(lib, h, net):
+    out = []
+    for i in range(lib.fb_num_tensors(h, net)):
+        off, rows, cols = C.c_size_t(), C.c_int(), C.c_int()
+        name = C.create_string_buffer(64)
+        assert lib.fb_tensor_info(h, net, i, C.byref(off), C.byref(rows), C.byref(cols), name, 64) == 0
+        out.append((name.value.decode(), off.value, (rows.value, cols.value) if cols.value else (rows.value,)))
+    return out
+
+
+@pytest.mark.parametrize("d", [O.Dims(), O.Dims(obs_dim=78, action_dim=12, goal_dim=2), O.Dims(obs_dim=17, z_dim=100, goal_dim=17),
+                               O.Dims(obs_dim=11, action_dim=3, z_dim=10, goal_dim=11, hidden_dim=48, feature_dim=24, backward_hidden_dim=30)])
+def test_flat_layout_matches_reference_registration_order(d):
+    L, lib = _lib()
+    rc, h = _create(L, lib, d, use_goal=int(d.goal_dim != d.obs_dim))
+    assert rc == 0
+    for net, spec in ((L.NET_FORWARD, O.forward_map_spec(d)), (L.NET_BACKWARD, O.backward_map_spec(d)), (L.NET_ACTOR, O.actor_spec(d))):
+        tab = _table(lib, h, net)
+        assert [(n, s) for n, _, s in tab] == [(n, tuple(s)) for n, s in spec]
+        offs = [o for _, o, _ in tab]
+        assert offs == sorted(offs) and all(o % 32 == 0 for o in offs)           # 128-byte aligned, non-overlapping
+        for (n, o, s), (_, o2, _) in zip(tab, tab[1:]):
+            assert o + int(np.prod(s)) <= o2
+    n_fb, n_actor = lib.fb_flat_size(h, 0), lib.fb_flat_size(h, 1)
+    assert n_fb % 4 == 0 and n_actor % 4 == 0
+    last = _table(lib, h, L.NET_BACKWARD)[-1]
+    assert last[1] + int(np.prod(last[2])) <= n_fb
+    assert lib.fb_workspace_bytes(h) > 0
+    lib.fb_destroy(h)
+
+
+def test_default_layout_parameter_counts():
+    """forward_net 3 363 940, backward_net 317 754, actor 2 211 846 parameters."""
+    L, lib = _lib()
+    rc, h = _create(L, lib, O.Dims(), batch=1024)
+    assert rc == 0
+    counts = [sum(int(np.prod(s)) for _, _, s in _table(lib, h, net)) for net in (L.NET_FORWARD, L.NET_BACKWARD, L.NET_ACTOR)]
+    assert counts == [3363940, 317754, 2211846]
+    lib.fb_destroy(h)
+
+
+def test_create_rejects_bad_configs():
+    L, lib = _lib()
+    d = O.Dims()
+    assert _create(L, lib, d, batch=1)[0] == -1                                      # batch < 2: no off-diagonal entries
+    assert _create(L, lib, d, batch=64, global_batch=32)[0] == -1                    # local rows exceed the global batch
+    assert _create(L, lib, d, batch=64, global_batch=128, row_offset=96)[0] == -1    # row block sticks out
+    assert _create(L, lib, dataclasses.replace(d, goal_dim=3))[0] == -1              # goal_dim != obs_dim without a goal space
+    assert _create(L, lib, dataclasses.replace(d, hidden_dim=4096))[0] == -3         # LayerNorm width beyond the kernels' limit
+    rc, h = _create(L, lib, d, batch=64, global_batch=128, row_offset=64)
+    assert rc == 0
+    lib.fb_destroy(h)
+    # calls on an unbound handle fail with FB_E_STATE instead of touching the device
+    rc, h = _create(L, lib, d)
+    assert lib.fb_run(h, L.PHASE_ALL, 0, None) == -2
+    assert lib.fb_set_z(h, None, None) == -2
+    lib.fb_destroy(h)
+
+
+def test_batch_row_layout_is_16_byte_aligned():
+    L, lib = _lib()
+    offs, pitch = (C.c_int32 * 9)(), C.c_int32()
+    assert lib.fb_batch_row_layout(24, 6, 3, 50, 1, offs, C.byref(pitch)) == 0
+    o = list(offs)
+    assert all(x % 4 == 0 for x in o) and pitch.value % 4 == 0
+    assert o == sorted(o) and o[0] == 0 and o[1] == 24 and o[2] == 32 and o[3] == 36 and o[4] == 60 and o[5] == 64 and o[6] == 68
+    assert pitch.value == 68 + 52 + 24 + 4
+
+
+def test_config_surface_matches_reference_dataclass():
+    """Every field of the reference's FBDDPGAgentConfig (fb_ddpg.py:37-82), same order and same default."""
+    from controllable_agent_b200.agent import FBDDPGAgentConfig
+    ref_fields = [
+        ("_target_", None), ("name", "fb_ddpg"), ("obs_type", "???"), ("obs_shape", "???"), ("action_shape", "???"), ("device", "${device}"),
+        ("lr", 1e-4), ("lr_coef", 1), ("fb_target_tau", 0.01), ("update_every_steps", 2), ("use_tb", "${use_tb}"), ("use_wandb", "${use_wandb}"),
+        ("use_hiplog", "${use_hiplog}"), ("num_expl_steps", "???"), ("num_inference_steps", 5120), ("hidden_dim", 1024),
+        ("backward_hidden_dim", 526), ("feature_dim", 512), ("z_dim", 50), ("stddev_schedule", "0.2"), ("stddev_clip", 0.3),
+        ("update_z_every_step", 300), ("update_z_proba", 1.0), ("nstep", 1), ("batch_size", 1024), ("init_fb", True),
+        ("update_encoder", "${update_encoder}"), ("goal_space", "${goal_space}"), ("ortho_coef", 1.0), ("log_std_bounds", (-5, 2)),
+        ("temp", 1), ("boltzmann", False), ("debug", False), ("future_ratio", 0.0), ("mix_ratio", 0.5), ("rand_weight", False),
+        ("preprocess", True), ("norm_z", True), ("q_loss", False), ("q_loss_coef", 0.01), ("additional_metric", False), ("add_trunk", False)]
+    mine = dataclasses.fields(FBDDPGAgentConfig)
+    assert [f.name for f in mine[:len(ref_fields)]] == [n for n, _ in ref_fields]
+    cfg = FBDDPGAgentConfig()
+    for name, default in ref_fields[1:]:
+        assert getattr(cfg, name) == default, name
+    assert cfg._target_.endswith(".FBDDPGAgent")
+
+
+def test_no_cpu_fallback():
+    from controllable_agent_b200 import FBDDPGAgent, FBStepEngine, EngineConfig
+    with pytest.raises(RuntimeError, match="no CPU"):
+        FBStepEngine(EngineConfig(batch=8, obs_dim=4, action_dim=2, z_dim=4, goal_dim=4), "cpu")
+    with pytest.raises(RuntimeError, match="CPU fallback"):
+        FBDDPGAgent(obs_type="states", obs_shape=(24,), action_shape=(6,), device="cpu", num_expl_steps=0, update_encoder=True,
+                    goal_space=None, use_tb=False, use_wandb=False, use_hiplog=False)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            FBStepEngine(EngineConfig(batch=8, obs_dim=4, action_dim=2, z_dim=4, goal_dim=4), "cuda")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "controllable_agent_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in text.lower() or fn == "README.md", f"{fn} mentions the oracle"
+
+
+def test_module_mirrors_match_oracle_forward():
+    """The host-side nn.Module mirrors (act / infer_meta plumbing) compute what the oracle restatement computes."""
+    from controllable_agent_b200 import modules as M
+    torch.manual_seed(0)
+    d = O.Dims(obs_dim=11, action_dim=3, z_dim=10, goal_dim=11, hidden_dim=48, feature_dim=24, backward_hidden_dim=30)
+    actor, fwd, bwd = M.Actor(11, 10, 3, 24, 48), M.ForwardMap(11, 10, 3, 24, 48), M.BackwardMap(11, 10, 30)
+    assert [n for n, _ in actor.named_parameters()] == [n for n, _ in O.actor_spec(d)]
+    assert [n for n, _ in fwd.named_parameters()] == [n for n, _ in O.forward_map_spec(d)]
+    assert [n for n, _ in bwd.named_parameters()] == [n for n, _ in O.backward_map_spec(d)]
+    obs, z, act = torch.randn(5, 11), torch.randn(5, 10), torch.rand(5, 3) * 2 - 1
+    with torch.no_grad():
+        pa, pf, pb = (dict(m.named_parameters()) for m in (actor, fwd, bwd))
+        assert torch.allclose(actor(obs, z, 0.2).mean, O.actor_mean(pa, obs, z), atol=1e-6)
+        f1, f2 = fwd(obs, z, act)
+        o1, o2 = O.forward_map(pf, obs, z, act)
+        assert torch.allclose(f1, o1, atol=1e-6) and torch.allclose(f2, o2, atol=1e-6)
+        assert torch.allclose(bwd(obs), O.backward_map(pb, obs, 10), atol=1e-6)
+    assert M.schedule("linear(1,0.2,200)", 100) == pytest.approx(0.6)
+    assert M.schedule("step_linear(1,0.5,100,0.1,100)", 150) == pytest.approx(0.3)
+    # same construction order + same init calls => same parameters as the reference for the same torch seed
+    g = load_golden("update_small")
+    ref = subtree(g, "param0/actor")
+    assert tuple(ref["obs_net.0.weight"].shape) == (48, 11)
+
+
+@pytest.mark.parametrize("case,dims,seed", [("small", (11, 10, 3, 24, 48, 30, 11), 11), ("wide", (24, 50, 6, 64, 128, 70, 24), 37)])
+def test_seeded_init_reproduces_reference_parameters(case, dims, seed):
+    """Building the mirrors in the reference's order (Actor, ForwardMap, BackwardMap, ... fb_ddpg.py:117-139) after the same
+    torch.manual_seed consumes the CPU generator identically: the 2-D weights equal the reference agent's (to the ulp-level
+    differences LAPACK's QR shows between thread counts; a different random stream would differ by O(0.1))."""
+    from controllable_agent_b200 import modules as M
+    O_, Z, A, Fd, H, Hb, G = dims
+    g = load_golden(f"update_{case}")
+    torch.manual_seed(seed)
+    actor = M.Actor(O_, Z, A, Fd, H)
+    fwd = M.ForwardMap(O_, Z, A, Fd, H)
+    bwd = M.BackwardMap(G, Z, Hb)
+    for net, key in ((actor, "actor"), (fwd, "forward_net"), (bwd, "backward_net")):
+        for name, p in net.named_parameters():
+            if p.dim() == 2:   # the fixture perturbs only 1-D tensors of the online nets
+                np.testing.assert_allclose(p.detach().numpy(), g[f"param0/{key}/{name}"], rtol=0, atol=2e-5, err_msg=f"{key}/{name}")
