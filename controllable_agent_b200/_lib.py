@@ -14,7 +14,8 @@ import typing as tp
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libfb_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", n) for n in ("fb_b200.cu", "plan.cuh", "kernels.cuh", "gemm_simt.cuh", "common.cuh")]
+SOURCES = [os.path.join(HERE, "csrc", n) for n in ("fb_b200.cu", "plan.cuh", "kernels.cuh", "gemm_simt.cuh", "contract_tc.cuh", "common.cuh")]
+CONTRACT_TCGEN05, CONTRACT_SIMT = 0, 1
 HEADER = os.path.join(ROOT, "include", "fb_b200.h")
 
 FB_ABI_VERSION = 1
@@ -45,7 +46,7 @@ class fb_config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("batch", C.c_int32), ("global_batch", C.c_int32), ("row_offset", C.c_int32),
                 ("obs_dim", C.c_int32), ("action_dim", C.c_int32), ("z_dim", C.c_int32), ("goal_dim", C.c_int32),
                 ("hidden_dim", C.c_int32), ("feature_dim", C.c_int32), ("backward_hidden_dim", C.c_int32),
-                ("use_goal", C.c_int32), ("rng_device", C.c_int32),
+                ("use_goal", C.c_int32), ("rng_device", C.c_int32), ("contract_mode", C.c_int32),
                 ("ortho_coef", C.c_float), ("mix_ratio", C.c_float),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
                 ("seed", C.c_uint64)]
@@ -100,7 +101,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "fb_batch_row_layout": (_i, [_i, _i, _i, _i, _i, _pi32, _pi32]),
     "fb_replay_gather": (_i, [C.POINTER(fb_replay_view), _i, _i, _vp, _vp, _vp, _i, _f, _vp, _i, _vp]),
     "fb_replay_pack_episode": (_i, [C.POINTER(fb_replay_view), _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "fb_sgemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fb_sgemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fb_fp32_peak_tflops": (_i, [C.POINTER(C.c_double), _vp]),
 }
 

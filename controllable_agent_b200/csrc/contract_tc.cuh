@@ -1,0 +1,296 @@
+// The batch x batch successor-measure contraction of update_fb on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+//   M_k = F_k . B^T,  tM = min_k(tF_k . tB^T),  Cov = B . B^T          (fb_ddpg.py:313-315, 320-321, 344)
+//   loss sums + dL/dM_k, dL/dCov                                        (fb_ddpg.py:322-326, 345-347)
+//
+// are computed tile by tile without ever materialising the einsum outputs or the boolean off-diagonal mask: one CTA owns
+// a 128 x 64 tile of the [rows x cols] pair space, accumulates up to five products for it in TMEM (5 x 64 fp32 columns),
+// and its epilogue turns them straight into the gradient tiles G1, G2 (= dL/dM_k), Gc (= ortho_coef * dL/dCov) and the
+// fp64 loss sums.
+//
+// Precision: kind::tf32 reads fp32 operands and drops the low 13 mantissa bits, which alone would put a ~1e-3 relative
+// error on every product (the parity gate is 1e-3 on gradients).  Each operand is therefore split once per step
+// (k_contract_split) into  x = hi + lo,  hi = x with the low 13 bits cleared (what the tensor core sees when given x),
+// lo = x - hi (exact in fp32), and each product is issued as three MMA chains  hi.hi + lo.hi + hi.lo  ("3xTF32"),
+// which restores ~2^-21 relative accuracy at 3x the tensor work of a contraction that is <2% of the step.
+//
+// Operand storage: X2[m] = [n_rows][2 * KP] fp32 with columns [0, KP) = x (zero padded from Z to KP = 32 * ceil(Z / 32)),
+// [KP, 2 KP) = lo.  TMA (SWIZZLE_128B, boxes of 64 rows x 32 floats) stages them K-major in shared memory exactly in
+// the canonical UMMA K-major SW128 layout (8-row x 128-byte atoms, SBO = 1024 B).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+#define CT_TILE_M 128
+#define CT_TILE_N 64
+#define CT_MAX_PRODUCTS 5
+#define CT_TMEM_COLS 512
+#define CT_THREADS 128
+
+enum { CT_MODE_ROW = 0, CT_MODE_COL = 1 };
+enum { CT_F1 = 0, CT_F2, CT_TF1, CT_TF2, CT_B, CT_TB, CT_NUM_OPERANDS };
+
+struct __align__(64) ContractParams {
+  CUtensorMap maps[CT_NUM_OPERANDS];  // one per split operand, box = 32 floats x 64 rows
+  int prod_a[CT_MAX_PRODUCTS], prod_b[CT_MAX_PRODUCTS];  // operand ids of each product; A rows = tile rows, B rows = tile cols
+  int n_products, mode;
+  int nr, nc;              // rows / cols of the pair space handled by this launch
+  int a_row0;              // first row of the A-side operands inside their arrays (row_offset for ROW mode)
+  int diag0;               // column index of the diagonal for row 0 (row_offset)
+  int nbox;                // KP / 32
+  int ksteps;              // ceil(Z / 8) MMA k-steps per chain
+  int ld;                  // leading dimension of the G outputs
+  float* G1; float* G2; float* Gc;   // ROW: [nr, ld]; COL: G1, G2 only
+  float* Gt1; float* Gt2;            // ROW, optional (single GPU): transposed copies [nc, ld] so the COL launch is not needed
+  const float* disc; int disc_stride;  // ROW: discount of local row i; COL: discount of global column j
+  float inv_noff, inv_n, c4;           // 1/(n(n-1)), 1/n, 4 * ortho_coef / (n(n-1))
+  double* acc;
+};
+
+__device__ __forceinline__ uint32_t ct_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ct_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ct_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ct_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ct_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ct_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(ct_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void ct_tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   ct_smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(ct_smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start address, LBO = 0, SBO = 1024 B, version 1, layout type 2
+__device__ __forceinline__ uint64_t ct_umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = 64
+__device__ __forceinline__ uint32_t ct_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CT_TILE_N >> 3) << 17) | ((uint32_t)(CT_TILE_M >> 4) << 24);
+}
+__device__ __forceinline__ void ct_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void ct_mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ct_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ct_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split the exchange block into tensor-core operands: out[m][row] = [x (Z, zero padded to KP) | lo (KP)]
+__global__ void __launch_bounds__(256) k_contract_split(const float* __restrict__ blk, int blk_pitch, int ldz, int rows, int Z, int KP,
+                                                        float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = CT_NUM_OPERANDS * rows * KP;
+  if (idx >= total) return;
+  const int c = idx % KP;
+  const int r = (idx / KP) % rows;
+  const int m = idx / (KP * rows);
+  float x = 0.f, lo = 0.f;
+  if (c < Z) {
+    x = blk[(size_t)r * blk_pitch + m * ldz + c];
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    lo = x - hi;
+  }
+  float* o = out + ((size_t)m * rows + r) * (2 * KP);
+  o[c] = x;
+  o[KP + c] = lo;
+}
+
+// dynamic smem: [stage][A raw | A lo | B raw | B lo], each part nbox boxes of (rows x 128 B); 1024-byte aligned
+__global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_constant__ ContractParams P) {
+  extern __shared__ __align__(1024) uint8_t ct_smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[2];
+  __shared__ __align__(8) uint64_t bar_empty[2];
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ double red[6][4];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ct_smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.y, tile_n = blockIdx.x;
+  const int row0 = tile_m * CT_TILE_M, col0 = tile_n * CT_TILE_N;
+  const int nbox = P.nbox;
+  const uint32_t a_part = (uint32_t)nbox * CT_TILE_M * 128u;   // bytes of one A part (raw or lo)
+  const uint32_t b_part = (uint32_t)nbox * CT_TILE_N * 128u;
+  const uint32_t stage_bytes = 2u * a_part + 2u * b_part;
+  const int nstage = (2u * stage_bytes <= 200u * 1024u) ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { ct_mbar_init(&bar_full[s], 1); ct_mbar_init(&bar_empty[s], 1); }
+    ct_mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ct_smem_u32(&tmem_base_smem)), "r"(CT_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (threadIdx.x == 0) {
+    // ---- single-thread producer + MMA issuer: loads run one product ahead of the tensor core ----
+    auto issue_loads = [&](int p) {
+      const int s = p % nstage;
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      ct_mbar_expect_tx(&bar_full[s], stage_bytes);
+      const CUtensorMap* ma = &P.maps[P.prod_a[p]];
+      const CUtensorMap* mb = &P.maps[P.prod_b[p]];
+      const int KP = nbox * 32;
+      for (int part = 0; part < 2; ++part) {       // 0: raw, 1: lo
+        for (int b = 0; b < nbox; ++b) {
+          const int kcol = part * KP + b * 32;
+          uint8_t* da = st + part * a_part + (size_t)b * CT_TILE_M * 128;
+          ct_tma_load_2d(da, ma, &bar_full[s], kcol, P.a_row0 + row0);
+          ct_tma_load_2d(da + 64 * 128, ma, &bar_full[s], kcol, P.a_row0 + row0 + 64);
+          uint8_t* db = st + 2 * a_part + part * b_part + (size_t)b * CT_TILE_N * 128;
+          ct_tma_load_2d(db, mb, &bar_full[s], kcol, col0);
+        }
+      }
+    };
+    const uint32_t idesc = ct_idesc();
+    const int np = P.n_products;
+    for (int p = 0; p < nstage && p < np; ++p) issue_loads(p);
+    for (int p = 0; p < np; ++p) {
+      const int s = p % nstage;
+      ct_mbar_wait(&bar_full[s], (p / nstage) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sbase = ct_smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t d_tmem = tmem_base + (uint32_t)p * CT_TILE_N;
+      // chains: (A raw, B raw), (A lo, B raw), (A raw, B lo)
+      for (int chain = 0; chain < 3; ++chain) {
+        const uint32_t abase = sbase + (chain == 1 ? a_part : 0u);
+        const uint32_t bbase = sbase + 2u * a_part + (chain == 2 ? b_part : 0u);
+        for (int ks = 0; ks < P.ksteps; ++ks) {
+          const uint32_t box = (uint32_t)ks >> 2, kin = (uint32_t)ks & 3u;
+          const uint64_t ad = ct_umma_desc(abase + box * CT_TILE_M * 128u + kin * 32u);
+          const uint64_t bd = ct_umma_desc(bbase + box * CT_TILE_N * 128u + kin * 32u);
+          ct_mma_tf32(d_tmem, ad, bd, idesc, (chain | ks) != 0 ? 1u : 0u);
+        }
+      }
+      ct_mma_commit(&bar_empty[s]);   // arrives when the MMAs above have finished reading this stage
+      if (p + nstage < np) {
+        ct_mbar_wait(&bar_empty[s], (p / nstage) & 1);
+        issue_loads(p + nstage);
+      }
+    }
+    ct_mma_commit(&bar_done);
+  }
+  __syncwarp();
+  ct_mbar_wait(&bar_done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- epilogue: thread = one row of the tile (TMEM lane), 16 columns at a time ----
+  const int r_local = warp * 32 + lane;
+  const int row = row0 + r_local;
+  const bool row_ok = row < P.nr;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  double a_off = 0.0, a_diag = 0.0, a_cov = 0.0, a_covd = 0.0, a_tm = 0.0, a_m1 = 0.0;
+  const float inv_noff = P.inv_noff, inv_n = P.inv_n, c4 = P.c4;
+  const int diag_col = P.diag0 + row;
+  float g_row = 0.f;
+  if (P.mode == CT_MODE_ROW && row_ok) g_row = P.disc[(size_t)row * P.disc_stride];
+#pragma unroll 1
+  for (int cb = 0; cb < CT_TILE_N; cb += 16) {
+    float m1[16], m2[16], t1[16], t2[16], cv[16];
+    ct_tmem_ld16(lane_addr + 0 * CT_TILE_N + cb, m1);
+    ct_tmem_ld16(lane_addr + 1 * CT_TILE_N + cb, m2);
+    ct_tmem_ld16(lane_addr + 2 * CT_TILE_N + cb, t1);
+    ct_tmem_ld16(lane_addr + 3 * CT_TILE_N + cb, t2);
+    if (P.mode == CT_MODE_ROW) ct_tmem_ld16(lane_addr + 4 * CT_TILE_N + cb, cv);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = col0 + cb + j;
+        if (col >= P.nc) continue;
+        const float tm = fminf(t1[j], t2[j]);
+        const size_t o = (size_t)row * P.ld + col;
+        if (P.mode == CT_MODE_ROW) {
+          a_tm += tm; a_m1 += m1[j];
+          float g1, g2, gc;
+          if (col != diag_col) {
+            const float d1 = m1[j] - g_row * tm, d2 = m2[j] - g_row * tm;
+            a_off += (double)d1 * d1 + (double)d2 * d2;
+            a_cov += (double)cv[j] * cv[j];
+            g1 = d1 * inv_noff; g2 = d2 * inv_noff; gc = c4 * cv[j];
+          } else {
+            a_diag += (double)m1[j] + (double)m2[j];
+            a_covd += cv[j];
+            g1 = -inv_n; g2 = -inv_n; gc = 0.f;
+          }
+          P.G1[o] = g1; P.G2[o] = g2; P.Gc[o] = gc;
+          if (P.Gt1) {  // transposed copies: for a fixed column the 32 lanes of a warp write 32 consecutive floats
+            const size_t ot = (size_t)col * P.ld + row;
+            P.Gt1[ot] = g1; P.Gt2[ot] = g2;
+          }
+        } else {
+          // COL mode: rows are the LOCAL columns t of the loss matrices, cols run over all global rows s
+          float g1, g2;
+          if (col != diag_col) {
+            const float g = __ldg(P.disc + (size_t)col * P.disc_stride);
+            g1 = (m1[j] - g * tm) * inv_noff; g2 = (m2[j] - g * tm) * inv_noff;
+          } else {
+            g1 = -inv_n; g2 = -inv_n;
+          }
+          P.G1[o] = g1; P.G2[o] = g2;
+        }
+      }
+    }
+  }
+  if (P.mode == CT_MODE_ROW) {
+    double vals[6] = {a_off, a_diag, a_cov, a_covd, a_tm, a_m1};
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double v = warp_sum_d(vals[i]);
+      if (lane == 0) red[i][warp] = v;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (P.mode == CT_MODE_ROW && threadIdx.x < 6) {
+    const int slot[6] = {ACC_OFFDIAG_SQ, ACC_DIAG, ACC_COV_OFF_SQ, ACC_COV_DIAG, ACC_TARGET_M, ACC_M1};
+    atomicAdd(P.acc + slot[threadIdx.x], red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3]);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(CT_TMEM_COLS) : "memory");
+  }
+}

@@ -144,6 +144,30 @@ static L2Desc b_l2(const BAct& b, int Z) {
 struct HeadAct { Mat h1, out; };
 
 // ------------------------------------------------------------------------------------------------
+// TMA tensor maps for the tcgen05 contraction (driver entry point fetched through the runtime: no -lcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_operand_map(CUtensorMap* map, float* base, int rows, int cols) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return FB_E_STATE;
+    fn = (EncodeTiledFn)p;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {32u, 64u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FB_OK : FB_E_STATE;
+}
+
+// ------------------------------------------------------------------------------------------------
 // the plan
 // ------------------------------------------------------------------------------------------------
 static int build_gather_params(const fb_replay_view& v, GatherParams& gp, const BatchLayout& L, int out_ld);
@@ -373,13 +397,65 @@ static int build_plan(fb_handle* h) {
   // =========================== FB_PHASE_FB_LOSS =================================================
   // (multi-GPU: the caller all-gathers blk_local -> blk_global between FB_FWD and FB_LOSS)
   b.set_phase(FB_PHASE_FB_LOSS);
-  {
+  const bool use_tc = c.contract_mode == FB_CONTRACT_TCGEN05 && Z <= 128;
+  const float inv_noff = 1.0f / ((float)n * (float)(n - 1)), inv_n = 1.0f / (float)n;
+  if (use_tc) {
+    // tcgen05 path (contract_tc.cuh): split operands -> fused contraction + loss + dL/dM tiles
+    const int nbox = fb_ceil_div(Z, 32), KP = nbox * 32;
+    float* x2 = (float*)ws_alloc(h, (size_t)CT_NUM_OPERANDS * n * 2 * KP * sizeof(float));
+    {
+      const float* blk = bg.p; const int pitch = bg.ld;
+      b.push([blk, pitch, ldZ, n, Z, KP, x2](cudaStream_t s) {
+        k_contract_split<<<fb_ceil_div(CT_NUM_OPERANDS * n * KP, 256), 256, 0, s>>>(blk, pitch, ldZ, n, Z, KP, x2);
+        return cudaGetLastError();
+      }, FB_OPK_ELEMENTWISE, 0.0, 4.0 * CT_NUM_OPERANDS * n * 3.0 * KP);
+    }
+    ContractParams cp; memset(&cp, 0, sizeof(cp));
+    if (h->ws_base) {
+      for (int m = 0; m < CT_NUM_OPERANDS; ++m) {
+        int rc = encode_operand_map(&cp.maps[m], x2 + (size_t)m * n * 2 * KP, n, 2 * KP);
+        if (rc != FB_OK) return rc;
+      }
+    }
+    cp.nbox = nbox; cp.ksteps = fb_ceil_div(Z, 8); cp.ld = M1.ld; cp.inv_noff = inv_noff; cp.inv_n = inv_n;
+    cp.c4 = 4.0f * c.ortho_coef * inv_noff; cp.acc = acc; cp.diag0 = c.row_offset;
+    const size_t stage_bytes = (size_t)nbox * (2 * CT_TILE_M + 2 * CT_TILE_N) * 128;
+    const size_t smem_bytes = (2 * stage_bytes <= 200u * 1024u ? 2 : 1) * stage_bytes + 1024;
+    h->contract_smem = smem_bytes;
+    const double tile_flops = 2.0 * 3.0 * cp.ksteps * 8.0;  // per pair, per product (3 chains)
+    {
+      ContractParams r = cp;
+      const int pa[5] = {CT_F1, CT_F2, CT_TF1, CT_TF2, CT_B}, pb[5] = {CT_B, CT_B, CT_TB, CT_TB, CT_B};
+      for (int i = 0; i < 5; ++i) { r.prod_a[i] = pa[i]; r.prod_b[i] = pb[i]; }
+      r.n_products = 5; r.mode = CT_MODE_ROW; r.nr = B; r.nc = n; r.a_row0 = c.row_offset;
+      r.G1 = M1.p; r.G2 = M2.p; r.Gc = Cov.p;
+      r.Gt1 = (n == B) ? Mt1.p : nullptr; r.Gt2 = (n == B) ? Mt2.p : nullptr;
+      r.disc = bl.p + disc_col; r.disc_stride = bl.ld;
+      b.push([r, smem_bytes](cudaStream_t s) {
+        dim3 grid(fb_ceil_div(r.nc, CT_TILE_N), fb_ceil_div(r.nr, CT_TILE_M));
+        k_contract_tc<<<grid, CT_THREADS, smem_bytes, s>>>(r);
+        return cudaGetLastError();
+      }, FB_OPK_CONTRACT, 5.0 * tile_flops * B * (double)n, 4.0 * (5.0 * B * (double)n + 6.0 * n * 2.0 * KP));
+    }
+    if (n != B) {  // multi-GPU: the column block of dL/dM (rows = local t, columns = all global s) for dB
+      ContractParams r = cp;
+      const int pa[4] = {CT_B, CT_B, CT_TB, CT_TB}, pb[4] = {CT_F1, CT_F2, CT_TF1, CT_TF2};
+      for (int i = 0; i < 4; ++i) { r.prod_a[i] = pa[i]; r.prod_b[i] = pb[i]; }
+      r.n_products = 4; r.mode = CT_MODE_COL; r.nr = B; r.nc = n; r.a_row0 = c.row_offset;
+      r.G1 = Mt1.p; r.G2 = Mt2.p;
+      r.disc = bg.p + disc_col; r.disc_stride = bg.ld;
+      b.push([r, smem_bytes](cudaStream_t s) {
+        dim3 grid(fb_ceil_div(r.nc, CT_TILE_N), fb_ceil_div(r.nr, CT_TILE_M));
+        k_contract_tc<<<grid, CT_THREADS, smem_bytes, s>>>(r);
+        return cudaGetLastError();
+      }, FB_OPK_CONTRACT, 4.0 * tile_flops * B * (double)n, 4.0 * (2.0 * B * (double)n + 6.0 * n * 2.0 * KP));
+    }
+  } else {
     auto outer = [&](const Mat& X, const Mat& Yall, const Mat& C) {  // C[rows(X), n] = X . Yall^T  (K = Z)
       return gemm_raw(X.p, X.ld, 1, Yall.p, Yall.ld, 1, C.p, C.ld, X.rows, Yall.rows, Z, nullptr, 0, nullptr, 0);
     };
     b.gemm({outer(F1, Bg, M1), outer(F2, Bg, M2), outer(tF1, tBg, T1), outer(tF2, tBg, T2), outer(Bm, Bg, Cov),
             outer(Bm, F1g, Mt1), outer(Bm, F2g, Mt2), outer(tB, tF1g, Tt1), outer(tB, tF2g, Tt2)});
-    const float inv_noff = 1.0f / ((float)n * (float)(n - 1)), inv_n = 1.0f / (float)n;
     LossElemParams lp; memset(&lp, 0, sizeof(lp));
     lp.M1 = M1.p; lp.M2 = M2.p; lp.T1 = T1.p; lp.T2 = T2.p; lp.Cov = Cov.p; lp.nr = B; lp.nc = n; lp.ld = M1.ld; lp.row0 = c.row_offset;
     lp.disc = bl.p + disc_col; lp.disc_stride = bl.ld; lp.inv_noff = inv_noff; lp.inv_n = inv_n; lp.ortho_coef = c.ortho_coef; lp.acc = acc;
@@ -396,6 +472,8 @@ static int build_plan(fb_handle* h) {
       k_fb_loss_elem_t<<<grid, 256, 0, s>>>(lt);
       return cudaGetLastError();
     }, FB_OPK_LOSS, 0.0, 4.0 * 6.0 * (double)B * (double)n);
+  }
+  {
     b.memset0(dblk.p, (size_t)dblk.rows * dblk.ld * sizeof(float));
     const float coef = -4.0f * c.ortho_coef * inv_n;
     b.push([dB, Bm, B, Z, coef](cudaStream_t s) {
@@ -688,6 +766,7 @@ int fb_bind(fb_handle* h, const fb_buffers* bufs, void* stream) {
   int rc = build_plan(h);
   if (rc != FB_OK) return rc;
   CK(cudaFuncSetAttribute(k_gemm_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  if (h->contract_smem) CK(cudaFuncSetAttribute(k_contract_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->contract_smem));
   CK(cudaMemsetAsync(h->ws_base, 0, h->ws_bytes, s));
   CK(cudaMemcpyAsync(h->ws_base, h->arena.data(), h->arena.size(), cudaMemcpyHostToDevice, s));
   k_iota<<<fb_ceil_div(h->cfg.batch, 256), 256, 0, s>>>(h->d_perm, h->cfg.batch);
@@ -933,13 +1012,12 @@ int fb_replay_pack_episode(const fb_replay_view* view, float* d_rows_mut, int sl
 }
 
 int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, int M, int N, int K, int lda, int ldb, int ldc,
-             int a_kmajor, int b_kmajor, int relu, int splitk, void* stream) {
+             int a_kmajor, int b_kmajor, int relu, int splitk, int tile_cfg, void* stream) {
   if (!dA || !dB || !dC || M < 1 || N < 1 || K < 1) return FB_E_ARG;
+  if (tile_cfg > 2) return FB_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   GemmDesc d = gemm_raw(dA, lda, a_kmajor, dB, ldb, b_kmajor, dC, ldc, M, N, K, d_bias, relu ? GF_RELU : 0, nullptr, 0);
-  d.cfg = (M > 64 && N > 64) ? GEMM_CFG_BIG : GEMM_CFG_SMALL;
-  const int bm = d.cfg == GEMM_CFG_BIG ? 128 : 64;
-  d.tiles_m = fb_ceil_div(M, bm); d.tiles_n = fb_ceil_div(N, bm);
+  gemm_set_tile(d, tile_cfg >= 0 ? tile_cfg : ((M > 64 && N > 64) ? GEMM_CFG_BIG : GEMM_CFG_SMALL));
   if (splitk < 1) splitk = 1;
   if (splitk > 1) { if (relu) return FB_E_ARG; d.flags |= GF_ATOMIC; }
   d.k_per_split = fb_round_up(fb_ceil_div(K, splitk), GEMM_BK);

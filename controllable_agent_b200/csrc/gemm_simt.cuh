@@ -1,13 +1,20 @@
 // Grouped fp32 SIMT SGEMM for the MLP stacks of the FB-DDPG step (sm_100a CUDA cores).
 //
-// One launch executes a *group* of independent problems C = epi(alpha * op(A) . op(B)^T + bias): the
-// layers of different networks that sit at the same depth of the step's dependency graph are issued
-// together so that a launch fills the 148 SMs even though each problem only has M = batch = 1024 rows.
+// One launch executes a *group* of independent problems C = epi(op(A) . op(B)^T [+ op(A2) . op(B2)^T] + bias): the
+// layers of different networks that sit at the same depth of the step's dependency graph are issued together so that a
+// launch fills the 148 SMs even though each problem only has M = batch = 1024 rows.
 //
 // op(A)[m,k]: a_kmajor ? A[m*lda+k] : A[k*lda+m]      op(B)[n,k]: b_kmajor ? B[n*ldb+k] : B[k*ldb+n]
 //   forward  Y  = X . W^T      : A = X  (k-major), B = W  [N,K] (k-major)       (nn.Linear, fb_modules.py:76)
 //   backward dX = dY . W       : A = dY (k-major), B = W  as [k=N_out][n=K_in]  (mn-major)
 //   backward dW = dY^T . X     : A = dY as [k=batch][m=N_out] (mn-major), B = X as [k=batch][n=K_in] (mn-major)
+//
+// Kernel structure: 256 threads, CTA tile BM x BN in {128x128, 128x64, 64x64}, BK = 16, per-thread micro-tile
+// (BM/16) x (BN/16) in registers.  Operand tiles are staged global -> shared with cp.async (LDGSTS, zero-fill for
+// ragged edges) in a 3-stage ring: one __syncthreads per k-tile, no register staging.  Both tiles live in shared
+// memory as S[k][m] so that the FFMA loop reads its fragments as LDS.128 over 4 consecutive m; a k-major operand is
+// transposed on the way in by 4-byte cp.async scatters, with an XOR swizzle of the m index by the k-chunk so that the
+// scatter is bank-conflict free.
 #pragma once
 #include "common.cuh"
 
@@ -17,7 +24,7 @@ enum {
   GF_MASK_TANH = 4,  // C *= (1 - mask^2)                    (backward through a saved tanh output)
   GF_ATOMIC = 8      // C += result with fp32 atomics (split-K or several problems sharing one C)
 };
-enum { GEMM_CFG_BIG = 0, GEMM_CFG_SMALL = 1 };  // 128x128 tile, 8x8 per thread / 64x64 tile, 4x4 per thread
+enum { GEMM_CFG_BIG = 0, GEMM_CFG_SMALL = 1, GEMM_CFG_WIDE = 2 };  // 128x128 / 64x64 / 128x64 CTA tiles
 
 struct __align__(16) GemmDesc {
   const float* A;
@@ -39,211 +46,176 @@ struct __align__(16) GemmDesc {
 
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM_BYTES = 2 * GEMM_BK * (128 + 4 + 128 + 4) * 4;
+constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * (128 + 128) * GEMM_BK * 4;  // 49152
 
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// swizzled position of (k, m) inside a staged tile S[BK][ROWS]: m ^ (8 * ((k >> 2) & 3)) keeps 4-float groups intact
+__device__ __forceinline__ int gemm_sw(int k, int m, int rows) { return k * rows + (m ^ (((k >> 2) & 3) << 3)); }
+
+// stage one ROWS x BK operand tile (rows [row0, row0+ROWS) x k [k0, k0+BK), clipped to rows_total / kend) into S[k][m]
 template <int ROWS, bool KMAJOR>
-__device__ __forceinline__ float4 gemm_load_slot(const float* __restrict__ base, int ld, int rows_total, int row0,
-                                                 int k0, int kend, int slot, bool vec) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (KMAJOR) {
-    const int r = slot >> 2, k = k0 + ((slot & 3) << 2);
-    const int row = row0 + r;
-    if (row < rows_total && k < kend) {
-      const float* p = base + (size_t)row * ld + k;
-      if (vec && k + 3 < kend) {
-        v = __ldg(reinterpret_cast<const float4*>(p));
+__device__ __forceinline__ void gemm_stage_tile(float* __restrict__ S, const float* __restrict__ base, int ld, int rows_total,
+                                                int row0, int k0, int kend, bool vec) {
+  constexpr int CHUNKS = ROWS * GEMM_BK / 4;
+  static_assert(CHUNKS % GEMM_THREADS == 0, "tile chunks must divide over the CTA");
+#pragma unroll
+  for (int t = 0; t < CHUNKS / GEMM_THREADS; ++t) {
+    const int c = threadIdx.x + t * GEMM_THREADS;
+    if (KMAJOR) {
+      // 4 consecutive k of one row -> 4 scattered 4-byte copies (transpose); any alignment
+      const int r = c >> 2, kc = (c & 3) << 2;
+      const int row = row0 + r, k = k0 + kc;
+      const int nvalid = (row < rows_total) ? max(0, min(4, kend - k)) : 0;
+      const float* src = nvalid > 0 ? base + (size_t)row * ld + k : base;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cp_async4(S + gemm_sw(kc + e, r, ROWS), e < nvalid ? src + e : base, e < nvalid ? 4 : 0);
+    } else {
+      constexpr int C4 = ROWS / 4;
+      const int kk = c / C4, rc = (c % C4) << 2;
+      const int k = k0 + kk, row = row0 + rc;
+      float* dst = S + gemm_sw(kk, rc, ROWS);
+      const int nvalid = (k < kend) ? max(0, min(4, rows_total - row)) : 0;
+      const float* src = nvalid > 0 ? base + (size_t)k * ld + row : base;
+      if (vec) {
+        cp_async16(dst, src, nvalid * 4);
       } else {
-        v.x = __ldg(p);
-        if (k + 1 < kend) v.y = __ldg(p + 1);
-        if (k + 2 < kend) v.z = __ldg(p + 2);
-        if (k + 3 < kend) v.w = __ldg(p + 3);
-      }
-    }
-  } else {
-    constexpr int C4 = ROWS / 4;
-    const int k = k0 + slot / C4, row = row0 + (slot % C4) * 4;
-    if (k < kend && row < rows_total) {
-      const float* p = base + (size_t)k * ld + row;
-      if (vec && row + 3 < rows_total) {
-        v = __ldg(reinterpret_cast<const float4*>(p));
-      } else {
-        v.x = __ldg(p);
-        if (row + 1 < rows_total) v.y = __ldg(p + 1);
-        if (row + 2 < rows_total) v.z = __ldg(p + 2);
-        if (row + 3 < rows_total) v.w = __ldg(p + 3);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cp_async4(dst + e, e < nvalid ? src + e : base, e < nvalid ? 4 : 0);
       }
     }
   }
-  return v;
 }
 
-template <int ROWS, bool KMAJOR>
-__device__ __forceinline__ void gemm_store_slot(float* __restrict__ S, int slot, float4 v) {
-  constexpr int LDS = ROWS + 4;
-  if (KMAJOR) {
-    const int r = slot >> 2, k = (slot & 3) << 2;
-    S[(k + 0) * LDS + r] = v.x;
-    S[(k + 1) * LDS + r] = v.y;
-    S[(k + 2) * LDS + r] = v.z;
-    S[(k + 3) * LDS + r] = v.w;
-  } else {
-    constexpr int C4 = ROWS / 4;
-    const int k = slot / C4, c = (slot % C4) * 4;
-    *reinterpret_cast<float4*>(&S[k * LDS + c]) = v;
-  }
-}
-
-// accumulate op(A)[m0.., kbeg..kend) . op(B)[n0.., kbeg..kend)^T into acc (register-prefetch double buffering)
-template <int BM, int BN, int TM, int TN, bool AK, bool BKM>
-__device__ __forceinline__ void gemm_accumulate(const float* __restrict__ A, const float* __restrict__ B, int lda, int ldb,
-                                                int M, int N, int m0, int n0, int kbeg, int kend, bool avec, bool bvec,
-                                                float* __restrict__ smem, float (&acc)[TM][TN]) {
-  constexpr int BK = GEMM_BK;
-  constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
-  constexpr int A_SLOTS = BM * BK / 4 / GEMM_THREADS;
-  constexpr int B_SLOTS = BN * BK / 4 / GEMM_THREADS;
-  static_assert(A_SLOTS >= 1 && B_SLOTS >= 1, "tile too small for 256 threads");
-  static_assert((BM / TM) * (BN / TN) == GEMM_THREADS, "thread tiling must cover the CTA tile");
-  float* As = smem;                    // [2][BK][LDA_S]
-  float* Bs = smem + 2 * BK * LDA_S;   // [2][BK][LDB_S]
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  float4 ra[A_SLOTS], rb[B_SLOTS];
-
-  const int nk = (kend - kbeg + BK - 1) / BK;
-  if (nk <= 0) return;
-#pragma unroll
-  for (int i = 0; i < A_SLOTS; ++i) ra[i] = gemm_load_slot<BM, AK>(A, lda, M, m0, kbeg, kend, tid + i * GEMM_THREADS, avec);
-#pragma unroll
-  for (int i = 0; i < B_SLOTS; ++i) rb[i] = gemm_load_slot<BN, BKM>(B, ldb, N, n0, kbeg, kend, tid + i * GEMM_THREADS, bvec);
-#pragma unroll
-  for (int i = 0; i < A_SLOTS; ++i) gemm_store_slot<BM, AK>(As, tid + i * GEMM_THREADS, ra[i]);
-#pragma unroll
-  for (int i = 0; i < B_SLOTS; ++i) gemm_store_slot<BN, BKM>(Bs, tid + i * GEMM_THREADS, rb[i]);
-  __syncthreads();
-
-  for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    const bool more = kt + 1 < nk;
-    if (more) {
-      const int k0 = kbeg + (kt + 1) * BK;
-#pragma unroll
-      for (int i = 0; i < A_SLOTS; ++i) ra[i] = gemm_load_slot<BM, AK>(A, lda, M, m0, k0, kend, tid + i * GEMM_THREADS, avec);
-#pragma unroll
-      for (int i = 0; i < B_SLOTS; ++i) rb[i] = gemm_load_slot<BN, BKM>(B, ldb, N, n0, k0, kend, tid + i * GEMM_THREADS, bvec);
-    }
-    const float* __restrict__ as = As + buf * BK * LDA_S;
-    const float* __restrict__ bs = Bs + buf * BK * LDB_S;
-#pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      float a[TM], b[TN];
-      {
-        const float4 t = *reinterpret_cast<const float4*>(&as[kk * LDA_S + ty * 4]);
-        a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
-      }
-      if (TM == 8) {
-        const float4 t = *reinterpret_cast<const float4*>(&as[kk * LDA_S + BM / 2 + ty * 4]);
-        a[TM - 4] = t.x; a[TM - 3] = t.y; a[TM - 2] = t.z; a[TM - 1] = t.w;
-      }
-      {
-        const float4 t = *reinterpret_cast<const float4*>(&bs[kk * LDB_S + tx * 4]);
-        b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
-      }
-      if (TN == 8) {
-        const float4 t = *reinterpret_cast<const float4*>(&bs[kk * LDB_S + BN / 2 + tx * 4]);
-        b[TN - 4] = t.x; b[TN - 3] = t.y; b[TN - 2] = t.z; b[TN - 1] = t.w;
-      }
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    if (more) {
-      float* an = As + (buf ^ 1) * BK * LDA_S;
-      float* bn = Bs + (buf ^ 1) * BK * LDB_S;
-#pragma unroll
-      for (int i = 0; i < A_SLOTS; ++i) gemm_store_slot<BM, AK>(an, tid + i * GEMM_THREADS, ra[i]);
-#pragma unroll
-      for (int i = 0; i < B_SLOTS; ++i) gemm_store_slot<BN, BKM>(bn, tid + i * GEMM_THREADS, rb[i]);
-    }
-    __syncthreads();
-  }
-}
-
-template <int BM, int BN, int TM, int TN, bool AK, bool BKM>
+template <int BM, int BN, bool AK, bool BKM>
 __device__ __forceinline__ void gemm_tile(const GemmDesc& d, int tm, int tn, int ks, float* __restrict__ smem) {
+  constexpr int TM = BM / 16, TN = BN / 16;
+  constexpr int A_STAGE = BM * GEMM_BK, B_STAGE = BN * GEMM_BK, STAGE = A_STAGE + B_STAGE;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = tm * BM, n0 = tn * BN;
-  const int M = d.M, N = d.N;
-  const bool avec = d.a_vec != 0, bvec = d.b_vec != 0;
+  // `d` lives in shared memory: its fields are re-read where needed instead of being pinned in registers
+  const int kbeg = ks * d.k_per_split;
+  const int kend = min(d.K, kbeg + d.k_per_split);
+  const int nk = (kend - kbeg + GEMM_BK - 1) / GEMM_BK + (d.K2 + GEMM_BK - 1) / GEMM_BK;  // K2 never meets split-K
+
   float acc[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  {
-    const int kbeg = ks * d.k_per_split;
-    const int kend = min(d.K, kbeg + d.k_per_split);
-    gemm_accumulate<BM, BN, TM, TN, AK, BKM>(d.A, d.B, d.lda, d.ldb, M, N, m0, n0, kbeg, kend, avec, bvec, smem, acc);
-  }
-  if (d.K2 > 0)  // second segment (never combined with split-K)
-    gemm_accumulate<BM, BN, TM, TN, AK, BKM>(d.A2, d.B2, d.lda, d.ldb, M, N, m0, n0, 0, d.K2, avec, bvec, smem, acc);
+  // staging cursor: walks the k-tiles of segment 0 (A, B), then of segment 1 (A2, B2)
+  const float* sA = d.A;
+  const float* sB = d.B;
+  int sk = kbeg, skend = kend;
+  auto stage = [&](int buf) {
+    if (sk >= skend) { sA = d.A2; sB = d.B2; sk = 0; skend = d.K2; }
+    float* As = smem + buf * STAGE;
+    gemm_stage_tile<BM, AK>(As, sA, d.lda, d.M, m0, sk, skend, d.a_vec != 0);
+    gemm_stage_tile<BN, BKM>(As + A_STAGE, sB, d.ldb, d.N, n0, sk, skend, d.b_vec != 0);
+    sk += GEMM_BK;
+  };
 
-  // ---- epilogue ----
+#pragma unroll
+  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+    if (s < nk) stage(s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<GEMM_STAGES - 2>();
+    __syncthreads();  // tile kt has landed for every thread; every thread is done reading tile kt-1
+    if (kt + GEMM_STAGES - 1 < nk) stage((kt + GEMM_STAGES - 1) % GEMM_STAGES);  // overwrites the buffer of tile kt-1
+    cp_async_commit();
+
+    const float* __restrict__ as = smem + (kt % GEMM_STAGES) * STAGE;
+    const float* __restrict__ bs = as + A_STAGE;
+#pragma unroll
+    for (int kk = 0; kk < GEMM_BK; ++kk) {
+      const int sw = ((kk >> 2) & 3) << 3;
+      float a[TM], b[TN];
+#pragma unroll
+      for (int g = 0; g < TM / 4; ++g) {
+        const float4 t = *reinterpret_cast<const float4*>(&as[kk * BM + ((g * 64 + ty * 4) ^ sw)]);
+        a[g * 4 + 0] = t.x; a[g * 4 + 1] = t.y; a[g * 4 + 2] = t.z; a[g * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int g = 0; g < TN / 4; ++g) {
+        const float4 t = *reinterpret_cast<const float4*>(&bs[kk * BN + ((g * 64 + tx * 4) ^ sw)]);
+        b[g * 4 + 0] = t.x; b[g * 4 + 1] = t.y; b[g * 4 + 2] = t.z; b[g * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: thread rows (i>>2)*64 + ty*4 + (i&3), columns (j>>2)*64 + tx*4 + (j&3) ----
+  const int M = d.M, N = d.N;
   const float alpha = d.alpha;
   const float* __restrict__ bias = (ks == 0) ? d.bias : nullptr;
   const float* __restrict__ mask = d.mask;
   const int flags = d.flags, ldc = d.ldc, ldmask = d.ldmask;
+  const bool cvec = d.c_vec != 0;
   float* __restrict__ C = d.C;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
-    const int row = m0 + ((i < 4) ? (ty * 4 + i) : (BM / 2 + ty * 4 + (i - 4)));
+    const int row = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
     if (row >= M) continue;
 #pragma unroll
-    for (int jc = 0; jc < TN / 4; ++jc) {
-      const int col = n0 + ((jc == 0) ? tx * 4 : (BN / 2 + tx * 4));
+    for (int g = 0; g < TN / 4; ++g) {
+      const int col = n0 + g * 64 + tx * 4;
       if (col >= N) continue;
       float v[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float x = alpha * acc[i][jc * 4 + j];
-        if (col + j < N) {
-          if (bias) x += __ldg(bias + col + j);
+      for (int e = 0; e < 4; ++e) {
+        float x = alpha * acc[i][g * 4 + e];
+        if (col + e < N) {
+          if (bias) x += __ldg(bias + col + e);
           if (flags & GF_RELU) x = fmaxf(x, 0.f);
-          if (flags & GF_MASK_RELU) x = (__ldg(mask + (size_t)row * ldmask + col + j) > 0.f) ? x : 0.f;
-          if (flags & GF_MASK_TANH) {
-            const float t = __ldg(mask + (size_t)row * ldmask + col + j);
-            x *= (1.f - t * t);
-          }
+          if (flags & GF_MASK_RELU) x = (__ldg(mask + (size_t)row * ldmask + col + e) > 0.f) ? x : 0.f;
+          if (flags & GF_MASK_TANH) { const float t = __ldg(mask + (size_t)row * ldmask + col + e); x *= (1.f - t * t); }
         }
-        v[j] = x;
+        v[e] = x;
       }
       float* cp = C + (size_t)row * ldc + col;
       if (flags & GF_ATOMIC) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (col + j < N) atomicAdd(cp + j, v[j]);
-      } else if (d.c_vec && col + 3 < N) {
+        for (int e = 0; e < 4; ++e)
+          if (col + e < N) atomicAdd(cp + e, v[e]);
+      } else if (cvec && col + 3 < N) {
         *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (col + j < N) cp[j] = v[j];
+        for (int e = 0; e < 4; ++e)
+          if (col + e < N) cp[e] = v[e];
       }
     }
   }
 }
 
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN>
 __device__ __forceinline__ void gemm_dispatch_major(const GemmDesc& d, int tm, int tn, int ks, float* smem) {
   if (d.a_kmajor) {
-    if (d.b_kmajor) gemm_tile<BM, BN, TM, TN, true, true>(d, tm, tn, ks, smem);
-    else gemm_tile<BM, BN, TM, TN, true, false>(d, tm, tn, ks, smem);
+    if (d.b_kmajor) gemm_tile<BM, BN, true, true>(d, tm, tn, ks, smem);
+    else gemm_tile<BM, BN, true, false>(d, tm, tn, ks, smem);
   } else {
-    if (d.b_kmajor) gemm_tile<BM, BN, TM, TN, false, true>(d, tm, tn, ks, smem);
-    else gemm_tile<BM, BN, TM, TN, false, false>(d, tm, tn, ks, smem);
+    if (d.b_kmajor) gemm_tile<BM, BN, false, true>(d, tm, tn, ks, smem);
+    else gemm_tile<BM, BN, false, false>(d, tm, tn, ks, smem);
   }
 }
 
@@ -262,6 +234,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_grouped(const GemmDesc
   const int ks = local / per_split;
   const int t = local - ks * per_split;
   const int tm = t / sd.tiles_n, tn = t - tm * sd.tiles_n;
-  if (sd.cfg == GEMM_CFG_BIG) gemm_dispatch_major<128, 128, 8, 8>(sd, tm, tn, ks, gemm_smem);
-  else gemm_dispatch_major<64, 64, 4, 4>(sd, tm, tn, ks, gemm_smem);
+  if (sd.cfg == GEMM_CFG_BIG) gemm_dispatch_major<128, 128>(sd, tm, tn, ks, gemm_smem);
+  else if (sd.cfg == GEMM_CFG_WIDE) gemm_dispatch_major<128, 64>(sd, tm, tn, ks, gemm_smem);
+  else gemm_dispatch_major<64, 64>(sd, tm, tn, ks, gemm_smem);
 }

@@ -15,6 +15,7 @@
 #include "../../include/fb_b200.h"
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
+#include "contract_tc.cuh"
 
 #define FB_NUM_PHASES 10
 #define FB_DESC_ARENA_BYTES (1u << 20)
@@ -69,6 +70,7 @@ struct fb_handle {
   std::map<std::string, Mat> views;
   std::map<uint32_t, cudaGraphExec_t> graphs;
   cudaStream_t capture_stream = nullptr;
+  size_t contract_smem = 0;  // dynamic shared memory of k_contract_tc (0: SIMT contraction)
   // fixed workspace objects
   DevScalars* d_sc = nullptr;
   double* d_acc = nullptr;
@@ -183,40 +185,53 @@ static GemmDesc lin_dw(const Mat& dY, const Mat& X, const Mat& dW) {
 
 struct GroupLaunch { const GemmDesc* d_descs; int nprob, ctas; double flops, bytes; };
 
+static void gemm_set_tile(GemmDesc& d, int cfg) {
+  d.cfg = cfg;
+  const int bm = cfg == GEMM_CFG_SMALL ? 64 : 128, bn = cfg == GEMM_CFG_BIG ? 128 : 64;
+  d.tiles_m = fb_ceil_div(d.M, bm); d.tiles_n = fb_ceil_div(d.N, bn);
+}
+
 static GroupLaunch finalize_group(fb_handle* h, std::vector<GemmDesc> g, char* d_arena) {
-  // tile configuration per problem
-  int big_tiles = 0;
-  for (auto& d : g) {
-    d.cfg = (d.M > 64 && d.N > 64) ? GEMM_CFG_BIG : GEMM_CFG_SMALL;
-    const int bm = d.cfg == GEMM_CFG_BIG ? 128 : 64;
-    d.tiles_m = fb_ceil_div(d.M, bm); d.tiles_n = fb_ceil_div(d.N, bm);
-    big_tiles += d.tiles_m * d.tiles_n;
-  }
-  int total = 0;
-  for (auto& d : g) total += d.tiles_m * d.tiles_n;
+  // Tile configuration: the largest CTA tile that still gives the launch >= 2 CTAs per SM (a lone 8-warp CTA cannot hide
+  // the shared-memory latency of the FFMA loop); narrow outputs (N <= 64) never use the 128-wide tile.
   const int target = 2 * FB_SM_COUNT;
+  const int order[3] = {GEMM_CFG_BIG, GEMM_CFG_WIDE, GEMM_CFG_SMALL};
+  int total = 0;
+  for (int c = 0; c < 3; ++c) {
+    total = 0;
+    for (auto& d : g) {
+      int cfg = order[c];
+      if (d.N <= 64 && cfg == GEMM_CFG_BIG) cfg = GEMM_CFG_WIDE;
+      if (d.M <= 64) cfg = GEMM_CFG_SMALL;
+      gemm_set_tile(d, cfg);
+      int sk_possible = 1;
+      if ((d.flags & GF_ATOMIC) && d.K2 == 0 && !(d.flags & GF_RELU)) sk_possible = d.K / 256 > 0 ? d.K / 256 : 1;
+      total += d.tiles_m * d.tiles_n * (sk_possible > 8 ? 8 : sk_possible);
+    }
+    if (total >= target) break;
+  }
+  int tiles_total = 0;
+  for (auto& d : g) tiles_total += d.tiles_m * d.tiles_n;
   int work = 0;
   for (auto& d : g) {
     const int tiles = d.tiles_m * d.tiles_n;
     int sk = 1;
     const bool can_split = (d.flags & GF_ATOMIC) && d.K2 == 0 && !(d.flags & GF_RELU);
-    if (can_split && total < target) {
-      sk = fb_ceil_div(target, total);
-      const int max_sk = d.K / 128 > 0 ? d.K / 128 : 1;
+    if (can_split && tiles_total < target) {
+      sk = fb_ceil_div(target, tiles_total);
+      const int max_sk = d.K / 256 > 0 ? d.K / 256 : 1;
       if (sk > max_sk) sk = max_sk;
-      if (sk > 16) sk = 16;
+      if (sk > 8) sk = 8;
     }
     int kps = fb_round_up(fb_ceil_div(d.K, sk), GEMM_BK);
     sk = fb_ceil_div(d.K, kps);
     d.splitk = sk; d.k_per_split = kps;
-    if (sk == 1 && (d.flags & GF_ATOMIC) == 0) d.k_per_split = fb_round_up(d.K, GEMM_BK);
     d.a_vec = aligned16(d.A) && (d.lda % 4 == 0) && (d.K2 == 0 || aligned16(d.A2));
     d.b_vec = aligned16(d.B) && (d.ldb % 4 == 0) && (d.K2 == 0 || aligned16(d.B2));
     d.c_vec = aligned16(d.C) && (d.ldc % 4 == 0);
     d.work_begin = work; d.work_count = tiles * sk;
     work += d.work_count;
   }
-  (void)big_tiles;
   GroupLaunch gl;
   gl.flops = 0.0; gl.bytes = 0.0;
   for (auto& d : g) {

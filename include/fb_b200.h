@@ -43,6 +43,8 @@ enum {
   FB_E_UNSUPPORTED = -3 /* configuration branch the kernels do not implement */
 };
 
+enum { FB_CONTRACT_TCGEN05 = 0, FB_CONTRACT_SIMT = 1 };
+
 /* nets, in the order their flat segments are described */
 enum { FB_NET_FORWARD = 0, FB_NET_BACKWARD = 1, FB_NET_ACTOR = 2 };
 
@@ -80,6 +82,8 @@ typedef struct fb_config {
   int32_t use_goal;            /* goal_space is not None: B reads goal / next_goal instead of obs */
   int32_t rng_device;          /* 1: indices, perm, mix mask, z and action noise are drawn on the device
                                   (Philox) inside FB_PHASE_SAMPLE; 0: the caller provides them */
+  int32_t contract_mode;       /* batch x batch contraction + loss of FB_PHASE_FB_LOSS: FB_CONTRACT_TCGEN05 (tensor cores,
+                                  3xTF32, z_dim <= 128) or FB_CONTRACT_SIMT (fp32 CUDA cores, materialised matrices) */
   float ortho_coef, mix_ratio;
   float beta1, beta2, adam_eps; /* torch.optim.Adam defaults 0.9 / 0.999 / 1e-8 */
   uint64_t seed;               /* Philox seed for rng_device */
@@ -208,9 +212,10 @@ int fb_replay_gather(const fb_replay_view* view, int obs_dim, int action_dim, co
 int fb_replay_pack_episode(const fb_replay_view* view, float* d_rows_mut, int slot, int rows, int obs_dim, int action_dim,
                            const float* d_obs, const float* d_action, const float* d_reward, const float* d_discount,
                            const float* d_goal, const float* d_extra, void* stream);
-/* C[M,N] (+)= op(A)·op(B)^T with the grouped SIMT SGEMM used by the plan (single problem) */
+/* C[M,N] (+)= op(A)·op(B)^T with the grouped SIMT SGEMM used by the plan (single problem).  tile_cfg: -1 automatic,
+ * 0 = 128x128, 1 = 64x64, 2 = 128x64 CTA tile.  splitk > 1 accumulates into C with atomics (C must be zeroed). */
 int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, int M, int N, int K, int lda, int ldb,
-             int ldc, int a_kmajor, int b_kmajor, int relu, int splitk, void* stream);
+             int ldc, int a_kmajor, int b_kmajor, int relu, int splitk, int tile_cfg, void* stream);
 /* FMA-chain microbenchmark: returns measured fp32 TFLOP/s of the CUDA cores (synchronises) */
 int fb_fp32_peak_tflops(double* out_tflops, void* stream);
 

@@ -48,7 +48,7 @@ def sgemm_sweep() -> None:
         A = torch.randn((M, K) if ak else (K, M), device="cuda")
         B = torch.randn((N, K) if bk else (K, N), device="cuda")
         Cm = torch.zeros(M, N, device="cuda")
-        args = (A.data_ptr(), B.data_ptr(), Cm.data_ptr(), None, M, N, K, A.shape[1], B.shape[1], N, ak, bk, 0, 1, s)
+        args = (A.data_ptr(), B.data_ptr(), Cm.data_ptr(), None, M, N, K, A.shape[1], B.shape[1], N, ak, bk, 0, 1, -1, s)
         for _ in range(3):
             L.check(lib.fb_sgemm(*args))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
