@@ -14,8 +14,9 @@ import typing as tp
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libfb_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", n) for n in ("fb_b200.cu", "plan.cuh", "kernels.cuh", "gemm_simt.cuh", "contract_tc.cuh", "common.cuh")]
+SOURCES = [os.path.join(HERE, "csrc", n) for n in ("fb_b200.cu", "plan.cuh", "kernels.cuh", "gemm_simt.cuh", "gemm_tc.cuh", "contract_tc.cuh", "common.cuh")]
 CONTRACT_TCGEN05, CONTRACT_SIMT = 0, 1
+MLP_TCGEN05, MLP_SIMT = 0, 1
 HEADER = os.path.join(ROOT, "include", "fb_b200.h")
 
 FB_ABI_VERSION = 1
@@ -39,14 +40,14 @@ PHASE_ALL = (1 << 10) - 1
 METRIC_KEYS = ("target_M", "M1", "F1", "B", "B_norm", "z_norm", "fb_loss", "fb_diag", "fb_offdiag", "orth_loss",
                "orth_loss_diag", "orth_loss_offdiag", "orth_linf", "orth_l2", "actor_loss", "q", "actor_logprob")
 METRIC_COUNT = 32
-OP_KINDS = ("gemm", "layernorm", "elementwise", "colsum", "adam", "gather", "loss", "memset", "contract")
+OP_KINDS = ("gemm", "layernorm", "elementwise", "colsum", "adam", "gather", "loss", "memset", "contract", "gemm_tc", "transpose")
 
 
 class fb_config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("batch", C.c_int32), ("global_batch", C.c_int32), ("row_offset", C.c_int32),
                 ("obs_dim", C.c_int32), ("action_dim", C.c_int32), ("z_dim", C.c_int32), ("goal_dim", C.c_int32),
                 ("hidden_dim", C.c_int32), ("feature_dim", C.c_int32), ("backward_hidden_dim", C.c_int32),
-                ("use_goal", C.c_int32), ("rng_device", C.c_int32), ("contract_mode", C.c_int32),
+                ("use_goal", C.c_int32), ("rng_device", C.c_int32), ("contract_mode", C.c_int32), ("mlp_mode", C.c_int32),
                 ("ortho_coef", C.c_float), ("mix_ratio", C.c_float),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
                 ("seed", C.c_uint64)]

@@ -8,6 +8,32 @@
 static int phase_index(uint32_t bit) { int i = 0; while ((1u << i) != bit) ++i; return i; }
 
 // ------------------------------------------------------------------------------------------------
+// TMA tensor maps for the tcgen05 contraction (driver entry point fetched through the runtime: no -lcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_tiled_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return FB_E_STATE;
+    fn = (EncodeTiledFn)p;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FB_OK : FB_E_STATE;
+}
+
+static int encode_operand_map(CUtensorMap* map, float* base, int rows, int cols) { return encode_tiled_map(map, base, rows, cols, cols, 64); }
+
+// ------------------------------------------------------------------------------------------------
 // op recorders
 // ------------------------------------------------------------------------------------------------
 struct Builder {
@@ -19,8 +45,69 @@ struct Builder {
     h->ops[phase].push_back(Op{std::move(fn), kind, flops, bytes});
   }
 
+  int rc = FB_OK;  // first error met while building (tensor-map encoding)
+
+  // can this problem run on the tensor cores (gemm_tc.cuh)?  TMA needs 16-byte aligned bases and leading dimensions
+  bool tc_ok(const GemmDesc& g) const {
+    if (h->cfg.mlp_mode != FB_MLP_TCGEN05 || !g.a_kmajor || (g.flags & GF_ATOMIC) || g.M < 32 || g.K < 8) return false;
+    if (!aligned16(g.A) || g.lda % 4 || (g.K2 && !aligned16(g.A2))) return false;
+    if (g.b_kmajor && (!aligned16(g.B) || g.ldb % 4 || (g.K2 && !aligned16(g.B2)))) return false;
+    return true;
+  }
+  // transposed copy of a [K][N] (mn-major) operand, refreshed at the start of the current phase
+  const float* transposed(const float* Bp, int K, int N, int ldb, int* ld_out) {
+    *ld_out = fb_round_up(K, 4);
+    for (auto& t : h->phase_transposes[phase])
+      if (t.in == Bp && t.rows == K && t.cols == N && t.ld_in == ldb) return t.out;
+    TransposeDesc t; memset(&t, 0, sizeof(t));
+    t.in = Bp; t.rows = K; t.cols = N; t.ld_in = ldb; t.ld_out = *ld_out;
+    t.out = (float*)ws_alloc(h, (size_t)N * t.ld_out * sizeof(float));
+    h->phase_transposes[phase].push_back(t);
+    return t.out;
+  }
+  void gemm_tc(const std::vector<GemmDesc>& g) {
+    std::vector<TcGemmDesc> v;
+    int work = 0;
+    double flops = 0.0, bytes = 0.0;
+    for (const GemmDesc& s : g) {
+      TcGemmDesc d; memset(&d, 0, sizeof(d));
+      d.C = s.C; d.bias = s.bias; d.mask = s.mask; d.M = s.M; d.N = s.N; d.K = s.K; d.K2 = s.K2;
+      d.ldc = s.ldc; d.ldmask = s.ldmask; d.flags = s.flags; d.bn = s.N > 64 ? 128 : 64;
+      d.tiles_m = fb_ceil_div(s.M, TC_BM); d.tiles_n = fb_ceil_div(s.N, d.bn);
+      d.work_begin = work; d.work_count = d.tiles_m * d.tiles_n; work += d.work_count;
+      const float *B1 = s.B, *B2 = s.B2;
+      int ldb = s.ldb, ldb2 = s.ldb;
+      if (!s.b_kmajor) {
+        B1 = transposed(s.B, s.K, s.N, s.ldb, &ldb);
+        if (s.K2) B2 = transposed(s.B2, s.K2, s.N, s.ldb, &ldb2);
+      }
+      if (h->ws_base && rc == FB_OK) {
+        rc = encode_tiled_map(&d.mapA, s.A, s.M, s.K, s.lda, TC_BM);
+        if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, B1, s.N, s.K, ldb, d.bn);
+        if (rc == FB_OK && s.K2) rc = encode_tiled_map(&d.mapA2, s.A2, s.M, s.K2, s.lda, TC_BM);
+        if (rc == FB_OK && s.K2) rc = encode_tiled_map(&d.mapB2, B2, s.N, s.K2, ldb2, d.bn);
+      }
+      const double k = (double)s.K + s.K2;
+      flops += 2.0 * s.M * (double)s.N * k;
+      bytes += 4.0 * ((double)s.M * k + (double)s.N * k + (double)s.M * s.N);
+      v.push_back(d);
+    }
+    const TcGemmDesc* dd = arena_put(h, v, d_arena);
+    const int n = (int)v.size();
+    h->uses_gemm_tc = true;
+    push([dd, n, work](cudaStream_t s) {
+      k_gemm_tc<<<work, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, n);
+      return cudaGetLastError();
+    }, FB_OPK_GEMM_TC, flops, bytes);
+  }
+
   void gemm(std::vector<GemmDesc> g) {
     if (g.empty()) return;
+    std::vector<GemmDesc> tc, simt;
+    for (auto& d : g) (tc_ok(d) ? tc : simt).push_back(d);
+    if (!tc.empty()) gemm_tc(tc);
+    if (simt.empty()) return;
+    g = std::move(simt);
     GroupLaunch gl = finalize_group(h, std::move(g), d_arena);
     push([gl](cudaStream_t s) {
       k_gemm_grouped<<<gl.ctas, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(gl.d_descs, gl.nprob);
@@ -144,30 +231,6 @@ static L2Desc b_l2(const BAct& b, int Z) {
 struct HeadAct { Mat h1, out; };
 
 // ------------------------------------------------------------------------------------------------
-// TMA tensor maps for the tcgen05 contraction (driver entry point fetched through the runtime: no -lcuda)
-// ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int encode_operand_map(CUtensorMap* map, float* base, int rows, int cols) {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return FB_E_STATE;
-    fn = (EncodeTiledFn)p;
-  }
-  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-  const cuuint32_t box[2] = {32u, 64u};
-  const cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? FB_OK : FB_E_STATE;
-}
-
-// ------------------------------------------------------------------------------------------------
 // the plan
 // ------------------------------------------------------------------------------------------------
 static int build_gather_params(const fb_replay_view& v, GatherParams& gp, const BatchLayout& L, int out_ld);
@@ -179,6 +242,7 @@ static int build_plan(fb_handle* h) {
   const int G = c.goal_dim;
   const bool use_goal = c.use_goal != 0;
   for (auto& v : h->ops) v.clear();
+  for (auto& v : h->phase_transposes) v.clear();
   h->views.clear();
   h->arena.clear();
   h->ws_off = 0;
@@ -611,6 +675,25 @@ static int build_plan(fb_handle* h) {
     b.push([mp](cudaStream_t s) { k_metric_final<<<1, 32, 0, s>>>(mp); return cudaGetLastError(); });
   }
 
+  // weight transposes of each phase go in front of its first launch (one grouped launch per phase)
+  for (int ph = 0; ph < FB_NUM_PHASES; ++ph) {
+    std::vector<TransposeDesc>& tv = h->phase_transposes[ph];
+    if (tv.empty()) continue;
+    int ctas = 0;
+    double bytes = 0.0;
+    for (auto& t : tv) {
+      t.cta_begin = ctas; t.ctas_x = fb_ceil_div(t.cols, 32); ctas += t.ctas_x * fb_ceil_div(t.rows, 32);
+      bytes += 8.0 * t.rows * (double)t.cols;
+    }
+    const TransposeDesc* dd = arena_put(h, tv, d_arena);
+    const int nt = (int)tv.size();
+    Op op{[dd, nt, ctas](cudaStream_t s) {
+            k_transpose_grouped<<<ctas, 256, 0, s>>>(dd, nt);
+            return cudaGetLastError();
+          }, FB_OPK_TRANSPOSE, 0.0, bytes};
+    h->ops[ph].insert(h->ops[ph].begin(), op);
+  }
+  if (b.rc != FB_OK) return b.rc;
   if (h->arena.size() > FB_DESC_ARENA_BYTES) return FB_E_STATE;
   h->ws_off = (h->ws_off + 255) / 256 * 256;
   return FB_OK;
@@ -766,6 +849,7 @@ int fb_bind(fb_handle* h, const fb_buffers* bufs, void* stream) {
   int rc = build_plan(h);
   if (rc != FB_OK) return rc;
   CK(cudaFuncSetAttribute(k_gemm_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  if (h->uses_gemm_tc) CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   if (h->contract_smem) CK(cudaFuncSetAttribute(k_contract_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->contract_smem));
   CK(cudaMemsetAsync(h->ws_base, 0, h->ws_bytes, s));
   CK(cudaMemcpyAsync(h->ws_base, h->arena.data(), h->arena.size(), cudaMemcpyHostToDevice, s));
@@ -1014,8 +1098,47 @@ int fb_replay_pack_episode(const fb_replay_view* view, float* d_rows_mut, int sl
 int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, int M, int N, int K, int lda, int ldb, int ldc,
              int a_kmajor, int b_kmajor, int relu, int splitk, int tile_cfg, void* stream) {
   if (!dA || !dB || !dC || M < 1 || N < 1 || K < 1) return FB_E_ARG;
-  if (tile_cfg > 2) return FB_E_ARG;
+  if (tile_cfg > 3) return FB_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (tile_cfg == 3) {  // tcgen05 3xTF32 kernel
+    if (!a_kmajor || splitk > 1 || !aligned16(dA) || lda % 4) return FB_E_UNSUPPORTED;
+    const float* Bp = dB;
+    int ldbp = ldb;
+    float* tmp = nullptr;
+    if (!b_kmajor) {
+      ldbp = fb_round_up(K, 4);
+      CK(cudaMallocAsync(&tmp, (size_t)N * ldbp * sizeof(float), s));
+      TransposeDesc t; memset(&t, 0, sizeof(t));
+      t.in = dB; t.out = tmp; t.rows = K; t.cols = N; t.ld_in = ldb; t.ld_out = ldbp; t.cta_begin = 0; t.ctas_x = fb_ceil_div(N, 32);
+      TransposeDesc* dt = nullptr;
+      CK(cudaMallocAsync(&dt, sizeof(t), s));
+      CK(cudaMemcpyAsync(dt, &t, sizeof(t), cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));
+      k_transpose_grouped<<<t.ctas_x * fb_ceil_div(K, 32), 256, 0, s>>>(dt, 1);
+      CK(cudaGetLastError());
+      CK(cudaFreeAsync(dt, s));
+      Bp = tmp;
+    } else if (!aligned16(dB) || ldb % 4) {
+      return FB_E_UNSUPPORTED;
+    }
+    TcGemmDesc d; memset(&d, 0, sizeof(d));
+    d.C = dC; d.bias = d_bias; d.M = M; d.N = N; d.K = K; d.ldc = ldc; d.flags = relu ? GF_RELU : 0; d.bn = N > 64 ? 128 : 64;
+    d.tiles_m = fb_ceil_div(M, TC_BM); d.tiles_n = fb_ceil_div(N, d.bn); d.work_begin = 0; d.work_count = d.tiles_m * d.tiles_n;
+    int rc = encode_tiled_map(&d.mapA, dA, M, K, lda, TC_BM);
+    if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, Bp, N, K, ldbp, d.bn);
+    if (rc != FB_OK) return rc;
+    TcGemmDesc* dd = nullptr;
+    CK(cudaMallocAsync(&dd, sizeof(d), s));
+    CK(cudaMemcpyAsync(dd, &d, sizeof(d), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    k_gemm_tc<<<d.work_count, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, 1);
+    CK(cudaGetLastError());
+    CK(cudaFreeAsync(dd, s));
+    if (tmp) CK(cudaFreeAsync(tmp, s));
+    CK(cudaStreamSynchronize(s));
+    return FB_OK;
+  }
   GemmDesc d = gemm_raw(dA, lda, a_kmajor, dB, ldb, b_kmajor, dC, ldc, M, N, K, d_bias, relu ? GF_RELU : 0, nullptr, 0);
   gemm_set_tile(d, tile_cfg >= 0 ? tile_cfg : ((M > 64 && N > 64) ? GEMM_CFG_BIG : GEMM_CFG_SMALL));
   if (splitk < 1) splitk = 1;

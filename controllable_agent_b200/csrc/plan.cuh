@@ -16,6 +16,7 @@
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
 #include "contract_tc.cuh"
+#include "gemm_tc.cuh"
 
 #define FB_NUM_PHASES 10
 #define FB_DESC_ARENA_BYTES (1u << 20)
@@ -71,6 +72,8 @@ struct fb_handle {
   std::map<uint32_t, cudaGraphExec_t> graphs;
   cudaStream_t capture_stream = nullptr;
   size_t contract_smem = 0;  // dynamic shared memory of k_contract_tc (0: SIMT contraction)
+  bool uses_gemm_tc = false;
+  std::vector<TransposeDesc> phase_transposes[FB_NUM_PHASES];  // weight transposes a phase needs before its first launch
   // fixed workspace objects
   DevScalars* d_sc = nullptr;
   double* d_acc = nullptr;
@@ -145,7 +148,7 @@ static Mat ws_mat(fb_handle* h, int rows, int cols, const char* name = nullptr) 
 }
 template <typename T>
 static T* arena_put(fb_handle* h, const std::vector<T>& v, char* d_arena) {
-  size_t off = (h->arena.size() + 15) / 16 * 16;
+  size_t off = (h->arena.size() + 127) / 128 * 128;  // tensor maps inside descriptors need 64-byte alignment
   h->arena.resize(off + v.size() * sizeof(T));
   memcpy(h->arena.data() + off, v.data(), v.size() * sizeof(T));
   return reinterpret_cast<T*>(d_arena + off);

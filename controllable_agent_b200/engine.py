@@ -30,6 +30,7 @@ class EngineConfig:
     use_goal: bool = False
     rng_device: bool = False
     contract_mode: int = L.CONTRACT_TCGEN05   # batch x batch contraction: tcgen05 3xTF32 (default) or fp32 SIMT
+    mlp_mode: int = L.MLP_TCGEN05             # wide Linear fwd / dX products: tcgen05 3xTF32 (default) or fp32 SIMT
     ortho_coef: float = 1.0
     mix_ratio: float = 0.5
     beta1: float = 0.9
@@ -58,7 +59,7 @@ class FBStepEngine:
                         row_offset=cfg.row_offset, obs_dim=cfg.obs_dim, action_dim=cfg.action_dim, z_dim=cfg.z_dim,
                         goal_dim=cfg.goal_dim, hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim,
                         backward_hidden_dim=cfg.backward_hidden_dim, use_goal=int(cfg.use_goal),
-                        rng_device=int(cfg.rng_device), contract_mode=int(cfg.contract_mode), ortho_coef=cfg.ortho_coef, mix_ratio=cfg.mix_ratio,
+                        rng_device=int(cfg.rng_device), contract_mode=int(cfg.contract_mode), mlp_mode=int(cfg.mlp_mode), ortho_coef=cfg.ortho_coef, mix_ratio=cfg.mix_ratio,
                         beta1=cfg.beta1, beta2=cfg.beta2, adam_eps=cfg.adam_eps, seed=cfg.seed)
         h = C.c_void_p()
         L.check(self.lib.fb_create(C.byref(c), C.byref(h)), "fb_create")

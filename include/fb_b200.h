@@ -44,6 +44,7 @@ enum {
 };
 
 enum { FB_CONTRACT_TCGEN05 = 0, FB_CONTRACT_SIMT = 1 };
+enum { FB_MLP_TCGEN05 = 0, FB_MLP_SIMT = 1 };
 
 /* nets, in the order their flat segments are described */
 enum { FB_NET_FORWARD = 0, FB_NET_BACKWARD = 1, FB_NET_ACTOR = 2 };
@@ -84,6 +85,9 @@ typedef struct fb_config {
                                   (Philox) inside FB_PHASE_SAMPLE; 0: the caller provides them */
   int32_t contract_mode;       /* batch x batch contraction + loss of FB_PHASE_FB_LOSS: FB_CONTRACT_TCGEN05 (tensor cores,
                                   3xTF32, z_dim <= 128) or FB_CONTRACT_SIMT (fp32 CUDA cores, materialised matrices) */
+  int32_t mlp_mode;            /* wide nn.Linear forward / dX products: FB_MLP_TCGEN05 (tensor cores, 3xTF32, where TMA can
+                                  address the operands; the rest and all dW products stay on the fp32 SIMT kernel) or
+                                  FB_MLP_SIMT (every product on fp32 CUDA cores) */
   float ortho_coef, mix_ratio;
   float beta1, beta2, adam_eps; /* torch.optim.Adam defaults 0.9 / 0.999 / 1e-8 */
   uint64_t seed;               /* Philox seed for rng_device */
@@ -174,7 +178,7 @@ int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream);
 int fb_launch_count(fb_handle* h, uint32_t phase_mask);
 /* kinds of launch reported by fb_profile_ops */
 enum { FB_OPK_GEMM = 0, FB_OPK_LAYERNORM, FB_OPK_ELEMENTWISE, FB_OPK_COLSUM, FB_OPK_ADAM, FB_OPK_GATHER, FB_OPK_LOSS,
-       FB_OPK_MEMSET, FB_OPK_CONTRACT };
+       FB_OPK_MEMSET, FB_OPK_CONTRACT, FB_OPK_GEMM_TC, FB_OPK_TRANSPOSE };
 /* run the launches of `phase_mask` eagerly `reps` times with a CUDA event between consecutive launches (on `stream`) and
  * report, per launch: mean duration (ms), kind (FB_OPK_*), algorithmic FLOPs and algorithmic bytes.  Returns the number
  * of launches (<= cap) or a negative error.  Synchronises.  Executes the step for real (parameters move). */
@@ -213,7 +217,8 @@ int fb_replay_pack_episode(const fb_replay_view* view, float* d_rows_mut, int sl
                            const float* d_obs, const float* d_action, const float* d_reward, const float* d_discount,
                            const float* d_goal, const float* d_extra, void* stream);
 /* C[M,N] (+)= op(A)·op(B)^T with the grouped SIMT SGEMM used by the plan (single problem).  tile_cfg: -1 automatic,
- * 0 = 128x128, 1 = 64x64, 2 = 128x64 CTA tile.  splitk > 1 accumulates into C with atomics (C must be zeroed). */
+ * 0 = 128x128, 1 = 64x64, 2 = 128x64 CTA tile, 3 = the tcgen05 3xTF32 kernel (a_kmajor = 1, 16-byte aligned operands,
+ * splitk = 1; synchronises).  splitk > 1 accumulates into C with atomics (C must be zeroed). */
 int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, int M, int N, int K, int lda, int ldb,
              int ldc, int a_kmajor, int b_kmajor, int relu, int splitk, int tile_cfg, void* stream);
 /* FMA-chain microbenchmark: returns measured fp32 TFLOP/s of the CUDA cores (synchronises) */

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def _create(L, lib, d, batch=64, **kw):
     c = L.fb_config(abi_version=L.FB_ABI_VERSION, batch=batch, global_batch=kw.get("global_batch", batch), row_offset=kw.get("row_offset", 0),
                     obs_dim=d.obs_dim, action_dim=d.action_dim, z_dim=d.z_dim, goal_dim=d.goal_dim, hidden_dim=d.hidden_dim,
-                    feature_dim=d.feature_dim, backward_hidden_dim=d.backward_hidden_dim, use_goal=kw.get("use_goal", 0), rng_device=0, contract_mode=kw.get("contract_mode", 0),
+                    feature_dim=d.feature_dim, backward_hidden_dim=d.backward_hidden_dim, use_goal=kw.get("use_goal", 0), rng_device=0, contract_mode=kw.get("contract_mode", 0), mlp_mode=kw.get("mlp_mode", 0),
                     ortho_coef=1.0, mix_ratio=0.5, beta1=0.9, beta2=0.999, adam_eps=1e-8, seed=0)
     h = C.c_void_p()
     return lib.fb_create(C.byref(c), C.byref(h)), h
