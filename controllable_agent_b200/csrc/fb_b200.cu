@@ -47,50 +47,65 @@ struct Builder {
 
   int rc = FB_OK;  // first error met while building (tensor-map encoding)
 
-  // can this problem run on the tensor cores (gemm_tc.cuh)?  TMA needs 16-byte aligned bases and leading dimensions
+  // can this problem run on the tensor cores (gemm_tc.cuh)?  Operands TMA cannot address directly are staged (see stage_operand)
   bool tc_ok(const GemmDesc& g) const {
-    if (h->cfg.mlp_mode != FB_MLP_TCGEN05 || !g.a_kmajor || (g.flags & GF_ATOMIC) || g.M < 32 || g.K < 8) return false;
-    if (!aligned16(g.A) || g.lda % 4 || (g.K2 && !aligned16(g.A2))) return false;
-    if (g.b_kmajor && (!aligned16(g.B) || g.ldb % 4 || (g.K2 && !aligned16(g.B2)))) return false;
+    if (h->cfg.mlp_mode != FB_MLP_TCGEN05 || (g.flags & GF_SHARED_C) || g.M < 8 || g.K < 8) return false;
     return true;
   }
-  // transposed copy of a [K][N] (mn-major) operand, refreshed at the start of the current phase
-  const float* transposed(const float* Bp, int K, int N, int ldb, int* ld_out) {
+  // K-major, TMA-addressable view of an operand: the operand itself when it already is one, otherwise a staged copy
+  // (transposed for mn-major operands) produced by the transpose launch that precedes the GEMM launch
+  const float* stage_operand(std::vector<TransposeDesc>& pending, const float* p, int kmajor, int rows, int K, int ld, int* ld_out) {
+    if (kmajor && aligned16(p) && ld % 4 == 0) { *ld_out = ld; return p; }
     *ld_out = fb_round_up(K, 4);
-    for (auto& t : h->phase_transposes[phase])
-      if (t.in == Bp && t.rows == K && t.cols == N && t.ld_in == ldb) return t.out;
     TransposeDesc t; memset(&t, 0, sizeof(t));
-    t.in = Bp; t.rows = K; t.cols = N; t.ld_in = ldb; t.ld_out = *ld_out;
-    t.out = (float*)ws_alloc(h, (size_t)N * t.ld_out * sizeof(float));
-    h->phase_transposes[phase].push_back(t);
+    t.in = p; t.ld_in = ld; t.ld_out = *ld_out; t.transpose = kmajor ? 0 : 1;
+    if (kmajor) { t.rows = rows; t.cols = K; } else { t.rows = K; t.cols = rows; }   // mn-major storage is [K][rows]
+    for (auto& q : pending)
+      if (q.in == t.in && q.rows == t.rows && q.cols == t.cols && q.ld_in == t.ld_in && q.transpose == t.transpose) return q.out;
+    t.out = (float*)ws_alloc(h, (size_t)rows * t.ld_out * sizeof(float));
+    pending.push_back(t);
     return t.out;
   }
   void gemm_tc(const std::vector<GemmDesc>& g) {
     std::vector<TcGemmDesc> v;
+    std::vector<TransposeDesc> pending;
     int work = 0;
     double flops = 0.0, bytes = 0.0;
     for (const GemmDesc& s : g) {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
       d.C = s.C; d.bias = s.bias; d.mask = s.mask; d.M = s.M; d.N = s.N; d.K = s.K; d.K2 = s.K2;
-      d.ldc = s.ldc; d.ldmask = s.ldmask; d.flags = s.flags; d.bn = s.N > 64 ? 128 : 64;
+      d.ldc = s.ldc; d.ldmask = s.ldmask; d.flags = s.flags & (GF_RELU | GF_MASK_RELU | GF_MASK_TANH); d.bn = s.N > 64 ? 128 : 64;
       d.tiles_m = fb_ceil_div(s.M, TC_BM); d.tiles_n = fb_ceil_div(s.N, d.bn);
       d.work_begin = work; d.work_count = d.tiles_m * d.tiles_n; work += d.work_count;
-      const float *B1 = s.B, *B2 = s.B2;
-      int ldb = s.ldb, ldb2 = s.ldb;
-      if (!s.b_kmajor) {
-        B1 = transposed(s.B, s.K, s.N, s.ldb, &ldb);
-        if (s.K2) B2 = transposed(s.B2, s.K2, s.N, s.ldb, &ldb2);
-      }
+      int lda = 0, ldb = 0, lda2 = 0, ldb2 = 0;
+      const float* A1 = stage_operand(pending, s.A, s.a_kmajor, s.M, s.K, s.lda, &lda);
+      const float* B1 = stage_operand(pending, s.B, s.b_kmajor, s.N, s.K, s.ldb, &ldb);
+      const float* A2 = s.K2 ? stage_operand(pending, s.A2, s.a_kmajor, s.M, s.K2, s.lda, &lda2) : nullptr;
+      const float* B2 = s.K2 ? stage_operand(pending, s.B2, s.b_kmajor, s.N, s.K2, s.ldb, &ldb2) : nullptr;
       if (h->ws_base && rc == FB_OK) {
-        rc = encode_tiled_map(&d.mapA, s.A, s.M, s.K, s.lda, TC_BM);
+        rc = encode_tiled_map(&d.mapA, A1, s.M, s.K, lda, TC_BM);
         if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, B1, s.N, s.K, ldb, d.bn);
-        if (rc == FB_OK && s.K2) rc = encode_tiled_map(&d.mapA2, s.A2, s.M, s.K2, s.lda, TC_BM);
+        if (rc == FB_OK && s.K2) rc = encode_tiled_map(&d.mapA2, A2, s.M, s.K2, lda2, TC_BM);
         if (rc == FB_OK && s.K2) rc = encode_tiled_map(&d.mapB2, B2, s.N, s.K2, ldb2, d.bn);
       }
       const double k = (double)s.K + s.K2;
       flops += 2.0 * s.M * (double)s.N * k;
       bytes += 4.0 * ((double)s.M * k + (double)s.N * k + (double)s.M * s.N);
       v.push_back(d);
+    }
+    if (!pending.empty()) {
+      int ctas = 0;
+      double tbytes = 0.0;
+      for (auto& t : pending) {
+        t.cta_begin = ctas; t.ctas_x = fb_ceil_div(t.cols, 32); ctas += t.ctas_x * fb_ceil_div(t.rows, 32);
+        tbytes += 8.0 * t.rows * (double)t.cols;
+      }
+      const TransposeDesc* td = arena_put(h, pending, d_arena);
+      const int nt = (int)pending.size();
+      push([td, nt, ctas](cudaStream_t s) {
+        k_transpose_grouped<<<ctas, 256, 0, s>>>(td, nt);
+        return cudaGetLastError();
+      }, FB_OPK_TRANSPOSE, 0.0, tbytes);
     }
     const TcGemmDesc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
@@ -242,7 +257,6 @@ static int build_plan(fb_handle* h) {
   const int G = c.goal_dim;
   const bool use_goal = c.use_goal != 0;
   for (auto& v : h->ops) v.clear();
-  for (auto& v : h->phase_transposes) v.clear();
   h->views.clear();
   h->arena.clear();
   h->ws_off = 0;
@@ -545,7 +559,7 @@ static int build_plan(fb_handle* h) {
       return cudaGetLastError();
     });
     auto inner = [&](const Mat& Gm, const Mat& Yall, const Mat& C) {  // C[B, Z] += Gm[B, n] . Yall[n, Z]
-      GemmDesc d = gemm_raw(Gm.p, Gm.ld, 1, Yall.p, Yall.ld, 0, C.p, C.ld, Gm.rows, Z, n, nullptr, GF_ATOMIC, nullptr, 0);
+      GemmDesc d = gemm_raw(Gm.p, Gm.ld, 1, Yall.p, Yall.ld, 0, C.p, C.ld, Gm.rows, Z, n, nullptr, GF_ATOMIC | GF_SHARED_C, nullptr, 0);
       return d;
     };
     b.gemm({inner(M1, Bg, dF1), inner(M2, Bg, dF2), inner(Mt1, F1g, dB), inner(Mt2, F2g, dB), inner(Cov, Bg, dB)});
@@ -675,24 +689,6 @@ static int build_plan(fb_handle* h) {
     b.push([mp](cudaStream_t s) { k_metric_final<<<1, 32, 0, s>>>(mp); return cudaGetLastError(); });
   }
 
-  // weight transposes of each phase go in front of its first launch (one grouped launch per phase)
-  for (int ph = 0; ph < FB_NUM_PHASES; ++ph) {
-    std::vector<TransposeDesc>& tv = h->phase_transposes[ph];
-    if (tv.empty()) continue;
-    int ctas = 0;
-    double bytes = 0.0;
-    for (auto& t : tv) {
-      t.cta_begin = ctas; t.ctas_x = fb_ceil_div(t.cols, 32); ctas += t.ctas_x * fb_ceil_div(t.rows, 32);
-      bytes += 8.0 * t.rows * (double)t.cols;
-    }
-    const TransposeDesc* dd = arena_put(h, tv, d_arena);
-    const int nt = (int)tv.size();
-    Op op{[dd, nt, ctas](cudaStream_t s) {
-            k_transpose_grouped<<<ctas, 256, 0, s>>>(dd, nt);
-            return cudaGetLastError();
-          }, FB_OPK_TRANSPOSE, 0.0, bytes};
-    h->ops[ph].insert(h->ops[ph].begin(), op);
-  }
   if (b.rc != FB_OK) return b.rc;
   if (h->arena.size() > FB_DESC_ARENA_BYTES) return FB_E_STATE;
   h->ws_off = (h->ws_off + 255) / 256 * 256;
@@ -1109,7 +1105,7 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
       ldbp = fb_round_up(K, 4);
       CK(cudaMallocAsync(&tmp, (size_t)N * ldbp * sizeof(float), s));
       TransposeDesc t; memset(&t, 0, sizeof(t));
-      t.in = dB; t.out = tmp; t.rows = K; t.cols = N; t.ld_in = ldb; t.ld_out = ldbp; t.cta_begin = 0; t.ctas_x = fb_ceil_div(N, 32);
+      t.in = dB; t.out = tmp; t.rows = K; t.cols = N; t.ld_in = ldb; t.ld_out = ldbp; t.transpose = 1; t.cta_begin = 0; t.ctas_x = fb_ceil_div(N, 32);
       TransposeDesc* dt = nullptr;
       CK(cudaMallocAsync(&dt, sizeof(t), s));
       CK(cudaMemcpyAsync(dt, &t, sizeof(t), cudaMemcpyHostToDevice, s));

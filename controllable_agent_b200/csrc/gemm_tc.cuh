@@ -2,17 +2,22 @@
 // MLP stacks:    C[M,N] = epi( A[M,K] . B[N,K]^T  (+ A2[M,K2] . B2[N,K2]^T)  + bias )      A, B row-major, K contiguous
 //
 //   forward  Y  = X . W^T   : A = X,  B = W              (nn.Linear, fb_modules.py:76)
-//   backward dX = dY . W    : A = dY, B = W^T (a transposed copy of the weight kept by the plan)
+//   backward dX = dY . W    : A = dY, B = W^T          (transposed copy staged by the plan right before the launch)
+//   backward dW = dY^T . X  : A = dY^T, B = X^T        (both staged transposed: K = batch becomes the contiguous dimension)
 //
 // Why tensor cores here: the parity gate is 1e-3 on gradients against an fp32 reference, which plain TF32 (10-bit
 // mantissa) cannot hold, but the split  x = hi + lo  (hi = x with the low 13 mantissa bits cleared = exactly what
 // kind::tf32 reads, lo = x - hi, exact) with three MMA chains  hi.hi + lo.hi + hi.lo  reproduces fp32 products to ~2^-21
 // and still runs several times faster than the CUDA-core FFMA loop.  The fp32 SIMT kernel (gemm_simt.cuh) remains for the
-// operands TMA cannot address (leading dimension not a multiple of 4 floats) and for the dW = dY^T . X products.
+// tiny / shared-output products.  Operands TMA cannot address directly (mn-major, or a leading dimension that is not a
+// multiple of 4 floats) are first staged into an aligned K-major copy by k_transpose_grouped.
 //
 // CTA = one 128 x BN output tile (BN = 128 or 64), 6 warps:
 //   warp 0      TMA producer      raw fp32 tiles (BK = 32 floats = one 128-byte swizzle atom) -> smem ring, 3 stages
-//   warp 1      MMA issuer        one thread: 3 chains x 4 tcgen05.mma (M128 x BN x K8, kind::tf32) per stage, accumulator in TMEM
+//   warp 1      MMA issuer        one thread: 3 chains x 4 tcgen05.mma (M128 x BN x K8, kind::tf32) per stage, accumulators in TMEM
+//                                 (the tensor core's fp32 accumulate truncates, a bias that grows with the number of sequential
+//                                 accumulations: the hi.hi chain is therefore spread round-robin over three accumulators and the
+//                                 two small correction chains go to a fourth; the epilogue adds the four in IEEE fp32)
 //   warps 2..5  lo-part builders  lo = x - trunc_tf32(x) for the landed A and B tiles (elementwise, layout agnostic),
 //                                 then the epilogue: tcgen05.ld, bias / ReLU / ReLU-mask / tanh'-mask, global store
 #pragma once
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_smem)), "r"(128) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_smem)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -165,9 +170,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
         for (int chain = 0; chain < 3; ++chain) {   // (A raw, B raw), (A lo, B raw), (A raw, B lo)
           const uint32_t a = st + (chain == 1 ? 32768u : 0u);
           const uint32_t b = st + 16384u + (chain == 2 ? 32768u : 0u);
+          // accumulators: columns [j*bn, (j+1)*bn): j = kb % 3 for hi.hi, j = 3 for the two correction chains
+          const uint32_t acc = tmem_base + (uint32_t)(chain == 0 ? (kb % 3) : 3) * (uint32_t)bn;
 #pragma unroll
-          for (int ks = 0; ks < TC_BK / 8; ++ks)
-            tc_mma_tf32(tmem_base, tc_umma_desc(a + ks * 32u), tc_umma_desc(b + ks * 32u), idesc, (kb | chain | ks) != 0 ? 1u : 0u);
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const bool first = (ks == 0) && (chain == 0 ? kb < 3 : (kb == 0 && chain == 1));
+            tc_mma_tf32(acc, tc_umma_desc(a + ks * 32u), tc_umma_desc(b + ks * 32u), idesc, first ? 0u : 1u);
+          }
         }
         tc_mma_commit(&bar_empty[s]);
       }
@@ -207,10 +216,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
     const float* __restrict__ mask = d->mask;
     float* __restrict__ C = d->C;
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+    const int n_hh = nk < 3 ? nk : 3;   // hi.hi accumulators that were written
     for (int cb = 0; cb < bn; cb += 16) {
-      float v[16];
-      tc_tmem_ld16(lane_addr + (uint32_t)cb, v);
+      float v[16], u[16];
+      tc_tmem_ld16(lane_addr + (uint32_t)(3 * bn + cb), v);   // correction chains first (smallest terms)
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int a = n_hh - 1; a >= 0; --a) {
+        tc_tmem_ld16(lane_addr + (uint32_t)(a * bn + cb), u);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += u[j];
+      }
       const int col0 = n0 + cb;
       if (!row_ok || col0 >= N) continue;
 #pragma unroll
@@ -239,12 +255,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
-// out[c][r] = in[r][c]  (transposed weight copies for the dX products); grid (ceil(cols/32), ceil(rows/32)), block (32, 8)
-struct TransposeDesc { const float* in; float* out; int rows, cols, ld_in, ld_out, cta_begin, ctas_x; };
+// operand staging for the tensor-core GEMM: out = in^T (transpose = 1) or an aligned copy of in (transpose = 0), with a
+// 16-byte aligned base and leading dimension so that TMA can address it.  32 x 32 tiles through shared memory.
+struct TransposeDesc { const float* in; float* out; int rows, cols, ld_in, ld_out, transpose, cta_begin, ctas_x; };
 
 __global__ void __launch_bounds__(256) k_transpose_grouped(const TransposeDesc* __restrict__ descs, int nprob) {
   __shared__ float tile[32][33];
@@ -254,6 +271,13 @@ __global__ void __launch_bounds__(256) k_transpose_grouped(const TransposeDesc* 
   const int local = blockIdx.x - d.cta_begin;
   const int bx = local % d.ctas_x, by = local / d.ctas_x;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (!d.transpose) {
+    for (int j = ty; j < 32; j += 8) {
+      const int r = by * 32 + j, c = bx * 32 + tx;
+      if (r < d.rows && c < d.cols) d.out[(size_t)r * d.ld_out + c] = d.in[(size_t)r * d.ld_in + c];
+    }
+    return;
+  }
   for (int j = ty; j < 32; j += 8) {
     const int r = by * 32 + j, c = bx * 32 + tx;
     tile[j][tx] = (r < d.rows && c < d.cols) ? d.in[(size_t)r * d.ld_in + c] : 0.f;

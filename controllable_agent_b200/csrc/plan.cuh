@@ -73,7 +73,6 @@ struct fb_handle {
   cudaStream_t capture_stream = nullptr;
   size_t contract_smem = 0;  // dynamic shared memory of k_contract_tc (0: SIMT contraction)
   bool uses_gemm_tc = false;
-  std::vector<TransposeDesc> phase_transposes[FB_NUM_PHASES];  // weight transposes a phase needs before its first launch
   // fixed workspace objects
   DevScalars* d_sc = nullptr;
   double* d_acc = nullptr;
