@@ -63,6 +63,9 @@ struct Builder {
     for (auto& q : pending)
       if (q.in == t.in && q.rows == t.rows && q.cols == t.cols && q.ld_in == t.ld_in && q.transpose == t.transpose) return q.out;
     t.out = (float*)ws_alloc(h, (size_t)rows * t.ld_out * sizeof(float));
+    if (getenv("FB_DEBUG_PLAN"))
+      fprintf(stderr, "[fb plan %s] phase %d stage in=%p rows=%d cols=%d ld_in=%d T=%d -> off=%zu bytes=%zu\n", h->ws_base ? "real" : "dry",
+              phase, (const void*)p, t.rows, t.cols, t.ld_in, t.transpose, (size_t)((char*)t.out - h->ws_base), (size_t)rows * t.ld_out * 4);
     pending.push_back(t);
     return t.out;
   }
@@ -692,6 +695,8 @@ static int build_plan(fb_handle* h) {
   if (b.rc != FB_OK) return b.rc;
   if (h->arena.size() > FB_DESC_ARENA_BYTES) return FB_E_STATE;
   h->ws_off = (h->ws_off + 255) / 256 * 256;
+  if (getenv("FB_DEBUG_PLAN")) fprintf(stderr, "[fb plan %s] workspace %zu bytes, arena %zu bytes\n", h->ws_base ? "real" : "dry", h->ws_off, h->arena.size());
+  if (h->ws_base && h->ws_off > h->ws_bytes) return FB_E_STATE;  // the sizing pass and the binding pass must agree
   return FB_OK;
 }
 
@@ -776,9 +781,16 @@ int fb_create(const fb_config* cfg, fb_handle** out) {
   memset(&h->bufs, 0, sizeof(h->bufs));
   memset(&h->replay, 0, sizeof(h->replay));
   build_layout(h);
-  // dry run of the plan against a null workspace to size it
+  // sizing pass: build the plan against fake, never dereferenced, mutually distinct base addresses (the plan de-duplicates
+  // staged operands by address, so the caller's segments must not alias each other here any more than they will later)
   h->ws_base = nullptr;
+  {
+    float** seg[] = {&h->bufs.d_param_fb, &h->bufs.d_grad_fb, &h->bufs.d_m_fb, &h->bufs.d_v_fb, &h->bufs.d_target_fb,
+                     &h->bufs.d_param_actor, &h->bufs.d_grad_actor, &h->bufs.d_m_actor, &h->bufs.d_v_actor};
+    for (int i = 0; i < 9; ++i) *seg[i] = reinterpret_cast<float*>((uintptr_t)(i + 1) << 40);
+  }
   int rc = build_plan(h);
+  memset(&h->bufs, 0, sizeof(h->bufs));
   if (rc != FB_OK) { delete h; return rc; }
   h->ws_bytes = h->ws_off;
   for (auto& v : h->ops) v.clear();

@@ -212,9 +212,8 @@ def test_agent_device_rng_step_statistics_and_api():
         obs, nobs = e.view("actor_in_o")[B:], e.view("actor_in_o")[:B]
         # every gathered (obs, next_obs) pair must be consecutive rows of one stored episode
         rows = buf._rows[:9, :, :O_].reshape(-1, O_)
-        d = torch.cdist(obs, rows)
-        idx = d.argmin(1)
-        assert float(d.min(1).values.max()) == 0.0
+        idx = torch.cdist(obs.double(), rows.double()).argmin(1)
+        assert torch.equal(rows[idx], obs)       # gathered rows are bit-exact copies of stored rows
         assert torch.equal(rows[idx + 1], nobs) and bool(((idx % 31) < 30).all())
     assert not torch.equal(seen_z[0], seen_z[1])       # fresh draws each step
     assert not torch.equal(agent.forward_net.F1[0].weight, p0) and not torch.equal(agent.forward_target_net.F1[0].weight, t0)
