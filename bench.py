@@ -47,6 +47,7 @@ def parse() -> argparse.Namespace:
     p.add_argument("--cpu-steps", type=int, default=12, help="timed steps of the cpu_baseline leg (rank 0, N=1)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--mlp-mode", default="tcgen05", choices=["tcgen05", "simt"], help="wide Linear products: tensor cores (3xTF32) or fp32 CUDA cores")
     return p.parse_args()
 
 
@@ -207,7 +208,7 @@ def run_ours(a: argparse.Namespace) -> None:
     common = dict(obs_type="states", obs_shape=(a.obs_dim,), action_shape=(a.action_dim,), device=str(dev), num_expl_steps=0,
                   update_encoder=True, goal_space=None, update_every_steps=1, batch_size=a.batch, z_dim=a.z_dim,
                   use_cuda_graph=not a.no_graph)
-    agent = FBDDPGAgent(use_tb=False, use_wandb=False, use_hiplog=False, rng_mode="device", **common)
+    agent = FBDDPGAgent(use_tb=False, use_wandb=False, use_hiplog=False, rng_mode="device", mlp_mode=a.mlp_mode, **common)
     eng = agent.engine
 
     def barrier() -> None:
@@ -269,26 +270,52 @@ def run_ours(a: argparse.Namespace) -> None:
             k = by_kind.setdefault(o["kind"], {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
             k["ms"] += o["ms"]; k["launches"] += 1; k["flops"] += o["flops"]; k["bytes"] += o["bytes"]
         roofline = None
-        if "gemm" in by_kind:
+        total_ms = sum(v["ms"] for v in by_kind.values()) or 1.0
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        if "gemm_tc" in by_kind:
+            # dominant kernel: the tcgen05 3xTF32 grouped GEMM.  Tensor roofline for fp32-grade products on this kernel:
+            # measured dense bf16 rate / 2 (kind::tf32 runs at half the bf16 rate) / 3 (three MMA chains per product).
+            bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
+            src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+            gk = by_kind["gemm_tc"]
+            achieved = gk["flops"] / (gk["ms"] * 1e-3) / 1e12
+            peak = bf16 / 6.0
+            roofline = {"kernel": "k_gemm_tc (tcgen05 kind::tf32, 3xTF32 split, TMA + TMEM): all wide nn.Linear forward / dX / dW products",
+                        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                        "peak_source": f"{src} = {bf16:.1f} TFLOP/s dense bf16; /2 for tf32, /3 for the three chains of an fp32-grade product "
+                                       "(achieved counts each algorithmic fp32 FLOP once)",
+                        "achieved_tensor_tflops_tf32": 3.0 * achieved, "frac_of_tf32_peak": 3.0 * achieved / (bf16 / 2.0),
+                        "launches_per_step": gk["launches"], "avg_launch_us": 1e3 * gk["ms"] / gk["launches"],
+                        "algorithmic_gflop_per_step": gk["flops"] / 1e9, "share_of_step": gk["ms"] / total_ms}
+        elif "gemm" in by_kind:
             import ctypes as C
             peak = C.c_double()
             L.check(L.load().fb_fp32_peak_tflops(C.byref(peak), torch.cuda.current_stream(dev).cuda_stream))
             gk = by_kind["gemm"]
             achieved = gk["flops"] / (gk["ms"] * 1e-3) / 1e12
-            total_ms = sum(v["ms"] for v in by_kind.values())
             roofline = {"kernel": "k_gemm_grouped (fp32 SIMT grouped SGEMM: all MLP forward/backward layers)", "bound": "fp32_fma",
                         "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
                         "peak_source": "FMA-chain microbenchmark (fb_fp32_peak_tflops) measured in this run; MEASURED_PEAKS.json has "
                                        "no fp32 CUDA-core figure (nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
                         "launches_per_step": gk["launches"], "avg_launch_us": 1e3 * gk["ms"] / gk["launches"],
                         "algorithmic_gflop_per_step": gk["flops"] / 1e9, "share_of_step": gk["ms"] / total_ms}
+        if roofline is not None and "adam" in by_kind:
+            ak = by_kind["adam"]
+            hbm = float(peaks.get("hbm_gbs", 6650.0))
+            roofline["secondary"] = {"kernel": "k_adam (Adam + target soft update + gradient clear)", "bound": "hbm",
+                                     "achieved": ak["bytes"] / (ak["ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                     "frac": ak["bytes"] / (ak["ms"] * 1e-3) / 1e9 / hbm}
         cpu = None
         if world == 1 and not a.no_cpu_baseline:
             cpu = cpu_reference_steps_per_sec(a, a.cpu_steps, 2, budget_s=40.0)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")}
         cfg = workload(a)
         cfg.update({"parallelism": f"dp{world}" if world > 1 else "single GPU", "per_gpu_batch": Bl, "cuda_graph": not a.no_graph,
-                    "rng": "device Philox inside the step graph",
+                    "rng": "device Philox inside the step graph", "mlp_mode": a.mlp_mode,
                     "l2": "inputs exceed L2: each step gathers random rows of a replay far larger than the 126 MB L2; weights and "
                           "activations are re-used step to step exactly as in training"})
         line = {"metric": METRIC, "value": a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,

@@ -101,6 +101,8 @@ class FBDDPGAgentConfig:
     rng_mode: str = "device"     # "device": Philox draws inside the step graph; "reference": numpy/torch draws in the
     #                              reference's order (Appendix B of SURVEY.md), uploaded per step
     use_cuda_graph: bool = True
+    mlp_mode: str = "tcgen05"   # wide Linear products: "tcgen05" (3xTF32 tensor cores) or "simt" (fp32 CUDA cores)
+    contract_mode: str = "tcgen05"  # batch x batch contraction: "tcgen05" or "simt"
 
 
 def register_hydra() -> None:
@@ -159,7 +161,9 @@ class FBDDPGAgent:
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
-            mix_ratio=cfg.mix_ratio, seed=seed, global_batch=cfg.batch_size, row_offset=self.rank * local), device)
+            mix_ratio=cfg.mix_ratio, seed=seed, global_batch=cfg.batch_size, row_offset=self.rank * local,
+            mlp_mode=L.MLP_SIMT if cfg.mlp_mode == "simt" else L.MLP_TCGEN05,
+            contract_mode=L.CONTRACT_SIMT if cfg.contract_mode == "simt" else L.CONTRACT_TCGEN05), device)
 
         # networks: constructed on the CPU in the reference's order (Actor, ForwardMap, BackwardMap, BackwardMap target,
         # ForwardMap target — fb_ddpg.py:117-139) so that the torch CPU generator is consumed identically, then moved
