@@ -42,7 +42,7 @@ struct Builder {
   int phase = 0;
   void set_phase(uint32_t bit) { phase = phase_index(bit); }
   void push(OpFn fn, int kind = FB_OPK_ELEMENTWISE, double flops = 0.0, double bytes = 0.0) {
-    h->ops[phase].push_back(Op{std::move(fn), kind, flops, bytes});
+    h->ops[phase].push_back(Op{std::move(fn), kind, flops, bytes, 0, 0});
   }
 
   int rc = FB_OK;  // first error met while building (tensor-map encoding)
@@ -54,37 +54,64 @@ struct Builder {
   }
   // K-major, TMA-addressable view of an operand: the operand itself when it already is one, otherwise a staged copy
   // (transposed for mn-major operands) produced by the transpose launch that precedes the GEMM launch
-  const float* stage_operand(std::vector<TransposeDesc>& pending, const float* p, int kmajor, int rows, int K, int ld, int* ld_out) {
+  // is the source of this operand final when the current phase starts?  (weights and targets: always; workspace buffers
+  // written by the forward phases: for the loss / backward phases)
+  bool is_early(const float* p) const {
+    const fb_buffers& bf = h->bufs;
+    auto in = [&](const float* base, size_t n) { return base && p >= base && p < base + n; };
+    if (in(bf.d_param_fb, h->seg_fb.size) || in(bf.d_target_fb, h->seg_fb.size) || in(bf.d_param_actor, h->seg_actor.size)) return true;
+    const bool backward_phase = phase == phase_index(FB_PHASE_FB_LOSS) || phase == phase_index(FB_PHASE_FB_BWD) ||
+                                phase == phase_index(FB_PHASE_ACTOR_BWD);
+    const char* c = reinterpret_cast<const char*>(p);
+    return backward_phase && c >= h->ws_base && c < h->ws_base + h->ws_fwd_end;
+  }
+  const float* stage_operand(std::vector<TransposeDesc>& pending, bool* used_early, const float* p, int kmajor, int rows, int K, int ld,
+                             int* ld_out) {
     if (kmajor && aligned16(p) && ld % 4 == 0) { *ld_out = ld; return p; }
     *ld_out = fb_round_up(K, 4);
     TransposeDesc t; memset(&t, 0, sizeof(t));
     t.in = p; t.ld_in = ld; t.ld_out = *ld_out; t.transpose = kmajor ? 0 : 1;
     if (kmajor) { t.rows = rows; t.cols = K; } else { t.rows = K; t.cols = rows; }   // mn-major storage is [K][rows]
-    for (auto& q : pending)
+    const bool early = is_early(p);
+    std::vector<TransposeDesc>& list = early ? h->early_stage[phase] : pending;
+    if (early) *used_early = true;
+    for (auto& q : list)
       if (q.in == t.in && q.rows == t.rows && q.cols == t.cols && q.ld_in == t.ld_in && q.transpose == t.transpose) return q.out;
     t.out = (float*)ws_alloc(h, (size_t)rows * t.ld_out * sizeof(float));
     if (getenv("FB_DEBUG_PLAN"))
-      fprintf(stderr, "[fb plan %s] phase %d stage in=%p rows=%d cols=%d ld_in=%d T=%d -> off=%zu bytes=%zu\n", h->ws_base ? "real" : "dry",
-              phase, (const void*)p, t.rows, t.cols, t.ld_in, t.transpose, (size_t)((char*)t.out - h->ws_base), (size_t)rows * t.ld_out * 4);
-    pending.push_back(t);
+      fprintf(stderr, "[fb plan %s] phase %d stage(%s) in=%p rows=%d cols=%d ld_in=%d T=%d -> off=%zu bytes=%zu\n", h->ws_base ? "real" : "dry",
+              phase, early ? "early" : "late", (const void*)p, t.rows, t.cols, t.ld_in, t.transpose, (size_t)((char*)t.out - h->ws_base),
+              (size_t)rows * t.ld_out * 4);
+    list.push_back(t);
     return t.out;
   }
   void gemm_tc(const std::vector<GemmDesc>& g) {
     std::vector<TcGemmDesc> v;
     std::vector<TransposeDesc> pending;
+    bool used_early = false;
     int work = 0;
     double flops = 0.0, bytes = 0.0;
+    // tile width: the widest BN that still gives the launch about one CTA per SM (a CTA's k-loop is MMA-bound, so a narrower
+    // tile shortens the critical path of an under-filled launch)
+    int bn_group = 32;
+    for (int cand : {128, 64}) {
+      int tiles = 0;
+      for (const GemmDesc& s : g) tiles += fb_ceil_div(s.M, TC_BM) * fb_ceil_div(s.N, cand);
+      if (tiles >= 120) { bn_group = cand; break; }
+    }
     for (const GemmDesc& s : g) {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
       d.C = s.C; d.bias = s.bias; d.mask = s.mask; d.M = s.M; d.N = s.N; d.K = s.K; d.K2 = s.K2;
-      d.ldc = s.ldc; d.ldmask = s.ldmask; d.flags = s.flags & (GF_RELU | GF_MASK_RELU | GF_MASK_TANH); d.bn = s.N > 64 ? 128 : 64;
+      d.ldc = s.ldc; d.ldmask = s.ldmask; d.flags = s.flags & (GF_RELU | GF_MASK_RELU | GF_MASK_TANH);
+      d.bn = s.N <= 32 ? 32 : (s.N <= 64 ? 64 : 128);
+      if (d.bn > bn_group) d.bn = bn_group;
       d.tiles_m = fb_ceil_div(s.M, TC_BM); d.tiles_n = fb_ceil_div(s.N, d.bn);
       d.work_begin = work; d.work_count = d.tiles_m * d.tiles_n; work += d.work_count;
       int lda = 0, ldb = 0, lda2 = 0, ldb2 = 0;
-      const float* A1 = stage_operand(pending, s.A, s.a_kmajor, s.M, s.K, s.lda, &lda);
-      const float* B1 = stage_operand(pending, s.B, s.b_kmajor, s.N, s.K, s.ldb, &ldb);
-      const float* A2 = s.K2 ? stage_operand(pending, s.A2, s.a_kmajor, s.M, s.K2, s.lda, &lda2) : nullptr;
-      const float* B2 = s.K2 ? stage_operand(pending, s.B2, s.b_kmajor, s.N, s.K2, s.ldb, &ldb2) : nullptr;
+      const float* A1 = stage_operand(pending, &used_early, s.A, s.a_kmajor, s.M, s.K, s.lda, &lda);
+      const float* B1 = stage_operand(pending, &used_early, s.B, s.b_kmajor, s.N, s.K, s.ldb, &ldb);
+      const float* A2 = s.K2 ? stage_operand(pending, &used_early, s.A2, s.a_kmajor, s.M, s.K2, s.lda, &lda2) : nullptr;
+      const float* B2 = s.K2 ? stage_operand(pending, &used_early, s.B2, s.b_kmajor, s.N, s.K2, s.ldb, &ldb2) : nullptr;
       if (h->ws_base && rc == FB_OK) {
         rc = encode_tiled_map(&d.mapA, A1, s.M, s.K, lda, TC_BM);
         if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, B1, s.N, s.K, ldb, d.bn);
@@ -96,6 +123,7 @@ struct Builder {
       bytes += 4.0 * ((double)s.M * k + (double)s.N * k + (double)s.M * s.N);
       v.push_back(d);
     }
+    if (used_early && h->early_join[phase] < 0) h->early_join[phase] = (int)h->ops[phase].size();  // the next op pushed must join
     if (!pending.empty()) {
       int ctas = 0;
       double tbytes = 0.0;
@@ -260,6 +288,8 @@ static int build_plan(fb_handle* h) {
   const int G = c.goal_dim;
   const bool use_goal = c.use_goal != 0;
   for (auto& v : h->ops) v.clear();
+  for (auto& v : h->early_stage) v.clear();
+  for (auto& j : h->early_join) j = -1;
   h->views.clear();
   h->arena.clear();
   h->ws_off = 0;
@@ -350,6 +380,8 @@ static int build_plan(fb_handle* h) {
   BAct bMix = b_alloc(h, mix_in, b_mix_out, "Bmix");
   BAct bT = b_alloc(h, goal_next, tB, "Bt");
   BAct bO = b_alloc(h, goal_next, Bm, "Bo");
+
+  h->ws_fwd_end = h->ws_off;  // everything allocated so far is written by MIX / FB_FWD / ACTOR_FWD (or is an input)
 
   // loss matrices (row block and column block); Mat cols = n
   Mat M1 = ws_mat(h, B, n, "M1"), M2 = ws_mat(h, B, n, "M2"), T1 = ws_mat(h, B, n, "T1"), T2 = ws_mat(h, B, n, "T2");
@@ -554,26 +586,42 @@ static int build_plan(fb_handle* h) {
       return cudaGetLastError();
     }, FB_OPK_LOSS, 0.0, 4.0 * 6.0 * (double)B * (double)n);
   }
-  {
+  // second stage: dF_k = G_k . B_all,  dB = Gt_1 . F1_all + Gt_2 . F2_all + Gc . B_all  (+ the diagonal term, added by k_l2norm_bwd)
+  const float db_coef = -4.0f * c.ortho_coef * inv_n;   // d(-2 c mean_s Cov_ss)/dB_s = -(4c/n) B_s
+  Mat dBparts = ws_mat(h, B, 3 * ldZ, "dBparts");
+  const bool tc_inner = c.mlp_mode == FB_MLP_TCGEN05;
+  if (tc_inner) {
+    auto inner = [&](const Mat& Gm, const Mat& Yall, const Mat& C) {  // C[B, Z] = Gm[B, n] . Yall[n, Z]
+      return gemm_raw(Gm.p, Gm.ld, 1, Yall.p, Yall.ld, 0, C.p, C.ld, Gm.rows, Z, n, nullptr, 0, nullptr, 0);
+    };
+    b.gemm({inner(M1, Bg, dF1), inner(M2, Bg, dF2), inner(Mt1, F1g, dBparts.cs(0, Z)), inner(Mt2, F2g, dBparts.cs(ldZ, Z)),
+            inner(Cov, Bg, dBparts.cs(2 * ldZ, Z))});
+  } else {
     b.memset0(dblk.p, (size_t)dblk.rows * dblk.ld * sizeof(float));
-    const float coef = -4.0f * c.ortho_coef * inv_n;
-    b.push([dB, Bm, B, Z, coef](cudaStream_t s) {
-      k_loss_init_db<<<fb_ceil_div(B * Z, 256), 256, 0, s>>>(dB.p, dB.ld, Bm.p, Bm.ld, B, Z, coef);
+    b.push([dB, Bm, B, Z, db_coef](cudaStream_t s) {   // dB starts from the diagonal term, the products accumulate onto it
+      k_loss_init_db<<<fb_ceil_div(B * Z, 256), 256, 0, s>>>(dB.p, dB.ld, Bm.p, Bm.ld, B, Z, db_coef);
       return cudaGetLastError();
     });
     auto inner = [&](const Mat& Gm, const Mat& Yall, const Mat& C) {  // C[B, Z] += Gm[B, n] . Yall[n, Z]
-      GemmDesc d = gemm_raw(Gm.p, Gm.ld, 1, Yall.p, Yall.ld, 0, C.p, C.ld, Gm.rows, Z, n, nullptr, GF_ATOMIC | GF_SHARED_C, nullptr, 0);
-      return d;
+      return gemm_raw(Gm.p, Gm.ld, 1, Yall.p, Yall.ld, 0, C.p, C.ld, Gm.rows, Z, n, nullptr, GF_ATOMIC | GF_SHARED_C, nullptr, 0);
     };
     b.gemm({inner(M1, Bg, dF1), inner(M2, Bg, dF2), inner(Mt1, F1g, dB), inner(Mt2, F2g, dB), inner(Cov, Bg, dB)});
   }
 
   // =========================== FB_PHASE_FB_BWD ==================================================
   b.set_phase(FB_PHASE_FB_BWD);
-  b.push([dB, Bm, bO, draw, B, Z](cudaStream_t s) {
-    k_l2norm_bwd<<<fb_ceil_div(B, 8), 256, 0, s>>>(dB.p, dB.ld, Bm.p, Bm.ld, bO.nrm, draw.p, draw.ld, B, Z);
-    return cudaGetLastError();
-  });
+  {
+    const float* p0 = tc_inner ? dBparts.p : dB.p;
+    const float* p1 = tc_inner ? dBparts.p + ldZ : nullptr;
+    const float* p2 = tc_inner ? dBparts.p + 2 * ldZ : nullptr;
+    const int ldp = tc_inner ? dBparts.ld : dB.ld;
+    float* dsum = tc_inner ? dB.p : nullptr;   // keep the "dB" view complete on both paths
+    const float coef = tc_inner ? db_coef : 0.f;
+    b.push([p0, p1, p2, ldp, coef, dsum, dB, Bm, bO, draw, B, Z](cudaStream_t s) {
+      k_l2norm_bwd<<<fb_ceil_div(B, 8), 256, 0, s>>>(p0, p1, p2, ldp, coef, dsum, dB.ld, Bm.p, Bm.ld, bO.nrm, draw.p, draw.ld, B, Z);
+      return cudaGetLastError();
+    });
+  }
   b.colsum({mk_colsum(dF1, pF.gv(HD_1 + 3)), mk_colsum(dF2, pF.gv(HD_2 + 3)), mk_colsum(draw, pB.gv(7))});
   b.gemm({lin_dw(dF1, h1F1, pF.gw(HD_1 + 2)), lin_dw(dF2, h1F2, pF.gw(HD_2 + 2)), lin_dw(draw, bO.h2, pB.gw(6)),
           lin_dx(dF1, pF.w(HD_1 + 2), dh1_1, GF_MASK_RELU, &h1F1), lin_dx(dF2, pF.w(HD_2 + 2), dh1_2, GF_MASK_RELU, &h1F2),
@@ -692,6 +740,25 @@ static int build_plan(fb_handle* h) {
     b.push([mp](cudaStream_t s) { k_metric_final<<<1, 32, 0, s>>>(mp); return cudaGetLastError(); });
   }
 
+  // early-staged operands: one grouped launch per phase on the side lane, issued first; its first consumer joins
+  for (int ph = 0; ph < FB_NUM_PHASES; ++ph) {
+    std::vector<TransposeDesc>& tv = h->early_stage[ph];
+    if (tv.empty()) continue;
+    int ctas = 0;
+    double tbytes = 0.0;
+    for (auto& t : tv) {
+      t.cta_begin = ctas; t.ctas_x = fb_ceil_div(t.cols, 32); ctas += t.ctas_x * fb_ceil_div(t.rows, 32);
+      tbytes += 8.0 * t.rows * (double)t.cols;
+    }
+    const TransposeDesc* td = arena_put(h, tv, d_arena);
+    const int nt = (int)tv.size();
+    if (h->early_join[ph] >= 0 && h->early_join[ph] < (int)h->ops[ph].size()) h->ops[ph][h->early_join[ph]].join = 1;
+    Op op{[td, nt, ctas](cudaStream_t s) {
+            k_transpose_grouped<<<ctas, 256, 0, s>>>(td, nt);
+            return cudaGetLastError();
+          }, FB_OPK_TRANSPOSE, 0.0, tbytes, 1, 0};
+    h->ops[ph].insert(h->ops[ph].begin(), op);
+  }
   if (b.rc != FB_OK) return b.rc;
   if (h->arena.size() > FB_DESC_ARENA_BYTES) return FB_E_STATE;
   h->ws_off = (h->ws_off + 255) / 256 * 256;
@@ -802,6 +869,9 @@ void fb_destroy(fb_handle* h) {
   if (!h) return;
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
@@ -940,9 +1010,34 @@ int fb_set_noise(fb_handle* h, const float* d_noise_fb, const float* d_noise_act
 }
 
 static cudaError_t run_eager(fb_handle* h, uint32_t mask, cudaStream_t s) {
+  bool side_pending = false;
   for (int ph = 0; ph < FB_NUM_PHASES; ++ph) {
     if (!(mask & (1u << ph))) continue;
-    for (auto& op : h->ops[ph]) CKE(op(s));
+    for (auto& op : h->ops[ph]) {
+      if (op.lane == 1) {
+        if (!h->side_stream) {
+          CKE(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+          CKE(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+          CKE(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        }
+        CKE(cudaEventRecord(h->ev_fork, s));               // fork: the side lane sees everything issued so far
+        CKE(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        CKE(op(h->side_stream));
+        side_pending = true;
+      } else {
+        if (op.join && side_pending) {
+          CKE(cudaEventRecord(h->ev_join, h->side_stream));
+          CKE(cudaStreamWaitEvent(s, h->ev_join, 0));
+          side_pending = false;
+        }
+        CKE(op(s));
+      }
+    }
+    if (side_pending) {  // a phase never leaves side work dangling (graph capture needs every fork joined)
+      CKE(cudaEventRecord(h->ev_join, h->side_stream));
+      CKE(cudaStreamWaitEvent(s, h->ev_join, 0));
+      side_pending = false;
+    }
   }
   return cudaSuccess;
 }

@@ -391,19 +391,32 @@ __global__ void __launch_bounds__(256) k_l2norm_fwd(const L2Desc* __restrict__ d
   if (lane == 0 && d.nrm) d.nrm[r] = nrm;
 }
 
-// dx = (sqrt(Z)/nrm) * (dy - xh * (xh . dy)),  xh = y / sqrt(Z)
-__global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy,
-                                                    const float* __restrict__ nrm, float* __restrict__ dx, int lddx, int rows, int Z) {
+// dx = (sqrt(Z)/nrm) * (dy - xh * (xh . dy)),  xh = y / sqrt(Z).  dy is the sum of up to three partial gradients plus coef * y
+// (the partial products of the tensor-core loss path and the diagonal orthonormality term); the total is also written to dsum.
+__global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ dy0, const float* __restrict__ dy1,
+                                                    const float* __restrict__ dy2, int lddy, float coef, float* __restrict__ dsum,
+                                                    int ldsum, const float* __restrict__ y, int ldy, const float* __restrict__ nrm,
+                                                    float* __restrict__ dx, int lddx, int rows, int Z) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   const float sq = sqrtf((float)Z), isq = 1.0f / sq;
   float dot = 0.f;
-  for (int c = lane; c < Z; c += 32) dot += y[(size_t)r * ldy + c] * isq * dy[(size_t)r * lddy + c];
+  for (int c = lane; c < Z; c += 32) {
+    const float yv = y[(size_t)r * ldy + c];
+    float g = dy0[(size_t)r * lddy + c] + coef * yv;
+    if (dy1) g += dy1[(size_t)r * lddy + c];
+    if (dy2) g += dy2[(size_t)r * lddy + c];
+    if (dsum) dsum[(size_t)r * ldsum + c] = g;
+    dot += yv * isq * g;
+  }
   dot = warp_sum(dot);
   const float k = sq / nrm[r];
   for (int c = lane; c < Z; c += 32) {
-    const float xh = y[(size_t)r * ldy + c] * isq;
-    dx[(size_t)r * lddx + c] = k * (dy[(size_t)r * lddy + c] - xh * dot);
+    const float yv = y[(size_t)r * ldy + c];
+    float g = dy0[(size_t)r * lddy + c] + coef * yv;
+    if (dy1) g += dy1[(size_t)r * lddy + c];
+    if (dy2) g += dy2[(size_t)r * lddy + c];
+    dx[(size_t)r * lddx + c] = k * (g - yv * isq * dot);
   }
 }
 

@@ -49,6 +49,8 @@ struct Op {
   int kind;
   double flops;  // algorithmic FLOPs of this launch (2 x MACs for GEMM groups)
   double bytes;  // algorithmic bytes read + written
+  int lane;      // 0: main stream; 1: side stream (forks from the main stream where it is issued)
+  int join;      // main-lane op that must wait for the side-lane work issued before it
   cudaError_t operator()(cudaStream_t s) const { return fn(s); }
 };
 
@@ -73,6 +75,12 @@ struct fb_handle {
   cudaStream_t capture_stream = nullptr;
   size_t contract_smem = 0;  // dynamic shared memory of k_contract_tc (0: SIMT contraction)
   bool uses_gemm_tc = false;
+  // operands whose source is final when a phase starts (weights, activations of earlier phases) are staged on a side stream
+  std::vector<TransposeDesc> early_stage[FB_NUM_PHASES];
+  int early_join[FB_NUM_PHASES];     // index of the first op of the phase that consumes them (-1: none)
+  size_t ws_fwd_end = 0;             // workspace offset below which every buffer is written by a forward phase
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // fixed workspace objects
   DevScalars* d_sc = nullptr;
   double* d_acc = nullptr;
