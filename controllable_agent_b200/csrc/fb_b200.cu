@@ -41,8 +41,8 @@ struct Builder {
   char* d_arena;
   int phase = 0;
   void set_phase(uint32_t bit) { phase = phase_index(bit); }
-  void push(OpFn fn, int kind = FB_OPK_ELEMENTWISE, double flops = 0.0, double bytes = 0.0) {
-    h->ops[phase].push_back(Op{std::move(fn), kind, flops, bytes, 0, 0});
+  void push(OpFn fn, int kind = FB_OPK_ELEMENTWISE, double flops = 0.0, double bytes = 0.0, int lane = 0) {
+    h->ops[phase].push_back(Op{std::move(fn), kind, flops, bytes, lane, 0});
   }
 
   int rc = FB_OK;  // first error met while building (tensor-map encoding)
@@ -178,10 +178,14 @@ struct Builder {
       d.cta_begin = ctas; d.cta_count = fb_ceil_div(d.rows, FB_LN_BWD_ROWS_PER_CTA); ctas += d.cta_count;
       bytes += 16.0 * d.rows * (double)d.D;
     }
+    bool vec = true;  // every problem narrow enough and 16-byte aligned for the register-resident variant?
+    for (auto& d : v)
+      vec = vec && d.D <= 1024 && d.ld % 4 == 0 && d.ld_dy % 4 == 0 && aligned16(d.dy) && aligned16(d.y) && aligned16(d.x) && aligned16(d.dx);
     const LnBwdDesc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
-    push([dd, n, ctas](cudaStream_t s) {
-      k_ln_tanh_bwd<<<ctas, 256, 0, s>>>(dd, n);
+    push([dd, n, ctas, vec](cudaStream_t s) {
+      if (vec) k_ln_tanh_bwd_v4<<<ctas, 256, 0, s>>>(dd, n);
+      else k_ln_tanh_bwd<<<ctas, 256, 0, s>>>(dd, n);
       return cudaGetLastError();
     }, FB_OPK_LAYERNORM, 0.0, bytes);
   }
@@ -208,7 +212,7 @@ struct Builder {
     push([dd, n, ctas](cudaStream_t s) {
       k_colsum<<<ctas, 256, 0, s>>>(dd, n);
       return cudaGetLastError();
-    }, FB_OPK_COLSUM, 0.0, bytes);
+    }, FB_OPK_COLSUM, 0.0, bytes, 1);  // side lane: bias gradients are leaves of the dependency graph (joined at phase end)
   }
   void memset0(void* p, size_t bytes) {
     push([p, bytes](cudaStream_t s) { return cudaMemsetAsync(p, 0, bytes, s); }, FB_OPK_MEMSET, 0.0, (double)bytes);

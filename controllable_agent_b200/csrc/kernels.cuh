@@ -371,6 +371,105 @@ __global__ void __launch_bounds__(256) k_ln_tanh_bwd(const LnBwdDesc* __restrict
   }
 }
 
+// Vectorised variant for D <= 1024 with 16-byte aligned rows: each lane keeps its 8 float4 columns of the row in registers
+// (one pass over dy / y / x), and its share of dgamma / dbeta in registers across the rows of the CTA (no per-element
+// shared-memory atomics); per CTA one shared-memory combine across the 8 warps, then one global atomic per column.
+__global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const LnBwdDesc* __restrict__ descs, int nprob) {
+  constexpr int NV = 8;  // float4s per lane: D <= 32 * 4 * 8 = 1024
+  __shared__ float s_dg[1024];
+  __shared__ float s_db[1024];
+  int p = 0;
+  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;
+  const LnBwdDesc d = descs[p];
+  const int cta = blockIdx.x - d.cta_begin;
+  const bool affine = d.dgamma != nullptr;
+  const int D = d.D;
+  if (affine) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) { s_dg[c] = 0.f; s_db[c] = 0.f; }
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = cta * FB_LN_BWD_ROWS_PER_CTA;
+  const float invD = 1.0f / (float)D;
+  float4 gam[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    gam[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < D) {
+      gam[i].x = __ldg(d.gamma + c);
+      if (c + 1 < D) gam[i].y = __ldg(d.gamma + c + 1);
+      if (c + 2 < D) gam[i].z = __ldg(d.gamma + c + 2);
+      if (c + 3 < D) gam[i].w = __ldg(d.gamma + c + 3);
+    }
+  }
+  float4 adg[NV], adb[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { adg[i] = make_float4(0.f, 0.f, 0.f, 0.f); adb[i] = adg[i]; }
+  for (int rr = warp; rr < FB_LN_BWD_ROWS_PER_CTA; rr += 8) {
+    const int r = r0 + rr;
+    if (r >= d.rows) break;
+    const float4* dy = reinterpret_cast<const float4*>(d.dy + (size_t)r * d.ld_dy);
+    const float4* y = reinterpret_cast<const float4*>(d.y + (size_t)r * d.ld);
+    const float4* x = reinterpret_cast<const float4*>(d.x + (size_t)r * d.ld);
+    const float mean = d.mean[r], rstd = d.rstd[r];
+    float4 g[NV], xh[NV];
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + 32 * i, c = q * 4;
+      g[i] = make_float4(0.f, 0.f, 0.f, 0.f); xh[i] = g[i];
+      if (c < D) {
+        const float4 dv = dy[q], yv = y[q], xv = x[q];
+        g[i].x = dv.x * (1.f - yv.x * yv.x); xh[i].x = (xv.x - mean) * rstd;
+        if (c + 1 < D) { g[i].y = dv.y * (1.f - yv.y * yv.y); xh[i].y = (xv.y - mean) * rstd; }
+        if (c + 2 < D) { g[i].z = dv.z * (1.f - yv.z * yv.z); xh[i].z = (xv.z - mean) * rstd; }
+        if (c + 3 < D) { g[i].w = dv.w * (1.f - yv.w * yv.w); xh[i].w = (xv.w - mean) * rstd; }
+        const float4 gg = make_float4(g[i].x * gam[i].x, g[i].y * gam[i].y, g[i].z * gam[i].z, g[i].w * gam[i].w);
+        a += gg.x + gg.y + gg.z + gg.w;
+        b += gg.x * xh[i].x + gg.y * xh[i].y + gg.z * xh[i].z + gg.w * xh[i].w;
+      }
+    }
+    a = warp_sum(a) * invD; b = warp_sum(b) * invD;
+    float4* dx = reinterpret_cast<float4*>(d.dx + (size_t)r * d.ld_dy);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + 32 * i, c = q * 4;
+      if (c < D) {
+        float4 o;
+        o.x = rstd * (g[i].x * gam[i].x - a - xh[i].x * b);
+        o.y = rstd * (g[i].y * gam[i].y - a - xh[i].y * b);
+        o.z = rstd * (g[i].z * gam[i].z - a - xh[i].z * b);
+        o.w = rstd * (g[i].w * gam[i].w - a - xh[i].w * b);
+        if (c + 3 < D) {
+          dx[q] = o;
+        } else {  // ragged tail (D not a multiple of 4): the row pitch still holds a full float4, only valid lanes are stored
+          float* ds = reinterpret_cast<float*>(dx + q);
+          ds[0] = o.x;
+          if (c + 1 < D) ds[1] = o.y;
+          if (c + 2 < D) ds[2] = o.z;
+        }
+        adg[i].x += g[i].x * xh[i].x; adg[i].y += g[i].y * xh[i].y; adg[i].z += g[i].z * xh[i].z; adg[i].w += g[i].w * xh[i].w;
+        adb[i].x += g[i].x; adb[i].y += g[i].y; adb[i].z += g[i].z; adb[i].w += g[i].w;
+      }
+    }
+  }
+  if (affine) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < D) {
+        atomicAdd(&s_dg[c], adg[i].x); atomicAdd(&s_db[c], adb[i].x);
+        if (c + 1 < D) { atomicAdd(&s_dg[c + 1], adg[i].y); atomicAdd(&s_db[c + 1], adb[i].y); }
+        if (c + 2 < D) { atomicAdd(&s_dg[c + 2], adg[i].z); atomicAdd(&s_db[c + 2], adb[i].z); }
+        if (c + 3 < D) { atomicAdd(&s_dg[c + 3], adg[i].w); atomicAdd(&s_db[c + 3], adb[i].w); }
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) { atomicAdd(d.dgamma + c, s_dg[c]); atomicAdd(d.dbeta + c, s_db[c]); }
+  }
+}
+
 // ---- sqrt(Z) * F.normalize (fb_modules.py:33-40, 227-229) ------------------------------------------
 struct L2Desc { const float* x; float* y; float* nrm; int rows, Z, ldx, ldy, row_begin; };
 
