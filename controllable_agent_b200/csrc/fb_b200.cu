@@ -41,8 +41,13 @@ struct Builder {
   char* d_arena;
   int phase = 0;
   void set_phase(uint32_t bit) { phase = phase_index(bit); }
-  void push(OpFn fn, int kind = FB_OPK_ELEMENTWISE, double flops = 0.0, double bytes = 0.0, int lane = 0) {
-    h->ops[phase].push_back(Op{std::move(fn), kind, flops, bytes, lane, 0});
+  int cur_lane = 0;        // lane of the ops recorded next (1: a side-lane chain, e.g. the z-mixing forward)
+  bool fork_next = false;  // the next side-lane op recorded starts a chain: it forks from the main lane
+  void push(OpFn fn, int kind = FB_OPK_ELEMENTWISE, double flops = 0.0, double bytes = 0.0, int lane = -1) {
+    int fork = 0;
+    if (lane < 0) { lane = cur_lane; if (lane == 1 && fork_next) { fork = 1; fork_next = false; } }
+    else if (lane == 1) fork = 1;   // a lone side-lane leaf (bias column sums) forks where it is issued
+    h->ops[phase].push_back(Op{std::move(fn), kind, flops, bytes, lane, 0, fork});
   }
 
   int rc = FB_OK;  // first error met while building (tensor-map encoding)
@@ -50,6 +55,10 @@ struct Builder {
   // can this problem run on the tensor cores (gemm_tc.cuh)?  Operands TMA cannot address directly are staged (see stage_operand)
   bool tc_ok(const GemmDesc& g) const {
     if (h->cfg.mlp_mode != FB_MLP_TCGEN05 || (g.flags & GF_SHARED_C) || g.M < 8 || g.K < 8) return false;
+    // a first-layer product (K = obs + action / z, tens of columns) whose weight would need an aligned staged copy is
+    // cheaper on the SIMT kernel than a staging launch plus a tensor-core launch
+    const bool a_direct = g.a_kmajor && aligned16(g.A) && g.lda % 4 == 0, b_direct = g.b_kmajor && aligned16(g.B) && g.ldb % 4 == 0;
+    if (g.K < 128 && g.a_kmajor && g.b_kmajor && !(a_direct && b_direct)) return false;
     return true;
   }
   // K-major, TMA-addressable view of an operand: the operand itself when it already is one, otherwise a staged copy
@@ -123,7 +132,9 @@ struct Builder {
       bytes += 4.0 * ((double)s.M * k + (double)s.N * k + (double)s.M * s.N);
       v.push_back(d);
     }
-    if (used_early && h->early_join[phase] < 0) h->early_join[phase] = (int)h->ops[phase].size();  // the next op pushed must join
+    // the first MAIN-lane op that consumes early-staged operands joins the side lane (side-lane consumers follow the staging
+    // launch on the same stream)
+    if (used_early && cur_lane == 0 && h->early_join[phase] < 0) h->early_join[phase] = (int)h->ops[phase].size();
     if (!pending.empty()) {
       int ctas = 0;
       double tbytes = 0.0;
@@ -164,10 +175,13 @@ struct Builder {
     int rows = 0;
     double bytes = 0.0;
     for (auto& d : v) { d.row_begin = rows; rows += d.rows; bytes += 8.0 * d.rows * (double)d.D; }
+    bool vec = true;
+    for (auto& d : v) vec = vec && d.D <= 1024 && d.ld % 4 == 0 && aligned16(d.x) && aligned16(d.y);
     const LnDesc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
-    push([dd, n, rows](cudaStream_t s) {
-      k_ln_tanh_fwd<<<fb_ceil_div(rows, 8), 256, 0, s>>>(dd, n, rows);
+    push([dd, n, rows, vec](cudaStream_t s) {
+      if (vec) k_ln_tanh_fwd_v4<<<fb_ceil_div(rows, 8), 256, 0, s>>>(dd, n, rows);
+      else k_ln_tanh_fwd<<<fb_ceil_div(rows, 8), 256, 0, s>>>(dd, n, rows);
       return cudaGetLastError();
     }, FB_OPK_LAYERNORM, 0.0, bytes);
   }
@@ -461,6 +475,9 @@ static int build_plan(fb_handle* h) {
     b.push([sp, packed](cudaStream_t s) { k_stage_inputs<<<sp.batch, 128, 0, s>>>(sp, packed); return cudaGetLastError(); });
   }
   const bool do_mix = c.mix_ratio > 0.f;
+  // The z-mixing forward (a chain of five small launches) runs on the side lane while the main lane already computes the
+  // first layers that do not depend on z (actor.obs_net, F.obs_action_net, both backward nets); the phase end joins them.
+  b.cur_lane = 1; b.fork_next = true;
   if (do_mix) {  // mix_z = backward_net(backward_input[perm]) on every row; rows outside the mask are ignored
     b.gemm({lin_fwd(bMix.x, pB.w(0), pB.v(1), bMix.pre, 0)});
     b.ln_fwd({b_ln(bMix, pB)});
@@ -474,16 +491,17 @@ static int build_plan(fb_handle* h) {
     zp.mix_mask = do_mix ? h->d_mix_mask : nullptr; zp.z = z.p; zp.actor_in_oz = actor_in_oz.p; zp.ldOZ = actor_in_oz.ld;
     b.push([zp](cudaStream_t s) { k_z_final<<<fb_ceil_div(zp.batch, 8), 256, 0, s>>>(zp); return cudaGetLastError(); });
   }
+  b.cur_lane = 0;
+  b.gemm({lin_fwd(eAo.x, pA.w(A_O + 0), pA.v(A_O + 1), eAo.pre, 0), lin_fwd(eFoa.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eFoa.pre, 0),
+          lin_fwd(bO.x, pB.w(0), pB.v(1), bO.pre, 0), lin_fwd(bT.x, pBt.w(0), pBt.v(1), bT.pre, 0)});
+  b.ln_fwd({embed_ln(eAo, pA.sub(A_O)), embed_ln(eFoa, pF.sub(E_OA)), b_ln(bO, pB), b_ln(bT, pBt)});
 
   // =========================== FB_PHASE_FB_FWD ==================================================
   b.set_phase(FB_PHASE_FB_FWD);
   b.memset0(acc, 8 * sizeof(double));
-  b.gemm({lin_fwd(eAo.x, pA.w(A_O + 0), pA.v(A_O + 1), eAo.pre, 0), lin_fwd(eAoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eAoz.pre, 0),
-          lin_fwd(eFoa.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eFoa.pre, 0), lin_fwd(eFoz.x, pF.w(E_OZ + 0), pF.v(E_OZ + 1), eFoz.pre, 0),
-          lin_fwd(eFtoz.x, pFt.w(E_OZ + 0), pFt.v(E_OZ + 1), eFtoz.pre, 0),
-          lin_fwd(bO.x, pB.w(0), pB.v(1), bO.pre, 0), lin_fwd(bT.x, pBt.w(0), pBt.v(1), bT.pre, 0)});
-  b.ln_fwd({embed_ln(eAo, pA.sub(A_O)), embed_ln(eAoz, pA.sub(A_OZ)), embed_ln(eFoa, pF.sub(E_OA)), embed_ln(eFoz, pF.sub(E_OZ)),
-            embed_ln(eFtoz, pFt.sub(E_OZ)), b_ln(bO, pB), b_ln(bT, pBt)});
+  b.gemm({lin_fwd(eAoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eAoz.pre, 0), lin_fwd(eFoz.x, pF.w(E_OZ + 0), pF.v(E_OZ + 1), eFoz.pre, 0),
+          lin_fwd(eFtoz.x, pFt.w(E_OZ + 0), pFt.v(E_OZ + 1), eFtoz.pre, 0)});
+  b.ln_fwd({embed_ln(eAoz, pA.sub(A_OZ)), embed_ln(eFoz, pF.sub(E_OZ)), embed_ln(eFtoz, pFt.sub(E_OZ))});
   b.gemm({lin_fwd(eAo.y, pA.w(A_O + 4), pA.v(A_O + 5), eAo.out, GF_RELU), lin_fwd(eAoz.y, pA.w(A_OZ + 4), pA.v(A_OZ + 5), eAoz.out, GF_RELU),
           lin_fwd(eFoa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eFoa.out, GF_RELU), lin_fwd(eFoz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eFoz.out, GF_RELU),
           lin_fwd(eFtoz.y, pFt.w(E_OZ + 4), pFt.v(E_OZ + 5), eFtoz.out, GF_RELU),
@@ -760,7 +778,7 @@ static int build_plan(fb_handle* h) {
     Op op{[td, nt, ctas](cudaStream_t s) {
             k_transpose_grouped<<<ctas, 256, 0, s>>>(td, nt);
             return cudaGetLastError();
-          }, FB_OPK_TRANSPOSE, 0.0, tbytes, 1, 0};
+          }, FB_OPK_TRANSPOSE, 0.0, tbytes, 1, 0, 1};
     h->ops[ph].insert(h->ops[ph].begin(), op);
   }
   if (b.rc != FB_OK) return b.rc;
@@ -1024,8 +1042,10 @@ static cudaError_t run_eager(fb_handle* h, uint32_t mask, cudaStream_t s) {
           CKE(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
           CKE(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         }
-        CKE(cudaEventRecord(h->ev_fork, s));               // fork: the side lane sees everything issued so far
-        CKE(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        if (op.fork || !side_pending) {                    // fork: the side lane sees everything issued so far on the main lane
+          CKE(cudaEventRecord(h->ev_fork, s));
+          CKE(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        }
         CKE(op(h->side_stream));
         side_pending = true;
       } else {

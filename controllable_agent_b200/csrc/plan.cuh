@@ -49,8 +49,10 @@ struct Op {
   int kind;
   double flops;  // algorithmic FLOPs of this launch (2 x MACs for GEMM groups)
   double bytes;  // algorithmic bytes read + written
-  int lane;      // 0: main stream; 1: side stream (forks from the main stream where it is issued)
+  int lane;      // 0: main stream; 1: side stream
   int join;      // main-lane op that must wait for the side-lane work issued before it
+  int fork;      // side-lane op that must first wait for the main-lane work issued before it (otherwise it only follows the
+                 // side-lane ops issued before it)
   cudaError_t operator()(cudaStream_t s) const { return fn(s); }
 };
 
