@@ -158,23 +158,32 @@ def run_reference(a: argparse.Namespace) -> None:
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
 class HostReplay:
-    """A host-memory (pinned) replay with the reference's sample() contract, for the end-to-end leg: every step's batch
-    is gathered on the host and crosses PCIe inside the timed region."""
+    """A host-memory replay with the reference's sample() contract, for the end-to-end leg: every step's batch is gathered
+    on the host (numpy fancy indexing into pinned staging buffers) and crosses PCIe inside the timed region."""
 
-    def __init__(self, obs, action, reward, discount, gamma: float) -> None:
+    def __init__(self, obs, action, reward, discount, gamma: float, batch: int) -> None:
+        import torch
         self.obs, self.action, self.reward, self.discount, self.gamma = obs, action, reward, discount, gamma
         self._discount, self._future = gamma, 1.0
+        pin = lambda d: torch.empty((2, batch, d), dtype=torch.float32).pin_memory()  # noqa: E731  (double-buffered)
+        self.stage = {"obs": pin(obs.shape[-1]), "action": pin(action.shape[-1]), "reward": pin(1), "discount": pin(1),
+                      "next_obs": pin(obs.shape[-1])}
+        self.flip = 0
 
     def sample(self, batch_size: int):
         import numpy as np
-        import torch
         from controllable_agent_b200 import EpisodeBatch
         E, R = self.obs.shape[:2]
         ep = np.random.randint(0, E, size=batch_size)
         t = np.random.randint(0, R - 1, size=batch_size) + 1
-        pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory()  # noqa: E731
-        return EpisodeBatch(obs=pin(self.obs[ep, t - 1]), action=pin(self.action[ep, t]), reward=pin(self.reward[ep, t]),
-                            discount=pin(self.gamma * self.discount[ep, t]), next_obs=pin(self.obs[ep, t]))
+        self.flip ^= 1
+        out = {k: v[self.flip] for k, v in self.stage.items()}
+        out["obs"].numpy()[...] = self.obs[ep, t - 1]
+        out["action"].numpy()[...] = self.action[ep, t]
+        out["reward"].numpy()[...] = self.reward[ep, t]
+        np.multiply(self.discount[ep, t], self.gamma, out=out["discount"].numpy())
+        out["next_obs"].numpy()[...] = self.obs[ep, t]
+        return EpisodeBatch(**out)
 
 
 def run_ours(a: argparse.Namespace) -> None:
@@ -240,7 +249,7 @@ def run_ours(a: argparse.Namespace) -> None:
     rs = np.random.RandomState(7 + rank)
     Eh = min(E, 200)
     host = HostReplay(rs.standard_normal((Eh, R, a.obs_dim)).astype(np.float32), rs.uniform(-1, 1, (Eh, R, a.action_dim)).astype(np.float32),
-                      rs.uniform(0, 1, (Eh, R, 1)).astype(np.float32), np.ones((Eh, R, 1), np.float32), 0.98)
+                      rs.uniform(0, 1, (Eh, R, 1)).astype(np.float32), np.ones((Eh, R, 1), np.float32), 0.98, a.batch // world)
     agent.cfg.use_tb = True          # metrics on: one D2H read of the step's losses per step
     agent.cfg.rng_mode = "reference"  # host-drawn perm / mix mask, torch-drawn z and noise, uploaded per step
     for i in range(3):

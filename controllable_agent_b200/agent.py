@@ -456,7 +456,9 @@ class FBDDPGAgent:
             if fused:
                 ep_idx, step_idx, future_idx = replay_loader.draw_indices(B)
             else:
-                batch = replay_loader.sample(B).to(c.device)
+                # a host replay (the reference's ReplayBuffer): its numpy / pinned fields go straight to the engine, which
+                # uploads them with asynchronous copies (instead of EpisodeBatch.to's one blocking copy per field)
+                batch = replay_loader.sample(B)
                 mask &= ~L.PHASE_SAMPLE
             z = self.sample_z(B, device=self.draw_device)
             perm = torch.randperm(B)

@@ -28,10 +28,10 @@
 
 #define TC_BM 128
 #define TC_BK 32
-#define TC_STAGES 3
+#define TC_MAX_STAGES 6
 #define TC_THREADS 192
-#define TC_STAGE_BYTES 65536           // [A raw 16K | B raw 16K | A lo 16K | B lo 16K]
-#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024)
+#define TC_RING_BYTES 196608           // shared-memory ring; a stage is [A raw 16K | B raw BN*128 | A lo 16K | B lo BN*128]
+#define TC_SMEM_BYTES (TC_RING_BYTES + 1024)
 
 struct __align__(64) TcGemmDesc {
   CUtensorMap mapA, mapB, mapA2, mapB2;  // box = 32 floats x 128 rows (A) / BN rows (B), SWIZZLE_128B
@@ -99,9 +99,9 @@ __device__ __forceinline__ void tc_tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __restrict__ descs, int nprob) {
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
-  __shared__ __align__(8) uint64_t bar_raw[TC_STAGES];    // TMA -> lo builders
-  __shared__ __align__(8) uint64_t bar_ready[TC_STAGES];  // lo builders -> MMA issuer
-  __shared__ __align__(8) uint64_t bar_empty[TC_STAGES];  // MMA issuer (tcgen05.commit) -> TMA producer
+  __shared__ __align__(8) uint64_t bar_raw[TC_MAX_STAGES];    // TMA -> lo builders
+  __shared__ __align__(8) uint64_t bar_ready[TC_MAX_STAGES];  // lo builders -> MMA issuer
+  __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];  // MMA issuer (tcgen05.commit) -> TMA producer
   __shared__ __align__(8) uint64_t bar_accum;             // all MMAs retired -> epilogue
   __shared__ uint32_t tmem_base_smem;
 
@@ -117,12 +117,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
   const int m0 = tm * TC_BM, n0 = tn * bn;
   const int nk1 = (d->K + TC_BK - 1) / TC_BK;
   const int nk = nk1 + (d->K2 + TC_BK - 1) / TC_BK;
+  // ring geometry: narrower B tiles leave room for more stages (3 at BN = 128, 4 at BN = 64 / 32)
+  const uint32_t half_bytes = 16384u + (uint32_t)bn * 128u;   // raw (or lo) part of a stage: A tile then B tile
+  const uint32_t stage_bytes = 2u * half_bytes;
+  const int nst = min(TC_MAX_STAGES, (int)(TC_RING_BYTES / stage_bytes));
 
   const uint32_t smem_base = (tc_smem_u32(tc_smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = tc_smem_raw + (smem_base - tc_smem_u32(tc_smem_raw));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < TC_MAX_STAGES; ++s) {
       tc_mbar_init(&bar_raw[s], 1);
       tc_mbar_init(&bar_ready[s], 128);
       tc_mbar_init(&bar_empty[s], 1);
@@ -144,10 +148,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       // ===== TMA producer =====
       const uint32_t tx_bytes = (uint32_t)(TC_BM + bn) * 128u;
       for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % TC_STAGES;
-        if (kb >= TC_STAGES) tc_mbar_wait(&bar_empty[s], ((kb / TC_STAGES) - 1) & 1);
+        const int s = kb % nst;
+        if (kb >= nst) tc_mbar_wait(&bar_empty[s], ((kb / nst) - 1) & 1);
         tc_mbar_expect_tx(&bar_raw[s], tx_bytes);
-        const uint32_t st = smem_base + (uint32_t)s * TC_STAGE_BYTES;
+        const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
         if (kb < nk1) {
           tc_tma_load_2d(st, &d->mapA, &bar_raw[s], kb * TC_BK, m0);
           tc_tma_load_2d(st + 16384u, &d->mapB, &bar_raw[s], kb * TC_BK, n0);
@@ -162,14 +166,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       // ===== MMA issuer =====
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % TC_STAGES;
-        tc_mbar_wait(&bar_ready[s], (kb / TC_STAGES) & 1);
+        const int s = kb % nst;
+        tc_mbar_wait(&bar_ready[s], (kb / nst) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = smem_base + (uint32_t)s * TC_STAGE_BYTES;
+        const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
 #pragma unroll
         for (int chain = 0; chain < 3; ++chain) {   // (A raw, B raw), (A lo, B raw), (A raw, B lo)
-          const uint32_t a = st + (chain == 1 ? 32768u : 0u);
-          const uint32_t b = st + 16384u + (chain == 2 ? 32768u : 0u);
+          const uint32_t a = st + (chain == 1 ? half_bytes : 0u);
+          const uint32_t b = st + 16384u + (chain == 2 ? half_bytes : 0u);
           // accumulators: columns [j*bn, (j+1)*bn): j = kb % 3 for hi.hi, j = 3 for the two correction chains
           const uint32_t acc = tmem_base + (uint32_t)(chain == 0 ? (kb % 3) : 3) * (uint32_t)bn;
 #pragma unroll
@@ -187,10 +191,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
     const int t = threadIdx.x - 64;
     const int nvec = (TC_BM + bn) * 8;   // float4s of the raw A and B tiles (contiguous: A 16 KB then B)
     for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % TC_STAGES;
-      tc_mbar_wait(&bar_raw[s], (kb / TC_STAGES) & 1);
-      float4* raw = reinterpret_cast<float4*>(smem_gen + (size_t)s * TC_STAGE_BYTES);
-      float4* lo = raw + 32768 / 16;
+      const int s = kb % nst;
+      tc_mbar_wait(&bar_raw[s], (kb / nst) & 1);
+      float4* raw = reinterpret_cast<float4*>(smem_gen + (size_t)s * stage_bytes);
+      float4* lo = raw + half_bytes / 16;
 #pragma unroll 4
       for (int i = t; i < nvec; i += 128) {
         const float4 x = raw[i];
@@ -229,6 +233,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       }
       const int col0 = n0 + cb;
       if (!row_ok || col0 >= N) continue;
+      float mk[16];
+      if (flags & (GF_MASK_RELU | GF_MASK_TANH)) {   // the saved activation of this row: 4 x 128-bit loads when aligned
+        const float* mp = mask + (size_t)row * ldmask + col0;
+        if (((ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0) && col0 + 15 < N) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(mp + j));
+            mk[j] = t4.x; mk[j + 1] = t4.y; mk[j + 2] = t4.z; mk[j + 3] = t4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mk[j] = (col0 + j < N) ? __ldg(mp + j) : 0.f;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int col = col0 + j;
@@ -236,8 +254,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
           float x = v[j];
           if (bias) x += __ldg(bias + col);
           if (flags & GF_RELU) x = fmaxf(x, 0.f);
-          if (flags & GF_MASK_RELU) x = (__ldg(mask + (size_t)row * ldmask + col) > 0.f) ? x : 0.f;
-          if (flags & GF_MASK_TANH) { const float tt = __ldg(mask + (size_t)row * ldmask + col); x *= (1.f - tt * tt); }
+          if (flags & GF_MASK_RELU) x = (mk[j] > 0.f) ? x : 0.f;
+          if (flags & GF_MASK_TANH) x *= (1.f - mk[j] * mk[j]);
           v[j] = x;
         }
       }

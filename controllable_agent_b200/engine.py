@@ -80,6 +80,9 @@ class FBStepEngine:
         self.layout = {net: self._tensor_table(net) for net in (L.NET_FORWARD, L.NET_BACKWARD, L.NET_ACTOR)}
         self._scalars: tp.Optional[tp.Tuple[float, ...]] = None
         self._keepalive: tp.List[tp.Any] = []
+        self._idx_stage: tp.Optional[torch.Tensor] = None   # pinned staging ring for host-provided index arrays
+        self._idx_slot = 0
+        self._idx_events: tp.List[tp.Optional[torch.cuda.Event]] = [None] * 16
         mp = self.lib.fb_metrics_ptr(h)
         self._metrics = self._wrap(mp, L.METRIC_COUNT)
         self._metrics_host = torch.zeros(L.METRIC_COUNT, dtype=torch.float32).pin_memory()
@@ -152,14 +155,31 @@ class FBStepEngine:
         if x is None:
             return None
         t = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x)
-        t = t.to(device=self.device, dtype=torch.int32).contiguous()
+        if t.device != self.device:   # through a pinned staging ring so that the upload is asynchronous
+            if self._idx_stage is None:
+                self._idx_stage = torch.empty((16, self.cfg.batch), dtype=torch.int32).pin_memory()
+                self._idx_slot = 0
+            slot = self._idx_slot % 16
+            self._idx_slot += 1
+            if self._idx_events[slot] is not None:
+                self._idx_events[slot].synchronize()     # the upload that last used this slot has left the host buffer
+            stage = self._idx_stage[slot]
+            stage.copy_(t.reshape(-1))
+            t = stage.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._idx_events[slot] = ev
+        t = t.to(dtype=torch.int32).contiguous()
         assert t.numel() == self.cfg.batch
         return t
 
     def _dev_f32(self, x: tp.Any, cols: int) -> tp.Optional[torch.Tensor]:
         if x is None:
             return None
-        t = torch.as_tensor(x).to(device=self.device, dtype=torch.float32).contiguous()
+        t = torch.as_tensor(x)
+        if t.device != self.device:   # host -> device: asynchronous when the source is pinned, ordered on the current stream
+            t = t.to(device=self.device, dtype=torch.float32, non_blocking=True)
+        t = t.to(dtype=torch.float32).contiguous()
         assert t.numel() == self.cfg.batch * cols, (tuple(t.shape), self.cfg.batch, cols)
         return t
 
