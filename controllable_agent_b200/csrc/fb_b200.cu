@@ -74,25 +74,38 @@ struct Builder {
     const char* c = reinterpret_cast<const char*>(p);
     return backward_phase && c >= h->ws_base && c < h->ws_base + h->ws_fwd_end;
   }
+  // Returns the K-major, TMA-addressable view of an operand (the operand itself when it already is one, otherwise a staged
+  // copy).  *lo_out receives the operand's pre-split lo plane when one is produced: always for staged copies (the staging
+  // launch writes it for free), and for directly addressable operands only if `want_lo` and the source is final when the
+  // phase starts (weights: a lo-only staging entry on the side lane).
   const float* stage_operand(std::vector<TransposeDesc>& pending, bool* used_early, const float* p, int kmajor, int rows, int K, int ld,
-                             int* ld_out) {
-    if (kmajor && aligned16(p) && ld % 4 == 0) { *ld_out = ld; return p; }
-    *ld_out = fb_round_up(K, 4);
-    TransposeDesc t; memset(&t, 0, sizeof(t));
-    t.in = p; t.ld_in = ld; t.ld_out = *ld_out; t.transpose = kmajor ? 0 : 1;
-    if (kmajor) { t.rows = rows; t.cols = K; } else { t.rows = K; t.cols = rows; }   // mn-major storage is [K][rows]
+                             bool want_lo, int* ld_out, const float** lo_out, int* ld_lo) {
+    const bool direct = kmajor && aligned16(p) && ld % 4 == 0;
     const bool early = is_early(p);
+    *lo_out = nullptr; *ld_lo = 0;
+    if (direct && !(want_lo && early)) { *ld_out = ld; return p; }
+    const int lds = fb_round_up(K, 4);
+    TransposeDesc t; memset(&t, 0, sizeof(t));
+    t.in = p; t.ld_in = ld; t.ld_out = lds; t.transpose = kmajor ? 0 : 1;
+    if (kmajor) { t.rows = rows; t.cols = K; } else { t.rows = K; t.cols = rows; }   // mn-major storage is [K][rows]
     std::vector<TransposeDesc>& list = early ? h->early_stage[phase] : pending;
     if (early) *used_early = true;
     for (auto& q : list)
-      if (q.in == t.in && q.rows == t.rows && q.cols == t.cols && q.ld_in == t.ld_in && q.transpose == t.transpose) return q.out;
-    t.out = (float*)ws_alloc(h, (size_t)rows * t.ld_out * sizeof(float));
+      if (q.in == t.in && q.rows == t.rows && q.cols == t.cols && q.ld_in == t.ld_in && q.transpose == t.transpose) {
+        *lo_out = q.out_lo; *ld_lo = q.ld_out;
+        if (q.out) { *ld_out = q.ld_out; return q.out; }
+        *ld_out = ld; return p;
+      }
+    const size_t bytes = (size_t)rows * lds * sizeof(float);
+    t.out = direct ? nullptr : (float*)ws_alloc(h, bytes);
+    t.out_lo = (float*)ws_alloc(h, bytes);
     if (getenv("FB_DEBUG_PLAN"))
-      fprintf(stderr, "[fb plan %s] phase %d stage(%s) in=%p rows=%d cols=%d ld_in=%d T=%d -> off=%zu bytes=%zu\n", h->ws_base ? "real" : "dry",
-              phase, early ? "early" : "late", (const void*)p, t.rows, t.cols, t.ld_in, t.transpose, (size_t)((char*)t.out - h->ws_base),
-              (size_t)rows * t.ld_out * 4);
+      fprintf(stderr, "[fb plan %s] phase %d stage(%s%s) in=%p rows=%d cols=%d ld_in=%d T=%d bytes=%zu\n", h->ws_base ? "real" : "dry",
+              phase, early ? "early" : "late", direct ? ", lo only" : "", (const void*)p, t.rows, t.cols, t.ld_in, t.transpose, bytes);
     list.push_back(t);
-    return t.out;
+    *lo_out = t.out_lo; *ld_lo = lds;
+    if (t.out) { *ld_out = lds; return t.out; }
+    *ld_out = ld; return p;
   }
   void gemm_tc(const std::vector<GemmDesc>& g) {
     std::vector<TcGemmDesc> v;
@@ -108,24 +121,34 @@ struct Builder {
       for (const GemmDesc& s : g) tiles += fb_ceil_div(s.M, TC_BM) * fb_ceil_div(s.N, cand);
       if (tiles >= 120) { bn_group = cand; break; }
     }
+    int ring_bn = 32;
     for (const GemmDesc& s : g) {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
       d.C = s.C; d.bias = s.bias; d.mask = s.mask; d.M = s.M; d.N = s.N; d.K = s.K; d.K2 = s.K2;
       d.ldc = s.ldc; d.ldmask = s.ldmask; d.flags = s.flags & (GF_RELU | GF_MASK_RELU | GF_MASK_TANH);
       d.bn = s.N <= 32 ? 32 : (s.N <= 64 ? 64 : 128);
       if (d.bn > bn_group) d.bn = bn_group;
+      if (d.bn > ring_bn) ring_bn = d.bn;
       d.tiles_m = fb_ceil_div(s.M, TC_BM); d.tiles_n = fb_ceil_div(s.N, d.bn);
       d.work_begin = work; d.work_count = d.tiles_m * d.tiles_n; work += d.work_count;
-      int lda = 0, ldb = 0, lda2 = 0, ldb2 = 0;
-      const float* A1 = stage_operand(pending, &used_early, s.A, s.a_kmajor, s.M, s.K, s.lda, &lda);
-      const float* B1 = stage_operand(pending, &used_early, s.B, s.b_kmajor, s.N, s.K, s.ldb, &ldb);
-      const float* A2 = s.K2 ? stage_operand(pending, &used_early, s.A2, s.a_kmajor, s.M, s.K2, s.lda, &lda2) : nullptr;
-      const float* B2 = s.K2 ? stage_operand(pending, &used_early, s.B2, s.b_kmajor, s.N, s.K2, s.ldb, &ldb2) : nullptr;
+      int lda = 0, ldb = 0, lda2 = 0, ldb2 = 0, ldal = 0, ldbl = 0, ldal2 = 0, ldbl2 = 0;
+      const float *Alo = nullptr, *Blo = nullptr, *A2lo = nullptr, *B2lo = nullptr;
+      const float* A1 = stage_operand(pending, &used_early, s.A, s.a_kmajor, s.M, s.K, s.lda, false, &lda, &Alo, &ldal);
+      const float* B1 = stage_operand(pending, &used_early, s.B, s.b_kmajor, s.N, s.K, s.ldb, true, &ldb, &Blo, &ldbl);
+      const float* A2 = s.K2 ? stage_operand(pending, &used_early, s.A2, s.a_kmajor, s.M, s.K2, s.lda, false, &lda2, &A2lo, &ldal2) : nullptr;
+      const float* B2 = s.K2 ? stage_operand(pending, &used_early, s.B2, s.b_kmajor, s.N, s.K2, s.ldb, true, &ldb2, &B2lo, &ldbl2) : nullptr;
+      const bool a_pre = Alo && (!s.K2 || A2lo), b_pre = Blo && (!s.K2 || B2lo);
+      if (a_pre) d.flags |= TC_A_PRE;
+      if (b_pre) d.flags |= TC_B_PRE;
       if (h->ws_base && rc == FB_OK) {
         rc = encode_tiled_map(&d.mapA, A1, s.M, s.K, lda, TC_BM);
         if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, B1, s.N, s.K, ldb, d.bn);
         if (rc == FB_OK && s.K2) rc = encode_tiled_map(&d.mapA2, A2, s.M, s.K2, lda2, TC_BM);
         if (rc == FB_OK && s.K2) rc = encode_tiled_map(&d.mapB2, B2, s.N, s.K2, ldb2, d.bn);
+        if (rc == FB_OK && a_pre) rc = encode_tiled_map(&d.mapAlo, Alo, s.M, s.K, ldal, TC_BM);
+        if (rc == FB_OK && b_pre) rc = encode_tiled_map(&d.mapBlo, Blo, s.N, s.K, ldbl, d.bn);
+        if (rc == FB_OK && a_pre && s.K2) rc = encode_tiled_map(&d.mapA2lo, A2lo, s.M, s.K2, ldal2, TC_BM);
+        if (rc == FB_OK && b_pre && s.K2) rc = encode_tiled_map(&d.mapB2lo, B2lo, s.N, s.K2, ldbl2, d.bn);
       }
       const double k = (double)s.K + s.K2;
       flops += 2.0 * s.M * (double)s.N * k;
@@ -140,7 +163,7 @@ struct Builder {
       double tbytes = 0.0;
       for (auto& t : pending) {
         t.cta_begin = ctas; t.ctas_x = fb_ceil_div(t.cols, 32); ctas += t.ctas_x * fb_ceil_div(t.rows, 32);
-        tbytes += 8.0 * t.rows * (double)t.cols;
+        tbytes += (t.out ? 12.0 : 8.0) * t.rows * (double)t.cols;
       }
       const TransposeDesc* td = arena_put(h, pending, d_arena);
       const int nt = (int)pending.size();
@@ -152,8 +175,9 @@ struct Builder {
     const TcGemmDesc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
     h->uses_gemm_tc = true;
-    push([dd, n, work](cudaStream_t s) {
-      k_gemm_tc<<<work, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, n);
+    const int grid = work < FB_SM_COUNT ? work : FB_SM_COUNT;   // persistent: one CTA per SM walks the group's tiles
+    push([dd, n, work, grid, ring_bn](cudaStream_t s) {
+      k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, n, work, ring_bn);
       return cudaGetLastError();
     }, FB_OPK_GEMM_TC, flops, bytes);
   }
@@ -770,7 +794,7 @@ static int build_plan(fb_handle* h) {
     double tbytes = 0.0;
     for (auto& t : tv) {
       t.cta_begin = ctas; t.ctas_x = fb_ceil_div(t.cols, 32); ctas += t.ctas_x * fb_ceil_div(t.rows, 32);
-      tbytes += 8.0 * t.rows * (double)t.cols;
+      tbytes += (t.out ? 12.0 : 8.0) * t.rows * (double)t.cols;
     }
     const TransposeDesc* td = arena_put(h, tv, d_arena);
     const int nt = (int)tv.size();
@@ -1231,12 +1255,13 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
     if (!a_kmajor || splitk > 1 || !aligned16(dA) || lda % 4) return FB_E_UNSUPPORTED;
     const float* Bp = dB;
     int ldbp = ldb;
-    float* tmp = nullptr;
-    if (!b_kmajor) {
+    float *tmp = nullptr, *tmp_lo = nullptr;
+    if (!b_kmajor) {   // staged transposed copy + its pre-split lo plane (the TC_B_PRE path of the plan)
       ldbp = fb_round_up(K, 4);
       CK(cudaMallocAsync(&tmp, (size_t)N * ldbp * sizeof(float), s));
+      CK(cudaMallocAsync(&tmp_lo, (size_t)N * ldbp * sizeof(float), s));
       TransposeDesc t; memset(&t, 0, sizeof(t));
-      t.in = dB; t.out = tmp; t.rows = K; t.cols = N; t.ld_in = ldb; t.ld_out = ldbp; t.transpose = 1; t.cta_begin = 0; t.ctas_x = fb_ceil_div(N, 32);
+      t.in = dB; t.out = tmp; t.out_lo = tmp_lo; t.rows = K; t.cols = N; t.ld_in = ldb; t.ld_out = ldbp; t.transpose = 1; t.cta_begin = 0; t.ctas_x = fb_ceil_div(N, 32);
       TransposeDesc* dt = nullptr;
       CK(cudaMallocAsync(&dt, sizeof(t), s));
       CK(cudaMemcpyAsync(dt, &t, sizeof(t), cudaMemcpyHostToDevice, s));
@@ -1253,16 +1278,18 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
     d.tiles_m = fb_ceil_div(M, TC_BM); d.tiles_n = fb_ceil_div(N, d.bn); d.work_begin = 0; d.work_count = d.tiles_m * d.tiles_n;
     int rc = encode_tiled_map(&d.mapA, dA, M, K, lda, TC_BM);
     if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, Bp, N, K, ldbp, d.bn);
+    if (rc == FB_OK && tmp_lo) { rc = encode_tiled_map(&d.mapBlo, tmp_lo, N, K, ldbp, d.bn); d.flags |= TC_B_PRE; }
     if (rc != FB_OK) return rc;
     TcGemmDesc* dd = nullptr;
     CK(cudaMallocAsync(&dd, sizeof(d), s));
     CK(cudaMemcpyAsync(dd, &d, sizeof(d), cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    k_gemm_tc<<<d.work_count, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, 1);
+    k_gemm_tc<<<d.work_count < FB_SM_COUNT ? d.work_count : FB_SM_COUNT, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, 1, d.work_count, d.bn);
     CK(cudaGetLastError());
     CK(cudaFreeAsync(dd, s));
     if (tmp) CK(cudaFreeAsync(tmp, s));
+    if (tmp_lo) CK(cudaFreeAsync(tmp_lo, s));
     CK(cudaStreamSynchronize(s));
     return FB_OK;
   }
@@ -1283,6 +1310,58 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
   CK(cudaGetLastError());
   CK(cudaFreeAsync(dd, s));
   return FB_OK;
+}
+
+// Timing harness of the tcgen05 grouped GEMM on one synthetic problem replicated `nprob` times (a "group"): `reps` back-to-back
+// launches between two CUDA events.  dbg = TC_DBG_* knobs (0: the product kernel).  Synchronises; allocates its own operands.
+int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int dbg, int reps, float* ms_per_launch, void* stream) {
+  if (M < 1 || N < 1 || K < 8 || K % 4 || nprob < 1 || nprob > 16 || reps < 1 || !ms_per_launch) return FB_E_ARG;
+  if (bn != 32 && bn != 64 && bn != 128) return FB_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  float *A = nullptr, *B = nullptr, *Cm = nullptr;
+  TcGemmDesc* dd = nullptr;
+  const bool pre_b = dbg & (1 << 19), pre_a = dbg & (1 << 20);   // lo planes: a second (zero) copy behind the raw one
+  dbg &= ~((1 << 19) | (1 << 20));
+  CK(cudaMallocAsync(&A, (size_t)nprob * M * K * 4 * 2, s));
+  CK(cudaMallocAsync(&B, (size_t)nprob * N * K * 4 * 2, s));
+  CK(cudaMemsetAsync(A, 0, (size_t)nprob * M * K * 4 * 2, s));
+  CK(cudaMemsetAsync(B, 0, (size_t)nprob * N * K * 4 * 2, s));
+  CK(cudaMallocAsync(&Cm, (size_t)nprob * M * N * 4, s));
+  CK(cudaMallocAsync(&dd, sizeof(TcGemmDesc) * nprob, s));
+  CK(cudaMemsetAsync(A, 0x3c, (size_t)nprob * M * K * 4, s));
+  CK(cudaMemsetAsync(B, 0x3c, (size_t)nprob * N * K * 4, s));
+  std::vector<TcGemmDesc> v(nprob);
+  int work = 0, rc = FB_OK;
+  for (int i = 0; i < nprob && rc == FB_OK; ++i) {
+    TcGemmDesc& d = v[i]; memset(&d, 0, sizeof(d));
+    d.C = Cm + (size_t)i * M * N; d.M = M; d.N = N; d.K = K; d.ldc = N; d.flags = dbg; d.bn = bn;
+    d.tiles_m = fb_ceil_div(M, TC_BM); d.tiles_n = fb_ceil_div(N, bn); d.work_begin = work; d.work_count = d.tiles_m * d.tiles_n;
+    work += d.work_count;
+    rc = encode_tiled_map(&d.mapA, A + (size_t)i * M * K, M, K, K, TC_BM);
+    if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, B + (size_t)i * N * K, N, K, K, bn);
+    if (rc == FB_OK && pre_a) { rc = encode_tiled_map(&d.mapAlo, A + (size_t)(nprob + i) * M * K, M, K, K, TC_BM); d.flags |= TC_A_PRE; }
+    if (rc == FB_OK && pre_b) { rc = encode_tiled_map(&d.mapBlo, B + (size_t)(nprob + i) * N * K, N, K, K, bn); d.flags |= TC_B_PRE; }
+  }
+  if (rc == FB_OK) {
+    cudaEvent_t e0, e1;
+    CK(cudaMemcpyAsync(dd, v.data(), sizeof(TcGemmDesc) * nprob, cudaMemcpyHostToDevice, s));
+    CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int grid = work < FB_SM_COUNT ? work : FB_SM_COUNT;
+    for (int r = 0; r < 3; ++r) k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, nprob, work, bn);
+    CK(cudaEventRecord(e0, s));
+    for (int r = 0; r < reps; ++r) k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, nprob, work, bn);
+    CK(cudaEventRecord(e1, s));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  CK(cudaFreeAsync(A, s)); CK(cudaFreeAsync(B, s)); CK(cudaFreeAsync(Cm, s)); CK(cudaFreeAsync(dd, s));
+  CK(cudaStreamSynchronize(s));
+  return rc;
 }
 
 int fb_fp32_peak_tflops(double* out_tflops, void* stream) {

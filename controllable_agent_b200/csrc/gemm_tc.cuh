@@ -12,14 +12,22 @@
 // tiny / shared-output products.  Operands TMA cannot address directly (mn-major, or a leading dimension that is not a
 // multiple of 4 floats) are first staged into an aligned K-major copy by k_transpose_grouped.
 //
-// CTA = one 128 x BN output tile (BN = 128 or 64), 6 warps:
-//   warp 0      TMA producer      raw fp32 tiles (BK = 32 floats = one 128-byte swizzle atom) -> smem ring, 3 stages
+// Where the lo parts come from (profiles/r1c_gemm_tc_breakdown.txt: building them in shared memory costs as much
+// shared-memory bandwidth as the MMAs themselves): every operand that passes through a staging launch anyway (weights,
+// transposed operands) gets its lo plane written there, ONCE per step, and TMA loads it next to the raw tile
+// (TC_A_PRE / TC_B_PRE); only operands that come straight from the producing kernel (activations, K-major) are split
+// inside this kernel by the builder warps.
+//
+// Persistent CTAs (one per SM), each looping over 128 x BN output tiles of the whole group, 6 warps:
+//   warp 0      TMA producer      raw fp32 tiles (BK = 32 floats = one 128-byte swizzle atom) (+ pre-split lo tiles) -> smem
+//                                 ring; runs ahead into the next tile while the current one drains
 //   warp 1      MMA issuer        one thread: 3 chains x 4 tcgen05.mma (M128 x BN x K8, kind::tf32) per stage, accumulators in TMEM
 //                                 (the tensor core's fp32 accumulate truncates, a bias that grows with the number of sequential
 //                                 accumulations: the hi.hi chain is therefore spread round-robin over three accumulators and the
 //                                 two small correction chains go to a fourth; the epilogue adds the four in IEEE fp32)
-//   warps 2..5  lo-part builders  lo = x - trunc_tf32(x) for the landed A and B tiles (elementwise, layout agnostic),
-//                                 then the epilogue: tcgen05.ld, bias / ReLU / ReLU-mask / tanh'-mask, global store
+//   warps 2..5  lo-part builders  lo = x - trunc_tf32(x) for the landed tiles that were not pre-split,
+//                                 then the epilogue: tcgen05.ld, transpose through a padded smem scratch so that every global
+//                                 access (C, ReLU / tanh' mask) is a coalesced 128-bit one, bias / ReLU / masks
 #pragma once
 #include <cuda.h>
 
@@ -32,9 +40,18 @@
 #define TC_THREADS 192
 #define TC_RING_BYTES 196608           // shared-memory ring; a stage is [A raw 16K | B raw BN*128 | A lo 16K | B lo BN*128]
 #define TC_SMEM_BYTES (TC_RING_BYTES + 1024)
+#define TC_EPI_LD 36                   // padded row of the epilogue scratch (floats): conflict-free 128-bit writes and reads
+
+#define TC_A_PRE (1 << 8)    // mapAlo / mapA2lo address a pre-split lo plane of A
+#define TC_B_PRE (1 << 9)    // same for B
+// profiling knobs (fb_gemm_tc_bench only; results are wrong when set): which part of the pipeline bounds a tile
+#define TC_DBG_NOBUILD (1 << 16)   // lo builders skip the split (arrive as soon as the raw tiles land)
+#define TC_DBG_ONECHAIN (1 << 17)  // the MMA warp issues only the hi.hi chain
+#define TC_DBG_NOEPI (1 << 18)     // epilogue skipped
 
 struct __align__(64) TcGemmDesc {
-  CUtensorMap mapA, mapB, mapA2, mapB2;  // box = 32 floats x 128 rows (A) / BN rows (B), SWIZZLE_128B
+  CUtensorMap mapA, mapB, mapA2, mapB2;          // box = 32 floats x 128 rows (A) / BN rows (B), SWIZZLE_128B
+  CUtensorMap mapAlo, mapBlo, mapA2lo, mapB2lo;  // lo planes (same geometry), valid with TC_A_PRE / TC_B_PRE
   float* C;
   const float* bias;
   const float* mask;
@@ -97,28 +114,65 @@ __device__ __forceinline__ void tc_tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __restrict__ descs, int nprob) {
+__device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float4 tc_lo4(const float4 x) {
+  float4 l;
+  l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+  l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+  l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+  l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+  return l;
+}
+
+// lo = x - trunc_tf32(x) over CNT float4 per thread (128 threads): all loads first, then the stores
+template <int CNT>
+__device__ __forceinline__ void tc_build_lo(const float4* __restrict__ raw, float4* __restrict__ lo, int t) {
+  float4 x[CNT];
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) x[i] = raw[t + i * 128];
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) lo[t + i * 128] = tc_lo4(x[i]);
+}
+
+// which problem / tile of the group is work item w
+__device__ __forceinline__ const TcGemmDesc* tc_locate(const TcGemmDesc* __restrict__ descs, int nprob, int w, int* m0, int* n0) {
+  int p = 0;
+  while (p + 1 < nprob && descs[p + 1].work_begin <= w) ++p;
+  const TcGemmDesc* d = &descs[p];
+  const int local = w - d->work_begin;
+  const int tm = local / d->tiles_n, tn = local - tm * d->tiles_n;
+  *m0 = tm * TC_BM; *n0 = tn * d->bn;
+  return d;
+}
+
+// ring_bn: B-tile rows the ring geometry is laid out for (>= every problem's bn); total: tiles of the whole group
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __restrict__ descs, int nprob, int total, int ring_bn) {
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+  __shared__ __align__(16) float epi_scratch[4 * 32 * TC_EPI_LD];
   __shared__ __align__(8) uint64_t bar_raw[TC_MAX_STAGES];    // TMA -> lo builders
   __shared__ __align__(8) uint64_t bar_ready[TC_MAX_STAGES];  // lo builders -> MMA issuer
   __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];  // MMA issuer (tcgen05.commit) -> TMA producer
-  __shared__ __align__(8) uint64_t bar_accum;             // all MMAs retired -> epilogue
+  __shared__ __align__(8) uint64_t bar_accum;                 // all MMAs of a tile retired -> epilogue
+  __shared__ __align__(8) uint64_t bar_tmem_empty;            // epilogue has read the accumulators -> MMA issuer (next tile)
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // locate this CTA's problem and tile
-  const int w = blockIdx.x;
-  int p = 0;
-  while (p + 1 < nprob && descs[p + 1].work_begin <= w) ++p;
-  const TcGemmDesc* __restrict__ d = &descs[p];
-  const int local = w - d->work_begin;
-  const int tm = local / d->tiles_n, tn = local - tm * d->tiles_n;
-  const int bn = d->bn;
-  const int m0 = tm * TC_BM, n0 = tn * bn;
-  const int nk1 = (d->K + TC_BK - 1) / TC_BK;
-  const int nk = nk1 + (d->K2 + TC_BK - 1) / TC_BK;
   // ring geometry: narrower B tiles leave room for more stages (3 at BN = 128, 4 at BN = 64 / 32)
-  const uint32_t half_bytes = 16384u + (uint32_t)bn * 128u;   // raw (or lo) part of a stage: A tile then B tile
+  const uint32_t b_off = 16384u;
+  const uint32_t half_bytes = 16384u + (uint32_t)ring_bn * 128u;   // raw (or lo) part of a stage: A tile then B tile
   const uint32_t stage_bytes = 2u * half_bytes;
   const int nst = min(TC_MAX_STAGES, (int)(TC_RING_BYTES / stage_bytes));
 
@@ -132,6 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       tc_mbar_init(&bar_empty[s], 1);
     }
     tc_mbar_init(&bar_accum, 1);
+    tc_mbar_init(&bar_tmem_empty, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -146,128 +201,157 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      const uint32_t tx_bytes = (uint32_t)(TC_BM + bn) * 128u;
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % nst;
-        if (kb >= nst) tc_mbar_wait(&bar_empty[s], ((kb / nst) - 1) & 1);
-        tc_mbar_expect_tx(&bar_raw[s], tx_bytes);
-        const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
-        if (kb < nk1) {
-          tc_tma_load_2d(st, &d->mapA, &bar_raw[s], kb * TC_BK, m0);
-          tc_tma_load_2d(st + 16384u, &d->mapB, &bar_raw[s], kb * TC_BK, n0);
-        } else {
-          tc_tma_load_2d(st, &d->mapA2, &bar_raw[s], (kb - nk1) * TC_BK, m0);
-          tc_tma_load_2d(st + 16384u, &d->mapB2, &bar_raw[s], (kb - nk1) * TC_BK, n0);
+      uint32_t kbg = 0;   // k-blocks issued by this CTA so far (ring position), across tiles
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        int m0, n0;
+        const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0);
+        const int bn = d->bn, flags = d->flags;
+        const int nk1 = (d->K + TC_BK - 1) / TC_BK;
+        const int nk = nk1 + (d->K2 + TC_BK - 1) / TC_BK;
+        const uint32_t tx_bytes = (uint32_t)TC_BM * 128u * ((flags & TC_A_PRE) ? 2u : 1u) + (uint32_t)bn * 128u * ((flags & TC_B_PRE) ? 2u : 1u);
+        for (int kb = 0; kb < nk; ++kb, ++kbg) {
+          const uint32_t s = kbg % (uint32_t)nst;
+          if (kbg >= (uint32_t)nst) tc_mbar_wait(&bar_empty[s], ((kbg / (uint32_t)nst) - 1u) & 1u);
+          tc_mbar_expect_tx(&bar_raw[s], tx_bytes);
+          const uint32_t st = smem_base + s * stage_bytes;
+          const bool second = kb >= nk1;
+          const int kc = (second ? kb - nk1 : kb) * TC_BK;
+          tc_tma_load_2d(st, second ? &d->mapA2 : &d->mapA, &bar_raw[s], kc, m0);
+          tc_tma_load_2d(st + b_off, second ? &d->mapB2 : &d->mapB, &bar_raw[s], kc, n0);
+          if (flags & TC_A_PRE) tc_tma_load_2d(st + half_bytes, second ? &d->mapA2lo : &d->mapAlo, &bar_raw[s], kc, m0);
+          if (flags & TC_B_PRE) tc_tma_load_2d(st + half_bytes + b_off, second ? &d->mapB2lo : &d->mapBlo, &bar_raw[s], kc, n0);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % nst;
-        tc_mbar_wait(&bar_ready[s], (kb / nst) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
-#pragma unroll
-        for (int chain = 0; chain < 3; ++chain) {   // (A raw, B raw), (A lo, B raw), (A raw, B lo)
-          const uint32_t a = st + (chain == 1 ? half_bytes : 0u);
-          const uint32_t b = st + 16384u + (chain == 2 ? half_bytes : 0u);
-          // accumulators: columns [j*bn, (j+1)*bn): j = kb % 3 for hi.hi, j = 3 for the two correction chains
-          const uint32_t acc = tmem_base + (uint32_t)(chain == 0 ? (kb % 3) : 3) * (uint32_t)bn;
-#pragma unroll
-          for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            const bool first = (ks == 0) && (chain == 0 ? kb < 3 : (kb == 0 && chain == 1));
-            tc_mma_tf32(acc, tc_umma_desc(a + ks * 32u), tc_umma_desc(b + ks * 32u), idesc, first ? 0u : 1u);
-          }
+      uint32_t kbg = 0, it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        int m0, n0;
+        const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0);
+        const int bn = d->bn;
+        const int nk = (d->K + TC_BK - 1) / TC_BK + (d->K2 + TC_BK - 1) / TC_BK;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        const int nchain = (d->flags & TC_DBG_ONECHAIN) ? 1 : 3;
+        if (it > 0) {   // the previous tile's accumulators must have been read out
+          tc_mbar_wait(&bar_tmem_empty, (it - 1u) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        tc_mma_commit(&bar_empty[s]);
+        for (int kb = 0; kb < nk; ++kb, ++kbg) {
+          const uint32_t s = kbg % (uint32_t)nst;
+          tc_mbar_wait(&bar_ready[s], (kbg / (uint32_t)nst) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_base + s * stage_bytes;
+#pragma unroll
+          for (int chain = 0; chain < 3; ++chain) {   // (A raw, B raw), (A lo, B raw), (A raw, B lo)
+            if (chain >= nchain) break;
+            const uint32_t a = st + (chain == 1 ? half_bytes : 0u);
+            const uint32_t b = st + b_off + (chain == 2 ? half_bytes : 0u);
+            // accumulators: columns [j*bn, (j+1)*bn): j = kb % 3 for hi.hi, j = 3 for the two correction chains
+            const uint32_t acc = tmem_base + (uint32_t)(chain == 0 ? (kb % 3) : 3) * (uint32_t)bn;
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+              const bool first = (ks == 0) && (chain == 0 ? kb < 3 : (kb == 0 && chain == 1));
+              tc_mma_tf32(acc, tc_umma_desc(a + ks * 32u), tc_umma_desc(b + ks * 32u), idesc, first ? 0u : 1u);
+            }
+          }
+          tc_mma_commit(&bar_empty[s]);
+        }
+        tc_mma_commit(&bar_accum);
       }
-      tc_mma_commit(&bar_accum);
     }
   } else {
     // ===== lo-part builders (128 threads), then epilogue =====
     const int t = threadIdx.x - 64;
-    const int nvec = (TC_BM + bn) * 8;   // float4s of the raw A and B tiles (contiguous: A 16 KB then B)
-    for (int kb = 0; kb < nk; ++kb) {
-      const int s = kb % nst;
-      tc_mbar_wait(&bar_raw[s], (kb / nst) & 1);
-      float4* raw = reinterpret_cast<float4*>(smem_gen + (size_t)s * stage_bytes);
-      float4* lo = raw + half_bytes / 16;
-#pragma unroll 4
-      for (int i = t; i < nvec; i += 128) {
-        const float4 x = raw[i];
-        float4 l;
-        l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-        l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-        l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-        l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-        lo[i] = l;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
-      tc_mbar_arrive(&bar_ready[s]);
-    }
-    tc_mbar_wait(&bar_accum, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < d->M;
+    float* scr = epi_scratch + q * (32 * TC_EPI_LD);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int flags = d->flags, N = d->N, ldc = d->ldc, ldmask = d->ldmask;
-    const float* __restrict__ bias = d->bias;
-    const float* __restrict__ mask = d->mask;
-    float* __restrict__ C = d->C;
-    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
-    const int n_hh = nk < 3 ? nk : 3;   // hi.hi accumulators that were written
-    for (int cb = 0; cb < bn; cb += 16) {
-      float v[16], u[16];
-      tc_tmem_ld16(lane_addr + (uint32_t)(3 * bn + cb), v);   // correction chains first (smallest terms)
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      for (int a = n_hh - 1; a >= 0; --a) {
-        tc_tmem_ld16(lane_addr + (uint32_t)(a * bn + cb), u);
+    uint32_t kbg = 0, it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      int m0, n0;
+      const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0);
+      const int bn = d->bn, flags = d->flags;
+      const int nk = (d->K + TC_BK - 1) / TC_BK + (d->K2 + TC_BK - 1) / TC_BK;
+      const bool build_a = !(flags & (TC_A_PRE | TC_DBG_NOBUILD)), build_b = !(flags & (TC_B_PRE | TC_DBG_NOBUILD));
+      for (int kb = 0; kb < nk; ++kb, ++kbg) {
+        const uint32_t s = kbg % (uint32_t)nst;
+        tc_mbar_wait(&bar_raw[s], (kbg / (uint32_t)nst) & 1u);
+        const float4* raw = reinterpret_cast<const float4*>(smem_gen + (size_t)s * stage_bytes);
+        float4* lo = reinterpret_cast<float4*>(smem_gen + (size_t)s * stage_bytes + half_bytes);
+        if (build_a) tc_build_lo<8>(raw, lo, t);                       // A tile: 128 rows x 128 B = 1024 float4
+        if (build_b) {                                                 // B tile: bn rows x 128 B
+          if (bn == 128) tc_build_lo<8>(raw + 1024, lo + 1024, t);
+          else if (bn == 64) tc_build_lo<4>(raw + 1024, lo + 1024, t);
+          else tc_build_lo<2>(raw + 1024, lo + 1024, t);
+        }
+        if (build_a || build_b) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy
+        tc_mbar_arrive(&bar_ready[s]);
+      }
+      tc_mbar_wait(&bar_accum, it & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+      const int M = d->M, N = d->N, ldc = d->ldc, ldmask = d->ldmask;
+      const float* __restrict__ bias = d->bias;
+      const float* __restrict__ mask = d->mask;
+      float* __restrict__ C = d->C;
+      const bool c_vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+      const bool m_vec = ((ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
+      const bool b_vec = (reinterpret_cast<uintptr_t>(bias) & 15u) == 0;
+      const int n_hh = nk < 3 ? nk : 3;   // hi.hi accumulators that were written
+      const int sub = lane >> 3, c4 = (lane & 7) * 4;
+      for (int cb = 0; cb < ((flags & TC_DBG_NOEPI) ? 0 : bn); cb += 32) {
+        if (n0 + cb >= N) break;          // warp-uniform: nothing of this 32-column chunk is inside the matrix
+        float v[32], u[32];
+        tc_tmem_ld32(lane_addr + (uint32_t)(3 * bn + cb), v);   // correction chains first (smallest terms)
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int a = n_hh - 1; a >= 0; --a) {
+          tc_tmem_ld32(lane_addr + (uint32_t)(a * bn + cb), u);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += u[j];
-      }
-      const int col0 = n0 + cb;
-      if (!row_ok || col0 >= N) continue;
-      float mk[16];
-      if (flags & (GF_MASK_RELU | GF_MASK_TANH)) {   // the saved activation of this row: 4 x 128-bit loads when aligned
-        const float* mp = mask + (size_t)row * ldmask + col0;
-        if (((ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0) && col0 + 15 < N) {
+          for (int j = 0; j < 32; ++j) v[j] += u[j];
+        }
+        // thread = one row of the chunk -> scratch -> thread = 4 consecutive columns of 8 different rows
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(mp + j));
-            mk[j] = t4.x; mk[j + 1] = t4.y; mk[j + 2] = t4.z; mk[j + 3] = t4.w;
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(scr + lane * TC_EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const int col = n0 + cb + c4;
+        float bz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (bias && col < N) {
+          if (b_vec && col + 3 < N) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + col)); bz[0] = t4.x; bz[1] = t4.y; bz[2] = t4.z; bz[3] = t4.w; }
+          else { for (int j = 0; j < 4; ++j) if (col + j < N) bz[j] = __ldg(bias + col + j); }
+        }
+#pragma unroll
+        for (int r8 = 0; r8 < 8; ++r8) {
+          const int r = r8 * 4 + sub;
+          const int row = m0 + q * 32 + r;
+          const float4 x4 = *reinterpret_cast<const float4*>(scr + r * TC_EPI_LD + c4);
+          if (row >= M || col >= N) continue;
+          float x[4] = {x4.x + bz[0], x4.y + bz[1], x4.z + bz[2], x4.w + bz[3]};
+          const bool full = col + 3 < N;
+          if (flags & GF_RELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
           }
-        } else {
+          if (flags & (GF_MASK_RELU | GF_MASK_TANH)) {
+            const float* mp = mask + (size_t)row * ldmask + col;
+            float mk[4] = {0.f, 0.f, 0.f, 0.f};
+            if (m_vec && full) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(mp)); mk[0] = t4.x; mk[1] = t4.y; mk[2] = t4.z; mk[3] = t4.w; }
+            else { for (int j = 0; j < 4; ++j) if (col + j < N) mk[j] = __ldg(mp + j); }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) mk[j] = (col0 + j < N) ? __ldg(mp + j) : 0.f;
+            for (int j = 0; j < 4; ++j) {
+              if (flags & GF_MASK_RELU) x[j] = (mk[j] > 0.f) ? x[j] : 0.f;
+              if (flags & GF_MASK_TANH) x[j] *= (1.f - mk[j] * mk[j]);
+            }
+          }
+          float* cp = C + (size_t)row * ldc + col;
+          if (c_vec && full) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+          else { for (int j = 0; j < 4; ++j) if (col + j < N) cp[j] = x[j]; }
         }
+        __syncwarp();
       }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = col0 + j;
-        if (col < N) {
-          float x = v[j];
-          if (bias) x += __ldg(bias + col);
-          if (flags & GF_RELU) x = fmaxf(x, 0.f);
-          if (flags & GF_MASK_RELU) x = (mk[j] > 0.f) ? x : 0.f;
-          if (flags & GF_MASK_TANH) x *= (1.f - mk[j] * mk[j]);
-          v[j] = x;
-        }
-      }
-      float* cp = C + (size_t)row * ldc + col0;
-      if (vec_ok && col0 + 15 < N) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (col0 + j < N) cp[j] = v[j];
-      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      tc_mbar_arrive(&bar_tmem_empty);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -278,8 +362,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
 }
 
 // operand staging for the tensor-core GEMM: out = in^T (transpose = 1) or an aligned copy of in (transpose = 0), with a
-// 16-byte aligned base and leading dimension so that TMA can address it.  32 x 32 tiles through shared memory.
-struct TransposeDesc { const float* in; float* out; int rows, cols, ld_in, ld_out, transpose, cta_begin, ctas_x; };
+// 16-byte aligned base and leading dimension so that TMA can address it; out_lo (optional) receives the lo plane
+// x - trunc_tf32(x) of the same elements (out may then be null: the source itself is TMA-addressable and only its lo plane
+// is wanted).  32 x 32 tiles through shared memory.
+struct TransposeDesc { const float* in; float* out; float* out_lo; int rows, cols, ld_in, ld_out, transpose, cta_begin, ctas_x; };
+
+__device__ __forceinline__ float tc_lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 __global__ void __launch_bounds__(256) k_transpose_grouped(const TransposeDesc* __restrict__ descs, int nprob) {
   __shared__ float tile[32][33];
@@ -292,7 +380,11 @@ __global__ void __launch_bounds__(256) k_transpose_grouped(const TransposeDesc* 
   if (!d.transpose) {
     for (int j = ty; j < 32; j += 8) {
       const int r = by * 32 + j, c = bx * 32 + tx;
-      if (r < d.rows && c < d.cols) d.out[(size_t)r * d.ld_out + c] = d.in[(size_t)r * d.ld_in + c];
+      if (r < d.rows && c < d.cols) {
+        const float x = d.in[(size_t)r * d.ld_in + c];
+        if (d.out) d.out[(size_t)r * d.ld_out + c] = x;
+        if (d.out_lo) d.out_lo[(size_t)r * d.ld_out + c] = tc_lo1(x);
+      }
     }
     return;
   }
@@ -303,6 +395,10 @@ __global__ void __launch_bounds__(256) k_transpose_grouped(const TransposeDesc* 
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
     const int c = bx * 32 + j, r = by * 32 + tx;
-    if (c < d.cols && r < d.rows) d.out[(size_t)c * d.ld_out + r] = tile[tx][j];
+    if (c < d.cols && r < d.rows) {
+      const float x = tile[tx][j];
+      d.out[(size_t)c * d.ld_out + r] = x;
+      if (d.out_lo) d.out_lo[(size_t)c * d.ld_out + r] = tc_lo1(x);
+    }
   }
 }

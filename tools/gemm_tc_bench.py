@@ -1,0 +1,34 @@
+"""Where does a k_gemm_tc tile spend its time?  Runs the tcgen05 grouped GEMM on the step's problem shapes with the
+profiling knobs of fb_gemm_tc_bench.  GPU only."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from controllable_agent_b200 import _lib as L  # noqa: E402
+
+NOBUILD, ONECHAIN, NOEPI, PRE_B, PRE_A = 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20
+
+
+def main() -> None:
+    lib = L.load()
+    s = torch.cuda.current_stream().cuda_stream
+    ms = C.c_float()
+    shapes = [(1024, 1024, 1024, 128, 4), (1024, 1024, 1024, 128, 1), (1024, 512, 1024, 128, 5), (1024, 1024, 1024, 64, 1),
+              (1024, 50, 1024, 64, 4), (1024, 50, 1024, 32, 4), (1024, 1024, 50 // 4 * 4 + 4, 128, 4), (4096, 4096, 4096, 128, 1)]
+    for (M, N, K, bn, nprob) in shapes:
+        row = []
+        for dbg in (0, PRE_B, PRE_A | PRE_B, NOBUILD, NOBUILD | ONECHAIN, NOBUILD | ONECHAIN | NOEPI, NOEPI):
+            L.check(lib.fb_gemm_tc_bench(M, N, K, bn, nprob, dbg, 20, C.byref(ms), s))
+            row.append(ms.value * 1e3)
+        fl = 2.0 * M * N * K * nprob
+        tiles = -(-M // 128) * -(-N // bn) * nprob
+        print(f"M={M} N={N} K={K} bn={bn} x{nprob} ({tiles} tiles): build A+B {row[0]:7.1f} us ({fl / row[0] / 1e6:6.1f} TF/s) | "
+              f"pre-split B {row[1]:7.1f} ({fl / row[1] / 1e6:6.1f}) | pre-split A+B {row[2]:7.1f} ({fl / row[2] / 1e6:6.1f}) | nobuild {row[3]:7.1f} | "
+              f"nobuild+1chain {row[4]:7.1f} | +noepi {row[5]:7.1f} | noepi {row[6]:7.1f}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
