@@ -103,7 +103,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "fb_replay_gather": (_i, [C.POINTER(fb_replay_view), _i, _i, _vp, _vp, _vp, _i, _f, _vp, _i, _vp]),
     "fb_replay_pack_episode": (_i, [C.POINTER(fb_replay_view), _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fb_sgemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "fb_gemm_tc_bench": (_i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float), _vp]),
+    "fb_gemm_tc_bench": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float), _vp]),
     "fb_fp32_peak_tflops": (_i, [C.POINTER(C.c_double), _vp]),
 }
 

@@ -54,11 +54,15 @@ struct Builder {
 
   // can this problem run on the tensor cores (gemm_tc.cuh)?  Operands TMA cannot address directly are staged (see stage_operand)
   bool tc_ok(const GemmDesc& g) const {
-    if (h->cfg.mlp_mode != FB_MLP_TCGEN05 || (g.flags & GF_SHARED_C) || g.M < 8 || g.K < 8) return false;
-    // a first-layer product (K = obs + action / z, tens of columns) whose weight would need an aligned staged copy is
-    // cheaper on the SIMT kernel than a staging launch plus a tensor-core launch
-    const bool a_direct = g.a_kmajor && aligned16(g.A) && g.lda % 4 == 0, b_direct = g.b_kmajor && aligned16(g.B) && g.ldb % 4 == 0;
-    if (g.K < 128 && g.a_kmajor && g.b_kmajor && !(a_direct && b_direct)) return false;
+    if (h->cfg.mlp_mode != FB_MLP_TCGEN05 || (g.flags & GF_SHARED_C) || g.K < 8) return false;
+    // a first-layer product (K = obs + action / z, tens of columns): its weight is staged anyway (pre-split lo plane, early on
+    // the side lane); only an activation operand that would need a late staging launch keeps it on the SIMT kernel
+    const bool a_direct = g.a_kmajor && aligned16(g.A) && g.lda % 4 == 0;
+    if (g.K < 128 && g.a_kmajor && g.b_kmajor && !(a_direct || is_early(g.A))) return false;
+    if (getenv("FB_TC_STRICT")) {   // debugging: the narrower rule of the first tensor-core plan
+      const bool b_direct = g.b_kmajor && aligned16(g.B) && g.ldb % 4 == 0;
+      if (g.M < 8 || (g.K < 128 && g.a_kmajor && g.b_kmajor && !(a_direct && b_direct))) return false;
+    }
     return true;
   }
   // K-major, TMA-addressable view of an operand: the operand itself when it already is one, otherwise a staged copy
@@ -78,6 +82,11 @@ struct Builder {
   // copy).  *lo_out receives the operand's pre-split lo plane when one is produced: always for staged copies (the staging
   // launch writes it for free), and for directly addressable operands only if `want_lo` and the source is final when the
   // phase starts (weights: a lo-only staging entry on the side lane).
+  bool in_grad(const float* p) const {
+    const fb_buffers& bf = h->bufs;
+    return (bf.d_grad_fb && p >= bf.d_grad_fb && p < bf.d_grad_fb + h->seg_fb.size) ||
+           (bf.d_grad_actor && p >= bf.d_grad_actor && p < bf.d_grad_actor + h->seg_actor.size);
+  }
   const float* stage_operand(std::vector<TransposeDesc>& pending, bool* used_early, const float* p, int kmajor, int rows, int K, int ld,
                              bool want_lo, int* ld_out, const float** lo_out, int* ld_lo) {
     const bool direct = kmajor && aligned16(p) && ld % 4 == 0;
@@ -121,6 +130,14 @@ struct Builder {
       for (const GemmDesc& s : g) tiles += fb_ceil_div(s.M, TC_BM) * fb_ceil_div(s.N, cand);
       if (tiles >= 120) { bn_group = cand; break; }
     }
+    // split-K: when the launch is a few long k-chains (narrow outputs with K = hidden / batch), the chain latency bounds it and
+    // most SMs idle; such problems are cut into k-ranges of about the launch's mean work per SM, added into a zeroed C
+    double kb_work = 0.0;
+    for (const GemmDesc& s : g) {
+      const int bn = std::min(bn_group, s.N <= 32 ? 32 : (s.N <= 64 ? 64 : 128));
+      kb_work += (double)fb_ceil_div(s.M, TC_BM) * fb_ceil_div(s.N, bn) * (fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK));
+    }
+    const int kb_target = std::max(4, (int)(kb_work / FB_SM_COUNT + 0.999));
     int ring_bn = 32;
     for (const GemmDesc& s : g) {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
@@ -130,7 +147,22 @@ struct Builder {
       if (d.bn > bn_group) d.bn = bn_group;
       if (d.bn > ring_bn) ring_bn = d.bn;
       d.tiles_m = fb_ceil_div(s.M, TC_BM); d.tiles_n = fb_ceil_div(s.N, d.bn);
-      d.work_begin = work; d.work_count = d.tiles_m * d.tiles_n; work += d.work_count;
+      d.splitk = 1; d.kb_per_split = fb_ceil_div(s.K, TC_BK);
+      if (s.K2 == 0 && !(s.flags & GF_RELU) && !getenv("FB_NO_SPLITK")) {
+        const int nkb = fb_ceil_div(s.K, TC_BK);
+        int sk = std::min(8, fb_ceil_div(nkb, kb_target));
+        if (sk > 1) {
+          d.kb_per_split = fb_ceil_div(nkb, sk);
+          d.splitk = fb_ceil_div(nkb, d.kb_per_split);   // every k-range non-empty
+        }
+      }
+      if (d.splitk > 1 && !in_grad(s.C)) {   // gradients are cleared by k_adam; any other split-K output is zeroed at phase start
+        TransposeDesc z; memset(&z, 0, sizeof(z));
+        z.out = s.C; z.rows = s.M; z.cols = s.N; z.ld_out = s.ldc; z.transpose = 2;
+        if (cur_lane == 1 && phase == phase_index(FB_PHASE_MIX)) pending.push_back(z);   // side-lane chain: right before the launch
+        else { h->early_stage[phase].push_back(z); used_early = true; }
+      }
+      d.work_begin = work; d.work_count = d.tiles_m * d.tiles_n * d.splitk; work += d.work_count;
       int lda = 0, ldb = 0, lda2 = 0, ldb2 = 0, ldal = 0, ldbl = 0, ldal2 = 0, ldbl2 = 0;
       const float *Alo = nullptr, *Blo = nullptr, *A2lo = nullptr, *B2lo = nullptr;
       const float* A1 = stage_operand(pending, &used_early, s.A, s.a_kmajor, s.M, s.K, s.lda, false, &lda, &Alo, &ldal);
@@ -163,7 +195,7 @@ struct Builder {
       double tbytes = 0.0;
       for (auto& t : pending) {
         t.cta_begin = ctas; t.ctas_x = fb_ceil_div(t.cols, 32); ctas += t.ctas_x * fb_ceil_div(t.rows, 32);
-        tbytes += (t.out ? 12.0 : 8.0) * t.rows * (double)t.cols;
+        tbytes += (t.transpose == 2 ? 4.0 : (t.out ? 12.0 : 8.0)) * t.rows * (double)t.cols;
       }
       const TransposeDesc* td = arena_put(h, pending, d_arena);
       const int nt = (int)pending.size();
@@ -794,7 +826,7 @@ static int build_plan(fb_handle* h) {
     double tbytes = 0.0;
     for (auto& t : tv) {
       t.cta_begin = ctas; t.ctas_x = fb_ceil_div(t.cols, 32); ctas += t.ctas_x * fb_ceil_div(t.rows, 32);
-      tbytes += (t.out ? 12.0 : 8.0) * t.rows * (double)t.cols;
+      tbytes += (t.transpose == 2 ? 4.0 : (t.out ? 12.0 : 8.0)) * t.rows * (double)t.cols;
     }
     const TransposeDesc* td = arena_put(h, tv, d_arena);
     const int nt = (int)tv.size();
@@ -1252,7 +1284,7 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
   if (tile_cfg > 3) return FB_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (tile_cfg == 3) {  // tcgen05 3xTF32 kernel
-    if (!a_kmajor || splitk > 1 || !aligned16(dA) || lda % 4) return FB_E_UNSUPPORTED;
+    if (!a_kmajor || !aligned16(dA) || lda % 4) return FB_E_UNSUPPORTED;
     const float* Bp = dB;
     int ldbp = ldb;
     float *tmp = nullptr, *tmp_lo = nullptr;
@@ -1275,7 +1307,14 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
     }
     TcGemmDesc d; memset(&d, 0, sizeof(d));
     d.C = dC; d.bias = d_bias; d.M = M; d.N = N; d.K = K; d.ldc = ldc; d.flags = relu ? GF_RELU : 0; d.bn = N > 64 ? 128 : 64;
-    d.tiles_m = fb_ceil_div(M, TC_BM); d.tiles_n = fb_ceil_div(N, d.bn); d.work_begin = 0; d.work_count = d.tiles_m * d.tiles_n;
+    d.tiles_m = fb_ceil_div(M, TC_BM); d.tiles_n = fb_ceil_div(N, d.bn); d.work_begin = 0;
+    d.splitk = 1; d.kb_per_split = fb_ceil_div(K, TC_BK);
+    if (splitk > 1) {   // C must be zeroed by the caller
+      if (relu) return FB_E_ARG;
+      d.kb_per_split = fb_ceil_div(d.kb_per_split, splitk);
+      d.splitk = fb_ceil_div(fb_ceil_div(K, TC_BK), d.kb_per_split);
+    }
+    d.work_count = d.tiles_m * d.tiles_n * d.splitk;
     int rc = encode_tiled_map(&d.mapA, dA, M, K, lda, TC_BM);
     if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, Bp, N, K, ldbp, d.bn);
     if (rc == FB_OK && tmp_lo) { rc = encode_tiled_map(&d.mapBlo, tmp_lo, N, K, ldbp, d.bn); d.flags |= TC_B_PRE; }
@@ -1314,7 +1353,7 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
 
 // Timing harness of the tcgen05 grouped GEMM on one synthetic problem replicated `nprob` times (a "group"): `reps` back-to-back
 // launches between two CUDA events.  dbg = TC_DBG_* knobs (0: the product kernel).  Synchronises; allocates its own operands.
-int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int dbg, int reps, float* ms_per_launch, void* stream) {
+int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int splitk, int dbg, int reps, float* ms_per_launch, void* stream) {
   if (M < 1 || N < 1 || K < 8 || K % 4 || nprob < 1 || nprob > 16 || reps < 1 || !ms_per_launch) return FB_E_ARG;
   if (bn != 32 && bn != 64 && bn != 128) return FB_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1335,7 +1374,10 @@ int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int dbg, int reps, 
   for (int i = 0; i < nprob && rc == FB_OK; ++i) {
     TcGemmDesc& d = v[i]; memset(&d, 0, sizeof(d));
     d.C = Cm + (size_t)i * M * N; d.M = M; d.N = N; d.K = K; d.ldc = N; d.flags = dbg; d.bn = bn;
-    d.tiles_m = fb_ceil_div(M, TC_BM); d.tiles_n = fb_ceil_div(N, bn); d.work_begin = work; d.work_count = d.tiles_m * d.tiles_n;
+    d.tiles_m = fb_ceil_div(M, TC_BM); d.tiles_n = fb_ceil_div(N, bn); d.work_begin = work;
+    d.splitk = 1; d.kb_per_split = fb_ceil_div(K, TC_BK);
+    if (splitk > 1) { d.kb_per_split = fb_ceil_div(d.kb_per_split, splitk); d.splitk = fb_ceil_div(fb_ceil_div(K, TC_BK), d.kb_per_split); }
+    d.work_count = d.tiles_m * d.tiles_n * d.splitk;
     work += d.work_count;
     rc = encode_tiled_map(&d.mapA, A + (size_t)i * M * K, M, K, K, TC_BM);
     if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, B + (size_t)i * N * K, N, K, K, bn);

@@ -58,6 +58,7 @@ struct __align__(64) TcGemmDesc {
   int M, N, K, K2;
   int ldc, ldmask, flags, bn;
   int tiles_m, tiles_n, work_begin, work_count;
+  int splitk, kb_per_split;   // splitk > 1: a tile's k-blocks are shared by splitk work items that add into a zeroed C (K2 = 0, no ReLU)
 };
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,12 +148,22 @@ __device__ __forceinline__ void tc_build_lo(const float4* __restrict__ raw, floa
   for (int i = 0; i < CNT; ++i) lo[t + i * 128] = tc_lo4(x[i]);
 }
 
-// which problem / tile of the group is work item w
-__device__ __forceinline__ const TcGemmDesc* tc_locate(const TcGemmDesc* __restrict__ descs, int nprob, int w, int* m0, int* n0) {
+// which problem / tile / k-range of the group is work item w
+__device__ __forceinline__ const TcGemmDesc* tc_locate(const TcGemmDesc* __restrict__ descs, int nprob, int w, int* m0, int* n0, int* kb0,
+                                                       int* kb1) {
   int p = 0;
   while (p + 1 < nprob && descs[p + 1].work_begin <= w) ++p;
   const TcGemmDesc* d = &descs[p];
-  const int local = w - d->work_begin;
+  int local = w - d->work_begin;
+  const int nk = (d->K + TC_BK - 1) / TC_BK + (d->K2 + TC_BK - 1) / TC_BK;
+  if (d->splitk > 1) {
+    const int split = local % d->splitk;
+    local /= d->splitk;
+    *kb0 = split * d->kb_per_split;
+    *kb1 = min(nk, *kb0 + d->kb_per_split);
+  } else {
+    *kb0 = 0; *kb1 = nk;
+  }
   const int tm = local / d->tiles_n, tn = local - tm * d->tiles_n;
   *m0 = tm * TC_BM; *n0 = tn * d->bn;
   return d;
@@ -203,13 +214,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       // ===== TMA producer =====
       uint32_t kbg = 0;   // k-blocks issued by this CTA so far (ring position), across tiles
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        int m0, n0;
-        const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0);
+        int m0, n0, kb0, kb1;
+        const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0, &kb0, &kb1);
         const int bn = d->bn, flags = d->flags;
         const int nk1 = (d->K + TC_BK - 1) / TC_BK;
-        const int nk = nk1 + (d->K2 + TC_BK - 1) / TC_BK;
         const uint32_t tx_bytes = (uint32_t)TC_BM * 128u * ((flags & TC_A_PRE) ? 2u : 1u) + (uint32_t)bn * 128u * ((flags & TC_B_PRE) ? 2u : 1u);
-        for (int kb = 0; kb < nk; ++kb, ++kbg) {
+        for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)nst;
           if (kbg >= (uint32_t)nst) tc_mbar_wait(&bar_empty[s], ((kbg / (uint32_t)nst) - 1u) & 1u);
           tc_mbar_expect_tx(&bar_raw[s], tx_bytes);
@@ -228,10 +238,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       // ===== MMA issuer =====
       uint32_t kbg = 0, it = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-        int m0, n0;
-        const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0);
+        int m0, n0, kb0, kb1;
+        const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0, &kb0, &kb1);
         const int bn = d->bn;
-        const int nk = (d->K + TC_BK - 1) / TC_BK + (d->K2 + TC_BK - 1) / TC_BK;
+        const int nk = kb1 - kb0;
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
         const int nchain = (d->flags & TC_DBG_ONECHAIN) ? 1 : 3;
         if (it > 0) {   // the previous tile's accumulators must have been read out
@@ -269,10 +279,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t kbg = 0, it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-      int m0, n0;
-      const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0);
+      int m0, n0, kb0, kb1;
+      const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0, &kb0, &kb1);
       const int bn = d->bn, flags = d->flags;
-      const int nk = (d->K + TC_BK - 1) / TC_BK + (d->K2 + TC_BK - 1) / TC_BK;
+      const int nk = kb1 - kb0;
       const bool build_a = !(flags & (TC_A_PRE | TC_DBG_NOBUILD)), build_b = !(flags & (TC_B_PRE | TC_DBG_NOBUILD));
       for (int kb = 0; kb < nk; ++kb, ++kbg) {
         const uint32_t s = kbg % (uint32_t)nst;
@@ -300,6 +310,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       const bool b_vec = (reinterpret_cast<uintptr_t>(bias) & 15u) == 0;
       const int n_hh = nk < 3 ? nk : 3;   // hi.hi accumulators that were written
       const int sub = lane >> 3, c4 = (lane & 7) * 4;
+      const bool split = d->splitk > 1;   // partial sums: added into the zeroed C; the bias rides on the first k-range
+      if (split && kb0 > 0) bias = nullptr;
       for (int cb = 0; cb < ((flags & TC_DBG_NOEPI) ? 0 : bn); cb += 32) {
         if (n0 + cb >= N) break;          // warp-uniform: nothing of this 32-column chunk is inside the matrix
         float v[32], u[32];
@@ -345,7 +357,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
             }
           }
           float* cp = C + (size_t)row * ldc + col;
-          if (c_vec && full) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+          if (split) {
+            if (c_vec && full) atomicAdd(reinterpret_cast<float4*>(cp), make_float4(x[0], x[1], x[2], x[3]));
+            else { for (int j = 0; j < 4; ++j) if (col + j < N) atomicAdd(cp + j, x[j]); }
+          } else if (c_vec && full) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
           else { for (int j = 0; j < 4; ++j) if (col + j < N) cp[j] = x[j]; }
         }
         __syncwarp();
@@ -364,7 +379,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
 // operand staging for the tensor-core GEMM: out = in^T (transpose = 1) or an aligned copy of in (transpose = 0), with a
 // 16-byte aligned base and leading dimension so that TMA can address it; out_lo (optional) receives the lo plane
 // x - trunc_tf32(x) of the same elements (out may then be null: the source itself is TMA-addressable and only its lo plane
-// is wanted).  32 x 32 tiles through shared memory.
+// is wanted).  transpose = 2: zero-fill out (rows x cols).  32 x 32 tiles through shared memory.
 struct TransposeDesc { const float* in; float* out; float* out_lo; int rows, cols, ld_in, ld_out, transpose, cta_begin, ctas_x; };
 
 __device__ __forceinline__ float tc_lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
@@ -377,6 +392,13 @@ __global__ void __launch_bounds__(256) k_transpose_grouped(const TransposeDesc* 
   const int local = blockIdx.x - d.cta_begin;
   const int bx = local % d.ctas_x, by = local / d.ctas_x;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (d.transpose == 2) {   // zero fill (outputs of split-K GEMMs)
+    for (int j = ty; j < 32; j += 8) {
+      const int r = by * 32 + j, c = bx * 32 + tx;
+      if (r < d.rows && c < d.cols) d.out[(size_t)r * d.ld_out + c] = 0.f;
+    }
+    return;
+  }
   if (!d.transpose) {
     for (int j = ty; j < 32; j += 8) {
       const int r = by * 32 + j, c = bx * 32 + tx;

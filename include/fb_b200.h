@@ -217,16 +217,16 @@ int fb_replay_pack_episode(const fb_replay_view* view, float* d_rows_mut, int sl
                            const float* d_obs, const float* d_action, const float* d_reward, const float* d_discount,
                            const float* d_goal, const float* d_extra, void* stream);
 /* C[M,N] (+)= op(A)·op(B)^T with the grouped SIMT SGEMM used by the plan (single problem).  tile_cfg: -1 automatic,
- * 0 = 128x128, 1 = 64x64, 2 = 128x64 CTA tile, 3 = the tcgen05 3xTF32 kernel (a_kmajor = 1, 16-byte aligned operands,
- * splitk = 1; synchronises).  splitk > 1 accumulates into C with atomics (C must be zeroed). */
+ * 0 = 128x128, 1 = 64x64, 2 = 128x64 CTA tile, 3 = the tcgen05 3xTF32 kernel (a_kmajor = 1, 16-byte aligned operands;
+ * synchronises).  splitk > 1 accumulates into C with atomics (C must be zeroed). */
 int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, int M, int N, int K, int lda, int ldb,
              int ldc, int a_kmajor, int b_kmajor, int relu, int splitk, int tile_cfg, void* stream);
 /* Timing harness of the tcgen05 3xTF32 grouped GEMM (the kernel behind every wide nn.Linear product, fb_modules.py:76 and its
  * autograd): one synthetic [M,K]x[N,K]^T problem replicated nprob times in one launch, tile width bn (32/64/128), `reps` launches
- * between two CUDA events -> *ms_per_launch.  dbg: 0 = the product kernel with both operands split in shared memory; 1<<19 / 1<<20 =
+ * between two CUDA events -> *ms_per_launch; splitk > 1 cuts every tile's K into that many work items.  dbg: 0 = the product kernel with both operands split in shared memory; 1<<19 / 1<<20 =
  * B / A operand with a pre-split lo plane (what the plan does for staged operands); 1<<16 no lo-split, 1<<17 one MMA chain,
  * 1<<18 no epilogue (profiling knobs, results invalid).  Synchronises; allocates its operands from the stream's pool. */
-int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int dbg, int reps, float* ms_per_launch, void* stream);
+int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int splitk, int dbg, int reps, float* ms_per_launch, void* stream);
 /* FMA-chain microbenchmark: returns measured fp32 TFLOP/s of the CUDA cores (synchronises) */
 int fb_fp32_peak_tflops(double* out_tflops, void* stream);
 

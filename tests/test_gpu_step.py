@@ -159,20 +159,40 @@ def _to(p, dt):
     return {k: v.to(dt) for k, v in p.items()}
 
 
-def test_full_width_step_against_oracle():
+class _ForcedRelu:
+    """Stand-in for torch.relu inside the oracle: every ReLU takes the branch the engine took (mask = the engine's saved
+    activation > 0), so that the two evaluate the SAME piece of the piecewise-linear network.  Records how many units
+    the oracle itself would have switched differently and how close to zero their pre-activations were."""
+
+    def __init__(self, masks):
+        self.masks, self.i, self.flips, self.worst = masks, 0, 0, 0.0
+
+    def __call__(self, x):
+        m = self.masks[self.i].to(x.dtype)
+        self.i += 1
+        assert m.shape == x.shape, (self.i, m.shape, x.shape)
+        diff = (x > 0) != (m > 0)
+        if bool(diff.any()):
+            self.flips += int(diff.sum())
+            self.worst = max(self.worst, float(x.detach().abs()[diff].max() / x.detach().abs().mean()))
+        return x * m
+
+
+def test_full_width_step_against_oracle(monkeypatch):
     """Default widths of the reference config (hidden 1024, feature 512, backward hidden 526, z 50, obs 24, act 6) at
     batch 256 (BASELINE.json configs[0]); oracle on CPU from the same seeded parameters and inputs.
 
-    The oracle is evaluated twice: in fp32 (the reference's arithmetic) and in fp64 (exact for this purpose).  At these
-    widths the fp32 reference itself sits ~1.5e-3 away from the exact gradient on some tensors (a ReLU unit whose
-    pre-activation is ~0 flips between summation orders; SURVEY.md 7.3 measured 9e-4 between 1 and 8 CPU threads), so the
-    1e-3 gate against fp32 cannot be met by ANY independent fp32 evaluation of such a tensor.  Gates: tensors behind no ReLU
-    (the last Linear of every head: no flip possible) within 1e-4 of exact; every other tensor within 2e-4 of the exact or of
-    the fp32 reference gradient, or else inside the flip-noise band 1e-3 + 2 x (the reference's own distance from exact)
-    of both."""
+    At these widths (1.3 M ReLU units per step) some pre-activation is always within fp32 rounding of zero, and such a
+    unit switches between summation orders: the reference's own fp32 evaluation sits up to ~6e-3 from the exact gradient
+    on whole tensors for that reason alone (SURVEY.md 7.3 measured 9e-4 between 1 and 8 CPU threads), so a per-tensor
+    1e-3 gate against ONE fp32 evaluation cannot be met by any independent evaluation.  The test therefore pins the
+    branch: the fp64 oracle is evaluated with every ReLU taking the branch the engine took (_ForcedRelu), which must
+    differ from the oracle's own choice only on units whose pre-activation is ~0 (|x| < 1e-4 of the layer's mean |x|,
+    and only a handful of them); on that common branch every gradient tensor must match to 2e-4 (observed ~3e-6), the
+    losses / metrics to 1e-3 against the unforced fp32 oracle."""
     L = _L()
     d = O.Dims()
-    B = 256
+    B, Fd = 256, d.feature_dim
     gen = torch.Generator().manual_seed(11)
     actor = O.init_params(O.actor_spec(d), gen)
     fwd = O.init_params(O.forward_map_spec(d), gen)
@@ -202,40 +222,73 @@ def test_full_width_step_against_oracle():
     eng.run(L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD | L.PHASE_METRICS)
     torch.cuda.synchronize()
     assert rel(eng.view("z"), z) < 1e-5
-    zz = eng.view("z").detach().cpu()   # evaluate both oracles on the engine's z so that the mix forward is not compared twice
+    zz = eng.view("z").detach().cpu()   # evaluate the oracles on the engine's z so that the mix forward is not compared twice
     f32, f64 = torch.float32, torch.float64
-    ora = {dt: O.fb_loss_and_grads(_to(fwd, dt), _to(bwd, dt), _to(fwd_t, dt), _to(bwd_t, dt), _to(actor, dt), obs.to(dt), action.to(dt),
+
+    def act(name, r0=0, c0=None):   # the engine's post-ReLU activation -> branch mask
+        v = eng.view(name).detach().cpu()[r0:r0 + B]
+        return (v if c0 is None else v[:, c0:c0 + Fd]) > 0
+
+    def run_fb(dt):
+        return O.fb_loss_and_grads(_to(fwd, dt), _to(bwd, dt), _to(fwd_t, dt), _to(bwd_t, dt), _to(actor, dt), obs.to(dt), action.to(dt),
                                    discount.to(dt), next_obs.to(dt), next_obs.to(dt), zz.to(dt), noise_fb.to(dt), 0.2, 0.3, 1.0, d.z_dim)
-           for dt in (f32, f64)}
+
+    ora32 = run_fb(f32)
+    # ReLU call order of fb_loss_and_grads: actor(next_obs) [obs_z_net, obs_net, policy], target F [oa, oz, F1, F2], target B,
+    # online F [oa, oz, F1, F2], online B
+    forced = _ForcedRelu([act("hA", 0, Fd), act("hA", 0, 0), act("actor.policy.h1"), act("hFt", 0, 0), act("hFt", 0, Fd),
+                          act("Ft.F1.h1"), act("Ft.F2.h1"), act("Bt.h2"), act("hF", 0, 0), act("hF", 0, Fd), act("F.F1.h1"),
+                          act("F.F2.h1"), act("Bo.h2")])
+    with monkeypatch.context() as mp:
+        mp.setattr(torch, "relu", forced)
+        ora = run_fb(f64)
+    assert forced.i == len(forced.masks)
+    print(f"fb step: {forced.flips} of ~{13 * B * 1024} ReLU units on the other branch than the fp64 oracle, largest |x|/mean|x| {forced.worst:.1e}")
+    assert forced.flips <= 64 and forced.worst < 1e-4
     m = eng.read_metrics()
-    for k, v in ora[f32]["metrics"].items():
+    for k, v in ora32["metrics"].items():
         assert m[k] == pytest.approx(v, rel=REL_TOL, abs=1e-5), k
     for name in ("next_action", "tF1", "tF2", "tB", "F1", "F2", "B", "dF1", "dF2", "dB"):
-        assert rel(eng.view(name), ora[f64][name]) < 1e-4, name
-    worst64, worst32, ref_own = 0.0, 0.0, 0.0
+        assert rel(eng.view(name), ora[name]) < 1e-4, name
+    worst, ref_own, bad = 0.0, 0.0, []
     for net, key in ((L.NET_FORWARD, "grads_forward"), (L.NET_BACKWARD, "grads_backward")):
         got = read_tensors(eng, net, "grad")
-        for name in ora[f32][key]:
-            e64, e32 = rel(got[name], ora[f64][key][name]), rel(got[name], ora[f32][key][name])
-            own = rel(ora[f32][key][name], ora[f64][key][name])
-            worst64, worst32, ref_own = max(worst64, e64), max(worst32, e32), max(ref_own, own)
-            if name in ("F1.2.weight", "F1.2.bias", "F2.2.weight", "F2.2.bias", "B.5.weight", "B.5.bias"):
-                assert e64 < 1e-4, (key, name, e64)
-            assert min(e64, e32) < 2e-4 or max(e64, e32) < REL_TOL + 2 * own, (key, name, e64, e32, own)
-    print(f"fb grads: worst vs exact {worst64:.2e}, worst vs fp32 reference {worst32:.2e}, fp32 reference vs exact {ref_own:.2e}")
+        for name in ora[key]:
+            e = rel(got[name], ora[key][name])
+            worst, ref_own = max(worst, e), max(ref_own, rel(ora32[key][name], ora[key][name]))
+            if e >= 2e-4:
+                bad.append((key, name, e))
+    print(f"fb grads: worst vs the fp64 oracle on the engine's branch {worst:.2e} (the unforced fp32 oracle sits {ref_own:.2e} from it)")
+    assert not bad, bad
     eng.run(L.PHASE_FB_ADAM)
     fwd1 = read_tensors(eng, L.NET_FORWARD, "param")
     eng.run(L.PHASE_ACTOR_FWD | L.PHASE_ACTOR_BWD | L.PHASE_METRICS)
     torch.cuda.synchronize()
-    ora_a = {dt: O.actor_loss_and_grads(_to(actor, dt), _to(fwd1, dt), obs.to(dt), zz.to(dt), noise_actor.to(dt), 0.2, 0.3) for dt in (f32, f64)}
+
+    def run_actor(dt):
+        return O.actor_loss_and_grads(_to(actor, dt), _to(fwd1, dt), obs.to(dt), zz.to(dt), noise_actor.to(dt), 0.2, 0.3)
+
+    ora32 = run_actor(f32)
+    # actor(obs) [obs_z_net, obs_net, policy] = rows B..2B of the batched actor forward, then F(obs, z, action) [oa, oz, F1, F2]
+    forced = _ForcedRelu([act("hA", B, Fd), act("hA", B, 0), act("actor.policy.h1", B), act("hF2", 0, 0), act("hF2", 0, Fd),
+                          act("F2.F1.h1"), act("F2.F2.h1")])
+    with monkeypatch.context() as mp:
+        mp.setattr(torch, "relu", forced)
+        ora_a = run_actor(f64)
+    assert forced.i == len(forced.masks)
+    print(f"actor step: {forced.flips} ReLU units on the other branch than the fp64 oracle, largest |x|/mean|x| {forced.worst:.1e}")
+    assert forced.flips <= 64 and forced.worst < 1e-4
     m = eng.read_metrics()
-    assert m["actor_loss"] == pytest.approx(float(ora_a[f32]["actor_loss"]), rel=REL_TOL, abs=1e-5)
+    assert m["actor_loss"] == pytest.approx(float(ora32["actor_loss"]), rel=REL_TOL, abs=1e-5)
     got = read_tensors(eng, L.NET_ACTOR, "grad")
-    for name in ora_a[f32]["grads_actor"]:
-        e64 = rel(got[name], ora_a[f64]["grads_actor"][name])
-        own = rel(ora_a[f32]["grads_actor"][name], ora_a[f64]["grads_actor"][name])
-        e32 = rel(got[name], ora_a[f32]["grads_actor"][name])
-        assert min(e64, e32) < 2e-4 or max(e64, e32) < REL_TOL + 2 * own, (name, e64, e32, own)
+    worst, ref_own, bad = 0.0, 0.0, []
+    for name in ora_a["grads_actor"]:
+        e = rel(got[name], ora_a["grads_actor"][name])
+        worst, ref_own = max(worst, e), max(ref_own, rel(ora32["grads_actor"][name], ora_a["grads_actor"][name]))
+        if e >= 2e-4:
+            bad.append((name, e))
+    print(f"actor grads: worst vs the fp64 oracle on the engine's branch {worst:.2e} (the unforced fp32 oracle sits {ref_own:.2e} from it)")
+    assert not bad, bad
     eng.close()
 
 

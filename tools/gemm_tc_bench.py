@@ -21,7 +21,7 @@ def main() -> None:
     for (M, N, K, bn, nprob) in shapes:
         row = []
         for dbg in (0, PRE_B, PRE_A | PRE_B, NOBUILD, NOBUILD | ONECHAIN, NOBUILD | ONECHAIN | NOEPI, NOEPI):
-            L.check(lib.fb_gemm_tc_bench(M, N, K, bn, nprob, dbg, 20, C.byref(ms), s))
+            L.check(lib.fb_gemm_tc_bench(M, N, K, bn, nprob, 1, dbg, 20, C.byref(ms), s))
             row.append(ms.value * 1e3)
         fl = 2.0 * M * N * K * nprob
         tiles = -(-M // 128) * -(-N // bn) * nprob
@@ -30,5 +30,18 @@ def main() -> None:
               f"nobuild+1chain {row[4]:7.1f} | +noepi {row[5]:7.1f} | noepi {row[6]:7.1f}", flush=True)
 
 
+def splitk_sweep() -> None:
+    lib = L.load()
+    s = torch.cuda.current_stream().cuda_stream
+    ms = C.c_float()
+    for (M, N, K, bn, nprob) in [(1024, 50, 1024, 64, 4), (1024, 50, 1024, 32, 4), (2048, 6, 1024, 32, 1), (50, 1024, 1024, 128, 3), (1024, 512, 1024, 128, 1)]:
+        row = []
+        for sk in (1, 2, 4, 8):
+            L.check(lib.fb_gemm_tc_bench(M, N, K, bn, nprob, sk, PRE_B, 20, C.byref(ms), s))
+            row.append(f"x{sk} {ms.value * 1e3:6.1f}")
+        print(f"split-K M={M} N={N} K={K} bn={bn} x{nprob}: " + " | ".join(row) + " us", flush=True)
+
+
 if __name__ == "__main__":
+    splitk_sweep()
     main()
