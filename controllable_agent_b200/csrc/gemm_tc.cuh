@@ -314,6 +314,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       if (split && kb0 > 0) bias = nullptr;
       for (int cb = 0; cb < ((flags & TC_DBG_NOEPI) ? 0 : bn); cb += 32) {
         if (n0 + cb >= N) break;          // warp-uniform: nothing of this 32-column chunk is inside the matrix
+        // the saved activations this thread's 8 output float4s are masked with: issued first, so that their L2 latency
+        // hides behind the TMEM reads and the transpose (a load -> use -> store chain per row serialises 8 round trips)
+        const int col = n0 + cb + c4;
+        const bool full = col + 3 < N;
+        float4 mk4[8];
+        if (flags & (GF_MASK_RELU | GF_MASK_TANH)) {
+#pragma unroll
+          for (int r8 = 0; r8 < 8; ++r8) {
+            const int row = m0 + q * 32 + r8 * 4 + sub;
+            mk4[r8] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < M && col < N) {
+              const float* mp = mask + (size_t)row * ldmask + col;
+              if (m_vec && full) mk4[r8] = __ldg(reinterpret_cast<const float4*>(mp));
+              else {
+                mk4[r8].x = __ldg(mp);
+                if (col + 1 < N) mk4[r8].y = __ldg(mp + 1);
+                if (col + 2 < N) mk4[r8].z = __ldg(mp + 2);
+                if (col + 3 < N) mk4[r8].w = __ldg(mp + 3);
+              }
+            }
+          }
+        }
+        float bz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (bias && col < N) {
+          if (b_vec && full) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + col)); bz[0] = t4.x; bz[1] = t4.y; bz[2] = t4.z; bz[3] = t4.w; }
+          else { for (int j = 0; j < 4; ++j) if (col + j < N) bz[j] = __ldg(bias + col + j); }
+        }
         float v[32], u[32];
         tc_tmem_ld32(lane_addr + (uint32_t)(3 * bn + cb), v);   // correction chains first (smallest terms)
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -327,12 +354,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(scr + lane * TC_EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
-        const int col = n0 + cb + c4;
-        float bz[4] = {0.f, 0.f, 0.f, 0.f};
-        if (bias && col < N) {
-          if (b_vec && col + 3 < N) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + col)); bz[0] = t4.x; bz[1] = t4.y; bz[2] = t4.z; bz[3] = t4.w; }
-          else { for (int j = 0; j < 4; ++j) if (col + j < N) bz[j] = __ldg(bias + col + j); }
-        }
 #pragma unroll
         for (int r8 = 0; r8 < 8; ++r8) {
           const int r = r8 * 4 + sub;
@@ -340,16 +361,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
           const float4 x4 = *reinterpret_cast<const float4*>(scr + r * TC_EPI_LD + c4);
           if (row >= M || col >= N) continue;
           float x[4] = {x4.x + bz[0], x4.y + bz[1], x4.z + bz[2], x4.w + bz[3]};
-          const bool full = col + 3 < N;
           if (flags & GF_RELU) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
           }
           if (flags & (GF_MASK_RELU | GF_MASK_TANH)) {
-            const float* mp = mask + (size_t)row * ldmask + col;
-            float mk[4] = {0.f, 0.f, 0.f, 0.f};
-            if (m_vec && full) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(mp)); mk[0] = t4.x; mk[1] = t4.y; mk[2] = t4.z; mk[3] = t4.w; }
-            else { for (int j = 0; j < 4; ++j) if (col + j < N) mk[j] = __ldg(mp + j); }
+            const float mk[4] = {mk4[r8].x, mk4[r8].y, mk4[r8].z, mk4[r8].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (flags & GF_MASK_RELU) x[j] = (mk[j] > 0.f) ? x[j] : 0.f;
