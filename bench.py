@@ -158,17 +158,13 @@ def run_reference(a: argparse.Namespace) -> None:
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
 class HostReplay:
-    """A host-memory replay with the reference's sample() contract, for the end-to-end leg: every step's batch is gathered
-    on the host (numpy fancy indexing into pinned staging buffers) and crosses PCIe inside the timed region."""
+    """A host-memory replay with the reference's sample() contract (in_memory_replay_buffer.py:139-190: numpy index draws and
+    fancy-index gathers returning numpy arrays), for the end-to-end leg: every step's batch is gathered on the host and
+    crosses PCIe inside the timed region."""
 
-    def __init__(self, obs, action, reward, discount, gamma: float, batch: int) -> None:
-        import torch
-        self.obs, self.action, self.reward, self.discount, self.gamma = obs, action, reward, discount, gamma
+    def __init__(self, obs, action, reward, discount, gamma: float) -> None:
+        self.obs, self.action, self.reward, self.discount = obs, action, reward, discount
         self._discount, self._future = gamma, 1.0
-        pin = lambda d: torch.empty((2, batch, d), dtype=torch.float32).pin_memory()  # noqa: E731  (double-buffered)
-        self.stage = {"obs": pin(obs.shape[-1]), "action": pin(action.shape[-1]), "reward": pin(1), "discount": pin(1),
-                      "next_obs": pin(obs.shape[-1])}
-        self.flip = 0
 
     def sample(self, batch_size: int):
         import numpy as np
@@ -176,14 +172,8 @@ class HostReplay:
         E, R = self.obs.shape[:2]
         ep = np.random.randint(0, E, size=batch_size)
         t = np.random.randint(0, R - 1, size=batch_size) + 1
-        self.flip ^= 1
-        out = {k: v[self.flip] for k, v in self.stage.items()}
-        out["obs"].numpy()[...] = self.obs[ep, t - 1]
-        out["action"].numpy()[...] = self.action[ep, t]
-        out["reward"].numpy()[...] = self.reward[ep, t]
-        np.multiply(self.discount[ep, t], self.gamma, out=out["discount"].numpy())
-        out["next_obs"].numpy()[...] = self.obs[ep, t]
-        return EpisodeBatch(**out)
+        return EpisodeBatch(obs=self.obs[ep, t - 1], action=self.action[ep, t], reward=self.reward[ep, t],
+                            discount=self.discount[ep, t] * self._discount, next_obs=self.obs[ep, t])
 
 
 def run_ours(a: argparse.Namespace) -> None:
@@ -249,26 +239,36 @@ def run_ours(a: argparse.Namespace) -> None:
     rs = np.random.RandomState(7 + rank)
     Eh = min(E, 200)
     host = HostReplay(rs.standard_normal((Eh, R, a.obs_dim)).astype(np.float32), rs.uniform(-1, 1, (Eh, R, a.action_dim)).astype(np.float32),
-                      rs.uniform(0, 1, (Eh, R, 1)).astype(np.float32), np.ones((Eh, R, 1), np.float32), 0.98, a.batch // world)
+                      rs.uniform(0, 1, (Eh, R, 1)).astype(np.float32), np.ones((Eh, R, 1), np.float32), 0.98)
     agent.cfg.use_tb = True          # metrics on: one D2H read of the step's losses per step
-    agent.cfg.rng_mode = "reference"  # host-drawn perm / mix mask, torch-drawn z and noise, uploaded per step
-    for i in range(3):
-        agent.update(host, i)
-    barrier()
-    t0 = time.perf_counter()
-    ev0.record()
-    for i in range(e2e_steps):
-        m = agent.update(host, i)
-    ev1.record()
-    barrier()
-    e2e_ms = torch.tensor([max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+
+    def e2e_leg(prefetch: bool) -> float:
+        agent.cfg.prefetch_host_batch = prefetch
+        agent._prefetched = None
+        for i in range(3):
+            agent.update(host, i)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        m_ = None
+        for i in range(e2e_steps):
+            m_ = agent.update(host, i)
+        ev1.record()
+        barrier()
+        t = torch.tensor([max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_leg.metrics = m_
+        return float(t.item())
+
+    e2e_ms_serial = e2e_leg(False)   # sample -> upload -> step -> read, strictly in sequence (the reference's own order)
+    e2e_ms = e2e_leg(True)           # the next batch is sampled and uploaded while the step runs (cfg.prefetch_host_batch)
+    m = e2e_leg.metrics
+    agent.cfg.prefetch_host_batch = False
     Bl = a.batch // world
-    h2d = 4 * Bl * (2 * a.obs_dim + a.action_dim + 1) + 4 * Bl * (a.z_dim + 2 * a.action_dim) + 4 * Bl * 2
+    h2d = 4 * Bl * eng._row_pitch   # one copy of the packed batch rows [obs | action | reward, discount | next_obs], 16-byte aligned fields
     d2h = 4 * L.METRIC_COUNT
     agent.cfg.use_tb = False
-    agent.cfg.rng_mode = "device"
 
     # ---- per-kernel timings (CUDA events between launches, eager) -> roofline of the dominant kernel -----------------
     line: dict = {}
@@ -330,9 +330,11 @@ def run_ours(a: argparse.Namespace) -> None:
         line = {"metric": METRIC, "value": a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
-                "e2e": {"value": e2e_steps / (float(e2e_ms.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                        "path": "FBDDPGAgent.update(host_replay, step): host numpy gather -> pinned -> H2D, metrics block D2H"},
+                "e2e": {"value": e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "steps": e2e_steps, "value_without_prefetch": e2e_steps / (e2e_ms_serial * 1e-3),
+                        "path": "FBDDPGAgent.update(host_replay, step): host numpy sample() -> pinned packed rows -> one H2D -> step graph (device RNG) -> "
+                                "metrics block D2H, every step; value: agent.prefetch_host_batch=True (the next step's sample + upload is "
+                                "issued while this step runs on the GPU), value_without_prefetch: strictly serial"},
                 "gpu_launches": launches_per_step * a.steps, "launches_per_step": launches_per_step,
                 "roofline": roofline, "cpu_baseline": cpu,
                 "breakdown_ms": {k: round(v["ms"], 4) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1]["ms"])},

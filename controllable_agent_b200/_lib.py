@@ -35,6 +35,7 @@ PHASE_ACTOR_BWD = 1 << 7
 PHASE_ACTOR_ADAM = 1 << 8
 PHASE_METRICS = 1 << 9
 PHASE_ALL = (1 << 10) - 1
+RUN_HOST_BATCH = 1 << 15   # modifier of PHASE_SAMPLE: batch rows supplied by the caller (fb_upload_batch), gather skipped
 
 # index of each scalar of the metrics block (FB_M_* in fb_b200.h) -> key of the dict FBDDPGAgent.update returns
 METRIC_KEYS = ("target_M", "M1", "F1", "B", "B_norm", "z_norm", "fb_loss", "fb_diag", "fb_offdiag", "orth_loss",
@@ -89,6 +90,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "fb_set_step_scalars": (_i, [_vp, C.POINTER(fb_step_scalars), _vp]),
     "fb_set_indices": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fb_set_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fb_upload_batch": (_i, [_vp, _vp, _i, _vp]),
     "fb_set_z": (_i, [_vp, _vp, _vp]),
     "fb_set_noise": (_i, [_vp, _vp, _vp, _vp]),
     "fb_run": (_i, [_vp, _u32, _i, _vp]),

@@ -103,6 +103,9 @@ class FBDDPGAgentConfig:
     use_cuda_graph: bool = True
     mlp_mode: str = "tcgen05"   # wide Linear products: "tcgen05" (3xTF32 tensor cores) or "simt" (fp32 CUDA cores)
     contract_mode: str = "tcgen05"  # batch x batch contraction: "tcgen05" or "simt"
+    prefetch_host_batch: bool = False   # host replay only: sample + upload the NEXT update's batch while this update's step runs
+    #                                     on the GPU (same numpy draw order as the reference as long as nothing else samples the
+    #                                     replay between updates; for a static replay, e.g. train_offline)
 
 
 def register_hydra() -> None:
@@ -196,6 +199,7 @@ class FBDDPGAgent:
         self.backward_target_net.train()
         self.actor_success: tp.List[float] = []
         self._replay_key: tp.Any = None
+        self._prefetched: tp.Any = None   # id of the host replay whose next batch is already in the packed block
         self.last_update_launches = 0
         # where rng_mode="reference" makes its torch draws (z, action noise): the agent's device, like the reference run
         # with device=cuda; tests point it at "cpu" to replay the CPU-generated golden trajectories
@@ -372,7 +376,7 @@ class FBDDPGAgent:
             self.last_update_launches = e.launch_count(mask)
             return
         import torch.distributed as dist
-        seg1 = mask & (L.PHASE_SAMPLE | L.PHASE_MIX | L.PHASE_FB_FWD)
+        seg1 = mask & (L.PHASE_SAMPLE | L.PHASE_MIX | L.PHASE_FB_FWD | L.RUN_HOST_BATCH)
         seg2 = mask & (L.PHASE_FB_LOSS | L.PHASE_FB_BWD)
         seg3 = mask & (L.PHASE_FB_ADAM | L.PHASE_ACTOR_FWD | L.PHASE_ACTOR_BWD)
         seg4 = mask & (L.PHASE_ACTOR_ADAM | L.PHASE_METRICS)
@@ -449,16 +453,21 @@ class FBDDPGAgent:
         else:
             self._set_scalars(step)
         mask = L.PHASE_ALL & ~L.PHASE_METRICS
-        if fused and c.rng_mode == "device":
-            pass  # every draw happens inside FB_PHASE_SAMPLE
+        use_goal = c.goal_space is not None
+        if not fused:
+            # a host replay (the reference's ReplayBuffer): its numpy fields go to the engine's packed batch block with one
+            # asynchronous copy from pinned staging (instead of EpisodeBatch.to's one blocking copy per field)
+            if self._prefetched != id(replay_loader):
+                self._upload_host_batch(replay_loader, B)
+            self._prefetched = None
+        if c.rng_mode == "device":
+            if not fused:
+                mask |= L.RUN_HOST_BATCH   # FB_PHASE_SAMPLE draws z / noise / perm / mix mask on the device, no gather
         else:
             # the reference's RNG streams in the reference's order
             if fused:
                 ep_idx, step_idx, future_idx = replay_loader.draw_indices(B)
             else:
-                # a host replay (the reference's ReplayBuffer): its numpy / pinned fields go straight to the engine, which
-                # uploads them with asynchronous copies (instead of EpisodeBatch.to's one blocking copy per field)
-                batch = replay_loader.sample(B)
                 mask &= ~L.PHASE_SAMPLE
             z = self.sample_z(B, device=self.draw_device)
             perm = torch.randperm(B)
@@ -469,15 +478,16 @@ class FBDDPGAgent:
                 e.set_indices(ep_idx, step_idx, future_idx, perm, mix)
             else:
                 e.set_indices(perm=perm, mix_mask=mix)
-                use_goal = c.goal_space is not None
-                if use_goal:
-                    assert batch.goal is not None and batch.next_goal is not None
-                e.set_batch(batch.obs, batch.action, batch.discount, batch.next_obs, batch.goal if use_goal else None,
-                            batch.next_goal if use_goal else None)
             e.set_z(z)
             e.set_noise(noise_fb, noise_actor)
-        if self._metrics_enabled():
-            self._run(mask | L.PHASE_METRICS)
+        want_metrics = self._metrics_enabled()
+        self._run(mask | L.PHASE_METRICS if want_metrics else mask)
+        if not fused and c.prefetch_host_batch:
+            # the step is in flight: sample the next batch and enqueue its upload behind it (stream order keeps this step's
+            # reads of the packed block ahead of the copy)
+            self._upload_host_batch(replay_loader, B)
+            self._prefetched = id(replay_loader)
+        if want_metrics:
             m = e.read_metrics()
             if self.world > 1:
                 m = self._reduce_metrics(m)
@@ -485,9 +495,15 @@ class FBDDPGAgent:
             metrics["fb_opt_lr"] = self.fb_opt.param_groups[0]["lr"]
             if c.use_tb or c.use_wandb:   # the actor block logs under a narrower condition (fb_ddpg.py:413)
                 metrics.update({k: m[k] for k in L.METRIC_KEYS[14:]})
-        else:
-            self._run(mask)
         return metrics
+
+    def _upload_host_batch(self, replay_loader: tp.Any, B: int) -> None:
+        batch = replay_loader.sample(B)
+        use_goal = self.cfg.goal_space is not None
+        if use_goal:
+            assert batch.goal is not None and batch.next_goal is not None
+        self.engine.upload_batch(batch.obs, batch.action, batch.discount, batch.next_obs, batch.goal if use_goal else None,
+                                 batch.next_goal if use_goal else None)
 
     def _reduce_metrics(self, m: tp.Dict[str, float]) -> tp.Dict[str, float]:
         """Per-rank metric blocks -> global values: loss-type entries are partial sums over the rank's rows, the

@@ -493,7 +493,8 @@ static int build_plan(fb_handle* h) {
     rp.noise_actor = h->noise_actor.p;
     fb_handle* hh = h;
     b.push([rp, sc, hh](cudaStream_t s) mutable {
-      rp.ep_len = hh->replay.d_episode_len; rp.rows_per_episode = hh->replay.rows_per_episode;
+      rp.ep_len = hh->replay_bound ? hh->replay.d_episode_len : nullptr;   // no replay (host batches): no index draws
+      rp.rows_per_episode = hh->replay_bound ? hh->replay.rows_per_episode : 2;
       k_rng_draw<<<fb_ceil_div(rp.batch, 8), 256, 0, s>>>(rp, sc);
       return cudaGetLastError();
     });
@@ -515,6 +516,7 @@ static int build_plan(fb_handle* h) {
                                                                  &sc->replay_discount, 0.f, hh->packed.p);
       return cudaGetLastError();
     }, FB_OPK_GATHER, 0.0, 2.0 * 4.0 * (double)B * (double)h->bl.pitch);
+    h->ops[b.phase].back().replay_only = 1;
   }
 
   // =========================== FB_PHASE_MIX =====================================================
@@ -810,7 +812,7 @@ static int build_plan(fb_handle* h) {
   {
     unsigned int* linf = h->d_linf;
     b.push([Bg, n, Z, acc, linf](cudaStream_t s) {
-      k_metric_cov<<<Z, 128, 0, s>>>(Bg.p, Bg.ld, n, Z, acc, linf);
+      k_metric_cov<<<Z, 256, 0, s>>>(Bg.p, Bg.ld, n, Z, acc, linf);
       return cudaGetLastError();
     });
     MetricFinalParams mp; memset(&mp, 0, sizeof(mp));
@@ -1067,6 +1069,14 @@ int fb_set_batch(fb_handle* h, const float* d_obs, const float* d_action, const 
   return FB_OK;
 }
 
+int fb_upload_batch(fb_handle* h, const float* h_rows, int pitch, void* stream) {
+  if (!h || !h->bound) return FB_E_STATE;
+  if (!h_rows || pitch != h->bl.pitch) return FB_E_ARG;
+  CK(cudaMemcpy2DAsync(h->packed.p, (size_t)h->packed.ld * sizeof(float), h_rows, (size_t)pitch * sizeof(float), (size_t)pitch * sizeof(float),
+                       (size_t)h->cfg.batch, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return FB_OK;
+}
+
 static int copy_rows(const Mat& dst, const float* src, cudaStream_t s) {
   CK(cudaMemcpy2DAsync(dst.p, dst.ld * sizeof(float), src, dst.cols * sizeof(float), dst.cols * sizeof(float), dst.rows,
                        cudaMemcpyDeviceToDevice, s));
@@ -1092,6 +1102,7 @@ static cudaError_t run_eager(fb_handle* h, uint32_t mask, cudaStream_t s) {
   for (int ph = 0; ph < FB_NUM_PHASES; ++ph) {
     if (!(mask & (1u << ph))) continue;
     for (auto& op : h->ops[ph]) {
+      if (op.replay_only && (mask & FB_RUN_HOST_BATCH)) continue;
       if (op.lane == 1) {
         if (!h->side_stream) {
           CKE(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
@@ -1124,7 +1135,7 @@ static cudaError_t run_eager(fb_handle* h, uint32_t mask, cudaStream_t s) {
 
 int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream) {
   if (!h || !h->bound) return FB_E_STATE;
-  if ((phase_mask & FB_PHASE_SAMPLE) && !h->replay_bound) return FB_E_STATE;
+  if ((phase_mask & FB_PHASE_SAMPLE) && !(phase_mask & FB_RUN_HOST_BATCH) && !h->replay_bound) return FB_E_STATE;
   cudaStream_t s = (cudaStream_t)stream;
   if (!use_graph) return (int)run_eager(h, phase_mask, s);
   auto it = h->graphs.find(phase_mask);
@@ -1155,7 +1166,8 @@ int fb_launch_count(fb_handle* h, uint32_t phase_mask) {
   if (!h || !h->bound) return FB_E_STATE;
   int n = 0;
   for (int ph = 0; ph < FB_NUM_PHASES; ++ph)
-    if (phase_mask & (1u << ph)) n += (int)h->ops[ph].size();
+    if (phase_mask & (1u << ph))
+      for (auto& op : h->ops[ph]) n += (op.replay_only && (phase_mask & FB_RUN_HOST_BATCH)) ? 0 : 1;
   return n;
 }
 

@@ -216,8 +216,9 @@ __global__ void __launch_bounds__(256) k_rng_draw(RngParams P, const DevScalars*
     const int tmax = max(P.rows_per_episode - 1, 1);
     int ep = 0, t = 1, len = 1;
     uint4 r = make_uint4(0u, 0u, 0u, 0u);
-    for (uint32_t attempt = 0; attempt < 64u; ++attempt) {
+    for (uint32_t attempt = 0; attempt < (P.ep_len ? 64u : 1u); ++attempt) {
       r = ph(ctr, (uint32_t)warp, 8u + attempt);
+      if (!P.ep_len) break;   // host-supplied batches: only the mix mask / permutation key of this row are needed
       ep = (int)(((unsigned long long)r.x * (unsigned long long)n_ep) >> 32);
       t = 1 + (int)(((unsigned long long)r.y * (unsigned long long)tmax) >> 32);
       len = P.ep_len[ep];
@@ -868,19 +869,41 @@ __global__ void __launch_bounds__(256) k_metric_rows(const float* __restrict__ F
   }
 }
 
-// eye_diff = B^T B / n - I  (Z x Z): block a computes row a; linf via atomicMax on the float bits (values >= 0)
-__global__ void __launch_bounds__(128) k_metric_cov(const float* __restrict__ Bm, int ldb, int rows, int Z, double* acc,
+// eye_diff = B^T B / n - I  (Z x Z): block a computes row a; its 8 warps each take every 8th batch row (lane = column b,
+// coalesced), partial rows are summed through shared memory; linf via atomicMax on the float bits (values >= 0)
+__global__ void __launch_bounds__(256) k_metric_cov(const float* __restrict__ Bm, int ldb, int rows, int Z, double* acc,
                                                     unsigned int* linf_bits) {
-  const int a = blockIdx.x;
+  __shared__ float part[8][128];
+  const int a = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float mx = 0.f, sq = 0.f;
-  for (int b = threadIdx.x; b < Z; b += blockDim.x) {
-    float s = 0.f;
-    for (int r = 0; r < rows; ++r) s += Bm[(size_t)r * ldb + a] * Bm[(size_t)r * ldb + b];
-    const float e = s / (float)rows - (a == b ? 1.f : 0.f);
-    mx = fmaxf(mx, fabsf(e)); sq += e * e;
+  for (int b0 = 0; b0 < Z; b0 += 128) {   // 128 columns per pass (one pass for z_dim <= 128)
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = warp; r < rows; r += 8) {
+      const float* row = Bm + (size_t)r * ldb;
+      const float va = __ldg(row + a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int b = b0 + j * 32 + lane;
+        if (b < Z) s[j] = fmaf(va, __ldg(row + b), s[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) part[warp][j * 32 + lane] = s[j];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int b = b0 + threadIdx.x;
+      if (b < Z) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+        const float e = t / (float)rows - (a == b ? 1.f : 0.f);
+        mx = fmaxf(mx, fabsf(e)); sq += e * e;
+      }
+    }
+    __syncthreads();
   }
   mx = warp_max(mx); sq = warp_sum(sq);
-  if ((threadIdx.x & 31) == 0) { atomicMax(linf_bits, __float_as_uint(mx)); atomicAdd(acc + ACC_ORTH_SQ, (double)sq); }
+  if (lane == 0 && warp < 4) { atomicMax(linf_bits, __float_as_uint(mx)); atomicAdd(acc + ACC_ORTH_SQ, (double)sq); }
 }
 
 struct MetricFinalParams {

@@ -53,6 +53,7 @@ struct Op {
   int join;      // main-lane op that must wait for the side-lane work issued before it
   int fork;      // side-lane op that must first wait for the main-lane work issued before it (otherwise it only follows the
                  // side-lane ops issued before it)
+  int replay_only = 0;  // skipped under FB_RUN_HOST_BATCH (the replay gather)
   cudaError_t operator()(cudaStream_t s) const { return fn(s); }
 };
 

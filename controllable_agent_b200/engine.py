@@ -83,6 +83,13 @@ class FBStepEngine:
         self._idx_stage: tp.Optional[torch.Tensor] = None   # pinned staging ring for host-provided index arrays
         self._idx_slot = 0
         self._idx_events: tp.List[tp.Optional[torch.cuda.Event]] = [None] * 16
+        # host-batch staging (upload_batch): two pinned [batch, pitch] blocks in the packed row layout of the library
+        offs, pitch = (C.c_int32 * 9)(), C.c_int32()
+        L.check(self.lib.fb_batch_row_layout(cfg.obs_dim, cfg.action_dim, cfg.goal_dim if cfg.use_goal else 0, 0, 0, offs, C.byref(pitch)))
+        self._row_offsets, self._row_pitch = list(offs), pitch.value
+        self._row_stage: tp.Optional[torch.Tensor] = None
+        self._row_events: tp.List[tp.Optional[torch.cuda.Event]] = [None, None]
+        self._row_slot = 0
         mp = self.lib.fb_metrics_ptr(h)
         self._metrics = self._wrap(mp, L.METRIC_COUNT)
         self._metrics_host = torch.zeros(L.METRIC_COUNT, dtype=torch.float32).pin_memory()
@@ -198,6 +205,38 @@ class FBStepEngine:
               self._dev_f32(next_goal, c.goal_dim) if c.use_goal else None]
         L.check(self.lib.fb_set_batch(self.h, *[_ptr(t) for t in ts], self._stream()), "fb_set_batch")
         self._keepalive_batch = ts
+
+    def upload_batch(self, obs: tp.Any, action: tp.Any, discount: tp.Any, next_obs: tp.Any, goal: tp.Any = None,
+                     next_goal: tp.Any = None) -> int:
+        """Host arrays of one sampled batch (EpisodeBatch fields, replay_buffer.py:27-40) -> the step's packed batch
+        block with ONE asynchronous host-to-device copy (the reference's EpisodeBatch.to issues one blocking pageable
+        copy per field, replay_buffer.py:50-63).  Returns the bytes copied."""
+        c = self.cfg
+        if self._row_stage is None:
+            self._row_stage = torch.zeros((2, c.batch, self._row_pitch), dtype=torch.float32).pin_memory()
+        slot = self._row_slot
+        self._row_slot ^= 1
+        if self._row_events[slot] is not None:
+            self._row_events[slot].synchronize()   # the copy that last read this block has completed
+        rows = self._row_stage[slot].numpy()
+        o = self._row_offsets   # obs, action, (reward, discount), next_obs, goal, next_goal, ...
+
+        def put(off: int, x: tp.Any, dim: int) -> None:
+            a = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+            rows[:, off:off + dim] = a.reshape(c.batch, dim)
+
+        put(o[0], obs, c.obs_dim)
+        put(o[1], action, c.action_dim)
+        put(o[2] + 1, discount, 1)
+        put(o[3], next_obs, c.obs_dim)
+        if c.use_goal:
+            put(o[4], goal, c.goal_dim)
+            put(o[5], next_goal, c.goal_dim)
+        L.check(self.lib.fb_upload_batch(self.h, self._row_stage[slot].data_ptr(), self._row_pitch, self._stream()), "fb_upload_batch")
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._row_events[slot] = ev
+        return 4 * c.batch * self._row_pitch
 
     def set_z(self, z: tp.Any) -> None:
         t = self._dev_f32(z, self.cfg.z_dim)

@@ -61,7 +61,11 @@ enum {
   FB_PHASE_ACTOR_BWD = 1 << 7,  /* dQ -> dF -> da -> backward through actor -> grad_actor */
   FB_PHASE_ACTOR_ADAM = 1 << 8, /* Adam on actor + grad clear */
   FB_PHASE_METRICS = 1 << 9,    /* finalise the metrics block (means, orth_linf, orth_l2) */
-  FB_PHASE_ALL = (1 << 10) - 1
+  FB_PHASE_ALL = (1 << 10) - 1,
+  /* modifier of FB_PHASE_SAMPLE: the caller supplied the batch rows (fb_upload_batch / fb_set_batch), e.g. sampled from a
+   * host-resident replay buffer (in_memory_replay_buffer.py:139-190 run by the caller): the device RNG draws of the phase
+   * still run (rng_device = 1), the replay gather is skipped and no replay needs to be bound */
+  FB_RUN_HOST_BATCH = 1 << 15
 };
 
 /* index of each scalar in the metrics block (float[FB_METRIC_COUNT]) — keys of the dict returned
@@ -164,6 +168,11 @@ int fb_set_indices(fb_handle* h, const int32_t* d_ep_idx, const int32_t* d_step_
  * multiplied by the replay discount. */
 int fb_set_batch(fb_handle* h, const float* d_obs, const float* d_action, const float* d_discount,
                  const float* d_next_obs, const float* d_goal, const float* d_next_goal, void* stream);
+/* Host-buffer form of fb_set_batch = EpisodeBatch.to(device) (replay_buffer.py:50-63) as ONE copy: h_rows is [batch, pitch]
+ * floats in HOST memory (pinned for an asynchronous copy) laid out by fb_batch_row_layout(obs, action, goal_dim or 0, 0, 0):
+ * obs | action | reward, discount (already times the replay discount) | next_obs | goal | next_goal.  The copy is enqueued
+ * on `stream`; the caller keeps h_rows alive until it has completed. */
+int fb_upload_batch(fb_handle* h, const float* h_rows, int pitch, void* stream);
 /* rng_device == 0: the random z of fb_ddpg.py:451 ([batch, z_dim], rows of norm sqrt(z_dim)) */
 int fb_set_z(fb_handle* h, const float* d_z, void* stream);
 /* rng_device == 0: the two N(0,1) draws of utils.py:178 ([batch, action_dim] each): update_fb's

@@ -244,6 +244,49 @@ def test_agent_device_rng_step_statistics_and_api():
     assert fresh.engine.get_adam_steps() == (5, 5)
 
 
+def test_agent_host_replay_with_device_rng():
+    """A host-memory replay (the reference's ReplayBuffer contract: sample() -> numpy EpisodeBatch) feeding the device step
+    with rng_mode=device: the batch crosses as one packed upload (fb_upload_batch), FB_PHASE_SAMPLE draws z / noise / perm /
+    mix mask on the device without a bound replay (FB_RUN_HOST_BATCH), with and without a goal space."""
+    from controllable_agent_b200 import EpisodeBatch, FBDDPGAgent, _lib as L
+    for goal_space, G in ((None, 0), ("simplified_walker", 3)):
+        torch.manual_seed(5)
+        B, O_, A_, Z = 128, 24, 6, 50
+        agent = FBDDPGAgent(obs_type="states", obs_shape=(O_,), action_shape=(A_,), device="cuda", num_expl_steps=0, update_encoder=True,
+                            goal_space=goal_space, use_tb=True, use_wandb=True, use_hiplog=False, batch_size=B, update_every_steps=1,
+                            hidden_dim=256, feature_dim=128, backward_hidden_dim=134)
+        rs = np.random.RandomState(1)
+
+        class Host:
+            samples = []
+
+            def sample(self, n):
+                f = lambda *shape: rs.standard_normal(shape).astype(np.float32)  # noqa: E731
+                Host.samples.append(EpisodeBatch(obs=f(n, O_), action=rs.uniform(-1, 1, (n, A_)).astype(np.float32), reward=f(n, 1),
+                                                 discount=np.full((n, 1), 0.98, np.float32), next_obs=f(n, O_),
+                                                 goal=f(n, G) if G else None, next_goal=f(n, G) if G else None))
+                return Host.samples[-1]
+
+        zs, host = [], Host()
+        for step in range(6):
+            agent.cfg.prefetch_host_batch = step >= 3   # steps 3..5: the next batch is sampled + uploaded while the step runs
+            m = agent.update(host, step)
+            assert set(m) == set(L.METRIC_KEYS) | {"fb_opt_lr"} and all(np.isfinite(v) for v in m.values()), m
+            assert m["z_norm"] == pytest.approx(np.sqrt(Z), rel=1e-4)
+            assert len(Host.samples) == step + 1 + (1 if step >= 3 else 0)
+            e, b = agent.engine, Host.samples[step]
+            assert torch.equal(e.view("actor_in_o")[B:].cpu(), torch.from_numpy(b.obs))
+            assert torch.equal(e.view("actor_in_o")[:B].cpu(), torch.from_numpy(b.next_obs))
+            assert torch.equal(e.view("in_oa")[:, O_:].cpu(), torch.from_numpy(b.action))
+            assert torch.equal(e.view("discount").cpu(), torch.from_numpy(b.discount))
+            assert torch.equal(e.view("next_goal").cpu(), torch.from_numpy(b.next_goal if G else b.next_obs))
+            zs.append(e.view("z").clone())
+        assert not torch.equal(zs[0], zs[1]) and not torch.equal(zs[1], zs[2])
+        assert agent.engine.get_adam_steps() == (6, 6)
+        assert agent.last_update_launches == agent.engine.launch_count(L.PHASE_ALL | L.RUN_HOST_BATCH)
+        assert agent.engine.launch_count(L.PHASE_ALL | L.RUN_HOST_BATCH) == agent.engine.launch_count(L.PHASE_ALL) - 1
+
+
 def test_unsupported_branches_raise():
     from controllable_agent_b200 import FBDDPGAgent
     base = dict(obs_type="states", obs_shape=(24,), action_shape=(6,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,
