@@ -82,6 +82,21 @@ struct Builder {
   // copy).  *lo_out receives the operand's pre-split lo plane when one is produced: always for staged copies (the staging
   // launch writes it for free), and for directly addressable operands only if `want_lo` and the source is final when the
   // phase starts (weights: a lo-only staging entry on the side lane).
+  // first phase (of a full step) at whose start `p` holds its final value for a consumer in the current phase
+  int avail_of(const float* p) const {
+    const fb_buffers& bf = h->bufs;
+    auto in = [&](const float* base, size_t n) { return base && p >= base && p < base + n; };
+    if (in(bf.d_param_actor, h->seg_actor.size)) return 0;                       // changes only in ACTOR_ADAM (last)
+    if (in(bf.d_param_fb, h->seg_fb.size) || in(bf.d_target_fb, h->seg_fb.size))   // changes in FB_ADAM
+      return phase <= phase_index(FB_PHASE_FB_ADAM) ? 0 : phase_index(FB_PHASE_ACTOR_FWD);
+    // forward activations: MIX / FB_FWD outputs are final when FB_LOSS starts; ACTOR_FWD outputs when ACTOR_BWD starts
+    if (phase == phase_index(FB_PHASE_FB_LOSS) || phase == phase_index(FB_PHASE_FB_BWD)) return phase_index(FB_PHASE_FB_LOSS);
+    return phase;
+  }
+  void add_early(const TransposeDesc& t, int avail) {
+    h->early_stage[phase].push_back(t);
+    h->early_avail[phase].push_back(avail);
+  }
   bool in_grad(const float* p) const {
     const fb_buffers& bf = h->bufs;
     return (bf.d_grad_fb && p >= bf.d_grad_fb && p < bf.d_grad_fb + h->seg_fb.size) ||
@@ -111,7 +126,7 @@ struct Builder {
     if (getenv("FB_DEBUG_PLAN"))
       fprintf(stderr, "[fb plan %s] phase %d stage(%s%s) in=%p rows=%d cols=%d ld_in=%d T=%d bytes=%zu\n", h->ws_base ? "real" : "dry",
               phase, early ? "early" : "late", direct ? ", lo only" : "", (const void*)p, t.rows, t.cols, t.ld_in, t.transpose, bytes);
-    list.push_back(t);
+    if (early) add_early(t, avail_of(p)); else pending.push_back(t);
     *lo_out = t.out_lo; *ld_lo = lds;
     if (t.out) { *ld_out = lds; return t.out; }
     *ld_out = ld; return p;
@@ -147,9 +162,9 @@ struct Builder {
       if (d.bn > bn_group) d.bn = bn_group;
       if (d.bn > ring_bn) ring_bn = d.bn;
       d.tiles_m = fb_ceil_div(s.M, TC_BM); d.tiles_n = fb_ceil_div(s.N, d.bn);
-      d.splitk = 1; d.kb_per_split = fb_ceil_div(s.K, TC_BK);
-      if (s.K2 == 0 && !(s.flags & GF_RELU) && !getenv("FB_NO_SPLITK")) {
-        const int nkb = fb_ceil_div(s.K, TC_BK);
+      d.splitk = 1; d.kb_per_split = fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK);
+      if (!(s.flags & GF_RELU) && !getenv("FB_NO_SPLITK")) {
+        const int nkb = fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK);   // a k-range may straddle the two products
         int sk = std::min(8, fb_ceil_div(nkb, kb_target));
         if (sk > 1) {
           d.kb_per_split = fb_ceil_div(nkb, sk);
@@ -160,7 +175,7 @@ struct Builder {
         TransposeDesc z; memset(&z, 0, sizeof(z));
         z.out = s.C; z.rows = s.M; z.cols = s.N; z.ld_out = s.ldc; z.transpose = 2;
         if (cur_lane == 1 && phase == phase_index(FB_PHASE_MIX)) pending.push_back(z);   // side-lane chain: right before the launch
-        else { h->early_stage[phase].push_back(z); used_early = true; }
+        else { add_early(z, phase); used_early = true; }
       }
       d.work_begin = work; d.work_count = d.tiles_m * d.tiles_n * d.splitk; work += d.work_count;
       int lda = 0, ldb = 0, lda2 = 0, ldb2 = 0, ldal = 0, ldbl = 0, ldal2 = 0, ldbl2 = 0;
@@ -187,9 +202,6 @@ struct Builder {
       bytes += 4.0 * ((double)s.M * k + (double)s.N * k + (double)s.M * s.N);
       v.push_back(d);
     }
-    // the first MAIN-lane op that consumes early-staged operands joins the side lane (side-lane consumers follow the staging
-    // launch on the same stream)
-    if (used_early && cur_lane == 0 && h->early_join[phase] < 0) h->early_join[phase] = (int)h->ops[phase].size();
     if (!pending.empty()) {
       int ctas = 0;
       double tbytes = 0.0;
@@ -212,6 +224,7 @@ struct Builder {
       k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, n, work, ring_bn);
       return cudaGetLastError();
     }, FB_OPK_GEMM_TC, flops, bytes);
+    if (used_early) h->ops[phase].back().wait_stage = 1;   // operands staged on the staging lane: wait for this phase's staging event
   }
 
   void gemm(std::vector<GemmDesc> g) {
@@ -363,7 +376,8 @@ static int build_plan(fb_handle* h) {
   const bool use_goal = c.use_goal != 0;
   for (auto& v : h->ops) v.clear();
   for (auto& v : h->early_stage) v.clear();
-  for (auto& j : h->early_join) j = -1;
+  for (auto& v : h->early_avail) v.clear();
+  for (auto& v : h->stage_batches) v.clear();
   h->views.clear();
   h->arena.clear();
   h->ws_off = 0;
@@ -820,24 +834,26 @@ static int build_plan(fb_handle* h) {
     b.push([mp](cudaStream_t s) { k_metric_final<<<1, 32, 0, s>>>(mp); return cudaGetLastError(); });
   }
 
-  // early-staged operands: one grouped launch per phase on the side lane, issued first; its first consumer joins
+  // staged operands: one grouped launch per (consumer phase, availability) on the staging lane
   for (int ph = 0; ph < FB_NUM_PHASES; ++ph) {
     std::vector<TransposeDesc>& tv = h->early_stage[ph];
-    if (tv.empty()) continue;
-    int ctas = 0;
-    double tbytes = 0.0;
-    for (auto& t : tv) {
-      t.cta_begin = ctas; t.ctas_x = fb_ceil_div(t.cols, 32); ctas += t.ctas_x * fb_ceil_div(t.rows, 32);
-      tbytes += (t.transpose == 2 ? 4.0 : (t.out ? 12.0 : 8.0)) * t.rows * (double)t.cols;
+    std::vector<int> avails = h->early_avail[ph];
+    std::sort(avails.begin(), avails.end());
+    avails.erase(std::unique(avails.begin(), avails.end()), avails.end());
+    for (int av : avails) {
+      std::vector<TransposeDesc> sub;
+      for (size_t i = 0; i < tv.size(); ++i)
+        if (h->early_avail[ph][i] == av) sub.push_back(tv[i]);
+      int ctas = 0;
+      double tbytes = 0.0;
+      for (auto& t : sub) {
+        t.cta_begin = ctas; t.ctas_x = fb_ceil_div(t.cols, 32); ctas += t.ctas_x * fb_ceil_div(t.rows, 32);
+        tbytes += (t.transpose == 2 ? 4.0 : (t.out ? 12.0 : 8.0)) * t.rows * (double)t.cols;
+      }
+      fb_handle::StageBatch sb;
+      sb.avail = av; sb.d_descs = arena_put(h, sub, d_arena); sb.n = (int)sub.size(); sb.ctas = ctas; sb.bytes = tbytes;
+      h->stage_batches[ph].push_back(sb);
     }
-    const TransposeDesc* td = arena_put(h, tv, d_arena);
-    const int nt = (int)tv.size();
-    if (h->early_join[ph] >= 0 && h->early_join[ph] < (int)h->ops[ph].size()) h->ops[ph][h->early_join[ph]].join = 1;
-    Op op{[td, nt, ctas](cudaStream_t s) {
-            k_transpose_grouped<<<ctas, 256, 0, s>>>(td, nt);
-            return cudaGetLastError();
-          }, FB_OPK_TRANSPOSE, 0.0, tbytes, 1, 0, 1};
-    h->ops[ph].insert(h->ops[ph].begin(), op);
   }
   if (b.rc != FB_OK) return b.rc;
   if (h->arena.size() > FB_DESC_ARENA_BYTES) return FB_E_STATE;
@@ -950,8 +966,11 @@ void fb_destroy(fb_handle* h) {
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->stage_stream) cudaStreamDestroy(h->stage_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_stage_fork) cudaEventDestroy(h->ev_stage_fork);
+  for (auto& e : h->ev_stage) if (e) cudaEventDestroy(e);
   delete h;
 }
 
@@ -1097,22 +1116,55 @@ int fb_set_noise(fb_handle* h, const float* d_noise_fb, const float* d_noise_act
   return rc;
 }
 
+static cudaError_t ensure_streams(fb_handle* h) {
+  if (h->side_stream) return cudaSuccess;
+  CKE(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+  CKE(cudaStreamCreateWithFlags(&h->stage_stream, cudaStreamNonBlocking));
+  CKE(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CKE(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  CKE(cudaEventCreateWithFlags(&h->ev_stage_fork, cudaEventDisableTiming));
+  for (auto& e : h->ev_stage) CKE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return cudaSuccess;
+}
+
+static cudaError_t launch_stage_batch(const fb_handle::StageBatch& sb, cudaStream_t s) {
+  k_transpose_grouped<<<sb.ctas, 256, 0, s>>>(sb.d_descs, sb.n);
+  return cudaGetLastError();
+}
+
+// Three lanes: the caller's stream carries the dependency chain; the side stream carries chains whose inputs are final early
+// (z mixing, bias column sums); the staging stream carries operand staging, launched as soon as its sources are final.
 static cudaError_t run_eager(fb_handle* h, uint32_t mask, cudaStream_t s) {
   bool side_pending = false;
+  CKE(ensure_streams(h));
+  size_t issued[FB_NUM_PHASES] = {};   // staging batches of each consumer phase launched so far (batches are sorted by availability)
   for (int ph = 0; ph < FB_NUM_PHASES; ++ph) {
     if (!(mask & (1u << ph))) continue;
+    // staging whose sources are final by now, for this and every later phase of the mask
+    bool forked = false;
+    for (int P = ph; P < FB_NUM_PHASES; ++P) {
+      if (!(mask & (1u << P))) continue;
+      auto& sbs = h->stage_batches[P];
+      const bool no_hoist = getenv("FB_NO_HOIST") != nullptr;
+      while (issued[P] < sbs.size() && (sbs[issued[P]].avail <= ph && (!no_hoist || P == ph))) {
+        if (!forked) {   // the staging lane sees everything issued so far on the main lane
+          CKE(cudaEventRecord(h->ev_stage_fork, s));
+          CKE(cudaStreamWaitEvent(h->stage_stream, h->ev_stage_fork, 0));
+          forked = true;
+        }
+        CKE(launch_stage_batch(sbs[issued[P]], h->stage_stream));
+        if (++issued[P] == sbs.size()) CKE(cudaEventRecord(h->ev_stage[P], h->stage_stream));
+      }
+    }
     for (auto& op : h->ops[ph]) {
       if (op.replay_only && (mask & FB_RUN_HOST_BATCH)) continue;
+      const bool staged = op.wait_stage && !h->stage_batches[ph].empty();
       if (op.lane == 1) {
-        if (!h->side_stream) {
-          CKE(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
-          CKE(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-          CKE(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-        }
         if (op.fork || !side_pending) {                    // fork: the side lane sees everything issued so far on the main lane
           CKE(cudaEventRecord(h->ev_fork, s));
           CKE(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
         }
+        if (staged) CKE(cudaStreamWaitEvent(h->side_stream, h->ev_stage[ph], 0));
         CKE(op(h->side_stream));
         side_pending = true;
       } else {
@@ -1121,6 +1173,7 @@ static cudaError_t run_eager(fb_handle* h, uint32_t mask, cudaStream_t s) {
           CKE(cudaStreamWaitEvent(s, h->ev_join, 0));
           side_pending = false;
         }
+        if (staged) CKE(cudaStreamWaitEvent(s, h->ev_stage[ph], 0));
         CKE(op(s));
       }
     }
@@ -1129,6 +1182,7 @@ static cudaError_t run_eager(fb_handle* h, uint32_t mask, cudaStream_t s) {
       CKE(cudaStreamWaitEvent(s, h->ev_join, 0));
       side_pending = false;
     }
+    if (!h->stage_batches[ph].empty()) CKE(cudaStreamWaitEvent(s, h->ev_stage[ph], 0));   // the staging lane is joined at the latest here
   }
   return cudaSuccess;
 }
@@ -1166,8 +1220,10 @@ int fb_launch_count(fb_handle* h, uint32_t phase_mask) {
   if (!h || !h->bound) return FB_E_STATE;
   int n = 0;
   for (int ph = 0; ph < FB_NUM_PHASES; ++ph)
-    if (phase_mask & (1u << ph))
+    if (phase_mask & (1u << ph)) {
+      n += (int)h->stage_batches[ph].size();
       for (auto& op : h->ops[ph]) n += (op.replay_only && (phase_mask & FB_RUN_HOST_BATCH)) ? 0 : 1;
+    }
   return n;
 }
 
@@ -1176,10 +1232,21 @@ int fb_profile_ops(fb_handle* h, uint32_t phase_mask, int reps, void* stream, fl
   if (!h || !h->bound) return FB_E_STATE;
   if (reps < 1 || cap < 1 || !ms_out) return FB_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  std::vector<const Op*> ops;
+  // every launch of the phases, the staging batches of a phase listed before its ops (all serialised on `s` here)
+  std::vector<Op> stage_ops;
   for (int ph = 0; ph < FB_NUM_PHASES; ++ph)
     if (phase_mask & (1u << ph))
+      for (auto& sb : h->stage_batches[ph]) {
+        fb_handle::StageBatch c = sb;
+        stage_ops.push_back(Op{[c](cudaStream_t st) { return launch_stage_batch(c, st); }, FB_OPK_TRANSPOSE, 0.0, sb.bytes, 2, 0, 0});
+      }
+  std::vector<const Op*> ops;
+  size_t si = 0;
+  for (int ph = 0; ph < FB_NUM_PHASES; ++ph)
+    if (phase_mask & (1u << ph)) {
+      for (size_t k = 0; k < h->stage_batches[ph].size(); ++k) ops.push_back(&stage_ops[si++]);
       for (auto& op : h->ops[ph]) ops.push_back(&op);
+    }
   const int n = (int)ops.size();
   if (n > cap) return FB_E_ARG;
   std::vector<cudaEvent_t> ev(n + 1);

@@ -58,7 +58,7 @@ struct __align__(64) TcGemmDesc {
   int M, N, K, K2;
   int ldc, ldmask, flags, bn;
   int tiles_m, tiles_n, work_begin, work_count;
-  int splitk, kb_per_split;   // splitk > 1: a tile's k-blocks are shared by splitk work items that add into a zeroed C (K2 = 0, no ReLU)
+  int splitk, kb_per_split;   // splitk > 1: a tile's k-blocks (of both products) are shared by splitk work items that add into a zeroed C (no ReLU)
 };
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -54,6 +54,7 @@ struct Op {
   int fork;      // side-lane op that must first wait for the main-lane work issued before it (otherwise it only follows the
                  // side-lane ops issued before it)
   int replay_only = 0;  // skipped under FB_RUN_HOST_BATCH (the replay gather)
+  int wait_stage = 0;   // consumes operands staged for this phase on the staging lane: waits for the phase's staging event
   cudaError_t operator()(cudaStream_t s) const { return fn(s); }
 };
 
@@ -78,12 +79,18 @@ struct fb_handle {
   cudaStream_t capture_stream = nullptr;
   size_t contract_smem = 0;  // dynamic shared memory of k_contract_tc (0: SIMT contraction)
   bool uses_gemm_tc = false;
-  // operands whose source is final when a phase starts (weights, activations of earlier phases) are staged on a side stream
+  // Operands whose source is final before the consuming phase starts (weights, activations of earlier phases) are staged
+  // (aligned / transposed copies, pre-split lo planes, zero fills) on a staging lane, as early as their source allows: an
+  // entry of phase P with availability a is launched at the start of the first phase >= a of the running mask, so that the
+  // staging of FB_FWD / FB_BWD / ACTOR_BWD operands hides behind the phases before them.
   std::vector<TransposeDesc> early_stage[FB_NUM_PHASES];
-  int early_join[FB_NUM_PHASES];     // index of the first op of the phase that consumes them (-1: none)
+  std::vector<int> early_avail[FB_NUM_PHASES];   // per entry: first phase at whose start the source is final
+  struct StageBatch { int avail; const TransposeDesc* d_descs; int n, ctas; double bytes; };
+  std::vector<StageBatch> stage_batches[FB_NUM_PHASES];
   size_t ws_fwd_end = 0;             // workspace offset below which every buffer is written by a forward phase
-  cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side_stream = nullptr, stage_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_stage_fork = nullptr;
+  cudaEvent_t ev_stage[FB_NUM_PHASES] = {};
   // fixed workspace objects
   DevScalars* d_sc = nullptr;
   double* d_acc = nullptr;
