@@ -66,3 +66,10 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   sincosf(6.28318530717958647692f * u01(b), &s, &c);
   return make_float2(r * c, r * s);
 }
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may start while
+// its predecessor in the stream is still running, once every CTA of the predecessor has executed fb_pdl_trigger() (or
+// exited); it must call fb_pdl_wait() before touching anything the predecessor reads or writes.  Used to overlap the
+// prologue of k_gemm_tc (barrier init, TMEM allocation) with the tail of the kernel before it.
+__device__ __forceinline__ void fb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void fb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

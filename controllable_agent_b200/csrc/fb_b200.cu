@@ -221,8 +221,14 @@ struct Builder {
     h->uses_gemm_tc = true;
     const int grid = work < FB_SM_COUNT ? work : FB_SM_COUNT;   // persistent: one CTA per SM walks the group's tiles
     push([dd, n, work, grid, ring_bn](cudaStream_t s) {
-      k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, n, work, ring_bn);
-      return cudaGetLastError();
+      // programmatic dependent launch: the kernel's prologue may overlap the tail of the launch before it (fb_pdl_wait inside)
+      cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr; cfg.numAttrs = getenv("FB_NO_PDL") ? 0 : 1;
+      return cudaLaunchKernelEx(&cfg, k_gemm_tc, dd, n, work, ring_bn);
     }, FB_OPK_GEMM_TC, flops, bytes);
     if (used_early) h->ops[phase].back().wait_stage = 1;   // operands staged on the staging lane: wait for this phase's staging event
   }

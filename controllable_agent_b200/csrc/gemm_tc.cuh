@@ -171,6 +171,7 @@ __device__ __forceinline__ const TcGemmDesc* tc_locate(const TcGemmDesc* __restr
 
 // ring_bn: B-tile rows the ring geometry is laid out for (>= every problem's bn); total: tiles of the whole group
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __restrict__ descs, int nprob, int total, int ring_bn) {
+  fb_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   __shared__ __align__(16) float epi_scratch[4 * 32 * TC_EPI_LD];
   __shared__ __align__(8) uint64_t bar_raw[TC_MAX_STAGES];    // TMA -> lo builders
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  fb_pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -402,6 +404,7 @@ struct TransposeDesc { const float* in; float* out; float* out_lo; int rows, col
 __device__ __forceinline__ float tc_lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 __global__ void __launch_bounds__(256) k_transpose_grouped(const TransposeDesc* __restrict__ descs, int nprob) {
+  fb_pdl_trigger();
   __shared__ float tile[32][33];
   int p = 0;
   while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;

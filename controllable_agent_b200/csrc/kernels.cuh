@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(const __grid_constant__ Gat
                                                      const int* __restrict__ step_idx, const int* __restrict__ future_idx,
                                                      int batch, const float* __restrict__ discount_scale_dev,
                                                      float discount_scale_host, float* __restrict__ out) {
+  fb_pdl_trigger();
   const GatherParams* gp = &gpv;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= batch) return;
@@ -160,6 +161,7 @@ struct StageParams {
 };
 
 __global__ void __launch_bounds__(128) k_stage_inputs(StageParams P, const float* __restrict__ packed) {
+  fb_pdl_trigger();
   const int r = blockIdx.x;
   if (r >= P.batch) return;
   const BatchLayout& L = P.L;
@@ -295,6 +297,7 @@ struct LnDesc {
 };
 
 __global__ void __launch_bounds__(256) k_ln_tanh_fwd(const LnDesc* __restrict__ descs, int nprob, int total_rows) {
+  fb_pdl_trigger();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= total_rows) return;
   int p = 0;
@@ -317,6 +320,7 @@ __global__ void __launch_bounds__(256) k_ln_tanh_fwd(const LnDesc* __restrict__ 
 // Vectorised forward for D <= 1024 and 16-byte aligned rows: the row lives in registers (one global read), two-pass
 // mean / variance on the register copy like nn.LayerNorm, float4 stores.
 __global__ void __launch_bounds__(256) k_ln_tanh_fwd_v4(const LnDesc* __restrict__ descs, int nprob, int total_rows) {
+  fb_pdl_trigger();
   constexpr int NV = 8;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= total_rows) return;
@@ -386,6 +390,7 @@ struct LnBwdDesc {
 #define FB_LN_BWD_ROWS_PER_CTA 16
 
 __global__ void __launch_bounds__(256) k_ln_tanh_bwd(const LnBwdDesc* __restrict__ descs, int nprob) {
+  fb_pdl_trigger();
   __shared__ float s_dg[FB_MAX_LN_DIM];
   __shared__ float s_db[FB_MAX_LN_DIM];
   int p = 0;
@@ -436,6 +441,7 @@ __global__ void __launch_bounds__(256) k_ln_tanh_bwd(const LnBwdDesc* __restrict
 // (one pass over dy / y / x), and its share of dgamma / dbeta in registers across the rows of the CTA (no per-element
 // shared-memory atomics); per CTA one shared-memory combine across the 8 warps, then one global atomic per column.
 __global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const LnBwdDesc* __restrict__ descs, int nprob) {
+  fb_pdl_trigger();
   constexpr int NV = 8;  // float4s per lane: D <= 32 * 4 * 8 = 1024
   __shared__ float s_dg[1024];
   __shared__ float s_db[1024];
@@ -535,6 +541,7 @@ __global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const LnBwdDesc* __restr
 struct L2Desc { const float* x; float* y; float* nrm; int rows, Z, ldx, ldy, row_begin; };
 
 __global__ void __launch_bounds__(256) k_l2norm_fwd(const L2Desc* __restrict__ descs, int nprob, int total_rows) {
+  fb_pdl_trigger();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= total_rows) return;
   int p = 0;
@@ -557,6 +564,7 @@ __global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ dy
                                                     const float* __restrict__ dy2, int lddy, float coef, float* __restrict__ dsum,
                                                     int ldsum, const float* __restrict__ y, int ldy, const float* __restrict__ nrm,
                                                     float* __restrict__ dx, int lddx, int rows, int Z) {
+  fb_pdl_trigger();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   const float sq = sqrtf((float)Z), isq = 1.0f / sq;
@@ -590,6 +598,7 @@ struct ZFinalParams {
 };
 
 __global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
+  fb_pdl_trigger();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= P.batch) return;
   const bool mix = P.mix_mask && P.mix_mask[r] != 0;
@@ -641,6 +650,7 @@ enum {
 };
 
 __global__ void __launch_bounds__(256) k_actor_out(ActorOutParams P, const DevScalars* __restrict__ sc) {
+  fb_pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = 2 * P.batch * P.A;
   double lp = 0.0;
@@ -767,6 +777,7 @@ __global__ void k_loss_init_db(float* __restrict__ dB, int lddb, const float* __
 __global__ void __launch_bounds__(256) k_actor_q(const float* __restrict__ F1, const float* __restrict__ F2, int ldf,
                                                  const float* __restrict__ z, int ldz, float* __restrict__ dF1,
                                                  float* __restrict__ dF2, int lddf, int rows, int Z, float inv_n, double* acc) {
+  fb_pdl_trigger();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   float q1 = 0.f, q2 = 0.f;
@@ -792,6 +803,7 @@ struct ColsumDesc { const float* src; float* dst; int rows, N, ld, cta_begin, ct
 #define FB_COLSUM_ROWS_PER_CTA 128
 
 __global__ void __launch_bounds__(256) k_colsum(const ColsumDesc* __restrict__ descs, int nprob) {
+  fb_pdl_trigger();
   int p = 0;
   while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;
   const ColsumDesc d = descs[p];
@@ -822,6 +834,7 @@ __global__ void __launch_bounds__(256) k_colsum(const ColsumDesc* __restrict__ d
 __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                               float4* __restrict__ v, float4* __restrict__ target, size_t n4, size_t split4,
                                               const DevScalars* __restrict__ sc, int which, float beta1, float beta2, float eps) {
+  fb_pdl_trigger();
   const float bc1 = which == 0 ? sc->bc1_fb : sc->bc1_actor;
   const float bc2s = which == 0 ? sc->bc2s_fb : sc->bc2s_actor;
   const float lr_a = which == 0 ? sc->lr_forward : sc->lr_actor;
