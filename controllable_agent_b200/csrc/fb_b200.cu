@@ -40,7 +40,15 @@ struct Builder {
   fb_handle* h;
   char* d_arena;
   int phase = 0;
-  void set_phase(uint32_t bit) { phase = phase_index(bit); }
+  void set_phase(uint32_t bit) { phase = phase_index(bit); produced.clear(); }
+  // outputs of tensor-core GEMMs of the current phase (direct stores, no split-K): a later dW product that needs such an output
+  // transposed (K = batch contiguous) gets it from the producer's epilogue (TcGemmDesc::CT) instead of a staging launch
+  struct Produced { const float* C; int M, N, ldc; size_t arena_off; };
+  std::vector<Produced> produced;
+  void invalidate_produced(const float* p) {   // another kernel rewrites the buffer in place
+    for (size_t i = 0; i < produced.size();)
+      if (p >= produced[i].C && p < produced[i].C + (size_t)produced[i].M * produced[i].ldc) produced.erase(produced.begin() + i); else ++i;
+  }
   int cur_lane = 0;        // lane of the ops recorded next (1: a side-lane chain, e.g. the z-mixing forward)
   bool fork_next = false;  // the next side-lane op recorded starts a chain: it forks from the main lane
   void push(OpFn fn, int kind = FB_OPK_ELEMENTWISE, double flops = 0.0, double bytes = 0.0, int lane = -1) {
@@ -109,6 +117,20 @@ struct Builder {
     *lo_out = nullptr; *ld_lo = 0;
     if (direct && !(want_lo && early)) { *ld_out = ld; return p; }
     const int lds = fb_round_up(K, 4);
+    if (!kmajor && !early && !getenv("FB_NO_CT")) {
+      for (auto& pr : produced) {
+        if (K != pr.M || ld != pr.ldc || p < pr.C || p + rows > pr.C + pr.N) continue;
+        TcGemmDesc* hd = reinterpret_cast<TcGemmDesc*>(h->arena.data() + pr.arena_off);
+        if (!hd->CT) {
+          hd->ldct = fb_round_up(pr.M, 4);
+          hd->CT = (float*)ws_alloc(h, (size_t)pr.N * hd->ldct * sizeof(float));
+          hd->CT_lo = (float*)ws_alloc(h, (size_t)pr.N * hd->ldct * sizeof(float));
+        }
+        const size_t c0 = (size_t)(p - pr.C);
+        *ld_out = hd->ldct; *ld_lo = hd->ldct; *lo_out = hd->CT_lo + c0 * hd->ldct;
+        return hd->CT + c0 * hd->ldct;
+      }
+    }
     TransposeDesc t; memset(&t, 0, sizeof(t));
     t.in = p; t.ld_in = ld; t.ld_out = lds; t.transpose = kmajor ? 0 : 1;
     if (kmajor) { t.rows = rows; t.cols = K; } else { t.rows = K; t.cols = rows; }   // mn-major storage is [K][rows]
@@ -137,24 +159,62 @@ struct Builder {
     bool used_early = false;
     int work = 0;
     double flops = 0.0, bytes = 0.0;
-    // tile width: the widest BN that still gives the launch about one CTA per SM (a CTA's k-loop is MMA-bound, so a narrower
-    // tile shortens the critical path of an under-filled launch)
-    int bn_group = 32;
-    for (int cand : {128, 64}) {
-      int tiles = 0;
-      for (const GemmDesc& s : g) tiles += fb_ceil_div(s.M, TC_BM) * fb_ceil_div(s.N, cand);
-      if (tiles >= 120) { bn_group = cand; break; }
+    // Tile width and split-K of the launch, from a cost model of the persistent kernel (profiles/r1c_gemm_tc_breakdown.txt):
+    // a k-block of a 128 x bn tile costs f(bn) (shared-memory bound: 1.0 / 0.8 / 0.72 for bn = 128 / 64 / 32, in units of
+    // ~0.7 us), a work item additionally its epilogue; CTA c of min(items, 148) executes items c, c + grid, ... so the
+    // launch lasts as long as its most loaded CTA.  Candidates: bn in {128, 64, 32} x split-K in {1, 2, 3, 4, 6, 8} (only
+    // problems whose epilogue is linear may be split; their partial sums are added into a zeroed C).  Problems are ordered
+    // longest k-chain first, which makes the round-robin an LPT schedule.
+    std::vector<GemmDesc> gs = g;
+    int bn_group = 128, sk_group = 1;
+    {
+      auto natural_bn = [](int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); };
+      auto nkb_of = [](const GemmDesc& s) { return fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK); };
+      double best = 1e30;
+      for (int bn : {128, 64, 32}) {
+        for (int sk : {1, 2, 3, 4, 6, 8}) {
+          if (sk > 1 && getenv("FB_NO_SPLITK")) continue;
+          struct Item { double cost; int count; };
+          std::vector<Item> items;
+          for (const GemmDesc& s : gs) {
+            const int bnp = std::min(bn, natural_bn(s.N)), nkb = nkb_of(s);
+            const bool splittable = !(s.flags & GF_RELU) && nkb >= 8;
+            int len = nkb, parts = 1;
+            if (splittable && sk > 1) { len = fb_ceil_div(nkb, std::min(sk, nkb / 4)); parts = fb_ceil_div(nkb, len); }
+            const double f = bnp == 128 ? 1.0 : (bnp == 64 ? 0.8 : 0.72);
+            const double epi = (2.0 + bnp / 64.0) * (parts > 1 ? 2.0 : 1.0);
+            items.push_back(Item{len * f + epi, fb_ceil_div(s.M, TC_BM) * fb_ceil_div(s.N, bnp) * parts});
+          }
+          std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.cost > y.cost; });
+          int total = 0;
+          for (auto& it : items) total += it.count;
+          const int grid = std::min(total, FB_SM_COUNT);
+          std::vector<double> load(grid, 0.0);
+          int w = 0;
+          for (auto& it : items)
+            for (int i = 0; i < it.count; ++i, ++w) load[w % grid] += it.cost;
+          double cost = 0.0;
+          for (double l : load) cost = std::max(cost, l);
+          cost += 0.02 * sk + (bn == 128 ? 0.0 : 0.01);   // ties: fewer splits, wider tiles
+          if (cost < best) { best = cost; bn_group = bn; sk_group = sk; }
+        }
+      }
+      if (getenv("FB_DEBUG_PLAN")) {
+        fprintf(stderr, "[fb plan %s] phase %d gemm_tc group: bn=%d splitk=%d model cost %.1f :", h->ws_base ? "real" : "dry", phase, bn_group, sk_group, best);
+        for (const GemmDesc& s : gs) fprintf(stderr, " [%dx%dx%d%s%s]", s.M, s.N, s.K + s.K2, s.K2 ? "(K2)" : "", (s.flags & GF_RELU) ? " relu" : "");
+        fprintf(stderr, "\n");
+      }
+      std::stable_sort(gs.begin(), gs.end(), [&](const GemmDesc& x, const GemmDesc& y) {
+        auto len = [&](const GemmDesc& s) {
+          const int nkb = nkb_of(s);
+          const bool splittable = !(s.flags & GF_RELU) && nkb >= 8;
+          return (splittable && sk_group > 1) ? fb_ceil_div(nkb, std::min(sk_group, nkb / 4)) : nkb;
+        };
+        return len(x) > len(y);
+      });
     }
-    // split-K: when the launch is a few long k-chains (narrow outputs with K = hidden / batch), the chain latency bounds it and
-    // most SMs idle; such problems are cut into k-ranges of about the launch's mean work per SM, added into a zeroed C
-    double kb_work = 0.0;
-    for (const GemmDesc& s : g) {
-      const int bn = std::min(bn_group, s.N <= 32 ? 32 : (s.N <= 64 ? 64 : 128));
-      kb_work += (double)fb_ceil_div(s.M, TC_BM) * fb_ceil_div(s.N, bn) * (fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK));
-    }
-    const int kb_target = std::max(4, (int)(kb_work / FB_SM_COUNT + 0.999));
     int ring_bn = 32;
-    for (const GemmDesc& s : g) {
+    for (const GemmDesc& s : gs) {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
       d.C = s.C; d.bias = s.bias; d.mask = s.mask; d.M = s.M; d.N = s.N; d.K = s.K; d.K2 = s.K2;
       d.ldc = s.ldc; d.ldmask = s.ldmask; d.flags = s.flags & (GF_RELU | GF_MASK_RELU | GF_MASK_TANH);
@@ -163,13 +223,10 @@ struct Builder {
       if (d.bn > ring_bn) ring_bn = d.bn;
       d.tiles_m = fb_ceil_div(s.M, TC_BM); d.tiles_n = fb_ceil_div(s.N, d.bn);
       d.splitk = 1; d.kb_per_split = fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK);
-      if (!(s.flags & GF_RELU) && !getenv("FB_NO_SPLITK")) {
-        const int nkb = fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK);   // a k-range may straddle the two products
-        int sk = std::min(8, fb_ceil_div(nkb, kb_target));
-        if (sk > 1) {
-          d.kb_per_split = fb_ceil_div(nkb, sk);
-          d.splitk = fb_ceil_div(nkb, d.kb_per_split);   // every k-range non-empty
-        }
+      if (!(s.flags & GF_RELU) && sk_group > 1 && d.kb_per_split >= 8) {   // a k-range may straddle the two products
+        const int nkb = d.kb_per_split;
+        d.kb_per_split = fb_ceil_div(nkb, std::min(sk_group, nkb / 4));
+        d.splitk = fb_ceil_div(nkb, d.kb_per_split);   // every k-range non-empty
       }
       if (d.splitk > 1 && !in_grad(s.C)) {   // gradients are cleared by k_adam; any other split-K output is zeroed at phase start
         TransposeDesc z; memset(&z, 0, sizeof(z));
@@ -219,6 +276,9 @@ struct Builder {
     const TcGemmDesc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
     h->uses_gemm_tc = true;
+    for (int i = 0; i < n; ++i)
+      if (v[i].splitk == 1 && v[i].M % 4 == 0 && cur_lane == 0)
+        produced.push_back(Produced{v[i].C, v[i].M, v[i].N, v[i].ldc, (size_t)((const char*)(dd + i) - d_arena)});
     const int grid = work < FB_SM_COUNT ? work : FB_SM_COUNT;   // persistent: one CTA per SM walks the group's tiles
     push([dd, n, work, grid, ring_bn](cudaStream_t s) {
       // programmatic dependent launch: the kernel's prologue may overlap the tail of the launch before it (fb_pdl_wait inside)
@@ -267,6 +327,7 @@ struct Builder {
       d.cta_begin = ctas; d.cta_count = fb_ceil_div(d.rows, FB_LN_BWD_ROWS_PER_CTA); ctas += d.cta_count;
       bytes += 16.0 * d.rows * (double)d.D;
     }
+    for (auto& d : v) invalidate_produced(d.dx);
     bool vec = true;  // every problem narrow enough and 16-byte aligned for the register-resident variant?
     for (auto& d : v)
       vec = vec && d.D <= 1024 && d.ld % 4 == 0 && d.ld_dy % 4 == 0 && aligned16(d.dy) && aligned16(d.y) && aligned16(d.x) && aligned16(d.dx);

@@ -58,6 +58,9 @@ struct __align__(64) TcGemmDesc {
   int M, N, K, K2;
   int ldc, ldmask, flags, bn;
   int tiles_m, tiles_n, work_begin, work_count;
+  float* CT;      // optional: C^T [N, ldct] written next to C (the K-major operand of a later dW product: K = batch contiguous),
+  float* CT_lo;   //           and its pre-split lo plane; requires splitk == 1 and M % 4 == 0
+  int ldct, pad0;
   int splitk, kb_per_split;   // splitk > 1: a tile's k-blocks (of both products) are shared by splitk work items that add into a zeroed C (no ReLU)
 };
 
@@ -314,6 +317,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       const int sub = lane >> 3, c4 = (lane & 7) * 4;
       const bool split = d->splitk > 1;   // partial sums: added into the zeroed C; the bias rides on the first k-range
       if (split && kb0 > 0) bias = nullptr;
+      float* __restrict__ CT = d->CT;
+      float* __restrict__ CT_lo = d->CT_lo;
+      const int ldct = d->ldct;
       for (int cb = 0; cb < ((flags & TC_DBG_NOEPI) ? 0 : bn); cb += 32) {
         if (n0 + cb >= N) break;          // warp-uniform: nothing of this 32-column chunk is inside the matrix
         // the saved activations this thread's 8 output float4s are masked with: issued first, so that their L2 latency
@@ -356,11 +362,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(scr + lane * TC_EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
+        float4 xf[8];   // final values (kept for the transposed copy)
 #pragma unroll
         for (int r8 = 0; r8 < 8; ++r8) {
           const int r = r8 * 4 + sub;
           const int row = m0 + q * 32 + r;
           const float4 x4 = *reinterpret_cast<const float4*>(scr + r * TC_EPI_LD + c4);
+          xf[r8] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row >= M || col >= N) continue;
           float x[4] = {x4.x + bz[0], x4.y + bz[1], x4.z + bz[2], x4.w + bz[3]};
           if (flags & GF_RELU) {
@@ -381,6 +389,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
             else { for (int j = 0; j < 4; ++j) if (col + j < N) atomicAdd(cp + j, x[j]); }
           } else if (c_vec && full) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
           else { for (int j = 0; j < 4; ++j) if (col + j < N) cp[j] = x[j]; }
+          xf[r8] = make_float4(x[0], x[1], x[2], x[3]);
+        }
+        if (CT) {
+          // transposed copy: final values back into the scratch, column-major with an odd pitch (conflict-free both ways), then
+          // lane = (column j of 4, row group g of 8) writes 4 consecutive rows of one column = 16 contiguous bytes of C^T,
+          // 8 lanes = one 128-byte run
+          __syncwarp();
+#pragma unroll
+          for (int r8 = 0; r8 < 8; ++r8) {
+            const int r = r8 * 4 + sub;
+            scr[(c4 + 0) * 33 + r] = xf[r8].x; scr[(c4 + 1) * 33 + r] = xf[r8].y;
+            scr[(c4 + 2) * 33 + r] = xf[r8].z; scr[(c4 + 3) * 33 + r] = xf[r8].w;
+          }
+          __syncwarp();
+          const int g = lane & 7, jj = lane >> 3;
+          const int rowT = m0 + q * 32 + 4 * g;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const int cl = c8 * 4 + jj, colT = n0 + cb + cl;
+            if (colT < N && rowT < M) {
+              const float4 t4 = make_float4(scr[cl * 33 + 4 * g], scr[cl * 33 + 4 * g + 1], scr[cl * 33 + 4 * g + 2], scr[cl * 33 + 4 * g + 3]);
+              *reinterpret_cast<float4*>(CT + (size_t)colT * ldct + rowT) = t4;
+              if (CT_lo) *reinterpret_cast<float4*>(CT_lo + (size_t)colT * ldct + rowT) = tc_lo4(t4);
+            }
+          }
         }
         __syncwarp();
       }
