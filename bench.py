@@ -194,7 +194,9 @@ def run_ours(a: argparse.Namespace) -> None:
 
     torch.manual_seed(1 + rank)
     np.random.seed(1 + rank)
-    E = a.episodes // world
+    from controllable_agent_b200.dist_utils import shard_episodes
+    e0_, e1_ = shard_episodes(a.episodes, world, rank)
+    E = e1_ - e0_
     R = a.episode_len + 1
     replay = ReplayBuffer(max_episodes=E, discount=0.98, future=0.99, device=dev)
     g = torch.Generator(device=dev).manual_seed(100 + rank)

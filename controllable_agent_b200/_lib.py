@@ -35,6 +35,8 @@ PHASE_ACTOR_BWD = 1 << 7
 PHASE_ACTOR_ADAM = 1 << 8
 PHASE_METRICS = 1 << 9
 PHASE_ALL = (1 << 10) - 1
+PHASE_INFER_ACTOR, PHASE_INFER_B, PHASE_INFER_BN = 1 << 10, 1 << 11, 1 << 12   # inference plans (run on their own)
+INFER_ROWS = 8
 RUN_HOST_BATCH = 1 << 15   # modifier of PHASE_SAMPLE: batch rows supplied by the caller (fb_upload_batch), gather skipped
 
 # index of each scalar of the metrics block (FB_M_* in fb_b200.h) -> key of the dict FBDDPGAgent.update returns

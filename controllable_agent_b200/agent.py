@@ -24,6 +24,7 @@ from torch.distributions.utils import _standard_normal
 
 from . import _lib as L
 from . import modules as M
+from .dist_utils import reduce_metrics, shard_layout
 from .engine import EngineConfig, FBStepEngine
 from .replay import ReplayBuffer
 
@@ -155,16 +156,14 @@ class FBDDPGAgent:
         self.world, self.rank = 1, 0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world, self.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
-        if cfg.batch_size % self.world:
-            raise ValueError(f"batch_size {cfg.batch_size} must be divisible by the world size {self.world}")
-        local = cfg.batch_size // self.world
+        local, row_offset = shard_layout(cfg.batch_size, self.world, self.rank)
 
         seed = int(torch.initial_seed() % (2 ** 63)) + 7919 * self.rank
         self.engine = FBStepEngine(EngineConfig(
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
-            mix_ratio=cfg.mix_ratio, seed=seed, global_batch=cfg.batch_size, row_offset=self.rank * local,
+            mix_ratio=cfg.mix_ratio, seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
             mlp_mode=L.MLP_SIMT if cfg.mlp_mode == "simt" else L.MLP_TCGEN05,
             contract_mode=L.CONTRACT_SIMT if cfg.contract_mode == "simt" else L.CONTRACT_TCGEN05), device)
 
@@ -278,18 +277,18 @@ class FBDDPGAgent:
         self.solved_meta = state["solved_meta"]
         self.train(state["training"])
 
-    # -- inference helpers (per environment step) --------------------------------------
+    # -- inference helpers (per environment step): forward passes through the library's inference plans ----
     def get_goal_meta(self, goal_array: np.ndarray) -> MetaDict:
-        desired_goal = torch.tensor(goal_array).unsqueeze(0).to(self.cfg.device)
-        with torch.no_grad():
-            z = self.backward_net(desired_goal)
+        """fb_ddpg.py:177-186."""
+        z = self.engine.infer_backward(np.asarray(goal_array, dtype=np.float32).reshape(1, -1))[0]
         if self.cfg.norm_z:
-            z = math.sqrt(self.cfg.z_dim) * F.normalize(z, dim=1)
+            z = math.sqrt(self.cfg.z_dim) * z / max(float(np.linalg.norm(z)), 1e-12)
         meta = OrderedDict()
-        meta["z"] = z.squeeze(0).cpu().numpy()
+        meta["z"] = z.astype(np.float32)
         return meta
 
     def infer_meta(self, replay_loader: tp.Any) -> MetaDict:
+        """fb_ddpg.py:188-199."""
         obs_list, reward_list = [], []
         batch_size = 0
         while batch_size < self.cfg.num_inference_steps:
@@ -303,13 +302,12 @@ class FBDDPGAgent:
         return self.infer_meta_from_obs_and_rewards(obs, reward)
 
     def infer_meta_from_obs_and_rewards(self, obs: torch.Tensor, reward: torch.Tensor) -> MetaDict:
-        with torch.no_grad():
-            b = self.backward_net(obs)
-        z = torch.matmul(reward.T, b) / reward.shape[0]
+        """fb_ddpg.py:201-222: z = reward^T . B(obs) / N, then the sqrt(z_dim) projection."""
+        z = self.engine.infer_backward_weighted_sum(obs, reward) / float(reward.shape[0])
         if self.cfg.norm_z:
-            z = math.sqrt(self.cfg.z_dim) * F.normalize(z, dim=1)
+            z = math.sqrt(self.cfg.z_dim) * z / max(float(np.linalg.norm(z)), 1e-12)
         meta = OrderedDict()
-        meta["z"] = z.squeeze().cpu().numpy()
+        meta["z"] = z.astype(np.float32)
         return meta
 
     def sample_z(self, size: int, device: tp.Union[str, torch.device] = "cpu") -> torch.Tensor:
@@ -331,31 +329,35 @@ class FBDDPGAgent:
         return meta
 
     def act(self, obs: tp.Any, meta: MetaDict, step: int, eval_mode: bool) -> tp.Any:
-        obs = torch.as_tensor(obs, device=self.cfg.device, dtype=torch.float32).unsqueeze(0)
-        h = self.encoder(obs)
-        z = torch.as_tensor(meta["z"], device=self.cfg.device).unsqueeze(0)
-        stddev = M.schedule(self.cfg.stddev_schedule, step)
-        dist = self.actor(h, z, stddev)
+        """fb_ddpg.py:258-281: one actor forward per environment step (the library's FB_PHASE_INFER_ACTOR graph)."""
+        obs_np = np.asarray(obs, dtype=np.float32).reshape(1, -1)
+        z_np = np.asarray(meta["z"], dtype=np.float32).reshape(1, -1)
+        mu = self.engine.infer_actor(obs_np, z_np)
         if eval_mode:
-            action = dist.mean
-            if self.cfg.additional_metric:
-                F_mean_s = self.forward_net(obs, z, action)
-                F_rand_s = self.forward_net(obs, z, torch.zeros_like(action).uniform_(-1.0, 1.0))
-                Qs = [torch.min(*(torch.einsum("sd, sd -> s", Fk, z) for Fk in Fs)) for Fs in [F_mean_s, F_rand_s]]
-                self.actor_success = (Qs[0] > Qs[1]).cpu().numpy().tolist()
+            action = mu
+            if self.cfg.additional_metric:   # F(s, z, mu) against F(s, z, random action): diagnostic branch, parameter-view modules
+                with torch.no_grad():
+                    o, z = (torch.as_tensor(x, device=self.cfg.device) for x in (obs_np, z_np))
+                    a = torch.as_tensor(mu, device=self.cfg.device)
+                    Qs = [torch.min(*(torch.einsum("sd, sd -> s", Fk, z) for Fk in self.forward_net(o, z, act_)))
+                          for act_ in (a, torch.zeros_like(a).uniform_(-1.0, 1.0))]
+                    self.actor_success = (Qs[0] > Qs[1]).cpu().numpy().tolist()
         else:
-            action = dist.sample()
-            if step < self.cfg.num_expl_steps:
-                action.uniform_(-1.0, 1.0)
-        return action.detach().cpu().numpy()[0]
+            # TruncatedNormal(mu, std).sample() with clip=None (utils.py:176-185), drawn from the device generator like the reference
+            stddev = M.schedule(self.cfg.stddev_schedule, step)
+            eps = _standard_normal((1, self.action_dim), dtype=torch.float32, device=self.cfg.device).cpu().numpy() * np.float32(stddev)
+            action = np.clip(mu + eps, -1.0 + 1e-6, 1.0 - 1e-6).astype(np.float32)
+            if step < self.cfg.num_expl_steps:   # the reference draws the sample first, then overwrites it (same generator order)
+                action = torch.empty((1, self.action_dim), dtype=torch.float32, device=self.cfg.device).uniform_(-1.0, 1.0).cpu().numpy()
+        return action[0]
 
     def compute_z_correl(self, time_step: tp.Any, meta: MetaDict) -> float:
+        """fb_ddpg.py:283-289 (F.normalize(z, 1) there is the L1 normalisation: p = 1, dim = 1)."""
         goal = time_step.goal if self.cfg.goal_space is not None else time_step.observation
-        with torch.no_grad():
-            zs = [torch.Tensor(x).unsqueeze(0).float().to(self.cfg.device) for x in [goal, meta["z"]]]
-            zs[0] = self.backward_net(zs[0])
-            zs = [F.normalize(z, 1) for z in zs]
-            return torch.matmul(zs[0], zs[1].T).item()
+        b = self.engine.infer_backward(np.asarray(goal, dtype=np.float32).reshape(1, -1))[0].astype(np.float64)
+        z = np.asarray(meta["z"], dtype=np.float64)
+        b, z = b / max(np.abs(b).sum(), 1e-12), z / max(np.abs(z).sum(), 1e-12)
+        return float(np.dot(b, z))
 
     # -- the gradient step ---------------------------------------------------------------------------
     def _metrics_enabled(self) -> bool:
@@ -508,9 +510,4 @@ class FBDDPGAgent:
     def _reduce_metrics(self, m: tp.Dict[str, float]) -> tp.Dict[str, float]:
         """Per-rank metric blocks -> global values: loss-type entries are partial sums over the rank's rows, the
         others are per-rank means (or replicated)."""
-        import torch.distributed as dist
-        mean_keys = {"target_M", "M1", "F1", "B", "B_norm", "z_norm", "orth_linf", "orth_l2"}
-        t = torch.tensor([m[k] / self.world if k in mean_keys else m[k] for k in L.METRIC_KEYS], dtype=torch.float64,
-                         device=self.engine.device)
-        dist.all_reduce(t)
-        return {k: float(v) for k, v in zip(L.METRIC_KEYS, t.tolist())}
+        return reduce_metrics(m, L.METRIC_KEYS, self.world, self.engine.device)

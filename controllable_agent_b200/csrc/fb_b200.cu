@@ -61,7 +61,9 @@ struct Builder {
   int rc = FB_OK;  // first error met while building (tensor-map encoding)
 
   // can this problem run on the tensor cores (gemm_tc.cuh)?  Operands TMA cannot address directly are staged (see stage_operand)
+  bool force_simt = false;   // inference plans: a handful of rows, the fp32 CUDA-core kernel
   bool tc_ok(const GemmDesc& g) const {
+    if (force_simt) return false;
     if (h->cfg.mlp_mode != FB_MLP_TCGEN05 || (g.flags & GF_SHARED_C) || g.K < 8) return false;
     // a first-layer product (K = obs + action / z, tens of columns): its weight is staged anyway (pre-split lo plane, early on
     // the side lane); only an activation operand that would need a late staging launch keeps it on the SIMT kernel
@@ -900,6 +902,56 @@ static int build_plan(fb_handle* h) {
     mp.acc = acc; mp.linf_bits = linf; mp.out = h->d_metrics; mp.n_local = B; mp.n_global = n; mp.Z = Z; mp.ortho_coef = c.ortho_coef;
     b.push([mp](cudaStream_t s) { k_metric_final<<<1, 32, 0, s>>>(mp); return cudaGetLastError(); });
   }
+
+  // =========================== inference plans ==================================================
+  // act / get_goal_meta / compute_z_correl / infer_meta_from_obs_and_rewards (fb_ddpg.py:177-222,258-289): forward passes of
+  // the online actor / backward_net on caller-filled blocks, no gradients; a few rows -> the fp32 SIMT kernel
+  b.force_simt = true;
+  {
+    const int R = FB_INFER_ROWS;
+    Mat io = ws_mat(h, R, O, "infer_obs"), iz = ws_mat(h, R, Z, "infer_z"), ioz = ws_mat(h, R, O + Z, "infer_oz");
+    Mat ihA = ws_mat(h, R, 2 * Fd, "infer_hA"), ih1 = ws_mat(h, R, H, "infer_h1"), ipre = ws_mat(h, R, A, "infer_pre");
+    Mat imu = ws_mat(h, R, A, "infer_mu");
+    EmbedAct eo = embed_alloc(h, io, ihA.cs(0, Fd), H, "infer.obs_net"), eoz = embed_alloc(h, ioz, ihA.cs(Fd, Fd), H, "infer.obs_z_net");
+    b.set_phase(FB_PHASE_INFER_ACTOR);
+    b.push([=](cudaStream_t s) {
+      k_infer_concat<<<R, 128, 0, s>>>(io.p, io.ld, iz.p, iz.ld, ioz.p, ioz.ld, R, O, Z);
+      return cudaGetLastError();
+    });
+    b.gemm({lin_fwd(eo.x, pA.w(A_O + 0), pA.v(A_O + 1), eo.pre, 0), lin_fwd(eoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eoz.pre, 0)});
+    b.ln_fwd({embed_ln(eo, pA.sub(A_O)), embed_ln(eoz, pA.sub(A_OZ))});
+    b.gemm({lin_fwd(eo.y, pA.w(A_O + 4), pA.v(A_O + 5), eo.out, GF_RELU), lin_fwd(eoz.y, pA.w(A_OZ + 4), pA.v(A_OZ + 5), eoz.out, GF_RELU)});
+    b.gemm({lin_fwd(ihA, pA.w(A_POL + 0), pA.v(A_POL + 1), ih1, GF_RELU)});
+    b.gemm({lin_fwd(ih1, pA.w(A_POL + 2), pA.v(A_POL + 3), ipre, 0)});
+    b.push([=](cudaStream_t s) {
+      k_infer_tanh<<<fb_ceil_div(R * A, 128), 128, 0, s>>>(ipre.p, imu.p, ipre.ld, R, A);
+      return cudaGetLastError();
+    });
+
+    Mat ig = ws_mat(h, R, G, "infer_goal"), ib = ws_mat(h, R, Z, "infer_b");
+    BAct b1 = b_alloc(h, ig, ib, "infer.B");
+    b.set_phase(FB_PHASE_INFER_B);
+    b.gemm({lin_fwd(b1.x, pB.w(0), pB.v(1), b1.pre, 0)});
+    b.ln_fwd({b_ln(b1, pB)});
+    b.gemm({lin_fwd(b1.y, pB.w(4), pB.v(5), b1.h2, GF_RELU)});
+    b.gemm({lin_fwd(b1.h2, pB.w(6), pB.v(7), b1.raw, 0)});
+    b.l2_fwd({b_l2(b1, Z)});
+
+    Mat igN = ws_mat(h, B, G, "infer_goal_batch"), irN = ws_mat(h, B, 1, "infer_reward"), ibN = ws_mat(h, B, Z, "infer_b_batch");
+    Mat izs = ws_mat(h, 1, Z, "infer_zsum");
+    BAct bN = b_alloc(h, igN, ibN, "infer.BN");
+    b.set_phase(FB_PHASE_INFER_BN);
+    b.gemm({lin_fwd(bN.x, pB.w(0), pB.v(1), bN.pre, 0)});
+    b.ln_fwd({b_ln(bN, pB)});
+    b.gemm({lin_fwd(bN.y, pB.w(4), pB.v(5), bN.h2, GF_RELU)});
+    b.gemm({lin_fwd(bN.h2, pB.w(6), pB.v(7), bN.raw, 0)});
+    b.l2_fwd({b_l2(bN, Z)});
+    b.push([=](cudaStream_t s) {
+      k_infer_weighted_colsum<<<fb_ceil_div(Z, 32), 256, 0, s>>>(ibN.p, ibN.ld, irN.p, irN.ld, B, Z, izs.p);
+      return cudaGetLastError();
+    });
+  }
+  b.force_simt = false;
 
   // staged operands: one grouped launch per (consumer phase, availability) on the staging lane
   for (int ph = 0; ph < FB_NUM_PHASES; ++ph) {

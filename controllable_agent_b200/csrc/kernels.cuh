@@ -954,6 +954,37 @@ __global__ void k_metric_final(MetricFinalParams P) {
 }
 
 // ---- fp32 FMA-chain microbenchmark (roofline denominator for the CUDA-core GEMMs) ---------------------
+// ---- inference plans (FB_PHASE_INFER_*) --------------------------------------------------------------
+// [obs | z] rows for the actor's obs_z_net (fb_modules.py:114)
+__global__ void k_infer_concat(const float* __restrict__ obs, int ldo, const float* __restrict__ z, int ldz, float* __restrict__ out, int ldout,
+                               int rows, int O, int Z) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  for (int c = threadIdx.x; c < O + Z; c += blockDim.x) out[(size_t)r * ldout + c] = c < O ? obs[(size_t)r * ldo + c] : z[(size_t)r * ldz + c - O];
+}
+// mu = tanh(policy output)  (fb_modules.py:121)
+__global__ void k_infer_tanh(const float* __restrict__ pre, float* __restrict__ mu, int ld, int rows, int A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * A) { const int r = i / A, a = i - r * A; mu[(size_t)r * ld + a] = tanhf(pre[(size_t)r * ld + a]); }
+}
+// zsum[c] += sum_r reward[r] * b[r, c]   (fb_ddpg.py:215: z = reward^T . B): block = 32 columns, 8 warps stride the rows
+__global__ void __launch_bounds__(256) k_infer_weighted_colsum(const float* __restrict__ b, int ldb, const float* __restrict__ reward, int ldr,
+                                                               int rows, int Z, float* __restrict__ zsum) {
+  __shared__ float part[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (c < Z)
+    for (int r = warp; r < rows; r += 8) s = fmaf(__ldg(reward + (size_t)r * ldr), __ldg(b + (size_t)r * ldb + c), s);
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && c < Z) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    atomicAdd(zsum + c, t);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters) {
   float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
   const float b = 1.000001f, c = 1e-7f;

@@ -18,7 +18,8 @@
 #include "contract_tc.cuh"
 #include "gemm_tc.cuh"
 
-#define FB_NUM_PHASES 10
+#define FB_NUM_PHASES 13
+#define FB_INFER_ROWS 8   // rows of the per-environment-step inference plans (act / get_goal_meta / compute_z_correl)
 #define FB_DESC_ARENA_BYTES (1u << 20)
 #define FB_SM_COUNT 148
 

@@ -284,6 +284,67 @@ class FBStepEngine:
         return (self._wrap(pl.value, self.cfg.batch * n.value).view(self.cfg.batch, n.value),
                 self._wrap(pg.value, gb * n.value).view(gb, n.value))
 
+    # -- inference plans (per environment step / zero-shot inference; fb_ddpg.py:177-222,258-289) ----------------
+    def _infer_io(self) -> tp.Dict[str, tp.Any]:
+        if getattr(self, "_infer", None) is None:
+            c = self.cfg
+            names = ("infer_obs", "infer_z", "infer_mu", "infer_goal", "infer_b", "infer_goal_batch", "infer_reward", "infer_zsum")
+            views = {n: self.view(n) for n in names}
+            R = L.INFER_ROWS
+            pin = lambda *shape: torch.zeros(shape, dtype=torch.float32).pin_memory()  # noqa: E731
+            self._infer = {"v": views, "obs": pin(R, c.obs_dim), "z": pin(R, c.z_dim), "mu": pin(R, c.action_dim),
+                           "goal": pin(R, c.goal_dim), "b": pin(R, c.z_dim), "zsum": pin(1, c.z_dim)}
+        return self._infer
+
+    def infer_actor(self, obs: np.ndarray, z: np.ndarray, graph: bool = True) -> np.ndarray:
+        """mu = tanh(policy(obs, z)) of the online actor for up to 8 rows (fb_modules.py:110-122): one small upload, the
+        FB_PHASE_INFER_ACTOR graph, one small read-back."""
+        io = self._infer_io()
+        n = obs.shape[0]
+        assert n <= L.INFER_ROWS and z.shape[0] == n
+        io["obs"][:n] = torch.from_numpy(np.ascontiguousarray(obs, dtype=np.float32))
+        io["z"][:n] = torch.from_numpy(np.ascontiguousarray(z, dtype=np.float32))
+        io["v"]["infer_obs"].copy_(io["obs"], non_blocking=True)
+        io["v"]["infer_z"].copy_(io["z"], non_blocking=True)
+        self.run(L.PHASE_INFER_ACTOR, graph=graph)
+        io["mu"].copy_(io["v"]["infer_mu"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return io["mu"][:n].numpy().copy()
+
+    def infer_backward(self, goal: np.ndarray, graph: bool = True) -> np.ndarray:
+        """sqrt(z_dim) * normalize(backward_net(goal)) for up to 8 rows (fb_modules.py:223-230)."""
+        io = self._infer_io()
+        n = goal.shape[0]
+        assert n <= L.INFER_ROWS
+        io["goal"][:n] = torch.from_numpy(np.ascontiguousarray(goal, dtype=np.float32))
+        io["v"]["infer_goal"].copy_(io["goal"], non_blocking=True)
+        self.run(L.PHASE_INFER_B, graph=graph)
+        io["b"].copy_(io["v"]["infer_b"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return io["b"][:n].numpy().copy()
+
+    def infer_backward_weighted_sum(self, goal: tp.Any, reward: tp.Any, graph: bool = True) -> np.ndarray:
+        """sum_i reward_i * backward_net(goal_i) over N rows (fb_ddpg.py:213-215), in chunks of `batch` rows (the last chunk
+        padded with zero rewards)."""
+        io = self._infer_io()
+        B = self.cfg.batch
+        goal = torch.as_tensor(goal, dtype=torch.float32)
+        reward = torch.as_tensor(reward, dtype=torch.float32).reshape(-1, 1)
+        N = goal.shape[0]
+        assert reward.shape[0] == N
+        vg, vr = io["v"]["infer_goal_batch"], io["v"]["infer_reward"]
+        io["v"]["infer_zsum"].zero_()
+        for i in range(0, N, B):
+            n = min(B, N - i)
+            if n < B:
+                vr.zero_()
+            vg[:n].copy_(goal[i:i + n], non_blocking=True)
+            vr[:n].copy_(reward[i:i + n], non_blocking=True)
+            self.run(L.PHASE_INFER_BN, graph=graph)
+        io["zsum"].copy_(io["v"]["infer_zsum"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return io["zsum"][0].numpy().copy()
+
     def metrics_tensor(self) -> torch.Tensor:
         return self._metrics
 

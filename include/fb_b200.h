@@ -61,7 +61,18 @@ enum {
   FB_PHASE_ACTOR_BWD = 1 << 7,  /* dQ -> dF -> da -> backward through actor -> grad_actor */
   FB_PHASE_ACTOR_ADAM = 1 << 8, /* Adam on actor + grad clear */
   FB_PHASE_METRICS = 1 << 9,    /* finalise the metrics block (means, orth_linf, orth_l2) */
-  FB_PHASE_ALL = (1 << 10) - 1,
+  FB_PHASE_ALL = (1 << 10) - 1, /* the gradient step */
+  /* Inference plans (no gradients, online networks; fb_ddpg.py:177-222,258-289), each run on its own with fb_run(mask, ...).
+   * Inputs / outputs are the named workspace blocks below (fb_workspace_view), FB_INFER_ROWS = 8 rows for the per-step ones:
+   *   FB_PHASE_INFER_ACTOR   "infer_obs" [8, obs], "infer_z" [8, z]  ->  "infer_mu" [8, action] = tanh(policy(obs, z))   (act)
+   *   FB_PHASE_INFER_B       "infer_goal" [8, goal]  ->  "infer_b" [8, z] = sqrt(z_dim) normalize(backward_net(goal))
+   *                          (get_goal_meta, compute_z_correl)
+   *   FB_PHASE_INFER_BN      "infer_goal_batch" [batch, goal], "infer_reward" [batch, 1]  ->  "infer_zsum" [1, z] +=
+   *                          sum_i reward_i * backward_net(goal_i)   (infer_meta_from_obs_and_rewards, one chunk of `batch` rows;
+   *                          the caller zeroes infer_zsum before the first chunk and pads the last chunk with zero rewards) */
+  FB_PHASE_INFER_ACTOR = 1 << 10,
+  FB_PHASE_INFER_B = 1 << 11,
+  FB_PHASE_INFER_BN = 1 << 12,
   /* modifier of FB_PHASE_SAMPLE: the caller supplied the batch rows (fb_upload_batch / fb_set_batch), e.g. sampled from a
    * host-resident replay buffer (in_memory_replay_buffer.py:139-190 run by the caller): the device RNG draws of the phase
    * still run (rng_device = 1), the replay gather is skipped and no replay needs to be bound */

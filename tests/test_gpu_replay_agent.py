@@ -287,6 +287,49 @@ def test_agent_host_replay_with_device_rng():
         assert agent.engine.launch_count(L.PHASE_ALL | L.RUN_HOST_BATCH) == agent.engine.launch_count(L.PHASE_ALL) - 1
 
 
+@pytest.mark.parametrize("goal_space,G", [(None, 24), ("simplified_walker", 3)])
+def test_inference_plans_match_the_module_forward(goal_space, G):
+    """act / get_goal_meta / compute_z_correl / infer_meta_from_obs_and_rewards run through the library's inference plans
+    (FB_PHASE_INFER_*); checked against the same networks evaluated by the parameter-view nn.Modules (modules.py mirrors
+    fb_modules.py; pinned against the oracle in test_cpu_boundary.py), at the reference's default widths."""
+    import math
+    import torch.nn.functional as F
+    from controllable_agent_b200 import FBDDPGAgent
+    torch.manual_seed(9)
+    O_, A_, Z = 24, 6, 50
+    agent = FBDDPGAgent(obs_type="states", obs_shape=(O_,), action_shape=(A_,), device="cuda", num_expl_steps=0, update_encoder=True,
+                        goal_space=goal_space, use_tb=False, use_wandb=False, use_hiplog=False, batch_size=256, num_inference_steps=600)
+    for p in list(agent.actor.parameters()) + list(agent.backward_net.parameters()):   # biases / LN affine away from their init
+        if p.dim() == 1:
+            p.data.add_(0.1 * torch.randn_like(p))
+    rs = np.random.RandomState(4)
+    for trial in range(3):
+        obs, goal = rs.standard_normal(O_).astype(np.float32), rs.standard_normal(G).astype(np.float32)
+        meta = agent.init_meta()
+        with torch.no_grad():
+            o, z = torch.as_tensor(obs).cuda()[None], torch.as_tensor(meta["z"]).cuda()[None]
+            mu_ref = agent.actor(o, z, 0.2).mean[0].cpu().numpy()
+            b_ref = agent.backward_net(torch.as_tensor(goal).cuda()[None])
+            zg_ref = (math.sqrt(Z) * F.normalize(b_ref, dim=1))[0].cpu().numpy()
+            corr_ref = torch.matmul(F.normalize(b_ref, 1), F.normalize(z, 1).T).item()
+        assert np.abs(agent.act(obs, meta, 0, eval_mode=True) - mu_ref).max() < 2e-5
+        a = agent.act(obs, meta, 0, eval_mode=False)
+        assert a.shape == (A_,) and np.all(np.abs(a) <= 1) and np.abs(a - mu_ref).max() < 0.2 * 6   # mu + N(0, 0.2) noise
+        assert np.abs(agent.get_goal_meta(goal)["z"] - zg_ref).max() < 2e-4
+
+        class TS:
+            observation = goal if goal_space is None else obs
+        TS.goal = goal
+        assert agent.compute_z_correl(TS, meta) == pytest.approx(corr_ref, rel=1e-3, abs=1e-6)
+    N = 600   # two full chunks of 256 rows and a padded one
+    xs, rw = torch.randn(N, G, device="cuda"), torch.rand(N, 1, device="cuda")
+    with torch.no_grad():
+        zr = torch.matmul(rw.T, agent.backward_net(xs)) / N
+        zr = (math.sqrt(Z) * F.normalize(zr, dim=1))[0].cpu().numpy()
+    got = agent.infer_meta_from_obs_and_rewards(xs, rw)["z"]
+    assert got.shape == (Z,) and np.abs(got - zr).max() < 2e-4
+
+
 def test_unsupported_branches_raise():
     from controllable_agent_b200 import FBDDPGAgent
     base = dict(obs_type="states", obs_shape=(24,), action_shape=(6,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,

@@ -322,7 +322,7 @@ def test_contraction_tcgen05_matches_simt_and_oracle(case):
 
 
 @pytest.mark.parametrize("contract_mode", [0, 1])
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_step_sums_to_single_gpu_step(world, contract_mode):
     """Multi-GPU decomposition emulated on one device: `world` engines own disjoint row blocks of one global
     batch, exchange the [F1|F2|tF1|tF2|B|tB|discount] block, and the SUM of their flat gradients / loss partials must equal the
