@@ -33,6 +33,17 @@ static int encode_tiled_map(CUtensorMap* map, const float* base, int rows, int c
 
 static int encode_operand_map(CUtensorMap* map, float* base, int rows, int cols) { return encode_tiled_map(map, base, rows, cols, cols, 64); }
 
+static int make_tc_launch(const std::vector<TcGemmDesc>& v, int total, int ring_bn, TcLaunch* out) {
+  if (v.size() > TC_MAX_PROBS) return FB_E_UNSUPPORTED;
+  memset(out, 0, sizeof(*out));
+  out->nprob = (int)v.size(); out->total = total; out->ring_bn = ring_bn;
+  for (size_t i = 0; i < v.size(); ++i) {
+    const TcGemmDesc& d = v[i];
+    out->p[i] = TcProb{d.M, d.N, d.K, d.K2, d.bn, d.flags, d.tiles_n, d.work_begin, d.splitk, d.kb_per_split};
+  }
+  return FB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // op recorders
 // ------------------------------------------------------------------------------------------------
@@ -282,7 +293,9 @@ struct Builder {
       if (v[i].splitk == 1 && v[i].M % 4 == 0 && cur_lane == 0)
         produced.push_back(Produced{v[i].C, v[i].M, v[i].N, v[i].ldc, (size_t)((const char*)(dd + i) - d_arena)});
     const int grid = work < FB_SM_COUNT ? work : FB_SM_COUNT;   // persistent: one CTA per SM walks the group's tiles
-    push([dd, n, work, grid, ring_bn](cudaStream_t s) {
+    TcLaunch hdr;
+    if (make_tc_launch(v, work, ring_bn, &hdr) != FB_OK && rc == FB_OK) rc = FB_E_UNSUPPORTED;
+    push([dd, hdr, grid](cudaStream_t s) {
       // programmatic dependent launch: the kernel's prologue may overlap the tail of the launch before it (fb_pdl_wait inside)
       cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = s;
@@ -290,7 +303,7 @@ struct Builder {
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = attr; cfg.numAttrs = getenv("FB_NO_PDL") ? 0 : 1;
-      return cudaLaunchKernelEx(&cfg, k_gemm_tc, dd, n, work, ring_bn);
+      return cudaLaunchKernelEx(&cfg, k_gemm_tc, dd, hdr);
     }, FB_OPK_GEMM_TC, flops, bytes);
     if (used_early) h->ops[phase].back().wait_stage = 1;   // operands staged on the staging lane: wait for this phase's staging event
   }
@@ -1522,7 +1535,9 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
     CK(cudaMemcpyAsync(dd, &d, sizeof(d), cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    k_gemm_tc<<<d.work_count < FB_SM_COUNT ? d.work_count : FB_SM_COUNT, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, 1, d.work_count, d.bn);
+    TcLaunch hdr;
+    make_tc_launch(std::vector<TcGemmDesc>(1, d), d.work_count, d.bn, &hdr);
+    k_gemm_tc<<<d.work_count < FB_SM_COUNT ? d.work_count : FB_SM_COUNT, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, hdr);
     CK(cudaGetLastError());
     CK(cudaFreeAsync(dd, s));
     if (tmp) CK(cudaFreeAsync(tmp, s));
@@ -1588,9 +1603,11 @@ int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int splitk, int dbg
     CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const int grid = work < FB_SM_COUNT ? work : FB_SM_COUNT;
-    for (int r = 0; r < 3; ++r) k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, nprob, work, bn);
+    TcLaunch hdr;
+    make_tc_launch(v, work, bn, &hdr);
+    for (int r = 0; r < 3; ++r) k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, hdr);
     CK(cudaEventRecord(e0, s));
-    for (int r = 0; r < reps; ++r) k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, nprob, work, bn);
+    for (int r = 0; r < reps; ++r) k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, hdr);
     CK(cudaEventRecord(e1, s));
     CK(cudaEventSynchronize(e1));
     CK(cudaGetLastError());

@@ -64,6 +64,13 @@ struct __align__(64) TcGemmDesc {
   int splitk, kb_per_split;   // splitk > 1: a tile's k-blocks (of both products) are shared by splitk work items that add into a zeroed C (no ReLU)
 };
 
+// Launch header passed BY VALUE (kernel parameter = constant bank): everything a role needs to find its tile and size its
+// loops without a dependent chain of global loads (a search over the 1 KB descriptors costs one L2 round trip per problem,
+// several microseconds of every launch); the descriptors in global memory only supply tensor maps and pointers.
+#define TC_MAX_PROBS 16
+struct TcProb { int M, N, K, K2, bn, flags, tiles_n, work_begin, splitk, kb_per_split; };
+struct TcLaunch { int nprob, total, ring_bn, pad; TcProb p[TC_MAX_PROBS]; };
+
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count) : "memory");
@@ -151,29 +158,33 @@ __device__ __forceinline__ void tc_build_lo(const float4* __restrict__ raw, floa
   for (int i = 0; i < CNT; ++i) lo[t + i * 128] = tc_lo4(x[i]);
 }
 
-// which problem / tile / k-range of the group is work item w
-__device__ __forceinline__ const TcGemmDesc* tc_locate(const TcGemmDesc* __restrict__ descs, int nprob, int w, int* m0, int* n0, int* kb0,
-                                                       int* kb1) {
+// which problem / tile / k-range of the group is work item w (header only: no global loads)
+__device__ __forceinline__ int tc_locate(const TcLaunch& L, int w, int* m0, int* n0, int* kb0, int* kb1) {
   int p = 0;
-  while (p + 1 < nprob && descs[p + 1].work_begin <= w) ++p;
-  const TcGemmDesc* d = &descs[p];
-  int local = w - d->work_begin;
-  const int nk = (d->K + TC_BK - 1) / TC_BK + (d->K2 + TC_BK - 1) / TC_BK;
-  if (d->splitk > 1) {
-    const int split = local % d->splitk;
-    local /= d->splitk;
-    *kb0 = split * d->kb_per_split;
-    *kb1 = min(nk, *kb0 + d->kb_per_split);
+  while (p + 1 < L.nprob && L.p[p + 1].work_begin <= w) ++p;
+  const TcProb& d = L.p[p];
+  int local = w - d.work_begin;
+  const int nk = (d.K + TC_BK - 1) / TC_BK + (d.K2 + TC_BK - 1) / TC_BK;
+  if (d.splitk > 1) {
+    const int split = local % d.splitk;
+    local /= d.splitk;
+    *kb0 = split * d.kb_per_split;
+    *kb1 = min(nk, *kb0 + d.kb_per_split);
   } else {
     *kb0 = 0; *kb1 = nk;
   }
-  const int tm = local / d->tiles_n, tn = local - tm * d->tiles_n;
-  *m0 = tm * TC_BM; *n0 = tn * d->bn;
-  return d;
+  const int tm = local / d.tiles_n, tn = local - tm * d.tiles_n;
+  *m0 = tm * TC_BM; *n0 = tn * d.bn;
+  return p;
+}
+
+__device__ __forceinline__ void tc_prefetch_map(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
 
 // ring_bn: B-tile rows the ring geometry is laid out for (>= every problem's bn); total: tiles of the whole group
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __restrict__ descs, int nprob, int total, int ring_bn) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __restrict__ descs, const __grid_constant__ TcLaunch L) {
+  const int total = L.total, ring_bn = L.ring_bn;
   fb_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   __shared__ __align__(16) float epi_scratch[4 * 32 * TC_EPI_LD];
@@ -220,9 +231,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       uint32_t kbg = 0;   // k-blocks issued by this CTA so far (ring position), across tiles
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         int m0, n0, kb0, kb1;
-        const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0, &kb0, &kb1);
-        const int bn = d->bn, flags = d->flags;
-        const int nk1 = (d->K + TC_BK - 1) / TC_BK;
+        const int pi = tc_locate(L, w, &m0, &n0, &kb0, &kb1);
+        const TcGemmDesc* __restrict__ d = &descs[pi];
+        const int bn = L.p[pi].bn, flags = L.p[pi].flags;
+        const int nk1 = (L.p[pi].K + TC_BK - 1) / TC_BK;
+        if (kb0 < nk1) { tc_prefetch_map(&d->mapA); tc_prefetch_map(&d->mapB); }
         const uint32_t tx_bytes = (uint32_t)TC_BM * 128u * ((flags & TC_A_PRE) ? 2u : 1u) + (uint32_t)bn * 128u * ((flags & TC_B_PRE) ? 2u : 1u);
         for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)nst;
@@ -244,11 +257,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       uint32_t kbg = 0, it = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
         int m0, n0, kb0, kb1;
-        const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0, &kb0, &kb1);
-        const int bn = d->bn;
+        const int pi = tc_locate(L, w, &m0, &n0, &kb0, &kb1);
+        const int bn = L.p[pi].bn;
         const int nk = kb1 - kb0;
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        const int nchain = (d->flags & TC_DBG_ONECHAIN) ? 1 : 3;
+        const int nchain = (L.p[pi].flags & TC_DBG_ONECHAIN) ? 1 : 3;
         if (it > 0) {   // the previous tile's accumulators must have been read out
           tc_mbar_wait(&bar_tmem_empty, (it - 1u) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -285,9 +298,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
     uint32_t kbg = 0, it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       int m0, n0, kb0, kb1;
-      const TcGemmDesc* __restrict__ d = tc_locate(descs, nprob, w, &m0, &n0, &kb0, &kb1);
-      const int bn = d->bn, flags = d->flags;
+      const int pi = tc_locate(L, w, &m0, &n0, &kb0, &kb1);
+      const TcGemmDesc* __restrict__ d = &descs[pi];
+      const int bn = L.p[pi].bn, flags = L.p[pi].flags;
       const int nk = kb1 - kb0;
+      // epilogue pointers: loaded now, used after the mainloop (their latency hides behind it)
+      const int M = L.p[pi].M, N = L.p[pi].N, ldc = d->ldc, ldmask = d->ldmask;
+      const float* __restrict__ bias = d->bias;
+      const float* __restrict__ mask = d->mask;
+      float* __restrict__ C = d->C;
+      float* __restrict__ CT = d->CT;
+      float* __restrict__ CT_lo = d->CT_lo;
+      const int ldct = d->ldct;
       const bool build_a = !(flags & (TC_A_PRE | TC_DBG_NOBUILD)), build_b = !(flags & (TC_B_PRE | TC_DBG_NOBUILD));
       for (int kb = 0; kb < nk; ++kb, ++kbg) {
         const uint32_t s = kbg % (uint32_t)nst;
@@ -306,20 +328,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       tc_mbar_wait(&bar_accum, it & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-      const int M = d->M, N = d->N, ldc = d->ldc, ldmask = d->ldmask;
-      const float* __restrict__ bias = d->bias;
-      const float* __restrict__ mask = d->mask;
-      float* __restrict__ C = d->C;
       const bool c_vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
       const bool m_vec = ((ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
       const bool b_vec = (reinterpret_cast<uintptr_t>(bias) & 15u) == 0;
       const int n_hh = nk < 3 ? nk : 3;   // hi.hi accumulators that were written
       const int sub = lane >> 3, c4 = (lane & 7) * 4;
-      const bool split = d->splitk > 1;   // partial sums: added into the zeroed C; the bias rides on the first k-range
+      const bool split = L.p[pi].splitk > 1;   // partial sums: added into the zeroed C; the bias rides on the first k-range
       if (split && kb0 > 0) bias = nullptr;
-      float* __restrict__ CT = d->CT;
-      float* __restrict__ CT_lo = d->CT_lo;
-      const int ldct = d->ldct;
       for (int cb = 0; cb < ((flags & TC_DBG_NOEPI) ? 0 : bn); cb += 32) {
         if (n0 + cb >= N) break;          // warp-uniform: nothing of this 32-column chunk is inside the matrix
         // the saved activations this thread's 8 output float4s are masked with: issued first, so that their L2 latency
