@@ -116,6 +116,7 @@ __device__ __forceinline__ void ct_tmem_ld16(uint32_t taddr, float (&v)[16]) {
 __global__ void __launch_bounds__(256) k_contract_split(const float* __restrict__ blk, int blk_pitch, int ldz, int rows, int Z, int KP,
                                                         float* __restrict__ out) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = CT_NUM_OPERANDS * rows * KP;
   if (idx >= total) return;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(256) k_contract_split(const float* __restrict_
 // dynamic smem: [stage][A raw | A lo | B raw | B lo], each part nbox boxes of (rows x 128 B); 1024-byte aligned
 __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_constant__ ContractParams P) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   extern __shared__ __align__(1024) uint8_t ct_smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[2];
   __shared__ __align__(8) uint64_t bar_empty[2];

@@ -33,6 +33,21 @@ static int encode_tiled_map(CUtensorMap* map, const float* base, int rows, int c
 
 static int encode_operand_map(CUtensorMap* map, float* base, int rows, int cols) { return encode_tiled_map(map, base, rows, cols, cols, 64); }
 
+// Every kernel of the plan is launched with the programmatic-serialization attribute: it may become resident while its
+// predecessor in the stream still runs and waits in fb_pdl_wait() (first statement of every kernel; after the prologue in
+// k_gemm_tc), which hides the launch latency of the ~60 dependent launches of a step.  FB_NO_PDL=1 launches them plainly.
+template <typename... KArgs, typename... Args>
+static void fb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  static const bool pdl = getenv("FB_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface through cudaGetLastError() at the call site
+}
+
 static int make_tc_launch(const std::vector<TcGemmDesc>& v, int total, int ring_bn, TcLaunch* out) {
   if (v.size() > TC_MAX_PROBS) return FB_E_UNSUPPORTED;
   memset(out, 0, sizeof(*out));
@@ -282,7 +297,7 @@ struct Builder {
       const TransposeDesc* td = arena_put(h, pending, d_arena);
       const int nt = (int)pending.size();
       push([td, nt, ctas](cudaStream_t s) {
-        k_transpose_grouped<<<ctas, 256, 0, s>>>(td, nt);
+        fb_launch_pdl(k_transpose_grouped, dim3(ctas), dim3(256), 0, s, td, nt);
         return cudaGetLastError();
       }, FB_OPK_TRANSPOSE, 0.0, tbytes);
     }
@@ -317,7 +332,7 @@ struct Builder {
     g = std::move(simt);
     GroupLaunch gl = finalize_group(h, std::move(g), d_arena);
     push([gl](cudaStream_t s) {
-      k_gemm_grouped<<<gl.ctas, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(gl.d_descs, gl.nprob);
+      fb_launch_pdl(k_gemm_grouped, dim3(gl.ctas), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, s, gl.d_descs, gl.nprob);
       return cudaGetLastError();
     }, FB_OPK_GEMM, gl.flops, gl.bytes);
   }
@@ -330,8 +345,8 @@ struct Builder {
     const LnDesc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
     push([dd, n, rows, vec](cudaStream_t s) {
-      if (vec) k_ln_tanh_fwd_v4<<<fb_ceil_div(rows, 8), 256, 0, s>>>(dd, n, rows);
-      else k_ln_tanh_fwd<<<fb_ceil_div(rows, 8), 256, 0, s>>>(dd, n, rows);
+      if (vec) fb_launch_pdl(k_ln_tanh_fwd_v4, dim3(fb_ceil_div(rows, 8)), dim3(256), 0, s, dd, n, rows);
+      else fb_launch_pdl(k_ln_tanh_fwd, dim3(fb_ceil_div(rows, 8)), dim3(256), 0, s, dd, n, rows);
       return cudaGetLastError();
     }, FB_OPK_LAYERNORM, 0.0, bytes);
   }
@@ -349,8 +364,8 @@ struct Builder {
     const LnBwdDesc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
     push([dd, n, ctas, vec](cudaStream_t s) {
-      if (vec) k_ln_tanh_bwd_v4<<<ctas, 256, 0, s>>>(dd, n);
-      else k_ln_tanh_bwd<<<ctas, 256, 0, s>>>(dd, n);
+      if (vec) fb_launch_pdl(k_ln_tanh_bwd_v4, dim3(ctas), dim3(256), 0, s, dd, n);
+      else fb_launch_pdl(k_ln_tanh_bwd, dim3(ctas), dim3(256), 0, s, dd, n);
       return cudaGetLastError();
     }, FB_OPK_LAYERNORM, 0.0, bytes);
   }
@@ -360,7 +375,7 @@ struct Builder {
     const L2Desc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
     push([dd, n, rows](cudaStream_t s) {
-      k_l2norm_fwd<<<fb_ceil_div(rows, 8), 256, 0, s>>>(dd, n, rows);
+      fb_launch_pdl(k_l2norm_fwd, dim3(fb_ceil_div(rows, 8)), dim3(256), 0, s, dd, n, rows);
       return cudaGetLastError();
     });
   }
@@ -375,7 +390,7 @@ struct Builder {
     const ColsumDesc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
     push([dd, n, ctas](cudaStream_t s) {
-      k_colsum<<<ctas, 256, 0, s>>>(dd, n);
+      fb_launch_pdl(k_colsum, dim3(ctas), dim3(256), 0, s, dd, n);
       return cudaGetLastError();
     }, FB_OPK_COLSUM, 0.0, bytes, 1);  // side lane: bias gradients are leaves of the dependency graph (joined at phase end)
   }
@@ -591,16 +606,16 @@ static int build_plan(fb_handle* h) {
     b.push([rp, sc, hh](cudaStream_t s) mutable {
       rp.ep_len = hh->replay_bound ? hh->replay.d_episode_len : nullptr;   // no replay (host batches): no index draws
       rp.rows_per_episode = hh->replay_bound ? hh->replay.rows_per_episode : 2;
-      k_rng_draw<<<fb_ceil_div(rp.batch, 8), 256, 0, s>>>(rp, sc);
+      fb_launch_pdl(k_rng_draw, dim3(fb_ceil_div(rp.batch, 8)), dim3(256), 0, s, rp, sc);
       return cudaGetLastError();
     });
     int npow2 = 1; while (npow2 < B) npow2 <<= 1;
     unsigned int* keys = h->d_perm_keys; int* perm = h->d_perm;
     b.push([keys, perm, B, npow2](cudaStream_t s) {
-      k_randperm<<<1, 1024, npow2 * sizeof(unsigned long long), s>>>(keys, B, npow2, perm);
+      fb_launch_pdl(k_randperm, dim3(1), dim3(1024), npow2 * sizeof(unsigned long long), s, keys, B, npow2, perm);
       return cudaGetLastError();
     });
-    b.push([sc](cudaStream_t s) { k_tick<<<1, 32, 0, s>>>(sc, 2, 0.f, 0.f); return cudaGetLastError(); });
+    b.push([sc](cudaStream_t s) { fb_launch_pdl(k_tick, dim3(1), dim3(32), 0, s, sc, 2, 0.f, 0.f); return cudaGetLastError(); });
   }
   {
     fb_handle* hh = h;
@@ -608,7 +623,7 @@ static int build_plan(fb_handle* h) {
       if (!hh->replay_bound) return cudaErrorInvalidValue;
       GatherParams gp;
       if (build_gather_params(hh->replay, gp, hh->bl, hh->packed.ld) != FB_OK) return cudaErrorInvalidValue;
-      k_gather_rows<<<fb_ceil_div(hh->cfg.batch, 8), 256, 0, s>>>(gp, hh->d_ep_idx, hh->d_step_idx, nullptr, hh->cfg.batch,
+      fb_launch_pdl(k_gather_rows, dim3(fb_ceil_div(hh->cfg.batch, 8)), dim3(256), 0, s, gp, hh->d_ep_idx, hh->d_step_idx, nullptr, hh->cfg.batch,
                                                                  &sc->replay_discount, 0.f, hh->packed.p);
       return cudaGetLastError();
     }, FB_OPK_GATHER, 0.0, 2.0 * 4.0 * (double)B * (double)h->bl.pitch);
@@ -626,7 +641,7 @@ static int build_plan(fb_handle* h) {
     sp.blk = bl.p; sp.blk_pitch = bl.ld; sp.disc_col = disc_col;
     sp.perm = h->d_perm; sp.mix_override = nullptr;
     const float* packed = h->packed.p;
-    b.push([sp, packed](cudaStream_t s) { k_stage_inputs<<<sp.batch, 128, 0, s>>>(sp, packed); return cudaGetLastError(); });
+    b.push([sp, packed](cudaStream_t s) { fb_launch_pdl(k_stage_inputs, dim3(sp.batch), dim3(128), 0, s, sp, packed); return cudaGetLastError(); });
   }
   const bool do_mix = c.mix_ratio > 0.f;
   // The z-mixing forward (a chain of five small launches) runs on the side lane while the main lane already computes the
@@ -643,7 +658,7 @@ static int build_plan(fb_handle* h) {
     ZFinalParams zp; memset(&zp, 0, sizeof(zp));
     zp.batch = B; zp.Z = Z; zp.O = O; zp.z_rand = h->z_rand.p; zp.ldZ = z.ld; zp.b_mix = b_mix_out.p; zp.ld_bmix = b_mix_out.ld;
     zp.mix_mask = do_mix ? h->d_mix_mask : nullptr; zp.z = z.p; zp.actor_in_oz = actor_in_oz.p; zp.ldOZ = actor_in_oz.ld;
-    b.push([zp](cudaStream_t s) { k_z_final<<<fb_ceil_div(zp.batch, 8), 256, 0, s>>>(zp); return cudaGetLastError(); });
+    b.push([zp](cudaStream_t s) { fb_launch_pdl(k_z_final, dim3(fb_ceil_div(zp.batch, 8)), dim3(256), 0, s, zp); return cudaGetLastError(); });
   }
   b.cur_lane = 0;
   b.gemm({lin_fwd(eAo.x, pA.w(A_O + 0), pA.v(A_O + 1), eAo.pre, 0), lin_fwd(eFoa.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eFoa.pre, 0),
@@ -671,7 +686,7 @@ static int build_plan(fb_handle* h) {
     ap.in_noa = in_noa.p; ap.in_oa2 = in_oa2.p; ap.ldOA = in_noa.ld; ap.next_action = next_action.p; ap.action_new = action_new.p;
     ap.acc = acc;
     b.push([ap, sc](cudaStream_t s) {
-      k_actor_out<<<fb_ceil_div(2 * ap.batch * ap.A, 256), 256, 0, s>>>(ap, sc);
+      fb_launch_pdl(k_actor_out, dim3(fb_ceil_div(2 * ap.batch * ap.A, 256)), dim3(256), 0, s, ap, sc);
       return cudaGetLastError();
     });
   }
@@ -695,7 +710,7 @@ static int build_plan(fb_handle* h) {
     {
       const float* blk = bg.p; const int pitch = bg.ld;
       b.push([blk, pitch, ldZ, n, Z, KP, x2](cudaStream_t s) {
-        k_contract_split<<<fb_ceil_div(CT_NUM_OPERANDS * n * KP, 256), 256, 0, s>>>(blk, pitch, ldZ, n, Z, KP, x2);
+        fb_launch_pdl(k_contract_split, dim3(fb_ceil_div(CT_NUM_OPERANDS * n * KP, 256)), dim3(256), 0, s, blk, pitch, ldZ, n, Z, KP, x2);
         return cudaGetLastError();
       }, FB_OPK_ELEMENTWISE, 0.0, 4.0 * CT_NUM_OPERANDS * n * 3.0 * KP);
     }
@@ -722,7 +737,7 @@ static int build_plan(fb_handle* h) {
       r.disc = bl.p + disc_col; r.disc_stride = bl.ld;
       b.push([r, smem_bytes](cudaStream_t s) {
         dim3 grid(fb_ceil_div(r.nc, CT_TILE_N), fb_ceil_div(r.nr, CT_TILE_M));
-        k_contract_tc<<<grid, CT_THREADS, smem_bytes, s>>>(r);
+        fb_launch_pdl(k_contract_tc, dim3(grid), dim3(CT_THREADS), smem_bytes, s, r);
         return cudaGetLastError();
       }, FB_OPK_CONTRACT, 5.0 * tile_flops * B * (double)n, 4.0 * (5.0 * B * (double)n + 6.0 * n * 2.0 * KP));
     }
@@ -735,7 +750,7 @@ static int build_plan(fb_handle* h) {
       r.disc = bg.p + disc_col; r.disc_stride = bg.ld;
       b.push([r, smem_bytes](cudaStream_t s) {
         dim3 grid(fb_ceil_div(r.nc, CT_TILE_N), fb_ceil_div(r.nr, CT_TILE_M));
-        k_contract_tc<<<grid, CT_THREADS, smem_bytes, s>>>(r);
+        fb_launch_pdl(k_contract_tc, dim3(grid), dim3(CT_THREADS), smem_bytes, s, r);
         return cudaGetLastError();
       }, FB_OPK_CONTRACT, 4.0 * tile_flops * B * (double)n, 4.0 * (2.0 * B * (double)n + 6.0 * n * 2.0 * KP));
     }
@@ -750,7 +765,7 @@ static int build_plan(fb_handle* h) {
     lp.disc = bl.p + disc_col; lp.disc_stride = bl.ld; lp.inv_noff = inv_noff; lp.inv_n = inv_n; lp.ortho_coef = c.ortho_coef; lp.acc = acc;
     b.push([lp](cudaStream_t s) {
       dim3 grid(fb_ceil_div(lp.nc, 1024) > 0 ? fb_ceil_div(lp.nc, 1024) : 1, lp.nr < 592 ? lp.nr : 592);
-      k_fb_loss_elem<<<grid, 256, 0, s>>>(lp);
+      fb_launch_pdl(k_fb_loss_elem, dim3(grid), dim3(256), 0, s, lp);
       return cudaGetLastError();
     }, FB_OPK_LOSS, 0.0, 4.0 * 8.0 * (double)B * (double)n);
     LossElemTParams lt; memset(&lt, 0, sizeof(lt));
@@ -758,7 +773,7 @@ static int build_plan(fb_handle* h) {
     lt.disc = bg.p + disc_col; lt.disc_stride = bg.ld; lt.inv_noff = inv_noff; lt.inv_n = inv_n;
     b.push([lt](cudaStream_t s) {
       dim3 grid(fb_ceil_div(lt.nc, 1024) > 0 ? fb_ceil_div(lt.nc, 1024) : 1, lt.nr < 592 ? lt.nr : 592);
-      k_fb_loss_elem_t<<<grid, 256, 0, s>>>(lt);
+      fb_launch_pdl(k_fb_loss_elem_t, dim3(grid), dim3(256), 0, s, lt);
       return cudaGetLastError();
     }, FB_OPK_LOSS, 0.0, 4.0 * 6.0 * (double)B * (double)n);
   }
@@ -775,7 +790,7 @@ static int build_plan(fb_handle* h) {
   } else {
     b.memset0(dblk.p, (size_t)dblk.rows * dblk.ld * sizeof(float));
     b.push([dB, Bm, B, Z, db_coef](cudaStream_t s) {   // dB starts from the diagonal term, the products accumulate onto it
-      k_loss_init_db<<<fb_ceil_div(B * Z, 256), 256, 0, s>>>(dB.p, dB.ld, Bm.p, Bm.ld, B, Z, db_coef);
+      fb_launch_pdl(k_loss_init_db, dim3(fb_ceil_div(B * Z, 256)), dim3(256), 0, s, dB.p, dB.ld, Bm.p, Bm.ld, B, Z, db_coef);
       return cudaGetLastError();
     });
     auto inner = [&](const Mat& Gm, const Mat& Yall, const Mat& C) {  // C[B, Z] += Gm[B, n] . Yall[n, Z]
@@ -794,7 +809,7 @@ static int build_plan(fb_handle* h) {
     float* dsum = tc_inner ? dB.p : nullptr;   // keep the "dB" view complete on both paths
     const float coef = tc_inner ? db_coef : 0.f;
     b.push([p0, p1, p2, ldp, coef, dsum, dB, Bm, bO, draw, B, Z](cudaStream_t s) {
-      k_l2norm_bwd<<<fb_ceil_div(B, 8), 256, 0, s>>>(p0, p1, p2, ldp, coef, dsum, dB.ld, Bm.p, Bm.ld, bO.nrm, draw.p, draw.ld, B, Z);
+      fb_launch_pdl(k_l2norm_bwd, dim3(fb_ceil_div(B, 8)), dim3(256), 0, s, p0, p1, p2, ldp, coef, dsum, dB.ld, Bm.p, Bm.ld, bO.nrm, draw.p, draw.ld, B, Z);
       return cudaGetLastError();
     });
   }
@@ -830,11 +845,11 @@ static int build_plan(fb_handle* h) {
   b.set_phase(FB_PHASE_FB_ADAM);
   {
     const float b1 = c.beta1, b2 = c.beta2, eps = c.adam_eps;
-    b.push([sc, b1, b2](cudaStream_t s) { k_tick<<<1, 32, 0, s>>>(sc, 0, b1, b2); return cudaGetLastError(); });
+    b.push([sc, b1, b2](cudaStream_t s) { fb_launch_pdl(k_tick, dim3(1), dim3(32), 0, s, sc, 0, b1, b2); return cudaGetLastError(); });
     float4 *p = (float4*)bf.d_param_fb, *g = (float4*)bf.d_grad_fb, *m = (float4*)bf.d_m_fb, *v = (float4*)bf.d_v_fb, *t = (float4*)bf.d_target_fb;
     const size_t n4 = h->seg_fb.size / 4, split4 = h->bwd_offset / 4;
     b.push([=](cudaStream_t s) {
-      k_adam<<<FB_SM_COUNT * 8, 256, 0, s>>>(p, g, m, v, t, n4, split4, sc, 0, b1, b2, eps);
+      fb_launch_pdl(k_adam, dim3(FB_SM_COUNT * 8), dim3(256), 0, s, p, g, m, v, t, n4, split4, sc, 0, b1, b2, eps);
       return cudaGetLastError();
     }, FB_OPK_ADAM, 0.0, 4.0 * 4.0 * (double)n4 * 10.0);  // r(p,g,m,v,target) + w(p,g,m,v,target)
   }
@@ -850,7 +865,7 @@ static int build_plan(fb_handle* h) {
   {
     const float inv_n = 1.0f / (float)n;
     b.push([Fa1, Fa2, z, dFa1, dFa2, B, Z, inv_n, acc](cudaStream_t s) {
-      k_actor_q<<<fb_ceil_div(B, 8), 256, 0, s>>>(Fa1.p, Fa2.p, Fa1.ld, z.p, z.ld, dFa1.p, dFa2.p, dFa1.ld, B, Z, inv_n, acc);
+      fb_launch_pdl(k_actor_q, dim3(fb_ceil_div(B, 8)), dim3(256), 0, s, Fa1.p, Fa2.p, Fa1.ld, z.p, z.ld, dFa1.p, dFa2.p, dFa1.ld, B, Z, inv_n, acc);
       return cudaGetLastError();
     });
   }
@@ -888,11 +903,11 @@ static int build_plan(fb_handle* h) {
   b.set_phase(FB_PHASE_ACTOR_ADAM);
   {
     const float b1 = c.beta1, b2 = c.beta2, eps = c.adam_eps;
-    b.push([sc, b1, b2](cudaStream_t s) { k_tick<<<1, 32, 0, s>>>(sc, 1, b1, b2); return cudaGetLastError(); });
+    b.push([sc, b1, b2](cudaStream_t s) { fb_launch_pdl(k_tick, dim3(1), dim3(32), 0, s, sc, 1, b1, b2); return cudaGetLastError(); });
     float4 *p = (float4*)bf.d_param_actor, *g = (float4*)bf.d_grad_actor, *m = (float4*)bf.d_m_actor, *v = (float4*)bf.d_v_actor;
     const size_t n4 = h->seg_actor.size / 4;
     b.push([=](cudaStream_t s) {
-      k_adam<<<FB_SM_COUNT * 8, 256, 0, s>>>(p, g, m, v, nullptr, n4, n4, sc, 1, b1, b2, eps);
+      fb_launch_pdl(k_adam, dim3(FB_SM_COUNT * 8), dim3(256), 0, s, p, g, m, v, nullptr, n4, n4, sc, 1, b1, b2, eps);
       return cudaGetLastError();
     }, FB_OPK_ADAM, 0.0, 4.0 * 4.0 * (double)n4 * 8.0);
   }
@@ -902,18 +917,18 @@ static int build_plan(fb_handle* h) {
   b.memset0(acc + ACC_F1, 6 * sizeof(double));
   b.memset0(h->d_linf, 16);
   b.push([F1, Bm, z, B, Z, acc](cudaStream_t s) {
-    k_metric_rows<<<fb_ceil_div(B, 8), 256, 0, s>>>(F1.p, F1.ld, Bm.p, Bm.ld, z.p, z.ld, B, Z, acc);
+    fb_launch_pdl(k_metric_rows, dim3(fb_ceil_div(B, 8)), dim3(256), 0, s, F1.p, F1.ld, Bm.p, Bm.ld, z.p, z.ld, B, Z, acc);
     return cudaGetLastError();
   });
   {
     unsigned int* linf = h->d_linf;
     b.push([Bg, n, Z, acc, linf](cudaStream_t s) {
-      k_metric_cov<<<Z, 256, 0, s>>>(Bg.p, Bg.ld, n, Z, acc, linf);
+      fb_launch_pdl(k_metric_cov, dim3(Z), dim3(256), 0, s, Bg.p, Bg.ld, n, Z, acc, linf);
       return cudaGetLastError();
     });
     MetricFinalParams mp; memset(&mp, 0, sizeof(mp));
     mp.acc = acc; mp.linf_bits = linf; mp.out = h->d_metrics; mp.n_local = B; mp.n_global = n; mp.Z = Z; mp.ortho_coef = c.ortho_coef;
-    b.push([mp](cudaStream_t s) { k_metric_final<<<1, 32, 0, s>>>(mp); return cudaGetLastError(); });
+    b.push([mp](cudaStream_t s) { fb_launch_pdl(k_metric_final, dim3(1), dim3(32), 0, s, mp); return cudaGetLastError(); });
   }
 
   // =========================== inference plans ==================================================
@@ -928,7 +943,7 @@ static int build_plan(fb_handle* h) {
     EmbedAct eo = embed_alloc(h, io, ihA.cs(0, Fd), H, "infer.obs_net"), eoz = embed_alloc(h, ioz, ihA.cs(Fd, Fd), H, "infer.obs_z_net");
     b.set_phase(FB_PHASE_INFER_ACTOR);
     b.push([=](cudaStream_t s) {
-      k_infer_concat<<<R, 128, 0, s>>>(io.p, io.ld, iz.p, iz.ld, ioz.p, ioz.ld, R, O, Z);
+      fb_launch_pdl(k_infer_concat, dim3(R), dim3(128), 0, s, io.p, io.ld, iz.p, iz.ld, ioz.p, ioz.ld, R, O, Z);
       return cudaGetLastError();
     });
     b.gemm({lin_fwd(eo.x, pA.w(A_O + 0), pA.v(A_O + 1), eo.pre, 0), lin_fwd(eoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eoz.pre, 0)});
@@ -937,7 +952,7 @@ static int build_plan(fb_handle* h) {
     b.gemm({lin_fwd(ihA, pA.w(A_POL + 0), pA.v(A_POL + 1), ih1, GF_RELU)});
     b.gemm({lin_fwd(ih1, pA.w(A_POL + 2), pA.v(A_POL + 3), ipre, 0)});
     b.push([=](cudaStream_t s) {
-      k_infer_tanh<<<fb_ceil_div(R * A, 128), 128, 0, s>>>(ipre.p, imu.p, ipre.ld, R, A);
+      fb_launch_pdl(k_infer_tanh, dim3(fb_ceil_div(R * A, 128)), dim3(128), 0, s, ipre.p, imu.p, ipre.ld, R, A);
       return cudaGetLastError();
     });
 
@@ -960,7 +975,7 @@ static int build_plan(fb_handle* h) {
     b.gemm({lin_fwd(bN.h2, pB.w(6), pB.v(7), bN.raw, 0)});
     b.l2_fwd({b_l2(bN, Z)});
     b.push([=](cudaStream_t s) {
-      k_infer_weighted_colsum<<<fb_ceil_div(Z, 32), 256, 0, s>>>(ibN.p, ibN.ld, irN.p, irN.ld, B, Z, izs.p);
+      fb_launch_pdl(k_infer_weighted_colsum, dim3(fb_ceil_div(Z, 32)), dim3(256), 0, s, ibN.p, ibN.ld, irN.p, irN.ld, B, Z, izs.p);
       return cudaGetLastError();
     });
   }
@@ -1260,7 +1275,7 @@ static cudaError_t ensure_streams(fb_handle* h) {
 }
 
 static cudaError_t launch_stage_batch(const fb_handle::StageBatch& sb, cudaStream_t s) {
-  k_transpose_grouped<<<sb.ctas, 256, 0, s>>>(sb.d_descs, sb.n);
+  fb_launch_pdl(k_transpose_grouped, dim3(sb.ctas), dim3(256), 0, s, sb.d_descs, sb.n);
   return cudaGetLastError();
 }
 

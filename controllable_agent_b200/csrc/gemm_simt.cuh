@@ -223,6 +223,7 @@ __device__ __forceinline__ void gemm_dispatch_major(const GemmDesc& d, int tm, i
 // grid.x = total work items (tiles x k-splits) of the group
 __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm_grouped(const GemmDesc* __restrict__ descs, int nprob) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   extern __shared__ __align__(16) float gemm_smem[];
   __shared__ GemmDesc sd;
   const int w = blockIdx.x;

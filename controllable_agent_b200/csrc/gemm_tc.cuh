@@ -453,6 +453,7 @@ __device__ __forceinline__ float tc_lo1(float x) { return x - __uint_as_float(__
 
 __global__ void __launch_bounds__(256) k_transpose_grouped(const TransposeDesc* __restrict__ descs, int nprob) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   __shared__ float tile[32][33];
   int p = 0;
   while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;

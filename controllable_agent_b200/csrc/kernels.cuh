@@ -34,6 +34,8 @@ __global__ void k_set_adam_steps(DevScalars* s, long long fb, long long actor) {
 
 // which: 0 = fb optimizer, 1 = actor optimizer, 2 = rng counter
 __global__ void k_tick(DevScalars* s, int which, float beta1, float beta2) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (which == 2) { s->rng_counter += 1ull; return; }
   long long t = (which == 0 ? s->step_fb : s->step_actor) + 1;
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(const __grid_constant__ Gat
                                                      int batch, const float* __restrict__ discount_scale_dev,
                                                      float discount_scale_host, float* __restrict__ out) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   const GatherParams* gp = &gpv;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= batch) return;
@@ -162,6 +165,7 @@ struct StageParams {
 
 __global__ void __launch_bounds__(128) k_stage_inputs(StageParams P, const float* __restrict__ packed) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   const int r = blockIdx.x;
   if (r >= P.batch) return;
   const BatchLayout& L = P.L;
@@ -206,6 +210,8 @@ struct RngParams {
 };
 
 __global__ void __launch_bounds__(256) k_rng_draw(RngParams P, const DevScalars* __restrict__ sc) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= P.batch) return;
   Philox ph(P.seed);
@@ -270,6 +276,8 @@ __global__ void __launch_bounds__(256) k_rng_draw(RngParams P, const DevScalars*
 
 // random permutation of [0, n): bitonic sort of (key, index) pairs in one CTA (torch.randperm, fb_ddpg.py:467)
 __global__ void __launch_bounds__(1024) k_randperm(const unsigned int* __restrict__ keys, int n, int npow2, int* __restrict__ perm) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   extern __shared__ unsigned long long sp[];
   for (int i = threadIdx.x; i < npow2; i += blockDim.x)
     sp[i] = (i < n) ? (((unsigned long long)keys[i] << 32) | (unsigned int)i) : 0xffffffffffffffffull;
@@ -298,6 +306,7 @@ struct LnDesc {
 
 __global__ void __launch_bounds__(256) k_ln_tanh_fwd(const LnDesc* __restrict__ descs, int nprob, int total_rows) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= total_rows) return;
   int p = 0;
@@ -321,6 +330,7 @@ __global__ void __launch_bounds__(256) k_ln_tanh_fwd(const LnDesc* __restrict__ 
 // mean / variance on the register copy like nn.LayerNorm, float4 stores.
 __global__ void __launch_bounds__(256) k_ln_tanh_fwd_v4(const LnDesc* __restrict__ descs, int nprob, int total_rows) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   constexpr int NV = 8;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= total_rows) return;
@@ -391,6 +401,7 @@ struct LnBwdDesc {
 
 __global__ void __launch_bounds__(256) k_ln_tanh_bwd(const LnBwdDesc* __restrict__ descs, int nprob) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   __shared__ float s_dg[FB_MAX_LN_DIM];
   __shared__ float s_db[FB_MAX_LN_DIM];
   int p = 0;
@@ -442,6 +453,7 @@ __global__ void __launch_bounds__(256) k_ln_tanh_bwd(const LnBwdDesc* __restrict
 // shared-memory atomics); per CTA one shared-memory combine across the 8 warps, then one global atomic per column.
 __global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const LnBwdDesc* __restrict__ descs, int nprob) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   constexpr int NV = 8;  // float4s per lane: D <= 32 * 4 * 8 = 1024
   __shared__ float s_dg[1024];
   __shared__ float s_db[1024];
@@ -542,6 +554,7 @@ struct L2Desc { const float* x; float* y; float* nrm; int rows, Z, ldx, ldy, row
 
 __global__ void __launch_bounds__(256) k_l2norm_fwd(const L2Desc* __restrict__ descs, int nprob, int total_rows) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= total_rows) return;
   int p = 0;
@@ -565,6 +578,7 @@ __global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ dy
                                                     int ldsum, const float* __restrict__ y, int ldy, const float* __restrict__ nrm,
                                                     float* __restrict__ dx, int lddx, int rows, int Z) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   const float sq = sqrtf((float)Z), isq = 1.0f / sq;
@@ -599,6 +613,7 @@ struct ZFinalParams {
 
 __global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= P.batch) return;
   const bool mix = P.mix_mask && P.mix_mask[r] != 0;
@@ -651,6 +666,7 @@ enum {
 
 __global__ void __launch_bounds__(256) k_actor_out(ActorOutParams P, const DevScalars* __restrict__ sc) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = 2 * P.batch * P.A;
   double lp = 0.0;
@@ -694,6 +710,8 @@ struct LossElemParams {
 };
 
 __global__ void __launch_bounds__(256) k_fb_loss_elem(LossElemParams P) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   double a_off = 0.0, a_diag = 0.0, a_cov = 0.0, a_covd = 0.0, a_tm = 0.0, a_m1 = 0.0;
   for (int row = blockIdx.y; row < P.nr; row += gridDim.y) {
   const float g = P.disc[(size_t)row * P.disc_stride];
@@ -748,6 +766,8 @@ struct LossElemTParams {
 };
 
 __global__ void __launch_bounds__(256) k_fb_loss_elem_t(LossElemTParams P) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   for (int row = blockIdx.y; row < P.nr; row += gridDim.y) {
     const int diag_col = P.row0 + row;
     const size_t base = (size_t)row * P.ld;
@@ -767,6 +787,8 @@ __global__ void __launch_bounds__(256) k_fb_loss_elem_t(LossElemTParams P) {
 
 // dB starts from the diagonal term of the orthonormality loss: d(-2 c mean_s Cov_ss)/dB_s = -(4c/n) B_s
 __global__ void k_loss_init_db(float* __restrict__ dB, int lddb, const float* __restrict__ Bm, int ldb, int rows, int Z, float coef) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * Z) return;
   const int r = idx / Z, c = idx - r * Z;
@@ -778,6 +800,7 @@ __global__ void __launch_bounds__(256) k_actor_q(const float* __restrict__ F1, c
                                                  const float* __restrict__ z, int ldz, float* __restrict__ dF1,
                                                  float* __restrict__ dF2, int lddf, int rows, int Z, float inv_n, double* acc) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   float q1 = 0.f, q2 = 0.f;
@@ -804,6 +827,7 @@ struct ColsumDesc { const float* src; float* dst; int rows, N, ld, cta_begin, ct
 
 __global__ void __launch_bounds__(256) k_colsum(const ColsumDesc* __restrict__ descs, int nprob) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   int p = 0;
   while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;
   const ColsumDesc d = descs[p];
@@ -835,6 +859,7 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
                                               float4* __restrict__ v, float4* __restrict__ target, size_t n4, size_t split4,
                                               const DevScalars* __restrict__ sc, int which, float beta1, float beta2, float eps) {
   fb_pdl_trigger();
+  fb_pdl_wait();
   const float bc1 = which == 0 ? sc->bc1_fb : sc->bc1_actor;
   const float bc2s = which == 0 ? sc->bc2s_fb : sc->bc2s_actor;
   const float lr_a = which == 0 ? sc->lr_forward : sc->lr_actor;
@@ -868,6 +893,8 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
 // sums over the local rows of F1, B, |B_s|, |z_s|
 __global__ void __launch_bounds__(256) k_metric_rows(const float* __restrict__ F1, int ldf, const float* __restrict__ Bm, int ldb,
                                                      const float* __restrict__ z, int ldz, int rows, int Z, double* acc) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   float f = 0.f, b = 0.f, bb = 0.f, zz = 0.f;
@@ -886,6 +913,8 @@ __global__ void __launch_bounds__(256) k_metric_rows(const float* __restrict__ F
 // coalesced), partial rows are summed through shared memory; linf via atomicMax on the float bits (values >= 0)
 __global__ void __launch_bounds__(256) k_metric_cov(const float* __restrict__ Bm, int ldb, int rows, int Z, double* acc,
                                                     unsigned int* linf_bits) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   __shared__ float part[8][128];
   const int a = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float mx = 0.f, sq = 0.f;
@@ -925,6 +954,8 @@ struct MetricFinalParams {
 };
 // indices must match FB_M_* in fb_b200.h
 __global__ void k_metric_final(MetricFinalParams P) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double n = (double)P.n_global, nl = (double)P.n_local;
   const double noff = n * (n - 1.0);
@@ -958,18 +989,24 @@ __global__ void k_metric_final(MetricFinalParams P) {
 // [obs | z] rows for the actor's obs_z_net (fb_modules.py:114)
 __global__ void k_infer_concat(const float* __restrict__ obs, int ldo, const float* __restrict__ z, int ldz, float* __restrict__ out, int ldout,
                                int rows, int O, int Z) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   const int r = blockIdx.x;
   if (r >= rows) return;
   for (int c = threadIdx.x; c < O + Z; c += blockDim.x) out[(size_t)r * ldout + c] = c < O ? obs[(size_t)r * ldo + c] : z[(size_t)r * ldz + c - O];
 }
 // mu = tanh(policy output)  (fb_modules.py:121)
 __global__ void k_infer_tanh(const float* __restrict__ pre, float* __restrict__ mu, int ld, int rows, int A) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows * A) { const int r = i / A, a = i - r * A; mu[(size_t)r * ld + a] = tanhf(pre[(size_t)r * ld + a]); }
 }
 // zsum[c] += sum_r reward[r] * b[r, c]   (fb_ddpg.py:215: z = reward^T . B): block = 32 columns, 8 warps stride the rows
 __global__ void __launch_bounds__(256) k_infer_weighted_colsum(const float* __restrict__ b, int ldb, const float* __restrict__ reward, int ldr,
                                                                int rows, int Z, float* __restrict__ zsum) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
   __shared__ float part[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.x * 32 + lane;
   float s = 0.f;
