@@ -609,13 +609,11 @@ static int build_plan(fb_handle* h) {
       fb_launch_pdl(k_rng_draw, dim3(fb_ceil_div(rp.batch, 8)), dim3(256), 0, s, rp, sc);
       return cudaGetLastError();
     });
-    int npow2 = 1; while (npow2 < B) npow2 <<= 1;
     unsigned int* keys = h->d_perm_keys; int* perm = h->d_perm;
-    b.push([keys, perm, B, npow2](cudaStream_t s) {
-      fb_launch_pdl(k_randperm, dim3(1), dim3(1024), npow2 * sizeof(unsigned long long), s, keys, B, npow2, perm);
+    b.push([keys, perm, B, sc](cudaStream_t s) {
+      fb_launch_pdl(k_randperm, dim3(fb_ceil_div(B, 256)), dim3(256), (size_t)B * sizeof(unsigned int), s, keys, B, perm, sc);
       return cudaGetLastError();
     });
-    b.push([sc](cudaStream_t s) { fb_launch_pdl(k_tick, dim3(1), dim3(32), 0, s, sc, 2, 0.f, 0.f); return cudaGetLastError(); });
   }
   {
     fb_handle* hh = h;
@@ -667,7 +665,11 @@ static int build_plan(fb_handle* h) {
 
   // =========================== FB_PHASE_FB_FWD ==================================================
   b.set_phase(FB_PHASE_FB_FWD);
-  b.memset0(acc, 8 * sizeof(double));
+  {   // loss / log-prob accumulators of update_fb: zeroed on the staging lane (consumers: k_actor_out here, the contraction later)
+    TransposeDesc zd; memset(&zd, 0, sizeof(zd));
+    zd.out = reinterpret_cast<float*>(acc); zd.rows = 1; zd.cols = 16; zd.ld_out = 16; zd.transpose = 2;
+    b.add_early(zd, b.phase);
+  }
   b.gemm({lin_fwd(eAoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eAoz.pre, 0), lin_fwd(eFoz.x, pF.w(E_OZ + 0), pF.v(E_OZ + 1), eFoz.pre, 0),
           lin_fwd(eFtoz.x, pFt.w(E_OZ + 0), pFt.v(E_OZ + 1), eFtoz.pre, 0)});
   b.ln_fwd({embed_ln(eAoz, pA.sub(A_OZ)), embed_ln(eFoz, pF.sub(E_OZ)), embed_ln(eFtoz, pFt.sub(E_OZ))});
@@ -689,6 +691,7 @@ static int build_plan(fb_handle* h) {
       fb_launch_pdl(k_actor_out, dim3(fb_ceil_div(2 * ap.batch * ap.A, 256)), dim3(256), 0, s, ap, sc);
       return cudaGetLastError();
     });
+    h->ops[b.phase].back().wait_stage = 1;   // the zeroed accumulators
   }
   b.gemm({lin_fwd(eFtoa.x, pFt.w(E_OA + 0), pFt.v(E_OA + 1), eFtoa.pre, 0)});
   b.ln_fwd({embed_ln(eFtoa, pFt.sub(E_OA))});
@@ -845,7 +848,6 @@ static int build_plan(fb_handle* h) {
   b.set_phase(FB_PHASE_FB_ADAM);
   {
     const float b1 = c.beta1, b2 = c.beta2, eps = c.adam_eps;
-    b.push([sc, b1, b2](cudaStream_t s) { fb_launch_pdl(k_tick, dim3(1), dim3(32), 0, s, sc, 0, b1, b2); return cudaGetLastError(); });
     float4 *p = (float4*)bf.d_param_fb, *g = (float4*)bf.d_grad_fb, *m = (float4*)bf.d_m_fb, *v = (float4*)bf.d_v_fb, *t = (float4*)bf.d_target_fb;
     const size_t n4 = h->seg_fb.size / 4, split4 = h->bwd_offset / 4;
     b.push([=](cudaStream_t s) {
@@ -856,7 +858,11 @@ static int build_plan(fb_handle* h) {
 
   // =========================== FB_PHASE_ACTOR_FWD ===============================================
   b.set_phase(FB_PHASE_ACTOR_FWD);
-  b.memset0(acc + ACC_Q, 2 * sizeof(double));
+  {   // Q accumulator of update_actor: zeroed on the staging lane (consumer: k_actor_q)
+    TransposeDesc zd; memset(&zd, 0, sizeof(zd));
+    zd.out = reinterpret_cast<float*>(acc + ACC_Q); zd.rows = 1; zd.cols = 4; zd.ld_out = 4; zd.transpose = 2;
+    b.add_early(zd, b.phase);
+  }
   b.gemm({lin_fwd(eF2oa.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eF2oa.pre, 0), lin_fwd(eF2oz.x, pF.w(E_OZ + 0), pF.v(E_OZ + 1), eF2oz.pre, 0)});
   b.ln_fwd({embed_ln(eF2oa, pF.sub(E_OA)), embed_ln(eF2oz, pF.sub(E_OZ))});
   b.gemm({lin_fwd(eF2oa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eF2oa.out, GF_RELU), lin_fwd(eF2oz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eF2oz.out, GF_RELU)});
@@ -868,6 +874,7 @@ static int build_plan(fb_handle* h) {
       fb_launch_pdl(k_actor_q, dim3(fb_ceil_div(B, 8)), dim3(256), 0, s, Fa1.p, Fa2.p, Fa1.ld, z.p, z.ld, dFa1.p, dFa2.p, dFa1.ld, B, Z, inv_n, acc);
       return cudaGetLastError();
     });
+    h->ops[b.phase].back().wait_stage = 1;   // the zeroed accumulator
   }
 
   // =========================== FB_PHASE_ACTOR_BWD ===============================================
@@ -903,7 +910,6 @@ static int build_plan(fb_handle* h) {
   b.set_phase(FB_PHASE_ACTOR_ADAM);
   {
     const float b1 = c.beta1, b2 = c.beta2, eps = c.adam_eps;
-    b.push([sc, b1, b2](cudaStream_t s) { fb_launch_pdl(k_tick, dim3(1), dim3(32), 0, s, sc, 1, b1, b2); return cudaGetLastError(); });
     float4 *p = (float4*)bf.d_param_actor, *g = (float4*)bf.d_grad_actor, *m = (float4*)bf.d_m_actor, *v = (float4*)bf.d_v_actor;
     const size_t n4 = h->seg_actor.size / 4;
     b.push([=](cudaStream_t s) {

@@ -14,6 +14,7 @@ struct DevScalars {
   float bc1_fb, bc2s_fb, bc1_actor, bc2s_actor;  // Adam bias corrections: 1-beta1^t, sqrt(1-beta2^t)
   long long step_fb, step_actor;                 // 1-based Adam step counts
   unsigned long long rng_counter;                // bumped once per FB_PHASE_SAMPLE
+  unsigned int adam_ticket[2];                   // CTAs of k_adam that have finished (the last one advances the step count)
 };
 
 struct HostScalars {  // mirrors fb_step_scalars (fb_b200.h)
@@ -274,28 +275,25 @@ __global__ void __launch_bounds__(256) k_rng_draw(RngParams P, const DevScalars*
   }
 }
 
-// random permutation of [0, n): bitonic sort of (key, index) pairs in one CTA (torch.randperm, fb_ddpg.py:467)
-__global__ void __launch_bounds__(1024) k_randperm(const unsigned int* __restrict__ keys, int n, int npow2, int* __restrict__ perm) {
+// random permutation of [0, n) = argsort of n random keys (torch.randperm, fb_ddpg.py:467): every thread ranks one
+// (key, index) pair against all others held in shared memory (no dependent sort network: one pass, any number of CTAs).
+// The thread that owns pair 0 also bumps the RNG counter (the draws of this step are done: k_rng_draw ran before).
+__global__ void __launch_bounds__(256) k_randperm(const unsigned int* __restrict__ keys, int n, int* __restrict__ perm, DevScalars* sc) {
   fb_pdl_trigger();
   fb_pdl_wait();
-  extern __shared__ unsigned long long sp[];
-  for (int i = threadIdx.x; i < npow2; i += blockDim.x)
-    sp[i] = (i < n) ? (((unsigned long long)keys[i] << 32) | (unsigned int)i) : 0xffffffffffffffffull;
+  extern __shared__ unsigned int sk[];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = keys[i];
   __syncthreads();
-  for (int k = 2; k <= npow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = sp[i], b = sp[ixj];
-          const bool up = ((i & k) == 0);
-          if ((a > b) == up) { sp[i] = b; sp[ixj] = a; }
-        }
-      }
-      __syncthreads();
-    }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned int mine = sk[i];
+  int rank = 0;
+  for (int j = 0; j < n; ++j) {
+    const unsigned int k = sk[j];
+    rank += (k < mine || (k == mine && j < i)) ? 1 : 0;
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = (int)(sp[i] & 0xffffffffull);
+  perm[rank] = i;
+  if (i == 0) sc->rng_counter += 1ull;
 }
 
 // ---- LayerNorm + tanh ("ntanh", fb_modules.py:49-50) ------------------------------------------------
@@ -373,9 +371,12 @@ __global__ void __launch_bounds__(256) k_ln_tanh_fwd_v4(const LnDesc* __restrict
     const int q = lane + 32 * i, c = q * 4;
     if (c < D) {
       float o[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      // gamma / beta: 128-bit loads (every parameter tensor starts on a 128-byte boundary and is padded to 32 floats)
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(d.gamma + c)), b4 = __ldg(reinterpret_cast<const float4*>(d.beta + c));
+      const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (c + e < D) o[e] = tanhf((o[e] - mean) * rstd * __ldg(d.gamma + c + e) + __ldg(d.beta + c + e));
+        if (c + e < D) o[e] = tanhf((o[e] - mean) * rstd * gg[e] + bb[e]);
       if (c + 3 < D) {
         y[q] = make_float4(o[0], o[1], o[2], o[3]);
       } else {
@@ -397,7 +398,7 @@ struct LnBwdDesc {
   float* dgamma; float* dbeta;  // accumulated (atomics); both null when the affine grads are not needed
   int rows, D, ld, ld_dy, cta_begin, cta_count;
 };
-#define FB_LN_BWD_ROWS_PER_CTA 16
+#define FB_LN_BWD_ROWS_PER_CTA 8
 
 __global__ void __launch_bounds__(256) k_ln_tanh_bwd(const LnBwdDesc* __restrict__ descs, int nprob) {
   fb_pdl_trigger();
@@ -475,11 +476,11 @@ __global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const LnBwdDesc* __restr
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + 32 * i) * 4;
     gam[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < D) {
-      gam[i].x = __ldg(d.gamma + c);
-      if (c + 1 < D) gam[i].y = __ldg(d.gamma + c + 1);
-      if (c + 2 < D) gam[i].z = __ldg(d.gamma + c + 2);
-      if (c + 3 < D) gam[i].w = __ldg(d.gamma + c + 3);
+    if (c < D) {   // 128-bit load: parameter tensors are 128-byte aligned and padded to 32 floats; columns >= D are masked below
+      gam[i] = __ldg(reinterpret_cast<const float4*>(d.gamma + c));
+      if (c + 1 >= D) gam[i].y = 0.f;
+      if (c + 2 >= D) gam[i].z = 0.f;
+      if (c + 3 >= D) gam[i].w = 0.f;
     }
   }
   float4 adg[NV], adb[NV];
@@ -857,11 +858,19 @@ __global__ void __launch_bounds__(256) k_colsum(const ColsumDesc* __restrict__ d
 // Gradients are cleared after use so the next step's atomically-accumulated dW start from zero.
 __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                               float4* __restrict__ v, float4* __restrict__ target, size_t n4, size_t split4,
-                                              const DevScalars* __restrict__ sc, int which, float beta1, float beta2, float eps) {
+                                              DevScalars* __restrict__ sc, int which, float beta1, float beta2, float eps) {
   fb_pdl_trigger();
   fb_pdl_wait();
-  const float bc1 = which == 0 ? sc->bc1_fb : sc->bc1_actor;
-  const float bc2s = which == 0 ? sc->bc2s_fb : sc->bc2s_actor;
+  // this launch is Adam step t = (steps so far) + 1; every thread derives the bias corrections itself, the CTA that
+  // finishes last publishes t (no separate "tick" launch on the step's critical path)
+  __shared__ float s_bc[2];
+  const long long t = (which == 0 ? sc->step_fb : sc->step_actor) + 1;
+  if (threadIdx.x == 0) {   // fp64 pow once per CTA
+    s_bc[0] = (float)(1.0 - pow((double)beta1, (double)t));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, (double)t));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2s = s_bc[1];
   const float lr_a = which == 0 ? sc->lr_forward : sc->lr_actor;
   const float lr_b = which == 0 ? sc->lr_backward : sc->lr_actor;
   const float tau = sc->tau, gs = sc->grad_scale;
@@ -885,6 +894,15 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
       tt.x = tau * pp.x + (1.f - tau) * tt.x; tt.y = tau * pp.y + (1.f - tau) * tt.y;
       tt.z = tau * pp.z + (1.f - tau) * tt.z; tt.w = tau * pp.w + (1.f - tau) * tt.w;
       target[i] = tt;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&sc->adam_ticket[which], 1u) == gridDim.x - 1) {   // every other CTA has read the old step count long ago
+      if (which == 0) { sc->step_fb = t; sc->bc1_fb = bc1; sc->bc2s_fb = bc2s; }
+      else { sc->step_actor = t; sc->bc1_actor = bc1; sc->bc2s_actor = bc2s; }
+      sc->adam_ticket[which] = 0u;
     }
   }
 }
