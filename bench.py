@@ -47,6 +47,8 @@ def parse() -> argparse.Namespace:
     p.add_argument("--cpu-steps", type=int, default=12, help="timed steps of the cpu_baseline leg (rank 0, N=1)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--collectives", default="graph", choices=["graph", "torch"], help="multi-GPU exchange: NCCL calls captured in the step "
+                   "graph on the library's communicator, or torch.distributed calls between graph segments")
     p.add_argument("--mlp-mode", default="tcgen05", choices=["tcgen05", "simt"], help="wide Linear products: tensor cores (3xTF32) or fp32 CUDA cores")
     return p.parse_args()
 
@@ -209,7 +211,8 @@ def run_ours(a: argparse.Namespace) -> None:
     common = dict(obs_type="states", obs_shape=(a.obs_dim,), action_shape=(a.action_dim,), device=str(dev), num_expl_steps=0,
                   update_encoder=True, goal_space=None, update_every_steps=1, batch_size=a.batch, z_dim=a.z_dim,
                   use_cuda_graph=not a.no_graph)
-    agent = FBDDPGAgent(use_tb=False, use_wandb=False, use_hiplog=False, rng_mode="device", mlp_mode=a.mlp_mode, **common)
+    agent = FBDDPGAgent(use_tb=False, use_wandb=False, use_hiplog=False, rng_mode="device", mlp_mode=a.mlp_mode, collectives=a.collectives,
+                        **common)
     eng = agent.engine
 
     def barrier() -> None:
@@ -330,7 +333,8 @@ def run_ours(a: argparse.Namespace) -> None:
             cpu = cpu_reference_steps_per_sec(a, a.cpu_steps, 2, budget_s=40.0)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")}
         cfg = workload(a)
-        cfg.update({"parallelism": f"dp{world}" if world > 1 else "single GPU", "per_gpu_batch": Bl, "cuda_graph": not a.no_graph,
+        cfg.update({"parallelism": f"dp{world} (batch rows sharded; all-gather of the F/B row blocks + all-reduce of the flat gradients, "
+                                   f"collectives={a.collectives})" if world > 1 else "single GPU", "per_gpu_batch": Bl, "cuda_graph": not a.no_graph,
                     "rng": "device Philox inside the step graph", "mlp_mode": a.mlp_mode,
                     "l2": "inputs exceed L2: each step gathers random rows of a replay far larger than the 126 MB L2; weights and "
                           "activations are re-used step to step exactly as in training"})

@@ -43,7 +43,7 @@ RUN_HOST_BATCH = 1 << 15   # modifier of PHASE_SAMPLE: batch rows supplied by th
 METRIC_KEYS = ("target_M", "M1", "F1", "B", "B_norm", "z_norm", "fb_loss", "fb_diag", "fb_offdiag", "orth_loss",
                "orth_loss_diag", "orth_loss_offdiag", "orth_linf", "orth_l2", "actor_loss", "q", "actor_logprob")
 METRIC_COUNT = 32
-OP_KINDS = ("gemm", "layernorm", "elementwise", "colsum", "adam", "gather", "loss", "memset", "contract", "gemm_tc", "transpose")
+OP_KINDS = ("gemm", "layernorm", "elementwise", "colsum", "adam", "gather", "loss", "memset", "contract", "gemm_tc", "transpose", "collective")
 
 
 class fb_config(C.Structure):
@@ -93,6 +93,8 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "fb_set_indices": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fb_set_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fb_upload_batch": (_i, [_vp, _vp, _i, _vp]),
+    "fb_nccl_unique_id": (_i, [C.c_char_p, _vp]),
+    "fb_nccl_init": (_i, [_vp, C.c_char_p, _vp, _i, _i]),
     "fb_set_z": (_i, [_vp, _vp, _vp]),
     "fb_set_noise": (_i, [_vp, _vp, _vp, _vp]),
     "fb_run": (_i, [_vp, _u32, _i, _vp]),
@@ -112,7 +114,20 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
 }
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-ldl"]
+
+
+def nccl_library_path() -> tp.Optional[bytes]:
+    """The NCCL shared object torch uses (the wheel's nvidia/nccl/lib/libnccl.so.2), for fb_nccl_*; None -> soname lookup."""
+    try:
+        import nvidia.nccl as n
+        for d in n.__path__:
+            p = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                return p.encode()
+    except ImportError:
+        pass
+    return None
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:

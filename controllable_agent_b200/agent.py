@@ -104,6 +104,8 @@ class FBDDPGAgentConfig:
     use_cuda_graph: bool = True
     mlp_mode: str = "tcgen05"   # wide Linear products: "tcgen05" (3xTF32 tensor cores) or "simt" (fp32 CUDA cores)
     contract_mode: str = "tcgen05"  # batch x batch contraction: "tcgen05" or "simt"
+    collectives: str = "graph"   # multi-GPU exchange: "graph" = the library's own NCCL communicator, all-gather / all-reduce
+    #                              captured inside the step graph; "torch" = torch.distributed calls between graph segments
     prefetch_host_batch: bool = False   # host replay only: sample + upload the NEXT update's batch while this update's step runs
     #                                     on the GPU (same numpy draw order as the reference as long as nothing else samples the
     #                                     replay between updates; for a static replay, e.g. train_offline)
@@ -159,7 +161,16 @@ class FBDDPGAgent:
         local, row_offset = shard_layout(cfg.batch_size, self.world, self.rank)
 
         seed = int(torch.initial_seed() % (2 ** 63)) + 7919 * self.rank
-        self.engine = FBStepEngine(EngineConfig(
+        nccl = None
+        if self.world > 1 and cfg.collectives == "graph":
+            import ctypes as C
+            uid = C.create_string_buffer(128)
+            if self.rank == 0:
+                L.check(L.load().fb_nccl_unique_id(L.nccl_library_path(), uid), "fb_nccl_unique_id")
+            box = [uid.raw]
+            torch.distributed.broadcast_object_list(box, src=0, device=device)
+            nccl = (box[0], self.world, self.rank)
+        self.engine = FBStepEngine(EngineConfig(nccl=nccl,
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
@@ -373,7 +384,7 @@ class FBDDPGAgent:
     def _run(self, mask: int) -> None:
         """Enqueue the phases of `mask`; with >1 rank, split at the two exchange points (DESIGN.md "Multi-GPU")."""
         e, g = self.engine, bool(self.cfg.use_cuda_graph)
-        if self.world == 1:
+        if self.world == 1 or e.has_nccl:   # multi-GPU with the library's communicator: the collectives are launches of the plan
             e.run(mask, graph=g)
             self.last_update_launches = e.launch_count(mask)
             return

@@ -8,6 +8,38 @@
 static int phase_index(uint32_t bit) { int i = 0; while ((1u << i) != bit) ++i; return i; }
 
 // ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen: the library torch already loaded, or the path the host passes): no link-time dependency.
+// Minimal declarations of the stable NCCL 2 ABI (nccl.h): ncclUniqueId is 128 opaque bytes passed by value, ncclFloat32 = 7,
+// ncclSum = 0, results are 0 on success.
+// ------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+struct FbNcclId { char internal[128]; };
+struct FbNccl {
+  void* lib = nullptr;
+  int (*GetUniqueId)(FbNcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, FbNcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+};
+static FbNccl g_nccl;
+static int nccl_load(const char* path) {
+  if (g_nccl.lib) return FB_OK;
+  void* lib = nullptr;
+  if (path && *path) lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return FB_E_STATE;
+  g_nccl.GetUniqueId = (int (*)(FbNcclId*))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, FbNcclId, int))dlsym(lib, "ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.AllReduce) return FB_E_STATE;
+  g_nccl.lib = lib;
+  return FB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA tensor maps for the tcgen05 contraction (driver entry point fetched through the runtime: no -lcuda)
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -701,8 +733,17 @@ static int build_plan(fb_handle* h) {
   b.gemm({lin_fwd(h1Ft1, pFt.w(HD_1 + 2), pFt.v(HD_1 + 3), tF1, 0), lin_fwd(h1Ft2, pFt.w(HD_2 + 2), pFt.v(HD_2 + 3), tF2, 0),
           lin_fwd(h1F1, pF.w(HD_1 + 2), pF.v(HD_1 + 3), F1, 0), lin_fwd(h1F2, pF.w(HD_2 + 2), pF.v(HD_2 + 3), F2, 0)});
 
+  // multi-GPU exchange 1: every rank's [F1|F2|tF1|tF2|B|tB|discount] rows -> blk_global, in rank order.  Inside the step (and its
+  // CUDA graph) when the library owns a communicator (fb_nccl_init); otherwise the caller all-gathers between FB_FWD and FB_LOSS.
+  if (h->nccl_comm && n != B) {
+    fb_handle* hh = h;
+    const float* src = bl.p; float* dst = bg.p; const size_t count = (size_t)B * bl.ld;
+    b.push([hh, src, dst, count](cudaStream_t s) {
+      return g_nccl.AllGather(src, dst, count, 7 /* ncclFloat32 */, hh->nccl_comm, s) == 0 ? cudaSuccess : cudaErrorUnknown;
+    }, FB_OPK_COLLECTIVE, 0.0, 4.0 * (double)n * bl.ld);
+  }
+
   // =========================== FB_PHASE_FB_LOSS =================================================
-  // (multi-GPU: the caller all-gathers blk_local -> blk_global between FB_FWD and FB_LOSS)
   b.set_phase(FB_PHASE_FB_LOSS);
   const bool use_tc = c.contract_mode == FB_CONTRACT_TCGEN05 && Z <= 128;
   const float inv_noff = 1.0f / ((float)n * (float)(n - 1)), inv_n = 1.0f / (float)n;
@@ -844,6 +885,15 @@ static int build_plan(fb_handle* h) {
   b.colsum({mk_colsum(dy_oa, pF.gv(E_OA + 1)), mk_colsum(dy_oz, pF.gv(E_OZ + 1))});
   b.gemm({lin_dw(dy_oa, eFoa.x, pF.gw(E_OA + 0)), lin_dw(dy_oz, eFoz.x, pF.gw(E_OZ + 0))});
 
+  // multi-GPU exchange 2: the flat forward_net | backward_net gradient, summed over ranks (gradients only cross NVLink)
+  if (h->nccl_comm && n != B) {
+    fb_handle* hh = h;
+    float* gbuf = bf.d_grad_fb; const size_t count = h->seg_fb.size;
+    b.push([hh, gbuf, count](cudaStream_t s) {
+      return g_nccl.AllReduce(gbuf, gbuf, count, 7, 0 /* ncclSum */, hh->nccl_comm, s) == 0 ? cudaSuccess : cudaErrorUnknown;
+    }, FB_OPK_COLLECTIVE, 0.0, 8.0 * (double)count);
+  }
+
   // =========================== FB_PHASE_FB_ADAM =================================================
   b.set_phase(FB_PHASE_FB_ADAM);
   {
@@ -905,6 +955,14 @@ static int build_plan(fb_handle* h) {
   b.ln_bwd({embed_ln_bwd(eAo, pA.sub(A_O), dy_o, B, true), embed_ln_bwd(eAoz, pA.sub(A_OZ), dy_aoz, B, true)});
   b.colsum({mk_colsum(dy_o, pA.gv(A_O + 1)), mk_colsum(dy_aoz, pA.gv(A_OZ + 1))});
   b.gemm({lin_dw(dy_o, eAo.x.rs(B, B), pA.gw(A_O + 0)), lin_dw(dy_aoz, eAoz.x.rs(B, B), pA.gw(A_OZ + 0))});
+
+  if (h->nccl_comm && n != B) {   // multi-GPU exchange 3: the flat actor gradient
+    fb_handle* hh = h;
+    float* gbuf = bf.d_grad_actor; const size_t count = h->seg_actor.size;
+    b.push([hh, gbuf, count](cudaStream_t s) {
+      return g_nccl.AllReduce(gbuf, gbuf, count, 7, 0, hh->nccl_comm, s) == 0 ? cudaSuccess : cudaErrorUnknown;
+    }, FB_OPK_COLLECTIVE, 0.0, 8.0 * (double)count);
+  }
 
   // =========================== FB_PHASE_ACTOR_ADAM ==============================================
   b.set_phase(FB_PHASE_ACTOR_ADAM);
@@ -1124,6 +1182,7 @@ void fb_destroy(fb_handle* h) {
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_stage_fork) cudaEventDestroy(h->ev_stage_fork);
   for (auto& e : h->ev_stage) if (e) cudaEventDestroy(e);
+  if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   delete h;
 }
 
@@ -1238,6 +1297,27 @@ int fb_set_batch(fb_handle* h, const float* d_obs, const float* d_action, const 
   k_pack_batch<<<h->cfg.batch, 64, 0, (cudaStream_t)stream>>>(h->bl, h->cfg.batch, d_obs, d_action, d_discount, d_next_obs, d_goal,
                                                              d_next_goal, h->packed.p);
   CK(cudaGetLastError());
+  return FB_OK;
+}
+
+int fb_nccl_unique_id(const char* libnccl_path, void* id128) {
+  if (!id128) return FB_E_ARG;
+  int rc = nccl_load(libnccl_path);
+  if (rc != FB_OK) return rc;
+  return g_nccl.GetUniqueId(reinterpret_cast<FbNcclId*>(id128)) == 0 ? FB_OK : FB_E_STATE;
+}
+
+int fb_nccl_init(fb_handle* h, const char* libnccl_path, const void* id128, int world, int rank) {
+  if (!h || !id128 || world < 2 || rank < 0 || rank >= world) return FB_E_ARG;
+  if (h->bound || h->nccl_comm) return FB_E_STATE;   // before fb_bind: the plan places the collectives
+  if (h->cfg.global_batch != h->cfg.batch * world || h->cfg.row_offset != rank * h->cfg.batch) return FB_E_ARG;
+  int rc = nccl_load(libnccl_path);
+  if (rc != FB_OK) return rc;
+  FbNcclId id;
+  memcpy(&id, id128, sizeof(id));
+  void* comm = nullptr;
+  if (g_nccl.CommInitRank(&comm, world, id, rank) != 0 || !comm) return FB_E_STATE;
+  h->nccl_comm = comm; h->nccl_world = world; h->nccl_rank = rank;
   return FB_OK;
 }
 

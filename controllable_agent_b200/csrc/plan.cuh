@@ -106,6 +106,9 @@ struct fb_handle {
   fb_replay_view replay;
   bool replay_bound = false;
   bool have_perm = false, have_mix_mask = false;
+  // data-parallel exchange inside the step (fb_nccl_init before fb_bind): NCCL communicator of this rank, loaded with dlopen
+  void* nccl_comm = nullptr;
+  int nccl_world = 1, nccl_rank = 0;
 };
 
 // ------------------------------------------------------------------------------------------------

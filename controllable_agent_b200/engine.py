@@ -39,6 +39,7 @@ class EngineConfig:
     seed: int = 0
     global_batch: tp.Optional[int] = None   # multi-GPU: rows of all ranks; None = batch
     row_offset: int = 0                     # multi-GPU: global index of local row 0
+    nccl: tp.Optional[tp.Tuple[bytes, int, int]] = None   # (128-byte unique id, world, rank): collectives inside the step graph
 
 
 def _ptr(t: tp.Optional[torch.Tensor]) -> tp.Optional[int]:
@@ -64,6 +65,13 @@ class FBStepEngine:
         h = C.c_void_p()
         L.check(self.lib.fb_create(C.byref(c), C.byref(h)), "fb_create")
         self.h = h
+        self.has_nccl = False
+        if cfg.nccl is not None:   # before fb_bind: the plan places the all-gather / all-reduce launches
+            uid, world, rank = cfg.nccl
+            buf = C.create_string_buffer(uid, 128)
+            with torch.cuda.device(self.device):
+                L.check(self.lib.fb_nccl_init(h, L.nccl_library_path(), buf, world, rank), "fb_nccl_init")
+            self.has_nccl = True
         with torch.cuda.device(self.device):
             n_fb, n_actor = self.lib.fb_flat_size(h, 0), self.lib.fb_flat_size(h, 1)
             z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)  # noqa: E731

@@ -179,6 +179,14 @@ int fb_set_indices(fb_handle* h, const int32_t* d_ep_idx, const int32_t* d_step_
  * multiplied by the replay discount. */
 int fb_set_batch(fb_handle* h, const float* d_obs, const float* d_action, const float* d_discount,
                  const float* d_next_obs, const float* d_goal, const float* d_next_goal, void* stream);
+/* Data-parallel exchange inside the step (the reference has no distributed path).  One process per GPU: rank 0
+ * calls fb_nccl_unique_id (128 bytes) and ships the id to the other ranks; every rank then calls fb_nccl_init BEFORE fb_bind
+ * (cfg.global_batch = world * cfg.batch, cfg.row_offset = rank * cfg.batch).  The plan then contains the all-gather of the
+ * [F|B|targets|discount] row blocks at the end of FB_PHASE_FB_FWD and the all-reduce(sum) of the flat gradients at the end of
+ * FB_PHASE_FB_BWD / FB_PHASE_ACTOR_BWD, captured into the step's CUDA graph.  libnccl_path: the NCCL shared object to dlopen
+ * (NULL: "libnccl.so.2" as already loaded by the process). */
+int fb_nccl_unique_id(const char* libnccl_path, void* id128);
+int fb_nccl_init(fb_handle* h, const char* libnccl_path, const void* id128, int world, int rank);
 /* Host-buffer form of fb_set_batch = EpisodeBatch.to(device) (replay_buffer.py:50-63) as ONE copy: h_rows is [batch, pitch]
  * floats in HOST memory (pinned for an asynchronous copy) laid out by fb_batch_row_layout(obs, action, goal_dim or 0, 0, 0):
  * obs | action | reward, discount (already times the replay discount) | next_obs | goal | next_goal.  The copy is enqueued
@@ -198,7 +206,7 @@ int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream);
 int fb_launch_count(fb_handle* h, uint32_t phase_mask);
 /* kinds of launch reported by fb_profile_ops */
 enum { FB_OPK_GEMM = 0, FB_OPK_LAYERNORM, FB_OPK_ELEMENTWISE, FB_OPK_COLSUM, FB_OPK_ADAM, FB_OPK_GATHER, FB_OPK_LOSS,
-       FB_OPK_MEMSET, FB_OPK_CONTRACT, FB_OPK_GEMM_TC, FB_OPK_TRANSPOSE };
+       FB_OPK_MEMSET, FB_OPK_CONTRACT, FB_OPK_GEMM_TC, FB_OPK_TRANSPOSE, FB_OPK_COLLECTIVE };
 /* run the launches of `phase_mask` eagerly `reps` times with a CUDA event between consecutive launches (on `stream`) and
  * report, per launch: mean duration (ms), kind (FB_OPK_*), algorithmic FLOPs and algorithmic bytes.  Returns the number
  * of launches (<= cap) or a negative error.  Synchronises.  Executes the step for real (parameters move). */
