@@ -1667,6 +1667,14 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
 
 // Timing harness of the tcgen05 grouped GEMM on one synthetic problem replicated `nprob` times (a "group"): `reps` back-to-back
 // launches between two CUDA events.  dbg = TC_DBG_* knobs (0: the product kernel).  Synchronises; allocates its own operands.
+__global__ void k_fill_hash(float* p, size_t n, unsigned int seed) {   // pseudo-random values in [-1, 1) (bench operands)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned int x = (unsigned int)i * 2654435761u + seed;
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    p[i] = (float)(int)x * (1.0f / 2147483648.0f);
+  }
+}
+
 int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int splitk, int dbg, int reps, float* ms_per_launch, void* stream) {
   if (M < 1 || N < 1 || K < 8 || K % 4 || nprob < 1 || nprob > 16 || reps < 1 || !ms_per_launch) return FB_E_ARG;
   if (bn != 32 && bn != 64 && bn != 128) return FB_E_ARG;
@@ -1674,7 +1682,8 @@ int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int splitk, int dbg
   float *A = nullptr, *B = nullptr, *Cm = nullptr;
   TcGemmDesc* dd = nullptr;
   const bool pre_b = dbg & (1 << 19), pre_a = dbg & (1 << 20);   // lo planes: a second (zero) copy behind the raw one
-  dbg &= ~((1 << 19) | (1 << 20));
+  const bool random_fill = dbg & (1 << 21);                       // operands: pseudo-random instead of a constant
+  dbg &= ~((1 << 19) | (1 << 20) | (1 << 21));
   CK(cudaMallocAsync(&A, (size_t)nprob * M * K * 4 * 2, s));
   CK(cudaMallocAsync(&B, (size_t)nprob * N * K * 4 * 2, s));
   CK(cudaMemsetAsync(A, 0, (size_t)nprob * M * K * 4 * 2, s));
@@ -1683,6 +1692,10 @@ int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int splitk, int dbg
   CK(cudaMallocAsync(&dd, sizeof(TcGemmDesc) * nprob, s));
   CK(cudaMemsetAsync(A, 0x3c, (size_t)nprob * M * K * 4, s));
   CK(cudaMemsetAsync(B, 0x3c, (size_t)nprob * N * K * 4, s));
+  if (random_fill) {
+    k_fill_hash<<<1184, 256, 0, s>>>(A, (size_t)nprob * M * K * 2, 1u);
+    k_fill_hash<<<1184, 256, 0, s>>>(B, (size_t)nprob * N * K * 2, 2u);
+  }
   std::vector<TcGemmDesc> v(nprob);
   int work = 0, rc = FB_OK;
   for (int i = 0; i < nprob && rc == FB_OK; ++i) {

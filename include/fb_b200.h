@@ -252,7 +252,7 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
 /* Timing harness of the tcgen05 3xTF32 grouped GEMM (the kernel behind every wide nn.Linear product, fb_modules.py:76 and its
  * autograd): one synthetic [M,K]x[N,K]^T problem replicated nprob times in one launch, tile width bn (32/64/128), `reps` launches
  * between two CUDA events -> *ms_per_launch; splitk > 1 cuts every tile's K into that many work items.  dbg: 0 = the product kernel with both operands split in shared memory; 1<<19 / 1<<20 =
- * B / A operand with a pre-split lo plane (what the plan does for staged operands); 1<<16 no lo-split, 1<<17 one MMA chain,
+ * B / A operand with a pre-split lo plane (what the plan does for staged operands); 1<<21 = pseudo-random operands instead of a constant fill; 1<<16 no lo-split, 1<<17 one MMA chain,
  * 1<<18 no epilogue (profiling knobs, results invalid).  Synchronises; allocates its operands from the stream's pool. */
 int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int splitk, int dbg, int reps, float* ms_per_launch, void* stream);
 /* FMA-chain microbenchmark: returns measured fp32 TFLOP/s of the CUDA cores (synchronises) */

@@ -69,6 +69,30 @@ def test_sgemm_tcgen05_3xtf32_against_float64(M, N, K, bk, relu):
     assert float(dC[:, N:].abs().max()) == 0.0 if ldc > N else True
 
 
+@pytest.mark.parametrize("M,N,K,bk,splitk", [(1024, 50, 1024, 1, 4), (2048, 6, 1024, 0, 8), (50, 1024, 1024, 1, 3), (257, 129, 1028, 1, 5),
+                                              (128, 128, 64, 1, 2), (1024, 512, 2048, 0, 2)])
+def test_sgemm_tcgen05_split_k(M, N, K, bk, splitk):
+    """split-K of the tensor-core GEMM: every k-range adds its partial tile into a zeroed C (the bias rides on the first)."""
+    L = _L()
+    lib = L.load()
+    g = torch.Generator().manual_seed(M + N + K + splitk)
+    A = torch.randn((M, K), generator=g)
+    Bm = torch.randn((N, K) if bk else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = A.double() @ (Bm.double().T if bk else Bm.double()) + bias.double()
+    dA, dB, dbias = A.cuda(), Bm.cuda(), bias.cuda()
+    ldc = (N + 3) // 4 * 4
+    dC = torch.zeros(M, ldc, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    L.check(lib.fb_sgemm(dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), dbias.data_ptr(), M, N, K, A.shape[1], Bm.shape[1], ldc,
+                         1, bk, 0, splitk, 3, s))
+    torch.cuda.synchronize()
+    assert rel(dC[:, :N], ref) < 1e-5
+    assert float(dC[:, N:].abs().max()) == 0.0 if ldc > N else True
+    assert lib.fb_sgemm(dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), dbias.data_ptr(), M, N, K, A.shape[1], Bm.shape[1], ldc,
+                        1, bk, 1, splitk, 3, s) != 0      # a ReLU epilogue cannot be split
+
+
 def _run_update_case(g, d, use_goal, graph, mlp_mode=0):
     L = _L()
     t = {k: torch.from_numpy(np.array(v)) for k, v in subtree(g, "in").items()}

@@ -42,6 +42,22 @@ def splitk_sweep() -> None:
         print(f"split-K M={M} N={N} K={K} bn={bn} x{nprob}: " + " | ".join(row) + " us", flush=True)
 
 
+def data_sweep() -> None:
+    """Constant operands vs pseudo-random ones, 20 back-to-back launches (x20) vs one launch between the events (x1)."""
+    lib = L.load()
+    s = torch.cuda.current_stream().cuda_stream
+    ms = C.c_float()
+    RANDOM = 1 << 21
+    for (M, N, K, bn, nprob) in [(1024, 1024, 1024, 128, 4), (2048, 512, 1024, 128, 4), (1024, 1024, 1024, 128, 1), (1024, 1024, 1024, 128, 5)]:
+        row = []
+        for dbg in (PRE_B, PRE_B | RANDOM):
+            for reps in (20, 1):
+                L.check(lib.fb_gemm_tc_bench(M, N, K, bn, nprob, 1, dbg, reps, C.byref(ms), s))
+                row.append(f"{ms.value * 1e3:6.1f}")
+        print(f"data M={M} N={N} K={K} x{nprob}: constant fill x20 {row[0]} x1 {row[1]} | random fill x20 {row[2]} x1 {row[3]} us", flush=True)
+
+
 if __name__ == "__main__":
+    data_sweep()
     splitk_sweep()
     main()
