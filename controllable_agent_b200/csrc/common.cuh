@@ -73,3 +73,8 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
 // prologue of k_gemm_tc (barrier init, TMEM allocation) with the tail of the kernel before it.
 __device__ __forceinline__ void fb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Small descriptor tables travel BY VALUE as kernel parameters (constant bank): a grouped kernel then finds its problem without
+// a chain of dependent global loads (one L2 round trip per probed descriptor, microseconds on the step's critical path).
+template <typename D, int N>
+struct DescTable { int n; int pad[3]; D d[N]; };

@@ -328,6 +328,15 @@ struct Builder {
       }
       const TransposeDesc* td = arena_put(h, pending, d_arena);
       const int nt = (int)pending.size();
+      if (nt <= 8) {
+        DescTable<TransposeDesc, 8> tab; memset(&tab, 0, sizeof(tab));
+        tab.n = nt;
+        for (int i = 0; i < nt; ++i) tab.d[i] = pending[i];
+        push([tab, ctas](cudaStream_t s) {
+          fb_launch_pdl(k_transpose_grouped_tab, dim3(ctas), dim3(256), 0, s, tab);
+          return cudaGetLastError();
+        }, FB_OPK_TRANSPOSE, 0.0, tbytes);
+      } else
       push([td, nt, ctas](cudaStream_t s) {
         fb_launch_pdl(k_transpose_grouped, dim3(ctas), dim3(256), 0, s, td, nt);
         return cudaGetLastError();
@@ -374,11 +383,13 @@ struct Builder {
     for (auto& d : v) { d.row_begin = rows; rows += d.rows; bytes += 8.0 * d.rows * (double)d.D; }
     bool vec = true;
     for (auto& d : v) vec = vec && d.D <= 1024 && d.ld % 4 == 0 && aligned16(d.x) && aligned16(d.y);
-    const LnDesc* dd = arena_put(h, v, d_arena);
-    const int n = (int)v.size();
-    push([dd, n, rows, vec](cudaStream_t s) {
-      if (vec) fb_launch_pdl(k_ln_tanh_fwd_v4, dim3(fb_ceil_div(rows, 8)), dim3(256), 0, s, dd, n, rows);
-      else fb_launch_pdl(k_ln_tanh_fwd, dim3(fb_ceil_div(rows, 8)), dim3(256), 0, s, dd, n, rows);
+    DescTable<LnDesc, 8> tab; memset(&tab, 0, sizeof(tab));
+    if (v.size() > 8) { if (rc == FB_OK) rc = FB_E_UNSUPPORTED; return; }
+    tab.n = (int)v.size();
+    for (size_t i = 0; i < v.size(); ++i) tab.d[i] = v[i];
+    push([tab, rows, vec](cudaStream_t s) {
+      if (vec) fb_launch_pdl(k_ln_tanh_fwd_v4, dim3(fb_ceil_div(rows, 8)), dim3(256), 0, s, tab, rows);
+      else fb_launch_pdl(k_ln_tanh_fwd, dim3(fb_ceil_div(rows, 8)), dim3(256), 0, s, tab, rows);
       return cudaGetLastError();
     }, FB_OPK_LAYERNORM, 0.0, bytes);
   }
@@ -393,11 +404,13 @@ struct Builder {
     bool vec = true;  // every problem narrow enough and 16-byte aligned for the register-resident variant?
     for (auto& d : v)
       vec = vec && d.D <= 1024 && d.ld % 4 == 0 && d.ld_dy % 4 == 0 && aligned16(d.dy) && aligned16(d.y) && aligned16(d.x) && aligned16(d.dx);
-    const LnBwdDesc* dd = arena_put(h, v, d_arena);
-    const int n = (int)v.size();
-    push([dd, n, ctas, vec](cudaStream_t s) {
-      if (vec) fb_launch_pdl(k_ln_tanh_bwd_v4, dim3(ctas), dim3(256), 0, s, dd, n);
-      else fb_launch_pdl(k_ln_tanh_bwd, dim3(ctas), dim3(256), 0, s, dd, n);
+    DescTable<LnBwdDesc, 4> tab; memset(&tab, 0, sizeof(tab));
+    if (v.size() > 4) { if (rc == FB_OK) rc = FB_E_UNSUPPORTED; return; }
+    tab.n = (int)v.size();
+    for (size_t i = 0; i < v.size(); ++i) tab.d[i] = v[i];
+    push([tab, ctas, vec](cudaStream_t s) {
+      if (vec) fb_launch_pdl(k_ln_tanh_bwd_v4, dim3(ctas), dim3(256), 0, s, tab);
+      else fb_launch_pdl(k_ln_tanh_bwd, dim3(ctas), dim3(256), 0, s, tab);
       return cudaGetLastError();
     }, FB_OPK_LAYERNORM, 0.0, bytes);
   }

@@ -451,9 +451,19 @@ struct TransposeDesc { const float* in; float* out; float* out_lo; int rows, col
 
 __device__ __forceinline__ float tc_lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+__device__ __forceinline__ void transpose_grouped_body(const TransposeDesc* __restrict__ descs, int nprob);
 __global__ void __launch_bounds__(256) k_transpose_grouped(const TransposeDesc* __restrict__ descs, int nprob) {
   fb_pdl_trigger();
   fb_pdl_wait();
+  transpose_grouped_body(descs, nprob);
+}
+// the same with the descriptors by value (the late staging launches on the main lane: no dependent descriptor loads)
+__global__ void __launch_bounds__(256) k_transpose_grouped_tab(const __grid_constant__ DescTable<TransposeDesc, 8> T) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  transpose_grouped_body(T.d, T.n);
+}
+__device__ __forceinline__ void transpose_grouped_body(const TransposeDesc* __restrict__ descs, int nprob) {
   __shared__ float tile[32][33];
   int p = 0;
   while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;

@@ -302,9 +302,11 @@ struct LnDesc {
   int rows, D, ld, row_begin;  // row_begin: first global warp index of this problem
 };
 
-__global__ void __launch_bounds__(256) k_ln_tanh_fwd(const LnDesc* __restrict__ descs, int nprob, int total_rows) {
+__global__ void __launch_bounds__(256) k_ln_tanh_fwd(const __grid_constant__ DescTable<LnDesc, 8> T, int total_rows) {
   fb_pdl_trigger();
   fb_pdl_wait();
+  const LnDesc* descs = T.d;
+  const int nprob = T.n;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= total_rows) return;
   int p = 0;
@@ -326,9 +328,11 @@ __global__ void __launch_bounds__(256) k_ln_tanh_fwd(const LnDesc* __restrict__ 
 
 // Vectorised forward for D <= 1024 and 16-byte aligned rows: the row lives in registers (one global read), two-pass
 // mean / variance on the register copy like nn.LayerNorm, float4 stores.
-__global__ void __launch_bounds__(256) k_ln_tanh_fwd_v4(const LnDesc* __restrict__ descs, int nprob, int total_rows) {
+__global__ void __launch_bounds__(256) k_ln_tanh_fwd_v4(const __grid_constant__ DescTable<LnDesc, 8> T, int total_rows) {
   fb_pdl_trigger();
   fb_pdl_wait();
+  const LnDesc* descs = T.d;
+  const int nprob = T.n;
   constexpr int NV = 8;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= total_rows) return;
@@ -400,9 +404,11 @@ struct LnBwdDesc {
 };
 #define FB_LN_BWD_ROWS_PER_CTA 8
 
-__global__ void __launch_bounds__(256) k_ln_tanh_bwd(const LnBwdDesc* __restrict__ descs, int nprob) {
+__global__ void __launch_bounds__(256) k_ln_tanh_bwd(const __grid_constant__ DescTable<LnBwdDesc, 4> T) {
   fb_pdl_trigger();
   fb_pdl_wait();
+  const LnBwdDesc* descs = T.d;
+  const int nprob = T.n;
   __shared__ float s_dg[FB_MAX_LN_DIM];
   __shared__ float s_db[FB_MAX_LN_DIM];
   int p = 0;
@@ -452,9 +458,11 @@ __global__ void __launch_bounds__(256) k_ln_tanh_bwd(const LnBwdDesc* __restrict
 // Vectorised variant for D <= 1024 with 16-byte aligned rows: each lane keeps its 8 float4 columns of the row in registers
 // (one pass over dy / y / x), and its share of dgamma / dbeta in registers across the rows of the CTA (no per-element
 // shared-memory atomics); per CTA one shared-memory combine across the 8 warps, then one global atomic per column.
-__global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const LnBwdDesc* __restrict__ descs, int nprob) {
+__global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const __grid_constant__ DescTable<LnBwdDesc, 4> T) {
   fb_pdl_trigger();
   fb_pdl_wait();
+  const LnBwdDesc* descs = T.d;
+  const int nprob = T.n;
   constexpr int NV = 8;  // float4s per lane: D <= 32 * 4 * 8 = 1024
   __shared__ float s_dg[1024];
   __shared__ float s_db[1024];
