@@ -19,7 +19,7 @@ CONTRACT_TCGEN05, CONTRACT_SIMT = 0, 1
 MLP_TCGEN05, MLP_SIMT = 0, 1
 HEADER = os.path.join(ROOT, "include", "fb_b200.h")
 
-FB_ABI_VERSION = 1
+FB_ABI_VERSION = 2
 FB_OK = 0
 
 NET_FORWARD, NET_BACKWARD, NET_ACTOR = 0, 1, 2
@@ -52,7 +52,7 @@ class fb_config(C.Structure):
                 ("hidden_dim", C.c_int32), ("feature_dim", C.c_int32), ("backward_hidden_dim", C.c_int32),
                 ("use_goal", C.c_int32), ("rng_device", C.c_int32), ("contract_mode", C.c_int32), ("mlp_mode", C.c_int32),
                 ("ortho_coef", C.c_float), ("mix_ratio", C.c_float),
-                ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float), ("future_ratio", C.c_float),
                 ("seed", C.c_uint64)]
 
 
@@ -95,6 +95,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "fb_upload_batch": (_i, [_vp, _vp, _i, _vp]),
     "fb_nccl_unique_id": (_i, [C.c_char_p, _vp]),
     "fb_nccl_init": (_i, [_vp, C.c_char_p, _vp, _i, _i]),
+    "fb_set_future_mask": (_i, [_vp, _vp, _vp]),
     "fb_set_z": (_i, [_vp, _vp, _vp]),
     "fb_set_noise": (_i, [_vp, _vp, _vp, _vp]),
     "fb_run": (_i, [_vp, _u32, _i, _vp]),

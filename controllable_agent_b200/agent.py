@@ -136,8 +136,8 @@ class FBDDPGAgent:
             if getattr(cfg, key) != ok:
                 raise NotImplementedError(f"agent.{key}={getattr(cfg, key)} is a non-default branch of fb_ddpg.py the CUDA step "
                                           f"does not implement (supported: {key}={ok})")
-        if cfg.future_ratio > 0:
-            raise NotImplementedError("agent.future_ratio > 0 (hindsight z, fb_ddpg.py:488-491) is not implemented")
+        if not 0.0 <= cfg.future_ratio <= 1.0:
+            raise ValueError(f"agent.future_ratio must be in [0, 1] (got {cfg.future_ratio})")
         device = torch.device(cfg.device)
         if device.type != "cuda":
             raise RuntimeError(f"controllable_agent_b200.FBDDPGAgent needs device=cuda (got {cfg.device!r}); there is no "
@@ -174,7 +174,7 @@ class FBDDPGAgent:
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
-            mix_ratio=cfg.mix_ratio, seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
+            mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
             mlp_mode=L.MLP_SIMT if cfg.mlp_mode == "simt" else L.MLP_TCGEN05,
             contract_mode=L.CONTRACT_SIMT if cfg.contract_mode == "simt" else L.CONTRACT_TCGEN05), device)
 
@@ -491,6 +491,8 @@ class FBDDPGAgent:
                 e.set_indices(ep_idx, step_idx, future_idx, perm, mix)
             else:
                 e.set_indices(perm=perm, mix_mask=mix)
+            if c.future_ratio > 0:   # hindsight rows (fb_ddpg.py:488-491): drawn after the mix mask, like the reference
+                e.set_future_mask((np.random.uniform(size=B) < c.future_ratio).astype(np.int32))
             e.set_z(z)
             e.set_noise(noise_fb, noise_actor)
         want_metrics = self._metrics_enabled()
@@ -515,8 +517,10 @@ class FBDDPGAgent:
         use_goal = self.cfg.goal_space is not None
         if use_goal:
             assert batch.goal is not None and batch.next_goal is not None
+        fut = self.cfg.future_ratio > 0
         self.engine.upload_batch(batch.obs, batch.action, batch.discount, batch.next_obs, batch.goal if use_goal else None,
-                                 batch.next_goal if use_goal else None)
+                                 batch.next_goal if use_goal else None, batch.future_obs if fut else None,
+                                 batch.future_goal if (fut and use_goal) else None)
 
     def _reduce_metrics(self, m: tp.Dict[str, float]) -> tp.Dict[str, float]:
         """Per-rank metric blocks -> global values: loss-type entries are partial sums over the rank's rows, the

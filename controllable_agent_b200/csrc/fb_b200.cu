@@ -536,11 +536,13 @@ static int build_plan(fb_handle* h) {
   h->d_perm = (int*)ws_alloc(h, B * sizeof(int));
   h->d_identity_perm = (int*)ws_alloc(h, B * sizeof(int));
   h->d_mix_mask = (int*)ws_alloc(h, B * sizeof(int));
+  h->d_future_mask = (int*)ws_alloc(h, B * sizeof(int));
   h->d_perm_keys = (unsigned int*)ws_alloc(h, B * sizeof(int));
 
   // ---- packed batch rows ---------------------------------------------------------------------
   BatchLayout& L = h->bl;
-  make_batch_layout(L, O, A, use_goal ? G : 0, 0, 0);  // the step does not read meta / hindsight fields (future_ratio = 0)
+  const bool with_future = c.future_ratio > 0.f;   // hindsight z: the batch rows also carry future_obs / future_goal
+  make_batch_layout(L, O, A, use_goal ? G : 0, 0, with_future ? 1 : 0);  // the step does not read meta fields
   h->packed = ws_mat(h, B, L.pitch, "packed");
 
   // ---- step inputs ---------------------------------------------------------------------------
@@ -550,7 +552,7 @@ static int build_plan(fb_handle* h) {
   Mat in_noa = ws_mat(h, B, O + A, "in_noa");
   Mat in_oa2 = ws_mat(h, B, O + A, "in_oa2");
   Mat goal_next = ws_mat(h, B, G, "next_goal");
-  Mat mix_in = ws_mat(h, B, G, "mix_input");
+  Mat mix_in = ws_mat(h, with_future ? 2 * B : B, G, "mix_input");   // [backward_input[perm] ; future goal]
   h->z_rand = ws_mat(h, B, Z, "z_rand");
   Mat z = ws_mat(h, B, Z, "z");
   h->noise_fb = ws_mat(h, B, A, "noise_fb");
@@ -606,7 +608,7 @@ static int build_plan(fb_handle* h) {
   Mat Fa = ws_mat(h, B, 2 * ldZ, "Fa");
   Mat Fa1 = Fa.cs(0, Z), Fa2 = Fa.cs(ldZ, Z);
   h->views["F1a"] = Fa1; h->views["F2a"] = Fa2;
-  Mat b_mix_out = ws_mat(h, B, Z, "B_mix");
+  Mat b_mix_out = ws_mat(h, with_future ? 2 * B : B, Z, "B_mix");
   BAct bMix = b_alloc(h, mix_in, b_mix_out, "Bmix");
   BAct bT = b_alloc(h, goal_next, tB, "Bt");
   BAct bO = b_alloc(h, goal_next, Bm, "Bo");
@@ -644,6 +646,7 @@ static int build_plan(fb_handle* h) {
   if (c.rng_device) {
     RngParams rp; memset(&rp, 0, sizeof(rp));
     rp.seed = c.seed; rp.batch = B; rp.Z = Z; rp.A = A; rp.ldZ = h->z_rand.ld; rp.ldA = h->noise_fb.ld; rp.mix_ratio = c.mix_ratio;
+    rp.future_ratio = c.future_ratio; rp.future_mask = with_future ? h->d_future_mask : nullptr;
     rp.n_episodes = h->d_n_episodes; rp.ep_idx = h->d_ep_idx; rp.step_idx = h->d_step_idx; rp.future_idx = h->d_future_idx;
     rp.mix_mask = h->d_mix_mask; rp.perm_keys = h->d_perm_keys; rp.z_rand = h->z_rand.p; rp.noise_fb = h->noise_fb.p;
     rp.noise_actor = h->noise_actor.p;
@@ -666,7 +669,8 @@ static int build_plan(fb_handle* h) {
       if (!hh->replay_bound) return cudaErrorInvalidValue;
       GatherParams gp;
       if (build_gather_params(hh->replay, gp, hh->bl, hh->packed.ld) != FB_OK) return cudaErrorInvalidValue;
-      fb_launch_pdl(k_gather_rows, dim3(fb_ceil_div(hh->cfg.batch, 8)), dim3(256), 0, s, gp, hh->d_ep_idx, hh->d_step_idx, nullptr, hh->cfg.batch,
+      fb_launch_pdl(k_gather_rows, dim3(fb_ceil_div(hh->cfg.batch, 8)), dim3(256), 0, s, gp, hh->d_ep_idx, hh->d_step_idx,
+                    hh->bl.with_future ? hh->d_future_idx : nullptr, hh->cfg.batch,
                                                                  &sc->replay_discount, 0.f, hh->packed.p);
       return cudaGetLastError();
     }, FB_OPK_GATHER, 0.0, 2.0 * 4.0 * (double)B * (double)h->bl.pitch);
@@ -682,11 +686,11 @@ static int build_plan(fb_handle* h) {
     sp.in_oa = in_oa.p; sp.in_noa = in_noa.p; sp.in_oa2 = in_oa2.p; sp.ldOA = in_oa.ld;
     sp.goal_next = goal_next.p; sp.mix_in = mix_in.p; sp.ldG = goal_next.ld;
     sp.blk = bl.p; sp.blk_pitch = bl.ld; sp.disc_col = disc_col;
-    sp.perm = h->d_perm; sp.mix_override = nullptr;
+    sp.perm = h->d_perm; sp.mix_override = nullptr; sp.with_future = with_future ? 1 : 0;
     const float* packed = h->packed.p;
     b.push([sp, packed](cudaStream_t s) { fb_launch_pdl(k_stage_inputs, dim3(sp.batch), dim3(128), 0, s, sp, packed); return cudaGetLastError(); });
   }
-  const bool do_mix = c.mix_ratio > 0.f;
+  const bool do_mix = c.mix_ratio > 0.f || with_future;   // one backward_net forward serves the mixing rows and the hindsight rows
   // The z-mixing forward (a chain of five small launches) runs on the side lane while the main lane already computes the
   // first layers that do not depend on z (actor.obs_net, F.obs_action_net, both backward nets); the phase end joins them.
   b.cur_lane = 1; b.fork_next = true;
@@ -700,7 +704,7 @@ static int build_plan(fb_handle* h) {
   {
     ZFinalParams zp; memset(&zp, 0, sizeof(zp));
     zp.batch = B; zp.Z = Z; zp.O = O; zp.z_rand = h->z_rand.p; zp.ldZ = z.ld; zp.b_mix = b_mix_out.p; zp.ld_bmix = b_mix_out.ld;
-    zp.mix_mask = do_mix ? h->d_mix_mask : nullptr; zp.z = z.p; zp.actor_in_oz = actor_in_oz.p; zp.ldOZ = actor_in_oz.ld;
+    zp.mix_mask = c.mix_ratio > 0.f ? h->d_mix_mask : nullptr; zp.future_mask = with_future ? h->d_future_mask : nullptr; zp.z = z.p; zp.actor_in_oz = actor_in_oz.p; zp.ldOZ = actor_in_oz.ld;
     b.push([zp](cudaStream_t s) { fb_launch_pdl(k_z_final, dim3(fb_ceil_div(zp.batch, 8)), dim3(256), 0, s, zp); return cudaGetLastError(); });
   }
   b.cur_lane = 0;
@@ -1163,6 +1167,7 @@ int fb_create(const fb_config* cfg, fb_handle** out) {
     return FB_E_ARG;
   if (cfg->hidden_dim > FB_MAX_LN_DIM || cfg->backward_hidden_dim > FB_MAX_LN_DIM) return FB_E_UNSUPPORTED;
   if (!cfg->use_goal && cfg->goal_dim != cfg->obs_dim) return FB_E_ARG;
+  if (!(cfg->future_ratio >= 0.f && cfg->future_ratio <= 1.f) || !(cfg->mix_ratio >= 0.f && cfg->mix_ratio <= 1.f)) return FB_E_ARG;
   fb_handle* h = new fb_handle();
   h->cfg = *cfg;
   memset(&h->bufs, 0, sizeof(h->bufs));
@@ -1331,6 +1336,13 @@ int fb_nccl_init(fb_handle* h, const char* libnccl_path, const void* id128, int 
   void* comm = nullptr;
   if (g_nccl.CommInitRank(&comm, world, id, rank) != 0 || !comm) return FB_E_STATE;
   h->nccl_comm = comm; h->nccl_world = world; h->nccl_rank = rank;
+  return FB_OK;
+}
+
+int fb_set_future_mask(fb_handle* h, const int32_t* d_future_mask, void* stream) {
+  if (!h || !h->bound) return FB_E_STATE;
+  if (!d_future_mask || !(h->cfg.future_ratio > 0.f)) return FB_E_ARG;
+  CK(cudaMemcpyAsync(h->d_future_mask, d_future_mask, (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return FB_OK;
 }
 

@@ -160,6 +160,7 @@ struct StageParams {
   float* in_oa; float* in_noa; float* in_oa2; int ldOA;
   float* goal_next; float* mix_in; int ldG;
   float* blk; int blk_pitch, disc_col;
+  int with_future;            // rows [B, 2B) of mix_in = future_goal / future_obs (hindsight input, not permuted)
   const int* perm;            // null: identity (mix_in then holds un-permuted rows)
   const float* mix_override;  // tight [B, G]: explicit backward_input[perm] from fb_set_batch, or null
 };
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(128) k_stage_inputs(StageParams P, const float
     if (P.mix_override) m = P.mix_override[(size_t)r * G + c];
     else m = P.use_goal ? prow[L.off_goal + c] : prow[L.off_obs + c];
     P.mix_in[(size_t)r * P.ldG + c] = m;
+    if (P.with_future) P.mix_in[(size_t)(P.batch + r) * P.ldG + c] = P.use_goal ? row[L.off_future_goal + c] : row[L.off_future_obs + c];
   }
   if (threadIdx.x == 0) P.blk[(size_t)r * P.blk_pitch + P.disc_col] = row[L.off_rd + 1];
 }
@@ -203,7 +205,8 @@ __global__ void __launch_bounds__(128) k_stage_inputs(StageParams P, const float
 struct RngParams {
   unsigned long long seed;
   int batch, rows_per_episode, Z, A, ldZ, ldA;
-  float mix_ratio;
+  float mix_ratio, future_ratio;
+  int* future_mask;       // null: no hindsight
   const int* n_episodes;  // device scalar: len(buffer)
   const int* ep_len;
   int* ep_idx; int* step_idx; int* future_idx; int* mix_mask; unsigned int* perm_keys;
@@ -247,6 +250,7 @@ __global__ void __launch_bounds__(256) k_rng_draw(RngParams P, const DevScalars*
     P.mix_mask[warp] = (u01(r.w) - (1.0f / 16777216.0f) < P.mix_ratio) ? 1 : 0;
     const uint4 q = ph(ctr, (uint32_t)warp, 1u);
     P.perm_keys[warp] = q.x;
+    if (P.future_mask) P.future_mask[warp] = (u01(q.y) - (1.0f / 16777216.0f) < P.future_ratio) ? 1 : 0;
   }
   // z: Z normals, 4 per lane per pass
   float ss = 0.f;
@@ -617,6 +621,7 @@ struct ZFinalParams {
   const float* z_rand; int ldZ;
   const float* b_mix; int ld_bmix;      // already sqrt(Z)-normalised by BackwardMap; the reference renormalises
   const int* mix_mask;                  // null: no mixing
+  const int* future_mask;               // null: no hindsight; else rows [B, 2B) of b_mix hold backward_net(future goal)
   float* z; float* actor_in_oz; int ldOZ;
 };
 
@@ -625,9 +630,11 @@ __global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
   fb_pdl_wait();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= P.batch) return;
-  const bool mix = P.mix_mask && P.mix_mask[r] != 0;
+  const bool fut = P.future_mask && P.future_mask[r] != 0;   // applied after the mixing: it wins (fb_ddpg.py:488-491)
+  const bool mix = !fut && P.mix_mask && P.mix_mask[r] != 0;
   const float sq = sqrtf((float)P.Z);
-  const float* src = mix ? (P.b_mix + (size_t)r * P.ld_bmix) : (P.z_rand + (size_t)r * P.ldZ);
+  const float* src = fut ? (P.b_mix + (size_t)(P.batch + r) * P.ld_bmix)
+                         : (mix ? (P.b_mix + (size_t)r * P.ld_bmix) : (P.z_rand + (size_t)r * P.ldZ));
   float nrm = 1.f;
   if (mix) {
     float s = 0.f;

@@ -98,7 +98,7 @@ struct fb_handle {
   unsigned int* d_linf = nullptr;
   float* d_metrics = nullptr;
   int* d_n_episodes = nullptr;
-  int *d_ep_idx = nullptr, *d_step_idx = nullptr, *d_future_idx = nullptr, *d_perm = nullptr, *d_mix_mask = nullptr;
+  int *d_ep_idx = nullptr, *d_step_idx = nullptr, *d_future_idx = nullptr, *d_perm = nullptr, *d_mix_mask = nullptr, *d_future_mask = nullptr;
   unsigned int* d_perm_keys = nullptr;
   int* d_identity_perm = nullptr;
   Mat packed, z_rand, noise_fb, noise_actor, blk_local, blk_global;

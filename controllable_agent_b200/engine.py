@@ -33,6 +33,7 @@ class EngineConfig:
     mlp_mode: int = L.MLP_TCGEN05             # wide Linear fwd / dX products: tcgen05 3xTF32 (default) or fp32 SIMT
     ortho_coef: float = 1.0
     mix_ratio: float = 0.5
+    future_ratio: float = 0.0   # hindsight z (fb_ddpg.py:488-491)
     beta1: float = 0.9
     beta2: float = 0.999
     adam_eps: float = 1e-8
@@ -61,6 +62,7 @@ class FBStepEngine:
                         goal_dim=cfg.goal_dim, hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim,
                         backward_hidden_dim=cfg.backward_hidden_dim, use_goal=int(cfg.use_goal),
                         rng_device=int(cfg.rng_device), contract_mode=int(cfg.contract_mode), mlp_mode=int(cfg.mlp_mode), ortho_coef=cfg.ortho_coef, mix_ratio=cfg.mix_ratio,
+                        future_ratio=cfg.future_ratio,
                         beta1=cfg.beta1, beta2=cfg.beta2, adam_eps=cfg.adam_eps, seed=cfg.seed)
         h = C.c_void_p()
         L.check(self.lib.fb_create(C.byref(c), C.byref(h)), "fb_create")
@@ -93,7 +95,8 @@ class FBStepEngine:
         self._idx_events: tp.List[tp.Optional[torch.cuda.Event]] = [None] * 16
         # host-batch staging (upload_batch): two pinned [batch, pitch] blocks in the packed row layout of the library
         offs, pitch = (C.c_int32 * 9)(), C.c_int32()
-        L.check(self.lib.fb_batch_row_layout(cfg.obs_dim, cfg.action_dim, cfg.goal_dim if cfg.use_goal else 0, 0, 0, offs, C.byref(pitch)))
+        L.check(self.lib.fb_batch_row_layout(cfg.obs_dim, cfg.action_dim, cfg.goal_dim if cfg.use_goal else 0, 0,
+                                             int(cfg.future_ratio > 0), offs, C.byref(pitch)))
         self._row_offsets, self._row_pitch = list(offs), pitch.value
         self._row_stage: tp.Optional[torch.Tensor] = None
         self._row_events: tp.List[tp.Optional[torch.cuda.Event]] = [None, None]
@@ -215,7 +218,7 @@ class FBStepEngine:
         self._keepalive_batch = ts
 
     def upload_batch(self, obs: tp.Any, action: tp.Any, discount: tp.Any, next_obs: tp.Any, goal: tp.Any = None,
-                     next_goal: tp.Any = None) -> int:
+                     next_goal: tp.Any = None, future_obs: tp.Any = None, future_goal: tp.Any = None) -> int:
         """Host arrays of one sampled batch (EpisodeBatch fields, replay_buffer.py:27-40) -> the step's packed batch
         block with ONE asynchronous host-to-device copy (the reference's EpisodeBatch.to issues one blocking pageable
         copy per field, replay_buffer.py:50-63).  Returns the bytes copied."""
@@ -240,11 +243,22 @@ class FBStepEngine:
         if c.use_goal:
             put(o[4], goal, c.goal_dim)
             put(o[5], next_goal, c.goal_dim)
+        if c.future_ratio > 0:   # hindsight inputs (EpisodeBatch.future_obs / future_goal)
+            if future_obs is None or (c.use_goal and future_goal is None):
+                raise ValueError("future_ratio > 0 needs batches with future_obs / future_goal (a replay buffer with future < 1)")
+            put(o[7], future_obs, c.obs_dim)
+            if c.use_goal:
+                put(o[8], future_goal, c.goal_dim)
         L.check(self.lib.fb_upload_batch(self.h, self._row_stage[slot].data_ptr(), self._row_pitch, self._stream()), "fb_upload_batch")
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self._row_events[slot] = ev
         return 4 * c.batch * self._row_pitch
+
+    def set_future_mask(self, mask: tp.Any) -> None:
+        t = self._dev_i32(mask)
+        L.check(self.lib.fb_set_future_mask(self.h, _ptr(t), self._stream()), "fb_set_future_mask")
+        self._keepalive_future = t
 
     def set_z(self, z: tp.Any) -> None:
         t = self._dev_f32(z, self.cfg.z_dim)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 1
+#define FB_ABI_VERSION 2
 
 enum {
   FB_OK = 0,
@@ -105,6 +105,9 @@ typedef struct fb_config {
                                   FB_MLP_SIMT (every product on fp32 CUDA cores) */
   float ortho_coef, mix_ratio;
   float beta1, beta2, adam_eps; /* torch.optim.Adam defaults 0.9 / 0.999 / 1e-8 */
+  float future_ratio;          /* hindsight z (fb_ddpg.py:488-491): rows drawn with this probability take
+                                  z = backward_net(future_goal or future_obs); 0 disables it (the batch rows then carry no
+                                  future fields) */
   uint64_t seed;               /* Philox seed for rng_device */
 } fb_config;
 
@@ -188,10 +191,13 @@ int fb_set_batch(fb_handle* h, const float* d_obs, const float* d_action, const 
 int fb_nccl_unique_id(const char* libnccl_path, void* id128);
 int fb_nccl_init(fb_handle* h, const char* libnccl_path, const void* id128, int world, int rank);
 /* Host-buffer form of fb_set_batch = EpisodeBatch.to(device) (replay_buffer.py:50-63) as ONE copy: h_rows is [batch, pitch]
- * floats in HOST memory (pinned for an asynchronous copy) laid out by fb_batch_row_layout(obs, action, goal_dim or 0, 0, 0):
- * obs | action | reward, discount (already times the replay discount) | next_obs | goal | next_goal.  The copy is enqueued
+ * floats in HOST memory (pinned for an asynchronous copy) laid out by fb_batch_row_layout(obs, action, goal_dim or 0, 0,
+ * future_ratio > 0): obs | action | reward, discount (already times the replay discount) | next_obs | goal | next_goal
+ * [| future_obs | future_goal].  The copy is enqueued
  * on `stream`; the caller keeps h_rows alive until it has completed. */
 int fb_upload_batch(fb_handle* h, const float* h_rows, int pitch, void* stream);
+/* rng_device == 0, future_ratio > 0: the hindsight row mask of fb_ddpg.py:490 ([batch] int32, non-zero = hindsight z) */
+int fb_set_future_mask(fb_handle* h, const int32_t* d_future_mask, void* stream);
 /* rng_device == 0: the random z of fb_ddpg.py:451 ([batch, z_dim], rows of norm sqrt(z_dim)) */
 int fb_set_z(fb_handle* h, const float* d_z, void* stream);
 /* rng_device == 0: the two N(0,1) draws of utils.py:178 ([batch, action_dim] each): update_fb's

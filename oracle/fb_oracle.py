@@ -398,6 +398,7 @@ class OracleConfig:
     stddev_clip: float = 0.3
     ortho_coef: float = 1.0
     mix_ratio: float = 0.5
+    future_ratio: float = 0.0     # hindsight z (fb_ddpg.py:488-491)
     use_goal: bool = False        # goal_space is not None
     metrics: bool = True          # use_tb or use_wandb or use_hiplog
 
@@ -490,6 +491,11 @@ class OracleAgent:
             with torch.no_grad():
                 mix_z = backward_map(self.backward_net, backward_input[mix_idxs], d.z_dim)
             z[mix_idxs] = l2_project(mix_z, d.z_dim)
+        if cfg.future_ratio > 0:   # hindsight replay (fb_ddpg.py:488-491)
+            future_goal = t["future_goal"] if cfg.use_goal else t["future_obs"]
+            future_idxs = np.where(np.random.uniform(size=cfg.batch_size) < cfg.future_ratio)[0]
+            with torch.no_grad():
+                z[future_idxs] = backward_map(self.backward_net, future_goal[future_idxs], d.z_dim)
         metrics = self.update_fb(obs, action, discount, next_obs, next_goal, z, step)
         metrics.update(self.update_actor(obs, z, step))
         with torch.no_grad():

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import dataclasses
 import os
+import sys
 import typing as tp
 
 import numpy as np
@@ -40,7 +41,8 @@ def make_agent(R: tp.Any, case: tp.Mapping[str, tp.Any], use_tb: bool = True) ->
         obs_type="states", obs_shape=(case["obs_dim"],), action_shape=(case["action_dim"],), device="cpu",
         use_tb=use_tb, use_wandb=False, use_hiplog=False, num_expl_steps=0, update_encoder=False,
         goal_space=case["goal_space"], hidden_dim=case["hidden_dim"], feature_dim=case["feature_dim"],
-        backward_hidden_dim=case["backward_hidden_dim"], z_dim=case["z_dim"], batch_size=case["batch_size"])
+        backward_hidden_dim=case["backward_hidden_dim"], z_dim=case["z_dim"], batch_size=case["batch_size"],
+        future_ratio=case.get("future_ratio", 0.0))
     return R.FBDDPGAgent(**dataclasses.asdict(cfg))
 
 
@@ -254,6 +256,13 @@ def main() -> None:
     R = ref_shim.load()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)   # single-thread reductions: the most reproducible reference numbers
+    # hindsight trajectories (future_ratio > 0, fb_ddpg.py:488-491): added after the first fixtures, generated on their own
+    for name, base in (("future", "small"), ("future_goal", "goal")):
+        case = dict(CASES[base], future_ratio=0.4)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"trajectory_{name}.npz"), **gen_trajectory_case(R, case))
+        print("wrote trajectory_%s" % name)
+    if "--hindsight-only" in sys.argv:
+        return
     for name, case in CASES.items():
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"update_{name}.npz"), **gen_update_case(R, name, case))
         print("wrote update_%s" % name)

@@ -124,10 +124,11 @@ def _agent_for(g, case, **kw):
     hidden, oa = f["obs_action_net.0.weight"].shape
     obs_dim = a["obs_net.0.weight"].shape[1]
     agent = FBDDPGAgent(obs_type="states", obs_shape=(obs_dim,), action_shape=(oa - obs_dim,), device="cuda", num_expl_steps=0,
-                        update_encoder=True, goal_space={"small": None, "goal": "simplified_walker"}[case], use_tb=True, use_wandb=False,
+                        update_encoder=True, goal_space=None if case in ("small", "future") else "simplified_walker", use_tb=True, use_wandb=False,
                         use_hiplog=False, hidden_dim=hidden, feature_dim=f["obs_action_net.3.weight"].shape[0],
                         backward_hidden_dim=b["B.0.weight"].shape[0], z_dim=f["F1.2.weight"].shape[0],
-                        batch_size={"small": 32, "goal": 64}[case], update_every_steps=1, **kw)
+                        batch_size=32 if case in ("small", "future") else 64, update_every_steps=1,
+                        future_ratio=0.4 if case.startswith("future") else 0.0, **kw)
     for net, src in ((agent.actor, a), (agent.forward_net, f), (agent.backward_net, b), (agent.forward_target_net, f),
                      (agent.backward_target_net, b)):
         for (name, p) in net.named_parameters():
@@ -135,7 +136,7 @@ def _agent_for(g, case, **kw):
     return agent
 
 
-@pytest.mark.parametrize("case", ["small", "goal"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal"])
 @pytest.mark.parametrize("foreign_replay", [False, True])
 def test_agent_update_walks_reference_trajectory(case, foreign_replay):
     """agent.update(replay, step) x3 with the reference's RNG streams (rng_mode=reference, torch draws on the CPU generator
@@ -244,6 +245,39 @@ def test_agent_device_rng_step_statistics_and_api():
     assert fresh.engine.get_adam_steps() == (5, 5)
 
 
+def test_hindsight_rows_with_device_rng():
+    """future_ratio > 0 with rng_mode=device: the hindsight mask is drawn by the Philox kernel, masked rows take
+    z = backward_net(future_obs) (rows [B, 2B) of the batched backward_net forward), the others the mixed / random z."""
+    from controllable_agent_b200 import FBDDPGAgent, ReplayBuffer
+    torch.manual_seed(2)
+    B, O_, A_, Z = 256, 24, 6, 50
+    agent = FBDDPGAgent(obs_type="states", obs_shape=(O_,), action_shape=(A_,), device="cuda", num_expl_steps=0, update_encoder=True,
+                        goal_space=None, use_tb=True, use_wandb=False, use_hiplog=False, batch_size=B, update_every_steps=1,
+                        hidden_dim=256, feature_dim=128, backward_hidden_dim=134, future_ratio=0.3, mix_ratio=0.5)
+    rs = np.random.RandomState(0)
+    buf = ReplayBuffer(8, 0.98, 0.9)
+    for _ in range(8):
+        n = 40
+        buf.add_episode({"observation": rs.standard_normal((n + 1, O_)), "action": rs.uniform(-1, 1, (n + 1, A_)),
+                         "reward": rs.uniform(0, 1, (n + 1,)), "discount": np.ones(n + 1)})
+    fracs = []
+    for step in range(4):
+        m = agent.update(buf, step)
+        assert all(np.isfinite(v) for v in m.values()), m
+        e = agent.engine
+        z, bm, zr = e.view("z"), e.view("B_mix"), e.view("z_rand")
+        hind = (z == bm[B:]).all(dim=1)                      # hindsight rows: copied verbatim
+        mixed = ~hind & ~(z == zr).all(dim=1)                # mixing rows: renormalised backward_net(obs[perm])
+        fracs.append((float(hind.float().mean()), float(mixed.float().mean())))
+        assert torch.allclose(z.norm(dim=1), torch.full((B,), float(np.sqrt(Z)), device=z.device), rtol=1e-4)
+        # the hindsight input is a stored observation of the same episode at or after the sampled step
+        fin = e.view("mix_input")[B:]
+        rows = buf._rows[:8, :, :O_].reshape(-1, O_)
+        assert float(torch.cdist(fin.double(), rows.double()).min(dim=1).values.max()) == 0.0
+    h, mx = np.mean([f[0] for f in fracs]), np.mean([f[1] for f in fracs])
+    assert 0.2 < h < 0.4 and 0.25 < mx < 0.45, fracs    # 0.3 and 0.5 * 0.7
+
+
 def test_agent_host_replay_with_device_rng():
     """A host-memory replay (the reference's ReplayBuffer contract: sample() -> numpy EpisodeBatch) feeding the device step
     with rng_mode=device: the batch crosses as one packed upload (fb_upload_batch), FB_PHASE_SAMPLE draws z / noise / perm /
@@ -334,9 +368,11 @@ def test_unsupported_branches_raise():
     from controllable_agent_b200 import FBDDPGAgent
     base = dict(obs_type="states", obs_shape=(24,), action_shape=(6,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,
                 use_tb=False, use_wandb=False, use_hiplog=False)
-    for kw in (dict(boltzmann=True), dict(q_loss=True), dict(add_trunk=True), dict(preprocess=False), dict(future_ratio=0.1),
+    for kw in (dict(boltzmann=True), dict(q_loss=True), dict(add_trunk=True), dict(preprocess=False),
                dict(obs_type="pixels"), dict(rand_weight=True), dict(debug=True)):
         with pytest.raises(NotImplementedError):
             FBDDPGAgent(**{**base, **kw})
     with pytest.raises(RuntimeError):
         FBDDPGAgent(**{**base, "device": "cpu"})
+    with pytest.raises(ValueError):
+        FBDDPGAgent(**{**base, "future_ratio": 1.5})

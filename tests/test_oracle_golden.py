@@ -123,10 +123,10 @@ def test_replay_sample_bit_exact(case):
         assert set(batch["meta"].keys()) == {k[5:] for k in ref if k.startswith("meta/")}
 
 
-@pytest.mark.parametrize("case", ["small", "goal"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal"])
 def test_full_update_trajectory(case):
     """agent.update(replay, step) x3 with all RNG streams live: the oracle agent walks the
-    reference's trajectory from the same parameters and seeds."""
+    reference's trajectory from the same parameters and seeds ("future*": hindsight z, future_ratio = 0.4)."""
     torch.set_num_threads(1)
     g = load_golden(f"trajectory_{case}")
     a = subtree(g, "param0/actor")
@@ -137,7 +137,8 @@ def test_full_update_trajectory(case):
     d = O.Dims(obs_dim=obs_dim, action_dim=oa - obs_dim, z_dim=f["F1.2.weight"].shape[0], goal_dim=b["B.0.weight"].shape[1],
                hidden_dim=hidden, feature_dim=f["obs_action_net.3.weight"].shape[0], backward_hidden_dim=b["B.0.weight"].shape[0])
     use_goal = "ep0/goal" in g
-    agent = O.OracleAgent(O.OracleConfig(dims=d, batch_size={"small": 32, "goal": 64}[case], use_goal=use_goal))
+    agent = O.OracleAgent(O.OracleConfig(dims=d, batch_size=64 if use_goal else 32, use_goal=use_goal,
+                                         future_ratio=0.4 if case.startswith("future") else 0.0))
     agent.load_params(actor=a, forward_net=f, backward_net=b, forward_target_net=f, backward_target_net=b)
     buf = O.OracleReplay(4, 0.98, 0.99)
     for i in range(4):
