@@ -163,13 +163,18 @@ class FBDDPGAgent:
         seed = int(torch.initial_seed() % (2 ** 63)) + 7919 * self.rank
         nccl = None
         if self.world > 1 and cfg.collectives == "graph":
+            # the library's own NCCL communicator: rank 0 creates the 128-byte id, torch.distributed (plumbing) ships it
             import ctypes as C
             uid = C.create_string_buffer(128)
+            ok = 1
             if self.rank == 0:
-                L.check(L.load().fb_nccl_unique_id(L.nccl_library_path(), uid), "fb_nccl_unique_id")
-            box = [uid.raw]
+                ok = int(L.load().fb_nccl_unique_id(L.nccl_library_path(), uid) == L.FB_OK)
+            box = [uid.raw, ok]
             torch.distributed.broadcast_object_list(box, src=0, device=device)
-            nccl = (box[0], self.world, self.rank)
+            if box[1]:
+                nccl = (box[0], self.world, self.rank)
+            else:   # NCCL could not be loaded by the library: torch.distributed collectives between graph segments
+                logger.warning("libfb_b200 could not load NCCL; falling back to collectives='torch'")
         self.engine = FBStepEngine(EngineConfig(nccl=nccl,
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
