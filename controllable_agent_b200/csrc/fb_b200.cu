@@ -119,6 +119,16 @@ struct Builder {
   int rc = FB_OK;  // first error met while building (tensor-map encoding)
 
   // can this problem run on the tensor cores (gemm_tc.cuh)?  Operands TMA cannot address directly are staged (see stage_operand)
+  // Lazily-ReLU'd activations: a GF_RELU | GF_RELU_LAZY_OK product that the cost model wants to split along K stores its
+  // PRE-activation (atomic partial sums cannot be clamped); every consumer applies the ReLU itself: a tensor-core A operand in
+  // the builder warps (TC_A_RELU), a staged copy in the staging launch (TransposeDesc::relu), backward masks only test the
+  // sign.  Whole-plan registry (a buffer produced in FB_FWD is consumed in FB_BWD).
+  struct LazyRange { const float* p; size_t n; };
+  std::vector<LazyRange> lazy;
+  bool is_lazy(const float* p) const {
+    for (auto& r : lazy) if (p >= r.p && p < r.p + r.n) return true;
+    return false;
+  }
   bool force_simt = false;   // inference plans: a handful of rows, the fp32 CUDA-core kernel
   bool tc_ok(const GemmDesc& g) const {
     if (force_simt) return false;
@@ -193,6 +203,7 @@ struct Builder {
     }
     TransposeDesc t; memset(&t, 0, sizeof(t));
     t.in = p; t.ld_in = ld; t.ld_out = lds; t.transpose = kmajor ? 0 : 1;
+    t.relu = is_lazy(p) ? 1 : 0;
     if (kmajor) { t.rows = rows; t.cols = K; } else { t.rows = K; t.cols = rows; }   // mn-major storage is [K][rows]
     std::vector<TransposeDesc>& list = early ? h->early_stage[phase] : pending;
     if (early) *used_early = true;
@@ -230,6 +241,12 @@ struct Builder {
     {
       auto natural_bn = [](int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); };
       auto nkb_of = [](const GemmDesc& s) { return fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK); };
+      // linear epilogues may be split along K (atomic partial sums); a ReLU epilogue only if its consumers take the pre-activation
+      auto can_split = [](const GemmDesc& s, int nkb) {
+        if (nkb < 8) return false;
+        if (!(s.flags & GF_RELU)) return true;
+        return (s.flags & GF_RELU_LAZY_OK) != 0 && !getenv("FB_NO_LAZY_RELU");
+      };
       double best = 1e30;
       for (int bn : {128, 64, 32}) {
         for (int sk : {1, 2, 3, 4, 6, 8}) {
@@ -238,7 +255,7 @@ struct Builder {
           std::vector<Item> items;
           for (const GemmDesc& s : gs) {
             const int bnp = std::min(bn, natural_bn(s.N)), nkb = nkb_of(s);
-            const bool splittable = !(s.flags & GF_RELU) && nkb >= 8;
+            const bool splittable = can_split(s, nkb);
             int len = nkb, parts = 1;
             if (splittable && sk > 1) { len = fb_ceil_div(nkb, std::min(sk, nkb / 4)); parts = fb_ceil_div(nkb, len); }
             const double f = bnp == 128 ? 1.0 : (bnp == 64 ? 0.8 : 0.72);
@@ -267,7 +284,7 @@ struct Builder {
       std::stable_sort(gs.begin(), gs.end(), [&](const GemmDesc& x, const GemmDesc& y) {
         auto len = [&](const GemmDesc& s) {
           const int nkb = nkb_of(s);
-          const bool splittable = !(s.flags & GF_RELU) && nkb >= 8;
+          const bool splittable = can_split(s, nkb);
           return (splittable && sk_group > 1) ? fb_ceil_div(nkb, std::min(sk_group, nkb / 4)) : nkb;
         };
         return len(x) > len(y);
@@ -283,10 +300,15 @@ struct Builder {
       if (d.bn > ring_bn) ring_bn = d.bn;
       d.tiles_m = fb_ceil_div(s.M, TC_BM); d.tiles_n = fb_ceil_div(s.N, d.bn);
       d.splitk = 1; d.kb_per_split = fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK);
-      if (!(s.flags & GF_RELU) && sk_group > 1 && d.kb_per_split >= 8) {   // a k-range may straddle the two products
+      const bool may_split = !(s.flags & GF_RELU) || ((s.flags & GF_RELU_LAZY_OK) && !getenv("FB_NO_LAZY_RELU"));
+      if (may_split && sk_group > 1 && d.kb_per_split >= 8) {   // a k-range may straddle the two products
         const int nkb = d.kb_per_split;
         d.kb_per_split = fb_ceil_div(nkb, std::min(sk_group, nkb / 4));
         d.splitk = fb_ceil_div(nkb, d.kb_per_split);   // every k-range non-empty
+      }
+      if (d.splitk > 1 && (d.flags & GF_RELU)) {   // lazy ReLU: C receives the pre-activation, its consumers clamp it
+        d.flags &= ~GF_RELU;
+        lazy.push_back(LazyRange{s.C, (size_t)(s.M - 1) * s.ldc + s.N});
       }
       if (d.splitk > 1 && !in_grad(s.C)) {   // gradients are cleared by k_adam; any other split-K output is zeroed at phase start
         TransposeDesc z; memset(&z, 0, sizeof(z));
@@ -304,6 +326,9 @@ struct Builder {
       const bool a_pre = Alo && (!s.K2 || A2lo), b_pre = Blo && (!s.K2 || B2lo);
       if (a_pre) d.flags |= TC_A_PRE;
       if (b_pre) d.flags |= TC_B_PRE;
+      // lazily-ReLU'd operands used WITHOUT a staged copy: A is clamped by the builder warps; anything else is a plan error
+      if (A1 == s.A && is_lazy(s.A)) { if (a_pre || s.K2) { if (rc == FB_OK) rc = FB_E_STATE; } else d.flags |= TC_A_RELU; }
+      if ((B1 == s.B && is_lazy(s.B)) || (s.K2 && (is_lazy(s.A2) || is_lazy(s.B2)))) { if (rc == FB_OK) rc = FB_E_STATE; }
       if (h->ws_base && rc == FB_OK) {
         rc = encode_tiled_map(&d.mapA, A1, s.M, s.K, lda, TC_BM);
         if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, B1, s.N, s.K, ldb, d.bn);
@@ -371,6 +396,8 @@ struct Builder {
     if (!tc.empty()) gemm_tc(tc);
     if (simt.empty()) return;
     g = std::move(simt);
+    for (auto& d : g)   // the fp32 SIMT kernel has no lazy-ReLU operand path
+      if (is_lazy(d.A) || is_lazy(d.B) || (d.K2 && (is_lazy(d.A2) || is_lazy(d.B2)))) { if (rc == FB_OK) rc = FB_E_STATE; }
     GroupLaunch gl = finalize_group(h, std::move(g), d_arena);
     push([gl](cudaStream_t s) {
       fb_launch_pdl(k_gemm_grouped, dim3(gl.ctas), dim3(GEMM_THREADS), GEMM_SMEM_BYTES, s, gl.d_descs, gl.nprob);
@@ -697,7 +724,7 @@ static int build_plan(fb_handle* h) {
   if (do_mix) {  // mix_z = backward_net(backward_input[perm]) on every row; rows outside the mask are ignored
     b.gemm({lin_fwd(bMix.x, pB.w(0), pB.v(1), bMix.pre, 0)});
     b.ln_fwd({b_ln(bMix, pB)});
-    b.gemm({lin_fwd(bMix.y, pB.w(4), pB.v(5), bMix.h2, GF_RELU)});
+    b.gemm({lin_fwd(bMix.y, pB.w(4), pB.v(5), bMix.h2, GF_RELU | GF_RELU_LAZY_OK)});
     b.gemm({lin_fwd(bMix.h2, pB.w(6), pB.v(7), bMix.raw, 0)});
     b.l2_fwd({b_l2(bMix, Z)});
   }
@@ -722,11 +749,11 @@ static int build_plan(fb_handle* h) {
   b.gemm({lin_fwd(eAoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eAoz.pre, 0), lin_fwd(eFoz.x, pF.w(E_OZ + 0), pF.v(E_OZ + 1), eFoz.pre, 0),
           lin_fwd(eFtoz.x, pFt.w(E_OZ + 0), pFt.v(E_OZ + 1), eFtoz.pre, 0)});
   b.ln_fwd({embed_ln(eAoz, pA.sub(A_OZ)), embed_ln(eFoz, pF.sub(E_OZ)), embed_ln(eFtoz, pFt.sub(E_OZ))});
-  b.gemm({lin_fwd(eAo.y, pA.w(A_O + 4), pA.v(A_O + 5), eAo.out, GF_RELU), lin_fwd(eAoz.y, pA.w(A_OZ + 4), pA.v(A_OZ + 5), eAoz.out, GF_RELU),
-          lin_fwd(eFoa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eFoa.out, GF_RELU), lin_fwd(eFoz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eFoz.out, GF_RELU),
-          lin_fwd(eFtoz.y, pFt.w(E_OZ + 4), pFt.v(E_OZ + 5), eFtoz.out, GF_RELU),
-          lin_fwd(bO.y, pB.w(4), pB.v(5), bO.h2, GF_RELU), lin_fwd(bT.y, pBt.w(4), pBt.v(5), bT.h2, GF_RELU)});
-  b.gemm({lin_fwd(hA, pA.w(A_POL + 0), pA.v(A_POL + 1), h1A, GF_RELU),
+  b.gemm({lin_fwd(eAo.y, pA.w(A_O + 4), pA.v(A_O + 5), eAo.out, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(eAoz.y, pA.w(A_OZ + 4), pA.v(A_OZ + 5), eAoz.out, GF_RELU | GF_RELU_LAZY_OK),
+          lin_fwd(eFoa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eFoa.out, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(eFoz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eFoz.out, GF_RELU | GF_RELU_LAZY_OK),
+          lin_fwd(eFtoz.y, pFt.w(E_OZ + 4), pFt.v(E_OZ + 5), eFtoz.out, GF_RELU | GF_RELU_LAZY_OK),
+          lin_fwd(bO.y, pB.w(4), pB.v(5), bO.h2, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(bT.y, pBt.w(4), pBt.v(5), bT.h2, GF_RELU | GF_RELU_LAZY_OK)});
+  b.gemm({lin_fwd(hA, pA.w(A_POL + 0), pA.v(A_POL + 1), h1A, GF_RELU | GF_RELU_LAZY_OK),
           lin_fwd(bO.h2, pB.w(6), pB.v(7), bO.raw, 0), lin_fwd(bT.h2, pBt.w(6), pBt.v(7), bT.raw, 0)});
   b.gemm({lin_fwd(h1A, pA.w(A_POL + 2), pA.v(A_POL + 3), preA, 0)});
   b.l2_fwd({b_l2(bO, Z), b_l2(bT, Z)});
@@ -744,9 +771,9 @@ static int build_plan(fb_handle* h) {
   }
   b.gemm({lin_fwd(eFtoa.x, pFt.w(E_OA + 0), pFt.v(E_OA + 1), eFtoa.pre, 0)});
   b.ln_fwd({embed_ln(eFtoa, pFt.sub(E_OA))});
-  b.gemm({lin_fwd(eFtoa.y, pFt.w(E_OA + 4), pFt.v(E_OA + 5), eFtoa.out, GF_RELU)});
-  b.gemm({lin_fwd(hFt, pFt.w(HD_1 + 0), pFt.v(HD_1 + 1), h1Ft1, GF_RELU), lin_fwd(hFt, pFt.w(HD_2 + 0), pFt.v(HD_2 + 1), h1Ft2, GF_RELU),
-          lin_fwd(hF, pF.w(HD_1 + 0), pF.v(HD_1 + 1), h1F1, GF_RELU), lin_fwd(hF, pF.w(HD_2 + 0), pF.v(HD_2 + 1), h1F2, GF_RELU)});
+  b.gemm({lin_fwd(eFtoa.y, pFt.w(E_OA + 4), pFt.v(E_OA + 5), eFtoa.out, GF_RELU | GF_RELU_LAZY_OK)});
+  b.gemm({lin_fwd(hFt, pFt.w(HD_1 + 0), pFt.v(HD_1 + 1), h1Ft1, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(hFt, pFt.w(HD_2 + 0), pFt.v(HD_2 + 1), h1Ft2, GF_RELU | GF_RELU_LAZY_OK),
+          lin_fwd(hF, pF.w(HD_1 + 0), pF.v(HD_1 + 1), h1F1, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(hF, pF.w(HD_2 + 0), pF.v(HD_2 + 1), h1F2, GF_RELU | GF_RELU_LAZY_OK)});
   b.gemm({lin_fwd(h1Ft1, pFt.w(HD_1 + 2), pFt.v(HD_1 + 3), tF1, 0), lin_fwd(h1Ft2, pFt.w(HD_2 + 2), pFt.v(HD_2 + 3), tF2, 0),
           lin_fwd(h1F1, pF.w(HD_1 + 2), pF.v(HD_1 + 3), F1, 0), lin_fwd(h1F2, pF.w(HD_2 + 2), pF.v(HD_2 + 3), F2, 0)});
 
@@ -932,8 +959,8 @@ static int build_plan(fb_handle* h) {
   }
   b.gemm({lin_fwd(eF2oa.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eF2oa.pre, 0), lin_fwd(eF2oz.x, pF.w(E_OZ + 0), pF.v(E_OZ + 1), eF2oz.pre, 0)});
   b.ln_fwd({embed_ln(eF2oa, pF.sub(E_OA)), embed_ln(eF2oz, pF.sub(E_OZ))});
-  b.gemm({lin_fwd(eF2oa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eF2oa.out, GF_RELU), lin_fwd(eF2oz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eF2oz.out, GF_RELU)});
-  b.gemm({lin_fwd(hF2, pF.w(HD_1 + 0), pF.v(HD_1 + 1), h1Fa1, GF_RELU), lin_fwd(hF2, pF.w(HD_2 + 0), pF.v(HD_2 + 1), h1Fa2, GF_RELU)});
+  b.gemm({lin_fwd(eF2oa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eF2oa.out, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(eF2oz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eF2oz.out, GF_RELU | GF_RELU_LAZY_OK)});
+  b.gemm({lin_fwd(hF2, pF.w(HD_1 + 0), pF.v(HD_1 + 1), h1Fa1, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(hF2, pF.w(HD_2 + 0), pF.v(HD_2 + 1), h1Fa2, GF_RELU | GF_RELU_LAZY_OK)});
   b.gemm({lin_fwd(h1Fa1, pF.w(HD_1 + 2), pF.v(HD_1 + 3), Fa1, 0), lin_fwd(h1Fa2, pF.w(HD_2 + 2), pF.v(HD_2 + 3), Fa2, 0)});
   {
     const float inv_n = 1.0f / (float)n;

@@ -23,7 +23,9 @@ enum {
   GF_MASK_RELU = 2,  // C *= (mask > 0)                      (backward through a saved ReLU output)
   GF_MASK_TANH = 4,  // C *= (1 - mask^2)                    (backward through a saved tanh output)
   GF_ATOMIC = 8,     // C += result with fp32 atomics (split-K or several problems sharing one C)
-  GF_SHARED_C = 16   // (host only) several problems of the group accumulate into this C: must stay on the atomic path
+  GF_SHARED_C = 16,  // (host only) several problems of the group accumulate into this C: must stay on the atomic path
+  GF_RELU_LAZY_OK = 32  // (host only) with GF_RELU: every consumer of C can apply the ReLU itself (tensor-core A operand, staged
+                        // copies, sign masks), so the plan may store the pre-activation instead when that lets it split K
 };
 enum { GEMM_CFG_BIG = 0, GEMM_CFG_SMALL = 1, GEMM_CFG_WIDE = 2 };  // 128x128 / 64x64 / 128x64 CTA tiles
 

@@ -44,6 +44,8 @@
 
 #define TC_A_PRE (1 << 8)    // mapAlo / mapA2lo address a pre-split lo plane of A
 #define TC_B_PRE (1 << 9)    // same for B
+#define TC_A_RELU (1 << 10)  // A holds the pre-activation of a lazily-ReLU'd layer (a split-K producer): the builder warps clamp
+                             // the landed raw tile at 0 in shared memory before splitting it
 // profiling knobs (fb_gemm_tc_bench only; results are wrong when set): which part of the pipeline bounds a tile
 #define TC_DBG_NOBUILD (1 << 16)   // lo builders skip the split (arrive as soon as the raw tiles land)
 #define TC_DBG_ONECHAIN (1 << 17)  // the MMA warp issues only the hi.hi chain
@@ -156,6 +158,20 @@ __device__ __forceinline__ void tc_build_lo(const float4* __restrict__ raw, floa
   for (int i = 0; i < CNT; ++i) x[i] = raw[t + i * 128];
 #pragma unroll
   for (int i = 0; i < CNT; ++i) lo[t + i * 128] = tc_lo4(x[i]);
+}
+
+// the same for an A tile that still needs its ReLU: raw <- max(raw, 0) in place, lo from the clamped value
+template <int CNT>
+__device__ __forceinline__ void tc_build_lo_relu(float4* __restrict__ raw, float4* __restrict__ lo, int t) {
+  float4 x[CNT];
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) x[i] = raw[t + i * 128];
+#pragma unroll
+  for (int i = 0; i < CNT; ++i) {
+    x[i].x = fmaxf(x[i].x, 0.f); x[i].y = fmaxf(x[i].y, 0.f); x[i].z = fmaxf(x[i].z, 0.f); x[i].w = fmaxf(x[i].w, 0.f);
+    raw[t + i * 128] = x[i];
+    lo[t + i * 128] = tc_lo4(x[i]);
+  }
 }
 
 // which problem / tile / k-range of the group is work item w (header only: no global loads)
@@ -316,7 +332,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
         tc_mbar_wait(&bar_raw[s], (kbg / (uint32_t)nst) & 1u);
         const float4* raw = reinterpret_cast<const float4*>(smem_gen + (size_t)s * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem_gen + (size_t)s * stage_bytes + half_bytes);
-        if (build_a) tc_build_lo<8>(raw, lo, t);                       // A tile: 128 rows x 128 B = 1024 float4
+        if (build_a) {                                                 // A tile: 128 rows x 128 B = 1024 float4
+          if (flags & TC_A_RELU) tc_build_lo_relu<8>(const_cast<float4*>(raw), lo, t);
+          else tc_build_lo<8>(raw, lo, t);
+        }
         if (build_b) {                                                 // B tile: bn rows x 128 B
           if (bn == 128) tc_build_lo<8>(raw + 1024, lo + 1024, t);
           else if (bn == 64) tc_build_lo<4>(raw + 1024, lo + 1024, t);
@@ -447,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
 // 16-byte aligned base and leading dimension so that TMA can address it; out_lo (optional) receives the lo plane
 // x - trunc_tf32(x) of the same elements (out may then be null: the source itself is TMA-addressable and only its lo plane
 // is wanted).  transpose = 2: zero-fill out (rows x cols).  32 x 32 tiles through shared memory.
-struct TransposeDesc { const float* in; float* out; float* out_lo; int rows, cols, ld_in, ld_out, transpose, cta_begin, ctas_x; };
+struct TransposeDesc { const float* in; float* out; float* out_lo; int rows, cols, ld_in, ld_out, transpose, cta_begin, ctas_x, relu; };   // relu: the source is a lazily-ReLU'd pre-activation
 
 __device__ __forceinline__ float tc_lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
@@ -482,7 +501,8 @@ __device__ __forceinline__ void transpose_grouped_body(const TransposeDesc* __re
     for (int j = ty; j < 32; j += 8) {
       const int r = by * 32 + j, c = bx * 32 + tx;
       if (r < d.rows && c < d.cols) {
-        const float x = d.in[(size_t)r * d.ld_in + c];
+        float x = d.in[(size_t)r * d.ld_in + c];
+        if (d.relu) x = fmaxf(x, 0.f);
         if (d.out) d.out[(size_t)r * d.ld_out + c] = x;
         if (d.out_lo) d.out_lo[(size_t)r * d.ld_out + c] = tc_lo1(x);
       }
@@ -491,7 +511,9 @@ __device__ __forceinline__ void transpose_grouped_body(const TransposeDesc* __re
   }
   for (int j = ty; j < 32; j += 8) {
     const int r = by * 32 + j, c = bx * 32 + tx;
-    tile[j][tx] = (r < d.rows && c < d.cols) ? d.in[(size_t)r * d.ld_in + c] : 0.f;
+    float x = (r < d.rows && c < d.cols) ? d.in[(size_t)r * d.ld_in + c] : 0.f;
+    if (d.relu) x = fmaxf(x, 0.f);
+    tile[j][tx] = x;
   }
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
