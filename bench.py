@@ -301,9 +301,9 @@ def run_ours(a: argparse.Namespace) -> None:
             roofline = {"kernel": "k_gemm_tc (tcgen05 kind::tf32, 3xTF32 split, TMA + TMEM): all wide nn.Linear forward / dX / dW products",
                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the step's 29 k_gemm_tc launches of the
-                        # committed ncu --set full capture (profiles/r1c_ncu_key_metrics.csv); algorithmic operand + result bytes
+                        # committed ncu --set full capture (profiles/r1d_ncu_key_metrics.csv); algorithmic operand + result bytes
                         # of the same launches: bytes_per_launch below
-                        "traffic": 19.32e6, "traffic_unit": "bytes/launch (ncu, profiles/r1c_ncu_key_metrics.csv)",
+                        "traffic": 19.66e6, "traffic_unit": "bytes/launch (ncu, profiles/r1d_ncu_key_metrics.csv)",
                         "algorithmic_bytes_per_launch": gk["bytes"] / gk["launches"],
                         "peak_source": f"{src} = {bf16:.1f} TFLOP/s dense bf16; /2 for tf32, /3 for the three chains of an fp32-grade product "
                                        "(achieved counts each algorithmic fp32 FLOP once)",

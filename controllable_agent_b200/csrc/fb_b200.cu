@@ -1288,6 +1288,7 @@ int fb_bind(fb_handle* h, const fb_buffers* bufs, void* stream) {
   CK(cudaMemsetAsync(h->ws_base, 0, h->ws_bytes, s));
   CK(cudaMemcpyAsync(h->ws_base, h->arena.data(), h->arena.size(), cudaMemcpyHostToDevice, s));
   k_iota<<<fb_ceil_div(h->cfg.batch, 256), 256, 0, s>>>(h->d_perm, h->cfg.batch);
+  k_set_adam_steps<<<1, 32, 0, s>>>(h->d_sc, 0ll, 0ll, h->cfg.beta1, h->cfg.beta2);   // step counts 0, bias corrections of step 1
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
   h->bound = true;
@@ -1564,7 +1565,7 @@ const float* fb_metrics_ptr(const fb_handle* h) { return h && h->bound ? h->d_me
 
 int fb_set_adam_steps(fb_handle* h, int64_t fb_step, int64_t actor_step, void* stream) {
   if (!h || !h->bound) return FB_E_STATE;
-  k_set_adam_steps<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_sc, (long long)fb_step, (long long)actor_step);
+  k_set_adam_steps<<<1, 32, 0, (cudaStream_t)stream>>>(h->d_sc, (long long)fb_step, (long long)actor_step, h->cfg.beta1, h->cfg.beta2);
   CK(cudaGetLastError());
   return FB_OK;
 }

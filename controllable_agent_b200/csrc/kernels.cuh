@@ -11,7 +11,7 @@
 // ---- device-resident per-step scalars -------------------------------------------------------------
 struct DevScalars {
   float stddev, stddev_clip, lr_forward, lr_backward, lr_actor, tau, replay_discount, replay_future, grad_scale;
-  float bc1_fb, bc2s_fb, bc1_actor, bc2s_actor;  // Adam bias corrections: 1-beta1^t, sqrt(1-beta2^t)
+  float bc1_fb, bc2s_fb, bc1_actor, bc2s_actor;  // Adam bias corrections 1-beta1^t, sqrt(1-beta2^t) of the NEXT step t = step + 1
   long long step_fb, step_actor;                 // 1-based Adam step counts
   unsigned long long rng_counter;                // bumped once per FB_PHASE_SAMPLE
   unsigned int adam_ticket[2];                   // CTAs of k_adam that have finished (the last one advances the step count)
@@ -29,8 +29,17 @@ __global__ void k_set_scalars(DevScalars* s, HostScalars h) {
   }
 }
 
-__global__ void k_set_adam_steps(DevScalars* s, long long fb, long long actor) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { s->step_fb = fb; s->step_actor = actor; }
+__device__ __forceinline__ void adam_bias_corrections(float beta1, float beta2, long long t, float* bc1, float* bc2s) {
+  *bc1 = (float)(1.0 - pow((double)beta1, (double)t));
+  *bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)t));
+}
+__global__ void k_set_adam_steps(DevScalars* s, long long fb, long long actor, float beta1, float beta2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    s->step_fb = fb; s->step_actor = actor;
+    adam_bias_corrections(beta1, beta2, fb + 1, &s->bc1_fb, &s->bc2s_fb);
+    adam_bias_corrections(beta1, beta2, actor + 1, &s->bc1_actor, &s->bc2s_actor);
+    s->adam_ticket[0] = 0u; s->adam_ticket[1] = 0u;
+  }
 }
 
 // which: 0 = fb optimizer, 1 = actor optimizer, 2 = rng counter
@@ -285,14 +294,22 @@ __global__ void __launch_bounds__(256) k_rng_draw(RngParams P, const DevScalars*
 __global__ void __launch_bounds__(256) k_randperm(const unsigned int* __restrict__ keys, int n, int* __restrict__ perm, DevScalars* sc) {
   fb_pdl_trigger();
   fb_pdl_wait();
-  extern __shared__ unsigned int sk[];
+  extern __shared__ __align__(16) unsigned int sk[];
   for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = keys[i];
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned int mine = sk[i];
   int rank = 0;
-  for (int j = 0; j < n; ++j) {
+  const int n4 = n & ~3;
+  for (int j = 0; j < n4; j += 4) {   // 128-bit broadcast reads of the key table
+    const uint4 k = *reinterpret_cast<const uint4*>(sk + j);
+    rank += (k.x < mine || (k.x == mine && j < i)) ? 1 : 0;
+    rank += (k.y < mine || (k.y == mine && j + 1 < i)) ? 1 : 0;
+    rank += (k.z < mine || (k.z == mine && j + 2 < i)) ? 1 : 0;
+    rank += (k.w < mine || (k.w == mine && j + 3 < i)) ? 1 : 0;
+  }
+  for (int j = n4; j < n; ++j) {
     const unsigned int k = sk[j];
     rank += (k < mine || (k == mine && j < i)) ? 1 : 0;
   }
@@ -876,16 +893,12 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
                                               DevScalars* __restrict__ sc, int which, float beta1, float beta2, float eps) {
   fb_pdl_trigger();
   fb_pdl_wait();
-  // this launch is Adam step t = (steps so far) + 1; every thread derives the bias corrections itself, the CTA that
-  // finishes last publishes t (no separate "tick" launch on the step's critical path)
-  __shared__ float s_bc[2];
+  // this launch is Adam step t = (steps so far) + 1; its bias corrections were published by the previous step (or by
+  // fb_bind / fb_set_adam_steps); the CTA that finishes last publishes t and the corrections of step t + 1 (no separate
+  // "tick" launch on the step's critical path, no fp64 pow in front of the streaming loop)
   const long long t = (which == 0 ? sc->step_fb : sc->step_actor) + 1;
-  if (threadIdx.x == 0) {   // fp64 pow once per CTA
-    s_bc[0] = (float)(1.0 - pow((double)beta1, (double)t));
-    s_bc[1] = (float)sqrt(1.0 - pow((double)beta2, (double)t));
-  }
-  __syncthreads();
-  const float bc1 = s_bc[0], bc2s = s_bc[1];
+  const float bc1 = which == 0 ? sc->bc1_fb : sc->bc1_actor;
+  const float bc2s = which == 0 ? sc->bc2s_fb : sc->bc2s_actor;
   const float lr_a = which == 0 ? sc->lr_forward : sc->lr_actor;
   const float lr_b = which == 0 ? sc->lr_backward : sc->lr_actor;
   const float tau = sc->tau, gs = sc->grad_scale;
@@ -911,12 +924,14 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
       target[i] = tt;
     }
   }
-  __syncthreads();
+  __syncthreads();   // every thread of this CTA has read the scalars (no fence needed: the ticket orders reads of `sc`, not the
+                     // streamed parameter stores, which become visible at kernel end as usual)
   if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(&sc->adam_ticket[which], 1u) == gridDim.x - 1) {   // every other CTA has read the old step count long ago
-      if (which == 0) { sc->step_fb = t; sc->bc1_fb = bc1; sc->bc2s_fb = bc2s; }
-      else { sc->step_actor = t; sc->bc1_actor = bc1; sc->bc2s_actor = bc2s; }
+    if (atomicAdd(&sc->adam_ticket[which], 1u) == gridDim.x - 1) {   // every other CTA has read the scalars long ago
+      float n1, n2;
+      adam_bias_corrections(beta1, beta2, t + 1, &n1, &n2);
+      if (which == 0) { sc->step_fb = t; sc->bc1_fb = n1; sc->bc2s_fb = n2; }
+      else { sc->step_actor = t; sc->bc1_actor = n1; sc->bc2s_actor = n2; }
       sc->adam_ticket[which] = 0u;
     }
   }
