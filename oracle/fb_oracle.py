@@ -198,10 +198,25 @@ def sample_z(batch: int, z_dim: int, generator: tp.Optional[torch.Generator] = N
 # ------------------------------------------------------------------------------------------------
 # losses (fb_ddpg.py:303-348, 389-406)
 # ------------------------------------------------------------------------------------------------
+def q_loss_term(F1: Tensor, F2: Tensor, Bm: Tensor, tF1: Tensor, tF2: Tensor, discount: Tensor, z: Tensor) -> Tensor:
+    """The optional Q loss of update_fb (q_loss=True, fb_ddpg.py:330-340): F_k . z regressed on the implicit
+    reward B cov^-1 z plus the discounted target Q; everything on the target side is under no_grad."""
+    with torch.no_grad():
+        next_Q = torch.min(torch.einsum("sd, sd -> s", tF1, z), torch.einsum("sd, sd -> s", tF2, z))
+        cov = torch.matmul(Bm.T, Bm) / Bm.shape[0]
+        inv_cov = torch.inverse(cov)
+        implicit_reward = (torch.matmul(Bm, inv_cov) * z).sum(dim=1)
+        target_Q = implicit_reward.detach() + discount.squeeze(1) * next_Q
+    Q1, Q2 = (torch.einsum("sd, sd -> s", Fi, z) for Fi in (F1, F2))
+    return F.mse_loss(Q1, target_Q) + F.mse_loss(Q2, target_Q)
+
+
 def fb_loss_terms(F1: Tensor, F2: Tensor, Bm: Tensor, tF1: Tensor, tF2: Tensor, tB: Tensor,
-                  discount: Tensor, ortho_coef: float) -> tp.Dict[str, Tensor]:
+                  discount: Tensor, ortho_coef: float, z: tp.Optional[Tensor] = None,
+                  q_loss_coef: tp.Optional[float] = None) -> tp.Dict[str, Tensor]:
     """The batch x batch successor-measure loss and orthonormality regulariser, written the way the
-    reference writes it (einsum + boolean off-diagonal mask)."""
+    reference writes it (einsum + boolean off-diagonal mask).  `q_loss_coef` not None = cfg.q_loss
+    (needs `z`): adds q_loss_coef * q_loss_term(...) to fb_loss and reports it as "q_loss"."""
     target_M = torch.min(torch.einsum("sd, td -> st", tF1, tB), torch.einsum("sd, td -> st", tF2, tB))
     M1 = torch.einsum("sd, td -> st", F1, Bm)
     M2 = torch.einsum("sd, td -> st", F2, Bm)
@@ -213,15 +228,23 @@ def fb_loss_terms(F1: Tensor, F2: Tensor, Bm: Tensor, tF1: Tensor, tF2: Tensor, 
     orth_diag = -2 * cov.diag().mean()
     orth_offdiag = cov[off_diag].pow(2).mean()
     orth = orth_offdiag + orth_diag
-    return {"fb_loss": fb_offdiag + fb_diag + ortho_coef * orth, "fb_offdiag": fb_offdiag, "fb_diag": fb_diag,
-            "orth_loss": orth, "orth_loss_diag": orth_diag, "orth_loss_offdiag": orth_offdiag,
-            "target_M": target_M, "M1": M1}
+    fb_loss = fb_offdiag + fb_diag
+    out: tp.Dict[str, Tensor] = {}
+    if q_loss_coef is not None:   # added before the orthonormality term, like the reference (fb_ddpg.py:341,348)
+        assert z is not None
+        out["q_loss"] = q_loss_term(F1, F2, Bm, tF1, tF2, discount, z)
+        fb_loss = fb_loss + q_loss_coef * out["q_loss"]
+    out.update({"fb_loss": fb_loss + ortho_coef * orth, "fb_offdiag": fb_offdiag, "fb_diag": fb_diag,
+                "orth_loss": orth, "orth_loss_diag": orth_diag, "orth_loss_offdiag": orth_offdiag,
+                "target_M": target_M, "M1": M1})
+    return out
 
 
 def fb_metrics(terms: tp.Dict[str, Tensor], F1: Tensor, Bm: Tensor, z: Tensor) -> tp.Dict[str, float]:
-    """The metric block of update_fb (fb_ddpg.py:356-377), q_loss=False."""
-    eye_diff = torch.matmul(Bm.T, Bm) / Bm.shape[0] - torch.eye(Bm.shape[1])
-    return {"target_M": terms["target_M"].mean().item(), "M1": terms["M1"].mean().item(),
+    """The metric block of update_fb (fb_ddpg.py:356-377)."""
+    eye_diff = torch.matmul(Bm.T, Bm) / Bm.shape[0] - torch.eye(Bm.shape[1], dtype=Bm.dtype)
+    extra = {"q_loss": terms["q_loss"].item()} if "q_loss" in terms else {}
+    return {**extra, "target_M": terms["target_M"].mean().item(), "M1": terms["M1"].mean().item(),
             "F1": F1.mean().item(), "B": Bm.mean().item(),
             "B_norm": torch.norm(Bm, dim=-1).mean().item(), "z_norm": torch.norm(z, dim=-1).mean().item(),
             "fb_loss": terms["fb_loss"].item(), "fb_diag": terms["fb_diag"].item(),
@@ -239,7 +262,7 @@ def _with_grad(p: Params) -> Params:
 def fb_loss_and_grads(fwd: Params, bwd: Params, fwd_tgt: Params, bwd_tgt: Params, actor: Params,
                       obs: Tensor, action: Tensor, discount: Tensor, next_obs: Tensor, next_goal: Tensor,
                       z: Tensor, noise: Tensor, std: float, clip: tp.Optional[float], ortho_coef: float,
-                      z_dim: int) -> tp.Dict[str, tp.Any]:
+                      z_dim: int, q_loss_coef: tp.Optional[float] = None) -> tp.Dict[str, tp.Any]:
     """update_fb up to (not including) the optimizer step: loss terms, metrics, grads of every
     forward_net / backward_net tensor, and the intermediates a kernel test wants to look at."""
     with torch.no_grad():
@@ -250,7 +273,7 @@ def fb_loss_and_grads(fwd: Params, bwd: Params, fwd_tgt: Params, bwd_tgt: Params
     F1, F2 = forward_map(f, obs, z, action)
     Bm = backward_map(b, next_goal, z_dim)
     F1.retain_grad(), F2.retain_grad(), Bm.retain_grad()
-    terms = fb_loss_terms(F1, F2, Bm, tF1, tF2, tB, discount, ortho_coef)
+    terms = fb_loss_terms(F1, F2, Bm, tF1, tF2, tB, discount, ortho_coef, z, q_loss_coef)
     terms["fb_loss"].backward()
     return {"terms": {k: v.detach() for k, v in terms.items()},
             "metrics": fb_metrics({k: v.detach() for k, v in terms.items()}, F1.detach(), Bm.detach(), z),
@@ -262,7 +285,7 @@ def fb_loss_and_grads(fwd: Params, bwd: Params, fwd_tgt: Params, bwd_tgt: Params
 
 
 def actor_loss_and_grads(actor: Params, fwd: Params, obs: Tensor, z: Tensor, noise: Tensor, std: float,
-                         clip: tp.Optional[float]) -> tp.Dict[str, tp.Any]:
+                         clip: tp.Optional[float]) -> tp.Dict[str, tp.Any]:  # "q1_success": additional_metric (fb_ddpg.py:403-404)
     """update_actor up to the optimizer step (fb_ddpg.py:389-409), boltzmann=False."""
     a = _with_grad(actor)
     mu = actor_mean(a, obs, z)
@@ -275,6 +298,7 @@ def actor_loss_and_grads(actor: Params, fwd: Params, obs: Tensor, z: Tensor, noi
     loss = -Q.mean()
     loss.backward()
     return {"actor_loss": loss.detach(), "q": Q.mean().detach(), "actor_logprob": log_prob.mean().detach(),
+            "q1_success": (Q1 > Q2).float().mean().detach(),
             "grads_actor": collections.OrderedDict((k, v.grad) for k, v in a.items()),
             "action": action.detach(), "mu": mu.detach(), "Q1": Q1.detach(), "Q2": Q2.detach()}
 
@@ -401,6 +425,9 @@ class OracleConfig:
     future_ratio: float = 0.0     # hindsight z (fb_ddpg.py:488-491)
     use_goal: bool = False        # goal_space is not None
     metrics: bool = True          # use_tb or use_wandb or use_hiplog
+    q_loss: bool = False          # fb_ddpg.py:330-341
+    q_loss_coef: float = 0.01
+    additional_metric: bool = False   # q1_success (fb_ddpg.py:403-404,416-417)
 
 
 class OracleAgent:
@@ -448,7 +475,7 @@ class OracleAgent:
             tB = backward_map(self.backward_target_net, next_goal, d.z_dim)
         F1, F2 = forward_map(self.forward_net, obs, z, action)
         Bm = backward_map(self.backward_net, next_goal, d.z_dim)
-        terms = fb_loss_terms(F1, F2, Bm, tF1, tF2, tB, discount, cfg.ortho_coef)
+        terms = fb_loss_terms(F1, F2, Bm, tF1, tF2, tB, discount, cfg.ortho_coef, z, cfg.q_loss_coef if cfg.q_loss else None)
         metrics: tp.Dict[str, float] = {}
         if cfg.metrics:
             metrics = fb_metrics({k: v.detach() for k, v in terms.items()}, F1.detach(), Bm.detach(), z)
@@ -467,13 +494,17 @@ class OracleAgent:
         action = truncated_normal_sample(mu, noise, std, cfg.stddev_clip)
         log_prob = normal_log_prob(action, mu, std).sum(-1, keepdim=True)
         F1, F2 = forward_map(self.forward_net, obs, z, action)
-        Q = torch.min(torch.einsum("sd, sd -> s", F1, z), torch.einsum("sd, sd -> s", F2, z))
+        Q1, Q2 = torch.einsum("sd, sd -> s", F1, z), torch.einsum("sd, sd -> s", F2, z)
+        Q = torch.min(Q1, Q2)
         loss = -Q.mean()
         self.actor_opt.zero_grad(set_to_none=True)
         loss.backward()       # like the reference, this also fills forward_net grads (never used)
         self.actor_opt.step()
         if cfg.metrics:
-            return {"actor_loss": loss.item(), "q": Q.mean().item(), "actor_logprob": log_prob.mean().item()}
+            out = {"actor_loss": loss.item(), "q": Q.mean().item(), "actor_logprob": log_prob.mean().item()}
+            if cfg.additional_metric:
+                out["q1_success"] = (Q1 > Q2).float().mean().item()
+            return out
         return {}
 
     # -- fb_ddpg.py:427-520 --------------------------------------------------------------------

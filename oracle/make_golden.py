@@ -42,7 +42,8 @@ def make_agent(R: tp.Any, case: tp.Mapping[str, tp.Any], use_tb: bool = True) ->
         use_tb=use_tb, use_wandb=False, use_hiplog=False, num_expl_steps=0, update_encoder=False,
         goal_space=case["goal_space"], hidden_dim=case["hidden_dim"], feature_dim=case["feature_dim"],
         backward_hidden_dim=case["backward_hidden_dim"], z_dim=case["z_dim"], batch_size=case["batch_size"],
-        future_ratio=case.get("future_ratio", 0.0))
+        future_ratio=case.get("future_ratio", 0.0), q_loss=case.get("q_loss", False),
+        q_loss_coef=case.get("q_loss_coef", 0.01), additional_metric=case.get("additional_metric", False))
     return R.FBDDPGAgent(**dataclasses.asdict(cfg))
 
 
@@ -149,6 +150,8 @@ def gen_update_case(R: tp.Any, name: str, case: tp.Mapping[str, tp.Any]) -> tp.D
     out["cfg/lr"] = np.float64(agent.cfg.lr)
     out["cfg/tau"] = np.float64(agent.cfg.fb_target_tau)
     out["cfg/ortho_coef"] = np.float64(agent.cfg.ortho_coef)
+    if agent.cfg.q_loss:
+        out["cfg/q_loss_coef"] = np.float64(agent.cfg.q_loss_coef)
     return out
 
 
@@ -252,16 +255,35 @@ def gen_trajectory_case(R: tp.Any, case: tp.Mapping[str, tp.Any], steps: int = 3
     return out
 
 
+def write_qloss_cases(R: tp.Any) -> None:
+    """q_loss=True (fb_ddpg.py:330-341) and additional_metric=True (q1_success, fb_ddpg.py:403-404): added after the first
+    fixtures, generated on their own.  q_loss_coef is raised from its 0.01 default so that the term carries weight in the
+    gradients the fixtures pin."""
+    for name, base in (("qloss", "wide"), ("qloss_goal", "goal")):
+        case = dict(CASES[base], q_loss=True, q_loss_coef=0.5, additional_metric=True)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"update_{name}.npz"), **gen_update_case(R, name, case))
+        print("wrote update_%s" % name)
+    case = dict(CASES["small"], q_loss=True, q_loss_coef=0.5, additional_metric=True)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "trajectory_qloss.npz"), **gen_trajectory_case(R, case))
+    print("wrote trajectory_qloss")
+
+
 def main() -> None:
     R = ref_shim.load()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)   # single-thread reductions: the most reproducible reference numbers
+    if "--qloss-only" in sys.argv:
+        write_qloss_cases(R)
+        return
     # hindsight trajectories (future_ratio > 0, fb_ddpg.py:488-491): added after the first fixtures, generated on their own
     for name, base in (("future", "small"), ("future_goal", "goal")):
         case = dict(CASES[base], future_ratio=0.4)
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"trajectory_{name}.npz"), **gen_trajectory_case(R, case))
         print("wrote trajectory_%s" % name)
     if "--hindsight-only" in sys.argv:
+        return
+    write_qloss_cases(R)
+    if "--qloss-only" in sys.argv:
         return
     for name, case in CASES.items():
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"update_{name}.npz"), **gen_update_case(R, name, case))

@@ -9,7 +9,7 @@ import torch
 from conftest import load_golden, subtree
 from oracle import fb_oracle as O
 
-UPDATE_CASES = ["small", "goal", "wide"]
+UPDATE_CASES = ["small", "goal", "wide", "qloss", "qloss_goal"]   # qloss*: q_loss=True (fb_ddpg.py:330-341)
 
 
 def dims_from(g):
@@ -52,7 +52,8 @@ def test_update_fb_losses_and_grads(case):
         params(g, "param0/forward_net"), params(g, "param0/backward_net"), params(g, "param0/forward_target_net"),
         params(g, "param0/backward_target_net"), params(g, "param0/actor"), t["obs"], t["action"], t["discount"],
         t["next_obs"], t["next_goal"], t["z"], t["noise_fb"], float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]),
-        float(g["cfg/ortho_coef"]), d.z_dim)
+        float(g["cfg/ortho_coef"]), d.z_dim, float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None)
+    assert ("q_loss" in res["metrics"]) == case.startswith("qloss")
     for k, v in subtree(g, "metric_fb").items():
         if k == "fb_opt_lr":
             continue
@@ -81,6 +82,8 @@ def test_adam_actor_and_soft_update(case):
     assert float(res["actor_loss"]) == pytest.approx(float(m["actor_loss"]), rel=2e-5)
     assert float(res["q"]) == pytest.approx(float(m["q"]), rel=2e-5)
     assert float(res["actor_logprob"]) == pytest.approx(float(m["actor_logprob"]), rel=2e-5)
+    if "q1_success" in m:   # additional_metric=True fixtures
+        assert float(res["q1_success"]) == pytest.approx(float(m["q1_success"]), abs=1e-7)
     for name, ref in subtree(g, "grad_actor/actor").items():
         assert rel(res["grads_actor"][name].numpy(), ref) < 1e-5, name
     # soft update
@@ -123,7 +126,7 @@ def test_replay_sample_bit_exact(case):
         assert set(batch["meta"].keys()) == {k[5:] for k in ref if k.startswith("meta/")}
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss"])
 def test_full_update_trajectory(case):
     """agent.update(replay, step) x3 with all RNG streams live: the oracle agent walks the
     reference's trajectory from the same parameters and seeds ("future*": hindsight z, future_ratio = 0.4)."""
@@ -138,7 +141,8 @@ def test_full_update_trajectory(case):
                hidden_dim=hidden, feature_dim=f["obs_action_net.3.weight"].shape[0], backward_hidden_dim=b["B.0.weight"].shape[0])
     use_goal = "ep0/goal" in g
     agent = O.OracleAgent(O.OracleConfig(dims=d, batch_size=64 if use_goal else 32, use_goal=use_goal,
-                                         future_ratio=0.4 if case.startswith("future") else 0.0))
+                                         future_ratio=0.4 if case.startswith("future") else 0.0,
+                                         q_loss=case == "qloss", q_loss_coef=0.5, additional_metric=case == "qloss"))
     agent.load_params(actor=a, forward_net=f, backward_net=b, forward_target_net=f, backward_target_net=b)
     buf = O.OracleReplay(4, 0.98, 0.99)
     for i in range(4):
