@@ -19,7 +19,7 @@ CONTRACT_TCGEN05, CONTRACT_SIMT = 0, 1
 MLP_TCGEN05, MLP_SIMT = 0, 1
 HEADER = os.path.join(ROOT, "include", "fb_b200.h")
 
-FB_ABI_VERSION = 2
+FB_ABI_VERSION = 3
 FB_OK = 0
 
 NET_FORWARD, NET_BACKWARD, NET_ACTOR = 0, 1, 2
@@ -42,6 +42,8 @@ RUN_HOST_BATCH = 1 << 15   # modifier of PHASE_SAMPLE: batch rows supplied by th
 # index of each scalar of the metrics block (FB_M_* in fb_b200.h) -> key of the dict FBDDPGAgent.update returns
 METRIC_KEYS = ("target_M", "M1", "F1", "B", "B_norm", "z_norm", "fb_loss", "fb_diag", "fb_offdiag", "orth_loss",
                "orth_loss_diag", "orth_loss_offdiag", "orth_linf", "orth_l2", "actor_loss", "q", "actor_logprob")
+# slots behind them, filled on every step but only reported for the matching config flag (cfg.q_loss / cfg.additional_metric)
+OPTIONAL_METRIC_KEYS = ("q_loss", "q1_success")
 METRIC_COUNT = 32
 OP_KINDS = ("gemm", "layernorm", "elementwise", "colsum", "adam", "gather", "loss", "memset", "contract", "gemm_tc", "transpose", "collective")
 
@@ -53,7 +55,7 @@ class fb_config(C.Structure):
                 ("use_goal", C.c_int32), ("rng_device", C.c_int32), ("contract_mode", C.c_int32), ("mlp_mode", C.c_int32),
                 ("ortho_coef", C.c_float), ("mix_ratio", C.c_float),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float), ("future_ratio", C.c_float),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("q_loss", C.c_int32), ("q_loss_coef", C.c_float)]
 
 
 class fb_step_scalars(C.Structure):

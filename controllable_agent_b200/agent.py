@@ -117,8 +117,7 @@ def register_hydra() -> None:
     ConfigStore.instance().store(group="agent", name="fb_ddpg", node=FBDDPGAgentConfig)
 
 
-_UNSUPPORTED = {"boltzmann": False, "debug": False, "q_loss": False, "rand_weight": False, "preprocess": True, "add_trunk": False,
-                "norm_z": True}
+_UNSUPPORTED = {"boltzmann": False, "debug": False, "rand_weight": False, "preprocess": True, "add_trunk": False, "norm_z": True}
 
 
 class FBDDPGAgent:
@@ -179,7 +178,7 @@ class FBDDPGAgent:
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
-            mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
+            mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, q_loss=bool(cfg.q_loss), q_loss_coef=float(cfg.q_loss_coef), seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
             mlp_mode=L.MLP_SIMT if cfg.mlp_mode == "simt" else L.MLP_TCGEN05,
             contract_mode=L.CONTRACT_SIMT if cfg.contract_mode == "simt" else L.CONTRACT_TCGEN05), device)
 
@@ -436,9 +435,7 @@ class FBDDPGAgent:
         metrics: tp.Dict[str, float] = {}
         if self._metrics_enabled():
             self._run(mask | L.PHASE_METRICS)
-            m = e.read_metrics()
-            metrics = {k: m[k] for k in L.METRIC_KEYS[:14]}
-            metrics["fb_opt_lr"] = self.fb_opt.param_groups[0]["lr"]
+            metrics = self._fb_metrics(e.read_metrics())
         else:
             self._run(mask)
         return metrics
@@ -450,9 +447,23 @@ class FBDDPGAgent:
         self._run(L.PHASE_ACTOR_FWD | L.PHASE_ACTOR_BWD | L.PHASE_ACTOR_ADAM)
         if self.cfg.use_tb or self.cfg.use_wandb:
             e.run(L.PHASE_METRICS, graph=False)
-            m = e.read_metrics()
-            return {k: m[k] for k in L.METRIC_KEYS[14:]}
+            return self._actor_metrics(e.read_metrics())
         return {}
+
+    def _fb_metrics(self, m: tp.Mapping[str, float]) -> tp.Dict[str, float]:
+        """The keys update_fb reports (fb_ddpg.py:356-377) out of the metrics block."""
+        out = {k: m[k] for k in L.METRIC_KEYS[:14]}
+        if self.cfg.q_loss:
+            out["q_loss"] = m["q_loss"]
+        out["fb_opt_lr"] = self.fb_opt.param_groups[0]["lr"]
+        return out
+
+    def _actor_metrics(self, m: tp.Mapping[str, float]) -> tp.Dict[str, float]:
+        """The keys update_actor reports (fb_ddpg.py:413-418)."""
+        out = {k: m[k] for k in L.METRIC_KEYS[14:]}
+        if self.cfg.additional_metric:
+            out["q1_success"] = m["q1_success"]
+        return out
 
     def update(self, replay_loader: tp.Any, step: int) -> tp.Dict[str, float]:
         """fb_ddpg.py:427-520: sample, z draw + mixing, update_fb, update_actor, target soft updates."""
@@ -511,10 +522,9 @@ class FBDDPGAgent:
             m = e.read_metrics()
             if self.world > 1:
                 m = self._reduce_metrics(m)
-            metrics.update({k: m[k] for k in L.METRIC_KEYS[:14]})
-            metrics["fb_opt_lr"] = self.fb_opt.param_groups[0]["lr"]
+            metrics.update(self._fb_metrics(m))
             if c.use_tb or c.use_wandb:   # the actor block logs under a narrower condition (fb_ddpg.py:413)
-                metrics.update({k: m[k] for k in L.METRIC_KEYS[14:]})
+                metrics.update(self._actor_metrics(m))
         return metrics
 
     def _upload_host_batch(self, replay_loader: tp.Any, B: int) -> None:
@@ -530,4 +540,4 @@ class FBDDPGAgent:
     def _reduce_metrics(self, m: tp.Dict[str, float]) -> tp.Dict[str, float]:
         """Per-rank metric blocks -> global values: loss-type entries are partial sums over the rank's rows, the
         others are per-rank means (or replicated)."""
-        return reduce_metrics(m, L.METRIC_KEYS, self.world, self.engine.device)
+        return reduce_metrics(m, L.METRIC_KEYS + L.OPTIONAL_METRIC_KEYS, self.world, self.engine.device)

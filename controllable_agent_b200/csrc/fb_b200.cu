@@ -791,6 +791,24 @@ static int build_plan(fb_handle* h) {
   b.set_phase(FB_PHASE_FB_LOSS);
   const bool use_tc = c.contract_mode == FB_CONTRACT_TCGEN05 && Z <= 128;
   const float inv_noff = 1.0f / ((float)n * (float)(n - 1)), inv_n = 1.0f / (float)n;
+  double* q_inv = nullptr;
+  if (c.q_loss) {
+    // Q loss (fb_ddpg.py:330-341): cov = B^T B / n over the GLOBAL batch and its inverse depend on B only -> side lane, next to
+    // the contraction; the row pass that adds the term to dF_k opens FB_BWD (the phase end joins the lanes)
+    double* q_cov = (double*)ws_alloc(h, (size_t)Z * Z * sizeof(double));
+    q_inv = (double*)ws_alloc(h, (size_t)Z * Z * sizeof(double));
+    const float* Ball = Bg.p; const int ldb = Bg.ld;
+    b.push([Ball, ldb, n, Z, q_cov](cudaStream_t s) {
+      fb_launch_pdl(k_qloss_cov, dim3(Z), dim3(256), 0, s, Ball, ldb, n, Z, q_cov);
+      return cudaGetLastError();
+    }, FB_OPK_ELEMENTWISE, 2.0 * n * (double)Z * Z, 4.0 * n * (double)Z, 1);
+    const size_t inv_smem = (size_t)Z * 2 * Z * sizeof(double);
+    h->qloss_smem = inv_smem;
+    b.push([q_cov, q_inv, Z, inv_smem](cudaStream_t s) {
+      fb_launch_pdl(k_qloss_inverse, dim3(1), dim3(FB_QLOSS_INV_THREADS), inv_smem, s, (const double*)q_cov, Z, q_inv);
+      return cudaGetLastError();
+    }, FB_OPK_ELEMENTWISE, 2.0 * (double)Z * Z * Z, 16.0 * Z * (double)Z, 1);
+  }
   if (use_tc) {
     // tcgen05 path (contract_tc.cuh): split operands -> fused contraction + loss + dL/dM tiles
     const int nbox = fb_ceil_div(Z, 32), KP = nbox * 32;
@@ -889,6 +907,17 @@ static int build_plan(fb_handle* h) {
 
   // =========================== FB_PHASE_FB_BWD ==================================================
   b.set_phase(FB_PHASE_FB_BWD);
+  if (c.q_loss) {
+    QLossParams qp; memset(&qp, 0, sizeof(qp));
+    qp.F1 = F1.p; qp.F2 = F2.p; qp.tF1 = tF1.p; qp.tF2 = tF2.p; qp.Bm = Bm.p; qp.ldblk = bl.ld;
+    qp.disc = bl.p + disc_col; qp.disc_stride = bl.ld; qp.z = z.p; qp.ldz = z.ld;
+    qp.dF1 = dF1.p; qp.dF2 = dF2.p; qp.lddf = dF1.ld; qp.inv = q_inv; qp.rows = B; qp.Z = Z;
+    qp.gcoef = c.q_loss_coef * 2.0f * inv_n; qp.acc = acc;
+    b.push([qp](cudaStream_t s) {
+      fb_launch_pdl(k_qloss_rows, dim3(fb_ceil_div(qp.rows, 8)), dim3(256), 0, s, qp);
+      return cudaGetLastError();
+    }, FB_OPK_LOSS, 2.0 * B * (double)Z * Z, 4.0 * 8.0 * B * (double)Z);
+  }
   {
     const float* p0 = tc_inner ? dBparts.p : dB.p;
     const float* p1 = tc_inner ? dBparts.p + ldZ : nullptr;
@@ -1036,6 +1065,7 @@ static int build_plan(fb_handle* h) {
     });
     MetricFinalParams mp; memset(&mp, 0, sizeof(mp));
     mp.acc = acc; mp.linf_bits = linf; mp.out = h->d_metrics; mp.n_local = B; mp.n_global = n; mp.Z = Z; mp.ortho_coef = c.ortho_coef;
+    mp.q_loss_coef = c.q_loss ? c.q_loss_coef : 0.f;
     b.push([mp](cudaStream_t s) { fb_launch_pdl(k_metric_final, dim3(1), dim3(32), 0, s, mp); return cudaGetLastError(); });
   }
 
@@ -1195,6 +1225,7 @@ int fb_create(const fb_config* cfg, fb_handle** out) {
   if (cfg->hidden_dim > FB_MAX_LN_DIM || cfg->backward_hidden_dim > FB_MAX_LN_DIM) return FB_E_UNSUPPORTED;
   if (!cfg->use_goal && cfg->goal_dim != cfg->obs_dim) return FB_E_ARG;
   if (!(cfg->future_ratio >= 0.f && cfg->future_ratio <= 1.f) || !(cfg->mix_ratio >= 0.f && cfg->mix_ratio <= 1.f)) return FB_E_ARG;
+  if (cfg->q_loss && cfg->z_dim > FB_QLOSS_MAX_Z) return FB_E_UNSUPPORTED;
   fb_handle* h = new fb_handle();
   h->cfg = *cfg;
   memset(&h->bufs, 0, sizeof(h->bufs));
@@ -1285,6 +1316,7 @@ int fb_bind(fb_handle* h, const fb_buffers* bufs, void* stream) {
   CK(cudaFuncSetAttribute(k_gemm_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   if (h->uses_gemm_tc) CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   if (h->contract_smem) CK(cudaFuncSetAttribute(k_contract_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->contract_smem));
+  if (h->qloss_smem > 48u * 1024u) CK(cudaFuncSetAttribute(k_qloss_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qloss_smem));
   CK(cudaMemsetAsync(h->ws_base, 0, h->ws_bytes, s));
   CK(cudaMemcpyAsync(h->ws_base, h->arena.data(), h->arena.size(), cudaMemcpyHostToDevice, s));
   k_iota<<<fb_ceil_div(h->cfg.batch, 256), 256, 0, s>>>(h->d_perm, h->cfg.batch);

@@ -688,10 +688,10 @@ enum {
   ACC_TARGET_M,        // sum_{s,t} tM
   ACC_M1,              // sum_{s,t} M1
   ACC_LOGPROB,         // sum_s log N(a; mu, std)
-  ACC_PAD0,
+  ACC_QLOSS,           // q_loss = 1: sum_s sum_k (F_k[s].z_s - target_Q[s])^2
   // zeroed at the start of FB_PHASE_ACTOR_FWD
   ACC_Q,               // sum_s min_k Q_k
-  ACC_PAD1,
+  ACC_Q1_SUCCESS,      // number of rows with Q1 > Q2 (additional_metric, fb_ddpg.py:403-404)
   // zeroed at the start of FB_PHASE_METRICS
   ACC_F1, ACC_B, ACC_B_NORM, ACC_Z_NORM, ACC_ORTH_SQ, ACC_LINF_BITS,
   ACC_COUNT = 16
@@ -851,7 +851,143 @@ __global__ void __launch_bounds__(256) k_actor_q(const float* __restrict__ F1, c
     dF1[(size_t)r * lddf + c] = w1 * gz;
     dF2[(size_t)r * lddf + c] = w2 * gz;
   }
-  if (lane == 0) atomicAdd(acc + ACC_Q, (double)fminf(q1, q2));
+  if (lane == 0) {
+    atomicAdd(acc + ACC_Q, (double)fminf(q1, q2));
+    if (q1 > q2) atomicAdd(acc + ACC_Q1_SUCCESS, 1.0);
+  }
+}
+
+// ---- optional Q loss of update_fb (cfg.q_loss, fb_ddpg.py:330-341) -------------------------------------------
+//   next_Q = min_k tF_k[s].z_s;  cov = B^T B / n;  implicit_reward[s] = (B_s cov^-1) . z_s;  target_Q = implicit_reward + g_s next_Q
+//   q_loss = sum_k mean_s (F_k[s].z_s - target_Q[s])^2, all of target_Q under no_grad  =>  dF_k[s] += coef (2/n) (Q_k - target_Q) z_s
+// Three launches: cov (fp64 accumulation, one CTA per row, the work shape of k_metric_cov), its inverse (one CTA, Gauss-Jordan
+// with partial pivoting on [cov | I] in shared memory, fp64 — the matrix is z_dim x z_dim), and a row pass (one warp per sample).
+__global__ void __launch_bounds__(256) k_qloss_cov(const float* __restrict__ Bm, int ldb, int rows, int Z, double* __restrict__ cov) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  __shared__ double part[8][128];
+  const int a = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b0 = 0; b0 < Z; b0 += 128) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int r = warp; r < rows; r += 8) {
+      const float* row = Bm + (size_t)r * ldb;
+      const double va = (double)__ldg(row + a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int b = b0 + j * 32 + lane;
+        if (b < Z) s[j] = fma(va, (double)__ldg(row + b), s[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) part[warp][j * 32 + lane] = s[j];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int b = b0 + threadIdx.x;
+      if (b < Z) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+        cov[(size_t)a * Z + b] = t / (double)rows;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+#define FB_QLOSS_MAX_Z 118   // [Z][2Z] doubles of k_qloss_inverse must fit the 227 KB of shared memory a CTA can opt into
+#define FB_QLOSS_INV_THREADS 512
+__global__ void __launch_bounds__(FB_QLOSS_INV_THREADS) k_qloss_inverse(const double* __restrict__ cov, int Z, double* __restrict__ inv) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  extern __shared__ double aug[];   // [Z][2Z] = [cov | I] -> [I | cov^-1]
+  __shared__ double fcol[FB_QLOSS_MAX_Z];
+  __shared__ int piv_row;
+  const int W = 2 * Z, tid = threadIdx.x, lane = threadIdx.x & 31;
+  for (int i = tid; i < Z * W; i += blockDim.x) {
+    const int r = i / W, c = i - r * W;
+    aug[i] = c < Z ? cov[(size_t)r * Z + c] : (c - Z == r ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  for (int k = 0; k < Z; ++k) {
+    if (tid < 32) {   // pivot: the largest |entry| of column k at or below the diagonal (ties: the lowest row index)
+      double best = -1.0;
+      int bi = k;
+      for (int r = k + lane; r < Z; r += 32) {
+        const double v = fabs(aug[r * W + k]);
+        if (v > best) { best = v; bi = r; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(FB_FULL_MASK, best, o);
+        const int oi = __shfl_xor_sync(FB_FULL_MASK, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) piv_row = bi;
+    }
+    __syncthreads();
+    const int pr = piv_row;
+    if (pr != k)
+      for (int c = tid; c < W; c += blockDim.x) {
+        const double t = aug[k * W + c];
+        aug[k * W + c] = aug[pr * W + c];
+        aug[pr * W + c] = t;
+      }
+    __syncthreads();
+    const double p = aug[k * W + k];
+    __syncthreads();   // every thread holds the pivot before row k is scaled
+    for (int c = tid; c < W; c += blockDim.x) aug[k * W + c] /= p;
+    for (int r = tid; r < Z; r += blockDim.x) fcol[r] = (r == k) ? 0.0 : aug[r * W + k];   // column k of the OTHER rows (row k: only its
+    __syncthreads();                                                                      // entry [k][k] is touched by the scaling)
+    for (int i = tid; i < Z * W; i += blockDim.x) {
+      const int r = i / W, c = i - r * W;
+      const double f = fcol[r];
+      if (f != 0.0) aug[i] -= f * aug[k * W + c];
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < Z * Z; i += blockDim.x) {
+    const int r = i / Z, c = i - r * Z;
+    inv[i] = aug[r * W + Z + c];
+  }
+}
+
+struct QLossParams {
+  const float *F1, *F2, *tF1, *tF2, *Bm; int ldblk;   // local rows of the [F1|F2|tF1|tF2|B|tB|discount] block
+  const float* disc; int disc_stride;
+  const float* z; int ldz;
+  float* dF1; float* dF2; int lddf;                   // dL/dF_k of the batch x batch loss, the Q-loss term is added in place
+  const double* inv;                                  // cov^-1, [Z, Z]
+  int rows, Z;
+  float gcoef;                                        // q_loss_coef * 2 / n
+  double* acc;
+};
+__global__ void __launch_bounds__(256) k_qloss_rows(QLossParams P) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= P.rows) return;
+  const size_t ob = (size_t)r * P.ldblk;
+  const float* zr = P.z + (size_t)r * P.ldz;
+  double imp = 0.0;
+  float q1 = 0.f, q2 = 0.f, n1 = 0.f, n2 = 0.f;
+  for (int j = lane; j < P.Z; j += 32) {
+    double u = 0.0;   // (B_s cov^-1)_j : lane j reads column j of cov^-1 (coalesced across the warp)
+    for (int i = 0; i < P.Z; ++i) u = fma((double)__ldg(P.Bm + ob + i), __ldg(P.inv + (size_t)i * P.Z + j), u);
+    const float zz = zr[j];
+    imp = fma(u, (double)zz, imp);
+    q1 = fmaf(P.F1[ob + j], zz, q1); q2 = fmaf(P.F2[ob + j], zz, q2);
+    n1 = fmaf(P.tF1[ob + j], zz, n1); n2 = fmaf(P.tF2[ob + j], zz, n2);
+  }
+  imp = warp_sum_d(imp);
+  q1 = warp_sum(q1); q2 = warp_sum(q2); n1 = warp_sum(n1); n2 = warp_sum(n2);
+  const float target = (float)imp + P.disc[(size_t)r * P.disc_stride] * fminf(n1, n2);
+  const float e1 = q1 - target, e2 = q2 - target;
+  for (int j = lane; j < P.Z; j += 32) {
+    const float gz = P.gcoef * zr[j];
+    P.dF1[(size_t)r * P.lddf + j] += e1 * gz;
+    P.dF2[(size_t)r * P.lddf + j] += e2 * gz;
+  }
+  if (lane == 0) atomicAdd(P.acc + ACC_QLOSS, (double)e1 * e1 + (double)e2 * e2);
 }
 
 // ---- bias gradients: column sums over the batch ----------------------------------------------------
@@ -999,6 +1135,7 @@ __global__ void __launch_bounds__(256) k_metric_cov(const float* __restrict__ Bm
 struct MetricFinalParams {
   const double* acc; const unsigned int* linf_bits; float* out;
   int n_local, n_global, Z; float ortho_coef;
+  float q_loss_coef;   // 0 when cfg.q_loss is off (the accumulator then stays 0)
 };
 // indices must match FB_M_* in fb_b200.h
 __global__ void k_metric_final(MetricFinalParams P) {
@@ -1019,7 +1156,8 @@ __global__ void k_metric_final(MetricFinalParams P) {
   o[3] = (float)(P.acc[ACC_B] / (nl * P.Z));
   o[4] = (float)(P.acc[ACC_B_NORM] / nl);
   o[5] = (float)(P.acc[ACC_Z_NORM] / nl);
-  o[6] = (float)(fb_off + fb_diag + (double)P.ortho_coef * orth);
+  const double q_loss = P.acc[ACC_QLOSS] / n;
+  o[6] = (float)(fb_off + fb_diag + (double)P.q_loss_coef * q_loss + (double)P.ortho_coef * orth);
   o[7] = (float)fb_diag;
   o[8] = (float)fb_off;
   o[9] = (float)orth;
@@ -1030,6 +1168,8 @@ __global__ void k_metric_final(MetricFinalParams P) {
   o[14] = (float)(-P.acc[ACC_Q] / n);
   o[15] = (float)(P.acc[ACC_Q] / n);
   o[16] = (float)(P.acc[ACC_LOGPROB] / n);
+  o[17] = (float)q_loss;
+  o[18] = (float)(P.acc[ACC_Q1_SUCCESS] / n);
 }
 
 // ---- fp32 FMA-chain microbenchmark (roofline denominator for the CUDA-core GEMMs) ---------------------

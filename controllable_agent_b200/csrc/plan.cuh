@@ -79,6 +79,7 @@ struct fb_handle {
   std::map<uint32_t, cudaGraphExec_t> graphs;
   cudaStream_t capture_stream = nullptr;
   size_t contract_smem = 0;  // dynamic shared memory of k_contract_tc (0: SIMT contraction)
+  size_t qloss_smem = 0;     // dynamic shared memory of k_qloss_inverse (0: cfg.q_loss off)
   bool uses_gemm_tc = false;
   // Operands whose source is final before the consuming phase starts (weights, activations of earlier phases) are staged
   // (aligned / transposed copies, pre-split lo planes, zero fills) on a staging lane, as early as their source allows: an

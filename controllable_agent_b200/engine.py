@@ -34,6 +34,8 @@ class EngineConfig:
     ortho_coef: float = 1.0
     mix_ratio: float = 0.5
     future_ratio: float = 0.0   # hindsight z (fb_ddpg.py:488-491)
+    q_loss: bool = False        # the optional Q loss of update_fb (fb_ddpg.py:330-341)
+    q_loss_coef: float = 0.01
     beta1: float = 0.9
     beta2: float = 0.999
     adam_eps: float = 1e-8
@@ -63,7 +65,8 @@ class FBStepEngine:
                         backward_hidden_dim=cfg.backward_hidden_dim, use_goal=int(cfg.use_goal),
                         rng_device=int(cfg.rng_device), contract_mode=int(cfg.contract_mode), mlp_mode=int(cfg.mlp_mode), ortho_coef=cfg.ortho_coef, mix_ratio=cfg.mix_ratio,
                         future_ratio=cfg.future_ratio,
-                        beta1=cfg.beta1, beta2=cfg.beta2, adam_eps=cfg.adam_eps, seed=cfg.seed)
+                        beta1=cfg.beta1, beta2=cfg.beta2, adam_eps=cfg.adam_eps, seed=cfg.seed,
+                        q_loss=int(cfg.q_loss), q_loss_coef=cfg.q_loss_coef)
         h = C.c_void_p()
         L.check(self.lib.fb_create(C.byref(c), C.byref(h)), "fb_create")
         self.h = h
@@ -375,4 +378,4 @@ class FBStepEngine:
         self._metrics_host.copy_(self._metrics, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         vals = self._metrics_host.tolist()
-        return {k: vals[i] for i, k in enumerate(L.METRIC_KEYS)}
+        return {k: vals[i] for i, k in enumerate(L.METRIC_KEYS + L.OPTIONAL_METRIC_KEYS)}

@@ -11,7 +11,7 @@
  *                         host-resident replay buffer feeding the device step)
  *   FB_PHASE_SAMPLE       fb_ddpg.py:433-434,451,467,471 + utils.py:178 (index/z/noise draws + gather)
  *   FB_PHASE_MIX          fb_ddpg.py:470-485 (z mixing through backward_net)
- *   FB_PHASE_FB_FWD/LOSS/BWD   fb_ddpg.py:303-348,380-383 (update_fb forward, loss, backward)
+ *   FB_PHASE_FB_FWD/LOSS/BWD   fb_ddpg.py:303-348,380-383 (update_fb forward, loss incl. the optional Q loss :330-341, backward)
  *   FB_PHASE_FB_ADAM      fb_ddpg.py:384 (fb_opt.step) fused with utils.py:66-69 soft_update_params
  *                         (fb_ddpg.py:500-503; legal because update_actor never writes F/B)
  *   FB_PHASE_ACTOR_FWD/BWD     fb_ddpg.py:389-410 (update_actor forward, Q loss, backward)
@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 2
+#define FB_ABI_VERSION 3
 
 enum {
   FB_OK = 0,
@@ -84,7 +84,10 @@ enum {
 enum {
   FB_M_TARGET_M = 0, FB_M_M1, FB_M_F1, FB_M_B, FB_M_B_NORM, FB_M_Z_NORM, FB_M_FB_LOSS, FB_M_FB_DIAG,
   FB_M_FB_OFFDIAG, FB_M_ORTH_LOSS, FB_M_ORTH_LOSS_DIAG, FB_M_ORTH_LOSS_OFFDIAG, FB_M_ORTH_LINF, FB_M_ORTH_L2,
-  FB_M_ACTOR_LOSS, FB_M_Q, FB_M_ACTOR_LOGPROB, FB_M_COUNT_USED,
+  FB_M_ACTOR_LOSS, FB_M_Q, FB_M_ACTOR_LOGPROB,
+  FB_M_Q_LOSS,      /* cfg.q_loss (fb_ddpg.py:366-367); 0 otherwise */
+  FB_M_Q1_SUCCESS,  /* mean(Q1 > Q2) of update_actor, reported when cfg.additional_metric (fb_ddpg.py:403-404,416-417) */
+  FB_M_COUNT_USED,
   FB_METRIC_COUNT = 32
 };
 
@@ -109,6 +112,9 @@ typedef struct fb_config {
                                   z = backward_net(future_goal or future_obs); 0 disables it (the batch rows then carry no
                                   future fields) */
   uint64_t seed;               /* Philox seed for rng_device */
+  int32_t q_loss;              /* cfg.q_loss (fb_ddpg.py:330-341): add q_loss_coef * sum_k mse(F_k.z, implicit reward + discount *
+                                  min_k tF_k.z) to fb_loss, implicit reward = (B (B^T B / n)^-1) . z; z_dim <= 118 */
+  float q_loss_coef;
 } fb_config;
 
 /* per-step scalars (host values; copied to the device by fb_set_step_scalars) */

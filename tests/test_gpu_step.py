@@ -97,7 +97,8 @@ def _run_update_case(g, d, use_goal, graph, mlp_mode=0):
     L = _L()
     t = {k: torch.from_numpy(np.array(v)) for k, v in subtree(g, "in").items()}
     B = t["obs"].shape[0]
-    eng = make_engine(d, B, use_goal=use_goal, mix_ratio=0.5, ortho_coef=float(g["cfg/ortho_coef"]), mlp_mode=mlp_mode)
+    eng = make_engine(d, B, use_goal=use_goal, mix_ratio=0.5, ortho_coef=float(g["cfg/ortho_coef"]), mlp_mode=mlp_mode,
+                      q_loss_coef=float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None)
     load_params(eng, fwd=subtree(g, "param0/forward_net"), bwd=subtree(g, "param0/backward_net"),
                 actor=subtree(g, "param0/actor"), fwd_tgt=subtree(g, "param0/forward_target_net"),
                 bwd_tgt=subtree(g, "param0/backward_target_net"))
@@ -110,13 +111,14 @@ def _run_update_case(g, d, use_goal, graph, mlp_mode=0):
     return eng, t, L
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "wide"])
+@pytest.mark.parametrize("case", ["small", "goal", "wide", "qloss", "qloss_goal"])   # qloss*: cfg.q_loss (fb_ddpg.py:330-341)
 @pytest.mark.parametrize("graph,mlp_mode", [(False, 0), (True, 0), (True, 1)])
 def test_update_matches_reference_golden(case, graph, mlp_mode):
     g = load_golden(f"update_{case}")
     fwd, bwd, actor = (golden_params(g, f"param0/{n}") for n in ("forward_net", "backward_net", "actor"))
     d = dims_from_params(fwd, bwd, actor)
-    use_goal = case == "goal"
+    use_goal = case.endswith("goal")
+    q_coef = float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None
     eng, t, L = _run_update_case(g, d, use_goal, graph, mlp_mode)
 
     # ---- update_fb up to the gradients (fb_ddpg.py:303-383) ----
@@ -125,10 +127,13 @@ def test_update_matches_reference_golden(case, graph, mlp_mode):
     assert rel(eng.view("z"), t["z"]) < 1e-6
     ora = O.fb_loss_and_grads(fwd, bwd, golden_params(g, "param0/forward_target_net"), golden_params(g, "param0/backward_target_net"),
                               actor, t["obs"], t["action"], t["discount"], t["next_obs"], t["next_goal"], t["z"], t["noise_fb"],
-                              float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]), float(g["cfg/ortho_coef"]), d.z_dim)
+                              float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]), float(g["cfg/ortho_coef"]), d.z_dim, q_coef)
     for name in ("next_action", "tF1", "tF2", "tB", "F1", "F2", "B", "dF1", "dF2", "dB"):
         assert rel(eng.view(name), ora[name]) < REL_TOL, name
     m = eng.read_metrics()
+    assert ("metric_fb/q_loss" in g) == (q_coef is not None)
+    if q_coef is None:
+        assert m["q_loss"] == 0.0
     for k, v in subtree(g, "metric_fb").items():
         if k == "fb_opt_lr":
             continue
@@ -163,6 +168,7 @@ def test_update_matches_reference_golden(case, graph, mlp_mode):
     assert m["actor_loss"] == pytest.approx(float(ora_a["actor_loss"]), rel=REL_TOL, abs=1e-5)
     assert m["q"] == pytest.approx(float(ora_a["q"]), rel=REL_TOL, abs=1e-5)
     assert m["actor_logprob"] == pytest.approx(float(ora_a["actor_logprob"]), rel=REL_TOL, abs=1e-5)
+    assert abs(m["q1_success"] - float(ora_a["q1_success"])) <= 1.0 / t["obs"].shape[0] + 1e-6   # additional_metric (fb_ddpg.py:403-404)
     ref_m = subtree(g, "metric_actor")   # the reference's own numbers (its forward_net differs by Adam noise only)
     assert m["actor_loss"] == pytest.approx(float(ref_m["actor_loss"]), rel=5e-3, abs=1e-4)
     got = read_tensors(eng, L.NET_ACTOR, "grad")
@@ -345,12 +351,12 @@ def test_contraction_tcgen05_matches_simt_and_oracle(case):
         assert out[L.CONTRACT_TCGEN05]["metrics"][k] == pytest.approx(out[L.CONTRACT_SIMT]["metrics"][k], rel=2e-5, abs=1e-6), k
 
 
-@pytest.mark.parametrize("contract_mode", [0, 1])
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_step_sums_to_single_gpu_step(world, contract_mode):
+@pytest.mark.parametrize("world,contract_mode,q_coef", [(2, 0, None), (4, 0, None), (8, 0, None), (2, 1, None), (4, 1, None), (8, 1, None),
+                                                        (2, 0, 0.5), (4, 1, 0.5)])
+def test_sharded_step_sums_to_single_gpu_step(world, contract_mode, q_coef):
     """Multi-GPU decomposition emulated on one device: `world` engines own disjoint row blocks of one global
     batch, exchange the [F1|F2|tF1|tF2|B|tB|discount] block, and the SUM of their flat gradients / loss partials must equal the
-    single-engine step on the whole batch."""
+    single-engine step on the whole batch.  q_coef: with the optional Q loss (its covariance runs over the gathered B rows)."""
     L = _L()
     d = O.Dims(obs_dim=24, action_dim=6, z_dim=50, goal_dim=24, hidden_dim=128, feature_dim=64, backward_hidden_dim=70)
     B = 192 if world == 2 else 256
@@ -367,7 +373,7 @@ def test_sharded_step_sums_to_single_gpu_step(world, contract_mode):
     nf, na = torch.randn(B, d.action_dim, generator=gen), torch.randn(B, d.action_dim, generator=gen)
 
     def make(rows, offset):
-        e = make_engine(d, rows, global_batch=B, row_offset=offset, contract_mode=contract_mode)
+        e = make_engine(d, rows, global_batch=B, row_offset=offset, contract_mode=contract_mode, q_loss_coef=q_coef)
         load_params(e, fwd=fwd, bwd=bwd, actor=actor, fwd_tgt=fwd_t, bwd_tgt=bwd_t)
         e.set_scalars(0.2, 0.3, 1e-4, 1e-4, 1e-4, 0.01)
         sl = slice(offset, offset + rows)
@@ -376,7 +382,7 @@ def test_sharded_step_sums_to_single_gpu_step(world, contract_mode):
         e.set_noise(nf[sl], na[sl])
         return e
 
-    full = make_engine(d, B, contract_mode=contract_mode)
+    full = make_engine(d, B, contract_mode=contract_mode, q_loss_coef=q_coef)
     load_params(full, fwd=fwd, bwd=bwd, actor=actor, fwd_tgt=fwd_t, bwd_tgt=bwd_t)
     full.set_scalars(0.2, 0.3, 1e-4, 1e-4, 1e-4, 0.01)
     full.set_batch(obs, action, discount, next_obs)
@@ -399,7 +405,8 @@ def test_sharded_step_sums_to_single_gpu_step(world, contract_mode):
     torch.cuda.synchronize()
     total = sum(e.grad_fb for e in shards)                                  # what all_reduce(sum) produces
     assert rel(total, ref_grad) < 2e-5
-    for k in ("fb_loss", "fb_offdiag", "fb_diag", "orth_loss", "orth_loss_offdiag", "orth_loss_diag"):
+    assert (ref_m["q_loss"] > 0) == (q_coef is not None)
+    for k in ("fb_loss", "fb_offdiag", "fb_diag", "orth_loss", "orth_loss_offdiag", "orth_loss_diag", "q_loss"):
         assert sum(e.read_metrics()[k] for e in shards) == pytest.approx(ref_m[k], rel=1e-4, abs=1e-5), k
     # actor phase: every rank applies the same (summed) fb gradient, then the actor gradients sum as well
     full.run(L.PHASE_FB_ADAM | L.PHASE_ACTOR_FWD | L.PHASE_ACTOR_BWD | L.PHASE_METRICS)
