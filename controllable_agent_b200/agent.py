@@ -117,7 +117,7 @@ def register_hydra() -> None:
     ConfigStore.instance().store(group="agent", name="fb_ddpg", node=FBDDPGAgentConfig)
 
 
-_UNSUPPORTED = {"boltzmann": False, "debug": False, "rand_weight": False, "preprocess": True, "add_trunk": False, "norm_z": True}
+_UNSUPPORTED = {"boltzmann": False, "debug": False, "rand_weight": False, "preprocess": True, "add_trunk": False}
 
 
 class FBDDPGAgent:
@@ -178,7 +178,7 @@ class FBDDPGAgent:
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
-            mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, q_loss=bool(cfg.q_loss), q_loss_coef=float(cfg.q_loss_coef), seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
+            mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, q_loss=bool(cfg.q_loss), q_loss_coef=float(cfg.q_loss_coef), norm_z=bool(cfg.norm_z), seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
             mlp_mode=L.MLP_SIMT if cfg.mlp_mode == "simt" else L.MLP_TCGEN05,
             contract_mode=L.CONTRACT_SIMT if cfg.contract_mode == "simt" else L.CONTRACT_TCGEN05), device)
 
@@ -328,7 +328,10 @@ class FBDDPGAgent:
     def sample_z(self, size: int, device: tp.Union[str, torch.device] = "cpu") -> torch.Tensor:
         gaussian_rdv = torch.randn((size, self.cfg.z_dim), dtype=torch.float32, device=device)
         gaussian_rdv = F.normalize(gaussian_rdv, dim=1)
-        return math.sqrt(self.cfg.z_dim) * gaussian_rdv
+        if self.cfg.norm_z:
+            return math.sqrt(self.cfg.z_dim) * gaussian_rdv
+        uniform_rdv = torch.rand((size, self.cfg.z_dim), dtype=torch.float32, device=device)   # fb_ddpg.py:230-231
+        return np.sqrt(self.cfg.z_dim) * uniform_rdv * gaussian_rdv
 
     def init_meta(self) -> MetaDict:
         if self.solved_meta is not None:

@@ -523,8 +523,9 @@ static LnDesc b_ln(const BAct& b, const PSet& p) {
   d.rows = b.pre.rows; d.D = b.pre.cols; d.ld = b.pre.ld;
   return d;
 }
-static L2Desc b_l2(const BAct& b, int Z) {
+static L2Desc b_l2(const BAct& b, int Z, int normalize) {
   L2Desc d; memset(&d, 0, sizeof(d));
+  d.normalize = normalize;
   d.x = b.raw.p; d.y = b.out.p; d.nrm = b.nrm; d.rows = b.raw.rows; d.Z = Z; d.ldx = b.raw.ld; d.ldy = b.out.ld;
   return d;
 }
@@ -543,6 +544,7 @@ static int build_plan(fb_handle* h) {
   const int B = c.batch, n = c.global_batch, O = c.obs_dim, A = c.action_dim, Z = c.z_dim, H = c.hidden_dim, Fd = c.feature_dim;
   const int G = c.goal_dim;
   const bool use_goal = c.use_goal != 0;
+  const int nz = c.no_norm_z ? 0 : 1;   // cfg.norm_z: sqrt(Z)-sphere projection of backward_net outputs and of the mixed z
   for (auto& v : h->ops) v.clear();
   for (auto& v : h->early_stage) v.clear();
   for (auto& v : h->early_avail) v.clear();
@@ -672,7 +674,7 @@ static int build_plan(fb_handle* h) {
   b.set_phase(FB_PHASE_SAMPLE);
   if (c.rng_device) {
     RngParams rp; memset(&rp, 0, sizeof(rp));
-    rp.seed = c.seed; rp.batch = B; rp.Z = Z; rp.A = A; rp.ldZ = h->z_rand.ld; rp.ldA = h->noise_fb.ld; rp.mix_ratio = c.mix_ratio;
+    rp.seed = c.seed; rp.batch = B; rp.Z = Z; rp.A = A; rp.ldZ = h->z_rand.ld; rp.ldA = h->noise_fb.ld; rp.mix_ratio = c.mix_ratio; rp.norm_z = nz;
     rp.future_ratio = c.future_ratio; rp.future_mask = with_future ? h->d_future_mask : nullptr;
     rp.n_episodes = h->d_n_episodes; rp.ep_idx = h->d_ep_idx; rp.step_idx = h->d_step_idx; rp.future_idx = h->d_future_idx;
     rp.mix_mask = h->d_mix_mask; rp.perm_keys = h->d_perm_keys; rp.z_rand = h->z_rand.p; rp.noise_fb = h->noise_fb.p;
@@ -726,12 +728,12 @@ static int build_plan(fb_handle* h) {
     b.ln_fwd({b_ln(bMix, pB)});
     b.gemm({lin_fwd(bMix.y, pB.w(4), pB.v(5), bMix.h2, GF_RELU | GF_RELU_LAZY_OK)});
     b.gemm({lin_fwd(bMix.h2, pB.w(6), pB.v(7), bMix.raw, 0)});
-    b.l2_fwd({b_l2(bMix, Z)});
+    b.l2_fwd({b_l2(bMix, Z, nz)});
   }
   {
     ZFinalParams zp; memset(&zp, 0, sizeof(zp));
     zp.batch = B; zp.Z = Z; zp.O = O; zp.z_rand = h->z_rand.p; zp.ldZ = z.ld; zp.b_mix = b_mix_out.p; zp.ld_bmix = b_mix_out.ld;
-    zp.mix_mask = c.mix_ratio > 0.f ? h->d_mix_mask : nullptr; zp.future_mask = with_future ? h->d_future_mask : nullptr; zp.z = z.p; zp.actor_in_oz = actor_in_oz.p; zp.ldOZ = actor_in_oz.ld;
+    zp.mix_mask = c.mix_ratio > 0.f ? h->d_mix_mask : nullptr; zp.future_mask = with_future ? h->d_future_mask : nullptr; zp.z = z.p; zp.actor_in_oz = actor_in_oz.p; zp.ldOZ = actor_in_oz.ld; zp.renorm = nz;
     b.push([zp](cudaStream_t s) { fb_launch_pdl(k_z_final, dim3(fb_ceil_div(zp.batch, 8)), dim3(256), 0, s, zp); return cudaGetLastError(); });
   }
   b.cur_lane = 0;
@@ -756,7 +758,7 @@ static int build_plan(fb_handle* h) {
   b.gemm({lin_fwd(hA, pA.w(A_POL + 0), pA.v(A_POL + 1), h1A, GF_RELU | GF_RELU_LAZY_OK),
           lin_fwd(bO.h2, pB.w(6), pB.v(7), bO.raw, 0), lin_fwd(bT.h2, pBt.w(6), pBt.v(7), bT.raw, 0)});
   b.gemm({lin_fwd(h1A, pA.w(A_POL + 2), pA.v(A_POL + 3), preA, 0)});
-  b.l2_fwd({b_l2(bO, Z), b_l2(bT, Z)});
+  b.l2_fwd({b_l2(bO, Z, nz), b_l2(bT, Z, nz)});
   {
     ActorOutParams ap; memset(&ap, 0, sizeof(ap));
     ap.batch = B; ap.A = A; ap.O = O; ap.pre = preA.p; ap.mu = mu.p; ap.ldA = preA.ld;
@@ -925,8 +927,8 @@ static int build_plan(fb_handle* h) {
     const int ldp = tc_inner ? dBparts.ld : dB.ld;
     float* dsum = tc_inner ? dB.p : nullptr;   // keep the "dB" view complete on both paths
     const float coef = tc_inner ? db_coef : 0.f;
-    b.push([p0, p1, p2, ldp, coef, dsum, dB, Bm, bO, draw, B, Z](cudaStream_t s) {
-      fb_launch_pdl(k_l2norm_bwd, dim3(fb_ceil_div(B, 8)), dim3(256), 0, s, p0, p1, p2, ldp, coef, dsum, dB.ld, Bm.p, Bm.ld, bO.nrm, draw.p, draw.ld, B, Z);
+    b.push([p0, p1, p2, ldp, coef, dsum, dB, Bm, bO, draw, B, Z, nz](cudaStream_t s) {
+      fb_launch_pdl(k_l2norm_bwd, dim3(fb_ceil_div(B, 8)), dim3(256), 0, s, p0, p1, p2, ldp, coef, dsum, dB.ld, Bm.p, Bm.ld, bO.nrm, draw.p, draw.ld, B, Z, nz);
       return cudaGetLastError();
     });
   }
@@ -1101,7 +1103,7 @@ static int build_plan(fb_handle* h) {
     b.ln_fwd({b_ln(b1, pB)});
     b.gemm({lin_fwd(b1.y, pB.w(4), pB.v(5), b1.h2, GF_RELU)});
     b.gemm({lin_fwd(b1.h2, pB.w(6), pB.v(7), b1.raw, 0)});
-    b.l2_fwd({b_l2(b1, Z)});
+    b.l2_fwd({b_l2(b1, Z, nz)});
 
     Mat igN = ws_mat(h, B, G, "infer_goal_batch"), irN = ws_mat(h, B, 1, "infer_reward"), ibN = ws_mat(h, B, Z, "infer_b_batch");
     Mat izs = ws_mat(h, 1, Z, "infer_zsum");
@@ -1111,7 +1113,7 @@ static int build_plan(fb_handle* h) {
     b.ln_fwd({b_ln(bN, pB)});
     b.gemm({lin_fwd(bN.y, pB.w(4), pB.v(5), bN.h2, GF_RELU)});
     b.gemm({lin_fwd(bN.h2, pB.w(6), pB.v(7), bN.raw, 0)});
-    b.l2_fwd({b_l2(bN, Z)});
+    b.l2_fwd({b_l2(bN, Z, nz)});
     b.push([=](cudaStream_t s) {
       fb_launch_pdl(k_infer_weighted_colsum, dim3(fb_ceil_div(Z, 32)), dim3(256), 0, s, ibN.p, ibN.ld, irN.p, irN.ld, B, Z, izs.p);
       return cudaGetLastError();

@@ -215,6 +215,7 @@ struct RngParams {
   unsigned long long seed;
   int batch, rows_per_episode, Z, A, ldZ, ldA;
   float mix_ratio, future_ratio;
+  int norm_z;             // 0: z = sqrt(Z) * U(0,1) (x) normalize(N(0,I))  (cfg.norm_z == False, fb_ddpg.py:230-231)
   int* future_mask;       // null: no hindsight
   const int* n_episodes;  // device scalar: len(buffer)
   const int* ep_len;
@@ -277,7 +278,15 @@ __global__ void __launch_bounds__(256) k_rng_draw(RngParams P, const DevScalars*
   ss = warp_sum(ss);
   const float scale = sqrtf((float)P.Z) / fmaxf(sqrtf(ss), FB_NORMALIZE_EPS);
   __syncwarp();
-  for (int c = lane; c < P.Z; c += 32) P.z_rand[(size_t)warp * P.ldZ + c] *= scale;
+  for (int c = lane; c < P.Z; c += 32) {
+    float v = P.z_rand[(size_t)warp * P.ldZ + c] * scale;
+    if (!P.norm_z) {   // every coordinate scaled by its own U[0,1)
+      const uint4 q = ph(ctr, (uint32_t)warp, 2048u + (uint32_t)(c >> 2));
+      const uint32_t w = (c & 3) == 0 ? q.x : ((c & 3) == 1 ? q.y : ((c & 3) == 2 ? q.z : q.w));
+      v *= u01(w) - (1.0f / 16777216.0f);
+    }
+    P.z_rand[(size_t)warp * P.ldZ + c] = v;
+  }
   // action noise rows
   for (int base = 0; base < P.A; base += 64) {
     const uint4 r = ph(ctr, (uint32_t)warp, 4096u + (uint32_t)(base / 64) * 32u + lane);
@@ -580,7 +589,7 @@ __global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const __grid_constant__ 
 }
 
 // ---- sqrt(Z) * F.normalize (fb_modules.py:33-40, 227-229) ------------------------------------------
-struct L2Desc { const float* x; float* y; float* nrm; int rows, Z, ldx, ldy, row_begin; };
+struct L2Desc { const float* x; float* y; float* nrm; int rows, Z, ldx, ldy, row_begin; int normalize; };   // normalize = 0: y = x (norm_z off)
 
 __global__ void __launch_bounds__(256) k_l2norm_fwd(const L2Desc* __restrict__ descs, int nprob, int total_rows) {
   fb_pdl_trigger();
@@ -597,7 +606,7 @@ __global__ void __launch_bounds__(256) k_l2norm_fwd(const L2Desc* __restrict__ d
   const float nrm = fmaxf(sqrtf(warp_sum(s)), FB_NORMALIZE_EPS);
   const float sq = sqrtf((float)d.Z);
   float* y = d.y + (size_t)r * d.ldy;
-  for (int c = lane; c < d.Z; c += 32) y[c] = sq * (x[c] / nrm);
+  for (int c = lane; c < d.Z; c += 32) y[c] = d.normalize ? sq * (x[c] / nrm) : x[c];
   if (lane == 0 && d.nrm) d.nrm[r] = nrm;
 }
 
@@ -606,11 +615,21 @@ __global__ void __launch_bounds__(256) k_l2norm_fwd(const L2Desc* __restrict__ d
 __global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ dy0, const float* __restrict__ dy1,
                                                     const float* __restrict__ dy2, int lddy, float coef, float* __restrict__ dsum,
                                                     int ldsum, const float* __restrict__ y, int ldy, const float* __restrict__ nrm,
-                                                    float* __restrict__ dx, int lddx, int rows, int Z) {
+                                                    float* __restrict__ dx, int lddx, int rows, int Z, int normalize) {
   fb_pdl_trigger();
   fb_pdl_wait();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
+  if (!normalize) {   // norm_z off: the projection is the identity, dx = the summed gradient (the diagonal term survives)
+    for (int c = lane; c < Z; c += 32) {
+      float g = dy0[(size_t)r * lddy + c] + coef * y[(size_t)r * ldy + c];
+      if (dy1) g += dy1[(size_t)r * lddy + c];
+      if (dy2) g += dy2[(size_t)r * lddy + c];
+      if (dsum) dsum[(size_t)r * ldsum + c] = g;
+      dx[(size_t)r * lddx + c] = g;
+    }
+    return;
+  }
   const float sq = sqrtf((float)Z), isq = 1.0f / sq;
   float dot = 0.f;
   for (int c = lane; c < Z; c += 32) {
@@ -640,6 +659,7 @@ struct ZFinalParams {
   const int* mix_mask;                  // null: no mixing
   const int* future_mask;               // null: no hindsight; else rows [B, 2B) of b_mix hold backward_net(future goal)
   float* z; float* actor_in_oz; int ldOZ;
+  int renorm;                           // cfg.norm_z: re-project the mixed rows (fb_ddpg.py:483-484); 0 leaves them raw
 };
 
 __global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
@@ -649,17 +669,18 @@ __global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
   if (r >= P.batch) return;
   const bool fut = P.future_mask && P.future_mask[r] != 0;   // applied after the mixing: it wins (fb_ddpg.py:488-491)
   const bool mix = !fut && P.mix_mask && P.mix_mask[r] != 0;
+  const bool renorm = mix && P.renorm != 0;
   const float sq = sqrtf((float)P.Z);
   const float* src = fut ? (P.b_mix + (size_t)(P.batch + r) * P.ld_bmix)
                          : (mix ? (P.b_mix + (size_t)r * P.ld_bmix) : (P.z_rand + (size_t)r * P.ldZ));
   float nrm = 1.f;
-  if (mix) {
+  if (renorm) {
     float s = 0.f;
     for (int c = lane; c < P.Z; c += 32) s += src[c] * src[c];
     nrm = fmaxf(sqrtf(warp_sum(s)), FB_NORMALIZE_EPS);
   }
   for (int c = lane; c < P.Z; c += 32) {
-    const float v = mix ? sq * (src[c] / nrm) : src[c];
+    const float v = renorm ? sq * (src[c] / nrm) : src[c];
     P.z[(size_t)r * P.ldZ + c] = v;
     P.actor_in_oz[(size_t)r * P.ldOZ + P.O + c] = v;
     P.actor_in_oz[(size_t)(P.batch + r) * P.ldOZ + P.O + c] = v;

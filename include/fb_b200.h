@@ -115,6 +115,10 @@ typedef struct fb_config {
   int32_t q_loss;              /* cfg.q_loss (fb_ddpg.py:330-341): add q_loss_coef * sum_k mse(F_k.z, implicit reward + discount *
                                   min_k tF_k.z) to fb_loss, implicit reward = (B (B^T B / n)^-1) . z; z_dim <= 118 */
   float q_loss_coef;
+  int32_t no_norm_z;           /* cfg.norm_z == False: backward_net outputs are not projected on the sqrt(z_dim)-sphere
+                                  (fb_modules.py:227-229), mixed z is not re-projected (fb_ddpg.py:483-484) and the device z draw is
+                                  sqrt(z_dim) * U(0,1) (x) direction (fb_ddpg.py:230-231) */
+  int32_t reserved0;           /* 0 */
 } fb_config;
 
 /* per-step scalars (host values; copied to the device by fb_set_step_scalars) */

@@ -189,10 +189,14 @@ def schedule(schdl: tp.Any, step: int) -> float:
     raise NotImplementedError(schdl)
 
 
-def sample_z(batch: int, z_dim: int, generator: tp.Optional[torch.Generator] = None) -> Tensor:
-    """sample_z with norm_z=True (fb_ddpg.py:224-232): uniform on the sqrt(z_dim)-sphere."""
-    g = torch.randn((batch, z_dim), dtype=torch.float32, generator=generator)
-    return math.sqrt(z_dim) * F.normalize(g, dim=1)
+def sample_z(batch: int, z_dim: int, generator: tp.Optional[torch.Generator] = None, norm_z: bool = True) -> Tensor:
+    """sample_z (fb_ddpg.py:224-232): uniform on the sqrt(z_dim)-sphere; norm_z=False scales every coordinate of the
+    direction by its own U(0,1) draw (made after the normal draw, on the same generator)."""
+    g = F.normalize(torch.randn((batch, z_dim), dtype=torch.float32, generator=generator), dim=1)
+    if norm_z:
+        return math.sqrt(z_dim) * g
+    u = torch.rand((batch, z_dim), dtype=torch.float32, generator=generator)
+    return np.sqrt(z_dim) * u * g
 
 
 # ------------------------------------------------------------------------------------------------
@@ -262,16 +266,16 @@ def _with_grad(p: Params) -> Params:
 def fb_loss_and_grads(fwd: Params, bwd: Params, fwd_tgt: Params, bwd_tgt: Params, actor: Params,
                       obs: Tensor, action: Tensor, discount: Tensor, next_obs: Tensor, next_goal: Tensor,
                       z: Tensor, noise: Tensor, std: float, clip: tp.Optional[float], ortho_coef: float,
-                      z_dim: int, q_loss_coef: tp.Optional[float] = None) -> tp.Dict[str, tp.Any]:
+                      z_dim: int, q_loss_coef: tp.Optional[float] = None, norm_z: bool = True) -> tp.Dict[str, tp.Any]:
     """update_fb up to (not including) the optimizer step: loss terms, metrics, grads of every
     forward_net / backward_net tensor, and the intermediates a kernel test wants to look at."""
     with torch.no_grad():
         next_action = truncated_normal_sample(actor_mean(actor, next_obs, z), noise, std, clip)
         tF1, tF2 = forward_map(fwd_tgt, next_obs, z, next_action)
-        tB = backward_map(bwd_tgt, next_goal, z_dim)
+        tB = backward_map(bwd_tgt, next_goal, z_dim, norm_z)
     f, b = _with_grad(fwd), _with_grad(bwd)
     F1, F2 = forward_map(f, obs, z, action)
-    Bm = backward_map(b, next_goal, z_dim)
+    Bm = backward_map(b, next_goal, z_dim, norm_z)
     F1.retain_grad(), F2.retain_grad(), Bm.retain_grad()
     terms = fb_loss_terms(F1, F2, Bm, tF1, tF2, tB, discount, ortho_coef, z, q_loss_coef)
     terms["fb_loss"].backward()
@@ -428,6 +432,7 @@ class OracleConfig:
     q_loss: bool = False          # fb_ddpg.py:330-341
     q_loss_coef: float = 0.01
     additional_metric: bool = False   # q1_success (fb_ddpg.py:403-404,416-417)
+    norm_z: bool = True           # sqrt(z_dim)-sphere projection of B's output and of z (fb_modules.py:227-229, fb_ddpg.py:228,483)
 
 
 class OracleAgent:
@@ -472,9 +477,9 @@ class OracleAgent:
             noise = torch.randn(mu.shape, dtype=mu.dtype)
             next_action = truncated_normal_sample(mu, noise, std, cfg.stddev_clip)
             tF1, tF2 = forward_map(self.forward_target_net, next_obs, z, next_action)
-            tB = backward_map(self.backward_target_net, next_goal, d.z_dim)
+            tB = backward_map(self.backward_target_net, next_goal, d.z_dim, cfg.norm_z)
         F1, F2 = forward_map(self.forward_net, obs, z, action)
-        Bm = backward_map(self.backward_net, next_goal, d.z_dim)
+        Bm = backward_map(self.backward_net, next_goal, d.z_dim, cfg.norm_z)
         terms = fb_loss_terms(F1, F2, Bm, tF1, tF2, tB, discount, cfg.ortho_coef, z, cfg.q_loss_coef if cfg.q_loss else None)
         metrics: tp.Dict[str, float] = {}
         if cfg.metrics:
@@ -514,19 +519,19 @@ class OracleAgent:
         obs, action, discount, next_obs = t["obs"], t["action"], t["discount"], t["next_obs"]
         next_goal = t["next_goal"] if cfg.use_goal else next_obs
         backward_input = t["goal"] if cfg.use_goal else obs
-        z = sample_z(cfg.batch_size, d.z_dim)
+        z = sample_z(cfg.batch_size, d.z_dim, norm_z=cfg.norm_z)
         perm = torch.randperm(cfg.batch_size)
         backward_input = backward_input[perm]
         if cfg.mix_ratio > 0:
             mix_idxs = np.where(np.random.uniform(size=cfg.batch_size) < cfg.mix_ratio)[0]
             with torch.no_grad():
-                mix_z = backward_map(self.backward_net, backward_input[mix_idxs], d.z_dim)
-            z[mix_idxs] = l2_project(mix_z, d.z_dim)
+                mix_z = backward_map(self.backward_net, backward_input[mix_idxs], d.z_dim, cfg.norm_z)
+            z[mix_idxs] = l2_project(mix_z, d.z_dim) if cfg.norm_z else mix_z
         if cfg.future_ratio > 0:   # hindsight replay (fb_ddpg.py:488-491)
             future_goal = t["future_goal"] if cfg.use_goal else t["future_obs"]
             future_idxs = np.where(np.random.uniform(size=cfg.batch_size) < cfg.future_ratio)[0]
             with torch.no_grad():
-                z[future_idxs] = backward_map(self.backward_net, future_goal[future_idxs], d.z_dim)
+                z[future_idxs] = backward_map(self.backward_net, future_goal[future_idxs], d.z_dim, cfg.norm_z)
         metrics = self.update_fb(obs, action, discount, next_obs, next_goal, z, step)
         metrics.update(self.update_actor(obs, z, step))
         with torch.no_grad():

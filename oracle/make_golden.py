@@ -43,7 +43,8 @@ def make_agent(R: tp.Any, case: tp.Mapping[str, tp.Any], use_tb: bool = True) ->
         goal_space=case["goal_space"], hidden_dim=case["hidden_dim"], feature_dim=case["feature_dim"],
         backward_hidden_dim=case["backward_hidden_dim"], z_dim=case["z_dim"], batch_size=case["batch_size"],
         future_ratio=case.get("future_ratio", 0.0), q_loss=case.get("q_loss", False),
-        q_loss_coef=case.get("q_loss_coef", 0.01), additional_metric=case.get("additional_metric", False))
+        q_loss_coef=case.get("q_loss_coef", 0.01), additional_metric=case.get("additional_metric", False),
+        norm_z=case.get("norm_z", True))
     return R.FBDDPGAgent(**dataclasses.asdict(cfg))
 
 
@@ -152,6 +153,7 @@ def gen_update_case(R: tp.Any, name: str, case: tp.Mapping[str, tp.Any]) -> tp.D
     out["cfg/ortho_coef"] = np.float64(agent.cfg.ortho_coef)
     if agent.cfg.q_loss:
         out["cfg/q_loss_coef"] = np.float64(agent.cfg.q_loss_coef)
+    out["cfg/norm_z"] = np.int64(agent.cfg.norm_z)
     return out
 
 
@@ -268,12 +270,27 @@ def write_qloss_cases(R: tp.Any) -> None:
     print("wrote trajectory_qloss")
 
 
+def write_nonorm_cases(R: tp.Any) -> None:
+    """norm_z=False (fb_modules.py:227-229, fb_ddpg.py:228-231,483-484): raw backward_net outputs, z = sqrt(Z) U(0,1) (x) direction,
+    mixed z not re-projected; the diagonal orthonormality term then reaches the gradients."""
+    for name, base in (("nonorm", "small"), ("nonorm_goal", "goal")):
+        case = dict(CASES[base], norm_z=False)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"update_{name}.npz"), **gen_update_case(R, name, case))
+        print("wrote update_%s" % name)
+    case = dict(CASES["small"], norm_z=False, future_ratio=0.3)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "trajectory_nonorm.npz"), **gen_trajectory_case(R, case))
+    print("wrote trajectory_nonorm")
+
+
 def main() -> None:
     R = ref_shim.load()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)   # single-thread reductions: the most reproducible reference numbers
     if "--qloss-only" in sys.argv:
         write_qloss_cases(R)
+        return
+    if "--nonorm-only" in sys.argv:
+        write_nonorm_cases(R)
         return
     # hindsight trajectories (future_ratio > 0, fb_ddpg.py:488-491): added after the first fixtures, generated on their own
     for name, base in (("future", "small"), ("future_goal", "goal")):
@@ -285,6 +302,7 @@ def main() -> None:
     write_qloss_cases(R)
     if "--qloss-only" in sys.argv:
         return
+    write_nonorm_cases(R)
     for name, case in CASES.items():
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"update_{name}.npz"), **gen_update_case(R, name, case))
         print("wrote update_%s" % name)

@@ -124,11 +124,11 @@ def _agent_for(g, case, **kw):
     hidden, oa = f["obs_action_net.0.weight"].shape
     obs_dim = a["obs_net.0.weight"].shape[1]
     agent = FBDDPGAgent(obs_type="states", obs_shape=(obs_dim,), action_shape=(oa - obs_dim,), device="cuda", num_expl_steps=0,
-                        update_encoder=True, goal_space=None if case in ("small", "future", "qloss") else "simplified_walker", use_tb=True, use_wandb=False,
+                        update_encoder=True, goal_space=None if case in ("small", "future", "qloss", "nonorm") else "simplified_walker", use_tb=True, use_wandb=False,
                         use_hiplog=False, hidden_dim=hidden, feature_dim=f["obs_action_net.3.weight"].shape[0],
                         backward_hidden_dim=b["B.0.weight"].shape[0], z_dim=f["F1.2.weight"].shape[0],
-                        batch_size=32 if case in ("small", "future", "qloss") else 64, update_every_steps=1,
-                        future_ratio=0.4 if case.startswith("future") else 0.0, **kw)
+                        batch_size=32 if case in ("small", "future", "qloss", "nonorm") else 64, update_every_steps=1,
+                        future_ratio=0.4 if case.startswith("future") else (0.3 if case == "nonorm" else 0.0), **kw)
     for net, src in ((agent.actor, a), (agent.forward_net, f), (agent.backward_net, b), (agent.forward_target_net, f),
                      (agent.backward_target_net, b)):
         for (name, p) in net.named_parameters():
@@ -136,7 +136,7 @@ def _agent_for(g, case, **kw):
     return agent
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm"])
 @pytest.mark.parametrize("foreign_replay", [False, True])
 def test_agent_update_walks_reference_trajectory(case, foreign_replay):
     """agent.update(replay, step) x3 with the reference's RNG streams (rng_mode=reference, torch draws on the CPU generator
@@ -145,6 +145,8 @@ def test_agent_update_walks_reference_trajectory(case, foreign_replay):
     from controllable_agent_b200 import ReplayBuffer
     g = load_golden(f"trajectory_{case}")
     extra = dict(q_loss=True, q_loss_coef=0.5, additional_metric=True) if case == "qloss" else {}   # fb_ddpg.py:330-341,403-404
+    if case == "nonorm":   # norm_z = False with hindsight rows (future_ratio = 0.3)
+        extra = dict(norm_z=False)
     agent = _agent_for(g, case, rng_mode="reference", **extra)
     agent.draw_device = "cpu"
     eps = [subtree(g, f"ep{i}") for i in range(4)]
@@ -367,6 +369,38 @@ def test_inference_plans_match_the_module_forward(goal_space, G):
         zr = (math.sqrt(Z) * F.normalize(zr, dim=1))[0].cpu().numpy()
     got = agent.infer_meta_from_obs_and_rewards(xs, rw)["z"]
     assert got.shape == (Z,) and np.abs(got - zr).max() < 2e-4
+
+
+def test_device_rng_with_norm_z_off():
+    """rng_mode=device, norm_z=False: z = sqrt(Z) * U[0,1) (x) direction (fb_ddpg.py:230-231) -> E|z|^2 = Z/3; backward_net outputs and
+    the mixed rows stay un-projected."""
+    from controllable_agent_b200 import FBDDPGAgent, ReplayBuffer
+    torch.manual_seed(5)
+    O_, A_, Z, Bsz = 12, 4, 24, 512
+    kw = dict(obs_type="states", obs_shape=(O_,), action_shape=(A_,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,
+              use_tb=True, use_wandb=False, use_hiplog=False, hidden_dim=64, feature_dim=32, backward_hidden_dim=38, z_dim=Z, batch_size=Bsz,
+              update_every_steps=1, norm_z=False, lr=1e-12)   # lr ~ 0: the modules after the step still equal the step's networks
+    rs = np.random.RandomState(0)
+    buf = ReplayBuffer(8, 0.98, 0.99)
+    for _ in range(8):
+        buf.add_episode({"observation": rs.standard_normal((101, O_)), "action": rs.uniform(-1, 1, (101, A_)), "reward": rs.uniform(0, 1, 101),
+                         "discount": np.ones(101)})
+    agent = FBDDPGAgent(**kw, mix_ratio=0.0)
+    m = agent.update(buf, 0)
+    z = agent.engine.view("z").cpu().double()
+    assert float((z ** 2).sum(1).mean()) == pytest.approx(Z / 3.0, rel=0.06)
+    assert m["z_norm"] == pytest.approx(float(z.norm(dim=1).mean()), rel=1e-4)
+    assert float(z.abs().max()) < np.sqrt(Z)
+    Bm = agent.engine.view("B").cpu()
+    with torch.no_grad():
+        raw = agent.backward_net(agent.engine.view("next_goal").clone()).cpu()   # module forward with norm_z = False: no projection
+    assert float((Bm - raw).abs().max()) < 1e-4 * max(1.0, float(raw.abs().max()))
+    assert abs(m["B_norm"] - np.sqrt(Z)) > 1e-2 and abs(m["orth_loss_diag"] + 2 * Z) > 1e-2
+    mixed = FBDDPGAgent(**kw, mix_ratio=1.0)
+    mixed.update(buf, 0)
+    zb = mixed.engine.view("z").cpu()
+    assert float((zb.norm(dim=1) - np.sqrt(Z)).abs().min()) > 1e-3      # mixed rows are raw backward_net outputs, not re-projected
+    assert float((zb - mixed.engine.view("B_mix").cpu()[:Bsz]).abs().max()) == 0.0
 
 
 def test_unsupported_branches_raise():

@@ -98,7 +98,8 @@ def _run_update_case(g, d, use_goal, graph, mlp_mode=0):
     t = {k: torch.from_numpy(np.array(v)) for k, v in subtree(g, "in").items()}
     B = t["obs"].shape[0]
     eng = make_engine(d, B, use_goal=use_goal, mix_ratio=0.5, ortho_coef=float(g["cfg/ortho_coef"]), mlp_mode=mlp_mode,
-                      q_loss_coef=float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None)
+                      q_loss_coef=float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None,
+                      norm_z=bool(g["cfg/norm_z"]) if "cfg/norm_z" in g else True)
     load_params(eng, fwd=subtree(g, "param0/forward_net"), bwd=subtree(g, "param0/backward_net"),
                 actor=subtree(g, "param0/actor"), fwd_tgt=subtree(g, "param0/forward_target_net"),
                 bwd_tgt=subtree(g, "param0/backward_target_net"))
@@ -111,7 +112,8 @@ def _run_update_case(g, d, use_goal, graph, mlp_mode=0):
     return eng, t, L
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "wide", "qloss", "qloss_goal"])   # qloss*: cfg.q_loss (fb_ddpg.py:330-341)
+# qloss*: cfg.q_loss (fb_ddpg.py:330-341); nonorm*: cfg.norm_z = False (fb_modules.py:227-229)
+@pytest.mark.parametrize("case", ["small", "goal", "wide", "qloss", "qloss_goal", "nonorm", "nonorm_goal"])
 @pytest.mark.parametrize("graph,mlp_mode", [(False, 0), (True, 0), (True, 1)])
 def test_update_matches_reference_golden(case, graph, mlp_mode):
     g = load_golden(f"update_{case}")
@@ -119,6 +121,7 @@ def test_update_matches_reference_golden(case, graph, mlp_mode):
     d = dims_from_params(fwd, bwd, actor)
     use_goal = case.endswith("goal")
     q_coef = float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None
+    norm_z = bool(g["cfg/norm_z"]) if "cfg/norm_z" in g else True
     eng, t, L = _run_update_case(g, d, use_goal, graph, mlp_mode)
 
     # ---- update_fb up to the gradients (fb_ddpg.py:303-383) ----
@@ -127,7 +130,7 @@ def test_update_matches_reference_golden(case, graph, mlp_mode):
     assert rel(eng.view("z"), t["z"]) < 1e-6
     ora = O.fb_loss_and_grads(fwd, bwd, golden_params(g, "param0/forward_target_net"), golden_params(g, "param0/backward_target_net"),
                               actor, t["obs"], t["action"], t["discount"], t["next_obs"], t["next_goal"], t["z"], t["noise_fb"],
-                              float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]), float(g["cfg/ortho_coef"]), d.z_dim, q_coef)
+                              float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]), float(g["cfg/ortho_coef"]), d.z_dim, q_coef, norm_z)
     for name in ("next_action", "tF1", "tF2", "tB", "F1", "F2", "B", "dF1", "dF2", "dB"):
         assert rel(eng.view(name), ora[name]) < REL_TOL, name
     m = eng.read_metrics()

@@ -9,7 +9,7 @@ import torch
 from conftest import load_golden, subtree
 from oracle import fb_oracle as O
 
-UPDATE_CASES = ["small", "goal", "wide", "qloss", "qloss_goal"]   # qloss*: q_loss=True (fb_ddpg.py:330-341)
+UPDATE_CASES = ["small", "goal", "wide", "qloss", "qloss_goal", "nonorm", "nonorm_goal"]   # qloss*: q_loss=True (fb_ddpg.py:330-341); nonorm*: norm_z=False
 
 
 def dims_from(g):
@@ -52,7 +52,9 @@ def test_update_fb_losses_and_grads(case):
         params(g, "param0/forward_net"), params(g, "param0/backward_net"), params(g, "param0/forward_target_net"),
         params(g, "param0/backward_target_net"), params(g, "param0/actor"), t["obs"], t["action"], t["discount"],
         t["next_obs"], t["next_goal"], t["z"], t["noise_fb"], float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]),
-        float(g["cfg/ortho_coef"]), d.z_dim, float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None)
+        float(g["cfg/ortho_coef"]), d.z_dim, float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None,
+        norm_z=bool(g["cfg/norm_z"]) if "cfg/norm_z" in g else True)
+    assert (abs(res["metrics"]["orth_loss_diag"] + 2 * d.z_dim) > 1e-3) == case.startswith("nonorm")
     assert ("q_loss" in res["metrics"]) == case.startswith("qloss")
     for k, v in subtree(g, "metric_fb").items():
         if k == "fb_opt_lr":
@@ -126,7 +128,7 @@ def test_replay_sample_bit_exact(case):
         assert set(batch["meta"].keys()) == {k[5:] for k in ref if k.startswith("meta/")}
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm"])
 def test_full_update_trajectory(case):
     """agent.update(replay, step) x3 with all RNG streams live: the oracle agent walks the
     reference's trajectory from the same parameters and seeds ("future*": hindsight z, future_ratio = 0.4)."""
@@ -141,7 +143,8 @@ def test_full_update_trajectory(case):
                hidden_dim=hidden, feature_dim=f["obs_action_net.3.weight"].shape[0], backward_hidden_dim=b["B.0.weight"].shape[0])
     use_goal = "ep0/goal" in g
     agent = O.OracleAgent(O.OracleConfig(dims=d, batch_size=64 if use_goal else 32, use_goal=use_goal,
-                                         future_ratio=0.4 if case.startswith("future") else 0.0,
+                                         future_ratio=0.4 if case.startswith("future") else (0.3 if case == "nonorm" else 0.0),
+                                         norm_z=case != "nonorm",
                                          q_loss=case == "qloss", q_loss_coef=0.5, additional_metric=case == "qloss"))
     agent.load_params(actor=a, forward_net=f, backward_net=b, forward_target_net=f, backward_target_net=b)
     buf = O.OracleReplay(4, 0.98, 0.99)
