@@ -56,7 +56,7 @@ class fb_config(C.Structure):
                 ("ortho_coef", C.c_float), ("mix_ratio", C.c_float),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float), ("future_ratio", C.c_float),
                 ("seed", C.c_uint64), ("q_loss", C.c_int32), ("q_loss_coef", C.c_float),
-                ("no_norm_z", C.c_int32), ("reserved0", C.c_int32)]
+                ("no_norm_z", C.c_int32), ("rand_weight", C.c_int32)]
 
 
 class fb_step_scalars(C.Structure):
@@ -99,6 +99,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "fb_nccl_unique_id": (_i, [C.c_char_p, _vp]),
     "fb_nccl_init": (_i, [_vp, C.c_char_p, _vp, _i, _i]),
     "fb_set_future_mask": (_i, [_vp, _vp, _vp]),
+    "fb_set_mix_weights": (_i, [_vp, _vp, _vp, _vp]),
     "fb_set_z": (_i, [_vp, _vp, _vp]),
     "fb_set_noise": (_i, [_vp, _vp, _vp, _vp]),
     "fb_run": (_i, [_vp, _u32, _i, _vp]),

@@ -117,7 +117,7 @@ def register_hydra() -> None:
     ConfigStore.instance().store(group="agent", name="fb_ddpg", node=FBDDPGAgentConfig)
 
 
-_UNSUPPORTED = {"boltzmann": False, "debug": False, "rand_weight": False, "preprocess": True, "add_trunk": False}
+_UNSUPPORTED = {"boltzmann": False, "debug": False, "preprocess": True, "add_trunk": False}
 
 
 class FBDDPGAgent:
@@ -178,7 +178,7 @@ class FBDDPGAgent:
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
-            mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, q_loss=bool(cfg.q_loss), q_loss_coef=float(cfg.q_loss_coef), norm_z=bool(cfg.norm_z), seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
+            mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, q_loss=bool(cfg.q_loss), q_loss_coef=float(cfg.q_loss_coef), norm_z=bool(cfg.norm_z), rand_weight=bool(cfg.rand_weight), seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
             mlp_mode=L.MLP_SIMT if cfg.mlp_mode == "simt" else L.MLP_TCGEN05,
             contract_mode=L.CONTRACT_SIMT if cfg.contract_mode == "simt" else L.CONTRACT_TCGEN05), device)
 
@@ -504,6 +504,17 @@ class FBDDPGAgent:
             z = self.sample_z(B, device=self.draw_device)
             perm = torch.randperm(B)
             mix = (np.random.uniform(size=B) < c.mix_ratio).astype(np.int32) if c.mix_ratio > 0 else np.zeros(B, np.int32)
+            if c.rand_weight and c.mix_ratio > 0:
+                # fb_ddpg.py:477-480: torch.rand(nmix, B) then torch.rand(nmix, 1), both on the CPU generator whatever the device;
+                # scattered into the [B, B] block the library reads (row s = the weights of batch row s)
+                mix_idxs = np.where(mix)[0]
+                if getattr(self, "_mixw_stage", None) is None:
+                    self._mixw_stage = (torch.zeros((B, B), dtype=torch.float32).pin_memory(), torch.zeros(B, dtype=torch.float32).pin_memory())
+                w_full, u_full = self._mixw_stage
+                torch.cuda.current_stream(e.device).synchronize()   # the previous step's upload has left the pinned block
+                w_full[mix_idxs] = torch.rand(size=(mix_idxs.shape[0], B))
+                u_full[mix_idxs] = torch.rand(mix_idxs.shape[0], 1)[:, 0]
+                e.set_mix_weights(w_full, u_full)
             noise_fb = _standard_normal((B, self.action_dim), dtype=torch.float32, device=self.draw_device)
             noise_actor = _standard_normal((B, self.action_dim), dtype=torch.float32, device=self.draw_device)
             if fused:

@@ -588,6 +588,14 @@ static int build_plan(fb_handle* h) {
   h->noise_actor = ws_mat(h, B, A, "noise_actor");
   Mat mu = ws_mat(h, 2 * B, A, "mu_all");
   h->views["mu"] = mu.rs(B, B);
+  const bool rand_w = c.rand_weight != 0 && c.mix_ratio > 0.f;
+  Mat b_mixw;
+  if (rand_w) {
+    h->mix_w = ws_mat(h, B, B, "mix_w");
+    h->mix_u = (float*)ws_alloc(h, B * sizeof(float));
+    { Mat u; u.p = h->mix_u; u.rows = B; u.cols = 1; u.ld = 1; h->views["mix_u"] = u; }
+    b_mixw = ws_mat(h, B, Z, "B_mixw");
+  }
   Mat next_action = ws_mat(h, B, A, "next_action");
   Mat action_new = ws_mat(h, B, A, "action_new");
 
@@ -686,6 +694,14 @@ static int build_plan(fb_handle* h) {
       fb_launch_pdl(k_rng_draw, dim3(fb_ceil_div(rp.batch, 8)), dim3(256), 0, s, rp, sc);
       return cudaGetLastError();
     });
+    if (rand_w) {   // before k_randperm: it closes the step's draws by bumping the counter
+      MixWeightRngParams wp; memset(&wp, 0, sizeof(wp));
+      wp.seed = c.seed; wp.batch = B; wp.W = h->mix_w.p; wp.ldw = h->mix_w.ld; wp.u = h->mix_u;
+      b.push([wp, sc](cudaStream_t s) {
+        fb_launch_pdl(k_rng_mix_weights, dim3(FB_SM_COUNT * 4), dim3(256), 0, s, wp, sc);
+        return cudaGetLastError();
+      }, FB_OPK_ELEMENTWISE, 0.0, 4.0 * B * (double)B);
+    }
     unsigned int* keys = h->d_perm_keys; int* perm = h->d_perm;
     b.push([keys, perm, B, sc](cudaStream_t s) {
       fb_launch_pdl(k_randperm, dim3(fb_ceil_div(B, 256)), dim3(256), (size_t)B * sizeof(unsigned int), s, keys, B, perm, sc);
@@ -730,9 +746,20 @@ static int build_plan(fb_handle* h) {
     b.gemm({lin_fwd(bMix.h2, pB.w(6), pB.v(7), bMix.raw, 0)});
     b.l2_fwd({b_l2(bMix, Z, nz)});
   }
+  if (rand_w) {   // mixed rows = random weighted sums of all B rows of backward_net(backward_input[perm])
+    MixWeightParams mp; memset(&mp, 0, sizeof(mp));
+    mp.batch = B; mp.Z = Z; mp.b = b_mix_out.p; mp.ldb = b_mix_out.ld; mp.W = h->mix_w.p; mp.ldw = h->mix_w.ld; mp.u = h->mix_u;
+    mp.mix_mask = h->d_mix_mask; mp.out = b_mixw.p; mp.ldo = b_mixw.ld;
+    const size_t smem = (size_t)FB_MIXW_TILE * Z * sizeof(float);
+    b.push([mp, smem](cudaStream_t s) {
+      fb_launch_pdl(k_mix_rand_weight, dim3(fb_ceil_div(mp.batch, 8)), dim3(256), smem, s, mp);
+      return cudaGetLastError();
+    }, FB_OPK_ELEMENTWISE, 2.0 * B * (double)B * Z, 4.0 * (B * (double)B + 2.0 * B * Z));
+  }
   {
     ZFinalParams zp; memset(&zp, 0, sizeof(zp));
     zp.batch = B; zp.Z = Z; zp.O = O; zp.z_rand = h->z_rand.p; zp.ldZ = z.ld; zp.b_mix = b_mix_out.p; zp.ld_bmix = b_mix_out.ld;
+    zp.mix_src = rand_w ? b_mixw.p : b_mix_out.p; zp.ld_mix_src = rand_w ? b_mixw.ld : b_mix_out.ld;
     zp.mix_mask = c.mix_ratio > 0.f ? h->d_mix_mask : nullptr; zp.future_mask = with_future ? h->d_future_mask : nullptr; zp.z = z.p; zp.actor_in_oz = actor_in_oz.p; zp.ldOZ = actor_in_oz.ld; zp.renorm = nz;
     b.push([zp](cudaStream_t s) { fb_launch_pdl(k_z_final, dim3(fb_ceil_div(zp.batch, 8)), dim3(256), 0, s, zp); return cudaGetLastError(); });
   }
@@ -1228,6 +1255,7 @@ int fb_create(const fb_config* cfg, fb_handle** out) {
   if (!cfg->use_goal && cfg->goal_dim != cfg->obs_dim) return FB_E_ARG;
   if (!(cfg->future_ratio >= 0.f && cfg->future_ratio <= 1.f) || !(cfg->mix_ratio >= 0.f && cfg->mix_ratio <= 1.f)) return FB_E_ARG;
   if (cfg->q_loss && cfg->z_dim > FB_QLOSS_MAX_Z) return FB_E_UNSUPPORTED;
+  if (cfg->rand_weight && cfg->z_dim > FB_MIXW_MAX_Z) return FB_E_UNSUPPORTED;
   fb_handle* h = new fb_handle();
   h->cfg = *cfg;
   memset(&h->bufs, 0, sizeof(h->bufs));
@@ -1420,6 +1448,13 @@ static int copy_rows(const Mat& dst, const float* src, cudaStream_t s) {
   CK(cudaMemcpy2DAsync(dst.p, dst.ld * sizeof(float), src, dst.cols * sizeof(float), dst.cols * sizeof(float), dst.rows,
                        cudaMemcpyDeviceToDevice, s));
   return FB_OK;
+}
+
+int fb_set_mix_weights(fb_handle* h, const float* d_weight, const float* d_row_scale, void* stream) {
+  if (!h || !h->bound) return FB_E_STATE;
+  if (!d_weight || !d_row_scale || !h->mix_u) return FB_E_ARG;   // mix_u: the plan was built with rand_weight (and mix_ratio > 0)
+  CK(cudaMemcpyAsync(h->mix_u, d_row_scale, (size_t)h->cfg.batch * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return copy_rows(h->mix_w, d_weight, (cudaStream_t)stream);
 }
 
 int fb_set_z(fb_handle* h, const float* d_z, void* stream) {

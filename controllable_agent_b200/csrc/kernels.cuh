@@ -651,11 +651,85 @@ __global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ dy
   }
 }
 
+// ---- rand_weight mixing (cfg.rand_weight, fb_ddpg.py:475-482) -----------------------------------------------------
+//   weight = U(0,1)^[nmix, B], rows L2-normalised, each scaled by its own U(0,1);  mix_z = weight . backward_net(backward_input[perm])
+// The weight rows live in a [B, ldw] block (row s belongs to batch row s, rows outside the mix mask are never read): drawn here
+// with Philox (rng_device) or uploaded by the caller (fb_set_mix_weights, the reference's torch.rand draws).
+struct MixWeightRngParams { unsigned long long seed; int batch; float* W; int ldw; float* u; };
+__global__ void __launch_bounds__(256) k_rng_mix_weights(MixWeightRngParams P, const DevScalars* __restrict__ sc) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  const unsigned long long ctr = sc->rng_counter;   // k_randperm (the next launch) bumps it
+  Philox ph(P.seed);
+  const int q4 = P.ldw / 4;
+  const size_t total = (size_t)P.batch * q4;
+  const float lo = 1.0f / 16777216.0f;   // u01 is (0, 1]; torch.rand is [0, 1)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i / q4), c4 = (int)(i - (size_t)s * q4);
+    const uint4 r = ph(ctr, (uint32_t)s, 8192u + (uint32_t)c4);
+    *reinterpret_cast<float4*>(P.W + (size_t)s * P.ldw + 4 * c4) = make_float4(u01(r.x) - lo, u01(r.y) - lo, u01(r.z) - lo, u01(r.w) - lo);
+    if (c4 == 0) P.u[s] = u01(ph(ctr, (uint32_t)s, 2u).x) - lo;
+  }
+}
+
+struct MixWeightParams {
+  int batch, Z;
+  const float* b; int ldb;        // backward_net(backward_input[perm]), [batch, Z]
+  const float* W; int ldw;        // [batch, ldw] weight rows
+  const float* u;                 // [batch] row scales
+  const int* mix_mask;
+  float* out; int ldo;            // [batch, Z]: (u_s / |W_s|) sum_t W[s,t] b[t]  for the rows of the mix mask
+};
+#define FB_MIXW_TILE 64
+#define FB_MIXW_MAX_Z 128
+// one warp per output row, 8 rows per CTA; the CTA walks b in 64-row tiles staged in shared memory
+__global__ void __launch_bounds__(256) k_mix_rand_weight(MixWeightParams P) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  extern __shared__ float mixw_sb[];   // [FB_MIXW_TILE][Z]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * 8 + warp;
+  const bool active = s < P.batch && P.mix_mask[s] != 0;   // warp-uniform
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float ss = 0.f;
+  for (int t0 = 0; t0 < P.batch; t0 += FB_MIXW_TILE) {
+    const int nt = min(FB_MIXW_TILE, P.batch - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt * P.Z; i += blockDim.x) {
+      const int tt = i / P.Z, c = i - tt * P.Z;
+      mixw_sb[i] = P.b[(size_t)(t0 + tt) * P.ldb + c];
+    }
+    __syncthreads();
+    if (active) {
+      const float w0 = lane < nt ? P.W[(size_t)s * P.ldw + t0 + lane] : 0.f;
+      const float w1 = lane + 32 < nt ? P.W[(size_t)s * P.ldw + t0 + 32 + lane] : 0.f;
+      ss += w0 * w0 + w1 * w1;
+      for (int tt = 0; tt < nt; ++tt) {
+        const float wv = __shfl_sync(FB_FULL_MASK, tt < 32 ? w0 : w1, tt & 31);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = lane + 32 * j;
+          if (c < P.Z) acc[j] = fmaf(wv, mixw_sb[tt * P.Z + c], acc[j]);
+        }
+      }
+    }
+  }
+  if (!active) return;
+  ss = warp_sum(ss);
+  const float scale = P.u[s] / fmaxf(sqrtf(ss), FB_NORMALIZE_EPS);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane + 32 * j;
+    if (c < P.Z) P.out[(size_t)s * P.ldo + c] = scale * acc[j];
+  }
+}
+
 // ---- z finalisation (fb_ddpg.py:470-485): z[mix] = sqrt(Z) normalize(B(backward_input[perm])[mix]) ----
 struct ZFinalParams {
   int batch, Z, O;
   const float* z_rand; int ldZ;
   const float* b_mix; int ld_bmix;      // already sqrt(Z)-normalised by BackwardMap; the reference renormalises
+  const float* mix_src; int ld_mix_src; // where the mixing rows come from: b_mix, or the rand_weight combinations of its rows
   const int* mix_mask;                  // null: no mixing
   const int* future_mask;               // null: no hindsight; else rows [B, 2B) of b_mix hold backward_net(future goal)
   float* z; float* actor_in_oz; int ldOZ;
@@ -672,7 +746,7 @@ __global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
   const bool renorm = mix && P.renorm != 0;
   const float sq = sqrtf((float)P.Z);
   const float* src = fut ? (P.b_mix + (size_t)(P.batch + r) * P.ld_bmix)
-                         : (mix ? (P.b_mix + (size_t)r * P.ld_bmix) : (P.z_rand + (size_t)r * P.ldZ));
+                         : (mix ? (P.mix_src + (size_t)r * P.ld_mix_src) : (P.z_rand + (size_t)r * P.ldZ));
   float nrm = 1.f;
   if (renorm) {
     float s = 0.f;

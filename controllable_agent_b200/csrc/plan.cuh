@@ -103,6 +103,8 @@ struct fb_handle {
   unsigned int* d_perm_keys = nullptr;
   int* d_identity_perm = nullptr;
   Mat packed, z_rand, noise_fb, noise_actor, blk_local, blk_global;
+  Mat mix_w;                 // cfg.rand_weight: [batch, batch] weight rows
+  float* mix_u = nullptr;    //                  [batch] row scales
   BatchLayout bl;
   fb_replay_view replay;
   bool replay_bound = false;

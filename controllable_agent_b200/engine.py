@@ -36,6 +36,7 @@ class EngineConfig:
     future_ratio: float = 0.0   # hindsight z (fb_ddpg.py:488-491)
     q_loss: bool = False        # the optional Q loss of update_fb (fb_ddpg.py:330-341)
     q_loss_coef: float = 0.01
+    rand_weight: bool = False   # mixed z rows = random weighted sums of B rows (fb_ddpg.py:475-482)
     norm_z: bool = True         # sqrt(z_dim)-sphere projection of B's output / of z (fb_modules.py:227-229, fb_ddpg.py:228,483)
     beta1: float = 0.9
     beta2: float = 0.999
@@ -67,7 +68,7 @@ class FBStepEngine:
                         rng_device=int(cfg.rng_device), contract_mode=int(cfg.contract_mode), mlp_mode=int(cfg.mlp_mode), ortho_coef=cfg.ortho_coef, mix_ratio=cfg.mix_ratio,
                         future_ratio=cfg.future_ratio,
                         beta1=cfg.beta1, beta2=cfg.beta2, adam_eps=cfg.adam_eps, seed=cfg.seed,
-                        q_loss=int(cfg.q_loss), q_loss_coef=cfg.q_loss_coef, no_norm_z=int(not cfg.norm_z))
+                        q_loss=int(cfg.q_loss), q_loss_coef=cfg.q_loss_coef, no_norm_z=int(not cfg.norm_z), rand_weight=int(cfg.rand_weight))
         h = C.c_void_p()
         L.check(self.lib.fb_create(C.byref(c), C.byref(h)), "fb_create")
         self.h = h
@@ -263,6 +264,15 @@ class FBStepEngine:
         t = self._dev_i32(mask)
         L.check(self.lib.fb_set_future_mask(self.h, _ptr(t), self._stream()), "fb_set_future_mask")
         self._keepalive_future = t
+
+    def set_mix_weights(self, weight: tp.Any, row_scale: tp.Any) -> None:
+        """rand_weight with host RNG: the [batch, batch] U(0,1) weight rows and [batch] row scales (fb_ddpg.py:477-480)."""
+        B = self.cfg.batch
+        w = torch.as_tensor(weight, dtype=torch.float32).to(self.device, non_blocking=True).contiguous()
+        u = torch.as_tensor(row_scale, dtype=torch.float32).to(self.device, non_blocking=True).contiguous()
+        assert w.numel() == B * B and u.numel() == B
+        L.check(self.lib.fb_set_mix_weights(self.h, _ptr(w), _ptr(u), self._stream()), "fb_set_mix_weights")
+        self._keepalive_mixw = (w, u)
 
     def set_z(self, z: tp.Any) -> None:
         t = self._dev_f32(z, self.cfg.z_dim)

@@ -118,7 +118,10 @@ typedef struct fb_config {
   int32_t no_norm_z;           /* cfg.norm_z == False: backward_net outputs are not projected on the sqrt(z_dim)-sphere
                                   (fb_modules.py:227-229), mixed z is not re-projected (fb_ddpg.py:483-484) and the device z draw is
                                   sqrt(z_dim) * U(0,1) (x) direction (fb_ddpg.py:230-231) */
-  int32_t reserved0;           /* 0 */
+  int32_t rand_weight;         /* cfg.rand_weight (fb_ddpg.py:475-482): the mixed z rows are random weighted sums of ALL rows of
+                                  backward_net(backward_input[perm]) (weights U(0,1), rows L2-normalised, scaled by one U(0,1) each)
+                                  instead of single rows; z_dim <= 128.  rng_device = 0: the caller uploads the weights
+                                  (fb_set_mix_weights) */
 } fb_config;
 
 /* per-step scalars (host values; copied to the device by fb_set_step_scalars) */
@@ -208,6 +211,9 @@ int fb_nccl_init(fb_handle* h, const char* libnccl_path, const void* id128, int 
 int fb_upload_batch(fb_handle* h, const float* h_rows, int pitch, void* stream);
 /* rng_device == 0, future_ratio > 0: the hindsight row mask of fb_ddpg.py:490 ([batch] int32, non-zero = hindsight z) */
 int fb_set_future_mask(fb_handle* h, const int32_t* d_future_mask, void* stream);
+/* rng_device == 0, rand_weight = 1: the U(0,1) draws of fb_ddpg.py:477,479 as a [batch, batch] block (row s = the weight row of
+ * batch row s; rows outside the mix mask are ignored) and [batch] row scales */
+int fb_set_mix_weights(fb_handle* h, const float* d_weight, const float* d_row_scale, void* stream);
 /* rng_device == 0: the random z of fb_ddpg.py:451 ([batch, z_dim], rows of norm sqrt(z_dim)) */
 int fb_set_z(fb_handle* h, const float* d_z, void* stream);
 /* rng_device == 0: the two N(0,1) draws of utils.py:178 ([batch, action_dim] each): update_fb's

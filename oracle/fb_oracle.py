@@ -432,6 +432,7 @@ class OracleConfig:
     q_loss: bool = False          # fb_ddpg.py:330-341
     q_loss_coef: float = 0.01
     additional_metric: bool = False   # q1_success (fb_ddpg.py:403-404,416-417)
+    rand_weight: bool = False     # mixed z = random convex-like combinations of B rows (fb_ddpg.py:475-482)
     norm_z: bool = True           # sqrt(z_dim)-sphere projection of B's output and of z (fb_modules.py:227-229, fb_ddpg.py:228,483)
 
 
@@ -525,7 +526,12 @@ class OracleAgent:
         if cfg.mix_ratio > 0:
             mix_idxs = np.where(np.random.uniform(size=cfg.batch_size) < cfg.mix_ratio)[0]
             with torch.no_grad():
-                mix_z = backward_map(self.backward_net, backward_input[mix_idxs], d.z_dim, cfg.norm_z)
+                if cfg.rand_weight:   # fb_ddpg.py:475-482: rows of U(0,1) weights, L2-normalised, scaled by one U(0,1) each
+                    weight = F.normalize(torch.rand(size=(mix_idxs.shape[0], cfg.batch_size)), dim=1)
+                    weight = torch.rand(mix_idxs.shape[0], 1) * weight
+                    mix_z = torch.matmul(weight, backward_map(self.backward_net, backward_input, d.z_dim, cfg.norm_z))
+                else:
+                    mix_z = backward_map(self.backward_net, backward_input[mix_idxs], d.z_dim, cfg.norm_z)
             z[mix_idxs] = l2_project(mix_z, d.z_dim) if cfg.norm_z else mix_z
         if cfg.future_ratio > 0:   # hindsight replay (fb_ddpg.py:488-491)
             future_goal = t["future_goal"] if cfg.use_goal else t["future_obs"]

@@ -44,7 +44,7 @@ def make_agent(R: tp.Any, case: tp.Mapping[str, tp.Any], use_tb: bool = True) ->
         backward_hidden_dim=case["backward_hidden_dim"], z_dim=case["z_dim"], batch_size=case["batch_size"],
         future_ratio=case.get("future_ratio", 0.0), q_loss=case.get("q_loss", False),
         q_loss_coef=case.get("q_loss_coef", 0.01), additional_metric=case.get("additional_metric", False),
-        norm_z=case.get("norm_z", True))
+        norm_z=case.get("norm_z", True), rand_weight=case.get("rand_weight", False))
     return R.FBDDPGAgent(**dataclasses.asdict(cfg))
 
 
@@ -270,6 +270,15 @@ def write_qloss_cases(R: tp.Any) -> None:
     print("wrote trajectory_qloss")
 
 
+def write_randw_cases(R: tp.Any) -> None:
+    """rand_weight=True (fb_ddpg.py:475-482): mixed z = random weighted sums of backward_net rows.  With norm_z=True the row scale
+    cancels in the re-projection, so a norm_z=False trajectory pins the scale as well."""
+    for name, extra in (("randw", dict()), ("randw_nonorm", dict(norm_z=False))):
+        case = dict(CASES["small"], rand_weight=True, **extra)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"trajectory_{name}.npz"), **gen_trajectory_case(R, case))
+        print("wrote trajectory_%s" % name)
+
+
 def write_nonorm_cases(R: tp.Any) -> None:
     """norm_z=False (fb_modules.py:227-229, fb_ddpg.py:228-231,483-484): raw backward_net outputs, z = sqrt(Z) U(0,1) (x) direction,
     mixed z not re-projected; the diagonal orthonormality term then reaches the gradients."""
@@ -282,27 +291,28 @@ def write_nonorm_cases(R: tp.Any) -> None:
     print("wrote trajectory_nonorm")
 
 
-def main() -> None:
-    R = ref_shim.load()
-    os.makedirs(GOLDEN_DIR, exist_ok=True)
-    torch.set_num_threads(1)   # single-thread reductions: the most reproducible reference numbers
-    if "--qloss-only" in sys.argv:
-        write_qloss_cases(R)
-        return
-    if "--nonorm-only" in sys.argv:
-        write_nonorm_cases(R)
-        return
-    # hindsight trajectories (future_ratio > 0, fb_ddpg.py:488-491): added after the first fixtures, generated on their own
+def write_hindsight_cases(R: tp.Any) -> None:
+    """hindsight trajectories (future_ratio > 0, fb_ddpg.py:488-491)."""
     for name, base in (("future", "small"), ("future_goal", "goal")):
         case = dict(CASES[base], future_ratio=0.4)
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"trajectory_{name}.npz"), **gen_trajectory_case(R, case))
         print("wrote trajectory_%s" % name)
-    if "--hindsight-only" in sys.argv:
+
+
+# fixture families added after the first ones; `--<name>-only` regenerates one family without touching the others
+LATER_FAMILIES = {"hindsight": write_hindsight_cases, "qloss": write_qloss_cases, "nonorm": write_nonorm_cases, "randw": write_randw_cases}
+
+
+def main() -> None:
+    R = ref_shim.load()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(1)   # single-thread reductions: the most reproducible reference numbers
+    only = [n for n in LATER_FAMILIES if f"--{n}-only" in sys.argv]
+    for name, fn in LATER_FAMILIES.items():
+        if not only or name in only:
+            fn(R)
+    if only:
         return
-    write_qloss_cases(R)
-    if "--qloss-only" in sys.argv:
-        return
-    write_nonorm_cases(R)
     for name, case in CASES.items():
         np.savez_compressed(os.path.join(GOLDEN_DIR, f"update_{name}.npz"), **gen_update_case(R, name, case))
         print("wrote update_%s" % name)

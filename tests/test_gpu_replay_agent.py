@@ -118,16 +118,19 @@ def test_pack_episode_kernel_matches_host_packing():
     assert torch.equal(rows[3], buf._rows[3])
 
 
+SMALL_CASES = ("small", "future", "qloss", "nonorm", "randw", "randw_nonorm")   # fixtures generated from make_golden.CASES["small"]
+
+
 def _agent_for(g, case, **kw):
     from controllable_agent_b200 import FBDDPGAgent
     a, f, b = subtree(g, "param0/actor"), subtree(g, "param0/forward_net"), subtree(g, "param0/backward_net")
     hidden, oa = f["obs_action_net.0.weight"].shape
     obs_dim = a["obs_net.0.weight"].shape[1]
     agent = FBDDPGAgent(obs_type="states", obs_shape=(obs_dim,), action_shape=(oa - obs_dim,), device="cuda", num_expl_steps=0,
-                        update_encoder=True, goal_space=None if case in ("small", "future", "qloss", "nonorm") else "simplified_walker", use_tb=True, use_wandb=False,
+                        update_encoder=True, goal_space=None if case in SMALL_CASES else "simplified_walker", use_tb=True, use_wandb=False,
                         use_hiplog=False, hidden_dim=hidden, feature_dim=f["obs_action_net.3.weight"].shape[0],
                         backward_hidden_dim=b["B.0.weight"].shape[0], z_dim=f["F1.2.weight"].shape[0],
-                        batch_size=32 if case in ("small", "future", "qloss", "nonorm") else 64, update_every_steps=1,
+                        batch_size=32 if case in SMALL_CASES else 64, update_every_steps=1,
                         future_ratio=0.4 if case.startswith("future") else (0.3 if case == "nonorm" else 0.0), **kw)
     for net, src in ((agent.actor, a), (agent.forward_net, f), (agent.backward_net, b), (agent.forward_target_net, f),
                      (agent.backward_target_net, b)):
@@ -136,7 +139,7 @@ def _agent_for(g, case, **kw):
     return agent
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm"])
 @pytest.mark.parametrize("foreign_replay", [False, True])
 def test_agent_update_walks_reference_trajectory(case, foreign_replay):
     """agent.update(replay, step) x3 with the reference's RNG streams (rng_mode=reference, torch draws on the CPU generator
@@ -147,6 +150,8 @@ def test_agent_update_walks_reference_trajectory(case, foreign_replay):
     extra = dict(q_loss=True, q_loss_coef=0.5, additional_metric=True) if case == "qloss" else {}   # fb_ddpg.py:330-341,403-404
     if case == "nonorm":   # norm_z = False with hindsight rows (future_ratio = 0.3)
         extra = dict(norm_z=False)
+    if case.startswith("randw"):   # rand_weight = True (fb_ddpg.py:475-482), with and without the re-projection
+        extra = dict(rand_weight=True, norm_z=case == "randw")
     agent = _agent_for(g, case, rng_mode="reference", **extra)
     agent.draw_device = "cpu"
     eps = [subtree(g, f"ep{i}") for i in range(4)]
@@ -403,12 +408,45 @@ def test_device_rng_with_norm_z_off():
     assert float((zb - mixed.engine.view("B_mix").cpu()[:Bsz]).abs().max()) == 0.0
 
 
+def test_rand_weight_with_device_rng():
+    """rng_mode=device, rand_weight=True, norm_z=False: every row of z is either its random draw or
+    (u_s / |W_s|) sum_t W[s,t] B_mix[t] recomputed here in float64 from the library's own weight block (fb_ddpg.py:475-482)."""
+    from controllable_agent_b200 import FBDDPGAgent, ReplayBuffer
+    torch.manual_seed(6)
+    O_, A_, Z, Bsz = 12, 4, 24, 200
+    kw = dict(obs_type="states", obs_shape=(O_,), action_shape=(A_,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,
+              use_tb=True, use_wandb=False, use_hiplog=False, hidden_dim=64, feature_dim=32, backward_hidden_dim=38, z_dim=Z, batch_size=Bsz,
+              update_every_steps=1, norm_z=False, rand_weight=True, mix_ratio=0.5)
+    rs = np.random.RandomState(1)
+    buf = ReplayBuffer(8, 0.98, 0.99)
+    for _ in range(8):
+        buf.add_episode({"observation": rs.standard_normal((101, O_)), "action": rs.uniform(-1, 1, (101, A_)), "reward": rs.uniform(0, 1, 101),
+                         "discount": np.ones(101)})
+    agent = FBDDPGAgent(**kw)
+    seen = []
+    for step in range(2):
+        m = agent.update(buf, step)
+        assert all(np.isfinite(v) for v in m.values()), m
+        e = agent.engine
+        W, u = e.view("mix_w").cpu().double(), e.view("mix_u").cpu().double()[:, 0]
+        assert 0.0 <= float(W.min()) and float(W.max()) < 1.0 and float(W.mean()) == pytest.approx(0.5, abs=0.01)
+        assert 0.0 <= float(u.min()) and float(u.max()) < 1.0
+        cand = (u / W.norm(dim=1))[:, None] * (W @ e.view("B_mix").cpu().double()[:Bsz])
+        z, zr = e.view("z").cpu().double(), e.view("z_rand").cpu().double()
+        d_mix, d_rand = (z - cand).abs().max(dim=1).values, (z - zr).abs().max(dim=1).values
+        assert float(torch.minimum(d_mix, d_rand).max()) < 1e-5 * max(1.0, float(cand.abs().max()))
+        n_mixed = int((d_mix < d_rand).sum())
+        assert 0.35 * Bsz < n_mixed < 0.65 * Bsz, n_mixed
+        seen.append(W.clone())
+    assert not torch.equal(seen[0], seen[1])   # fresh weights every step
+
+
 def test_unsupported_branches_raise():
     from controllable_agent_b200 import FBDDPGAgent
     base = dict(obs_type="states", obs_shape=(24,), action_shape=(6,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,
                 use_tb=False, use_wandb=False, use_hiplog=False)
     for kw in (dict(boltzmann=True), dict(add_trunk=True), dict(preprocess=False),
-               dict(obs_type="pixels"), dict(rand_weight=True), dict(debug=True)):
+               dict(obs_type="pixels"), dict(debug=True)):
         with pytest.raises(NotImplementedError):
             FBDDPGAgent(**{**base, **kw})
     with pytest.raises(RuntimeError):

@@ -128,7 +128,7 @@ def test_replay_sample_bit_exact(case):
         assert set(batch["meta"].keys()) == {k[5:] for k in ref if k.startswith("meta/")}
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm"])
 def test_full_update_trajectory(case):
     """agent.update(replay, step) x3 with all RNG streams live: the oracle agent walks the
     reference's trajectory from the same parameters and seeds ("future*": hindsight z, future_ratio = 0.4)."""
@@ -144,7 +144,7 @@ def test_full_update_trajectory(case):
     use_goal = "ep0/goal" in g
     agent = O.OracleAgent(O.OracleConfig(dims=d, batch_size=64 if use_goal else 32, use_goal=use_goal,
                                          future_ratio=0.4 if case.startswith("future") else (0.3 if case == "nonorm" else 0.0),
-                                         norm_z=case != "nonorm",
+                                         norm_z=not case.endswith("nonorm"), rand_weight=case.startswith("randw"),
                                          q_loss=case == "qloss", q_loss_coef=0.5, additional_metric=case == "qloss"))
     agent.load_params(actor=a, forward_net=f, backward_net=b, forward_target_net=f, backward_target_net=b)
     buf = O.OracleReplay(4, 0.98, 0.99)
