@@ -63,21 +63,27 @@ def _embed_spec(prefix: str, in_dim: int, d: Dims) -> tp.List[tp.Tuple[str, tp.T
             (f"{prefix}.3.weight", (d.feature_dim, d.hidden_dim)), (f"{prefix}.3.bias", (d.feature_dim,))]
 
 
-def _head_spec(prefix: str, out_dim: int, d: Dims) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
-    """mlp(2*feature, hidden, "irelu", out)  (fb_modules.py:107,183-185)."""
-    return [(f"{prefix}.0.weight", (d.hidden_dim, 2 * d.feature_dim)), (f"{prefix}.0.bias", (d.hidden_dim,)),
+def _head_spec(prefix: str, out_dim: int, d: Dims, add_trunk: bool = False) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
+    """mlp(2*feature, hidden, "irelu", out), or mlp(hidden, hidden, "irelu", out) behind a trunk  (fb_modules.py:96-107,169-185)."""
+    in_dim = d.hidden_dim if add_trunk else 2 * d.feature_dim
+    return [(f"{prefix}.0.weight", (d.hidden_dim, in_dim)), (f"{prefix}.0.bias", (d.hidden_dim,)),
             (f"{prefix}.2.weight", (out_dim, d.hidden_dim)), (f"{prefix}.2.bias", (out_dim,))]
 
 
-def forward_map_spec(d: Dims) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
+def _trunk_spec(d: Dims, add_trunk: bool) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
+    """add_trunk=True: trunk = mlp(2*feature, hidden, "irelu"), registered between the embeds and the heads (fb_modules.py:99-100,172-173)."""
+    return [("trunk.0.weight", (d.hidden_dim, 2 * d.feature_dim)), ("trunk.0.bias", (d.hidden_dim,))] if add_trunk else []
+
+
+def forward_map_spec(d: Dims, add_trunk: bool = False) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
     return (_embed_spec("obs_action_net", d.obs_dim + d.action_dim, d)
-            + _embed_spec("obs_z_net", d.obs_dim + d.z_dim, d)
-            + _head_spec("F1", d.z_dim, d) + _head_spec("F2", d.z_dim, d))
+            + _embed_spec("obs_z_net", d.obs_dim + d.z_dim, d) + _trunk_spec(d, add_trunk)
+            + _head_spec("F1", d.z_dim, d, add_trunk) + _head_spec("F2", d.z_dim, d, add_trunk))
 
 
-def actor_spec(d: Dims) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
-    return (_embed_spec("obs_net", d.obs_dim, d) + _embed_spec("obs_z_net", d.obs_dim + d.z_dim, d)
-            + _head_spec("policy", d.action_dim, d))
+def actor_spec(d: Dims, add_trunk: bool = False) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
+    return (_embed_spec("obs_net", d.obs_dim, d) + _embed_spec("obs_z_net", d.obs_dim + d.z_dim, d) + _trunk_spec(d, add_trunk)
+            + _head_spec("policy", d.action_dim, d, add_trunk))
 
 
 def backward_map_spec(d: Dims) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
@@ -121,19 +127,26 @@ def _head(p: Params, prefix: str, h: Tensor) -> Tensor:
     return F.linear(h, p[f"{prefix}.2.weight"], p[f"{prefix}.2.bias"])
 
 
+def _trunk(p: Params, h: Tensor) -> Tensor:
+    """The optional trunk Linear -> ReLU (add_trunk=True), the identity otherwise (fb_modules.py:96-100,118-119)."""
+    if "trunk.0.weight" in p:
+        return torch.relu(F.linear(h, p["trunk.0.weight"], p["trunk.0.bias"]))
+    return h
+
+
 def forward_map(p: Params, obs: Tensor, z: Tensor, action: Tensor) -> tp.Tuple[Tensor, Tensor]:
-    """ForwardMap.forward, preprocess=True, add_trunk=False (fb_modules.py:187-199)."""
+    """ForwardMap.forward, preprocess=True (fb_modules.py:187-199)."""
     oa = _embed(p, "obs_action_net", torch.cat([obs, action], dim=-1))
     oz = _embed(p, "obs_z_net", torch.cat([obs, z], dim=-1))
-    h = torch.cat([oa, oz], dim=-1)
+    h = _trunk(p, torch.cat([oa, oz], dim=-1))
     return _head(p, "F1", h), _head(p, "F2", h)
 
 
 def actor_mean(p: Params, obs: Tensor, z: Tensor) -> Tensor:
-    """Actor.forward up to mu = tanh(policy(h)) (fb_modules.py:110-122)."""
+    """Actor.forward up to mu = tanh(policy(h)), preprocess=True (fb_modules.py:110-122)."""
     oz = _embed(p, "obs_z_net", torch.cat([obs, z], dim=-1))
     o = _embed(p, "obs_net", obs)
-    return torch.tanh(_head(p, "policy", torch.cat([o, oz], dim=-1)))
+    return torch.tanh(_head(p, "policy", _trunk(p, torch.cat([o, oz], dim=-1))))
 
 
 def l2_project(x: Tensor, z_dim: int) -> Tensor:
@@ -432,6 +445,7 @@ class OracleConfig:
     q_loss: bool = False          # fb_ddpg.py:330-341
     q_loss_coef: float = 0.01
     additional_metric: bool = False   # q1_success (fb_ddpg.py:403-404,416-417)
+    add_trunk: bool = False       # Linear(2 feature -> hidden) + ReLU between the embeds and the heads (fb_modules.py:96-100,169-173)
     rand_weight: bool = False     # mixed z = random convex-like combinations of B rows (fb_ddpg.py:475-482)
     norm_z: bool = True           # sqrt(z_dim)-sphere projection of B's output and of z (fb_modules.py:227-229, fb_ddpg.py:228,483)
 
@@ -445,8 +459,8 @@ class OracleAgent:
     def __init__(self, cfg: OracleConfig, generator: tp.Optional[torch.Generator] = None) -> None:
         self.cfg = cfg
         d = cfg.dims
-        self.actor = init_params(actor_spec(d), generator)
-        self.forward_net = init_params(forward_map_spec(d), generator)
+        self.actor = init_params(actor_spec(d, cfg.add_trunk), generator)
+        self.forward_net = init_params(forward_map_spec(d, cfg.add_trunk), generator)
         self.backward_net = init_params(backward_map_spec(d), generator)
         self.forward_target_net = collections.OrderedDict((k, v.clone()) for k, v in self.forward_net.items())
         self.backward_target_net = collections.OrderedDict((k, v.clone()) for k, v in self.backward_net.items())

@@ -44,7 +44,8 @@ def make_agent(R: tp.Any, case: tp.Mapping[str, tp.Any], use_tb: bool = True) ->
         backward_hidden_dim=case["backward_hidden_dim"], z_dim=case["z_dim"], batch_size=case["batch_size"],
         future_ratio=case.get("future_ratio", 0.0), q_loss=case.get("q_loss", False),
         q_loss_coef=case.get("q_loss_coef", 0.01), additional_metric=case.get("additional_metric", False),
-        norm_z=case.get("norm_z", True), rand_weight=case.get("rand_weight", False))
+        norm_z=case.get("norm_z", True), rand_weight=case.get("rand_weight", False),
+        add_trunk=case.get("add_trunk", False))
     return R.FBDDPGAgent(**dataclasses.asdict(cfg))
 
 
@@ -299,8 +300,19 @@ def write_hindsight_cases(R: tp.Any) -> None:
         print("wrote trajectory_%s" % name)
 
 
+def write_trunk_cases(R: tp.Any) -> None:
+    """add_trunk=True (fb_modules.py:96-100,169-173): a Linear + ReLU trunk between the embeds and the policy / F heads."""
+    for name, base in (("trunk", "small"), ("trunk_goal", "goal")):
+        case = dict(CASES[base], add_trunk=True)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"update_{name}.npz"), **gen_update_case(R, name, case))
+        print("wrote update_%s" % name)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "trajectory_trunk.npz"), **gen_trajectory_case(R, dict(CASES["small"], add_trunk=True)))
+    print("wrote trajectory_trunk")
+
+
 # fixture families added after the first ones; `--<name>-only` regenerates one family without touching the others
-LATER_FAMILIES = {"hindsight": write_hindsight_cases, "qloss": write_qloss_cases, "nonorm": write_nonorm_cases, "randw": write_randw_cases}
+LATER_FAMILIES = {"hindsight": write_hindsight_cases, "qloss": write_qloss_cases, "nonorm": write_nonorm_cases, "randw": write_randw_cases,
+                  "trunk": write_trunk_cases}
 
 
 def main() -> None:

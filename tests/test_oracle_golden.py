@@ -9,7 +9,7 @@ import torch
 from conftest import load_golden, subtree
 from oracle import fb_oracle as O
 
-UPDATE_CASES = ["small", "goal", "wide", "qloss", "qloss_goal", "nonorm", "nonorm_goal"]   # qloss*: q_loss=True (fb_ddpg.py:330-341); nonorm*: norm_z=False
+UPDATE_CASES = ["small", "goal", "wide", "qloss", "qloss_goal", "nonorm", "nonorm_goal", "trunk", "trunk_goal"]   # trunk*: add_trunk=True; qloss*: q_loss=True (fb_ddpg.py:330-341); nonorm*: norm_z=False
 
 
 def dims_from(g):
@@ -36,8 +36,9 @@ def rel(a, b):
 def test_spec_matches_reference_registration_order(case):
     g = load_golden(f"update_{case}")
     d = dims_from(g)
-    for net, spec in (("forward_net", O.forward_map_spec(d)), ("backward_net", O.backward_map_spec(d)),
-                      ("actor", O.actor_spec(d))):
+    trunk = case.startswith("trunk")
+    for net, spec in (("forward_net", O.forward_map_spec(d, trunk)), ("backward_net", O.backward_map_spec(d)),
+                      ("actor", O.actor_spec(d, trunk))):
         ref = subtree(g, f"param0/{net}")
         assert [n for n, _ in spec] == list(ref.keys())
         assert [tuple(s) for _, s in spec] == [v.shape for v in ref.values()]
@@ -128,7 +129,7 @@ def test_replay_sample_bit_exact(case):
         assert set(batch["meta"].keys()) == {k[5:] for k in ref if k.startswith("meta/")}
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm", "trunk"])
 def test_full_update_trajectory(case):
     """agent.update(replay, step) x3 with all RNG streams live: the oracle agent walks the
     reference's trajectory from the same parameters and seeds ("future*": hindsight z, future_ratio = 0.4)."""
@@ -144,7 +145,7 @@ def test_full_update_trajectory(case):
     use_goal = "ep0/goal" in g
     agent = O.OracleAgent(O.OracleConfig(dims=d, batch_size=64 if use_goal else 32, use_goal=use_goal,
                                          future_ratio=0.4 if case.startswith("future") else (0.3 if case == "nonorm" else 0.0),
-                                         norm_z=not case.endswith("nonorm"), rand_weight=case.startswith("randw"),
+                                         norm_z=not case.endswith("nonorm"), rand_weight=case.startswith("randw"), add_trunk=case == "trunk",
                                          q_loss=case == "qloss", q_loss_coef=0.5, additional_metric=case == "qloss"))
     agent.load_params(actor=a, forward_net=f, backward_net=b, forward_target_net=f, backward_target_net=b)
     buf = O.OracleReplay(4, 0.98, 0.99)
