@@ -620,9 +620,11 @@ static int build_plan(fb_handle* h) {
   PSet pB{&h->seg_fb, h->bwd_first, bf.d_param_fb, bf.d_grad_fb};
   PSet pBt{&h->seg_fb, h->bwd_first, bf.d_target_fb, nullptr};
   PSet pA{&h->seg_actor, 0, bf.d_param_actor, bf.d_grad_actor};
-  // sub-blocks: embed = 6 tensors (W0 b0 gamma beta W3 b3), head = 4 tensors (W1 b1 W2 b2)
-  const int E_OA = 0, E_OZ = 6, HD_1 = 12, HD_2 = 16;   // forward net
-  const int A_O = 0, A_OZ = 6, A_POL = 12;              // actor
+  // sub-blocks: embed = 6 tensors (W0 b0 gamma beta W3 b3), [trunk = 2 tensors (W b), cfg.add_trunk], head = 4 tensors (W1 b1 W2 b2)
+  const bool trunk = c.add_trunk != 0;
+  const int T_N = trunk ? 2 : 0;
+  const int E_OA = 0, E_OZ = 6, F_TR = 12, HD_1 = 12 + T_N, HD_2 = 16 + T_N;   // forward net
+  const int A_O = 0, A_OZ = 6, A_TR = 12, A_POL = 12 + T_N;                    // actor
 
   // ---- activations ---------------------------------------------------------------------------
   Mat hA = ws_mat(h, 2 * B, 2 * Fd, "hA");
@@ -637,6 +639,10 @@ static int build_plan(fb_handle* h) {
   EmbedAct eFoz = embed_alloc(h, actor_in_oz.rs(B, B), hF.cs(Fd, Fd), H, "F.obs_z_net");
   EmbedAct eF2oa = embed_alloc(h, in_oa2, hF2.cs(0, Fd), H, "F2.obs_action_net");
   EmbedAct eF2oz = embed_alloc(h, actor_in_oz.rs(B, B), hF2.cs(Fd, Fd), H, "F2.obs_z_net");
+  // add_trunk: ReLU(Linear(2 Fd -> H)) of each concatenated embed pair; the heads then read these instead of hA / hFt / hF / hF2
+  Mat trA, trFt, trF, trF2;
+  if (trunk) { trA = ws_mat(h, 2 * B, H, "actor.trunk"); trFt = ws_mat(h, B, H, "Ft.trunk"); trF = ws_mat(h, B, H, "F.trunk"); trF2 = ws_mat(h, B, H, "F2.trunk"); }
+  const Mat& inFt = trunk ? trFt : hFt; const Mat& inF = trunk ? trF : hF; const Mat& inF2 = trunk ? trF2 : hF2;
   Mat h1A = ws_mat(h, 2 * B, H, "actor.policy.h1");
   Mat preA = ws_mat(h, 2 * B, A, "actor.policy.out");
   Mat h1Ft1 = ws_mat(h, B, H, "Ft.F1.h1"), h1Ft2 = ws_mat(h, B, H, "Ft.F2.h1");
@@ -673,6 +679,8 @@ static int build_plan(fb_handle* h) {
   Mat dh1A = ws_mat(h, B, H, "dh1A");
   Mat dhA = ws_mat(h, B, 2 * Fd, "dhA");
   Mat dy_o = ws_mat(h, B, H, "dy_o"), dy_aoz = ws_mat(h, B, H, "dy_aoz");
+  Mat dtF, dtA;   // add_trunk: gradients w.r.t. the trunk outputs
+  if (trunk) { dtF = ws_mat(h, B, H, "dtF"); dtA = ws_mat(h, B, H, "dtA"); }
 
   Builder b{h, d_arena};
   DevScalars* sc = h->d_sc;
@@ -782,8 +790,14 @@ static int build_plan(fb_handle* h) {
           lin_fwd(eFoa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eFoa.out, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(eFoz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eFoz.out, GF_RELU | GF_RELU_LAZY_OK),
           lin_fwd(eFtoz.y, pFt.w(E_OZ + 4), pFt.v(E_OZ + 5), eFtoz.out, GF_RELU | GF_RELU_LAZY_OK),
           lin_fwd(bO.y, pB.w(4), pB.v(5), bO.h2, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(bT.y, pBt.w(4), pBt.v(5), bT.h2, GF_RELU | GF_RELU_LAZY_OK)});
-  b.gemm({lin_fwd(hA, pA.w(A_POL + 0), pA.v(A_POL + 1), h1A, GF_RELU | GF_RELU_LAZY_OK),
-          lin_fwd(bO.h2, pB.w(6), pB.v(7), bO.raw, 0), lin_fwd(bT.h2, pBt.w(6), pBt.v(7), bT.raw, 0)});
+  if (trunk) {
+    b.gemm({lin_fwd(hA, pA.w(A_TR + 0), pA.v(A_TR + 1), trA, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(hF, pF.w(F_TR + 0), pF.v(F_TR + 1), trF, GF_RELU | GF_RELU_LAZY_OK),
+            lin_fwd(bO.h2, pB.w(6), pB.v(7), bO.raw, 0), lin_fwd(bT.h2, pBt.w(6), pBt.v(7), bT.raw, 0)});
+    b.gemm({lin_fwd(trA, pA.w(A_POL + 0), pA.v(A_POL + 1), h1A, GF_RELU | GF_RELU_LAZY_OK)});
+  } else {
+    b.gemm({lin_fwd(hA, pA.w(A_POL + 0), pA.v(A_POL + 1), h1A, GF_RELU | GF_RELU_LAZY_OK),
+            lin_fwd(bO.h2, pB.w(6), pB.v(7), bO.raw, 0), lin_fwd(bT.h2, pBt.w(6), pBt.v(7), bT.raw, 0)});
+  }
   b.gemm({lin_fwd(h1A, pA.w(A_POL + 2), pA.v(A_POL + 3), preA, 0)});
   b.l2_fwd({b_l2(bO, Z, nz), b_l2(bT, Z, nz)});
   {
@@ -801,8 +815,9 @@ static int build_plan(fb_handle* h) {
   b.gemm({lin_fwd(eFtoa.x, pFt.w(E_OA + 0), pFt.v(E_OA + 1), eFtoa.pre, 0)});
   b.ln_fwd({embed_ln(eFtoa, pFt.sub(E_OA))});
   b.gemm({lin_fwd(eFtoa.y, pFt.w(E_OA + 4), pFt.v(E_OA + 5), eFtoa.out, GF_RELU | GF_RELU_LAZY_OK)});
-  b.gemm({lin_fwd(hFt, pFt.w(HD_1 + 0), pFt.v(HD_1 + 1), h1Ft1, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(hFt, pFt.w(HD_2 + 0), pFt.v(HD_2 + 1), h1Ft2, GF_RELU | GF_RELU_LAZY_OK),
-          lin_fwd(hF, pF.w(HD_1 + 0), pF.v(HD_1 + 1), h1F1, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(hF, pF.w(HD_2 + 0), pF.v(HD_2 + 1), h1F2, GF_RELU | GF_RELU_LAZY_OK)});
+  if (trunk) b.gemm({lin_fwd(hFt, pFt.w(F_TR + 0), pFt.v(F_TR + 1), trFt, GF_RELU | GF_RELU_LAZY_OK)});
+  b.gemm({lin_fwd(inFt, pFt.w(HD_1 + 0), pFt.v(HD_1 + 1), h1Ft1, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(inFt, pFt.w(HD_2 + 0), pFt.v(HD_2 + 1), h1Ft2, GF_RELU | GF_RELU_LAZY_OK),
+          lin_fwd(inF, pF.w(HD_1 + 0), pF.v(HD_1 + 1), h1F1, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(inF, pF.w(HD_2 + 0), pF.v(HD_2 + 1), h1F2, GF_RELU | GF_RELU_LAZY_OK)});
   b.gemm({lin_fwd(h1Ft1, pFt.w(HD_1 + 2), pFt.v(HD_1 + 3), tF1, 0), lin_fwd(h1Ft2, pFt.w(HD_2 + 2), pFt.v(HD_2 + 3), tF2, 0),
           lin_fwd(h1F1, pF.w(HD_1 + 2), pF.v(HD_1 + 3), F1, 0), lin_fwd(h1F2, pF.w(HD_2 + 2), pF.v(HD_2 + 3), F2, 0)});
 
@@ -965,11 +980,16 @@ static int build_plan(fb_handle* h) {
           lin_dx(draw, pB.w(6), dh2, GF_MASK_RELU, &bO.h2)});
   b.colsum({mk_colsum(dh1_1, pF.gv(HD_1 + 1)), mk_colsum(dh1_2, pF.gv(HD_2 + 1)), mk_colsum(dh2, pB.gv(5))});
   {
-    GemmDesc d = lin_dx(dh1_1, pF.w(HD_1 + 0), dhF, GF_MASK_RELU, &hF);
+    // both heads' dX products land in one buffer (K2 = the second head): the gradient of the heads' common input, masked by its ReLU
+    GemmDesc d = lin_dx(dh1_1, pF.w(HD_1 + 0), trunk ? dtF : dhF, GF_MASK_RELU, &inF);
     Mat w2 = pF.w(HD_2 + 0);
     d.A2 = dh1_2.p; d.B2 = w2.p; d.K2 = w2.rows;
-    b.gemm({lin_dw(dh1_1, hF, pF.gw(HD_1 + 0)), lin_dw(dh1_2, hF, pF.gw(HD_2 + 0)), d, lin_dw(dh2, bO.y, pB.gw(4)),
+    b.gemm({lin_dw(dh1_1, inF, pF.gw(HD_1 + 0)), lin_dw(dh1_2, inF, pF.gw(HD_2 + 0)), d, lin_dw(dh2, bO.y, pB.gw(4)),
             lin_dx(dh2, pB.w(4), dy1, 0, nullptr)});
+  }
+  if (trunk) {   // through the trunk: bias / weight gradients, then the gradient of the concatenated embeds
+    b.colsum({mk_colsum(dtF, pF.gv(F_TR + 1))});
+    b.gemm({lin_dw(dtF, hF, pF.gw(F_TR + 0)), lin_dx(dtF, pF.w(F_TR + 0), dhF, GF_MASK_RELU, &hF)});
   }
   Mat dhF_oa = dhF.cs(0, Fd), dhF_oz = dhF.cs(Fd, Fd);
   b.colsum({mk_colsum(dhF_oa, pF.gv(E_OA + 5)), mk_colsum(dhF_oz, pF.gv(E_OZ + 5))});
@@ -1018,7 +1038,8 @@ static int build_plan(fb_handle* h) {
   b.gemm({lin_fwd(eF2oa.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eF2oa.pre, 0), lin_fwd(eF2oz.x, pF.w(E_OZ + 0), pF.v(E_OZ + 1), eF2oz.pre, 0)});
   b.ln_fwd({embed_ln(eF2oa, pF.sub(E_OA)), embed_ln(eF2oz, pF.sub(E_OZ))});
   b.gemm({lin_fwd(eF2oa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eF2oa.out, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(eF2oz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eF2oz.out, GF_RELU | GF_RELU_LAZY_OK)});
-  b.gemm({lin_fwd(hF2, pF.w(HD_1 + 0), pF.v(HD_1 + 1), h1Fa1, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(hF2, pF.w(HD_2 + 0), pF.v(HD_2 + 1), h1Fa2, GF_RELU | GF_RELU_LAZY_OK)});
+  if (trunk) b.gemm({lin_fwd(hF2, pF.w(F_TR + 0), pF.v(F_TR + 1), trF2, GF_RELU | GF_RELU_LAZY_OK)});
+  b.gemm({lin_fwd(inF2, pF.w(HD_1 + 0), pF.v(HD_1 + 1), h1Fa1, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(inF2, pF.w(HD_2 + 0), pF.v(HD_2 + 1), h1Fa2, GF_RELU | GF_RELU_LAZY_OK)});
   b.gemm({lin_fwd(h1Fa1, pF.w(HD_1 + 2), pF.v(HD_1 + 3), Fa1, 0), lin_fwd(h1Fa2, pF.w(HD_2 + 2), pF.v(HD_2 + 3), Fa2, 0)});
   {
     const float inv_n = 1.0f / (float)n;
@@ -1034,10 +1055,18 @@ static int build_plan(fb_handle* h) {
   b.gemm({lin_dx(dFa1, pF.w(HD_1 + 2), dh1_1, GF_MASK_RELU, &h1Fa1), lin_dx(dFa2, pF.w(HD_2 + 2), dh1_2, GF_MASK_RELU, &h1Fa2)});
   {
     Mat hF2oa = hF2.cs(0, Fd);
-    GemmDesc d = lin_dx(dh1_1, pF.w(HD_1 + 0).cs(0, Fd), dhoa, GF_MASK_RELU, &hF2oa);
-    Mat w2 = pF.w(HD_2 + 0).cs(0, Fd);
-    d.A2 = dh1_2.p; d.B2 = w2.p; d.K2 = w2.rows;
-    b.gemm({d});
+    if (trunk) {   // heads -> trunk output (full width), then the obs_action half of the trunk's input
+      GemmDesc d = lin_dx(dh1_1, pF.w(HD_1 + 0), dtF, GF_MASK_RELU, &trF2);
+      Mat w2 = pF.w(HD_2 + 0);
+      d.A2 = dh1_2.p; d.B2 = w2.p; d.K2 = w2.rows;
+      b.gemm({d});
+      b.gemm({lin_dx(dtF, pF.w(F_TR + 0).cs(0, Fd), dhoa, GF_MASK_RELU, &hF2oa)});
+    } else {
+      GemmDesc d = lin_dx(dh1_1, pF.w(HD_1 + 0).cs(0, Fd), dhoa, GF_MASK_RELU, &hF2oa);
+      Mat w2 = pF.w(HD_2 + 0).cs(0, Fd);
+      d.A2 = dh1_2.p; d.B2 = w2.p; d.K2 = w2.rows;
+      b.gemm({d});
+    }
   }
   b.gemm({lin_dx(dhoa, pF.w(E_OA + 4), dy_oa, 0, nullptr)});
   b.ln_bwd({embed_ln_bwd(eF2oa, pF.sub(E_OA), dy_oa, 0, false)});
@@ -1049,7 +1078,14 @@ static int build_plan(fb_handle* h) {
   b.colsum({mk_colsum(dpreA, pA.gv(A_POL + 3))});
   b.gemm({lin_dw(dpreA, h1A_o, pA.gw(A_POL + 2)), lin_dx(dpreA, pA.w(A_POL + 2), dh1A, GF_MASK_RELU, &h1A_o)});
   b.colsum({mk_colsum(dh1A, pA.gv(A_POL + 1))});
-  b.gemm({lin_dw(dh1A, hA_o, pA.gw(A_POL + 0)), lin_dx(dh1A, pA.w(A_POL + 0), dhA, GF_MASK_RELU, &hA_o)});
+  if (trunk) {
+    Mat tA_o = trA.rs(B, B);
+    b.gemm({lin_dw(dh1A, tA_o, pA.gw(A_POL + 0)), lin_dx(dh1A, pA.w(A_POL + 0), dtA, GF_MASK_RELU, &tA_o)});
+    b.colsum({mk_colsum(dtA, pA.gv(A_TR + 1))});
+    b.gemm({lin_dw(dtA, hA_o, pA.gw(A_TR + 0)), lin_dx(dtA, pA.w(A_TR + 0), dhA, GF_MASK_RELU, &hA_o)});
+  } else {
+    b.gemm({lin_dw(dh1A, hA_o, pA.gw(A_POL + 0)), lin_dx(dh1A, pA.w(A_POL + 0), dhA, GF_MASK_RELU, &hA_o)});
+  }
   Mat dhA_o = dhA.cs(0, Fd), dhA_oz = dhA.cs(Fd, Fd);
   b.colsum({mk_colsum(dhA_o, pA.gv(A_O + 5)), mk_colsum(dhA_oz, pA.gv(A_OZ + 5))});
   b.gemm({lin_dw(dhA_o, eAo.y.rs(B, B), pA.gw(A_O + 4)), lin_dw(dhA_oz, eAoz.y.rs(B, B), pA.gw(A_OZ + 4)),
@@ -1116,7 +1152,13 @@ static int build_plan(fb_handle* h) {
     b.gemm({lin_fwd(eo.x, pA.w(A_O + 0), pA.v(A_O + 1), eo.pre, 0), lin_fwd(eoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eoz.pre, 0)});
     b.ln_fwd({embed_ln(eo, pA.sub(A_O)), embed_ln(eoz, pA.sub(A_OZ))});
     b.gemm({lin_fwd(eo.y, pA.w(A_O + 4), pA.v(A_O + 5), eo.out, GF_RELU), lin_fwd(eoz.y, pA.w(A_OZ + 4), pA.v(A_OZ + 5), eoz.out, GF_RELU)});
-    b.gemm({lin_fwd(ihA, pA.w(A_POL + 0), pA.v(A_POL + 1), ih1, GF_RELU)});
+    if (trunk) {
+      Mat ihT = ws_mat(h, R, H, "infer_trunk");
+      b.gemm({lin_fwd(ihA, pA.w(A_TR + 0), pA.v(A_TR + 1), ihT, GF_RELU)});
+      b.gemm({lin_fwd(ihT, pA.w(A_POL + 0), pA.v(A_POL + 1), ih1, GF_RELU)});
+    } else {
+      b.gemm({lin_fwd(ihA, pA.w(A_POL + 0), pA.v(A_POL + 1), ih1, GF_RELU)});
+    }
     b.gemm({lin_fwd(ih1, pA.w(A_POL + 2), pA.v(A_POL + 3), ipre, 0)});
     b.push([=](cudaStream_t s) {
       fb_launch_pdl(k_infer_tanh, dim3(fb_ceil_div(R * A, 128)), dim3(128), 0, s, ipre.p, imu.p, ipre.ld, R, A);

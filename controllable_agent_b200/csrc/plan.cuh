@@ -122,8 +122,8 @@ static void add_embed(SegmentLayout& s, const std::string& p, int in_dim, int H,
   s.add(p + ".1.weight", H, 0); s.add(p + ".1.bias", H, 0);
   s.add(p + ".3.weight", Fd, H); s.add(p + ".3.bias", Fd, 0);
 }
-static void add_head(SegmentLayout& s, const std::string& p, int Fd, int H, int out) {
-  s.add(p + ".0.weight", H, 2 * Fd); s.add(p + ".0.bias", H, 0);
+static void add_head(SegmentLayout& s, const std::string& p, int in_dim, int H, int out) {
+  s.add(p + ".0.weight", H, in_dim); s.add(p + ".0.bias", H, 0);
   s.add(p + ".2.weight", out, H); s.add(p + ".2.bias", out, 0);
 }
 static void build_layout(fb_handle* h) {
@@ -133,8 +133,10 @@ static void build_layout(fb_handle* h) {
   h->fwd_first = 0;
   add_embed(f, "obs_action_net", O + A, H, Fd);
   add_embed(f, "obs_z_net", O + Z, H, Fd);
-  add_head(f, "F1", Fd, H, Z);
-  add_head(f, "F2", Fd, H, Z);
+  const int head_in = c.add_trunk ? H : 2 * Fd;   // add_trunk: trunk = Linear(2 Fd -> H) + ReLU in front of the heads
+  if (c.add_trunk) { f.add("trunk.0.weight", H, 2 * Fd); f.add("trunk.0.bias", H, 0); }
+  add_head(f, "F1", head_in, H, Z);
+  add_head(f, "F2", head_in, H, Z);
   h->bwd_first = (int)f.t.size();
   h->bwd_offset = f.size;
   f.add("B.0.weight", Hb, G); f.add("B.0.bias", Hb, 0); f.add("B.1.weight", Hb, 0); f.add("B.1.bias", Hb, 0);
@@ -142,7 +144,8 @@ static void build_layout(fb_handle* h) {
   SegmentLayout& a = h->seg_actor;
   add_embed(a, "obs_net", O, H, Fd);
   add_embed(a, "obs_z_net", O + Z, H, Fd);
-  add_head(a, "policy", Fd, H, A);
+  if (c.add_trunk) { a.add("trunk.0.weight", H, 2 * Fd); a.add("trunk.0.bias", H, 0); }
+  add_head(a, "policy", head_in, H, A);
 }
 
 // a parameter set: values + (optional) gradient buffer sharing one layout

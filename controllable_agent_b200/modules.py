@@ -101,15 +101,15 @@ def mlp(*layers: tp.Union[int, str]) -> nn.Sequential:
 
 
 class Actor(nn.Module):
-    """fb_modules.Actor with preprocess=True, add_trunk=False (fb_modules.py:81-126)."""
+    """fb_modules.Actor with preprocess=True (fb_modules.py:81-126)."""
 
-    def __init__(self, obs_dim: int, z_dim: int, action_dim: int, feature_dim: int, hidden_dim: int) -> None:
+    def __init__(self, obs_dim: int, z_dim: int, action_dim: int, feature_dim: int, hidden_dim: int, add_trunk: bool = False) -> None:
         super().__init__()
         self.obs_dim, self.z_dim, self.action_dim = obs_dim, z_dim, action_dim
         self.obs_net = mlp(obs_dim, hidden_dim, "ntanh", feature_dim, "irelu")
         self.obs_z_net = mlp(obs_dim + z_dim, hidden_dim, "ntanh", feature_dim, "irelu")
-        self.trunk: nn.Module = nn.Identity()
-        self.policy = mlp(2 * feature_dim, hidden_dim, "irelu", action_dim)
+        self.trunk: nn.Module = mlp(2 * feature_dim, hidden_dim, "irelu") if add_trunk else nn.Identity()
+        self.policy = mlp(hidden_dim if add_trunk else 2 * feature_dim, hidden_dim, "irelu", action_dim)
         self.apply(weight_init)
 
     def forward(self, obs: torch.Tensor, z: torch.Tensor, std: float) -> TruncatedNormal:
@@ -121,16 +121,17 @@ class Actor(nn.Module):
 
 
 class ForwardMap(nn.Module):
-    """fb_modules.ForwardMap with preprocess=True, add_trunk=False (fb_modules.py:154-199)."""
+    """fb_modules.ForwardMap with preprocess=True (fb_modules.py:154-199)."""
 
-    def __init__(self, obs_dim: int, z_dim: int, action_dim: int, feature_dim: int, hidden_dim: int) -> None:
+    def __init__(self, obs_dim: int, z_dim: int, action_dim: int, feature_dim: int, hidden_dim: int, add_trunk: bool = False) -> None:
         super().__init__()
         self.obs_dim, self.z_dim, self.action_dim = obs_dim, z_dim, action_dim
         self.obs_action_net = mlp(obs_dim + action_dim, hidden_dim, "ntanh", feature_dim, "irelu")
         self.obs_z_net = mlp(obs_dim + z_dim, hidden_dim, "ntanh", feature_dim, "irelu")
-        self.trunk: nn.Module = nn.Identity()
-        self.F1 = mlp(2 * feature_dim, hidden_dim, "irelu", z_dim)
-        self.F2 = mlp(2 * feature_dim, hidden_dim, "irelu", z_dim)
+        self.trunk: nn.Module = mlp(2 * feature_dim, hidden_dim, "irelu") if add_trunk else nn.Identity()
+        head_in = hidden_dim if add_trunk else 2 * feature_dim
+        self.F1 = mlp(head_in, hidden_dim, "irelu", z_dim)
+        self.F2 = mlp(head_in, hidden_dim, "irelu", z_dim)
         self.apply(weight_init)
 
     def forward(self, obs: torch.Tensor, z: torch.Tensor, action: torch.Tensor) -> tp.Tuple[torch.Tensor, torch.Tensor]:

@@ -122,6 +122,10 @@ typedef struct fb_config {
                                   backward_net(backward_input[perm]) (weights U(0,1), rows L2-normalised, scaled by one U(0,1) each)
                                   instead of single rows; z_dim <= 128.  rng_device = 0: the caller uploads the weights
                                   (fb_set_mix_weights) */
+  int32_t add_trunk;           /* cfg.add_trunk (fb_modules.py:96-100,169-173): Actor and ForwardMap get a trunk Linear(2 feature_dim ->
+                                  hidden_dim) + ReLU between the embeds and the policy / F1 / F2 heads (whose first layer then reads
+                                  hidden_dim columns); tensors "trunk.0.weight", "trunk.0.bias" sit between the embeds and the heads */
+  int32_t reserved0;           /* 0 */
 } fb_config;
 
 /* per-step scalars (host values; copied to the device by fb_set_step_scalars) */

@@ -36,7 +36,9 @@ def _create(L, lib, d, batch=64, **kw):
     c = L.fb_config(abi_version=L.FB_ABI_VERSION, batch=batch, global_batch=kw.get("global_batch", batch), row_offset=kw.get("row_offset", 0),
                     obs_dim=d.obs_dim, action_dim=d.action_dim, z_dim=d.z_dim, goal_dim=d.goal_dim, hidden_dim=d.hidden_dim,
                     feature_dim=d.feature_dim, backward_hidden_dim=d.backward_hidden_dim, use_goal=kw.get("use_goal", 0), rng_device=0, contract_mode=kw.get("contract_mode", 0), mlp_mode=kw.get("mlp_mode", 0),
-                    ortho_coef=1.0, mix_ratio=0.5, beta1=0.9, beta2=0.999, adam_eps=1e-8, seed=0)
+                    ortho_coef=1.0, mix_ratio=kw.get("mix_ratio", 0.5), beta1=0.9, beta2=0.999, adam_eps=1e-8, seed=0,
+                    future_ratio=kw.get("future_ratio", 0.0), q_loss=kw.get("q_loss", 0), q_loss_coef=0.01, no_norm_z=kw.get("no_norm_z", 0),
+                    rand_weight=kw.get("rand_weight", 0), add_trunk=kw.get("add_trunk", 0))
     h = C.c_void_p()
     return lib.fb_create(C.byref(c), C.byref(h)), h
 
@@ -70,6 +72,32 @@ def test_flat_layout_matches_reference_registration_order(d):
     assert last[1] + int(np.prod(last[2])) <= n_fb
     assert lib.fb_workspace_bytes(h) > 0
     lib.fb_destroy(h)
+
+
+@pytest.mark.parametrize("d", [O.Dims(), O.Dims(obs_dim=11, action_dim=3, z_dim=10, goal_dim=11, hidden_dim=48, feature_dim=24, backward_hidden_dim=30)])
+def test_add_trunk_layout_and_optional_branch_plans(d):
+    """cfg.add_trunk (fb_modules.py:96-100,169-173): trunk tensors sit between the embeds and the heads, whose first layer then
+    reads hidden_dim columns.  fb_create runs the whole plan builder (sizing pass), so every combination of the optional branches
+    (q_loss, norm_z off, rand_weight, add_trunk, hindsight) must at least plan on both GEMM paths."""
+    L, lib = _lib()
+    rc, h = _create(L, lib, d, add_trunk=1)
+    assert rc == 0
+    for net, spec in ((L.NET_FORWARD, O.forward_map_spec(d, True)), (L.NET_BACKWARD, O.backward_map_spec(d)), (L.NET_ACTOR, O.actor_spec(d, True))):
+        assert [(n, s) for n, _, s in _table(lib, h, net)] == [(n, tuple(s)) for n, s in spec]
+    base_ws = lib.fb_workspace_bytes(h)
+    lib.fb_destroy(h)
+    rc, h = _create(L, lib, d)
+    assert rc == 0 and lib.fb_workspace_bytes(h) < base_ws   # the trunk activations cost workspace
+    lib.fb_destroy(h)
+    for bits in range(32):
+        kw = dict(q_loss=bits & 1, no_norm_z=(bits >> 1) & 1, rand_weight=(bits >> 2) & 1, add_trunk=(bits >> 3) & 1,
+                  future_ratio=0.3 if bits & 16 else 0.0)
+        for mlp_mode in (0, 1):
+            rc, h = _create(L, lib, d, mlp_mode=mlp_mode, contract_mode=mlp_mode, **kw)
+            assert rc == 0, (kw, mlp_mode)
+            lib.fb_destroy(h)
+    assert _create(L, lib, dataclasses.replace(d, z_dim=119, obs_dim=d.obs_dim), q_loss=1)[0] == -3      # the fp64 inverse lives in shared memory
+    assert _create(L, lib, dataclasses.replace(d, z_dim=129), rand_weight=1)[0] == -3
 
 
 def test_default_layout_parameter_counts():

@@ -118,7 +118,7 @@ def test_pack_episode_kernel_matches_host_packing():
     assert torch.equal(rows[3], buf._rows[3])
 
 
-SMALL_CASES = ("small", "future", "qloss", "nonorm", "randw", "randw_nonorm")   # fixtures generated from make_golden.CASES["small"]
+SMALL_CASES = ("small", "future", "qloss", "nonorm", "randw", "randw_nonorm", "trunk")   # fixtures generated from make_golden.CASES["small"]
 
 
 def _agent_for(g, case, **kw):
@@ -139,7 +139,7 @@ def _agent_for(g, case, **kw):
     return agent
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm", "trunk"])
 @pytest.mark.parametrize("foreign_replay", [False, True])
 def test_agent_update_walks_reference_trajectory(case, foreign_replay):
     """agent.update(replay, step) x3 with the reference's RNG streams (rng_mode=reference, torch draws on the CPU generator
@@ -152,6 +152,8 @@ def test_agent_update_walks_reference_trajectory(case, foreign_replay):
         extra = dict(norm_z=False)
     if case.startswith("randw"):   # rand_weight = True (fb_ddpg.py:475-482), with and without the re-projection
         extra = dict(rand_weight=True, norm_z=case == "randw")
+    if case == "trunk":   # add_trunk = True (fb_modules.py:96-100,169-173)
+        extra = dict(add_trunk=True)
     agent = _agent_for(g, case, rng_mode="reference", **extra)
     agent.draw_device = "cpu"
     eps = [subtree(g, f"ep{i}") for i in range(4)]
@@ -333,8 +335,8 @@ def test_agent_host_replay_with_device_rng():
         assert agent.engine.launch_count(L.PHASE_ALL | L.RUN_HOST_BATCH) == agent.engine.launch_count(L.PHASE_ALL) - 1
 
 
-@pytest.mark.parametrize("goal_space,G", [(None, 24), ("simplified_walker", 3)])
-def test_inference_plans_match_the_module_forward(goal_space, G):
+@pytest.mark.parametrize("goal_space,G,add_trunk", [(None, 24, False), ("simplified_walker", 3, False), (None, 24, True)])
+def test_inference_plans_match_the_module_forward(goal_space, G, add_trunk):
     """act / get_goal_meta / compute_z_correl / infer_meta_from_obs_and_rewards run through the library's inference plans
     (FB_PHASE_INFER_*); checked against the same networks evaluated by the parameter-view nn.Modules (modules.py mirrors
     fb_modules.py; pinned against the oracle in test_cpu_boundary.py), at the reference's default widths."""
@@ -344,7 +346,8 @@ def test_inference_plans_match_the_module_forward(goal_space, G):
     torch.manual_seed(9)
     O_, A_, Z = 24, 6, 50
     agent = FBDDPGAgent(obs_type="states", obs_shape=(O_,), action_shape=(A_,), device="cuda", num_expl_steps=0, update_encoder=True,
-                        goal_space=goal_space, use_tb=False, use_wandb=False, use_hiplog=False, batch_size=256, num_inference_steps=600)
+                        goal_space=goal_space, use_tb=False, use_wandb=False, use_hiplog=False, batch_size=256, num_inference_steps=600,
+                        add_trunk=add_trunk)
     for p in list(agent.actor.parameters()) + list(agent.backward_net.parameters()):   # biases / LN affine away from their init
         if p.dim() == 1:
             p.data.add_(0.1 * torch.randn_like(p))
@@ -445,7 +448,7 @@ def test_unsupported_branches_raise():
     from controllable_agent_b200 import FBDDPGAgent
     base = dict(obs_type="states", obs_shape=(24,), action_shape=(6,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,
                 use_tb=False, use_wandb=False, use_hiplog=False)
-    for kw in (dict(boltzmann=True), dict(add_trunk=True), dict(preprocess=False),
+    for kw in (dict(boltzmann=True), dict(preprocess=False),
                dict(obs_type="pixels"), dict(debug=True)):
         with pytest.raises(NotImplementedError):
             FBDDPGAgent(**{**base, **kw})

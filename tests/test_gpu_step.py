@@ -99,7 +99,8 @@ def _run_update_case(g, d, use_goal, graph, mlp_mode=0):
     B = t["obs"].shape[0]
     eng = make_engine(d, B, use_goal=use_goal, mix_ratio=0.5, ortho_coef=float(g["cfg/ortho_coef"]), mlp_mode=mlp_mode,
                       q_loss_coef=float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None,
-                      norm_z=bool(g["cfg/norm_z"]) if "cfg/norm_z" in g else True)
+                      norm_z=bool(g["cfg/norm_z"]) if "cfg/norm_z" in g else True,
+                      add_trunk="param0/actor/trunk.0.weight" in g)
     load_params(eng, fwd=subtree(g, "param0/forward_net"), bwd=subtree(g, "param0/backward_net"),
                 actor=subtree(g, "param0/actor"), fwd_tgt=subtree(g, "param0/forward_target_net"),
                 bwd_tgt=subtree(g, "param0/backward_target_net"))
@@ -112,8 +113,8 @@ def _run_update_case(g, d, use_goal, graph, mlp_mode=0):
     return eng, t, L
 
 
-# qloss*: cfg.q_loss (fb_ddpg.py:330-341); nonorm*: cfg.norm_z = False (fb_modules.py:227-229)
-@pytest.mark.parametrize("case", ["small", "goal", "wide", "qloss", "qloss_goal", "nonorm", "nonorm_goal"])
+# qloss*: cfg.q_loss (fb_ddpg.py:330-341); nonorm*: cfg.norm_z = False (fb_modules.py:227-229); trunk*: cfg.add_trunk (fb_modules.py:96-100)
+@pytest.mark.parametrize("case", ["small", "goal", "wide", "qloss", "qloss_goal", "nonorm", "nonorm_goal", "trunk", "trunk_goal"])
 @pytest.mark.parametrize("graph,mlp_mode", [(False, 0), (True, 0), (True, 1)])
 def test_update_matches_reference_golden(case, graph, mlp_mode):
     g = load_golden(f"update_{case}")
@@ -151,8 +152,13 @@ def test_update_matches_reference_golden(case, graph, mlp_mode):
     torch.cuda.synchronize()
     for net, key in ((L.NET_FORWARD, "forward_net"), (L.NET_BACKWARD, "backward_net")):
         got = read_tensors(eng, net, "param")
+        gref = subtree(g, f"grad_fb/{key}")
         for name, ref in subtree(g, f"param1/{key}").items():
-            assert np.abs(got[name].numpy() - ref).max() < 2e-5, (key, name)   # |dp| = lr = 1e-4 on step 1
+            # |dp| = lr = 1e-4 on step 1, in the direction of sign(g): an element whose gradient is ~0 next to the tensor's
+            # scale may take the other sign (2 lr apart); everything else sits within rounding
+            diff = np.abs(got[name].numpy() - ref)
+            flipped = diff >= 2e-5
+            assert diff.max() < 2.1e-4 and np.all(np.abs(gref[name][flipped]) <= 1e-4 * np.abs(gref[name]).max()), (key, name, diff.max())
         got = read_tensors(eng, net, "target")
         for name, ref in subtree(g, f"param1/{key.replace('_net', '_target_net')}").items():
             assert np.abs(got[name].numpy() - ref).max() < 1e-5, (key, name)
@@ -422,3 +428,49 @@ def test_sharded_step_sums_to_single_gpu_step(world, contract_mode, q_coef):
     assert sum(e.read_metrics()["actor_loss"] for e in shards) == pytest.approx(full.read_metrics()["actor_loss"], rel=1e-4, abs=1e-6)
     for e in shards + [full]:
         e.close()
+
+
+def test_add_trunk_wide_tcgen05_against_simt_and_oracle():
+    """cfg.add_trunk at widths where the tensor-core plan splits K (lazy-ReLU trunk outputs): the tcgen05 step, the fp32 SIMT step
+    and the fp32 oracle agree on losses and on every gradient tensor.  (Runs last: its tolerance is the only one not pinned by a
+    reference-generated fixture.)"""
+    L = _L()
+    d = O.Dims(obs_dim=24, action_dim=6, z_dim=50, goal_dim=24, hidden_dim=256, feature_dim=128, backward_hidden_dim=134)
+    B = 128
+    gen = torch.Generator().manual_seed(21)
+    actor = O.init_params(O.actor_spec(d, True), gen)
+    fwd = O.init_params(O.forward_map_spec(d, True), gen)
+    bwd = O.init_params(O.backward_map_spec(d), gen)
+    fwd_t = {k: v + 0.05 * torch.randn(v.shape, generator=gen) for k, v in fwd.items()}
+    bwd_t = {k: v + 0.05 * torch.randn(v.shape, generator=gen) for k, v in bwd.items()}
+    obs, next_obs = torch.randn(B, d.obs_dim, generator=gen), torch.randn(B, d.obs_dim, generator=gen)
+    action = torch.rand(B, d.action_dim, generator=gen) * 2 - 1
+    discount = torch.full((B, 1), 0.98)
+    z = O.sample_z(B, d.z_dim, gen)
+    nf, na = torch.randn(B, d.action_dim, generator=gen), torch.randn(B, d.action_dim, generator=gen)
+    ora = O.fb_loss_and_grads(fwd, bwd, fwd_t, bwd_t, actor, obs, action, discount, next_obs, next_obs, z, nf, 0.2, 0.3, 1.0, d.z_dim)
+    ora_a = O.actor_loss_and_grads(actor, fwd, obs, z, na, 0.2, 0.3)
+    got = {}
+    for mode in (L.MLP_TCGEN05, L.MLP_SIMT):
+        eng = make_engine(d, B, mix_ratio=0.0, mlp_mode=mode, add_trunk=True)
+        load_params(eng, fwd=fwd, bwd=bwd, actor=actor, fwd_tgt=fwd_t, bwd_tgt=bwd_t)
+        eng.set_scalars(0.2, 0.3, 1e-4, 1e-4, 1e-4, 0.01)
+        eng.set_batch(obs, action, discount, next_obs)
+        eng.set_z(z)
+        eng.set_noise(nf, na)
+        # no Adam in between: update_actor then sees the forward_net the oracle was given
+        eng.run(L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD | L.PHASE_ACTOR_FWD | L.PHASE_ACTOR_BWD | L.PHASE_METRICS, graph=True)
+        torch.cuda.synchronize()
+        got[mode] = (eng.read_metrics(), read_tensors(eng, L.NET_FORWARD, "grad"), read_tensors(eng, L.NET_BACKWARD, "grad"),
+                     read_tensors(eng, L.NET_ACTOR, "grad"))
+        eng.close()
+    for mode, (m, gf, gb, ga) in got.items():
+        assert m["fb_loss"] == pytest.approx(ora["metrics"]["fb_loss"], rel=REL_TOL), mode
+        assert m["actor_loss"] == pytest.approx(float(ora_a["actor_loss"]), rel=REL_TOL, abs=1e-5), mode
+        for mine, refs in ((gf, ora["grads_forward"]), (gb, ora["grads_backward"]), (ga, ora_a["grads_actor"])):
+            assert list(mine) == list(refs)
+            for name, ref in refs.items():
+                assert rel(mine[name], ref) < 3e-3, (mode, name, rel(mine[name], ref))
+    for a, b_ in zip(got[L.MLP_TCGEN05][1:], got[L.MLP_SIMT][1:]):
+        for name in a:
+            assert rel(a[name], b_[name]) < 3e-3, name
