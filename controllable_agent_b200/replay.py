@@ -89,6 +89,13 @@ class EpisodeBatch(tp.Generic[T]):
         return dataclasses.replace(self, reward=reward)
 
 
+def load_episode(fn: tp.Any) -> tp.Dict[str, np.ndarray]:
+    """url_benchmark.replay_buffer.load_episode (replay_buffer.py:119-123): one `.npz` file = one episode, field -> `[len+1, ...]`."""
+    with open(fn, "rb") as f:
+        data = np.load(f)
+        return {k: data[k] for k in data.keys()}
+
+
 def _round4(x: int) -> int:
     return (x + 3) // 4 * 4
 
@@ -417,6 +424,22 @@ class ReplayBuffer:
             if with_physics:
                 batch = dataclasses.replace(batch, _physics=torch.as_tensor(phy, device=self.device))
         return batch
+
+    def load(self, env: tp.Any, replay_dir: tp.Any, relabel: bool = True, goal_func: tp.Any = None) -> None:
+        """in_memory_replay_buffer.py:192-208: fill the buffer from a directory of per-episode `.npz` files (sorted by name) until it
+        is full.  Episodes are committed through add_episode(), so — unlike the reference, which leaves `_episodes_length` at 0 after
+        load() — the lengths, the fixed-length flag and `avg_episode_length` are correct afterwards.
+        `relabel=True` recomputes rewards (and goals) with the reference's own relabel_episode (replay_buffer.py), which needs
+        `env.physics` (dm_control) and therefore the reference package."""
+        import pathlib
+        for eps_fn in sorted(pathlib.Path(replay_dir).glob("*.npz")):
+            if self._full:
+                break
+            episode = load_episode(eps_fn)
+            if relabel:
+                from url_benchmark.replay_buffer import relabel_episode   # MuJoCo state replay: stays on the host, untouched
+                episode = relabel_episode(env, episode, goal_func)
+            self.add_episode(episode)
 
     def relabel(self, custom_reward: tp.Any) -> None:
         """in_memory_replay_buffer.py:210-216: recompute rewards from stored physics (host loop, as in the reference)."""

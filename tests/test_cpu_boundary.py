@@ -220,3 +220,28 @@ def test_seeded_init_reproduces_reference_parameters(case, dims, seed):
         for name, p in net.named_parameters():
             if p.dim() == 2:   # the fixture perturbs only 1-D tensors of the online nets
                 np.testing.assert_allclose(p.detach().numpy(), g[f"param0/{key}/{name}"], rtol=0, atol=2e-5, err_msg=f"{key}/{name}")
+
+
+def test_replay_load_reads_episode_files_in_order_until_full(tmp_path):
+    """ReplayBuffer.load (in_memory_replay_buffer.py:192-208): sorted `.npz` episodes, stop when the buffer is full.  The device
+    commit (add_episode) is GPU-tested; here it is replaced by a recorder that keeps the reference's ring bookkeeping."""
+    from controllable_agent_b200.replay import ReplayBuffer, load_episode
+
+    class Recorder(ReplayBuffer):
+        def add_episode(self, episode):
+            self.seen = getattr(self, "seen", []) + [episode]
+            self._idx = (self._idx + 1) % self._max_episodes
+            self._full = self._full or self._idx == 0
+
+    rs = np.random.RandomState(0)
+    for i in (3, 1, 2, 0, 4):
+        np.savez(tmp_path / f"episode_{i:03d}.npz", observation=rs.standard_normal((6, 5)).astype(np.float32) + i,
+                 action=np.full((6, 2), i, np.float32), reward=np.zeros((6, 1), np.float32), discount=np.ones((6, 1), np.float32))
+    ep = load_episode(tmp_path / "episode_002.npz")
+    assert set(ep) == {"observation", "action", "reward", "discount"} and ep["action"][0, 0] == 2
+    buf = Recorder(max_episodes=4, discount=0.98, future=0.99)
+    buf.load(None, tmp_path, relabel=False)
+    assert [int(e["action"][0, 0]) for e in buf.seen] == [0, 1, 2, 3] and buf._full      # the fifth file is not read: buffer full
+    big = Recorder(max_episodes=8, discount=0.98, future=0.99)
+    big.load(None, str(tmp_path), relabel=False)
+    assert len(big.seen) == 5 and not big._full and len(big) == 5
