@@ -75,13 +75,32 @@ def _trunk_spec(d: Dims, add_trunk: bool) -> tp.List[tp.Tuple[str, tp.Tuple[int,
     return [("trunk.0.weight", (d.hidden_dim, 2 * d.feature_dim)), ("trunk.0.bias", (d.hidden_dim,))] if add_trunk else []
 
 
-def forward_map_spec(d: Dims, add_trunk: bool = False) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
+def _deep_trunk_spec(in_dim: int, d: Dims) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
+    """preprocess=False: trunk = mlp(in, hidden, "ntanh", hidden, "irelu", hidden, "irelu")  (fb_modules.py:102-104,175-177)."""
+    h = d.hidden_dim
+    return [("trunk.0.weight", (h, in_dim)), ("trunk.0.bias", (h,)), ("trunk.1.weight", (h,)), ("trunk.1.bias", (h,)),
+            ("trunk.3.weight", (h, h)), ("trunk.3.bias", (h,)), ("trunk.5.weight", (h, h)), ("trunk.5.bias", (h,))]
+
+
+def forward_map_spec(d: Dims, add_trunk: bool = False, preprocess: bool = True) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
+    if not preprocess:
+        return (_deep_trunk_spec(d.obs_dim + d.z_dim + d.action_dim, d)
+                + _head_spec("F1", d.z_dim, d, True) + _head_spec("F2", d.z_dim, d, True))
     return (_embed_spec("obs_action_net", d.obs_dim + d.action_dim, d)
             + _embed_spec("obs_z_net", d.obs_dim + d.z_dim, d) + _trunk_spec(d, add_trunk)
             + _head_spec("F1", d.z_dim, d, add_trunk) + _head_spec("F2", d.z_dim, d, add_trunk))
 
 
-def actor_spec(d: Dims, add_trunk: bool = False) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
+def boltzmann_actor_spec(d: Dims) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
+    """DiagGaussianActor (boltzmann=True): policy = mlp(obs + z, hidden, "ntanh", hidden, "relu", 2 * action)  (fb_modules.py:129-139)."""
+    h = d.hidden_dim
+    return [("policy.0.weight", (h, d.obs_dim + d.z_dim)), ("policy.0.bias", (h,)), ("policy.1.weight", (h,)), ("policy.1.bias", (h,)),
+            ("policy.3.weight", (h, h)), ("policy.3.bias", (h,)), ("policy.5.weight", (2 * d.action_dim, h)), ("policy.5.bias", (2 * d.action_dim,))]
+
+
+def actor_spec(d: Dims, add_trunk: bool = False, preprocess: bool = True) -> tp.List[tp.Tuple[str, tp.Tuple[int, ...]]]:
+    if not preprocess:
+        return _deep_trunk_spec(d.obs_dim + d.z_dim, d) + _head_spec("policy", d.action_dim, d, True)
     return (_embed_spec("obs_net", d.obs_dim, d) + _embed_spec("obs_z_net", d.obs_dim + d.z_dim, d) + _trunk_spec(d, add_trunk)
             + _head_spec("policy", d.action_dim, d, add_trunk))
 
@@ -127,6 +146,14 @@ def _head(p: Params, prefix: str, h: Tensor) -> Tensor:
     return F.linear(h, p[f"{prefix}.2.weight"], p[f"{prefix}.2.bias"])
 
 
+def _deep_trunk(p: Params, x: Tensor) -> Tensor:
+    """preprocess=False trunk: Linear -> LayerNorm -> Tanh -> Linear -> ReLU -> Linear -> ReLU (fb_modules.py:102-104,175-177)."""
+    h = F.linear(x, p["trunk.0.weight"], p["trunk.0.bias"])
+    h = torch.tanh(F.layer_norm(h, (h.shape[-1],), p["trunk.1.weight"], p["trunk.1.bias"], LN_EPS))
+    h = torch.relu(F.linear(h, p["trunk.3.weight"], p["trunk.3.bias"]))
+    return torch.relu(F.linear(h, p["trunk.5.weight"], p["trunk.5.bias"]))
+
+
 def _trunk(p: Params, h: Tensor) -> Tensor:
     """The optional trunk Linear -> ReLU (add_trunk=True), the identity otherwise (fb_modules.py:96-100,118-119)."""
     if "trunk.0.weight" in p:
@@ -135,7 +162,10 @@ def _trunk(p: Params, h: Tensor) -> Tensor:
 
 
 def forward_map(p: Params, obs: Tensor, z: Tensor, action: Tensor) -> tp.Tuple[Tensor, Tensor]:
-    """ForwardMap.forward, preprocess=True (fb_modules.py:187-199)."""
+    """ForwardMap.forward (fb_modules.py:187-199); the parameter names tell the preprocess=False variant apart."""
+    if "obs_action_net.0.weight" not in p:
+        h = _deep_trunk(p, torch.cat([obs, z, action], dim=-1))
+        return _head(p, "F1", h), _head(p, "F2", h)
     oa = _embed(p, "obs_action_net", torch.cat([obs, action], dim=-1))
     oz = _embed(p, "obs_z_net", torch.cat([obs, z], dim=-1))
     h = _trunk(p, torch.cat([oa, oz], dim=-1))
@@ -143,10 +173,30 @@ def forward_map(p: Params, obs: Tensor, z: Tensor, action: Tensor) -> tp.Tuple[T
 
 
 def actor_mean(p: Params, obs: Tensor, z: Tensor) -> Tensor:
-    """Actor.forward up to mu = tanh(policy(h)), preprocess=True (fb_modules.py:110-122)."""
+    """Actor.forward up to mu = tanh(policy(h)) (fb_modules.py:110-122); preprocess=False is told apart by the parameter names."""
+    if "obs_net.0.weight" not in p:
+        return torch.tanh(_head(p, "policy", _deep_trunk(p, torch.cat([obs, z], dim=-1))))
     oz = _embed(p, "obs_z_net", torch.cat([obs, z], dim=-1))
     o = _embed(p, "obs_net", obs)
     return torch.tanh(_head(p, "policy", _trunk(p, torch.cat([o, oz], dim=-1))))
+
+
+def diag_gaussian_actor(p: Params, obs: Tensor, z: Tensor, log_std_bounds: tp.Tuple[float, float] = (-5, 2)) -> tp.Tuple[Tensor, Tensor]:
+    """DiagGaussianActor.forward (boltzmann=True, fb_modules.py:141-151): (mu, std) of the pre-tanh Normal."""
+    h = F.linear(torch.cat([obs, z], dim=-1), p["policy.0.weight"], p["policy.0.bias"])
+    h = torch.tanh(F.layer_norm(h, (h.shape[-1],), p["policy.1.weight"], p["policy.1.bias"], LN_EPS))
+    h = torch.relu(F.linear(h, p["policy.3.weight"], p["policy.3.bias"]))
+    mu, log_std = F.linear(h, p["policy.5.weight"], p["policy.5.bias"]).chunk(2, dim=-1)
+    lo, hi = log_std_bounds
+    log_std = lo + 0.5 * (hi - lo) * (torch.tanh(log_std) + 1)
+    return mu, log_std.exp()
+
+
+def squashed_normal_log_prob(x: Tensor, mu: Tensor, std: Tensor) -> Tensor:
+    """SquashedNormal.log_prob(tanh(x)) from the pre-tanh value x (what TanhTransform's cache hands back, utils.py:188-233):
+    Normal(mu, std).log_prob(x) - log|d tanh(x)/dx|, the Jacobian in the stable form of utils.py:212-215."""
+    base = -((x - mu) ** 2) / (2 * std ** 2) - std.log() - math.log(math.sqrt(2 * math.pi))
+    return base - 2.0 * (math.log(2.0) - x - F.softplus(-2.0 * x))
 
 
 def l2_project(x: Tensor, z_dim: int) -> Tensor:
@@ -279,11 +329,16 @@ def _with_grad(p: Params) -> Params:
 def fb_loss_and_grads(fwd: Params, bwd: Params, fwd_tgt: Params, bwd_tgt: Params, actor: Params,
                       obs: Tensor, action: Tensor, discount: Tensor, next_obs: Tensor, next_goal: Tensor,
                       z: Tensor, noise: Tensor, std: float, clip: tp.Optional[float], ortho_coef: float,
-                      z_dim: int, q_loss_coef: tp.Optional[float] = None, norm_z: bool = True) -> tp.Dict[str, tp.Any]:
+                      z_dim: int, q_loss_coef: tp.Optional[float] = None, norm_z: bool = True,
+                      boltzmann: bool = False) -> tp.Dict[str, tp.Any]:
     """update_fb up to (not including) the optimizer step: loss terms, metrics, grads of every
     forward_net / backward_net tensor, and the intermediates a kernel test wants to look at."""
     with torch.no_grad():
-        next_action = truncated_normal_sample(actor_mean(actor, next_obs, z), noise, std, clip)
+        if boltzmann:   # dist.sample() of the SquashedNormal (fb_ddpg.py:304-306): tanh of a Normal draw, no clipping
+            mu_b, std_b = diag_gaussian_actor(actor, next_obs, z)
+            next_action = torch.tanh(mu_b + std_b * noise)
+        else:
+            next_action = truncated_normal_sample(actor_mean(actor, next_obs, z), noise, std, clip)
         tF1, tF2 = forward_map(fwd_tgt, next_obs, z, next_action)
         tB = backward_map(bwd_tgt, next_goal, z_dim, norm_z)
     f, b = _with_grad(fwd), _with_grad(bwd)
@@ -302,17 +357,24 @@ def fb_loss_and_grads(fwd: Params, bwd: Params, fwd_tgt: Params, bwd_tgt: Params
 
 
 def actor_loss_and_grads(actor: Params, fwd: Params, obs: Tensor, z: Tensor, noise: Tensor, std: float,
-                         clip: tp.Optional[float]) -> tp.Dict[str, tp.Any]:  # "q1_success": additional_metric (fb_ddpg.py:403-404)
-    """update_actor up to the optimizer step (fb_ddpg.py:389-409), boltzmann=False."""
+                         clip: tp.Optional[float], boltzmann: bool = False, temp: float = 1.0) -> tp.Dict[str, tp.Any]:
+    """update_actor up to the optimizer step (fb_ddpg.py:389-409).  "q1_success": additional_metric (fb_ddpg.py:403-404).
+    boltzmann: DiagGaussianActor + SquashedNormal.rsample, loss = mean(temp * log_prob - Q)."""
     a = _with_grad(actor)
-    mu = actor_mean(a, obs, z)
-    action = truncated_normal_sample(mu, noise, std, clip)
-    log_prob = normal_log_prob(action, mu, std).sum(-1, keepdim=True)
+    if boltzmann:
+        mu, std_b = diag_gaussian_actor(a, obs, z)
+        x = mu + std_b * noise
+        action = torch.tanh(x)
+        log_prob = squashed_normal_log_prob(x, mu, std_b).sum(-1, keepdim=True)
+    else:
+        mu = actor_mean(a, obs, z)
+        action = truncated_normal_sample(mu, noise, std, clip)
+        log_prob = normal_log_prob(action, mu, std).sum(-1, keepdim=True)
     F1, F2 = forward_map(fwd, obs, z, action)
     Q1 = torch.einsum("sd, sd -> s", F1, z)
     Q2 = torch.einsum("sd, sd -> s", F2, z)
     Q = torch.min(Q1, Q2)
-    loss = -Q.mean()
+    loss = (temp * log_prob - Q).mean() if boltzmann else -Q.mean()
     loss.backward()
     return {"actor_loss": loss.detach(), "q": Q.mean().detach(), "actor_logprob": log_prob.mean().detach(),
             "q1_success": (Q1 > Q2).float().mean().detach(),
@@ -445,6 +507,9 @@ class OracleConfig:
     q_loss: bool = False          # fb_ddpg.py:330-341
     q_loss_coef: float = 0.01
     additional_metric: bool = False   # q1_success (fb_ddpg.py:403-404,416-417)
+    preprocess: bool = True       # False: one deep trunk on the concatenated inputs instead of the two embeds (fb_modules.py:102-104)
+    boltzmann: bool = False       # DiagGaussianActor + SquashedNormal, entropy-regularised actor loss (fb_ddpg.py:118-120,304-306,391-393,406)
+    temp: float = 1.0
     add_trunk: bool = False       # Linear(2 feature -> hidden) + ReLU between the embeds and the heads (fb_modules.py:96-100,169-173)
     rand_weight: bool = False     # mixed z = random convex-like combinations of B rows (fb_ddpg.py:475-482)
     norm_z: bool = True           # sqrt(z_dim)-sphere projection of B's output and of z (fb_modules.py:227-229, fb_ddpg.py:228,483)
@@ -459,8 +524,8 @@ class OracleAgent:
     def __init__(self, cfg: OracleConfig, generator: tp.Optional[torch.Generator] = None) -> None:
         self.cfg = cfg
         d = cfg.dims
-        self.actor = init_params(actor_spec(d, cfg.add_trunk), generator)
-        self.forward_net = init_params(forward_map_spec(d, cfg.add_trunk), generator)
+        self.actor = init_params(boltzmann_actor_spec(d) if cfg.boltzmann else actor_spec(d, cfg.add_trunk, cfg.preprocess), generator)
+        self.forward_net = init_params(forward_map_spec(d, cfg.add_trunk, cfg.preprocess), generator)
         self.backward_net = init_params(backward_map_spec(d), generator)
         self.forward_target_net = collections.OrderedDict((k, v.clone()) for k, v in self.forward_net.items())
         self.backward_target_net = collections.OrderedDict((k, v.clone()) for k, v in self.backward_net.items())
@@ -488,9 +553,13 @@ class OracleAgent:
         cfg, d = self.cfg, self.cfg.dims
         std = schedule(cfg.stddev_schedule, step)
         with torch.no_grad():
-            mu = actor_mean(self.actor, next_obs, z)
-            noise = torch.randn(mu.shape, dtype=mu.dtype)
-            next_action = truncated_normal_sample(mu, noise, std, cfg.stddev_clip)
+            if cfg.boltzmann:
+                mu, std_b = diag_gaussian_actor(self.actor, next_obs, z)
+                next_action = torch.tanh(mu + std_b * torch.randn(mu.shape, dtype=mu.dtype))
+            else:
+                mu = actor_mean(self.actor, next_obs, z)
+                noise = torch.randn(mu.shape, dtype=mu.dtype)
+                next_action = truncated_normal_sample(mu, noise, std, cfg.stddev_clip)
             tF1, tF2 = forward_map(self.forward_target_net, next_obs, z, next_action)
             tB = backward_map(self.backward_target_net, next_goal, d.z_dim, cfg.norm_z)
         F1, F2 = forward_map(self.forward_net, obs, z, action)
@@ -509,14 +578,20 @@ class OracleAgent:
     def update_actor(self, obs: Tensor, z: Tensor, step: int) -> tp.Dict[str, float]:
         cfg = self.cfg
         std = schedule(cfg.stddev_schedule, step)
-        mu = actor_mean(self.actor, obs, z)
-        noise = torch.randn(mu.shape, dtype=mu.dtype)
-        action = truncated_normal_sample(mu, noise, std, cfg.stddev_clip)
-        log_prob = normal_log_prob(action, mu, std).sum(-1, keepdim=True)
+        if cfg.boltzmann:
+            mu, std_b = diag_gaussian_actor(self.actor, obs, z)
+            x = mu + std_b * torch.randn(mu.shape, dtype=mu.dtype)
+            action = torch.tanh(x)
+            log_prob = squashed_normal_log_prob(x, mu, std_b).sum(-1, keepdim=True)
+        else:
+            mu = actor_mean(self.actor, obs, z)
+            noise = torch.randn(mu.shape, dtype=mu.dtype)
+            action = truncated_normal_sample(mu, noise, std, cfg.stddev_clip)
+            log_prob = normal_log_prob(action, mu, std).sum(-1, keepdim=True)
         F1, F2 = forward_map(self.forward_net, obs, z, action)
         Q1, Q2 = torch.einsum("sd, sd -> s", F1, z), torch.einsum("sd, sd -> s", F2, z)
         Q = torch.min(Q1, Q2)
-        loss = -Q.mean()
+        loss = (cfg.temp * log_prob - Q).mean() if cfg.boltzmann else -Q.mean()
         self.actor_opt.zero_grad(set_to_none=True)
         loss.backward()       # like the reference, this also fills forward_net grads (never used)
         self.actor_opt.step()

@@ -45,7 +45,8 @@ def make_agent(R: tp.Any, case: tp.Mapping[str, tp.Any], use_tb: bool = True) ->
         future_ratio=case.get("future_ratio", 0.0), q_loss=case.get("q_loss", False),
         q_loss_coef=case.get("q_loss_coef", 0.01), additional_metric=case.get("additional_metric", False),
         norm_z=case.get("norm_z", True), rand_weight=case.get("rand_weight", False),
-        add_trunk=case.get("add_trunk", False))
+        add_trunk=case.get("add_trunk", False), preprocess=case.get("preprocess", True), boltzmann=case.get("boltzmann", False),
+        temp=case.get("temp", 1))
     return R.FBDDPGAgent(**dataclasses.asdict(cfg))
 
 
@@ -155,6 +156,8 @@ def gen_update_case(R: tp.Any, name: str, case: tp.Mapping[str, tp.Any]) -> tp.D
     if agent.cfg.q_loss:
         out["cfg/q_loss_coef"] = np.float64(agent.cfg.q_loss_coef)
     out["cfg/norm_z"] = np.int64(agent.cfg.norm_z)
+    out["cfg/boltzmann"] = np.int64(agent.cfg.boltzmann)
+    out["cfg/temp"] = np.float64(agent.cfg.temp)
     return out
 
 
@@ -310,9 +313,21 @@ def write_trunk_cases(R: tp.Any) -> None:
     print("wrote trajectory_trunk")
 
 
+def write_oracle_only_cases(R: tp.Any) -> None:
+    """preprocess=False (one deep trunk, fb_modules.py:102-104,175-177) and boltzmann=True (DiagGaussianActor + SquashedNormal,
+    fb_ddpg.py:118-120,304-306,391-393,406): these pin the ORACLE for the two branches the CUDA step does not implement yet
+    (the agent raises NotImplementedError for them); the kernels of a later round are to be checked against these files."""
+    for name, extra in (("nopre", dict(preprocess=False)), ("boltz", dict(boltzmann=True, temp=0.7))):
+        case = dict(CASES["small"], **extra)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"update_{name}.npz"), **gen_update_case(R, name, case))
+        print("wrote update_%s" % name)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"trajectory_{name}.npz"), **gen_trajectory_case(R, case))
+        print("wrote trajectory_%s" % name)
+
+
 # fixture families added after the first ones; `--<name>-only` regenerates one family without touching the others
 LATER_FAMILIES = {"hindsight": write_hindsight_cases, "qloss": write_qloss_cases, "nonorm": write_nonorm_cases, "randw": write_randw_cases,
-                  "trunk": write_trunk_cases}
+                  "trunk": write_trunk_cases, "oracle": write_oracle_only_cases}
 
 
 def main() -> None:

@@ -171,3 +171,62 @@ def test_schedule():
     assert O.schedule("step_linear(1,0.5,100,0.1,100)", 150) == pytest.approx(0.3)
     with pytest.raises(NotImplementedError):
         O.schedule("cosine(1)", 0)
+
+
+SMALL = O.Dims(obs_dim=11, action_dim=3, z_dim=10, goal_dim=11, hidden_dim=48, feature_dim=24, backward_hidden_dim=30)   # make_golden.CASES["small"]
+
+
+@pytest.mark.parametrize("case", ["nopre", "boltz"])
+def test_oracle_only_branches_update(case):
+    """preprocess=False and boltzmann=True: the two fb_ddpg branches the CUDA step does not implement yet (the agent raises for
+    them).  The oracle is pinned against the reference here so that the kernels of a later round have a checker."""
+    g = load_golden(f"update_{case}")
+    boltz = bool(g["cfg/boltzmann"])
+    fwd_spec = O.forward_map_spec(SMALL, preprocess=case != "nopre")
+    act_spec = O.boltzmann_actor_spec(SMALL) if boltz else O.actor_spec(SMALL, preprocess=case != "nopre")
+    for net, spec in (("forward_net", fwd_spec), ("actor", act_spec), ("backward_net", O.backward_map_spec(SMALL))):
+        ref = subtree(g, f"param0/{net}")
+        assert [(n, tuple(s)) for n, s in spec] == [(k, v.shape) for k, v in ref.items()]
+    t = {k: torch.from_numpy(v.copy()) for k, v in subtree(g, "in").items()}
+    res = O.fb_loss_and_grads(
+        params(g, "param0/forward_net"), params(g, "param0/backward_net"), params(g, "param0/forward_target_net"),
+        params(g, "param0/backward_target_net"), params(g, "param0/actor"), t["obs"], t["action"], t["discount"],
+        t["next_obs"], t["next_goal"], t["z"], t["noise_fb"], float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]),
+        float(g["cfg/ortho_coef"]), SMALL.z_dim, boltzmann=boltz)
+    for k, v in subtree(g, "metric_fb").items():
+        if k != "fb_opt_lr":
+            assert res["metrics"][k] == pytest.approx(float(v), rel=2e-5, abs=2e-6), k
+    for net, key in (("forward_net", "grads_forward"), ("backward_net", "grads_backward")):
+        for name, ref in subtree(g, f"grad_fb/{net}").items():
+            assert rel(res[key][name].numpy(), ref) < 1e-5, (net, name)
+    res = O.actor_loss_and_grads(params(g, "param0/actor"), params(g, "param1/forward_net"), t["obs"], t["z"], t["noise_actor"],
+                                 float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]), boltzmann=boltz, temp=float(g["cfg/temp"]))
+    m = subtree(g, "metric_actor")
+    for k in ("actor_loss", "q", "actor_logprob"):
+        assert float(res[k]) == pytest.approx(float(m[k]), rel=2e-5, abs=2e-6), k
+    for name, ref in subtree(g, "grad_actor/actor").items():
+        assert rel(res["grads_actor"][name].numpy(), ref) < 1e-5, name
+
+
+@pytest.mark.parametrize("case", ["nopre", "boltz"])
+def test_oracle_only_branches_trajectory(case):
+    torch.set_num_threads(1)
+    g = load_golden(f"trajectory_{case}")
+    agent = O.OracleAgent(O.OracleConfig(dims=SMALL, batch_size=32, preprocess=case != "nopre", boltzmann=case == "boltz", temp=0.7))
+    a, f, b = subtree(g, "param0/actor"), subtree(g, "param0/forward_net"), subtree(g, "param0/backward_net")
+    agent.load_params(actor=a, forward_net=f, backward_net=b, forward_target_net=f, backward_target_net=b)
+    buf = O.OracleReplay(4, 0.98, 0.99)
+    for i in range(4):
+        buf.add_episode({k: (v if v.ndim > 1 else v[:, None]) for k, v in subtree(g, f"ep{i}").items()})
+    seed = int(g["seed"])
+    torch.manual_seed(seed + 1)
+    np.random.seed(seed + 1)
+    for step in range(int(g["steps"])):
+        m = agent.update(buf, step)
+        ref = subtree(g, f"step{step}")
+        assert set(ref) == set(m)
+        for k, v in ref.items():
+            assert m[k] == pytest.approx(float(v), rel=2e-4, abs=1e-5), (step, k)
+    for net in ("actor", "forward_net", "backward_net", "forward_target_net", "backward_target_net"):
+        for name, ref in subtree(g, f"paramN/{net}").items():
+            assert np.abs(getattr(agent, net)[name].detach().numpy() - ref).max() < 5e-5, (net, name)
