@@ -11,14 +11,25 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from controllable_agent_b200 import FBDDPGAgent, ReplayBuffer, _lib as L  # noqa: E402
 
 
-def step_table(batch: int, z_dim: int, reps: int) -> None:
+def _parse_overrides(items):
+    """`--agent q_loss=true add_trunk=true norm_z=false q_loss_coef=0.5` -> FBDDPGAgent keyword overrides."""
+    out = {}
+    for it in items or []:
+        k, v = it.split("=", 1)
+        low = v.lower()
+        out[k] = True if low == "true" else False if low == "false" else (float(v) if any(c in v for c in ".e") else int(v))
+    return out
+
+
+def step_table(batch: int, z_dim: int, reps: int, overrides=None) -> None:
     dev = torch.device("cuda")
     E, R, O_, A_ = 200, 1001, 24, 6
     replay = ReplayBuffer(E, 0.98, 0.99, device=dev)
     replay.load_storage({"observation": torch.randn(E, R, O_, device=dev), "action": torch.rand(E, R, A_, device=dev) * 2 - 1,
                          "reward": torch.rand(E, R, 1, device=dev), "discount": torch.ones(E, R, 1, device=dev)})
     agent = FBDDPGAgent(obs_type="states", obs_shape=(O_,), action_shape=(A_,), device="cuda", num_expl_steps=0, update_encoder=True,
-                        goal_space=None, use_tb=False, use_wandb=False, use_hiplog=False, batch_size=batch, z_dim=z_dim, update_every_steps=1)
+                        goal_space=None, use_tb=False, use_wandb=False, use_hiplog=False, batch_size=batch, z_dim=z_dim, update_every_steps=1,
+                        **(overrides or {}))
     for i in range(5):
         agent.update(replay, i)
     torch.cuda.synchronize()
@@ -29,7 +40,7 @@ def step_table(batch: int, z_dim: int, reps: int) -> None:
         acc += agent.engine.launch_count(1 << ph)
         bounds.append(acc)
     tot = sum(o["ms"] for o in ops)
-    print(f"batch={batch} z={z_dim}: {len(ops)} launches, {tot:.3f} ms eager-serial")
+    print(f"batch={batch} z={z_dim} {overrides or ''}: {len(ops)} launches, {tot:.3f} ms eager-serial")
     ph = 0
     for i, o in enumerate(ops):
         while i >= bounds[ph]:
@@ -86,7 +97,8 @@ if __name__ == "__main__":
     p.add_argument("--z-dim", type=int, default=50)
     p.add_argument("--reps", type=int, default=10)
     p.add_argument("--sweep", action="store_true")
+    p.add_argument("--agent", nargs="*", default=[], help="FBDDPGAgent config overrides, e.g. q_loss=true add_trunk=true rand_weight=true")
     a = p.parse_args()
-    step_table(a.batch, a.z_dim, a.reps)
+    step_table(a.batch, a.z_dim, a.reps, _parse_overrides(a.agent))
     if a.sweep:
         sgemm_sweep()
