@@ -57,7 +57,7 @@ class fb_config(C.Structure):
                 ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float), ("future_ratio", C.c_float),
                 ("seed", C.c_uint64), ("q_loss", C.c_int32), ("q_loss_coef", C.c_float),
                 ("no_norm_z", C.c_int32), ("rand_weight", C.c_int32),
-                ("add_trunk", C.c_int32), ("reserved0", C.c_int32)]
+                ("add_trunk", C.c_int32), ("no_preprocess", C.c_int32)]
 
 
 class fb_step_scalars(C.Structure):

@@ -117,7 +117,7 @@ def register_hydra() -> None:
     ConfigStore.instance().store(group="agent", name="fb_ddpg", node=FBDDPGAgentConfig)
 
 
-_UNSUPPORTED = {"boltzmann": False, "debug": False, "preprocess": True}
+_UNSUPPORTED = {"boltzmann": False, "debug": False}
 
 
 class FBDDPGAgent:
@@ -178,7 +178,7 @@ class FBDDPGAgent:
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
-            mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, q_loss=bool(cfg.q_loss), q_loss_coef=float(cfg.q_loss_coef), norm_z=bool(cfg.norm_z), rand_weight=bool(cfg.rand_weight), add_trunk=bool(cfg.add_trunk), seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
+            mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, q_loss=bool(cfg.q_loss), q_loss_coef=float(cfg.q_loss_coef), norm_z=bool(cfg.norm_z), rand_weight=bool(cfg.rand_weight), add_trunk=bool(cfg.add_trunk), preprocess=bool(cfg.preprocess), seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
             mlp_mode=L.MLP_SIMT if cfg.mlp_mode == "simt" else L.MLP_TCGEN05,
             contract_mode=L.CONTRACT_SIMT if cfg.contract_mode == "simt" else L.CONTRACT_TCGEN05), device)
 
@@ -186,11 +186,11 @@ class FBDDPGAgent:
         # ForwardMap target — fb_ddpg.py:117-139) so that the torch CPU generator is consumed identically, then moved
         # onto the flat device segments
         e = self.engine
-        self.actor = M.Actor(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk)
-        self.forward_net = M.ForwardMap(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk)
+        self.actor = M.Actor(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk, preprocess=cfg.preprocess)
+        self.forward_net = M.ForwardMap(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk, preprocess=cfg.preprocess)
         self.backward_net = M.BackwardMap(goal_dim, cfg.z_dim, cfg.backward_hidden_dim, norm_z=cfg.norm_z)
         self.backward_target_net = M.BackwardMap(goal_dim, cfg.z_dim, cfg.backward_hidden_dim, norm_z=cfg.norm_z)
-        self.forward_target_net = M.ForwardMap(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk)
+        self.forward_target_net = M.ForwardMap(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk, preprocess=cfg.preprocess)
         M.adopt_flat(self.actor, e.tensors(L.NET_ACTOR, "param"))
         M.adopt_flat(self.forward_net, e.tensors(L.NET_FORWARD, "param"))
         M.adopt_flat(self.backward_net, e.tensors(L.NET_BACKWARD, "param"))

@@ -389,7 +389,10 @@ struct Builder {
     if (used_early) h->ops[phase].back().wait_stage = 1;   // operands staged on the staging lane: wait for this phase's staging event
   }
 
+  // Problems with an empty dimension are dropped: a configuration without one of the embeds (preprocess = False) builds the same
+  // grouped launches with zero-row activations standing in for the missing network.
   void gemm(std::vector<GemmDesc> g) {
+    g.erase(std::remove_if(g.begin(), g.end(), [](const GemmDesc& d) { return d.M <= 0 || d.N <= 0 || d.K <= 0; }), g.end());
     if (g.empty()) return;
     std::vector<GemmDesc> tc, simt;
     for (auto& d : g) (tc_ok(d) ? tc : simt).push_back(d);
@@ -405,6 +408,8 @@ struct Builder {
     }, FB_OPK_GEMM, gl.flops, gl.bytes);
   }
   void ln_fwd(std::vector<LnDesc> v) {
+    v.erase(std::remove_if(v.begin(), v.end(), [](const LnDesc& d) { return d.rows <= 0; }), v.end());
+    if (v.empty()) return;
     int rows = 0;
     double bytes = 0.0;
     for (auto& d : v) { d.row_begin = rows; rows += d.rows; bytes += 8.0 * d.rows * (double)d.D; }
@@ -421,6 +426,8 @@ struct Builder {
     }, FB_OPK_LAYERNORM, 0.0, bytes);
   }
   void ln_bwd(std::vector<LnBwdDesc> v) {
+    v.erase(std::remove_if(v.begin(), v.end(), [](const LnBwdDesc& d) { return d.rows <= 0; }), v.end());
+    if (v.empty()) return;
     int ctas = 0;
     double bytes = 0.0;
     for (auto& d : v) {
@@ -452,6 +459,8 @@ struct Builder {
     });
   }
   void colsum(std::vector<ColsumDesc> v) {
+    v.erase(std::remove_if(v.begin(), v.end(), [](const ColsumDesc& d) { return d.rows <= 0; }), v.end());
+    if (v.empty()) return;
     int ctas = 0;
     double bytes = 0.0;
     for (auto& d : v) {
@@ -544,6 +553,13 @@ static int build_plan(fb_handle* h) {
   const int B = c.batch, n = c.global_batch, O = c.obs_dim, A = c.action_dim, Z = c.z_dim, H = c.hidden_dim, Fd = c.feature_dim;
   const int G = c.goal_dim;
   const bool use_goal = c.use_goal != 0;
+  // preprocess = False: ONE embed-shaped block (trunk.0 / .1 / .3, output width H) on [obs | z (| action)] followed by trunk.5 = the
+  // add_trunk layer with an H-wide input.  The plan below is the add_trunk plan in which the second embed of every pair has zero rows
+  // (its launches drop out in the Builder): for forward_net the obs_action slot is the one that stays, for the actor the obs_z slot.
+  const bool deep = c.no_preprocess != 0;
+  const int Fe = deep ? H : Fd;          // output width of an embed
+  const int Hc = deep ? H : 2 * Fd;      // width of the (concatenated) embed output the trunk / heads read
+  const int act_col = deep ? O + Z : O;  // column of the action inside the forward-net inputs
   const int nz = c.no_norm_z ? 0 : 1;   // cfg.norm_z: sqrt(Z)-sphere projection of backward_net outputs and of the mixed z
   for (auto& v : h->ops) v.clear();
   for (auto& v : h->early_stage) v.clear();
@@ -575,11 +591,11 @@ static int build_plan(fb_handle* h) {
   h->packed = ws_mat(h, B, L.pitch, "packed");
 
   // ---- step inputs ---------------------------------------------------------------------------
-  Mat actor_in_o = ws_mat(h, 2 * B, O, "actor_in_o");
+  Mat actor_in_o = ws_mat(h, deep ? 0 : 2 * B, O, "actor_in_o");
   Mat actor_in_oz = ws_mat(h, 2 * B, O + Z, "actor_in_oz");
-  Mat in_oa = ws_mat(h, B, O + A, "in_oa");
-  Mat in_noa = ws_mat(h, B, O + A, "in_noa");
-  Mat in_oa2 = ws_mat(h, B, O + A, "in_oa2");
+  Mat in_oa = ws_mat(h, B, act_col + A, "in_oa");      // [obs | action], or [obs | z | action]
+  Mat in_noa = ws_mat(h, B, act_col + A, "in_noa");
+  Mat in_oa2 = ws_mat(h, B, act_col + A, "in_oa2");
   Mat goal_next = ws_mat(h, B, G, "next_goal");
   Mat mix_in = ws_mat(h, with_future ? 2 * B : B, G, "mix_input");   // [backward_input[perm] ; future goal]
   h->z_rand = ws_mat(h, B, Z, "z_rand");
@@ -621,24 +637,26 @@ static int build_plan(fb_handle* h) {
   PSet pBt{&h->seg_fb, h->bwd_first, bf.d_target_fb, nullptr};
   PSet pA{&h->seg_actor, 0, bf.d_param_actor, bf.d_grad_actor};
   // sub-blocks: embed = 6 tensors (W0 b0 gamma beta W3 b3), [trunk = 2 tensors (W b), cfg.add_trunk], head = 4 tensors (W1 b1 W2 b2)
-  const bool trunk = c.add_trunk != 0;
-  const int T_N = trunk ? 2 : 0;
-  const int E_OA = 0, E_OZ = 6, F_TR = 12, HD_1 = 12 + T_N, HD_2 = 16 + T_N;   // forward net
-  const int A_O = 0, A_OZ = 6, A_TR = 12, A_POL = 12 + T_N;                    // actor
+  const bool trunk = c.add_trunk != 0 || deep;
+  const int T_N = trunk ? 2 : 0, NE = deep ? 6 : 12;
+  const int E_OA = 0, E_OZ = deep ? 0 : 6, F_TR = NE, HD_1 = NE + T_N, HD_2 = NE + 4 + T_N;   // forward net (deep: E_OZ is never launched)
+  const int A_O = 0, A_OZ = deep ? 0 : 6, A_TR = NE, A_POL = NE + T_N;                        // actor (deep: A_O is never launched)
 
   // ---- activations ---------------------------------------------------------------------------
-  Mat hA = ws_mat(h, 2 * B, 2 * Fd, "hA");
-  Mat hFt = ws_mat(h, B, 2 * Fd, "hFt");
-  Mat hF = ws_mat(h, B, 2 * Fd, "hF");
-  Mat hF2 = ws_mat(h, B, 2 * Fd, "hF2");
-  EmbedAct eAo = embed_alloc(h, actor_in_o, hA.cs(0, Fd), H, "actor.obs_net");
-  EmbedAct eAoz = embed_alloc(h, actor_in_oz, hA.cs(Fd, Fd), H, "actor.obs_z_net");
-  EmbedAct eFtoa = embed_alloc(h, in_noa, hFt.cs(0, Fd), H, "Ft.obs_action_net");
-  EmbedAct eFtoz = embed_alloc(h, actor_in_oz.rs(0, B), hFt.cs(Fd, Fd), H, "Ft.obs_z_net");
-  EmbedAct eFoa = embed_alloc(h, in_oa, hF.cs(0, Fd), H, "F.obs_action_net");
-  EmbedAct eFoz = embed_alloc(h, actor_in_oz.rs(B, B), hF.cs(Fd, Fd), H, "F.obs_z_net");
-  EmbedAct eF2oa = embed_alloc(h, in_oa2, hF2.cs(0, Fd), H, "F2.obs_action_net");
-  EmbedAct eF2oz = embed_alloc(h, actor_in_oz.rs(B, B), hF2.cs(Fd, Fd), H, "F2.obs_z_net");
+  Mat hA = ws_mat(h, 2 * B, Hc, "hA");
+  Mat hFt = ws_mat(h, B, Hc, "hFt");
+  Mat hF = ws_mat(h, B, Hc, "hF");
+  Mat hF2 = ws_mat(h, B, Hc, "hF2");
+  const int oz0 = deep ? 0 : Fd;   // first column of the obs_z embed inside the concatenated output
+  auto oz_rows = [&](int r0) { Mat m = actor_in_oz.rs(r0, B); if (deep) m.rows = 0; return m; };   // forward_net's obs_z embeds: absent when deep
+  EmbedAct eAo = embed_alloc(h, actor_in_o, hA.cs(0, Fe), H, "actor.obs_net");
+  EmbedAct eAoz = embed_alloc(h, actor_in_oz, hA.cs(oz0, Fe), H, "actor.obs_z_net");
+  EmbedAct eFtoa = embed_alloc(h, in_noa, hFt.cs(0, Fe), H, "Ft.obs_action_net");
+  EmbedAct eFtoz = embed_alloc(h, oz_rows(0), hFt.cs(oz0, Fe), H, "Ft.obs_z_net");
+  EmbedAct eFoa = embed_alloc(h, in_oa, hF.cs(0, Fe), H, "F.obs_action_net");
+  EmbedAct eFoz = embed_alloc(h, oz_rows(B), hF.cs(oz0, Fe), H, "F.obs_z_net");
+  EmbedAct eF2oa = embed_alloc(h, in_oa2, hF2.cs(0, Fe), H, "F2.obs_action_net");
+  EmbedAct eF2oz = embed_alloc(h, oz_rows(B), hF2.cs(oz0, Fe), H, "F2.obs_z_net");
   // add_trunk: ReLU(Linear(2 Fd -> H)) of each concatenated embed pair; the heads then read these instead of hA / hFt / hF / hF2
   Mat trA, trFt, trF, trF2;
   if (trunk) { trA = ws_mat(h, 2 * B, H, "actor.trunk"); trFt = ws_mat(h, B, H, "Ft.trunk"); trF = ws_mat(h, B, H, "F.trunk"); trF2 = ws_mat(h, B, H, "F2.trunk"); }
@@ -669,16 +687,16 @@ static int build_plan(fb_handle* h) {
   // backward scratch
   Mat dh1 = ws_mat(h, B, 2 * H, "dh1");          // [dh1_F1 | dh1_F2]
   Mat dh1_1 = dh1.cs(0, H), dh1_2 = dh1.cs(H, H);
-  Mat dhF = ws_mat(h, B, 2 * Fd, "dhF");
-  Mat dy_oa = ws_mat(h, B, H, "dy_oa"), dy_oz = ws_mat(h, B, H, "dy_oz");
+  Mat dhF = ws_mat(h, B, Hc, "dhF");
+  Mat dy_oa = ws_mat(h, B, H, "dy_oa"), dy_oz = ws_mat(h, deep ? 0 : B, H, "dy_oz");
   Mat dh2 = ws_mat(h, B, c.backward_hidden_dim, "dh2"), dy1 = ws_mat(h, B, c.backward_hidden_dim, "dy1");
   Mat dFa = ws_mat(h, B, 2 * ldZ, "dFa");
   Mat dFa1 = dFa.cs(0, Z), dFa2 = dFa.cs(ldZ, Z);
-  Mat dhoa = ws_mat(h, B, Fd, "dhoa");
+  Mat dhoa = ws_mat(h, B, Fe, "dhoa");
   Mat dpreA = ws_mat(h, B, A, "dpreA");
   Mat dh1A = ws_mat(h, B, H, "dh1A");
-  Mat dhA = ws_mat(h, B, 2 * Fd, "dhA");
-  Mat dy_o = ws_mat(h, B, H, "dy_o"), dy_aoz = ws_mat(h, B, H, "dy_aoz");
+  Mat dhA = ws_mat(h, B, Hc, "dhA");
+  Mat dy_o = ws_mat(h, deep ? 0 : B, H, "dy_o"), dy_aoz = ws_mat(h, B, H, "dy_aoz");
   Mat dtF, dtA;   // add_trunk: gradients w.r.t. the trunk outputs
   if (trunk) { dtF = ws_mat(h, B, H, "dtF"); dtA = ws_mat(h, B, H, "dtA"); }
 
@@ -735,7 +753,7 @@ static int build_plan(fb_handle* h) {
   {
     StageParams sp; memset(&sp, 0, sizeof(sp));
     sp.L = L; sp.batch = B; sp.use_goal = use_goal ? 1 : 0;
-    sp.actor_in_o = actor_in_o.p; sp.ldO = actor_in_o.ld; sp.actor_in_oz = actor_in_oz.p; sp.ldOZ = actor_in_oz.ld;
+    sp.actor_in_o = deep ? nullptr : actor_in_o.p; sp.ldO = actor_in_o.ld; sp.act_col = act_col; sp.actor_in_oz = actor_in_oz.p; sp.ldOZ = actor_in_oz.ld;
     sp.in_oa = in_oa.p; sp.in_noa = in_noa.p; sp.in_oa2 = in_oa2.p; sp.ldOA = in_oa.ld;
     sp.goal_next = goal_next.p; sp.mix_in = mix_in.p; sp.ldG = goal_next.ld;
     sp.blk = bl.p; sp.blk_pitch = bl.ld; sp.disc_col = disc_col;
@@ -769,12 +787,17 @@ static int build_plan(fb_handle* h) {
     zp.batch = B; zp.Z = Z; zp.O = O; zp.z_rand = h->z_rand.p; zp.ldZ = z.ld; zp.b_mix = b_mix_out.p; zp.ld_bmix = b_mix_out.ld;
     zp.mix_src = rand_w ? b_mixw.p : b_mix_out.p; zp.ld_mix_src = rand_w ? b_mixw.ld : b_mix_out.ld;
     zp.mix_mask = c.mix_ratio > 0.f ? h->d_mix_mask : nullptr; zp.future_mask = with_future ? h->d_future_mask : nullptr; zp.z = z.p; zp.actor_in_oz = actor_in_oz.p; zp.ldOZ = actor_in_oz.ld; zp.renorm = nz;
+    if (deep) { zp.f_in[0] = in_oa.p; zp.f_in[1] = in_noa.p; zp.f_in[2] = in_oa2.p; zp.ldF = in_oa.ld; }
     b.push([zp](cudaStream_t s) { fb_launch_pdl(k_z_final, dim3(fb_ceil_div(zp.batch, 8)), dim3(256), 0, s, zp); return cudaGetLastError(); });
   }
   b.cur_lane = 0;
-  b.gemm({lin_fwd(eAo.x, pA.w(A_O + 0), pA.v(A_O + 1), eAo.pre, 0), lin_fwd(eFoa.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eFoa.pre, 0),
+  // F's obs_action first layer does not read z in the default layout and runs here, next to the z-mixing chain; with
+  // preprocess = False its input is [obs | z | action], so it waits for z and joins the first group of FB_FWD instead
+  EmbedAct eFoa_early = eFoa, eFoa_late = eFoa;
+  { EmbedAct& off = deep ? eFoa_early : eFoa_late; off.x.rows = 0; off.pre.rows = 0; off.y.rows = 0; }
+  b.gemm({lin_fwd(eAo.x, pA.w(A_O + 0), pA.v(A_O + 1), eAo.pre, 0), lin_fwd(eFoa_early.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eFoa_early.pre, 0),
           lin_fwd(bO.x, pB.w(0), pB.v(1), bO.pre, 0), lin_fwd(bT.x, pBt.w(0), pBt.v(1), bT.pre, 0)});
-  b.ln_fwd({embed_ln(eAo, pA.sub(A_O)), embed_ln(eFoa, pF.sub(E_OA)), b_ln(bO, pB), b_ln(bT, pBt)});
+  b.ln_fwd({embed_ln(eAo, pA.sub(A_O)), embed_ln(eFoa_early, pF.sub(E_OA)), b_ln(bO, pB), b_ln(bT, pBt)});
 
   // =========================== FB_PHASE_FB_FWD ==================================================
   b.set_phase(FB_PHASE_FB_FWD);
@@ -784,8 +807,9 @@ static int build_plan(fb_handle* h) {
     b.add_early(zd, b.phase);
   }
   b.gemm({lin_fwd(eAoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eAoz.pre, 0), lin_fwd(eFoz.x, pF.w(E_OZ + 0), pF.v(E_OZ + 1), eFoz.pre, 0),
-          lin_fwd(eFtoz.x, pFt.w(E_OZ + 0), pFt.v(E_OZ + 1), eFtoz.pre, 0)});
-  b.ln_fwd({embed_ln(eAoz, pA.sub(A_OZ)), embed_ln(eFoz, pF.sub(E_OZ)), embed_ln(eFtoz, pFt.sub(E_OZ))});
+          lin_fwd(eFtoz.x, pFt.w(E_OZ + 0), pFt.v(E_OZ + 1), eFtoz.pre, 0),
+          lin_fwd(eFoa_late.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eFoa_late.pre, 0)});
+  b.ln_fwd({embed_ln(eAoz, pA.sub(A_OZ)), embed_ln(eFoz, pF.sub(E_OZ)), embed_ln(eFtoz, pFt.sub(E_OZ)), embed_ln(eFoa_late, pF.sub(E_OA))});
   b.gemm({lin_fwd(eAo.y, pA.w(A_O + 4), pA.v(A_O + 5), eAo.out, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(eAoz.y, pA.w(A_OZ + 4), pA.v(A_OZ + 5), eAoz.out, GF_RELU | GF_RELU_LAZY_OK),
           lin_fwd(eFoa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eFoa.out, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(eFoz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eFoz.out, GF_RELU | GF_RELU_LAZY_OK),
           lin_fwd(eFtoz.y, pFt.w(E_OZ + 4), pFt.v(E_OZ + 5), eFtoz.out, GF_RELU | GF_RELU_LAZY_OK),
@@ -802,7 +826,7 @@ static int build_plan(fb_handle* h) {
   b.l2_fwd({b_l2(bO, Z, nz), b_l2(bT, Z, nz)});
   {
     ActorOutParams ap; memset(&ap, 0, sizeof(ap));
-    ap.batch = B; ap.A = A; ap.O = O; ap.pre = preA.p; ap.mu = mu.p; ap.ldA = preA.ld;
+    ap.batch = B; ap.A = A; ap.O = O; ap.act_col = act_col; ap.pre = preA.p; ap.mu = mu.p; ap.ldA = preA.ld;
     ap.noise_fb = h->noise_fb.p; ap.noise_actor = h->noise_actor.p; ap.ldN = h->noise_fb.ld;
     ap.in_noa = in_noa.p; ap.in_oa2 = in_oa2.p; ap.ldOA = in_noa.ld; ap.next_action = next_action.p; ap.action_new = action_new.p;
     ap.acc = acc;
@@ -991,7 +1015,8 @@ static int build_plan(fb_handle* h) {
     b.colsum({mk_colsum(dtF, pF.gv(F_TR + 1))});
     b.gemm({lin_dw(dtF, hF, pF.gw(F_TR + 0)), lin_dx(dtF, pF.w(F_TR + 0), dhF, GF_MASK_RELU, &hF)});
   }
-  Mat dhF_oa = dhF.cs(0, Fd), dhF_oz = dhF.cs(Fd, Fd);
+  Mat dhF_oa = dhF.cs(0, Fe), dhF_oz = dhF.cs(oz0, Fe);
+  if (deep) dhF_oz.rows = 0;
   b.colsum({mk_colsum(dhF_oa, pF.gv(E_OA + 5)), mk_colsum(dhF_oz, pF.gv(E_OZ + 5))});
   {
     LnBwdDesc d; memset(&d, 0, sizeof(d));
@@ -1054,13 +1079,13 @@ static int build_plan(fb_handle* h) {
   b.set_phase(FB_PHASE_ACTOR_BWD);
   b.gemm({lin_dx(dFa1, pF.w(HD_1 + 2), dh1_1, GF_MASK_RELU, &h1Fa1), lin_dx(dFa2, pF.w(HD_2 + 2), dh1_2, GF_MASK_RELU, &h1Fa2)});
   {
-    Mat hF2oa = hF2.cs(0, Fd);
+    Mat hF2oa = hF2.cs(0, Fe);
     if (trunk) {   // heads -> trunk output (full width), then the obs_action half of the trunk's input
       GemmDesc d = lin_dx(dh1_1, pF.w(HD_1 + 0), dtF, GF_MASK_RELU, &trF2);
       Mat w2 = pF.w(HD_2 + 0);
       d.A2 = dh1_2.p; d.B2 = w2.p; d.K2 = w2.rows;
       b.gemm({d});
-      b.gemm({lin_dx(dtF, pF.w(F_TR + 0).cs(0, Fd), dhoa, GF_MASK_RELU, &hF2oa)});
+      b.gemm({lin_dx(dtF, pF.w(F_TR + 0).cs(0, Fe), dhoa, GF_MASK_RELU, &hF2oa)});
     } else {
       GemmDesc d = lin_dx(dh1_1, pF.w(HD_1 + 0).cs(0, Fd), dhoa, GF_MASK_RELU, &hF2oa);
       Mat w2 = pF.w(HD_2 + 0).cs(0, Fd);
@@ -1072,7 +1097,7 @@ static int build_plan(fb_handle* h) {
   b.ln_bwd({embed_ln_bwd(eF2oa, pF.sub(E_OA), dy_oa, 0, false)});
   {
     Mat muB = mu.rs(B, B);
-    b.gemm({lin_dx(dy_oa, pF.w(E_OA + 0).cs(O, A), dpreA, GF_MASK_TANH, &muB)});
+    b.gemm({lin_dx(dy_oa, pF.w(E_OA + 0).cs(act_col, A), dpreA, GF_MASK_TANH, &muB)});
   }
   Mat h1A_o = h1A.rs(B, B), hA_o = hA.rs(B, B);
   b.colsum({mk_colsum(dpreA, pA.gv(A_POL + 3))});
@@ -1086,7 +1111,8 @@ static int build_plan(fb_handle* h) {
   } else {
     b.gemm({lin_dw(dh1A, hA_o, pA.gw(A_POL + 0)), lin_dx(dh1A, pA.w(A_POL + 0), dhA, GF_MASK_RELU, &hA_o)});
   }
-  Mat dhA_o = dhA.cs(0, Fd), dhA_oz = dhA.cs(Fd, Fd);
+  Mat dhA_o = dhA.cs(0, Fe), dhA_oz = dhA.cs(oz0, Fe);
+  if (deep) dhA_o.rows = 0;
   b.colsum({mk_colsum(dhA_o, pA.gv(A_O + 5)), mk_colsum(dhA_oz, pA.gv(A_OZ + 5))});
   b.gemm({lin_dw(dhA_o, eAo.y.rs(B, B), pA.gw(A_O + 4)), lin_dw(dhA_oz, eAoz.y.rs(B, B), pA.gw(A_OZ + 4)),
           lin_dx(dhA_o, pA.w(A_O + 4), dy_o, 0, nullptr), lin_dx(dhA_oz, pA.w(A_OZ + 4), dy_aoz, 0, nullptr)});
@@ -1141,9 +1167,11 @@ static int build_plan(fb_handle* h) {
   {
     const int R = FB_INFER_ROWS;
     Mat io = ws_mat(h, R, O, "infer_obs"), iz = ws_mat(h, R, Z, "infer_z"), ioz = ws_mat(h, R, O + Z, "infer_oz");
-    Mat ihA = ws_mat(h, R, 2 * Fd, "infer_hA"), ih1 = ws_mat(h, R, H, "infer_h1"), ipre = ws_mat(h, R, A, "infer_pre");
+    Mat ihA = ws_mat(h, R, Hc, "infer_hA"), ih1 = ws_mat(h, R, H, "infer_h1"), ipre = ws_mat(h, R, A, "infer_pre");
     Mat imu = ws_mat(h, R, A, "infer_mu");
-    EmbedAct eo = embed_alloc(h, io, ihA.cs(0, Fd), H, "infer.obs_net"), eoz = embed_alloc(h, ioz, ihA.cs(Fd, Fd), H, "infer.obs_z_net");
+    Mat io_embed = io;
+    if (deep) io_embed.rows = 0;   // no obs-only embed
+    EmbedAct eo = embed_alloc(h, io_embed, ihA.cs(0, Fe), H, "infer.obs_net"), eoz = embed_alloc(h, ioz, ihA.cs(oz0, Fe), H, "infer.obs_z_net");
     b.set_phase(FB_PHASE_INFER_ACTOR);
     b.push([=](cudaStream_t s) {
       fb_launch_pdl(k_infer_concat, dim3(R), dim3(128), 0, s, io.p, io.ld, iz.p, iz.ld, ioz.p, ioz.ld, R, O, Z);

@@ -167,6 +167,7 @@ struct StageParams {
   float* actor_in_o; int ldO;
   float* actor_in_oz; int ldOZ;
   float* in_oa; float* in_noa; float* in_oa2; int ldOA;
+  int act_col;                // column of the action inside in_oa / in_noa / in_oa2: O, or O + Z when z sits between (preprocess = False)
   float* goal_next; float* mix_in; int ldG;
   float* blk; int blk_pitch, disc_col;
   int with_future;            // rows [B, 2B) of mix_in = future_goal / future_obs (hindsight input, not permuted)
@@ -184,15 +185,17 @@ __global__ void __launch_bounds__(128) k_stage_inputs(StageParams P, const float
   const int B = P.batch;
   for (int c = threadIdx.x; c < L.O; c += blockDim.x) {
     const float o = row[L.off_obs + c], no = row[L.off_next_obs + c];
-    P.actor_in_o[(size_t)r * P.ldO + c] = no;
-    P.actor_in_o[(size_t)(B + r) * P.ldO + c] = o;
+    if (P.actor_in_o) {   // null: no obs-only embed (preprocess = False)
+      P.actor_in_o[(size_t)r * P.ldO + c] = no;
+      P.actor_in_o[(size_t)(B + r) * P.ldO + c] = o;
+    }
     P.actor_in_oz[(size_t)r * P.ldOZ + c] = no;
     P.actor_in_oz[(size_t)(B + r) * P.ldOZ + c] = o;
     P.in_oa[(size_t)r * P.ldOA + c] = o;
     P.in_oa2[(size_t)r * P.ldOA + c] = o;
     P.in_noa[(size_t)r * P.ldOA + c] = no;
   }
-  for (int c = threadIdx.x; c < L.A; c += blockDim.x) P.in_oa[(size_t)r * P.ldOA + L.O + c] = row[L.off_action + c];
+  for (int c = threadIdx.x; c < L.A; c += blockDim.x) P.in_oa[(size_t)r * P.ldOA + P.act_col + c] = row[L.off_action + c];
   const int G = P.use_goal ? L.G : L.O;
   const int src = P.perm ? P.perm[r] : r;
   const float* prow = packed + (size_t)src * L.pitch;
@@ -733,6 +736,7 @@ struct ZFinalParams {
   const int* mix_mask;                  // null: no mixing
   const int* future_mask;               // null: no hindsight; else rows [B, 2B) of b_mix hold backward_net(future goal)
   float* z; float* actor_in_oz; int ldOZ;
+  float* f_in[3]; int ldF;              // preprocess = False: z also goes to column O of the three forward-net inputs [obs | z | action]
   int renorm;                           // cfg.norm_z: re-project the mixed rows (fb_ddpg.py:483-484); 0 leaves them raw
 };
 
@@ -758,6 +762,10 @@ __global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
     P.z[(size_t)r * P.ldZ + c] = v;
     P.actor_in_oz[(size_t)r * P.ldOZ + P.O + c] = v;
     P.actor_in_oz[(size_t)(P.batch + r) * P.ldOZ + P.O + c] = v;
+    if (P.f_in[0]) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) P.f_in[i][(size_t)r * P.ldF + P.O + c] = v;
+    }
   }
 }
 
@@ -766,6 +774,7 @@ __global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
 // rows [B,2B): obs side with update_actor's noise  -> action into in_oa2[:, O:], log-prob metric
 struct ActorOutParams {
   int batch, A, O;
+  int act_col;   // column of the action inside in_noa / in_oa2 (O, or O + Z for preprocess = False)
   const float* pre; float* mu; int ldA;
   const float* noise_fb; const float* noise_actor; int ldN;
   float* in_noa; float* in_oa2; int ldOA;
@@ -811,10 +820,10 @@ __global__ void __launch_bounds__(256) k_actor_out(ActorOutParams P, const DevSc
     const float x = mu + eps;
     const float act = fminf(fmaxf(x, -1.0f + FB_CLAMP_EPS), 1.0f - FB_CLAMP_EPS);
     if (fb_side) {
-      P.in_noa[(size_t)rb * P.ldOA + P.O + a] = act;
+      P.in_noa[(size_t)rb * P.ldOA + P.act_col + a] = act;
       P.next_action[(size_t)rb * P.ldA + a] = act;
     } else {
-      P.in_oa2[(size_t)rb * P.ldOA + P.O + a] = act;
+      P.in_oa2[(size_t)rb * P.ldOA + P.act_col + a] = act;
       P.action_new[(size_t)rb * P.ldA + a] = act;
       const float dlt = act - mu;
       lp = (double)(-(dlt * dlt) / (2.f * std * std) - logf(std) - 0.91893853320467274178f);

@@ -131,10 +131,16 @@ static void build_layout(fb_handle* h) {
   const int O = c.obs_dim, A = c.action_dim, Z = c.z_dim, G = c.goal_dim, H = c.hidden_dim, Fd = c.feature_dim, Hb = c.backward_hidden_dim;
   SegmentLayout& f = h->seg_fb;
   h->fwd_first = 0;
-  add_embed(f, "obs_action_net", O + A, H, Fd);
-  add_embed(f, "obs_z_net", O + Z, H, Fd);
-  const int head_in = c.add_trunk ? H : 2 * Fd;   // add_trunk: trunk = Linear(2 Fd -> H) + ReLU in front of the heads
-  if (c.add_trunk) { f.add("trunk.0.weight", H, 2 * Fd); f.add("trunk.0.bias", H, 0); }
+  const bool deep = c.no_preprocess != 0;         // preprocess = False: trunk.{0,1,3} = one embed-shaped block of width H, trunk.5 = Linear(H -> H)
+  const int head_in = (c.add_trunk || deep) ? H : 2 * Fd;   // add_trunk: trunk = Linear(2 Fd -> H) + ReLU in front of the heads
+  if (deep) {
+    add_embed(f, "trunk", O + Z + A, H, H);
+    f.add("trunk.5.weight", H, H); f.add("trunk.5.bias", H, 0);
+  } else {
+    add_embed(f, "obs_action_net", O + A, H, Fd);
+    add_embed(f, "obs_z_net", O + Z, H, Fd);
+    if (c.add_trunk) { f.add("trunk.0.weight", H, 2 * Fd); f.add("trunk.0.bias", H, 0); }
+  }
   add_head(f, "F1", head_in, H, Z);
   add_head(f, "F2", head_in, H, Z);
   h->bwd_first = (int)f.t.size();
@@ -142,9 +148,14 @@ static void build_layout(fb_handle* h) {
   f.add("B.0.weight", Hb, G); f.add("B.0.bias", Hb, 0); f.add("B.1.weight", Hb, 0); f.add("B.1.bias", Hb, 0);
   f.add("B.3.weight", Hb, Hb); f.add("B.3.bias", Hb, 0); f.add("B.5.weight", Z, Hb); f.add("B.5.bias", Z, 0);
   SegmentLayout& a = h->seg_actor;
-  add_embed(a, "obs_net", O, H, Fd);
-  add_embed(a, "obs_z_net", O + Z, H, Fd);
-  if (c.add_trunk) { a.add("trunk.0.weight", H, 2 * Fd); a.add("trunk.0.bias", H, 0); }
+  if (deep) {
+    add_embed(a, "trunk", O + Z, H, H);
+    a.add("trunk.5.weight", H, H); a.add("trunk.5.bias", H, 0);
+  } else {
+    add_embed(a, "obs_net", O, H, Fd);
+    add_embed(a, "obs_z_net", O + Z, H, Fd);
+    if (c.add_trunk) { a.add("trunk.0.weight", H, 2 * Fd); a.add("trunk.0.bias", H, 0); }
+  }
   add_head(a, "policy", head_in, H, A);
 }
 

@@ -36,6 +36,7 @@ class EngineConfig:
     future_ratio: float = 0.0   # hindsight z (fb_ddpg.py:488-491)
     q_loss: bool = False        # the optional Q loss of update_fb (fb_ddpg.py:330-341)
     q_loss_coef: float = 0.01
+    preprocess: bool = True     # False: one deep trunk instead of the two embeds (fb_modules.py:102-104,175-177)
     add_trunk: bool = False     # trunk Linear + ReLU between the embeds and the heads (fb_modules.py:96-100,169-173)
     rand_weight: bool = False   # mixed z rows = random weighted sums of B rows (fb_ddpg.py:475-482)
     norm_z: bool = True         # sqrt(z_dim)-sphere projection of B's output / of z (fb_modules.py:227-229, fb_ddpg.py:228,483)
@@ -69,7 +70,7 @@ class FBStepEngine:
                         rng_device=int(cfg.rng_device), contract_mode=int(cfg.contract_mode), mlp_mode=int(cfg.mlp_mode), ortho_coef=cfg.ortho_coef, mix_ratio=cfg.mix_ratio,
                         future_ratio=cfg.future_ratio,
                         beta1=cfg.beta1, beta2=cfg.beta2, adam_eps=cfg.adam_eps, seed=cfg.seed,
-                        q_loss=int(cfg.q_loss), q_loss_coef=cfg.q_loss_coef, no_norm_z=int(not cfg.norm_z), rand_weight=int(cfg.rand_weight), add_trunk=int(cfg.add_trunk))
+                        q_loss=int(cfg.q_loss), q_loss_coef=cfg.q_loss_coef, no_norm_z=int(not cfg.norm_z), rand_weight=int(cfg.rand_weight), add_trunk=int(cfg.add_trunk), no_preprocess=int(not cfg.preprocess))
         h = C.c_void_p()
         L.check(self.lib.fb_create(C.byref(c), C.byref(h)), "fb_create")
         self.h = h

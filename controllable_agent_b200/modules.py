@@ -103,42 +103,61 @@ def mlp(*layers: tp.Union[int, str]) -> nn.Sequential:
 class Actor(nn.Module):
     """fb_modules.Actor with preprocess=True (fb_modules.py:81-126)."""
 
-    def __init__(self, obs_dim: int, z_dim: int, action_dim: int, feature_dim: int, hidden_dim: int, add_trunk: bool = False) -> None:
+    def __init__(self, obs_dim: int, z_dim: int, action_dim: int, feature_dim: int, hidden_dim: int, add_trunk: bool = False,
+                 preprocess: bool = True) -> None:
         super().__init__()
-        self.obs_dim, self.z_dim, self.action_dim = obs_dim, z_dim, action_dim
-        self.obs_net = mlp(obs_dim, hidden_dim, "ntanh", feature_dim, "irelu")
-        self.obs_z_net = mlp(obs_dim + z_dim, hidden_dim, "ntanh", feature_dim, "irelu")
-        self.trunk: nn.Module = mlp(2 * feature_dim, hidden_dim, "irelu") if add_trunk else nn.Identity()
-        self.policy = mlp(hidden_dim if add_trunk else 2 * feature_dim, hidden_dim, "irelu", action_dim)
+        self.obs_dim, self.z_dim, self.action_dim, self.preprocess = obs_dim, z_dim, action_dim, preprocess
+        if preprocess:
+            self.obs_net = mlp(obs_dim, hidden_dim, "ntanh", feature_dim, "irelu")
+            self.obs_z_net = mlp(obs_dim + z_dim, hidden_dim, "ntanh", feature_dim, "irelu")
+            self.trunk: nn.Module = mlp(2 * feature_dim, hidden_dim, "irelu") if add_trunk else nn.Identity()
+            head_in = hidden_dim if add_trunk else 2 * feature_dim
+        else:   # fb_modules.py:102-104
+            self.trunk = mlp(obs_dim + z_dim, hidden_dim, "ntanh", hidden_dim, "irelu", hidden_dim, "irelu")
+            head_in = hidden_dim
+        self.policy = mlp(head_in, hidden_dim, "irelu", action_dim)
         self.apply(weight_init)
 
     def forward(self, obs: torch.Tensor, z: torch.Tensor, std: float) -> TruncatedNormal:
         assert z.shape[-1] == self.z_dim
-        obs_z = self.obs_z_net(torch.cat([obs, z], dim=-1))
-        o = self.obs_net(obs)
-        mu = torch.tanh(self.policy(self.trunk(torch.cat([o, obs_z], dim=-1))))
+        if self.preprocess:
+            obs_z = self.obs_z_net(torch.cat([obs, z], dim=-1))
+            o = self.obs_net(obs)
+            h = torch.cat([o, obs_z], dim=-1)
+        else:
+            h = torch.cat([obs, z], dim=-1)
+        mu = torch.tanh(self.policy(self.trunk(h)))
         return TruncatedNormal(mu, torch.ones_like(mu) * std)
 
 
 class ForwardMap(nn.Module):
     """fb_modules.ForwardMap with preprocess=True (fb_modules.py:154-199)."""
 
-    def __init__(self, obs_dim: int, z_dim: int, action_dim: int, feature_dim: int, hidden_dim: int, add_trunk: bool = False) -> None:
+    def __init__(self, obs_dim: int, z_dim: int, action_dim: int, feature_dim: int, hidden_dim: int, add_trunk: bool = False,
+                 preprocess: bool = True) -> None:
         super().__init__()
-        self.obs_dim, self.z_dim, self.action_dim = obs_dim, z_dim, action_dim
-        self.obs_action_net = mlp(obs_dim + action_dim, hidden_dim, "ntanh", feature_dim, "irelu")
-        self.obs_z_net = mlp(obs_dim + z_dim, hidden_dim, "ntanh", feature_dim, "irelu")
-        self.trunk: nn.Module = mlp(2 * feature_dim, hidden_dim, "irelu") if add_trunk else nn.Identity()
-        head_in = hidden_dim if add_trunk else 2 * feature_dim
+        self.obs_dim, self.z_dim, self.action_dim, self.preprocess = obs_dim, z_dim, action_dim, preprocess
+        if preprocess:
+            self.obs_action_net = mlp(obs_dim + action_dim, hidden_dim, "ntanh", feature_dim, "irelu")
+            self.obs_z_net = mlp(obs_dim + z_dim, hidden_dim, "ntanh", feature_dim, "irelu")
+            self.trunk: nn.Module = mlp(2 * feature_dim, hidden_dim, "irelu") if add_trunk else nn.Identity()
+            head_in = hidden_dim if add_trunk else 2 * feature_dim
+        else:   # fb_modules.py:175-177
+            self.trunk = mlp(obs_dim + z_dim + action_dim, hidden_dim, "ntanh", hidden_dim, "irelu", hidden_dim, "irelu")
+            head_in = hidden_dim
         self.F1 = mlp(head_in, hidden_dim, "irelu", z_dim)
         self.F2 = mlp(head_in, hidden_dim, "irelu", z_dim)
         self.apply(weight_init)
 
     def forward(self, obs: torch.Tensor, z: torch.Tensor, action: torch.Tensor) -> tp.Tuple[torch.Tensor, torch.Tensor]:
         assert z.shape[-1] == self.z_dim
-        oa = self.obs_action_net(torch.cat([obs, action], dim=-1))
-        oz = self.obs_z_net(torch.cat([obs, z], dim=-1))
-        h = self.trunk(torch.cat([oa, oz], dim=-1))
+        if self.preprocess:
+            oa = self.obs_action_net(torch.cat([obs, action], dim=-1))
+            oz = self.obs_z_net(torch.cat([obs, z], dim=-1))
+            h = torch.cat([oa, oz], dim=-1)
+        else:
+            h = torch.cat([obs, z, action], dim=-1)
+        h = self.trunk(h)
         return self.F1(h), self.F2(h)
 
 

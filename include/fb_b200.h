@@ -125,7 +125,9 @@ typedef struct fb_config {
   int32_t add_trunk;           /* cfg.add_trunk (fb_modules.py:96-100,169-173): Actor and ForwardMap get a trunk Linear(2 feature_dim ->
                                   hidden_dim) + ReLU between the embeds and the policy / F1 / F2 heads (whose first layer then reads
                                   hidden_dim columns); tensors "trunk.0.weight", "trunk.0.bias" sit between the embeds and the heads */
-  int32_t reserved0;           /* 0 */
+  int32_t no_preprocess;       /* cfg.preprocess == False (fb_modules.py:102-104,175-177): Actor / ForwardMap are one deep trunk
+                                  mlp(obs+z[+action], hidden, "ntanh", hidden, "irelu", hidden, "irelu") in front of the heads instead
+                                  of the two embeds; tensors "trunk.{0,1,3,5}.*" then the heads */
 } fb_config;
 
 /* per-step scalars (host values; copied to the device by fb_set_step_scalars) */

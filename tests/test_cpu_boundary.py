@@ -38,7 +38,7 @@ def _create(L, lib, d, batch=64, **kw):
                     feature_dim=d.feature_dim, backward_hidden_dim=d.backward_hidden_dim, use_goal=kw.get("use_goal", 0), rng_device=0, contract_mode=kw.get("contract_mode", 0), mlp_mode=kw.get("mlp_mode", 0),
                     ortho_coef=1.0, mix_ratio=kw.get("mix_ratio", 0.5), beta1=0.9, beta2=0.999, adam_eps=1e-8, seed=0,
                     future_ratio=kw.get("future_ratio", 0.0), q_loss=kw.get("q_loss", 0), q_loss_coef=0.01, no_norm_z=kw.get("no_norm_z", 0),
-                    rand_weight=kw.get("rand_weight", 0), add_trunk=kw.get("add_trunk", 0))
+                    rand_weight=kw.get("rand_weight", 0), add_trunk=kw.get("add_trunk", 0), no_preprocess=kw.get("no_preprocess", 0))
     h = C.c_void_p()
     return lib.fb_create(C.byref(c), C.byref(h)), h
 
@@ -89,9 +89,14 @@ def test_add_trunk_layout_and_optional_branch_plans(d):
     rc, h = _create(L, lib, d)
     assert rc == 0 and lib.fb_workspace_bytes(h) < base_ws   # the trunk activations cost workspace
     lib.fb_destroy(h)
-    for bits in range(32):
+    rc, h = _create(L, lib, d, no_preprocess=1)   # preprocess = False: trunk.{0,1,3,5} then the heads (fb_modules.py:102-104,175-177)
+    assert rc == 0
+    for net, spec in ((L.NET_FORWARD, O.forward_map_spec(d, preprocess=False)), (L.NET_ACTOR, O.actor_spec(d, preprocess=False))):
+        assert [(n, s) for n, _, s in _table(lib, h, net)] == [(n, tuple(s)) for n, s in spec]
+    lib.fb_destroy(h)
+    for bits in range(64):
         kw = dict(q_loss=bits & 1, no_norm_z=(bits >> 1) & 1, rand_weight=(bits >> 2) & 1, add_trunk=(bits >> 3) & 1,
-                  future_ratio=0.3 if bits & 16 else 0.0)
+                  future_ratio=0.3 if bits & 16 else 0.0, no_preprocess=(bits >> 5) & 1)
         for mlp_mode in (0, 1):
             rc, h = _create(L, lib, d, mlp_mode=mlp_mode, contract_mode=mlp_mode, **kw)
             assert rc == 0, (kw, mlp_mode)

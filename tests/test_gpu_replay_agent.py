@@ -118,17 +118,18 @@ def test_pack_episode_kernel_matches_host_packing():
     assert torch.equal(rows[3], buf._rows[3])
 
 
-SMALL_CASES = ("small", "future", "qloss", "nonorm", "randw", "randw_nonorm", "trunk")   # fixtures generated from make_golden.CASES["small"]
+SMALL_CASES = ("small", "future", "qloss", "nonorm", "randw", "randw_nonorm", "trunk", "nopre")   # fixtures generated from make_golden.CASES["small"]
 
 
 def _agent_for(g, case, **kw):
     from controllable_agent_b200 import FBDDPGAgent
     a, f, b = subtree(g, "param0/actor"), subtree(g, "param0/forward_net"), subtree(g, "param0/backward_net")
-    hidden, oa = f["obs_action_net.0.weight"].shape
-    obs_dim = a["obs_net.0.weight"].shape[1]
+    from gpu_common import dims_from_params
+    d = dims_from_params(f, b, a)
+    hidden, obs_dim, oa = d.hidden_dim, d.obs_dim, d.obs_dim + d.action_dim
     agent = FBDDPGAgent(obs_type="states", obs_shape=(obs_dim,), action_shape=(oa - obs_dim,), device="cuda", num_expl_steps=0,
                         update_encoder=True, goal_space=None if case in SMALL_CASES else "simplified_walker", use_tb=True, use_wandb=False,
-                        use_hiplog=False, hidden_dim=hidden, feature_dim=f["obs_action_net.3.weight"].shape[0],
+                        use_hiplog=False, hidden_dim=hidden, feature_dim=d.feature_dim,
                         backward_hidden_dim=b["B.0.weight"].shape[0], z_dim=f["F1.2.weight"].shape[0],
                         batch_size=32 if case in SMALL_CASES else 64, update_every_steps=1,
                         future_ratio=0.4 if case.startswith("future") else (0.3 if case == "nonorm" else 0.0), **kw)
@@ -139,7 +140,7 @@ def _agent_for(g, case, **kw):
     return agent
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm", "trunk"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm", "trunk", "nopre"])
 @pytest.mark.parametrize("foreign_replay", [False, True])
 def test_agent_update_walks_reference_trajectory(case, foreign_replay):
     """agent.update(replay, step) x3 with the reference's RNG streams (rng_mode=reference, torch draws on the CPU generator
@@ -154,6 +155,8 @@ def test_agent_update_walks_reference_trajectory(case, foreign_replay):
         extra = dict(rand_weight=True, norm_z=case == "randw")
     if case == "trunk":   # add_trunk = True (fb_modules.py:96-100,169-173)
         extra = dict(add_trunk=True)
+    if case == "nopre":   # preprocess = False (fb_modules.py:102-104,175-177)
+        extra = dict(preprocess=False)
     agent = _agent_for(g, case, rng_mode="reference", **extra)
     agent.draw_device = "cpu"
     eps = [subtree(g, f"ep{i}") for i in range(4)]
@@ -448,7 +451,7 @@ def test_unsupported_branches_raise():
     from controllable_agent_b200 import FBDDPGAgent
     base = dict(obs_type="states", obs_shape=(24,), action_shape=(6,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,
                 use_tb=False, use_wandb=False, use_hiplog=False)
-    for kw in (dict(boltzmann=True), dict(preprocess=False),
+    for kw in (dict(boltzmann=True),
                dict(obs_type="pixels"), dict(debug=True)):
         with pytest.raises(NotImplementedError):
             FBDDPGAgent(**{**base, **kw})

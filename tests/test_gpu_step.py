@@ -100,7 +100,8 @@ def _run_update_case(g, d, use_goal, graph, mlp_mode=0):
     eng = make_engine(d, B, use_goal=use_goal, mix_ratio=0.5, ortho_coef=float(g["cfg/ortho_coef"]), mlp_mode=mlp_mode,
                       q_loss_coef=float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None,
                       norm_z=bool(g["cfg/norm_z"]) if "cfg/norm_z" in g else True,
-                      add_trunk="param0/actor/trunk.0.weight" in g)
+                      add_trunk="param0/actor/trunk.0.weight" in g and "param0/actor/obs_net.0.weight" in g,
+                      preprocess="param0/actor/obs_net.0.weight" in g)
     load_params(eng, fwd=subtree(g, "param0/forward_net"), bwd=subtree(g, "param0/backward_net"),
                 actor=subtree(g, "param0/actor"), fwd_tgt=subtree(g, "param0/forward_target_net"),
                 bwd_tgt=subtree(g, "param0/backward_target_net"))
@@ -114,7 +115,7 @@ def _run_update_case(g, d, use_goal, graph, mlp_mode=0):
 
 
 # qloss*: cfg.q_loss (fb_ddpg.py:330-341); nonorm*: cfg.norm_z = False (fb_modules.py:227-229); trunk*: cfg.add_trunk (fb_modules.py:96-100)
-@pytest.mark.parametrize("case", ["small", "goal", "wide", "qloss", "qloss_goal", "nonorm", "nonorm_goal", "trunk", "trunk_goal"])
+@pytest.mark.parametrize("case", ["small", "goal", "wide", "qloss", "qloss_goal", "nonorm", "nonorm_goal", "trunk", "trunk_goal", "nopre"])
 @pytest.mark.parametrize("graph,mlp_mode", [(False, 0), (True, 0), (True, 1)])
 def test_update_matches_reference_golden(case, graph, mlp_mode):
     g = load_golden(f"update_{case}")
