@@ -5,17 +5,20 @@ One "step" = one `agent.update(replay, step)` with update_every_steps=1 (train_o
 z draw + mixing, update_fb (+Adam), update_actor (+Adam), both target soft updates.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]                  our arm (CUDA step, device-resident replay)
-  python bench.py --impl reference [--steps K] [--warmup W]            the reference algorithm on the host CPU cores
-                                                                       (oracle/ port, all host threads; rank 0 only)
+  python bench.py --impl reference [--steps K] [--warmup W]            the reference on the host CPU cores, all host threads,
+                                                                       rank 0 only: the UNMODIFIED reference files staged in
+                                                                       baseline/_ref (kind "reference"), else the oracle port
 N > 1 is launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...`; the GLOBAL batch stays
-1024 (strong scaling, BASELINE.json north_star), each rank steps 1024/N rows against its own replay shard and the ranks
-exchange the [batch, 6*z] embedding block (all-gather) and the two flat gradients (all-reduce) over NCCL.
+1024 (strong scaling, BASELINE.json north_star), each rank steps 1024/N rows against its own replay shard.
 
+Other BASELINE.json configs:  cfg 3: --obs-dim 78 --action-dim 12 --goal-space simplified_quadruped
+                              cfg 5: --obs-dim 17 --z-dim 100 --batch 4096 [--gpus 8]
 Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import json
 import os
 import subprocess
@@ -29,6 +32,10 @@ if ROOT not in sys.path:
 
 METRIC = "FB-DDPG gradient-steps/sec (batch=1024, z_dim=50)"
 UNIT = "gradient-steps/s"
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+GOAL_DIMS = {"simplified_walker": 3, "walker_pos_speed": 4, "walker_pos_speed_z": 6, "simplified_quadruped": 2, "quad_pos_speed": 7,
+             "simplified_jaco": 3, "simplified_point_mass_maze": 2}
+PARITY_TOL = 1e-3
 
 
 def parse() -> argparse.Namespace:
@@ -41,22 +48,28 @@ def parse() -> argparse.Namespace:
     p.add_argument("--z-dim", type=int, default=50)
     p.add_argument("--obs-dim", type=int, default=24)
     p.add_argument("--action-dim", type=int, default=6)
+    p.add_argument("--goal-space", default=None, help="agent.goal_space (e.g. simplified_quadruped: goal_dim 2); the replay then stores goals")
     p.add_argument("--episodes", type=int, default=5000, help="episodes of the synthetic replay (whole job)")
     p.add_argument("--episode-len", type=int, default=1000)
     p.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer end-to-end leg (0: min(steps, 100))")
     p.add_argument("--cpu-steps", type=int, default=12, help="timed steps of the cpu_baseline leg (rank 0, N=1)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-cuda-eager", action="store_true", help="skip the reference-on-cuda (PyTorch eager) leg")
+    p.add_argument("--no-parity-check", action="store_true")
     p.add_argument("--no-graph", action="store_true")
-    p.add_argument("--collectives", default="graph", choices=["graph", "torch"], help="multi-GPU exchange: NCCL calls captured in the step "
-                   "graph on the library's communicator, or torch.distributed calls between graph segments")
+    p.add_argument("--collectives", default="auto", choices=["auto", "p2p", "graph", "torch"],
+                   help="multi-GPU exchange: p2p = the library's own kernels over NVLink peer memory, graph = NCCL calls captured in the step "
+                        "graph on the library's communicator, torch = torch.distributed calls between graph segments; auto = the agent's default")
     p.add_argument("--mlp-mode", default="tcgen05", choices=["tcgen05", "simt"], help="wide Linear products: tensor cores (3xTF32) or fp32 CUDA cores")
     return p.parse_args()
 
 
 def workload(a: argparse.Namespace) -> dict:
-    return {"workload": f"walker_walk fb_ddpg offline (BASELINE.json configs[1]): obs={a.obs_dim} act={a.action_dim} z={a.z_dim} "
+    cfgname = "configs[1]" if (a.obs_dim, a.action_dim, a.z_dim, a.batch, a.goal_space) == (24, 6, 50, 1024, None) else "variant"
+    goal = f" goal_space={a.goal_space} (goal_dim {GOAL_DIMS.get(a.goal_space, '?')})" if a.goal_space else ""
+    return {"workload": f"fb_ddpg offline update (BASELINE.json {cfgname}): obs={a.obs_dim} act={a.action_dim} z={a.z_dim}{goal} "
                         f"batch={a.batch} hidden=1024 feature=512 backward_hidden=526, {a.episodes}x{a.episode_len}-step synthetic "
-                        "replay resident in HBM, update_every_steps=1",
+                        "replay, update_every_steps=1",
             "global_batch": a.batch, "episodes": a.episodes, "episode_len": a.episode_len}
 
 
@@ -109,45 +122,108 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# the reference algorithm on the host CPU (oracle/ is test infrastructure: only this leg and --impl reference run it)
+# synthetic replay in host memory, reference `_storage` layout: name -> [E, T+1, dim] fp32 (in_memory_replay_buffer.py:126)
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps_per_sec(a: argparse.Namespace, steps: int, warmup: int, budget_s: float = 150.0) -> dict:
+def host_storage(a: argparse.Namespace, episodes: int, seed: int, physics_dim: int = 0) -> dict:
+    import numpy as np
+    rs = np.random.default_rng(seed)
+    E, R = episodes, a.episode_len + 1
+    st = {"observation": rs.standard_normal((E, R, a.obs_dim), dtype=np.float32),
+          "action": rs.random((E, R, a.action_dim), dtype=np.float32) * 2 - 1,
+          "reward": rs.random((E, R, 1), dtype=np.float32),
+          "discount": np.ones((E, R, 1), np.float32)}
+    if a.goal_space:
+        st["goal"] = rs.standard_normal((E, R, GOAL_DIMS[a.goal_space]), dtype=np.float32)
+    if physics_dim:
+        st["physics"] = np.zeros((E, R, physics_dim), np.float32)   # the reference's sample() always reads it (:166)
+    return st
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference on the host CPU / on cuda through PyTorch eager.  oracle/ is test infrastructure: only these legs run it.
+# ---------------------------------------------------------------------------------------------------------------------
+def reference_staged() -> bool:
+    if os.environ.get("FB_BENCH_FORCE_PORT"):   # calibration runs: time the oracle port although the reference is staged
+        return False
+    return os.path.isfile(os.path.join(REF_DIR, "url_benchmark", "agent", "fb_ddpg.py"))
+
+
+def _all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is one process on the host cores, so it takes all of them."""
+    import torch
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def make_reference_agent(a: argparse.Namespace, device: str, storage: dict):
+    """(update callable, kind, description): the UNMODIFIED reference (baseline/_ref, imported under oracle/ref_shim.py's stubs for
+    hydra / omegaconf / dm_env / dmc / goals) when staged, else the oracle port (torch-CPU restatement of the same op sequence)."""
     import numpy as np
     import torch
+    E = storage["discount"].shape[0]
+    if reference_staged():
+        os.environ["FB_REFERENCE_ROOT"] = REF_DIR
+        from oracle import ref_shim
+        R = ref_shim.load()
+        torch.manual_seed(1)
+        np.random.seed(1)
+        cfg = R.FBDDPGAgentConfig(obs_type="states", obs_shape=(a.obs_dim,), action_shape=(a.action_dim,), device=device, use_tb=False,
+                                  use_wandb=False, use_hiplog=False, num_expl_steps=0, update_encoder=False, goal_space=a.goal_space,
+                                  z_dim=a.z_dim, batch_size=a.batch, update_every_steps=1)
+        agent = R.FBDDPGAgent(**dataclasses.asdict(cfg))
+        rb = R.ReplayBuffer(max_episodes=E, discount=0.98, future=0.99)
+        rb._storage = dict(storage)           # filled directly, as ReplayBuffer.load() fills it (in_memory_replay_buffer.py:192-208)
+        rb._episodes_length[:] = a.episode_len
+        rb._idx, rb._full = 0, True
+        return (lambda i: agent.update(rb, i)), "reference", (
+            f"unmodified url_benchmark FBDDPGAgent.update + ReplayBuffer.sample (baseline/_ref under oracle/ref_shim.py), device={device}")
+    if device != "cpu":
+        raise RuntimeError("baseline/_ref is not staged (run __graft_entry__.build() in the container): no reference for device=cuda")
     from oracle import fb_oracle as O
     torch.manual_seed(1)
     np.random.seed(1)
-    d = O.Dims(obs_dim=a.obs_dim, action_dim=a.action_dim, z_dim=a.z_dim, goal_dim=a.obs_dim)
-    agent = O.OracleAgent(O.OracleConfig(dims=d, batch_size=a.batch, metrics=False))
-    n_ep = 50
-    replay = O.OracleReplay(n_ep, 0.98, 0.99)
-    rng = np.random.RandomState(0)
-    for _ in range(n_ep):
-        replay.add_episode(O.synthetic_episode(rng, a.episode_len, d))
+    gd = GOAL_DIMS[a.goal_space] if a.goal_space else a.obs_dim
+    d = O.Dims(obs_dim=a.obs_dim, action_dim=a.action_dim, z_dim=a.z_dim, goal_dim=gd)
+    agent = O.OracleAgent(O.OracleConfig(dims=d, batch_size=a.batch, metrics=False, use_goal=bool(a.goal_space)))
+    replay = O.OracleReplay(E, 0.98, 0.99)
+    for e in range(E):
+        replay.add_episode({k: v[e] for k, v in storage.items() if k != "physics"})
+    return (lambda i: agent.update(replay, i)), "port", "oracle/fb_oracle.py OracleAgent (the reference's torch-CPU op sequence restated)"
+
+
+def time_reference(a: argparse.Namespace, device: str, steps: int, warmup: int, budget_s: float, episodes: int) -> dict:
+    import torch
+    threads = _all_host_threads()
+    storage = host_storage(a, episodes, seed=0, physics_dim=18)
+    update, kind, what = make_reference_agent(a, device, storage)
+    sync = (lambda: torch.cuda.synchronize()) if device != "cpu" else (lambda: None)
     t0 = time.perf_counter()
     for i in range(max(warmup, 1)):
-        agent.update(replay, i)
+        update(i)
+    sync()
     per = (time.perf_counter() - t0) / max(warmup, 1)
     done = steps
     if per * steps > budget_s:
         done = max(3, int(budget_s / per))
     t0 = time.perf_counter()
     for i in range(done):
-        agent.update(replay, i)
+        update(i)
+    sync()
     dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": UNIT, "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
-            "steps": done, "ms_per_step": 1e3 * dt / done,
-            "sample": f"{done} full agent.update() steps at batch={a.batch} (oracle/fb_oracle.py OracleAgent = the reference's "
-                      f"torch-CPU op sequence, {torch.get_num_threads()} threads) on a {n_ep}x{a.episode_len}-step synthetic replay"}
+    return {"value": done / dt, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": kind, "steps": done,
+            "ms_per_step": 1e3 * dt / done,
+            "sample": f"{done} full agent.update() steps at batch={a.batch} of {what}, {threads} torch threads, on a "
+                      f"{episodes}x{a.episode_len}-step synthetic replay in host memory"}
 
 
 def run_reference(a: argparse.Namespace) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_steps_per_sec(a, a.steps, a.warmup)
+    r = time_reference(a, "cpu", a.steps, a.warmup, budget_s=150.0, episodes=a.episodes)
     cfg = workload(a)
-    cfg["parallelism"] = f"host CPU, {r['cores']} torch threads"
+    cfg["parallelism"] = f"host CPU, {r['cores']} torch threads (torch.set_num_threads(os.cpu_count()), whatever the launcher exported)"
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": r["steps"],
             "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
@@ -164,18 +240,102 @@ class HostReplay:
     fancy-index gathers returning numpy arrays), for the end-to-end leg: every step's batch is gathered on the host and
     crosses PCIe inside the timed region."""
 
-    def __init__(self, obs, action, reward, discount, gamma: float) -> None:
-        self.obs, self.action, self.reward, self.discount = obs, action, reward, discount
+    def __init__(self, storage: dict, gamma: float) -> None:
+        self.s = storage
         self._discount, self._future = gamma, 1.0
 
     def sample(self, batch_size: int):
         import numpy as np
         from controllable_agent_b200 import EpisodeBatch
-        E, R = self.obs.shape[:2]
+        s = self.s
+        E, R = s["observation"].shape[:2]
         ep = np.random.randint(0, E, size=batch_size)
         t = np.random.randint(0, R - 1, size=batch_size) + 1
-        return EpisodeBatch(obs=self.obs[ep, t - 1], action=self.action[ep, t], reward=self.reward[ep, t],
-                            discount=self.discount[ep, t] * self._discount, next_obs=self.obs[ep, t])
+        goal = s["goal"][ep, t - 1] if "goal" in s else None
+        next_goal = s["goal"][ep, t] if "goal" in s else None
+        return EpisodeBatch(obs=s["observation"][ep, t - 1], action=s["action"][ep, t], reward=s["reward"][ep, t],
+                            discount=s["discount"][ep, t] * self._discount, next_obs=s["observation"][ep, t], goal=goal, next_goal=next_goal)
+
+
+def parity_check(agent, a: argparse.Namespace, world: int, rank: int, dev) -> dict:
+    """Two gradient steps from the current parameter snapshot on uploaded inputs (rows, z, action noise; mixing off), run (1) through
+    the N-rank path exactly as the timed region runs it (graph, collectives) and (2) on ONE engine holding the whole global batch;
+    compares the Adam first moments (linear in the two steps' gradients), the parameters, the targets and the losses.  At N = 1 the
+    second run is the eager (no-graph) launch sequence of the same engine.  Restores the snapshot afterwards."""
+    import numpy as np
+    import torch
+    from controllable_agent_b200 import _lib as L
+    from controllable_agent_b200.engine import FBStepEngine
+    e = agent.engine
+    n, Bl = a.batch, a.batch // world
+    flats = ("param_fb", "m_fb", "v_fb", "target_fb", "param_actor", "m_actor", "v_actor")
+    snap = {k: getattr(e, k).clone() for k in flats}
+    steps0 = e.get_adam_steps()
+    g = torch.Generator().manual_seed(4242)   # identical on every rank
+    G = agent.goal_dim if a.goal_space else 0
+    obs, nobs = torch.randn(n, a.obs_dim, generator=g), torch.randn(n, a.obs_dim, generator=g)
+    act = torch.rand(n, a.action_dim, generator=g) * 2 - 1
+    disc = 0.98 * (torch.rand(n, 1, generator=g) > 0.02).float()
+    goal, ngoal = (torch.randn(n, G, generator=g), torch.randn(n, G, generator=g)) if G else (None, None)
+    z = torch.randn(n, a.z_dim, generator=g)
+    z = (a.z_dim ** 0.5) * z / z.norm(dim=1, keepdim=True)
+    nf, na = torch.randn(n, a.action_dim, generator=g), torch.randn(n, a.action_dim, generator=g)
+    mask = (L.PHASE_ALL & ~L.PHASE_SAMPLE)
+
+    def feed(eng, sl: slice, rows: int) -> None:
+        eng.set_scalars(0.2, 0.3, 1e-4, 1e-4, 1e-4, 0.01)
+        eng.set_batch(obs[sl], act[sl], disc[sl], nobs[sl], goal[sl] if G else None, ngoal[sl] if G else None)
+        eng.set_z(z[sl])
+        eng.set_noise(nf[sl], na[sl])
+        eng.set_indices(perm=np.arange(rows, dtype=np.int32), mix_mask=np.zeros(rows, np.int32))
+
+    def run_two(eng, runner) -> dict:
+        ms = []
+        for _ in range(2):
+            runner()
+            torch.cuda.synchronize(dev)
+            ms.append(eng.read_metrics())
+        out = {k: getattr(eng, k).clone() for k in ("m_fb", "m_actor", "param_fb", "param_actor", "target_fb")}
+        out["metrics"] = ms
+        return out
+
+    def restore(eng) -> None:
+        for k, v in snap.items():
+            getattr(eng, k).copy_(v)
+        eng.set_adam_steps(*steps0)
+
+    feed(e, slice(rank * Bl, (rank + 1) * Bl), Bl)
+    got = run_two(e, lambda: agent._run(mask))
+    if world > 1:
+        got["metrics"] = [agent._reduce_metrics(m) for m in got["metrics"]]
+    restore(e)
+    res: dict = {"world": world, "steps": 2, "tol": PARITY_TOL}
+    if rank == 0:
+        if world > 1:
+            ref_eng = FBStepEngine(dataclasses.replace(e.cfg, batch=n, global_batch=None, row_offset=0, nccl=None, p2p=None), dev)
+            restore(ref_eng)
+            feed(ref_eng, slice(0, n), n)
+            ref = run_two(ref_eng, lambda: ref_eng.run(mask, graph=False))
+            res["against"] = "one engine, whole global batch, eager launches"
+        else:
+            feed(e, slice(0, n), n)
+            ref = run_two(e, lambda: e.run(mask, graph=False))
+            restore(e)
+            res["against"] = "the same engine, eager launches instead of the CUDA graph"
+
+        def rel(x, y) -> float:
+            return float((x.double() - y.double()).norm() / y.double().norm().clamp_min(1e-30))
+        errs = {k: rel(got[k], ref[k]) for k in ("m_fb", "m_actor", "param_fb", "param_actor", "target_fb")}
+        for s_ in range(2):
+            for k in ("fb_loss", "actor_loss"):
+                r_ = ref["metrics"][s_][k]
+                errs[f"{k}[{s_}]"] = abs(got["metrics"][s_][k] - r_) / max(abs(r_), 1e-30)
+        res["rel_err"] = {k: float(f"{v:.3e}") for k, v in errs.items()}
+        res["max_rel"] = max(errs.values())
+        res["ok"] = bool(res["max_rel"] <= PARITY_TOL) and all(np.isfinite(v) for v in errs.values())
+        if world > 1:
+            ref_eng.close()
+    return res
 
 
 def run_ours(a: argparse.Namespace) -> None:
@@ -206,19 +366,37 @@ def run_ours(a: argparse.Namespace) -> None:
                "action": torch.rand((E, R, a.action_dim), device=dev, generator=g) * 2 - 1,
                "reward": torch.rand((E, R, 1), device=dev, generator=g),
                "discount": torch.ones((E, R, 1), device=dev)}
+    if a.goal_space:
+        storage["goal"] = torch.randn((E, R, GOAL_DIMS[a.goal_space]), device=dev, generator=g)
     replay.load_storage(storage)
     del storage
     common = dict(obs_type="states", obs_shape=(a.obs_dim,), action_shape=(a.action_dim,), device=str(dev), num_expl_steps=0,
-                  update_encoder=True, goal_space=None, update_every_steps=1, batch_size=a.batch, z_dim=a.z_dim,
+                  update_encoder=True, goal_space=a.goal_space, update_every_steps=1, batch_size=a.batch, z_dim=a.z_dim,
                   use_cuda_graph=not a.no_graph)
-    agent = FBDDPGAgent(use_tb=False, use_wandb=False, use_hiplog=False, rng_mode="device", mlp_mode=a.mlp_mode, collectives=a.collectives,
-                        **common)
+    if a.collectives != "auto":
+        common["collectives"] = a.collectives
+    agent = FBDDPGAgent(use_tb=False, use_wandb=False, use_hiplog=False, rng_mode="device", mlp_mode=a.mlp_mode, **common)
     eng = agent.engine
 
     def barrier() -> None:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    # ---- parity self-check: the N-rank path against one engine on the whole batch (the only place real NCCL / P2P ranks exist) ----
+    parity = None
+    if not a.no_parity_check:
+        parity = parity_check(agent, a, world, rank, dev)
+        ok = torch.tensor([1 if (rank != 0 or parity.get("ok", False)) else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "parity_check failed", "parity_check": parity}), flush=True)
+            if world > 1:
+                dist.destroy_process_group()
+            raise SystemExit(3)
+        barrier()
 
     # ---- device-resident leg: `value` --------------------------------------------------------------------------------
     for i in range(max(a.warmup, 3)):
@@ -241,10 +419,8 @@ def run_ours(a: argparse.Namespace) -> None:
 
     # ---- end-to-end leg: host buffers, H2D of the step's inputs and D2H of its metrics inside the timed region -------
     e2e_steps = a.e2e_steps or min(a.steps, 100)
-    rs = np.random.RandomState(7 + rank)
-    Eh = min(E, 200)
-    host = HostReplay(rs.standard_normal((Eh, R, a.obs_dim)).astype(np.float32), rs.uniform(-1, 1, (Eh, R, a.action_dim)).astype(np.float32),
-                      rs.uniform(0, 1, (Eh, R, 1)).astype(np.float32), np.ones((Eh, R, 1), np.float32), 0.98)
+    hstore = host_storage(a, E, seed=7 + rank, physics_dim=18 if (rank == 0 and world == 1 and not a.no_cpu_baseline) else 0)
+    host = HostReplay(hstore, 0.98)
     agent.cfg.use_tb = True          # metrics on: one D2H read of the step's losses per step
 
     def e2e_leg(prefetch: bool) -> float:
@@ -266,12 +442,12 @@ def run_ours(a: argparse.Namespace) -> None:
         e2e_leg.metrics = m_
         return float(t.item())
 
-    e2e_ms_serial = e2e_leg(False)   # sample -> upload -> step -> read, strictly in sequence (the reference's own order)
-    e2e_ms = e2e_leg(True)           # the next batch is sampled and uploaded while the step runs (cfg.prefetch_host_batch)
+    e2e_ms = e2e_leg(False)            # default flags: sample -> upload -> step -> read, strictly in sequence (the reference's own order)
+    e2e_ms_prefetch = e2e_leg(True)    # opt-in cfg.prefetch_host_batch: the next batch is sampled and uploaded while the step runs
     m = e2e_leg.metrics
     agent.cfg.prefetch_host_batch = False
     Bl = a.batch // world
-    h2d = 4 * Bl * eng._row_pitch   # one copy of the packed batch rows [obs | action | reward, discount | next_obs], 16-byte aligned fields
+    h2d = 4 * Bl * eng._row_pitch   # one copy of the packed batch rows [obs | action | reward, discount | next_obs (| goals)], 16-byte aligned fields
     d2h = 4 * L.METRIC_COUNT
     agent.cfg.use_tb = False
 
@@ -292,24 +468,30 @@ def run_ours(a: argparse.Namespace) -> None:
             pass
         if "gemm_tc" in by_kind:
             # dominant kernel: the tcgen05 3xTF32 grouped GEMM.  Tensor roofline for fp32-grade products on this kernel:
-            # measured dense bf16 rate / 2 (kind::tf32 runs at half the bf16 rate) / 3 (three MMA chains per product).
-            bf16 = float(peaks.get("bf16_tflops_sustained", 1400.0))
-            src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+            # measured dense bf16 rate / 2 (kind::tf32 runs at half the bf16 rate) / 3 (three MMA chains per product).  The timed
+            # region is tens of milliseconds at full clocks, far from the power-capped steady state: the BURST figure applies.
+            burst = float(peaks.get("bf16_tflops", 1640.0))
+            sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
+            src = "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.64 PFLOP/s burst (B200_PROFILING.md)"
             gk = by_kind["gemm_tc"]
             achieved = gk["flops"] / (gk["ms"] * 1e-3) / 1e12
-            peak = bf16 / 6.0
+            peak = burst / 6.0
             roofline = {"kernel": "k_gemm_tc (tcgen05 kind::tf32, 3xTF32 split, TMA + TMEM): all wide nn.Linear forward / dX / dW products",
                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the step's 29 k_gemm_tc launches of the
-                        # committed ncu --set full capture (profiles/r1d_ncu_key_metrics.csv); algorithmic operand + result bytes
-                        # of the same launches: bytes_per_launch below
-                        "traffic": 19.66e6, "traffic_unit": "bytes/launch (ncu, profiles/r1d_ncu_key_metrics.csv)",
+                        "peak_sustained": sustained / 6.0, "frac_of_sustained": achieved / (sustained / 6.0),
+                        # not measured in this run: bench.py cannot read DRAM counters; the committed ncu --set full capture holds them
+                        "traffic": None,
+                        "traffic_from_profile": {"bytes_per_launch": 19.66e6, "source": "profiles/r1d_ncu_key_metrics.csv (dram__bytes_read.sum + "
+                                                 "dram__bytes_write.sum averaged over a step's k_gemm_tc launches; an earlier capture, not this run)"},
                         "algorithmic_bytes_per_launch": gk["bytes"] / gk["launches"],
-                        "peak_source": f"{src} = {bf16:.1f} TFLOP/s dense bf16; /2 for tf32, /3 for the three chains of an fp32-grade product "
-                                       "(achieved counts each algorithmic fp32 FLOP once)",
-                        "achieved_tensor_tflops_tf32": 3.0 * achieved, "frac_of_tf32_peak": 3.0 * achieved / (bf16 / 2.0),
+                        "peak_source": f"{src} = {burst:.1f} TFLOP/s dense bf16; /2 for tf32, /3 for the three chains of an fp32-grade product "
+                                       "(achieved counts each algorithmic fp32 FLOP once); timing = CUDA events around each eager launch "
+                                       "(each carries ~4 us of event overhead)",
+                        "achieved_tensor_tflops_tf32": 3.0 * achieved, "frac_of_tf32_peak": 3.0 * achieved / (burst / 2.0),
                         "launches_per_step": gk["launches"], "avg_launch_us": 1e3 * gk["ms"] / gk["launches"],
-                        "algorithmic_gflop_per_step": gk["flops"] / 1e9, "share_of_step": gk["ms"] / total_ms}
+                        "algorithmic_gflop_per_step": gk["flops"] / 1e9, "share_of_step": gk["ms"] / total_ms,
+                        "step_level": {"achieved": gk["flops"] / (ms_total / a.steps * 1e-3) / 1e12, "frac": gk["flops"] / (ms_total / a.steps * 1e-3) / 1e12 / peak,
+                                       "note": "all GEMM FLOPs of a step / the graph-replayed step time (no event overhead)"}}
         elif "gemm" in by_kind:
             import ctypes as C
             peak = C.c_double()
@@ -328,26 +510,37 @@ def run_ours(a: argparse.Namespace) -> None:
             roofline["secondary"] = {"kernel": "k_adam (Adam + target soft update + gradient clear)", "bound": "hbm",
                                      "achieved": ak["bytes"] / (ak["ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                      "frac": ak["bytes"] / (ak["ms"] * 1e-3) / 1e9 / hbm}
-        cpu = None
+        cpu = cuda_eager = None
         if world == 1 and not a.no_cpu_baseline:
-            cpu = cpu_reference_steps_per_sec(a, a.cpu_steps, 2, budget_s=40.0)
-            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")}
+            del host, hstore
+            r_ = time_reference(a, "cpu", a.cpu_steps, 2, budget_s=30.0, episodes=a.episodes)
+            cpu = {k: r_[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample")}
+            if not a.no_cuda_eager:
+                # the Blackwell bar of SURVEY.md 2a / 8d: the same unmodified reference with device=cuda (PyTorch eager kernels), on this GPU
+                try:
+                    r_ = time_reference(a, str(dev), 60, 5, budget_s=30.0, episodes=a.episodes)
+                    cuda_eager = {k: r_[k] for k in ("value", "unit", "kind", "sample")}
+                    cuda_eager["note"] = "reference FBDDPGAgent on device=cuda through PyTorch eager; host replay + EpisodeBatch.to(device) per step, as the reference runs it"
+                except Exception as exc:   # noqa: BLE001 — a reported leg, never fatal
+                    cuda_eager = {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
         cfg = workload(a)
-        cfg.update({"parallelism": f"dp{world} (batch rows sharded; all-gather of the F/B row blocks + all-reduce of the flat gradients, "
-                                   f"collectives={a.collectives})" if world > 1 else "single GPU", "per_gpu_batch": Bl, "cuda_graph": not a.no_graph,
+        coll = getattr(agent, "collectives_mode", a.collectives)
+        cfg.update({"parallelism": f"dp{world} (batch rows sharded; exchange of the F/B row blocks + reduction of the flat gradients, "
+                                   f"collectives={coll})" if world > 1 else "single GPU", "per_gpu_batch": Bl, "cuda_graph": not a.no_graph,
                     "rng": "device Philox inside the step graph", "mlp_mode": a.mlp_mode,
+                    "replay": f"value: {a.episodes} episodes resident in HBM (sharded {a.episodes // world}/rank); e2e: {E} episodes/rank in host memory",
                     "l2": "inputs exceed L2: each step gathers random rows of a replay far larger than the 126 MB L2; weights and "
                           "activations are re-used step to step exactly as in training"})
         line = {"metric": METRIC, "value": a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": {"value": e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "steps": e2e_steps, "value_without_prefetch": e2e_steps / (e2e_ms_serial * 1e-3),
-                        "path": "FBDDPGAgent.update(host_replay, step): host numpy sample() -> pinned packed rows -> one H2D -> step graph (device RNG) -> "
-                                "metrics block D2H, every step; value: agent.prefetch_host_batch=True (the next step's sample + upload is "
-                                "issued while this step runs on the GPU), value_without_prefetch: strictly serial"},
+                        "d2h_bytes_per_step": d2h, "steps": e2e_steps, "value_with_prefetch": e2e_steps / (e2e_ms_prefetch * 1e-3),
+                        "path": "FBDDPGAgent.update(host_replay, step) at default flags: host numpy sample() -> pinned packed rows -> one H2D -> "
+                                "step graph (device RNG) -> metrics block D2H, strictly in sequence every step; value_with_prefetch: the opt-in "
+                                "agent.prefetch_host_batch=True (next step's sample + upload issued while this step runs on the GPU)"},
                 "gpu_launches": launches_per_step * a.steps, "launches_per_step": launches_per_step,
-                "roofline": roofline, "cpu_baseline": cpu,
+                "roofline": roofline, "cpu_baseline": cpu, "reference_cuda_eager": cuda_eager, "parity_check": parity,
                 "breakdown_ms": {k: round(v["ms"], 4) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1]["ms"])},
                 "last_metrics": {k: m.get(k) for k in ("fb_loss", "actor_loss")}}
         print(json.dumps(line), flush=True)

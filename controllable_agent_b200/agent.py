@@ -120,6 +120,18 @@ def register_hydra() -> None:
 _UNSUPPORTED = {"boltzmann": False, "debug": False}
 
 
+class _EngineAdam(torch.optim.Adam):
+    """A real torch.optim.Adam (init_from / checkpoint code looks for Optimizer instances, fb_ddpg.py:173-175) whose moments are views
+    of the flat segments the CUDA step updates.  The Adam step COUNT lives on the device; `state_dict()` refreshes the per-parameter
+    `step` entries from it first, so whoever saves or copies the optimizer sees consistent bias corrections."""
+    _refresh: tp.Optional[tp.Callable[[], None]] = None
+
+    def state_dict(self) -> tp.Dict[str, tp.Any]:   # type: ignore[override]
+        if self._refresh is not None:
+            self._refresh()
+        return super().state_dict()
+
+
 class FBDDPGAgent:
 
     def __init__(self, **kwargs: tp.Any) -> None:
@@ -204,10 +216,11 @@ class FBDDPGAgent:
         # real torch optimizers (init_from / checkpoints look for them in __dict__, fb_ddpg.py:173-175); their state
         # tensors are views of the flat Adam moments the CUDA step updates
         self.encoder_opt: tp.Optional[torch.optim.Adam] = None
-        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=cfg.lr)
-        self.fb_opt = torch.optim.Adam([{"params": self.forward_net.parameters()},
-                                        {"params": self.backward_net.parameters(), "lr": cfg.lr_coef * cfg.lr}], lr=cfg.lr)
+        self.actor_opt = _EngineAdam(self.actor.parameters(), lr=cfg.lr)
+        self.fb_opt = _EngineAdam([{"params": self.forward_net.parameters()},
+                                   {"params": self.backward_net.parameters(), "lr": cfg.lr_coef * cfg.lr}], lr=cfg.lr)
         self._link_optimizer_state()
+        self.actor_opt._refresh = self.fb_opt._refresh = self._sync_optimizer_steps
         self.train()
         self.forward_target_net.train()
         self.backward_target_net.train()
@@ -425,6 +438,8 @@ class FBDDPGAgent:
         e.set_batch(obs, action, discount, next_obs, next_goal if use_goal else None, next_goal if use_goal else None)
         e.set_z(z)
         e.set_indices(mix_mask=np.zeros(e.cfg.batch, np.int32))
+        if self.cfg.future_ratio > 0:   # z is used as given: no hindsight rows either (the mask of the last update() must not linger)
+            e.set_future_mask(np.zeros(e.cfg.batch, np.int32))
         shape = (e.cfg.batch, self.action_dim)
         # update_fb's and update_actor's N(0,1) draws (utils.py:178), consumed from the device generator in that order
         e.set_noise(_standard_normal(shape, dtype=torch.float32, device=e.device),
@@ -476,6 +491,9 @@ class FBDDPGAgent:
             return metrics
         B = e.cfg.batch
         fused = isinstance(replay_loader, ReplayBuffer)
+        if c.future_ratio > 0 and float(getattr(replay_loader, "_future", 0.0)) >= 1.0:
+            # the reference asserts `future_goal is not None` (fb_ddpg.py:463): a replay with future = 1 samples no future rows
+            raise ValueError("agent.future_ratio > 0 needs a replay buffer created with future < 1 (it samples no future_obs / future_goal)")
         if fused:
             self._set_scalars(step, float(replay_loader._discount), float(replay_loader._future))
             key = (id(replay_loader), replay_loader._version, len(replay_loader))

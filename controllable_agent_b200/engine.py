@@ -47,10 +47,25 @@ class EngineConfig:
     global_batch: tp.Optional[int] = None   # multi-GPU: rows of all ranks; None = batch
     row_offset: int = 0                     # multi-GPU: global index of local row 0
     nccl: tp.Optional[tp.Tuple[bytes, int, int]] = None   # (128-byte unique id, world, rank): collectives inside the step graph
+    p2p: tp.Optional[tp.Tuple[int, int]] = None           # (world, rank): exchange by the library's own kernels over NVLink peer memory
 
 
 def _ptr(t: tp.Optional[torch.Tensor]) -> tp.Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+def _on_device(fn: tp.Callable) -> tp.Callable:
+    """Run a method with the engine's device current: the library launches on streams / with handles of THAT device, whatever
+    device the caller's thread has selected (cfg.device='cuda:1' while device 0 is current)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self: "FBStepEngine", *args: tp.Any, **kwargs: tp.Any) -> tp.Any:
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapped
 
 
 class FBStepEngine:
@@ -61,6 +76,8 @@ class FBStepEngine:
                                f"(got device={device!r})")
         if not torch.cuda.is_available():
             raise RuntimeError("CUDA is not available: controllable_agent_b200 has no CPU fallback")
+        if self.device.index is None:   # "cuda" -> the indexed current device: tensor.device comparisons and stream lookups need the index
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.lib = L.load()
         self.cfg = cfg
         c = L.fb_config(abi_version=L.FB_ABI_VERSION, batch=cfg.batch, global_batch=cfg.global_batch or cfg.batch,
@@ -167,6 +184,7 @@ class FBStepEngine:
         return torch.as_strided(flat, (rows.value, cols.value), (ld.value, 1))
 
     # -- per-step inputs -------------------------------------------------------------------------
+    @_on_device
     def set_scalars(self, stddev: float, stddev_clip: float, lr_forward: float, lr_backward: float, lr_actor: float,
                     tau: float, replay_discount: float = 1.0, replay_future: float = 1.0, grad_scale: float = 1.0) -> None:
         key = (stddev, stddev_clip, lr_forward, lr_backward, lr_actor, tau, replay_discount, replay_future, grad_scale)
@@ -180,7 +198,7 @@ class FBStepEngine:
         if x is None:
             return None
         t = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x)
-        if t.device != self.device:   # through a pinned staging ring so that the upload is asynchronous
+        if not (t.device.type == "cuda" and t.device.index == self.device.index):   # through a pinned staging ring so that the upload is asynchronous
             if self._idx_stage is None:
                 self._idx_stage = torch.empty((16, self.cfg.batch), dtype=torch.int32).pin_memory()
                 self._idx_slot = 0
@@ -202,18 +220,20 @@ class FBStepEngine:
         if x is None:
             return None
         t = torch.as_tensor(x)
-        if t.device != self.device:   # host -> device: asynchronous when the source is pinned, ordered on the current stream
+        if not (t.device.type == "cuda" and t.device.index == self.device.index):   # host -> device: asynchronous when the source is pinned, ordered on the current stream
             t = t.to(device=self.device, dtype=torch.float32, non_blocking=True)
         t = t.to(dtype=torch.float32).contiguous()
         assert t.numel() == self.cfg.batch * cols, (tuple(t.shape), self.cfg.batch, cols)
         return t
 
+    @_on_device
     def set_indices(self, ep_idx: tp.Any = None, step_idx: tp.Any = None, future_idx: tp.Any = None, perm: tp.Any = None,
                     mix_mask: tp.Any = None) -> None:
         ts = [self._dev_i32(x) for x in (ep_idx, step_idx, future_idx, perm, mix_mask)]
         L.check(self.lib.fb_set_indices(self.h, *[_ptr(t) for t in ts], self._stream()), "fb_set_indices")
         self._keepalive = ts  # copies are enqueued on the stream; keep the sources alive until the next call
 
+    @_on_device
     def set_batch(self, obs: tp.Any, action: tp.Any, discount: tp.Any, next_obs: tp.Any, goal: tp.Any = None,
                   next_goal: tp.Any = None) -> None:
         c = self.cfg
@@ -224,6 +244,7 @@ class FBStepEngine:
         L.check(self.lib.fb_set_batch(self.h, *[_ptr(t) for t in ts], self._stream()), "fb_set_batch")
         self._keepalive_batch = ts
 
+    @_on_device
     def upload_batch(self, obs: tp.Any, action: tp.Any, discount: tp.Any, next_obs: tp.Any, goal: tp.Any = None,
                      next_goal: tp.Any = None, future_obs: tp.Any = None, future_goal: tp.Any = None) -> int:
         """Host arrays of one sampled batch (EpisodeBatch fields, replay_buffer.py:27-40) -> the step's packed batch
@@ -262,11 +283,13 @@ class FBStepEngine:
         self._row_events[slot] = ev
         return 4 * c.batch * self._row_pitch
 
+    @_on_device
     def set_future_mask(self, mask: tp.Any) -> None:
         t = self._dev_i32(mask)
         L.check(self.lib.fb_set_future_mask(self.h, _ptr(t), self._stream()), "fb_set_future_mask")
         self._keepalive_future = t
 
+    @_on_device
     def set_mix_weights(self, weight: tp.Any, row_scale: tp.Any) -> None:
         """rand_weight with host RNG: the [batch, batch] U(0,1) weight rows and [batch] row scales (fb_ddpg.py:477-480)."""
         B = self.cfg.batch
@@ -276,34 +299,41 @@ class FBStepEngine:
         L.check(self.lib.fb_set_mix_weights(self.h, _ptr(w), _ptr(u), self._stream()), "fb_set_mix_weights")
         self._keepalive_mixw = (w, u)
 
+    @_on_device
     def set_z(self, z: tp.Any) -> None:
         t = self._dev_f32(z, self.cfg.z_dim)
         L.check(self.lib.fb_set_z(self.h, _ptr(t), self._stream()), "fb_set_z")
         self._keepalive_z = t
 
+    @_on_device
     def set_noise(self, noise_fb: tp.Any = None, noise_actor: tp.Any = None) -> None:
         a, b = self._dev_f32(noise_fb, self.cfg.action_dim), self._dev_f32(noise_actor, self.cfg.action_dim)
         L.check(self.lib.fb_set_noise(self.h, _ptr(a), _ptr(b), self._stream()), "fb_set_noise")
         self._keepalive_noise = (a, b)
 
+    @_on_device
     def bind_replay(self, view: "L.fb_replay_view") -> None:
         L.check(self.lib.fb_bind_replay(self.h, C.byref(view), self._stream()), "fb_bind_replay")
 
+    @_on_device
     def set_adam_steps(self, fb_step: int, actor_step: int) -> None:
         L.check(self.lib.fb_set_adam_steps(self.h, fb_step, actor_step, self._stream()), "fb_set_adam_steps")
 
+    @_on_device
     def get_adam_steps(self) -> tp.Tuple[int, int]:
         a, b = C.c_int64(), C.c_int64()
         L.check(self.lib.fb_get_adam_steps(self.h, C.byref(a), C.byref(b), self._stream()), "fb_get_adam_steps")
         return a.value, b.value
 
     # -- the step --------------------------------------------------------------------------------
+    @_on_device
     def run(self, mask: int = L.PHASE_ALL, graph: bool = False) -> None:
         L.check(self.lib.fb_run(self.h, mask, int(graph), self._stream()), f"fb_run(0x{mask:x})")
 
     def launch_count(self, mask: int = L.PHASE_ALL) -> int:
         return self.lib.fb_launch_count(self.h, mask)
 
+    @_on_device
     def profile_ops(self, mask: int = L.PHASE_ALL, reps: int = 5) -> tp.List[tp.Dict[str, tp.Any]]:
         """Per-launch CUDA-event timings of the phases in `mask` (runs the step `reps` times eagerly)."""
         cap = self.launch_count(mask)
@@ -334,6 +364,7 @@ class FBStepEngine:
                            "goal": pin(R, c.goal_dim), "b": pin(R, c.z_dim), "zsum": pin(1, c.z_dim)}
         return self._infer
 
+    @_on_device
     def infer_actor(self, obs: np.ndarray, z: np.ndarray, graph: bool = True) -> np.ndarray:
         """mu = tanh(policy(obs, z)) of the online actor for up to 8 rows (fb_modules.py:110-122): one small upload, the
         FB_PHASE_INFER_ACTOR graph, one small read-back."""
@@ -349,6 +380,7 @@ class FBStepEngine:
         torch.cuda.current_stream(self.device).synchronize()
         return io["mu"][:n].numpy().copy()
 
+    @_on_device
     def infer_backward(self, goal: np.ndarray, graph: bool = True) -> np.ndarray:
         """sqrt(z_dim) * normalize(backward_net(goal)) for up to 8 rows (fb_modules.py:223-230)."""
         io = self._infer_io()
@@ -361,6 +393,7 @@ class FBStepEngine:
         torch.cuda.current_stream(self.device).synchronize()
         return io["b"][:n].numpy().copy()
 
+    @_on_device
     def infer_backward_weighted_sum(self, goal: tp.Any, reward: tp.Any, graph: bool = True) -> np.ndarray:
         """sum_i reward_i * backward_net(goal_i) over N rows (fb_ddpg.py:213-215), in chunks of `batch` rows (the last chunk
         padded with zero rewards)."""
@@ -386,6 +419,7 @@ class FBStepEngine:
     def metrics_tensor(self) -> torch.Tensor:
         return self._metrics
 
+    @_on_device
     def read_metrics(self) -> tp.Dict[str, float]:
         """One D2H copy of the metrics block (replaces the ~19 .item() syncs of fb_ddpg.py:357-377,414-418)."""
         self._metrics_host.copy_(self._metrics, non_blocking=True)

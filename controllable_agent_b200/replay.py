@@ -96,6 +96,26 @@ def load_episode(fn: tp.Any) -> tp.Dict[str, np.ndarray]:
         return {k: data[k] for k in data.keys()}
 
 
+def relabel_episode(env: tp.Any, episode: tp.Dict[str, np.ndarray], goal_func: tp.Any) -> tp.Dict[str, np.ndarray]:
+    """Recompute an episode's rewards (and, with `goal_func`, its goals) by replaying the stored MuJoCo states through the task
+    (same contract as in_memory_replay_buffer.py:40-55).  Env stepping stays on the host, untouched: `env` is the reference's
+    dm_control wrapper (needs `physics.reset_context`, `physics.set_state`, `task.get_reward`)."""
+    states = np.asarray(episode["physics"])
+    rewards = np.empty((states.shape[0], 1), dtype=np.float32)
+    goals: tp.List[np.ndarray] = []
+    for i, state in enumerate(states):
+        with env.physics.reset_context():
+            env.physics.set_state(state)
+        rewards[i, 0] = env.task.get_reward(env.physics)
+        if goal_func is not None:
+            goals.append(np.asarray(goal_func(env), dtype=np.float32))
+    out = dict(episode)
+    out["reward"] = rewards
+    if goals:
+        out["goal"] = np.stack(goals).astype(np.float32)
+    return out
+
+
 def _round4(x: int) -> int:
     return (x + 3) // 4 * 4
 
@@ -132,7 +152,11 @@ class ReplayBuffer:
         self._rows_per_episode = 0
         self._row_stride = 0
         self._version = 0                                # bumped when the device storage is (re)allocated
-        self._staging: tp.Optional[torch.Tensor] = None
+        self._staging: tp.Optional[torch.Tensor] = None  # [2, R, stride] pinned: double-buffered episode uploads
+        self._staging_events: tp.List[tp.Optional[torch.cuda.Event]] = [None, None]
+        self._staging_slot = 0
+        self._storage_cache: tp.Optional[tp.Tuple[int, tp.Dict[str, np.ndarray]]] = None   # (content version, host view)
+        self._content = 0                                # bumped on every write to the device rows
 
     # -- bookkeeping identical to the reference ---------------------------------------------------
     def __len__(self) -> int:
@@ -230,7 +254,8 @@ class ReplayBuffer:
         self._rows = torch.zeros((self._max_episodes, self._rows_per_episode, self._row_stride), dtype=torch.float32,
                                  device=self.device)
         self._ep_len_dev = torch.zeros(self._max_episodes, dtype=torch.int32, device=self.device)
-        self._staging = torch.zeros((self._rows_per_episode, self._row_stride), dtype=torch.float32).pin_memory()
+        self._staging = torch.zeros((2, self._rows_per_episode, self._row_stride), dtype=torch.float32).pin_memory()
+        self._staging_events = [None, None]
         self._version += 1
 
     def _pack_host(self, ep: tp.Mapping[str, np.ndarray], out: np.ndarray) -> None:
@@ -244,10 +269,18 @@ class ReplayBuffer:
 
     def _upload_episode(self, ep: tp.Mapping[str, np.ndarray], slot: int, rows: int) -> None:
         assert self._rows is not None and self._staging is not None
-        stage = self._staging[:rows]
-        torch.cuda.current_stream(self.device).synchronize()   # the previous async copy out of the staging buffer
+        k = self._staging_slot
+        self._staging_slot ^= 1
+        ev = self._staging_events[k]
+        if ev is not None:
+            ev.synchronize()   # only the copy that last read THIS staging block (two episodes ago); the stream itself is never drained
+        stage = self._staging[k, :rows]
         self._pack_host(ep, stage.numpy())
         self._rows[slot, :rows].copy_(stage, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._staging_events[k] = ev
+        self._content += 1
 
     def load_storage(self, storage: tp.Mapping[str, tp.Any], episodes_length: tp.Optional[np.ndarray] = None,
                      n_episodes: tp.Optional[int] = None) -> None:
@@ -279,7 +312,9 @@ class ReplayBuffer:
         lens = self._episodes_length[:n]
         self._is_fixed_episode_length = bool(len(lens) == 0 or lens.min() == lens.max())
         self._ep_len_dev = torch.as_tensor(self._episodes_length, dtype=torch.int32, device=self.device)
-        self._staging = torch.zeros((R, self._row_stride), dtype=torch.float32).pin_memory()
+        self._staging = torch.zeros((2, R, self._row_stride), dtype=torch.float32).pin_memory()
+        self._staging_events = [None, None]
+        self._content += 1
         self._idx = n % self._max_episodes
         self._full = n >= self._max_episodes
         self._collected_episodes = n
@@ -293,12 +328,15 @@ class ReplayBuffer:
         out: tp.Dict[str, np.ndarray] = collections.OrderedDict()
         if self._rows is None:
             return out
+        if self._storage_cache is not None and self._storage_cache[0] == self._content:
+            return self._storage_cache[1]   # drivers read it repeatedly (train_offline.py:95, demo/main.py:108): one D2H per content version
         rows = self._rows.cpu().numpy()
         widths = dict(self._dims, reward=1, discount=1, **dict(self._extra))
         for name, o in self._offsets.items():
             if name != "__extra__":
                 out[name] = np.ascontiguousarray(rows[:, :, o:o + widths[name]])
         out.update(self._host)
+        self._storage_cache = (self._content, out)
         return out
 
     @_storage.setter
@@ -307,7 +345,8 @@ class ReplayBuffer:
 
     def __getstate__(self) -> tp.Dict[str, tp.Any]:
         state = {k: v for k, v in self.__dict__.items()
-                 if k not in ("_rows", "_ep_len_dev", "_staging", "_host", "_device", "_version")}
+                 if k not in ("_rows", "_ep_len_dev", "_staging", "_staging_events", "_staging_slot", "_storage_cache", "_content",
+                              "_host", "_device", "_version")}
         state["_storage"] = dict(self._storage)   # reference pickle layout (pretrain.py:437-449)
         return state
 
@@ -429,24 +468,24 @@ class ReplayBuffer:
         """in_memory_replay_buffer.py:192-208: fill the buffer from a directory of per-episode `.npz` files (sorted by name) until it
         is full.  Episodes are committed through add_episode(), so — unlike the reference, which leaves `_episodes_length` at 0 after
         load() — the lengths, the fixed-length flag and `avg_episode_length` are correct afterwards.
-        `relabel=True` recomputes rewards (and goals) with the reference's own relabel_episode (replay_buffer.py), which needs
-        `env.physics` (dm_control) and therefore the reference package."""
+        `relabel=True` recomputes rewards (and goals) through `env.physics` / `env.task` (relabel_episode above, the contract of
+        in_memory_replay_buffer.py:40-55)."""
         import pathlib
         for eps_fn in sorted(pathlib.Path(replay_dir).glob("*.npz")):
             if self._full:
                 break
             episode = load_episode(eps_fn)
             if relabel:
-                from url_benchmark.replay_buffer import relabel_episode   # MuJoCo state replay: stays on the host, untouched
-                episode = relabel_episode(env, episode, goal_func)
+                episode = relabel_episode(env, episode, goal_func)   # MuJoCo state replay: stays on the host, untouched
             self.add_episode(episode)
 
     def relabel(self, custom_reward: tp.Any) -> None:
         """in_memory_replay_buffer.py:210-216: recompute rewards from stored physics (host loop, as in the reference)."""
         assert self._rows is not None
         o = self._offsets["reward"]
-        for ep_idx, phy in enumerate(self._host["physics"]):
-            reward = np.array([custom_reward.from_physics(p) for p in phy], dtype=np.float32)
-            self._rows[ep_idx, :, o] = torch.as_tensor(reward, device=self.device)
-        self._max_episodes = len(self._host["physics"])
+        physics = self._host["physics"]
+        reward = np.array([[custom_reward.from_physics(p) for p in phy] for phy in physics], dtype=np.float32)   # [E, T+1]
+        self._rows[:len(physics), :, o] = torch.as_tensor(reward).to(self.device, non_blocking=False)
+        self._content += 1
+        self._max_episodes = len(physics)
         self._full = True

@@ -195,3 +195,36 @@ def test_reference_rng_mode_hands_over_the_reference_draws(make_agent, kw):
     np.testing.assert_array_equal(np.asarray(up[1]), ref.action)
     np.testing.assert_array_equal(np.asarray(up[2]), ref.discount)
     np.testing.assert_array_equal(np.asarray(up[3]), ref.next_obs)
+
+
+def test_hindsight_needs_a_replay_with_future_rows(make_agent):
+    """fb_ddpg.py:463 asserts `future_goal is not None`; here: a clear error before anything is launched."""
+    agent = make_agent(future_ratio=0.5)
+    replay = HostReplay(3, with_future=False)
+    replay._future = 1.0
+    with pytest.raises(ValueError, match="future < 1"):
+        agent.update(replay, 0)
+    assert not [c for c in agent.engine.calls if c[0] == "run"]
+
+
+def test_update_fb_on_explicit_tensors_clears_the_hindsight_mask(make_agent):
+    """update_fb promises `z` is used as given: with future_ratio > 0 the hindsight mask of the previous update() is zeroed."""
+    agent = make_agent(future_ratio=0.5)
+    agent.update(HostReplay(4), 0)
+    assert np.asarray(agent.engine.last("set_future_mask")[1][0]).sum() > 0   # update() drew hindsight rows
+    g = torch.Generator().manual_seed(0)
+    obs, nobs = torch.randn(BATCH, D.obs_dim, generator=g), torch.randn(BATCH, D.obs_dim, generator=g)
+    agent.update_fb(obs, torch.zeros(BATCH, D.action_dim), torch.ones(BATCH, 1), nobs, nobs, torch.randn(BATCH, D.z_dim, generator=g), 0)
+    assert np.asarray(agent.engine.last("set_future_mask")[1][0]).sum() == 0
+    assert np.asarray(agent.engine.last("set_indices")[2]["mix_mask"]).sum() == 0
+
+
+def test_optimizer_state_dict_reports_the_device_step_count(make_agent):
+    """fb_opt / actor_opt are real torch optimizers whose `step` entries follow the device-side Adam counters whenever their
+    state_dict() is taken (reference init_from, checkpoint code: fb_ddpg.py:173-175)."""
+    agent = make_agent()
+    assert isinstance(agent.fb_opt, torch.optim.Adam) and isinstance(agent.actor_opt, torch.optim.Optimizer)
+    agent.engine.get_adam_steps = lambda: (7, 5)
+    sd_fb, sd_actor = agent.fb_opt.state_dict(), agent.actor_opt.state_dict()
+    assert {float(s["step"]) for s in sd_fb["state"].values()} == {7.0}
+    assert {float(s["step"]) for s in sd_actor["state"].values()} == {5.0}

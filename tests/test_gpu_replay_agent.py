@@ -459,3 +459,143 @@ def test_unsupported_branches_raise():
         FBDDPGAgent(**{**base, "device": "cpu"})
     with pytest.raises(ValueError):
         FBDDPGAgent(**{**base, "future_ratio": 1.5})
+
+
+class _RefLayoutReplay:
+    """An object with the attribute layout of url_benchmark.in_memory_replay_buffer.ReplayBuffer (:66-88), built from a
+    reference-generated fixture: `_storage` name -> [max_episodes, T+1, dim] numpy, as its pickles hold it."""
+
+    def __init__(self, g, load_filled):
+        n, E = int(g["n_episodes"]), int(g["max_episodes"])
+        eps = [subtree(g, f"ep{i}") for i in range(n)]
+        self._max_episodes, self._discount, self._future = E, 0.98, float(g["future"])
+        self._max_episode_length = None
+        self._storage = {}
+        for name, v in eps[0].items():
+            v = v if v.ndim > 1 else v[:, None]
+            self._storage[name] = np.zeros((E,) + v.shape, np.float32)
+        for i in range(n):   # the ring: episode i lands in slot i % E, as add() / load() write it
+            for name, v in eps[i].items():
+                self._storage[name][i % E] = v if v.ndim > 1 else v[:, None]
+        self._idx, self._full = int(g["idx"]) if "idx" in g else n % E, bool(g["full"])
+        # load()-filled buffers leave the lengths at 0 (in_memory_replay_buffer.py:192-208; SURVEY.md 7.3)
+        self._episodes_length = np.zeros(E, np.int32) if load_filled else np.asarray(g["episodes_length"], np.int32)
+
+    def __len__(self):
+        return self._max_episodes if self._full else self._idx
+
+
+@pytest.mark.parametrize("load_filled", [False, True])
+def test_from_reference_adopts_a_reference_layout_buffer(load_filled):
+    """ReplayBuffer.from_reference on a reference-layout object (an ExORL-style pickle's content): storage lands in HBM, bookkeeping
+    carries over, sample() returns the reference's own draws bit-exactly (no test)."""
+    from controllable_agent_b200 import ReplayBuffer
+    g = load_golden("replay_fixed_goal_full")
+    other = _RefLayoutReplay(g, load_filled)
+    buf = ReplayBuffer.from_reference(other, device="cuda")
+    assert len(buf) == int(g["len"]) and buf._full == bool(g["full"]) and buf._idx == other._idx
+    assert buf._discount == 0.98 and buf._future == float(g["future"]) and buf._is_fixed_episode_length
+    np.testing.assert_array_equal(buf._episodes_length[:len(buf)], np.asarray(g["episodes_length"])[:len(buf)])
+    for draw in range(3):
+        np.random.seed(int(g["seed"]) + 100 + draw)
+        batch = buf.sample(16)
+        ref = subtree(g, f"draw{draw}")
+        for field in ("obs", "action", "reward", "discount", "next_obs", "goal", "next_goal", "future_obs", "future_goal"):
+            if field in ref:
+                np.testing.assert_array_equal(getattr(batch, field).cpu().numpy(), ref[field], err_msg=field)
+    st1 = buf._storage
+    assert buf._storage is st1, "the host view is cached until the device rows change"
+    np.testing.assert_array_equal(st1["observation"], other._storage["observation"])
+    buf.add_episode(subtree(g, "ep0"))
+    assert buf._storage is not st1
+
+
+class _StubEnv:
+    """physics.reset_context / set_state / task.get_reward: what relabel_episode (in_memory_replay_buffer.py:40-55) calls."""
+
+    class _Physics:
+        state = None
+
+        def reset_context(self):
+            import contextlib
+            return contextlib.nullcontext()
+
+        def set_state(self, s):
+            self.state = np.asarray(s)
+
+    class _Task:
+        @staticmethod
+        def get_reward(physics):
+            return float(physics.state.sum()) * 0.5 + 1.0
+
+    def __init__(self):
+        self.physics, self.task = self._Physics(), self._Task()
+
+
+def test_load_with_relabel_recomputes_rewards_and_goals(tmp_path):
+    """ReplayBuffer.load(env, dir) at its DEFAULT relabel=True (the import it relied on does not exist in the reference)."""
+    from controllable_agent_b200 import ReplayBuffer
+    rs = np.random.RandomState(0)
+    eps = []
+    for i in range(3):
+        ep = {"observation": rs.randn(6, 5).astype(np.float32), "action": rs.randn(6, 2).astype(np.float32),
+              "reward": np.zeros((6, 1), np.float32), "discount": np.ones((6, 1), np.float32), "physics": rs.randn(6, 4).astype(np.float32)}
+        np.savez(tmp_path / f"ep{i:02d}.npz", **ep)
+        eps.append(ep)
+    env = _StubEnv()
+    buf = ReplayBuffer(3, 0.98, 1.0)
+    buf.load(env, tmp_path, goal_func=lambda e: e.physics.state[:2] * 2.0)
+    assert len(buf) == 3 and buf._full
+    st = buf._storage
+    for i, ep in enumerate(eps):
+        np.testing.assert_allclose(st["reward"][i, :, 0], ep["physics"].sum(1) * 0.5 + 1.0, rtol=1e-6)
+        np.testing.assert_allclose(st["goal"][i], ep["physics"][:, :2] * 2.0, rtol=1e-6)
+    np.random.seed(5)
+    batch = buf.sample(8)
+    assert batch.goal is not None and batch.reward.shape == (8, 1)
+
+    class _Reward:
+        @staticmethod
+        def from_physics(p):
+            return float(p[0])
+    buf.relabel(_Reward())
+    np.testing.assert_allclose(buf._storage["reward"][:, :, 0], np.stack([ep["physics"][:, 0] for ep in eps]), rtol=1e-6)
+
+
+def test_update_fb_then_update_actor_on_explicit_tensors_against_oracle():
+    """The public update_fb / update_actor pair (fb_ddpg.py:291-421) on explicit tensors, with future_ratio > 0 configured and a
+    stale hindsight mask left behind by update(): z must be used as given."""
+    from controllable_agent_b200 import FBDDPGAgent, ReplayBuffer, _lib as L
+    from gpu_common import read_tensors
+    from oracle import fb_oracle as O
+    d = O.Dims(obs_dim=11, action_dim=3, z_dim=10, goal_dim=11, hidden_dim=48, feature_dim=24, backward_hidden_dim=30)
+    B = 32
+    torch.manual_seed(3)
+    np.random.seed(3)
+    agent = FBDDPGAgent(obs_type="states", obs_shape=(d.obs_dim,), action_shape=(d.action_dim,), device="cuda", num_expl_steps=0,
+                        update_encoder=True, goal_space=None, use_tb=True, use_wandb=False, use_hiplog=False, hidden_dim=d.hidden_dim,
+                        feature_dim=d.feature_dim, backward_hidden_dim=d.backward_hidden_dim, z_dim=d.z_dim, batch_size=B,
+                        update_every_steps=1, future_ratio=0.5, rng_mode="reference")
+    rs = np.random.RandomState(1)
+    replay = ReplayBuffer(4, 0.98, 0.9)
+    for _ in range(4):
+        replay.add_episode(O.synthetic_episode(rs, 20, d))
+    agent.update(replay, 0)   # leaves a hindsight mask and future rows behind
+    cpu = lambda net: {k: v.detach().cpu().clone() for k, v in net.named_parameters()}   # noqa: E731
+    actor, fwd, bwd = cpu(agent.actor), cpu(agent.forward_net), cpu(agent.backward_net)
+    fwd_t, bwd_t = cpu(agent.forward_target_net), cpu(agent.backward_target_net)
+    g = torch.Generator().manual_seed(9)
+    obs, nobs = torch.randn(B, d.obs_dim, generator=g), torch.randn(B, d.obs_dim, generator=g)
+    act = torch.rand(B, d.action_dim, generator=g) * 2 - 1
+    disc = torch.full((B, 1), 0.98)
+    z = O.sample_z(B, d.z_dim, g)
+    m = agent.update_fb(obs, act, disc, nobs, nobs, z, 1)
+    e = agent.engine
+    noise_fb, noise_actor = e.view("noise_fb").cpu(), e.view("noise_actor").cpu()
+    assert rel(e.view("z"), z) < 1e-6, "z is used as given"
+    ora = O.fb_loss_and_grads(fwd, bwd, fwd_t, bwd_t, actor, obs, act, disc, nobs, nobs, z, noise_fb, 0.2, 0.3, 1.0, d.z_dim)
+    assert m["fb_loss"] == pytest.approx(ora["metrics"]["fb_loss"], rel=1e-3)
+    fwd1 = read_tensors(e, L.NET_FORWARD, "param")
+    ma = agent.update_actor(obs, z, 1)
+    ora_a = O.actor_loss_and_grads(actor, fwd1, obs, z, noise_actor, 0.2, 0.3)
+    assert ma["actor_loss"] == pytest.approx(float(ora_a["actor_loss"]), rel=1e-3)
