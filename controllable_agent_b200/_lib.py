@@ -38,6 +38,7 @@ PHASE_ALL = (1 << 10) - 1
 PHASE_INFER_ACTOR, PHASE_INFER_B, PHASE_INFER_BN = 1 << 10, 1 << 11, 1 << 12   # inference plans (run on their own)
 INFER_ROWS = 8
 RUN_HOST_BATCH = 1 << 15   # modifier of PHASE_SAMPLE: batch rows supplied by the caller (fb_upload_batch), gather skipped
+RUN_UNFUSED = 1 << 14      # modifier: every launch of the plan as a kernel of its own (default: fused segments, k_fused_stack)
 
 # index of each scalar of the metrics block (FB_M_* in fb_b200.h) -> key of the dict FBDDPGAgent.update returns
 METRIC_KEYS = ("target_M", "M1", "F1", "B", "B_norm", "z_norm", "fb_loss", "fb_diag", "fb_offdiag", "orth_loss",

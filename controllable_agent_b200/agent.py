@@ -106,6 +106,8 @@ class FBDDPGAgentConfig:
     contract_mode: str = "tcgen05"  # batch x batch contraction: "tcgen05" or "simt"
     collectives: str = "graph"   # multi-GPU exchange: "graph" = the library's own NCCL communicator, all-gather / all-reduce
     #                              captured inside the step graph; "torch" = torch.distributed calls between graph segments
+    fuse_stacks: bool = True    # the MLP stacks as fused persistent kernels (one launch per forward / backward segment of the plan,
+    #                             k_fused_stack); False: one kernel per layer-level launch on main / side / staging lanes
     prefetch_host_batch: bool = False   # host replay only: sample + upload the NEXT update's batch while this update's step runs
     #                                     on the GPU (same numpy draw order as the reference as long as nothing else samples the
     #                                     replay between updates; for a static replay, e.g. train_offline)
@@ -186,7 +188,7 @@ class FBDDPGAgent:
                 nccl = (box[0], self.world, self.rank)
             else:   # NCCL could not be loaded by the library: torch.distributed collectives between graph segments
                 logger.warning("libfb_b200 could not load NCCL; falling back to collectives='torch'")
-        self.engine = FBStepEngine(EngineConfig(nccl=nccl,
+        self.engine = FBStepEngine(EngineConfig(nccl=nccl, fused=bool(cfg.fuse_stacks),
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,

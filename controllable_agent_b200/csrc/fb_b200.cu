@@ -366,6 +366,7 @@ struct Builder {
         fb_launch_pdl(k_transpose_grouped, dim3(ctas), dim3(256), 0, s, td, nt);
         return cudaGetLastError();
       }, FB_OPK_TRANSPOSE, 0.0, tbytes);
+      h->ops[phase].back().dev.set(FS_TRANSPOSE, ctas, FsPtrArgs{td, nt, 0});
     }
     const TcGemmDesc* dd = arena_put(h, v, d_arena);
     const int n = (int)v.size();
@@ -386,6 +387,7 @@ struct Builder {
       cfg.attrs = attr; cfg.numAttrs = getenv("FB_NO_PDL") ? 0 : 1;
       return cudaLaunchKernelEx(&cfg, k_gemm_tc, dd, hdr);
     }, FB_OPK_GEMM_TC, flops, bytes);
+    { FsGemmArgs fa; memset(&fa, 0, sizeof(fa)); fa.descs = dd; fa.hdr = hdr; h->ops[phase].back().dev.set(FS_GEMM_TC, work, fa); }
     if (used_early) h->ops[phase].back().wait_stage = 1;   // operands staged on the staging lane: wait for this phase's staging event
   }
 
@@ -424,6 +426,7 @@ struct Builder {
       else fb_launch_pdl(k_ln_tanh_fwd, dim3(fb_ceil_div(rows, 8)), dim3(256), 0, s, tab, rows);
       return cudaGetLastError();
     }, FB_OPK_LAYERNORM, 0.0, bytes);
+    { FsLnFwdArgs fa; memset(&fa, 0, sizeof(fa)); fa.tab = tab; fa.rows = rows; fa.vec = vec ? 1 : 0; h->ops[phase].back().dev.set(FS_LN_FWD, fb_ceil_div(rows, 8), fa); }
   }
   void ln_bwd(std::vector<LnBwdDesc> v) {
     v.erase(std::remove_if(v.begin(), v.end(), [](const LnBwdDesc& d) { return d.rows <= 0; }), v.end());
@@ -447,6 +450,7 @@ struct Builder {
       else fb_launch_pdl(k_ln_tanh_bwd, dim3(ctas), dim3(256), 0, s, tab);
       return cudaGetLastError();
     }, FB_OPK_LAYERNORM, 0.0, bytes);
+    { FsLnBwdArgs fa; memset(&fa, 0, sizeof(fa)); fa.tab = tab; fa.vec = vec ? 1 : 0; h->ops[phase].back().dev.set(FS_LN_BWD, ctas, fa); }
   }
   void l2_fwd(std::vector<L2Desc> v) {
     int rows = 0;
@@ -457,6 +461,7 @@ struct Builder {
       fb_launch_pdl(k_l2norm_fwd, dim3(fb_ceil_div(rows, 8)), dim3(256), 0, s, dd, n, rows);
       return cudaGetLastError();
     });
+    h->ops[phase].back().dev.set(FS_L2_FWD, fb_ceil_div(rows, 8), FsPtrArgs{dd, n, rows});
   }
   void colsum(std::vector<ColsumDesc> v) {
     v.erase(std::remove_if(v.begin(), v.end(), [](const ColsumDesc& d) { return d.rows <= 0; }), v.end());
@@ -474,6 +479,7 @@ struct Builder {
       fb_launch_pdl(k_colsum, dim3(ctas), dim3(256), 0, s, dd, n);
       return cudaGetLastError();
     }, FB_OPK_COLSUM, 0.0, bytes, 1);  // side lane: bias gradients are leaves of the dependency graph (joined at phase end)
+    h->ops[phase].back().dev.set(FS_COLSUM, ctas, FsPtrArgs{dd, n, 0});
   }
   void memset0(void* p, size_t bytes) {
     push([p, bytes](cudaStream_t s) { return cudaMemsetAsync(p, 0, bytes, s); }, FB_OPK_MEMSET, 0.0, (double)bytes);
@@ -583,6 +589,10 @@ static int build_plan(fb_handle* h) {
   h->d_mix_mask = (int*)ws_alloc(h, B * sizeof(int));
   h->d_future_mask = (int*)ws_alloc(h, B * sizeof(int));
   h->d_perm_keys = (unsigned int*)ws_alloc(h, B * sizeof(int));
+  h->d_prog = (char*)ws_alloc(h, FB_PROG_ARENA_BYTES);
+  h->d_fs_barrier = (unsigned long long*)ws_alloc(h, FS_NUM_BARRIERS * sizeof(unsigned long long));
+  h->d_fs_err = (unsigned int*)ws_alloc(h, 16);
+  h->fused_plans.clear(); h->prog_host.clear(); h->prog_uploaded = 0; h->n_fs_barriers = 0;
 
   // ---- packed batch rows ---------------------------------------------------------------------
   BatchLayout& L = h->bl;
@@ -760,6 +770,7 @@ static int build_plan(fb_handle* h) {
     sp.perm = h->d_perm; sp.mix_override = nullptr; sp.with_future = with_future ? 1 : 0;
     const float* packed = h->packed.p;
     b.push([sp, packed](cudaStream_t s) { fb_launch_pdl(k_stage_inputs, dim3(sp.batch), dim3(128), 0, s, sp, packed); return cudaGetLastError(); });
+    { FsStageInArgs fa; memset(&fa, 0, sizeof(fa)); fa.P = sp; fa.packed = packed; h->ops[b.phase].back().dev.set(FS_STAGE_INPUTS, sp.batch, fa); }
   }
   const bool do_mix = c.mix_ratio > 0.f || with_future;   // one backward_net forward serves the mixing rows and the hindsight rows
   // The z-mixing forward (a chain of five small launches) runs on the side lane while the main lane already computes the
@@ -789,6 +800,7 @@ static int build_plan(fb_handle* h) {
     zp.mix_mask = c.mix_ratio > 0.f ? h->d_mix_mask : nullptr; zp.future_mask = with_future ? h->d_future_mask : nullptr; zp.z = z.p; zp.actor_in_oz = actor_in_oz.p; zp.ldOZ = actor_in_oz.ld; zp.renorm = nz;
     if (deep) { zp.f_in[0] = in_oa.p; zp.f_in[1] = in_noa.p; zp.f_in[2] = in_oa2.p; zp.ldF = in_oa.ld; }
     b.push([zp](cudaStream_t s) { fb_launch_pdl(k_z_final, dim3(fb_ceil_div(zp.batch, 8)), dim3(256), 0, s, zp); return cudaGetLastError(); });
+    { FsZFinalArgs fa; memset(&fa, 0, sizeof(fa)); fa.P = zp; h->ops[b.phase].back().dev.set(FS_Z_FINAL, fb_ceil_div(zp.batch, 8), fa); }
   }
   b.cur_lane = 0;
   // F's obs_action first layer does not read z in the default layout and runs here, next to the z-mixing chain; with
@@ -834,6 +846,7 @@ static int build_plan(fb_handle* h) {
       fb_launch_pdl(k_actor_out, dim3(fb_ceil_div(2 * ap.batch * ap.A, 256)), dim3(256), 0, s, ap, sc);
       return cudaGetLastError();
     });
+    { FsActorOutArgs fa; memset(&fa, 0, sizeof(fa)); fa.P = ap; fa.sc = sc; h->ops[b.phase].back().dev.set(FS_ACTOR_OUT, fb_ceil_div(2 * ap.batch * ap.A, 256), fa); }
     h->ops[b.phase].back().wait_stage = 1;   // the zeroed accumulators
   }
   b.gemm({lin_fwd(eFtoa.x, pFt.w(E_OA + 0), pFt.v(E_OA + 1), eFtoa.pre, 0)});
@@ -997,6 +1010,12 @@ static int build_plan(fb_handle* h) {
       fb_launch_pdl(k_l2norm_bwd, dim3(fb_ceil_div(B, 8)), dim3(256), 0, s, p0, p1, p2, ldp, coef, dsum, dB.ld, Bm.p, Bm.ld, bO.nrm, draw.p, draw.ld, B, Z, nz);
       return cudaGetLastError();
     });
+    {
+      FsL2BwdArgs fa; memset(&fa, 0, sizeof(fa));
+      fa.dy0 = p0; fa.dy1 = p1; fa.dy2 = p2; fa.dsum = dsum; fa.y = Bm.p; fa.nrm = bO.nrm; fa.dx = draw.p;
+      fa.lddy = ldp; fa.ldsum = dB.ld; fa.ldy = Bm.ld; fa.lddx = draw.ld; fa.rows = B; fa.Z = Z; fa.normalize = nz; fa.coef = coef;
+      h->ops[b.phase].back().dev.set(FS_L2_BWD, fb_ceil_div(B, 8), fa);
+    }
   }
   b.colsum({mk_colsum(dF1, pF.gv(HD_1 + 3)), mk_colsum(dF2, pF.gv(HD_2 + 3)), mk_colsum(draw, pB.gv(7))});
   b.gemm({lin_dw(dF1, h1F1, pF.gw(HD_1 + 2)), lin_dw(dF2, h1F2, pF.gw(HD_2 + 2)), lin_dw(draw, bO.h2, pB.gw(6)),
@@ -1072,6 +1091,12 @@ static int build_plan(fb_handle* h) {
       fb_launch_pdl(k_actor_q, dim3(fb_ceil_div(B, 8)), dim3(256), 0, s, Fa1.p, Fa2.p, Fa1.ld, z.p, z.ld, dFa1.p, dFa2.p, dFa1.ld, B, Z, inv_n, acc);
       return cudaGetLastError();
     });
+    {
+      FsActorQArgs fa; memset(&fa, 0, sizeof(fa));
+      fa.F1 = Fa1.p; fa.F2 = Fa2.p; fa.z = z.p; fa.dF1 = dFa1.p; fa.dF2 = dFa2.p; fa.acc = acc;
+      fa.ldf = Fa1.ld; fa.ldz = z.ld; fa.lddf = dFa1.ld; fa.rows = B; fa.Z = Z; fa.inv_n = inv_n;
+      h->ops[b.phase].back().dev.set(FS_ACTOR_Q, fb_ceil_div(B, 8), fa);
+    }
     h->ops[b.phase].back().wait_stage = 1;   // the zeroed accumulator
   }
 
@@ -1236,6 +1261,7 @@ static int build_plan(fb_handle* h) {
       }
       fb_handle::StageBatch sb;
       sb.avail = av; sb.d_descs = arena_put(h, sub, d_arena); sb.n = (int)sub.size(); sb.ctas = ctas; sb.bytes = tbytes;
+      sb.dev.set(FS_TRANSPOSE, ctas, FsPtrArgs{sb.d_descs, sb.n, 0});
       h->stage_batches[ph].push_back(sb);
     }
   }
@@ -1415,6 +1441,15 @@ int fb_bind(fb_handle* h, const fb_buffers* bufs, void* stream) {
   if (rc != FB_OK) return rc;
   CK(cudaFuncSetAttribute(k_gemm_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   if (h->uses_gemm_tc) CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  if (h->uses_gemm_tc) {
+    CK(cudaFuncSetAttribute(k_fused_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    int dev = 0, sms = 0, per_sm = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_stack, FS_THREADS, TC_SMEM_BYTES));
+    if (per_sm < 1) return FB_E_UNSUPPORTED;
+    h->sm_count = sms;   // one resident CTA per SM: the grid barrier of k_fused_stack needs every CTA of the launch co-resident
+  }
   if (h->contract_smem) CK(cudaFuncSetAttribute(k_contract_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->contract_smem));
   if (h->qloss_smem > 48u * 1024u) CK(cudaFuncSetAttribute(k_qloss_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qloss_smem));
   CK(cudaMemsetAsync(h->ws_base, 0, h->ws_bytes, s));
@@ -1612,11 +1647,168 @@ static cudaError_t run_eager(fb_handle* h, uint32_t mask, cudaStream_t s) {
   return cudaSuccess;
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused execution (fused.cuh): the plan of a phase mask cut into units — fused segments and stand-alone launches
+// ------------------------------------------------------------------------------------------------
+// The walk below issues the launches in exactly the order run_eager does and assigns every fusable launch a STAGE of the current
+// segment: a main-lane launch opens the next stage; a side-lane launch (z-mixing chain, bias column sums) goes to the stage that
+// runs next to the following main-lane launch (fork), or behind the previous launch of its chain; a staging batch runs next to the
+// first launch of the phase that makes its sources final, and its consumers are held behind it.  A launch without a fused form
+// (RNG, replay gather, the contraction, q_loss, SIMT GEMMs, Adam, collectives, metrics) closes the segment and runs as a kernel of
+// its own in stream order — list order is a valid serialisation of the lanes, so any cut is correct.
+struct FusedSegment { std::vector<std::vector<const DevItem*>> stages; };
+
+static int fused_emit_program(fb_handle* h, const FusedSegment& seg) {
+  FsHeader hd; memset(&hd, 0, sizeof(hd));
+  std::vector<FsItem> items;
+  std::vector<char> blob;
+  if (seg.stages.size() > FS_MAX_STAGES) return -1;
+  hd.n_stages = (int)seg.stages.size();
+  for (size_t st = 0; st < seg.stages.size(); ++st) {
+    hd.first_item[st] = (int)items.size();
+    // GEMM items first: their tiles are the long poles of a stage, the block-style items fill the CTAs behind them
+    std::vector<const DevItem*> order;
+    for (auto* it : seg.stages[st]) if (it->type == FS_GEMM_TC) order.push_back(it);
+    for (auto* it : seg.stages[st]) if (it->type != FS_GEMM_TC) order.push_back(it);
+    for (auto* it : order) {
+      FsItem fi; fi.type = it->type; fi.count = it->count; fi.arg_off = (int)blob.size(); fi.arg_bytes = (int)((it->args.size() + 3) / 4 * 4);
+      if (fi.arg_bytes > FS_ARG_WORDS * 4) return -1;
+      blob.insert(blob.end(), it->args.begin(), it->args.end());
+      blob.resize((blob.size() + 15) / 16 * 16);
+      items.push_back(fi);
+    }
+  }
+  hd.first_item[seg.stages.size()] = (int)items.size();
+  hd.n_items = (int)items.size();
+  if (items.size() > FS_MAX_ITEMS) return -1;
+  const size_t base = (h->prog_host.size() + 127) / 128 * 128;
+  const size_t items_off = (sizeof(FsHeader) + 15) / 16 * 16;
+  const size_t args_off = items_off + (items.size() * sizeof(FsItem) + 15) / 16 * 16;
+  hd.items_off = (int)items_off;
+  for (auto& fi : items) fi.arg_off += (int)args_off;
+  if (base + args_off + blob.size() > FB_PROG_ARENA_BYTES) return -1;
+  h->prog_host.resize(base + args_off + blob.size());
+  memcpy(h->prog_host.data() + base, &hd, sizeof(hd));
+  memcpy(h->prog_host.data() + base + items_off, items.data(), items.size() * sizeof(FsItem));
+  memcpy(h->prog_host.data() + base + args_off, blob.data(), blob.size());
+  return (int)base;
+}
+
+static int build_fused_plan(fb_handle* h, uint32_t mask, fb_handle::FusedPlan& plan) {
+  FusedSegment seg;
+  int main_next = 0, side_next = 0;
+  bool side_pending = false;
+  int ready[FB_NUM_PHASES] = {};
+  size_t issued[FB_NUM_PHASES] = {};
+  int rc = FB_OK;
+  auto put = [&](int st, const DevItem* it) {
+    if ((int)seg.stages.size() <= st) seg.stages.resize(st + 1);
+    seg.stages[st].push_back(it);
+  };
+  auto close = [&]() {
+    if (!seg.stages.empty()) {
+      const int off = fused_emit_program(h, seg);
+      if (off < 0 || h->n_fs_barriers >= FS_NUM_BARRIERS) { rc = FB_E_STATE; }
+      else { fb_handle::Unit u; u.program = off; plan.units.push_back(u); plan.barrier_of.push_back(h->n_fs_barriers++); }
+    }
+    seg.stages.clear();
+    main_next = side_next = 0; side_pending = false;
+    for (auto& r : ready) r = 0;
+  };
+  for (int ph = 0; ph < FB_NUM_PHASES; ++ph) {
+    if (!(mask & (1u << ph))) continue;
+    for (int P = ph; P < FB_NUM_PHASES; ++P) {
+      if (!(mask & (1u << P))) continue;
+      auto& sbs = h->stage_batches[P];
+      while (issued[P] < sbs.size() && sbs[issued[P]].avail <= ph) {
+        put(main_next, &sbs[issued[P]].dev);
+        ready[P] = std::max(ready[P], main_next + 1);
+        ++issued[P];
+      }
+    }
+    for (auto& op : h->ops[ph]) {
+      if (op.replay_only && (mask & FB_RUN_HOST_BATCH)) continue;
+      const bool staged = op.wait_stage && !h->stage_batches[ph].empty();
+      if (op.dev.type == FS_NONE) {
+        close();
+        fb_handle::Unit u; u.op = &op; plan.units.push_back(u); plan.barrier_of.push_back(-1);
+        continue;
+      }
+      if (op.lane == 1) {
+        int st = (op.fork || !side_pending) ? std::max(main_next, side_next) : side_next;
+        if (staged) st = std::max(st, ready[ph]);
+        put(st, &op.dev);
+        side_next = st + 1; side_pending = true;
+      } else {
+        int st = main_next;
+        if (op.join && side_pending) { st = std::max(st, side_next); side_pending = false; }
+        if (staged) st = std::max(st, ready[ph]);
+        put(st, &op.dev);
+        main_next = st + 1;
+      }
+    }
+    if (side_pending) { main_next = std::max(main_next, side_next); side_pending = false; }
+    if (!h->stage_batches[ph].empty()) main_next = std::max(main_next, ready[ph]);
+  }
+  close();
+  return rc;
+}
+
+static cudaError_t launch_fused(fb_handle* h, int program, int barrier, cudaStream_t s) {
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(h->sm_count); cfg.blockDim = dim3(FS_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = getenv("FB_NO_PDL") ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, k_fused_stack, (const char*)(h->d_prog + program), h->d_fs_barrier + barrier, h->d_fs_err);
+}
+
+// the fused plan of `mask`, built (and its programs uploaded) on first use
+static int get_fused_plan(fb_handle* h, uint32_t mask, cudaStream_t s, fb_handle::FusedPlan** out) {
+  auto it = h->fused_plans.find(mask);
+  if (it == h->fused_plans.end()) {
+    fb_handle::FusedPlan plan;
+    int rc = build_fused_plan(h, mask, plan);
+    if (rc != FB_OK) return rc;
+    if (h->prog_host.size() > h->prog_uploaded) {
+      CK(cudaMemcpyAsync(h->d_prog + h->prog_uploaded, h->prog_host.data() + h->prog_uploaded, h->prog_host.size() - h->prog_uploaded,
+                         cudaMemcpyHostToDevice, s));
+      CK(cudaStreamSynchronize(s));   // prog_host may reallocate when the next plan is built
+      h->prog_uploaded = h->prog_host.size();
+    }
+    it = h->fused_plans.emplace(mask, std::move(plan)).first;
+  }
+  *out = &it->second;
+  return FB_OK;
+}
+
+static cudaError_t run_fused(fb_handle* h, const fb_handle::FusedPlan& plan, cudaStream_t s) {
+  for (size_t i = 0; i < plan.units.size(); ++i) {
+    const fb_handle::Unit& u = plan.units[i];
+    if (u.program >= 0) CKE(launch_fused(h, u.program, plan.barrier_of[i], s));
+    else CKE((*u.op)(s));
+  }
+  return cudaSuccess;
+}
+
+static bool fused_wanted(const fb_handle* h, uint32_t mask) {
+  static const bool off = getenv("FB_NO_FUSE") != nullptr;
+  if (off || (mask & FB_RUN_UNFUSED) || !h->uses_gemm_tc) return false;
+  return (mask & (FB_PHASE_INFER_ACTOR | FB_PHASE_INFER_B | FB_PHASE_INFER_BN)) == 0;   // a few rows on the SIMT kernel: nothing to fuse
+}
+
 int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream) {
   if (!h || !h->bound) return FB_E_STATE;
   if ((phase_mask & FB_PHASE_SAMPLE) && !(phase_mask & FB_RUN_HOST_BATCH) && !h->replay_bound) return FB_E_STATE;
   cudaStream_t s = (cudaStream_t)stream;
-  if (!use_graph) return (int)run_eager(h, phase_mask, s);
+  const bool fused = fused_wanted(h, phase_mask);
+  fb_handle::FusedPlan* fplan = nullptr;
+  if (fused) {   // before any capture: building the plan uploads its programs
+    int rc = get_fused_plan(h, phase_mask, s, &fplan);
+    if (rc != FB_OK) return rc;
+  }
+  if (!use_graph) return (int)(fused ? run_fused(h, *fplan, s) : run_eager(h, phase_mask, s));
   auto it = h->graphs.find(phase_mask);
   if (it == h->graphs.end()) {
     // capture on a private stream (the caller's may be the legacy default stream, which cannot capture);
@@ -1625,7 +1817,7 @@ int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream) {
     if (!h->capture_stream) CK(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
     cudaStream_t cs = h->capture_stream;
     CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    cudaError_t e = run_eager(h, phase_mask, cs);
+    cudaError_t e = fused ? run_fused(h, *fplan, cs) : run_eager(h, phase_mask, cs);
     cudaError_t e2 = cudaStreamEndCapture(cs, &graph);
     if (e != cudaSuccess || e2 != cudaSuccess) {
       if (graph) cudaGraphDestroy(graph);
@@ -1643,6 +1835,16 @@ int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream) {
 
 int fb_launch_count(fb_handle* h, uint32_t phase_mask) {
   if (!h || !h->bound) return FB_E_STATE;
+  if (fused_wanted(h, phase_mask)) {   // fused execution: one launch per unit (fused segment or stand-alone kernel)
+    auto it = h->fused_plans.find(phase_mask);
+    if (it != h->fused_plans.end()) return (int)it->second.units.size();
+    fb_handle::FusedPlan plan;
+    const size_t keep_prog = h->prog_host.size(); const int keep_bar = h->n_fs_barriers;
+    int rc = build_fused_plan(h, phase_mask, plan);
+    h->prog_host.resize(keep_prog); h->n_fs_barriers = keep_bar;   // a dry run: the real plan is built by fb_run
+    return rc == FB_OK ? (int)plan.units.size() : rc;
+  }
+  phase_mask &= ~(uint32_t)FB_RUN_UNFUSED;
   int n = 0;
   for (int ph = 0; ph < FB_NUM_PHASES; ++ph)
     if (phase_mask & (1u << ph)) {

@@ -198,54 +198,60 @@ __device__ __forceinline__ void tc_prefetch_map(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
 
-// ring_bn: B-tile rows the ring geometry is laid out for (>= every problem's bn); total: tiles of the whole group
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __restrict__ descs, const __grid_constant__ TcLaunch L) {
-  const int total = L.total, ring_bn = L.ring_bn;
-  fb_pdl_trigger();
-  extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
-  __shared__ __align__(16) float epi_scratch[4 * 32 * TC_EPI_LD];
-  __shared__ __align__(8) uint64_t bar_raw[TC_MAX_STAGES];    // TMA -> lo builders
-  __shared__ __align__(8) uint64_t bar_ready[TC_MAX_STAGES];  // lo builders -> MMA issuer
-  __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];  // MMA issuer (tcgen05.commit) -> TMA producer
-  __shared__ __align__(8) uint64_t bar_accum;                 // all MMAs of a tile retired -> epilogue
-  __shared__ __align__(8) uint64_t bar_tmem_empty;            // epilogue has read the accumulators -> MMA issuer (next tile)
-  __shared__ uint32_t tmem_base_smem;
+// Shared-memory objects of the GEMM roles (static in the owning kernel: k_gemm_tc, or the fused stack kernel of fused.cuh)
+struct TcShared {
+  uint64_t bar_raw[TC_MAX_STAGES];    // TMA -> lo builders
+  uint64_t bar_ready[TC_MAX_STAGES];  // lo builders -> MMA issuer
+  uint64_t bar_empty[TC_MAX_STAGES];  // MMA issuer (tcgen05.commit) -> TMA producer
+  uint64_t bar_accum;                 // all MMAs of a tile retired -> epilogue
+  uint64_t bar_tmem_empty;            // epilogue has read the accumulators -> MMA issuer (next tile)
+  uint32_t tmem_base;
+  uint32_t pad;
+};
 
+// one thread: (re)initialise the pipeline barriers of a launch / of a GEMM item of the fused kernel (reinit: the objects are live)
+__device__ __forceinline__ void tc_init_barriers(TcShared* sh, bool reinit) {
+  if (reinit) {
+    for (int s = 0; s < TC_MAX_STAGES; ++s) {
+      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_raw[s])) : "memory");
+      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_ready[s])) : "memory");
+      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_empty[s])) : "memory");
+    }
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_accum)) : "memory");
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_tmem_empty)) : "memory");
+  }
+  for (int s = 0; s < TC_MAX_STAGES; ++s) {
+    tc_mbar_init(&sh->bar_raw[s], 1);
+    tc_mbar_init(&sh->bar_ready[s], 128);
+    tc_mbar_init(&sh->bar_empty[s], 1);
+  }
+  tc_mbar_init(&sh->bar_accum, 1);
+  tc_mbar_init(&sh->bar_tmem_empty, 128);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// The three roles of one grouped launch, for the CTA that plays virtual CTA `vcta` of `ncta` (warps 0..5 of the block; further
+// warps fall through).  Barriers freshly initialised, TMEM allocated (sh->tmem_base), `L` readable by every thread (constant bank
+// or shared memory).  smem_base / smem_gen: the 1024-byte aligned operand ring (shared-window address / generic pointer).
+// Activations and masks produced by earlier launches are read with plain (coherent) loads: inside the fused kernel they were
+// written by other SMs during the same kernel.
+__device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcLaunch& L, int vcta, int ncta, TcShared* sh,
+                                              float* epi_scratch, uint32_t smem_base, uint8_t* smem_gen) {
+  const int total = L.total, ring_bn = L.ring_bn;
+  uint64_t* bar_raw = sh->bar_raw; uint64_t* bar_ready = sh->bar_ready; uint64_t* bar_empty = sh->bar_empty;
+  uint64_t& bar_accum = sh->bar_accum; uint64_t& bar_tmem_empty = sh->bar_tmem_empty;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ring geometry: narrower B tiles leave room for more stages (3 at BN = 128, 4 at BN = 64 / 32)
   const uint32_t b_off = 16384u;
   const uint32_t half_bytes = 16384u + (uint32_t)ring_bn * 128u;   // raw (or lo) part of a stage: A tile then B tile
   const uint32_t stage_bytes = 2u * half_bytes;
   const int nst = min(TC_MAX_STAGES, (int)(TC_RING_BYTES / stage_bytes));
-
-  const uint32_t smem_base = (tc_smem_u32(tc_smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = tc_smem_raw + (smem_base - tc_smem_u32(tc_smem_raw));
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_MAX_STAGES; ++s) {
-      tc_mbar_init(&bar_raw[s], 1);
-      tc_mbar_init(&bar_ready[s], 128);
-      tc_mbar_init(&bar_empty[s], 1);
-    }
-    tc_mbar_init(&bar_accum, 1);
-    tc_mbar_init(&bar_tmem_empty, 128);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_smem)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_base_smem;
-  fb_pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
-
+  const uint32_t tmem_base = sh->tmem_base;
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       uint32_t kbg = 0;   // k-blocks issued by this CTA so far (ring position), across tiles
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int w = vcta; w < total; w += ncta) {
         int m0, n0, kb0, kb1;
         const int pi = tc_locate(L, w, &m0, &n0, &kb0, &kb1);
         const TcGemmDesc* __restrict__ d = &descs[pi];
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
     if (lane == 0) {
       // ===== MMA issuer =====
       uint32_t kbg = 0, it = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      for (int w = vcta; w < total; w += ncta, ++it) {
         int m0, n0, kb0, kb1;
         const int pi = tc_locate(L, w, &m0, &n0, &kb0, &kb1);
         const int bn = L.p[pi].bn;
@@ -305,14 +311,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
         tc_mma_commit(&bar_accum);
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ===== lo-part builders (128 threads), then epilogue =====
     const int t = threadIdx.x - 64;
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
     float* scr = epi_scratch + q * (32 * TC_EPI_LD);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t kbg = 0, it = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+    for (int w = vcta; w < total; w += ncta, ++it) {
       int m0, n0, kb0, kb1;
       const int pi = tc_locate(L, w, &m0, &n0, &kb0, &kb1);
       const TcGemmDesc* __restrict__ d = &descs[pi];
@@ -368,12 +374,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
             mk4[r8] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < M && col < N) {
               const float* mp = mask + (size_t)row * ldmask + col;
-              if (m_vec && full) mk4[r8] = __ldg(reinterpret_cast<const float4*>(mp));
+              if (m_vec && full) mk4[r8] = *reinterpret_cast<const float4*>(mp);
               else {
-                mk4[r8].x = __ldg(mp);
-                if (col + 1 < N) mk4[r8].y = __ldg(mp + 1);
-                if (col + 2 < N) mk4[r8].z = __ldg(mp + 2);
-                if (col + 3 < N) mk4[r8].w = __ldg(mp + 3);
+                mk4[r8].x = mp[0];
+                if (col + 1 < N) mk4[r8].y = mp[1];
+                if (col + 2 < N) mk4[r8].z = mp[2];
+                if (col + 3 < N) mk4[r8].w = mp[3];
               }
             }
           }
@@ -455,10 +461,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       tc_mbar_arrive(&bar_tmem_empty);
     }
   }
+}
+
+// ring_bn: B-tile rows the ring geometry is laid out for (>= every problem's bn); total: tiles of the whole group
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __restrict__ descs, const __grid_constant__ TcLaunch L) {
+  fb_pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+  __shared__ __align__(16) float epi_scratch[4 * 32 * TC_EPI_LD];
+  __shared__ __align__(8) TcShared sh;
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t smem_base = (tc_smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = tc_smem_raw + (smem_base - tc_smem_u32(tc_smem_raw));
+
+  if (threadIdx.x == 0) tc_init_barriers(&sh, false);
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sh.tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  fb_pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
+
+  tc_gemm_roles(descs, L, blockIdx.x, gridDim.x, &sh, epi_scratch, smem_base, smem_gen);
+
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh.tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -470,24 +501,27 @@ struct TransposeDesc { const float* in; float* out; float* out_lo; int rows, col
 
 __device__ __forceinline__ float tc_lo1(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-__device__ __forceinline__ void transpose_grouped_body(const TransposeDesc* __restrict__ descs, int nprob);
+// tile_smem: 32 x 33 floats of shared memory
+__device__ __forceinline__ void transpose_grouped_body(const TransposeDesc* descs, int nprob, float* tile_smem, const int bid);
 __global__ void __launch_bounds__(256) k_transpose_grouped(const TransposeDesc* __restrict__ descs, int nprob) {
   fb_pdl_trigger();
   fb_pdl_wait();
-  transpose_grouped_body(descs, nprob);
+  __shared__ float tile_smem[32 * 33];
+  transpose_grouped_body(descs, nprob, tile_smem, blockIdx.x);
 }
 // the same with the descriptors by value (the late staging launches on the main lane: no dependent descriptor loads)
 __global__ void __launch_bounds__(256) k_transpose_grouped_tab(const __grid_constant__ DescTable<TransposeDesc, 8> T) {
   fb_pdl_trigger();
   fb_pdl_wait();
-  transpose_grouped_body(T.d, T.n);
+  __shared__ float tile_smem[32 * 33];
+  transpose_grouped_body(T.d, T.n, tile_smem, blockIdx.x);
 }
-__device__ __forceinline__ void transpose_grouped_body(const TransposeDesc* __restrict__ descs, int nprob) {
-  __shared__ float tile[32][33];
+__device__ __forceinline__ void transpose_grouped_body(const TransposeDesc* descs, int nprob, float* tile_smem, const int bid) {
+  float (*tile)[33] = reinterpret_cast<float (*)[33]>(tile_smem);
   int p = 0;
-  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;
+  while (p + 1 < nprob && descs[p + 1].cta_begin <= bid) ++p;
   const TransposeDesc d = descs[p];
-  const int local = blockIdx.x - d.cta_begin;
+  const int local = bid - d.cta_begin;
   const int bx = local % d.ctas_x, by = local / d.ctas_x;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   if (d.transpose == 2) {   // zero fill (outputs of split-K GEMMs)

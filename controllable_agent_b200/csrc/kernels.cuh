@@ -175,10 +175,9 @@ struct StageParams {
   const float* mix_override;  // tight [B, G]: explicit backward_input[perm] from fb_set_batch, or null
 };
 
-__global__ void __launch_bounds__(128) k_stage_inputs(StageParams P, const float* __restrict__ packed) {
-  fb_pdl_trigger();
-  fb_pdl_wait();
-  const int r = blockIdx.x;
+__device__ __forceinline__ void stage_inputs_body(StageParams P, const float* packed, const int bid) {
+
+  const int r = bid;
   if (r >= P.batch) return;
   const BatchLayout& L = P.L;
   const float* row = packed + (size_t)r * L.pitch;
@@ -208,6 +207,11 @@ __global__ void __launch_bounds__(128) k_stage_inputs(StageParams P, const float
     if (P.with_future) P.mix_in[(size_t)(P.batch + r) * P.ldG + c] = P.use_goal ? row[L.off_future_goal + c] : row[L.off_future_obs + c];
   }
   if (threadIdx.x == 0) P.blk[(size_t)r * P.blk_pitch + P.disc_col] = row[L.off_rd + 1];
+}
+__global__ void __launch_bounds__(128) k_stage_inputs(StageParams P, const float* __restrict__ packed) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  stage_inputs_body(P, packed, blockIdx.x);
 }
 
 // ---- device RNG (rng_device = 1) ----------------------------------------------------------------------
@@ -335,12 +339,9 @@ struct LnDesc {
   int rows, D, ld, row_begin;  // row_begin: first global warp index of this problem
 };
 
-__global__ void __launch_bounds__(256) k_ln_tanh_fwd(const __grid_constant__ DescTable<LnDesc, 8> T, int total_rows) {
-  fb_pdl_trigger();
-  fb_pdl_wait();
-  const LnDesc* descs = T.d;
-  const int nprob = T.n;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void ln_tanh_fwd_body(const LnDesc* descs, const int nprob, int total_rows, const int bid) {
+
+  const int gw = (bid * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= total_rows) return;
   int p = 0;
   while (p + 1 < nprob && descs[p + 1].row_begin <= gw) ++p;
@@ -358,16 +359,18 @@ __global__ void __launch_bounds__(256) k_ln_tanh_fwd(const __grid_constant__ Des
   for (int c = lane; c < d.D; c += 32) y[c] = tanhf((x[c] - mean) * rstd * __ldg(d.gamma + c) + __ldg(d.beta + c));
   if (lane == 0) { d.mean[r] = mean; d.rstd[r] = rstd; }
 }
+__global__ void __launch_bounds__(256) k_ln_tanh_fwd(const __grid_constant__ DescTable<LnDesc, 8> T, int total_rows) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  ln_tanh_fwd_body(T.d, T.n, total_rows, blockIdx.x);
+}
 
 // Vectorised forward for D <= 1024 and 16-byte aligned rows: the row lives in registers (one global read), two-pass
 // mean / variance on the register copy like nn.LayerNorm, float4 stores.
-__global__ void __launch_bounds__(256) k_ln_tanh_fwd_v4(const __grid_constant__ DescTable<LnDesc, 8> T, int total_rows) {
-  fb_pdl_trigger();
-  fb_pdl_wait();
-  const LnDesc* descs = T.d;
-  const int nprob = T.n;
+__device__ __forceinline__ void ln_tanh_fwd_v4_body(const LnDesc* descs, const int nprob, int total_rows, const int bid) {
+
   constexpr int NV = 8;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int gw = (bid * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= total_rows) return;
   int p = 0;
   while (p + 1 < nprob && descs[p + 1].row_begin <= gw) ++p;
@@ -425,6 +428,11 @@ __global__ void __launch_bounds__(256) k_ln_tanh_fwd_v4(const __grid_constant__ 
   }
   if (lane == 0) { d.mean[r] = mean; d.rstd[r] = rstd; }
 }
+__global__ void __launch_bounds__(256) k_ln_tanh_fwd_v4(const __grid_constant__ DescTable<LnDesc, 8> T, int total_rows) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  ln_tanh_fwd_v4_body(T.d, T.n, total_rows, blockIdx.x);
+}
 
 struct LnBwdDesc {
   const float* dy;   // grad w.r.t. the tanh output, [rows, ld_dy]
@@ -437,17 +445,13 @@ struct LnBwdDesc {
 };
 #define FB_LN_BWD_ROWS_PER_CTA 8
 
-__global__ void __launch_bounds__(256) k_ln_tanh_bwd(const __grid_constant__ DescTable<LnBwdDesc, 4> T) {
-  fb_pdl_trigger();
-  fb_pdl_wait();
-  const LnBwdDesc* descs = T.d;
-  const int nprob = T.n;
-  __shared__ float s_dg[FB_MAX_LN_DIM];
-  __shared__ float s_db[FB_MAX_LN_DIM];
+// s_dg, s_db: FB_MAX_LN_DIM floats of shared memory each
+__device__ __forceinline__ void ln_tanh_bwd_body(const LnBwdDesc* descs, const int nprob, float* s_dg, float* s_db, const int bid) {
+
   int p = 0;
-  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;
+  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)bid) ++p;
   const LnBwdDesc d = descs[p];
-  const int cta = blockIdx.x - d.cta_begin;
+  const int cta = bid - d.cta_begin;
   const bool affine = d.dgamma != nullptr;
   if (affine) {
     for (int c = threadIdx.x; c < d.D; c += blockDim.x) { s_dg[c] = 0.f; s_db[c] = 0.f; }
@@ -487,22 +491,25 @@ __global__ void __launch_bounds__(256) k_ln_tanh_bwd(const __grid_constant__ Des
     for (int c = threadIdx.x; c < d.D; c += blockDim.x) { atomicAdd(d.dgamma + c, s_dg[c]); atomicAdd(d.dbeta + c, s_db[c]); }
   }
 }
+__global__ void __launch_bounds__(256) k_ln_tanh_bwd(const __grid_constant__ DescTable<LnBwdDesc, 4> T) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  __shared__ float s_dg[FB_MAX_LN_DIM];
+  __shared__ float s_db[FB_MAX_LN_DIM];
+  ln_tanh_bwd_body(T.d, T.n, s_dg, s_db, blockIdx.x);
+}
 
 // Vectorised variant for D <= 1024 with 16-byte aligned rows: each lane keeps its 8 float4 columns of the row in registers
 // (one pass over dy / y / x), and its share of dgamma / dbeta in registers across the rows of the CTA (no per-element
 // shared-memory atomics); per CTA one shared-memory combine across the 8 warps, then one global atomic per column.
-__global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const __grid_constant__ DescTable<LnBwdDesc, 4> T) {
-  fb_pdl_trigger();
-  fb_pdl_wait();
-  const LnBwdDesc* descs = T.d;
-  const int nprob = T.n;
+// s_dg, s_db: 1024 floats of shared memory each
+__device__ __forceinline__ void ln_tanh_bwd_v4_body(const LnBwdDesc* descs, const int nprob, float* s_dg, float* s_db, const int bid) {
+
   constexpr int NV = 8;  // float4s per lane: D <= 32 * 4 * 8 = 1024
-  __shared__ float s_dg[1024];
-  __shared__ float s_db[1024];
   int p = 0;
-  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;
+  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)bid) ++p;
   const LnBwdDesc d = descs[p];
-  const int cta = blockIdx.x - d.cta_begin;
+  const int cta = bid - d.cta_begin;
   const bool affine = d.dgamma != nullptr;
   const int D = d.D;
   if (affine) {
@@ -590,14 +597,20 @@ __global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const __grid_constant__ 
     for (int c = threadIdx.x; c < D; c += blockDim.x) { atomicAdd(d.dgamma + c, s_dg[c]); atomicAdd(d.dbeta + c, s_db[c]); }
   }
 }
+__global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const __grid_constant__ DescTable<LnBwdDesc, 4> T) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  __shared__ float s_dg[1024];
+  __shared__ float s_db[1024];
+  ln_tanh_bwd_v4_body(T.d, T.n, s_dg, s_db, blockIdx.x);
+}
 
 // ---- sqrt(Z) * F.normalize (fb_modules.py:33-40, 227-229) ------------------------------------------
 struct L2Desc { const float* x; float* y; float* nrm; int rows, Z, ldx, ldy, row_begin; int normalize; };   // normalize = 0: y = x (norm_z off)
 
-__global__ void __launch_bounds__(256) k_l2norm_fwd(const L2Desc* __restrict__ descs, int nprob, int total_rows) {
-  fb_pdl_trigger();
-  fb_pdl_wait();
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void l2norm_fwd_body(const L2Desc* descs, int nprob, int total_rows, const int bid) {
+
+  const int gw = (bid * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= total_rows) return;
   int p = 0;
   while (p + 1 < nprob && descs[p + 1].row_begin <= gw) ++p;
@@ -612,16 +625,20 @@ __global__ void __launch_bounds__(256) k_l2norm_fwd(const L2Desc* __restrict__ d
   for (int c = lane; c < d.Z; c += 32) y[c] = d.normalize ? sq * (x[c] / nrm) : x[c];
   if (lane == 0 && d.nrm) d.nrm[r] = nrm;
 }
+__global__ void __launch_bounds__(256) k_l2norm_fwd(const L2Desc* __restrict__ descs, int nprob, int total_rows) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  l2norm_fwd_body(descs, nprob, total_rows, blockIdx.x);
+}
 
 // dx = (sqrt(Z)/nrm) * (dy - xh * (xh . dy)),  xh = y / sqrt(Z).  dy is the sum of up to three partial gradients plus coef * y
 // (the partial products of the tensor-core loss path and the diagonal orthonormality term); the total is also written to dsum.
-__global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ dy0, const float* __restrict__ dy1,
-                                                    const float* __restrict__ dy2, int lddy, float coef, float* __restrict__ dsum,
-                                                    int ldsum, const float* __restrict__ y, int ldy, const float* __restrict__ nrm,
-                                                    float* __restrict__ dx, int lddx, int rows, int Z, int normalize) {
-  fb_pdl_trigger();
-  fb_pdl_wait();
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void l2norm_bwd_body(const float* dy0, const float* dy1,
+                                                    const float* dy2, int lddy, float coef, float* dsum,
+                                                    int ldsum, const float* y, int ldy, const float* nrm,
+                                                    float* dx, int lddx, int rows, int Z, int normalize, const int bid) {
+
+  const int r = (bid * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   if (!normalize) {   // norm_z off: the projection is the identity, dx = the summed gradient (the diagonal term survives)
     for (int c = lane; c < Z; c += 32) {
@@ -652,6 +669,14 @@ __global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ dy
     if (dy2) g += dy2[(size_t)r * lddy + c];
     dx[(size_t)r * lddx + c] = k * (g - yv * isq * dot);
   }
+}
+__global__ void __launch_bounds__(256) k_l2norm_bwd(const float* __restrict__ dy0, const float* __restrict__ dy1,
+                                                    const float* __restrict__ dy2, int lddy, float coef, float* __restrict__ dsum,
+                                                    int ldsum, const float* __restrict__ y, int ldy, const float* __restrict__ nrm,
+                                                    float* __restrict__ dx, int lddx, int rows, int Z, int normalize) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  l2norm_bwd_body(dy0, dy1, dy2, lddy, coef, dsum, ldsum, y, ldy, nrm, dx, lddx, rows, Z, normalize, blockIdx.x);
 }
 
 // ---- rand_weight mixing (cfg.rand_weight, fb_ddpg.py:475-482) -----------------------------------------------------
@@ -740,10 +765,9 @@ struct ZFinalParams {
   int renorm;                           // cfg.norm_z: re-project the mixed rows (fb_ddpg.py:483-484); 0 leaves them raw
 };
 
-__global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
-  fb_pdl_trigger();
-  fb_pdl_wait();
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void z_final_body(ZFinalParams P, const int bid) {
+
+  const int r = (bid * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= P.batch) return;
   const bool fut = P.future_mask && P.future_mask[r] != 0;   // applied after the mixing: it wins (fb_ddpg.py:488-491)
   const bool mix = !fut && P.mix_mask && P.mix_mask[r] != 0;
@@ -767,6 +791,11 @@ __global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
       for (int i = 0; i < 3; ++i) P.f_in[i][(size_t)r * P.ldF + P.O + c] = v;
     }
   }
+}
+__global__ void __launch_bounds__(256) k_z_final(ZFinalParams P) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  z_final_body(P, blockIdx.x);
 }
 
 // ---- action sampling: mu = tanh(pre); TruncatedNormal.sample(clip) (utils.py:164-185) ---------------
@@ -801,10 +830,9 @@ enum {
   ACC_COUNT = 16
 };
 
-__global__ void __launch_bounds__(256) k_actor_out(ActorOutParams P, const DevScalars* __restrict__ sc) {
-  fb_pdl_trigger();
-  fb_pdl_wait();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void actor_out_body(ActorOutParams P, const DevScalars* sc, const int bid) {
+
+  const int idx = bid * blockDim.x + threadIdx.x;
   const int total = 2 * P.batch * P.A;
   double lp = 0.0;
   if (idx < total) {
@@ -831,6 +859,11 @@ __global__ void __launch_bounds__(256) k_actor_out(ActorOutParams P, const DevSc
   }
   lp = warp_sum_d(lp);
   if ((threadIdx.x & 31) == 0 && lp != 0.0) atomicAdd(P.acc + ACC_LOGPROB, lp);
+}
+__global__ void __launch_bounds__(256) k_actor_out(ActorOutParams P, const DevScalars* __restrict__ sc) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  actor_out_body(P, sc, blockIdx.x);
 }
 
 // ---- batch x batch loss, elementwise stage ----------------------------------------------------------
@@ -933,12 +966,11 @@ __global__ void k_loss_init_db(float* __restrict__ dB, int lddb, const float* __
 }
 
 // ---- actor Q loss (fb_ddpg.py:400-406): Q = min_k F_k . z, loss = -mean Q ------------------------
-__global__ void __launch_bounds__(256) k_actor_q(const float* __restrict__ F1, const float* __restrict__ F2, int ldf,
-                                                 const float* __restrict__ z, int ldz, float* __restrict__ dF1,
-                                                 float* __restrict__ dF2, int lddf, int rows, int Z, float inv_n, double* acc) {
-  fb_pdl_trigger();
-  fb_pdl_wait();
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void actor_q_body(const float* F1, const float* F2, int ldf,
+                                                 const float* z, int ldz, float* dF1,
+                                                 float* dF2, int lddf, int rows, int Z, float inv_n, double* acc, const int bid) {
+
+  const int r = (bid * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   float q1 = 0.f, q2 = 0.f;
   for (int c = lane; c < Z; c += 32) {
@@ -959,6 +991,13 @@ __global__ void __launch_bounds__(256) k_actor_q(const float* __restrict__ F1, c
     atomicAdd(acc + ACC_Q, (double)fminf(q1, q2));
     if (q1 > q2) atomicAdd(acc + ACC_Q1_SUCCESS, 1.0);
   }
+}
+__global__ void __launch_bounds__(256) k_actor_q(const float* __restrict__ F1, const float* __restrict__ F2, int ldf,
+                                                 const float* __restrict__ z, int ldz, float* __restrict__ dF1,
+                                                 float* __restrict__ dF2, int lddf, int rows, int Z, float inv_n, double* acc) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  actor_q_body(F1, F2, ldf, z, ldz, dF1, dF2, lddf, rows, Z, inv_n, acc, blockIdx.x);
 }
 
 // ---- optional Q loss of update_fb (cfg.q_loss, fb_ddpg.py:330-341) -------------------------------------------
@@ -1098,13 +1137,13 @@ __global__ void __launch_bounds__(256) k_qloss_rows(QLossParams P) {
 struct ColsumDesc { const float* src; float* dst; int rows, N, ld, cta_begin, ctas_n, ctas_r; };
 #define FB_COLSUM_ROWS_PER_CTA 128
 
-__global__ void __launch_bounds__(256) k_colsum(const ColsumDesc* __restrict__ descs, int nprob) {
-  fb_pdl_trigger();
-  fb_pdl_wait();
+// red_smem: 8 x 33 floats of shared memory
+__device__ __forceinline__ void colsum_body(const ColsumDesc* descs, int nprob, float* red_smem, const int bid) {
+
   int p = 0;
-  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)blockIdx.x) ++p;
+  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)bid) ++p;
   const ColsumDesc d = descs[p];
-  const int local = blockIdx.x - d.cta_begin;
+  const int local = bid - d.cta_begin;
   const int cn = local % d.ctas_n, cr = local / d.ctas_n;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = cn * 32 + tx;
@@ -1113,7 +1152,7 @@ __global__ void __launch_bounds__(256) k_colsum(const ColsumDesc* __restrict__ d
   float s = 0.f;
   if (col < d.N)
     for (int r = r0 + ty; r < r1; r += 8) s += d.src[(size_t)r * d.ld + col];
-  __shared__ float red[8][33];
+  float (*red)[33] = reinterpret_cast<float (*)[33]>(red_smem);
   red[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && col < d.N) {
@@ -1122,6 +1161,12 @@ __global__ void __launch_bounds__(256) k_colsum(const ColsumDesc* __restrict__ d
     for (int i = 0; i < 8; ++i) t += red[i][tx];
     atomicAdd(d.dst + col, t);
   }
+}
+__global__ void __launch_bounds__(256) k_colsum(const ColsumDesc* __restrict__ descs, int nprob) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  __shared__ float red_smem[8 * 33];
+  colsum_body(descs, nprob, red_smem, blockIdx.x);
 }
 
 // ---- Adam (torch.optim.Adam defaults, fb_ddpg.py:146-151) + target soft update (utils.py:66-69) -------

@@ -17,10 +17,12 @@
 #include "kernels.cuh"
 #include "contract_tc.cuh"
 #include "gemm_tc.cuh"
+#include "fused.cuh"
 
 #define FB_NUM_PHASES 13
 #define FB_INFER_ROWS 8   // rows of the per-environment-step inference plans (act / get_goal_meta / compute_z_correl)
 #define FB_DESC_ARENA_BYTES (1u << 20)
+#define FB_PROG_ARENA_BYTES (1u << 20)
 #define FB_SM_COUNT 148
 
 struct Mat {
@@ -44,6 +46,16 @@ struct SegmentLayout {
 };
 
 typedef std::function<cudaError_t(cudaStream_t)> OpFn;
+// what a launch looks like as an item of the fused stack kernel (fused.cuh): body type, virtual blocks, argument block.
+// type FS_NONE: the launch has no fused form and runs as a kernel of its own (it ends the current fused segment).
+struct DevItem {
+  int type = FS_NONE, count = 0;
+  std::vector<char> args;
+  template <typename T> void set(int t, int n, const T& a) {
+    type = t; count = n;
+    args.assign(reinterpret_cast<const char*>(&a), reinterpret_cast<const char*>(&a) + sizeof(T));
+  }
+};
 // kinds of launch, reported by fb_profile_ops (FB_OPK_* in fb_b200.h)
 struct Op {
   OpFn fn;
@@ -56,6 +68,7 @@ struct Op {
                  // side-lane ops issued before it)
   int replay_only = 0;  // skipped under FB_RUN_HOST_BATCH (the replay gather)
   int wait_stage = 0;   // consumes operands staged for this phase on the staging lane: waits for the phase's staging event
+  DevItem dev;          // fused form (FS_NONE: stand-alone only)
   cudaError_t operator()(cudaStream_t s) const { return fn(s); }
 };
 
@@ -87,7 +100,19 @@ struct fb_handle {
   // staging of FB_FWD / FB_BWD / ACTOR_BWD operands hides behind the phases before them.
   std::vector<TransposeDesc> early_stage[FB_NUM_PHASES];
   std::vector<int> early_avail[FB_NUM_PHASES];   // per entry: first phase at whose start the source is final
-  struct StageBatch { int avail; const TransposeDesc* d_descs; int n, ctas; double bytes; };
+  struct StageBatch { int avail; const TransposeDesc* d_descs; int n, ctas; double bytes; DevItem dev; };
+  // fused execution (fused.cuh): per phase mask, the plan cut into units = fused segments (one k_fused_stack launch walking a
+  // program of stages) and the launches that stay kernels of their own
+  struct Unit { int program = -1; const Op* op = nullptr; };   // program >= 0: offset of its header in the program arena
+  struct FusedPlan { std::vector<Unit> units; std::vector<int> barrier_of; };
+  std::map<uint32_t, FusedPlan> fused_plans;
+  std::vector<char> prog_host;        // host mirror of the program arena
+  size_t prog_uploaded = 0;           // bytes of prog_host already on the device
+  char* d_prog = nullptr;             // program arena (workspace)
+  unsigned long long* d_fs_barrier = nullptr;   // FS_NUM_BARRIERS monotonic grid-barrier counters
+  unsigned int* d_fs_err = nullptr;
+  int n_fs_barriers = 0;
+  int sm_count = FB_SM_COUNT;
   std::vector<StageBatch> stage_batches[FB_NUM_PHASES];
   size_t ws_fwd_end = 0;             // workspace offset below which every buffer is written by a forward phase
   cudaStream_t side_stream = nullptr, stage_stream = nullptr;

@@ -48,6 +48,7 @@ class EngineConfig:
     row_offset: int = 0                     # multi-GPU: global index of local row 0
     nccl: tp.Optional[tp.Tuple[bytes, int, int]] = None   # (128-byte unique id, world, rank): collectives inside the step graph
     p2p: tp.Optional[tp.Tuple[int, int]] = None           # (world, rank): exchange by the library's own kernels over NVLink peer memory
+    fused: bool = True   # runs of consecutive launches inside one persistent kernel per segment (k_fused_stack); False: one kernel per launch
 
 
 def _ptr(t: tp.Optional[torch.Tensor]) -> tp.Optional[int]:
@@ -327,16 +328,21 @@ class FBStepEngine:
 
     # -- the step --------------------------------------------------------------------------------
     @_on_device
-    def run(self, mask: int = L.PHASE_ALL, graph: bool = False) -> None:
+    def run(self, mask: int = L.PHASE_ALL, graph: bool = False, fused: tp.Optional[bool] = None) -> None:
+        if not (self.cfg.fused if fused is None else fused):
+            mask |= L.RUN_UNFUSED
         L.check(self.lib.fb_run(self.h, mask, int(graph), self._stream()), f"fb_run(0x{mask:x})")
 
-    def launch_count(self, mask: int = L.PHASE_ALL) -> int:
+    def launch_count(self, mask: int = L.PHASE_ALL, fused: tp.Optional[bool] = None) -> int:
+        """Kernel launches one run of `mask` issues (fused execution: one per fused segment / stand-alone kernel)."""
+        if not (self.cfg.fused if fused is None else fused):
+            mask |= L.RUN_UNFUSED
         return self.lib.fb_launch_count(self.h, mask)
 
     @_on_device
     def profile_ops(self, mask: int = L.PHASE_ALL, reps: int = 5) -> tp.List[tp.Dict[str, tp.Any]]:
         """Per-launch CUDA-event timings of the phases in `mask` (runs the step `reps` times eagerly)."""
-        cap = self.launch_count(mask)
+        cap = self.launch_count(mask, fused=False)
         ms, kind = (C.c_float * cap)(), (C.c_int32 * cap)()
         flops, nbytes = (C.c_double * cap)(), (C.c_double * cap)()
         n = self.lib.fb_profile_ops(self.h, mask, reps, self._stream(), ms, kind, flops, nbytes, cap)

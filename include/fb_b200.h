@@ -76,7 +76,12 @@ enum {
   /* modifier of FB_PHASE_SAMPLE: the caller supplied the batch rows (fb_upload_batch / fb_set_batch), e.g. sampled from a
    * host-resident replay buffer (in_memory_replay_buffer.py:139-190 run by the caller): the device RNG draws of the phase
    * still run (rng_device = 1), the replay gather is skipped and no replay needs to be bound */
-  FB_RUN_HOST_BATCH = 1 << 15
+  FB_RUN_HOST_BATCH = 1 << 15,
+  /* modifier: run every launch of the plan as a kernel of its own (main / side / staging lanes).  Default (flag clear, tensor-core
+   * plan): runs of consecutive launches execute inside ONE persistent kernel per segment (k_fused_stack: the fused forward /
+   * backward MLP-stack kernels — stages separated by a device-side grid barrier instead of kernel boundaries); both paths run the
+   * same device code per launch and produce the same values */
+  FB_RUN_UNFUSED = 1 << 14
 };
 
 /* index of each scalar in the metrics block (float[FB_METRIC_COUNT]) — keys of the dict returned

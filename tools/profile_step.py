@@ -37,7 +37,7 @@ def step_table(batch: int, z_dim: int, reps: int, overrides=None) -> None:
     names = ["SAMPLE", "MIX", "FB_FWD", "FB_LOSS", "FB_BWD", "FB_ADAM", "ACTOR_FWD", "ACTOR_BWD", "ACTOR_ADAM", "METRICS"]
     bounds, acc = [], 0
     for ph in range(10):
-        acc += agent.engine.launch_count(1 << ph)
+        acc += agent.engine.launch_count(1 << ph, fused=False)
         bounds.append(acc)
     tot = sum(o["ms"] for o in ops)
     print(f"batch={batch} z={z_dim} {overrides or ''}: {len(ops)} launches, {tot:.3f} ms eager-serial")
