@@ -46,6 +46,7 @@ METRIC_KEYS = ("target_M", "M1", "F1", "B", "B_norm", "z_norm", "fb_loss", "fb_d
 # slots behind them, filled on every step but only reported for the matching config flag (cfg.q_loss / cfg.additional_metric)
 OPTIONAL_METRIC_KEYS = ("q_loss", "q1_success")
 METRIC_COUNT = 32
+FS_TYPES = ("none", "gemm_tc", "ln_fwd", "ln_bwd", "transpose", "colsum", "l2_fwd", "l2_bwd", "stage_inputs", "z_final", "actor_out", "actor_q")
 OP_KINDS = ("gemm", "layernorm", "elementwise", "colsum", "adam", "gather", "loss", "memset", "contract", "gemm_tc", "transpose", "collective")
 
 
@@ -107,6 +108,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "fb_run": (_i, [_vp, _u32, _i, _vp]),
     "fb_launch_count": (_i, [_vp, _u32]),
     "fb_profile_ops": (_i, [_vp, _u32, _i, _vp, C.POINTER(C.c_float), _pi32, C.POINTER(C.c_double), C.POINTER(C.c_double), _i]),
+    "fb_fused_profile": (_i, [_vp, _u32, _i, _vp, C.POINTER(C.c_float), _pi32, _i]),
     "fb_metrics_ptr": (_vp, [_vp]),
     "fb_set_adam_steps": (_i, [_vp, C.c_int64, C.c_int64, _vp]),
     "fb_get_adam_steps": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp]),

@@ -106,8 +106,9 @@ class FBDDPGAgentConfig:
     contract_mode: str = "tcgen05"  # batch x batch contraction: "tcgen05" or "simt"
     collectives: str = "graph"   # multi-GPU exchange: "graph" = the library's own NCCL communicator, all-gather / all-reduce
     #                              captured inside the step graph; "torch" = torch.distributed calls between graph segments
-    fuse_stacks: bool = True    # the MLP stacks as fused persistent kernels (one launch per forward / backward segment of the plan,
-    #                             k_fused_stack); False: one kernel per layer-level launch on main / side / staging lanes
+    fuse_stacks: bool = False   # True: the MLP stacks as fused persistent kernels (one launch per forward / backward segment of the
+    #                             plan, k_fused_stack: 80 -> 13 launches per step); False (default, measured faster: the chain is bound by
+    #                             the latency inside each GEMM, not by launches): one kernel per layer-level launch on three lanes
     prefetch_host_batch: bool = False   # host replay only: sample + upload the NEXT update's batch while this update's step runs
     #                                     on the GPU (same numpy draw order as the reference as long as nothing else samples the
     #                                     replay between updates; for a static replay, e.g. train_offline)

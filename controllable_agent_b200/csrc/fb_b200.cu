@@ -13,6 +13,7 @@ static int phase_index(uint32_t bit) { int i = 0; while ((1u << i) != bit) ++i; 
 // ncclSum = 0, results are 0 on success.
 // ------------------------------------------------------------------------------------------------
 #include <dlfcn.h>
+#include <array>
 struct FbNcclId { char internal[128]; };
 struct FbNccl {
   void* lib = nullptr;
@@ -46,7 +47,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int encode_tiled_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows) {
+static int encode_tiled_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows, int box_cols = TC_BK) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -56,14 +57,14 @@ static int encode_tiled_map(CUtensorMap* map, const float* base, int rows, int c
   }
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};   // inner extent = one swizzle atom row (64 or 128 bytes)
   const cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? FB_OK : FB_E_STATE;
 }
 
-static int encode_operand_map(CUtensorMap* map, float* base, int rows, int cols) { return encode_tiled_map(map, base, rows, cols, cols, 64); }
+static int encode_operand_map(CUtensorMap* map, float* base, int rows, int cols) { return encode_tiled_map(map, base, rows, cols, cols, 64, 32); }   // contraction: 32-float boxes, SWIZZLE_128B
 
 // Every kernel of the plan is launched with the programmatic-serialization attribute: it may become resident while its
 // predecessor in the stream still runs and waits in fb_pdl_wait() (first statement of every kernel; after the prologue in
@@ -240,7 +241,7 @@ struct Builder {
     int bn_group = 128, sk_group = 1;
     {
       auto natural_bn = [](int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); };
-      auto nkb_of = [](const GemmDesc& s) { return fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK); };
+      auto nkb_of = [](const GemmDesc& s) { return fb_ceil_div(s.K, 32) + fb_ceil_div(s.K2, 32); };   // the model counts 32-float k-steps
       // linear epilogues may be split along K (atomic partial sums); a ReLU epilogue only if its consumers take the pre-activation
       auto can_split = [](const GemmDesc& s, int nkb) {
         if (nkb < 8) return false;
@@ -301,10 +302,11 @@ struct Builder {
       d.tiles_m = fb_ceil_div(s.M, TC_BM); d.tiles_n = fb_ceil_div(s.N, d.bn);
       d.splitk = 1; d.kb_per_split = fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK);
       const bool may_split = !(s.flags & GF_RELU) || ((s.flags & GF_RELU_LAZY_OK) && !getenv("FB_NO_LAZY_RELU"));
-      if (may_split && sk_group > 1 && d.kb_per_split >= 8) {   // a k-range may straddle the two products
-        const int nkb = d.kb_per_split;
-        d.kb_per_split = fb_ceil_div(nkb, std::min(sk_group, nkb / 4));
-        d.splitk = fb_ceil_div(nkb, d.kb_per_split);   // every k-range non-empty
+      const int nkb32 = fb_ceil_div(s.K, 32) + fb_ceil_div(s.K2, 32);
+      if (may_split && sk_group > 1 && nkb32 >= 8) {   // a k-range may straddle the two products
+        const int per32 = fb_ceil_div(nkb32, std::min(sk_group, nkb32 / 4));
+        d.splitk = fb_ceil_div(nkb32, per32);          // every k-range non-empty (also in TC_BK-sized k-blocks: see DESIGN.md)
+        d.kb_per_split = per32 * TC_KB_PER_32;
       }
       if (d.splitk > 1 && (d.flags & GF_RELU)) {   // lazy ReLU: C receives the pre-activation, its consumers clamp it
         d.flags &= ~GF_RELU;
@@ -592,6 +594,7 @@ static int build_plan(fb_handle* h) {
   h->d_prog = (char*)ws_alloc(h, FB_PROG_ARENA_BYTES);
   h->d_fs_barrier = (unsigned long long*)ws_alloc(h, FS_NUM_BARRIERS * sizeof(unsigned long long));
   h->d_fs_err = (unsigned int*)ws_alloc(h, 16);
+  h->d_fs_times = (unsigned long long*)ws_alloc(h, (FS_MAX_STAGES + 1) * sizeof(unsigned long long));
   h->fused_plans.clear(); h->prog_host.clear(); h->prog_uploaded = 0; h->n_fs_barriers = 0;
 
   // ---- packed batch rows ---------------------------------------------------------------------
@@ -1721,6 +1724,12 @@ static int build_fused_plan(fb_handle* h, uint32_t mask, fb_handle::FusedPlan& p
       if (!(mask & (1u << P))) continue;
       auto& sbs = h->stage_batches[P];
       while (issued[P] < sbs.size() && sbs[issued[P]].avail <= ph) {
+        if (getenv("FB_FUSE_STAGING_ALONE")) {   // experiment: staging batches as kernels of their own (full occupancy), between segments
+          close();
+          fb_handle::Unit u; u.sb = &sbs[issued[P]]; plan.units.push_back(u); plan.barrier_of.push_back(-1);
+          ++issued[P];
+          continue;
+        }
         put(main_next, &sbs[issued[P]].dev);
         ready[P] = std::max(ready[P], main_next + 1);
         ++issued[P];
@@ -1754,14 +1763,14 @@ static int build_fused_plan(fb_handle* h, uint32_t mask, fb_handle::FusedPlan& p
   return rc;
 }
 
-static cudaError_t launch_fused(fb_handle* h, int program, int barrier, cudaStream_t s) {
+static cudaError_t launch_fused(fb_handle* h, int program, int barrier, cudaStream_t s, unsigned long long* times = nullptr) {
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(h->sm_count); cfg.blockDim = dim3(FS_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = getenv("FB_NO_PDL") ? 0 : 1;
-  return cudaLaunchKernelEx(&cfg, k_fused_stack, (const char*)(h->d_prog + program), h->d_fs_barrier + barrier, h->d_fs_err);
+  return cudaLaunchKernelEx(&cfg, k_fused_stack, (const char*)(h->d_prog + program), h->d_fs_barrier + barrier, h->d_fs_err, times);
 }
 
 // the fused plan of `mask`, built (and its programs uploaded) on first use
@@ -1787,6 +1796,7 @@ static cudaError_t run_fused(fb_handle* h, const fb_handle::FusedPlan& plan, cud
   for (size_t i = 0; i < plan.units.size(); ++i) {
     const fb_handle::Unit& u = plan.units[i];
     if (u.program >= 0) CKE(launch_fused(h, u.program, plan.barrier_of[i], s));
+    else if (u.sb) CKE(launch_stage_batch(*u.sb, s));
     else CKE((*u.op)(s));
   }
   return cudaSuccess;
@@ -1898,6 +1908,60 @@ int fb_profile_ops(fb_handle* h, uint32_t phase_mask, int reps, void* stream, fl
     if (kind_out) kind_out[i] = ops[i]->kind;
     if (flops_out) flops_out[i] = ops[i]->flops;
     if (bytes_out) bytes_out[i] = ops[i]->bytes;
+  }
+  return n;
+}
+
+int fb_fused_profile(fb_handle* h, uint32_t phase_mask, int reps, void* stream, float* us_out, int32_t* info_out, int cap) {
+  if (!h || !h->bound) return FB_E_STATE;
+  if (reps < 1 || cap < 1 || !us_out || !info_out || !fused_wanted(h, phase_mask)) return FB_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  fb_handle::FusedPlan* plan = nullptr;
+  int rc = get_fused_plan(h, phase_mask, s, &plan);
+  if (rc != FB_OK) return rc;
+  // rows: one per stage of every fused unit, one per stand-alone unit (CUDA events); info = [unit, stage (-1: stand-alone), items,
+  // type of the first item (FS_*), its count]
+  std::vector<double> acc;
+  std::vector<std::array<int32_t, 5>> info;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int r = 0; r < reps; ++r) {
+    size_t row = 0;
+    for (size_t i = 0; i < plan->units.size(); ++i) {
+      const fb_handle::Unit& u = plan->units[i];
+      if (u.program >= 0) {
+        const FsHeader* hd = reinterpret_cast<const FsHeader*>(h->prog_host.data() + u.program);
+        const FsItem* items = reinterpret_cast<const FsItem*>(h->prog_host.data() + u.program + hd->items_off);
+        CK(launch_fused(h, u.program, plan->barrier_of[i], s, h->d_fs_times));
+        std::vector<unsigned long long> t(hd->n_stages + 1);
+        CK(cudaMemcpyAsync(t.data(), h->d_fs_times, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (int st = 0; st < hd->n_stages; ++st, ++row) {
+          if (r == 0) {
+            const int a = hd->first_item[st], b = hd->first_item[st + 1];
+            acc.push_back(0.0);
+            info.push_back({(int32_t)i, st, b - a, b > a ? items[a].type : 0, b > a ? items[a].count : 0});
+          }
+          acc[row] += (double)(t[st + 1] - t[st]) * 1e-3;
+        }
+      } else {
+        CK(cudaEventRecord(e0, s));
+        if (u.sb) CK(launch_stage_batch(*u.sb, s)); else CK((*u.op)(s));
+        CK(cudaEventRecord(e1, s));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (r == 0) { acc.push_back(0.0); info.push_back({(int32_t)i, -1, 1, u.sb ? -2 : -1 - u.op->kind, 0}); }
+        acc[row++] += (double)ms * 1e3;
+      }
+    }
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  const int n = (int)acc.size();
+  if (n > cap) return FB_E_ARG;
+  for (int i = 0; i < n; ++i) {
+    us_out[i] = (float)(acc[i] / reps);
+    for (int j = 0; j < 5; ++j) info_out[5 * i + j] = info[i][j];
   }
   return n;
 }

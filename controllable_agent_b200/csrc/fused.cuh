@@ -71,7 +71,15 @@ __device__ __forceinline__ void fs_grid_barrier(unsigned long long* counter, uns
   asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(FS_THREADS, 1) k_fused_stack(const char* __restrict__ prog, unsigned long long* barrier, unsigned int* err) {
+__device__ __forceinline__ unsigned long long fs_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// times (nullable): [FS_MAX_STAGES + 1] nanosecond stamps written by CTA 0 at the start of every stage and at the end (fb_fused_profile)
+__global__ void __launch_bounds__(FS_THREADS, 1) k_fused_stack(const char* __restrict__ prog, unsigned long long* barrier, unsigned int* err,
+                                                               unsigned long long* times) {
   fb_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t fs_smem_raw[];
   __shared__ __align__(16) float epi_scratch[4 * 32 * TC_EPI_LD];
@@ -111,6 +119,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_stack(const char* __res
 
   const int n_stages = hdr.n_stages;
   for (int st = 0; st < n_stages; ++st) {
+    if (times && blockIdx.x == 0 && tid == 0) times[st] = fs_globaltimer();
     unsigned int rot = 0;   // items of a stage start on consecutive CTAs, so that small items spread over the SMs the GEMM tiles leave idle
     for (int ii = hdr.first_item[st]; ii < hdr.first_item[st + 1]; ++ii) {
       const FsItem item = items[ii];
@@ -201,6 +210,10 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_stack(const char* __res
       rot += (unsigned int)count;
     }
     if (st + 1 < n_stages) fs_grid_barrier(barrier, G, err);
+  }
+  if (times) {   // end stamp: after every CTA is done (one more barrier episode, profiling runs only)
+    fs_grid_barrier(barrier, G, err);
+    if (blockIdx.x == 0 && tid == 0) times[n_stages] = fs_globaltimer();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

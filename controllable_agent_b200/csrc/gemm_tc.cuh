@@ -35,10 +35,16 @@
 #include "gemm_simt.cuh"  // GF_* epilogue flags
 
 #define TC_BM 128
-#define TC_BK 32
+#ifndef TC_BK
+#define TC_BK 32                       // k-block = one swizzle atom row: 32 floats (SWIZZLE_128B); -DTC_BK=16 builds the SWIZZLE_64B variant
+#endif                                 // (half-size stages, 6-deep ring: measured SLOWER, profiles/r2_gemm_tc_bk16_experiment.txt)
+#define TC_ROW_BYTES (TC_BK * 4)
+#define TC_A_TILE_BYTES (TC_BM * TC_ROW_BYTES)
+#define TC_KB_PER_32 (32 / TC_BK)      // k-blocks per 32 floats of K: the unit the host-side cost model and the accumulator rotation count in
 #define TC_MAX_STAGES 6
 #define TC_THREADS 192
-#define TC_RING_BYTES 196608           // shared-memory ring; a stage is [A raw 16K | B raw BN*128 | A lo 16K | B lo BN*128]
+#define TC_RING_BYTES 196608           // shared-memory ring; a stage is [A raw | B raw (BN rows) | A lo | B lo], rows of TC_ROW_BYTES.
+                                       // (3 stages at BN = 128 and TC_BK = 32)
 #define TC_SMEM_BYTES (TC_RING_BYTES + 1024)
 #define TC_EPI_LD 36                   // padded row of the epilogue scratch (floats): conflict-free 128-bit writes and reads
 
@@ -100,8 +106,9 @@ __device__ __forceinline__ void tc_tma_load_2d(uint32_t smem_dst, const CUtensor
                "l"(reinterpret_cast<uint64_t>(map)), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ uint64_t tc_umma_desc(uint32_t smem_addr) {  // K-major, SWIZZLE_128B, SBO = 1024 B, version 1
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+__device__ __forceinline__ uint64_t tc_umma_desc(uint32_t smem_addr) {  // K-major, swizzle = row bytes, SBO = 8 rows, version 1
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((8u * TC_ROW_BYTES) >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)(TC_BK == 32 ? 2 : 4) << 61);   // layout type: SWIZZLE_128B = 2, SWIZZLE_64B = 4
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -242,8 +249,8 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
   uint64_t& bar_accum = sh->bar_accum; uint64_t& bar_tmem_empty = sh->bar_tmem_empty;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // ring geometry: narrower B tiles leave room for more stages (3 at BN = 128, 4 at BN = 64 / 32)
-  const uint32_t b_off = 16384u;
-  const uint32_t half_bytes = 16384u + (uint32_t)ring_bn * 128u;   // raw (or lo) part of a stage: A tile then B tile
+  const uint32_t b_off = TC_A_TILE_BYTES;
+  const uint32_t half_bytes = TC_A_TILE_BYTES + (uint32_t)ring_bn * TC_ROW_BYTES;   // raw (or lo) part of a stage: A tile then B tile
   const uint32_t stage_bytes = 2u * half_bytes;
   const int nst = min(TC_MAX_STAGES, (int)(TC_RING_BYTES / stage_bytes));
   const uint32_t tmem_base = sh->tmem_base;
@@ -258,7 +265,7 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
         const int bn = L.p[pi].bn, flags = L.p[pi].flags;
         const int nk1 = (L.p[pi].K + TC_BK - 1) / TC_BK;
         if (kb0 < nk1) { tc_prefetch_map(&d->mapA); tc_prefetch_map(&d->mapB); }
-        const uint32_t tx_bytes = (uint32_t)TC_BM * 128u * ((flags & TC_A_PRE) ? 2u : 1u) + (uint32_t)bn * 128u * ((flags & TC_B_PRE) ? 2u : 1u);
+        const uint32_t tx_bytes = (uint32_t)TC_A_TILE_BYTES * ((flags & TC_A_PRE) ? 2u : 1u) + (uint32_t)bn * TC_ROW_BYTES * ((flags & TC_B_PRE) ? 2u : 1u);
         for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)nst;
           if (kbg >= (uint32_t)nst) tc_mbar_wait(&bar_empty[s], ((kbg / (uint32_t)nst) - 1u) & 1u);
@@ -298,11 +305,12 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
             if (chain >= nchain) break;
             const uint32_t a = st + (chain == 1 ? half_bytes : 0u);
             const uint32_t b = st + b_off + (chain == 2 ? half_bytes : 0u);
-            // accumulators: columns [j*bn, (j+1)*bn): j = kb % 3 for hi.hi, j = 3 for the two correction chains
-            const uint32_t acc = tmem_base + (uint32_t)(chain == 0 ? (kb % 3) : 3) * (uint32_t)bn;
+            // accumulators: columns [j*bn, (j+1)*bn): j = (32-float k-step) % 3 for hi.hi, j = 3 for the two correction chains
+            const int k32 = kb / TC_KB_PER_32;
+            const uint32_t acc = tmem_base + (uint32_t)(chain == 0 ? (k32 % 3) : 3) * (uint32_t)bn;
 #pragma unroll
             for (int ks = 0; ks < TC_BK / 8; ++ks) {
-              const bool first = (ks == 0) && (chain == 0 ? kb < 3 : (kb == 0 && chain == 1));
+              const bool first = (ks == 0) && (chain == 0 ? (k32 < 3 && kb % TC_KB_PER_32 == 0) : (kb == 0 && chain == 1));
               tc_mma_tf32(acc, tc_umma_desc(a + ks * 32u), tc_umma_desc(b + ks * 32u), idesc, first ? 0u : 1u);
             }
           }
@@ -338,14 +346,16 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
         tc_mbar_wait(&bar_raw[s], (kbg / (uint32_t)nst) & 1u);
         const float4* raw = reinterpret_cast<const float4*>(smem_gen + (size_t)s * stage_bytes);
         float4* lo = reinterpret_cast<float4*>(smem_gen + (size_t)s * stage_bytes + half_bytes);
-        if (build_a) {                                                 // A tile: 128 rows x 128 B = 1024 float4
-          if (flags & TC_A_RELU) tc_build_lo_relu<8>(const_cast<float4*>(raw), lo, t);
-          else tc_build_lo<8>(raw, lo, t);
+        if (build_a) {                                                 // A tile: 128 rows x TC_ROW_BYTES = 32 * TC_BK float4
+          if (flags & TC_A_RELU) tc_build_lo_relu<TC_BK / 4>(const_cast<float4*>(raw), lo, t);
+          else tc_build_lo<TC_BK / 4>(raw, lo, t);
         }
-        if (build_b) {                                                 // B tile: bn rows x 128 B
-          if (bn == 128) tc_build_lo<8>(raw + 1024, lo + 1024, t);
-          else if (bn == 64) tc_build_lo<4>(raw + 1024, lo + 1024, t);
-          else tc_build_lo<2>(raw + 1024, lo + 1024, t);
+        if (build_b) {                                                 // B tile: bn rows x TC_ROW_BYTES
+          constexpr int B_OFF4 = TC_A_TILE_BYTES / 16;
+          if (bn == 128) tc_build_lo<TC_BK / 4>(raw + B_OFF4, lo + B_OFF4, t);
+          else if (bn == 64) tc_build_lo<TC_BK / 8>(raw + B_OFF4, lo + B_OFF4, t);
+          else if (TC_BK == 32) tc_build_lo<2>(raw + B_OFF4, lo + B_OFF4, t);
+          else tc_build_lo<1>(raw + B_OFF4, lo + B_OFF4, t);
         }
         if (build_a || build_b) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy
         tc_mbar_arrive(&bar_ready[s]);
@@ -356,7 +366,7 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
       const bool c_vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
       const bool m_vec = ((ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
       const bool b_vec = (reinterpret_cast<uintptr_t>(bias) & 15u) == 0;
-      const int n_hh = nk < 3 ? nk : 3;   // hi.hi accumulators that were written
+      const int n_hh = min(3, (nk + TC_KB_PER_32 - 1) / TC_KB_PER_32);   // hi.hi accumulators that were written
       const int sub = lane >> 3, c4 = (lane & 7) * 4;
       const bool split = L.p[pi].splitk > 1;   // partial sums: added into the zeroed C; the bias rides on the first k-range
       if (split && kb0 > 0) bias = nullptr;

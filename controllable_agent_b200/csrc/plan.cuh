@@ -103,7 +103,7 @@ struct fb_handle {
   struct StageBatch { int avail; const TransposeDesc* d_descs; int n, ctas; double bytes; DevItem dev; };
   // fused execution (fused.cuh): per phase mask, the plan cut into units = fused segments (one k_fused_stack launch walking a
   // program of stages) and the launches that stay kernels of their own
-  struct Unit { int program = -1; const Op* op = nullptr; };   // program >= 0: offset of its header in the program arena
+  struct Unit { int program = -1; const Op* op = nullptr; const StageBatch* sb = nullptr; };   // program >= 0: offset of its header in the program arena
   struct FusedPlan { std::vector<Unit> units; std::vector<int> barrier_of; };
   std::map<uint32_t, FusedPlan> fused_plans;
   std::vector<char> prog_host;        // host mirror of the program arena
@@ -111,6 +111,7 @@ struct fb_handle {
   char* d_prog = nullptr;             // program arena (workspace)
   unsigned long long* d_fs_barrier = nullptr;   // FS_NUM_BARRIERS monotonic grid-barrier counters
   unsigned int* d_fs_err = nullptr;
+  unsigned long long* d_fs_times = nullptr;     // [FS_MAX_STAGES + 1] stage stamps of a profiled fused launch
   int n_fs_barriers = 0;
   int sm_count = FB_SM_COUNT;
   std::vector<StageBatch> stage_batches[FB_NUM_PHASES];

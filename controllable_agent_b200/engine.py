@@ -48,7 +48,8 @@ class EngineConfig:
     row_offset: int = 0                     # multi-GPU: global index of local row 0
     nccl: tp.Optional[tp.Tuple[bytes, int, int]] = None   # (128-byte unique id, world, rank): collectives inside the step graph
     p2p: tp.Optional[tp.Tuple[int, int]] = None           # (world, rank): exchange by the library's own kernels over NVLink peer memory
-    fused: bool = True   # runs of consecutive launches inside one persistent kernel per segment (k_fused_stack); False: one kernel per launch
+    fused: bool = False  # True: runs of consecutive launches inside one persistent kernel per segment (k_fused_stack, fused.cuh);
+    #                      False (default, the faster path on B200: DESIGN.md section 4b): one kernel per launch on three lanes
 
 
 def _ptr(t: tp.Optional[torch.Tensor]) -> tp.Optional[int]:
@@ -349,6 +350,22 @@ class FBStepEngine:
         if n < 0:
             L.check(n, "fb_profile_ops")
         return [{"ms": ms[i], "kind": L.OP_KINDS[kind[i]], "flops": flops[i], "bytes": nbytes[i]} for i in range(n)]
+
+    @_on_device
+    def fused_profile(self, mask: int = L.PHASE_ALL, reps: int = 5) -> tp.List[tp.Dict[str, tp.Any]]:
+        """Per-stage timings of the fused execution of `mask` (device timestamps between the grid barriers) and per-kernel
+        timings of the launches that stay kernels of their own."""
+        cap = 1024
+        us, info = (C.c_float * cap)(), (C.c_int32 * (5 * cap))()
+        n = self.lib.fb_fused_profile(self.h, mask, reps, self._stream(), us, info, cap)
+        if n < 0:
+            L.check(n, "fb_fused_profile")
+        out = []
+        for i in range(n):
+            unit, stage, items, t, count = (info[5 * i + j] for j in range(5))
+            what = L.FS_TYPES[t] if t >= 0 else ("staging batch" if t == -2 else "kernel:" + L.OP_KINDS[-1 - t])
+            out.append({"us": us[i], "unit": unit, "stage": stage, "items": items, "first": what, "count": count})
+        return out
 
     def gather_block(self) -> tp.Tuple[torch.Tensor, torch.Tensor]:
         """(local, global) packed [rows, pitch] blocks for the multi-GPU all-gather between FB_FWD and FB_LOSS."""

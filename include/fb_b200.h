@@ -245,6 +245,13 @@ enum { FB_OPK_GEMM = 0, FB_OPK_LAYERNORM, FB_OPK_ELEMENTWISE, FB_OPK_COLSUM, FB_
  * of launches (<= cap) or a negative error.  Synchronises.  Executes the step for real (parameters move). */
 int fb_profile_ops(fb_handle* h, uint32_t phase_mask, int reps, void* stream, float* ms_out, int32_t* kind_out,
                    double* flops_out, double* bytes_out, int cap);
+/* the same for fused execution (FB_RUN_UNFUSED clear): runs the units of `phase_mask` `reps` times and reports one row per STAGE
+ * of every fused segment (device-side %globaltimer stamps of CTA 0 between the grid barriers) and one row per stand-alone kernel
+ * (CUDA events): mean duration (us) and info[5] = {unit index, stage (-1: stand-alone kernel), items in the stage, body type of its
+ * first item (0 none, 1 grouped tcgen05 GEMM, 2 LayerNorm fwd, 3 LayerNorm bwd, 4 staging, 5 column sums, 6 / 7 L2 projection
+ * fwd / bwd, 8 input staging, 9 z mixing, 10 action sampling, 11 actor Q; stand-alone: -1 - FB_OPK_*, staging batch: -2), its
+ * work items}.  Returns the number of rows (<= cap) or a negative error.  Synchronises; executes the step for real. */
+int fb_fused_profile(fb_handle* h, uint32_t phase_mask, int reps, void* stream, float* us_out, int32_t* info_out, int cap);
 /* device pointer to the metrics block, float[FB_METRIC_COUNT], indices FB_M_* */
 const float* fb_metrics_ptr(const fb_handle* h);
 /* 1-based Adam step counters live on the device; these set them (checkpoint restore) */

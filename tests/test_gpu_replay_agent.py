@@ -141,8 +141,10 @@ def _agent_for(g, case, **kw):
 
 
 @pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm", "trunk", "nopre"])
-@pytest.mark.parametrize("foreign_replay", [False, True])
+@pytest.mark.parametrize("foreign_replay", [False, True, "fused"])   # "fused": HBM replay, the MLP stacks as fused persistent kernels
 def test_agent_update_walks_reference_trajectory(case, foreign_replay):
+    fuse = foreign_replay == "fused"
+    foreign_replay = foreign_replay is True
     """agent.update(replay, step) x3 with the reference's RNG streams (rng_mode=reference, torch draws on the CPU generator
     as in the CPU-generated fixture).  Step 0 is gated at 1e-3; later steps inherit Adam's sign(g) amplification of
     ulp-level gradient differences (SURVEY.md 7.3) and are gated loosely."""
@@ -157,7 +159,7 @@ def test_agent_update_walks_reference_trajectory(case, foreign_replay):
         extra = dict(add_trunk=True)
     if case == "nopre":   # preprocess = False (fb_modules.py:102-104,175-177)
         extra = dict(preprocess=False)
-    agent = _agent_for(g, case, rng_mode="reference", **extra)
+    agent = _agent_for(g, case, rng_mode="reference", fuse_stacks=fuse, **extra)
     agent.draw_device = "cpu"
     eps = [subtree(g, f"ep{i}") for i in range(4)]
     if foreign_replay:   # a host-memory replay object with the reference's sample() contract: explicit-batch path

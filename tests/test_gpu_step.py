@@ -93,11 +93,11 @@ def test_sgemm_tcgen05_split_k(M, N, K, bk, splitk):
                         1, bk, 1, splitk, 3, s) != 0      # a ReLU epilogue cannot be split
 
 
-def _run_update_case(g, d, use_goal, graph, mlp_mode=0):
+def _run_update_case(g, d, use_goal, graph, mlp_mode=0, fused=False):
     L = _L()
     t = {k: torch.from_numpy(np.array(v)) for k, v in subtree(g, "in").items()}
     B = t["obs"].shape[0]
-    eng = make_engine(d, B, use_goal=use_goal, mix_ratio=0.5, ortho_coef=float(g["cfg/ortho_coef"]), mlp_mode=mlp_mode,
+    eng = make_engine(d, B, use_goal=use_goal, mix_ratio=0.5, ortho_coef=float(g["cfg/ortho_coef"]), mlp_mode=mlp_mode, fused=fused,
                       q_loss_coef=float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None,
                       norm_z=bool(g["cfg/norm_z"]) if "cfg/norm_z" in g else True,
                       add_trunk="param0/actor/trunk.0.weight" in g and "param0/actor/obs_net.0.weight" in g,
@@ -116,15 +116,20 @@ def _run_update_case(g, d, use_goal, graph, mlp_mode=0):
 
 # qloss*: cfg.q_loss (fb_ddpg.py:330-341); nonorm*: cfg.norm_z = False (fb_modules.py:227-229); trunk*: cfg.add_trunk (fb_modules.py:96-100)
 @pytest.mark.parametrize("case", ["small", "goal", "wide", "qloss", "qloss_goal", "nonorm", "nonorm_goal", "trunk", "trunk_goal", "nopre"])
-@pytest.mark.parametrize("graph,mlp_mode", [(False, 0), (True, 0), (True, 1)])
-def test_update_matches_reference_golden(case, graph, mlp_mode):
+# (graph, mlp_mode, fused): eager / CUDA-graph launches of the per-layer plan, the fp32 SIMT plan, and the fused stack kernels
+# (k_fused_stack: the same plan as stages of one persistent kernel per segment), eager and under a graph
+@pytest.mark.parametrize("graph,mlp_mode,fused", [(False, 0, False), (True, 0, False), (True, 1, False), (False, 0, True), (True, 0, True)])
+def test_update_matches_reference_golden(case, graph, mlp_mode, fused):
     g = load_golden(f"update_{case}")
     fwd, bwd, actor = (golden_params(g, f"param0/{n}") for n in ("forward_net", "backward_net", "actor"))
     d = dims_from_params(fwd, bwd, actor)
     use_goal = case.endswith("goal")
     q_coef = float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None
     norm_z = bool(g["cfg/norm_z"]) if "cfg/norm_z" in g else True
-    eng, t, L = _run_update_case(g, d, use_goal, graph, mlp_mode)
+    eng, t, L = _run_update_case(g, d, use_goal, graph, mlp_mode, fused)
+    if fused:   # the segment really is one launch: MIX + FB_FWD up to the contraction, then the loss GEMMs + FB_BWD
+        assert eng.launch_count(L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD) < eng.launch_count(
+            L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD, fused=False) // 4
 
     # ---- update_fb up to the gradients (fb_ddpg.py:303-383) ----
     eng.run(L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD | L.PHASE_METRICS, graph=graph)
@@ -233,6 +238,8 @@ FULL_WIDTH_CASES = [
     ("cheetah_z100_b512", 512, 17, 6, 100, None, 14, 0),
     ("cheetah_z100_b512_simt", 512, 17, 6, 100, None, 14, 1),
     ("cheetah_z100_b4096", 4096, 17, 6, 100, None, 15, 0),
+    ("walker_b1024_fused", 1024, 24, 6, 50, None, 12, 2),               # mlp_mode 2 here: tcgen05 plan through the fused stack kernels
+    ("quadruped_goal2_b1024_fused", 1024, 78, 12, 50, 2, 13, 2),
 ]
 
 
@@ -276,7 +283,7 @@ def test_full_width_step_against_oracle(monkeypatch, case):
     with torch.no_grad():
         z[idx] = O.l2_project(O.backward_map(bwd, goal[perm][idx], d.z_dim), d.z_dim)
 
-    eng = make_engine(d, B, use_goal=use_goal, mlp_mode=mlp_mode)
+    eng = make_engine(d, B, use_goal=use_goal, mlp_mode=mlp_mode % 2, fused=mlp_mode == 2)
     load_params(eng, fwd=fwd, bwd=bwd, actor=actor, fwd_tgt=fwd_t, bwd_tgt=bwd_t)
     eng.set_scalars(0.2, 0.3, 1e-4, 1e-4, 1e-4, 0.01)
     eng.set_indices(perm=perm, mix_mask=mix_mask.int())

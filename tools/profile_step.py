@@ -21,7 +21,7 @@ def _parse_overrides(items):
     return out
 
 
-def step_table(batch: int, z_dim: int, reps: int, overrides=None) -> None:
+def step_table(batch: int, z_dim: int, reps: int, overrides=None, fused: bool = False) -> None:
     dev = torch.device("cuda")
     E, R, O_, A_ = 200, 1001, 24, 6
     replay = ReplayBuffer(E, 0.98, 0.99, device=dev)
@@ -33,6 +33,15 @@ def step_table(batch: int, z_dim: int, reps: int, overrides=None) -> None:
     for i in range(5):
         agent.update(replay, i)
     torch.cuda.synchronize()
+    if fused:
+        rows = agent.engine.fused_profile(L.PHASE_ALL, reps=reps)
+        tot = sum(r["us"] for r in rows)
+        print(f"batch={batch} z={z_dim} {overrides or ''}: fused execution, {len(set(r['unit'] for r in rows))} launches, "
+              f"{len(rows)} stages + kernels, {tot / 1e3:.3f} ms summed")
+        for i, r in enumerate(rows):
+            where = f"unit {r['unit']:2d} stage {r['stage']:2d}" if r["stage"] >= 0 else f"unit {r['unit']:2d} kernel  "
+            print(f"{i:3d} {where} {r['us']:8.1f} us  items {r['items']}  first {r['first']} x{r['count']}")
+        return
     ops = agent.engine.profile_ops(L.PHASE_ALL, reps=reps)
     names = ["SAMPLE", "MIX", "FB_FWD", "FB_LOSS", "FB_BWD", "FB_ADAM", "ACTOR_FWD", "ACTOR_BWD", "ACTOR_ADAM", "METRICS"]
     bounds, acc = [], 0
@@ -97,8 +106,9 @@ if __name__ == "__main__":
     p.add_argument("--z-dim", type=int, default=50)
     p.add_argument("--reps", type=int, default=10)
     p.add_argument("--sweep", action="store_true")
+    p.add_argument("--fused", action="store_true", help="per-stage table of the fused execution instead of the per-launch table")
     p.add_argument("--agent", nargs="*", default=[], help="FBDDPGAgent config overrides, e.g. q_loss=true add_trunk=true rand_weight=true")
     a = p.parse_args()
-    step_table(a.batch, a.z_dim, a.reps, _parse_overrides(a.agent))
+    step_table(a.batch, a.z_dim, a.reps, _parse_overrides(a.agent), fused=a.fused)
     if a.sweep:
         sgemm_sweep()
