@@ -269,7 +269,7 @@ def parity_check(agent, a: argparse.Namespace, world: int, rank: int, dev) -> di
     e = agent.engine
     n, Bl = a.batch, a.batch // world
     flats = ("param_fb", "m_fb", "v_fb", "target_fb", "param_actor", "m_actor", "v_actor")
-    snap = {k: getattr(e, k).clone() for k in flats}
+    snap = {k: getattr(e, k).clone() for k in flats}   # (p2p: dead moment ranges are zeros on both sides)
     steps0 = e.get_adam_steps()
     g = torch.Generator().manual_seed(4242)   # identical on every rank
     G = agent.goal_dim if a.goal_space else 0
@@ -295,7 +295,9 @@ def parity_check(agent, a: argparse.Namespace, world: int, rank: int, dev) -> di
             runner()
             torch.cuda.synchronize(dev)
             ms.append(eng.read_metrics())
-        out = {k: getattr(eng, k).clone() for k in ("m_fb", "m_actor", "param_fb", "param_actor", "target_fb")}
+        out = {k: getattr(eng, k).clone() for k in ("param_fb", "param_actor", "target_fb")}
+        fm = eng.full_moments()   # p2p exchange: the moment slices live on their owner ranks (all-gathered here: collective)
+        out["m_fb"], out["m_actor"] = fm["m_fb"], fm["m_actor"]
         out["metrics"] = ms
         return out
 

@@ -101,6 +101,11 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "fb_upload_batch": (_i, [_vp, _vp, _i, _vp]),
     "fb_nccl_unique_id": (_i, [C.c_char_p, _vp]),
     "fb_nccl_init": (_i, [_vp, C.c_char_p, _vp, _i, _i]),
+    "fb_p2p_create": (_i, [_vp, _i, _i, _vp, C.POINTER(fb_buffers)]),
+    "fb_p2p_attach": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "fb_p2p_arena": (_vp, [_vp]),
+    "fb_p2p_status": (_i, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), _vp]),
+    "fb_p2p_slice": (_i, [_vp, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "fb_set_future_mask": (_i, [_vp, _vp, _vp]),
     "fb_set_mix_weights": (_i, [_vp, _vp, _vp, _vp]),
     "fb_set_z": (_i, [_vp, _vp, _vp]),

@@ -104,8 +104,10 @@ class FBDDPGAgentConfig:
     use_cuda_graph: bool = True
     mlp_mode: str = "tcgen05"   # wide Linear products: "tcgen05" (3xTF32 tensor cores) or "simt" (fp32 CUDA cores)
     contract_mode: str = "tcgen05"  # batch x batch contraction: "tcgen05" or "simt"
-    collectives: str = "graph"   # multi-GPU exchange: "graph" = the library's own NCCL communicator, all-gather / all-reduce
-    #                              captured inside the step graph; "torch" = torch.distributed calls between graph segments
+    collectives: str = "p2p"     # multi-GPU exchange: "p2p" = the library's own kernels over NVLink peer memory (row scatter + fused
+    #                              reduce-scatter / Adam / all-gather, csrc/p2p.cuh); "graph" = the library's own NCCL communicator,
+    #                              all-gather / all-reduce captured inside the step graph; "torch" = torch.distributed calls between
+    #                              graph segments
     fuse_stacks: bool = False   # True: the MLP stacks as fused persistent kernels (one launch per forward / backward segment of the
     #                             plan, k_fused_stack: 80 -> 13 launches per step); False (default, measured faster: the chain is bound by
     #                             the latency inside each GEMM, not by launches): one kernel per layer-level launch on three lanes
@@ -175,8 +177,12 @@ class FBDDPGAgent:
         local, row_offset = shard_layout(cfg.batch_size, self.world, self.rank)
 
         seed = int(torch.initial_seed() % (2 ** 63)) + 7919 * self.rank
-        nccl = None
-        if self.world > 1 and cfg.collectives == "graph":
+        nccl, p2p = None, None
+        if cfg.collectives not in ("p2p", "graph", "torch"):
+            raise ValueError(f"agent.collectives must be p2p, graph or torch (got {cfg.collectives!r})")
+        if self.world > 1 and cfg.collectives == "p2p":
+            p2p = (self.world, self.rank)   # the library's own exchange kernels over NVLink peer memory (csrc/p2p.cuh)
+        elif self.world > 1 and cfg.collectives == "graph":
             # the library's own NCCL communicator: rank 0 creates the 128-byte id, torch.distributed (plumbing) ships it
             import ctypes as C
             uid = C.create_string_buffer(128)
@@ -185,11 +191,11 @@ class FBDDPGAgent:
                 ok = int(L.load().fb_nccl_unique_id(L.nccl_library_path(), uid) == L.FB_OK)
             box = [uid.raw, ok]
             torch.distributed.broadcast_object_list(box, src=0, device=device)
-            if box[1]:
-                nccl = (box[0], self.world, self.rank)
-            else:   # NCCL could not be loaded by the library: torch.distributed collectives between graph segments
-                logger.warning("libfb_b200 could not load NCCL; falling back to collectives='torch'")
-        self.engine = FBStepEngine(EngineConfig(nccl=nccl, fused=bool(cfg.fuse_stacks),
+            if not box[1]:   # never a silent change of path: the caller asked for in-graph NCCL
+                raise RuntimeError("libfb_b200 could not load NCCL for collectives='graph'; use collectives='p2p' (no NCCL needed) or 'torch'")
+            nccl = (box[0], self.world, self.rank)
+        self.collectives_mode = cfg.collectives if self.world > 1 else "none"
+        self.engine = FBStepEngine(EngineConfig(nccl=nccl, p2p=p2p, fused=bool(cfg.fuse_stacks),
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
@@ -289,6 +295,8 @@ class FBDDPGAgent:
         e = self.engine
         fb_step, actor_step = e.get_adam_steps()
         flats = {k: getattr(e, k).detach().cpu() for k in ("param_fb", "m_fb", "v_fb", "target_fb", "param_actor", "m_actor", "v_actor")}
+        if e.has_p2p:   # the Adam moments are sharded over the ranks: gather the slices (collective: every rank pickles together)
+            flats.update({k: v.cpu() for k, v in e.full_moments().items()})
         return {"cfg": dataclasses.asdict(self.cfg), "flats": flats, "adam_steps": (fb_step, actor_step),
                 "solved_meta": self.solved_meta, "training": self.training,
                 "lrs": ([g["lr"] for g in self.fb_opt.param_groups], [g["lr"] for g in self.actor_opt.param_groups])}
@@ -407,7 +415,7 @@ class FBDDPGAgent:
     def _run(self, mask: int) -> None:
         """Enqueue the phases of `mask`; with >1 rank, split at the two exchange points (DESIGN.md "Multi-GPU")."""
         e, g = self.engine, bool(self.cfg.use_cuda_graph)
-        if self.world == 1 or e.has_nccl:   # multi-GPU with the library's communicator: the collectives are launches of the plan
+        if self.world == 1 or e.has_nccl or e.has_p2p:   # the exchange kernels / NCCL calls are launches of the plan
             e.run(mask, graph=g)
             self.last_update_launches = e.launch_count(mask)
             return

@@ -634,6 +634,10 @@ static int build_plan(fb_handle* h) {
   h->blk_local = ws_mat(h, B, blk_pitch, "blk_local");
   if (n != B) h->blk_global = ws_mat(h, n, blk_pitch, "blk_global");
   else h->blk_global = h->blk_local;
+  if (n != B && h->p2p_on && h->ws_base) {   // peers store their rows straight into it: it lives in this rank's arena
+    h->blk_global.p = reinterpret_cast<float*>(h->p2p_arena + h->p2p_off_blk);
+    h->views["blk_global"] = h->blk_global;
+  }
   const Mat& bl = h->blk_local; const Mat& bg = h->blk_global;
   auto blkcol = [&](const Mat& m, int i) { Mat r = m; r.p = m.p + i * ldZ; r.cols = Z; return r; };
   Mat F1 = blkcol(bl, 0), F2 = blkcol(bl, 1), tF1 = blkcol(bl, 2), tF2 = blkcol(bl, 3), Bm = blkcol(bl, 4), tB = blkcol(bl, 5);
@@ -869,6 +873,20 @@ static int build_plan(fb_handle* h) {
     b.push([hh, src, dst, count](cudaStream_t s) {
       return g_nccl.AllGather(src, dst, count, 7 /* ncclFloat32 */, hh->nccl_comm, s) == 0 ? cudaSuccess : cudaErrorUnknown;
     }, FB_OPK_COLLECTIVE, 0.0, 4.0 * (double)n * bl.ld);
+  } else if (h->p2p_on && n != B) {
+    // peer-memory form (p2p.cuh): every rank is past the previous step (nobody still reads its global block), then each rank
+    // stores its rows into every arena, then waits until all R row blocks have landed in its own
+    const P2pPeers pp = h->p2p;
+    const float4* src = reinterpret_cast<const float4*>(bl.p);
+    const size_t off_blk = h->p2p_off_blk, n4 = (size_t)B * bl.ld / 4;
+    b.push([pp](cudaStream_t s) { fb_launch_pdl(k_p2p_barrier, dim3(1), dim3(32), 0, s, pp, (int)P2P_BAR_STEP, 1, 1); return cudaGetLastError(); },
+           FB_OPK_COLLECTIVE);
+    b.push([pp, src, off_blk, n4](cudaStream_t s) {
+      fb_launch_pdl(k_p2p_scatter_rows, dim3((unsigned)std::min<size_t>(FB_SM_COUNT, (n4 + 255) / 256)), dim3(256), 0, s, pp, src, off_blk, n4);
+      return cudaGetLastError();
+    }, FB_OPK_COLLECTIVE, 0.0, 4.0 * (double)n * bl.ld);
+    b.push([pp](cudaStream_t s) { fb_launch_pdl(k_p2p_barrier, dim3(1), dim3(32), 0, s, pp, (int)P2P_BAR_ROWS, 0, 1); return cudaGetLastError(); },
+           FB_OPK_COLLECTIVE);
   }
 
   // =========================== FB_PHASE_FB_LOSS =================================================
@@ -1055,12 +1073,17 @@ static int build_plan(fb_handle* h) {
   b.gemm({lin_dw(dy_oa, eFoa.x, pF.gw(E_OA + 0)), lin_dw(dy_oz, eFoz.x, pF.gw(E_OZ + 0))});
 
   // multi-GPU exchange 2: the flat forward_net | backward_net gradient, summed over ranks (gradients only cross NVLink)
+  const bool p2p_step = h->p2p_on && n != B;
   if (h->nccl_comm && n != B) {
     fb_handle* hh = h;
     float* gbuf = bf.d_grad_fb; const size_t count = h->seg_fb.size;
     b.push([hh, gbuf, count](cudaStream_t s) {
       return g_nccl.AllReduce(gbuf, gbuf, count, 7, 0 /* ncclSum */, hh->nccl_comm, s) == 0 ? cudaSuccess : cudaErrorUnknown;
     }, FB_OPK_COLLECTIVE, 0.0, 8.0 * (double)count);
+  } else if (p2p_step) {   // this rank's fb gradient is final: tell the peers, wait for theirs
+    const P2pPeers pp = h->p2p;
+    b.push([pp](cudaStream_t s) { fb_launch_pdl(k_p2p_barrier, dim3(1), dim3(32), 0, s, pp, (int)P2P_BAR_GRAD_FB, 1, 1); return cudaGetLastError(); },
+           FB_OPK_COLLECTIVE);
   }
 
   // =========================== FB_PHASE_FB_ADAM =================================================
@@ -1069,6 +1092,23 @@ static int build_plan(fb_handle* h) {
     const float b1 = c.beta1, b2 = c.beta2, eps = c.adam_eps;
     float4 *p = (float4*)bf.d_param_fb, *g = (float4*)bf.d_grad_fb, *m = (float4*)bf.d_m_fb, *v = (float4*)bf.d_v_fb, *t = (float4*)bf.d_target_fb;
     const size_t n4 = h->seg_fb.size / 4, split4 = h->bwd_offset / 4;
+    if (p2p_step) {
+      // reduce-scatter + Adam + all-gather over the arenas in one kernel, then (all slices landed) the local target lerp + gradient clear
+      const P2pPeers pp = h->p2p;
+      P2pAdamParams ap; memset(&ap, 0, sizeof(ap));
+      ap.off_grad = h->p2p_off_grad_fb; ap.off_param = h->p2p_off_param_fb; ap.m = m; ap.v = v; ap.n4 = n4; ap.split4 = split4;
+      ap.slice4 = (n4 + pp.world - 1) / pp.world; ap.sc = sc; ap.which = 0; ap.bar_param = P2P_BAR_PARAM_FB; ap.beta1 = b1; ap.beta2 = b2; ap.eps = eps;
+      b.push([pp, ap](cudaStream_t s) {
+        fb_launch_pdl(k_p2p_adam, dim3(FB_SM_COUNT * 2), dim3(256), 0, s, pp, ap);
+        return cudaGetLastError();
+      }, FB_OPK_ADAM, 0.0, 16.0 * (double)ap.slice4 * (pp.world + 5.0 + pp.world));   // r(g x R, p, m, v) + w(m, v, p x R) of one slice
+      b.push([pp](cudaStream_t s) { fb_launch_pdl(k_p2p_barrier, dim3(1), dim3(32), 0, s, pp, (int)P2P_BAR_PARAM_FB, 0, 1); return cudaGetLastError(); },
+             FB_OPK_COLLECTIVE);
+      b.push([=](cudaStream_t s) {
+        fb_launch_pdl(k_p2p_finish, dim3(FB_SM_COUNT * 8), dim3(256), 0, s, (const float4*)p, g, t, n4, (const DevScalars*)sc);
+        return cudaGetLastError();
+      }, FB_OPK_ADAM, 0.0, 16.0 * (double)n4 * 4.0);
+    } else
     b.push([=](cudaStream_t s) {
       fb_launch_pdl(k_adam, dim3(FB_SM_COUNT * 8), dim3(256), 0, s, p, g, m, v, t, n4, split4, sc, 0, b1, b2, eps);
       return cudaGetLastError();
@@ -1154,6 +1194,10 @@ static int build_plan(fb_handle* h) {
     b.push([hh, gbuf, count](cudaStream_t s) {
       return g_nccl.AllReduce(gbuf, gbuf, count, 7, 0, hh->nccl_comm, s) == 0 ? cudaSuccess : cudaErrorUnknown;
     }, FB_OPK_COLLECTIVE, 0.0, 8.0 * (double)count);
+  } else if (p2p_step) {
+    const P2pPeers pp = h->p2p;
+    b.push([pp](cudaStream_t s) { fb_launch_pdl(k_p2p_barrier, dim3(1), dim3(32), 0, s, pp, (int)P2P_BAR_GRAD_ACTOR, 1, 1); return cudaGetLastError(); },
+           FB_OPK_COLLECTIVE);
   }
 
   // =========================== FB_PHASE_ACTOR_ADAM ==============================================
@@ -1162,6 +1206,22 @@ static int build_plan(fb_handle* h) {
     const float b1 = c.beta1, b2 = c.beta2, eps = c.adam_eps;
     float4 *p = (float4*)bf.d_param_actor, *g = (float4*)bf.d_grad_actor, *m = (float4*)bf.d_m_actor, *v = (float4*)bf.d_v_actor;
     const size_t n4 = h->seg_actor.size / 4;
+    if (p2p_step) {
+      const P2pPeers pp = h->p2p;
+      P2pAdamParams ap; memset(&ap, 0, sizeof(ap));
+      ap.off_grad = h->p2p_off_grad_actor; ap.off_param = h->p2p_off_param_actor; ap.m = m; ap.v = v; ap.n4 = n4; ap.split4 = n4;
+      ap.slice4 = (n4 + pp.world - 1) / pp.world; ap.sc = sc; ap.which = 1; ap.bar_param = P2P_BAR_PARAM_ACTOR; ap.beta1 = b1; ap.beta2 = b2; ap.eps = eps;
+      b.push([pp, ap](cudaStream_t s) {
+        fb_launch_pdl(k_p2p_adam, dim3(FB_SM_COUNT * 2), dim3(256), 0, s, pp, ap);
+        return cudaGetLastError();
+      }, FB_OPK_ADAM, 0.0, 16.0 * (double)ap.slice4 * (pp.world + 5.0 + pp.world));
+      b.push([pp](cudaStream_t s) { fb_launch_pdl(k_p2p_barrier, dim3(1), dim3(32), 0, s, pp, (int)P2P_BAR_PARAM_ACTOR, 0, 1); return cudaGetLastError(); },
+             FB_OPK_COLLECTIVE);
+      b.push([=](cudaStream_t s) {
+        fb_launch_pdl(k_p2p_finish, dim3(FB_SM_COUNT * 8), dim3(256), 0, s, (const float4*)p, g, (float4*)nullptr, n4, (const DevScalars*)sc);
+        return cudaGetLastError();
+      }, FB_OPK_ADAM, 0.0, 16.0 * (double)n4);
+    } else
     b.push([=](cudaStream_t s) {
       fb_launch_pdl(k_adam, dim3(FB_SM_COUNT * 8), dim3(256), 0, s, p, g, m, v, nullptr, n4, n4, sc, 1, b1, b2, eps);
       return cudaGetLastError();
@@ -1388,6 +1448,9 @@ void fb_destroy(fb_handle* h) {
   if (h->ev_stage_fork) cudaEventDestroy(h->ev_stage_fork);
   for (auto& e : h->ev_stage) if (e) cudaEventDestroy(e);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+  for (int q = 0; q < P2P_MAX_WORLD; ++q)
+    if (h->p2p_ipc[q] && h->p2p.base[q]) cudaIpcCloseMemHandle(h->p2p.base[q]);
+  if (h->p2p_arena) cudaFree(h->p2p_arena);
   delete h;
 }
 
@@ -1432,6 +1495,12 @@ int fb_bind(fb_handle* h, const fb_buffers* bufs, void* stream) {
       !bufs->d_grad_actor || !bufs->d_m_actor || !bufs->d_v_actor || !bufs->d_workspace)
     return FB_E_ARG;
   if (bufs->workspace_bytes < h->ws_bytes) return FB_E_ARG;
+  if (h->p2p_on) {
+    if (!h->p2p_attached) return FB_E_STATE;
+    if ((char*)bufs->d_grad_fb != h->p2p_arena + h->p2p_off_grad_fb || (char*)bufs->d_grad_actor != h->p2p_arena + h->p2p_off_grad_actor ||
+        (char*)bufs->d_param_fb != h->p2p_arena + h->p2p_off_param_fb || (char*)bufs->d_param_actor != h->p2p_arena + h->p2p_off_param_actor)
+      return FB_E_ARG;   // gradients and parameters must be the arena's segments (fb_p2p_create filled them in)
+  }
   if (((uintptr_t)bufs->d_workspace & 255u) || ((uintptr_t)bufs->d_param_fb & 15u) || ((uintptr_t)bufs->d_param_actor & 15u) ||
       ((uintptr_t)bufs->d_grad_fb & 15u) || ((uintptr_t)bufs->d_grad_actor & 15u) || ((uintptr_t)bufs->d_target_fb & 15u))
     return FB_E_ARG;
@@ -1534,6 +1603,86 @@ int fb_nccl_init(fb_handle* h, const char* libnccl_path, const void* id128, int 
   void* comm = nullptr;
   if (g_nccl.CommInitRank(&comm, world, id, rank) != 0 || !comm) return FB_E_STATE;
   h->nccl_comm = comm; h->nccl_world = world; h->nccl_rank = rank;
+  return FB_OK;
+}
+
+// ---- peer-memory exchange (p2p.cuh) ----------------------------------------------------------------------------------------
+static size_t p2p_round(size_t x) { return (x + 255) / 256 * 256; }
+
+int fb_p2p_create(fb_handle* h, int world, int rank, void* ipc_handle64, fb_buffers* bufs) {
+  if (!h || !bufs || world < 2 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) return FB_E_ARG;
+  if (h->bound || h->p2p_on || h->nccl_comm) return FB_E_STATE;   // before fb_bind: the plan places the exchange kernels
+  if (h->cfg.global_batch != h->cfg.batch * world || h->cfg.row_offset != rank * h->cfg.batch) return FB_E_ARG;
+  const int ldZ = fb_round_up(h->cfg.z_dim, 4), blk_pitch = 6 * ldZ + 4;
+  size_t off = P2P_FLAG_BYTES;
+  h->p2p_off_grad_fb = off; off = p2p_round(off + h->seg_fb.size * sizeof(float));
+  h->p2p_off_grad_actor = off; off = p2p_round(off + h->seg_actor.size * sizeof(float));
+  h->p2p_off_param_fb = off; off = p2p_round(off + h->seg_fb.size * sizeof(float));
+  h->p2p_off_param_actor = off; off = p2p_round(off + h->seg_actor.size * sizeof(float));
+  h->p2p_off_blk = off; off = p2p_round(off + (size_t)h->cfg.global_batch * blk_pitch * sizeof(float));
+  h->p2p_bytes = off;
+  {   // load the exchange kernels now: a lazy module load at first launch may synchronise the context, which deadlocks when a
+      // barrier kernel of this context is already spinning on a peer that lives in the same context (several ranks on one device)
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, k_p2p_barrier)); CK(cudaFuncGetAttributes(&fa, k_p2p_scatter_rows));
+    CK(cudaFuncGetAttributes(&fa, k_p2p_adam)); CK(cudaFuncGetAttributes(&fa, k_p2p_finish));
+  }
+  CK(cudaMalloc((void**)&h->p2p_arena, off));
+  CK(cudaMemset(h->p2p_arena, 0, off));
+  CK(cudaDeviceSynchronize());
+  if (ipc_handle64) {
+    cudaIpcMemHandle_t ih;
+    static_assert(sizeof(ih) == 64, "CUDA IPC handles are 64 bytes");
+    CK(cudaIpcGetMemHandle(&ih, h->p2p_arena));
+    memcpy(ipc_handle64, &ih, sizeof(ih));
+  }
+  memset(&h->p2p, 0, sizeof(h->p2p));
+  h->p2p.world = world; h->p2p.rank = rank; h->p2p.base[rank] = h->p2p_arena;
+  h->p2p_on = true;
+  bufs->d_grad_fb = reinterpret_cast<float*>(h->p2p_arena + h->p2p_off_grad_fb);
+  bufs->d_grad_actor = reinterpret_cast<float*>(h->p2p_arena + h->p2p_off_grad_actor);
+  bufs->d_param_fb = reinterpret_cast<float*>(h->p2p_arena + h->p2p_off_param_fb);
+  bufs->d_param_actor = reinterpret_cast<float*>(h->p2p_arena + h->p2p_off_param_actor);
+  return FB_OK;
+}
+
+int fb_p2p_attach(fb_handle* h, const void* ipc_handles, void* const* local_arenas) {
+  if (!h || !h->p2p_on || h->bound || h->p2p_attached) return FB_E_STATE;
+  if (!ipc_handles && !local_arenas) return FB_E_ARG;
+  for (int q = 0; q < h->p2p.world; ++q) {
+    if (q == h->p2p.rank) continue;
+    if (local_arenas) {   // arenas of engines of this process (one device, or peer-enabled devices): plain pointers
+      if (!local_arenas[q]) return FB_E_ARG;
+      h->p2p.base[q] = (char*)local_arenas[q];
+    } else {
+      cudaIpcMemHandle_t ih;
+      memcpy(&ih, (const char*)ipc_handles + (size_t)q * sizeof(ih), sizeof(ih));
+      void* p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+      h->p2p.base[q] = (char*)p; h->p2p_ipc[q] = true;
+    }
+  }
+  h->p2p_attached = true;
+  return FB_OK;
+}
+
+void* fb_p2p_arena(fb_handle* h) { return h && h->p2p_on ? h->p2p_arena : nullptr; }
+
+int fb_p2p_status(fb_handle* h, uint32_t* code, uint64_t* epochs8, void* stream) {
+  if (!h || !h->p2p_on || !code) return FB_E_STATE;
+  P2pFlags f;
+  CK(cudaMemcpyAsync(&f, h->p2p_arena, sizeof(f), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  *code = f.error;
+  if (epochs8) for (int i = 0; i < P2P_NUM_BARRIERS; ++i) epochs8[i] = f.epoch[i];
+  return FB_OK;
+}
+
+int fb_p2p_slice(const fb_handle* h, int actor, size_t* first, size_t* count) {
+  if (!h || !h->p2p_on || !first || !count) return FB_E_STATE;
+  const size_t n4 = (actor ? h->seg_actor.size : h->seg_fb.size) / 4, slice4 = (n4 + h->p2p.world - 1) / h->p2p.world;
+  const size_t lo = std::min(n4, (size_t)h->p2p.rank * slice4), hi = std::min(n4, lo + slice4);
+  *first = 4 * lo; *count = 4 * (hi - lo);
   return FB_OK;
 }
 
@@ -1839,6 +1988,7 @@ int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream) {
     if (e != cudaSuccess) return (int)e;
     it = h->graphs.emplace(phase_mask, exec).first;
   }
+  if (use_graph == 2) return FB_OK;   // capture + instantiate only (ranks sharing a context instantiate before any of them spins)
   CK(cudaGraphLaunch(it->second, s));
   return FB_OK;
 }

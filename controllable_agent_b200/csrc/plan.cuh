@@ -18,6 +18,7 @@
 #include "contract_tc.cuh"
 #include "gemm_tc.cuh"
 #include "fused.cuh"
+#include "p2p.cuh"
 
 #define FB_NUM_PHASES 13
 #define FB_INFER_ROWS 8   // rows of the per-environment-step inference plans (act / get_goal_meta / compute_z_correl)
@@ -138,6 +139,12 @@ struct fb_handle {
   // data-parallel exchange inside the step (fb_nccl_init before fb_bind): NCCL communicator of this rank, loaded with dlopen
   void* nccl_comm = nullptr;
   int nccl_world = 1, nccl_rank = 0;
+  // data-parallel exchange by the library's own kernels over NVLink peer memory (p2p.cuh; fb_p2p_create / fb_p2p_attach before fb_bind)
+  bool p2p_on = false, p2p_attached = false;
+  P2pPeers p2p;
+  char* p2p_arena = nullptr;          // this rank's arena (owned: cudaMalloc)
+  bool p2p_ipc[P2P_MAX_WORLD] = {};   // peer arenas opened through CUDA IPC (to be closed)
+  size_t p2p_bytes = 0, p2p_off_grad_fb = 0, p2p_off_grad_actor = 0, p2p_off_param_fb = 0, p2p_off_param_actor = 0, p2p_off_blk = 0;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -71,7 +71,7 @@ def _on_device(fn: tp.Callable) -> tp.Callable:
 
 
 class FBStepEngine:
-    def __init__(self, cfg: EngineConfig, device: tp.Union[str, torch.device] = "cuda") -> None:
+    def __init__(self, cfg: EngineConfig, device: tp.Union[str, torch.device] = "cuda", p2p_attach: str = "ipc") -> None:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("controllable_agent_b200 runs on CUDA (sm_100a) only; there is no CPU path "
@@ -94,17 +94,64 @@ class FBStepEngine:
         L.check(self.lib.fb_create(C.byref(c), C.byref(h)), "fb_create")
         self.h = h
         self.has_nccl = False
+        self.has_p2p = False
+        self._arena_bufs: tp.Optional["L.fb_buffers"] = None
+        self._bound = False
         if cfg.nccl is not None:   # before fb_bind: the plan places the all-gather / all-reduce launches
             uid, world, rank = cfg.nccl
             buf = C.create_string_buffer(uid, 128)
             with torch.cuda.device(self.device):
                 L.check(self.lib.fb_nccl_init(h, L.nccl_library_path(), buf, world, rank), "fb_nccl_init")
             self.has_nccl = True
+        if cfg.p2p is not None:    # the library's own exchange kernels over peer memory: arena first, then the peers' arenas, then bind
+            world, rank = cfg.p2p
+            self._ipc_handle = C.create_string_buffer(64)
+            self._arena_bufs = L.fb_buffers()
+            with torch.cuda.device(self.device):
+                L.check(self.lib.fb_p2p_create(h, world, rank, self._ipc_handle, C.byref(self._arena_bufs)), "fb_p2p_create")
+            self.has_p2p = True
+            if p2p_attach == "ipc":   # one process per GPU: handles travel through torch.distributed (plumbing)
+                import torch.distributed as dist
+                handles: tp.List[tp.Any] = [None] * world
+                dist.all_gather_object(handles, self._ipc_handle.raw)
+                blob = C.create_string_buffer(b"".join(handles), 64 * world)
+                with torch.cuda.device(self.device):
+                    L.check(self.lib.fb_p2p_attach(h, blob, None), "fb_p2p_attach")
+                self._bind()
+                dist.barrier()    # every arena exists and is zeroed before anybody signals into it
+            # else: the caller attaches engines of this process to each other (attach_local) and that binds
+        else:
+            self._bind()
+
+    class _DeviceBlock:
+        """A device address range as a __cuda_array_interface__ object, so that torch can view memory the library allocated."""
+
+        def __init__(self, ptr: int, n: int) -> None:
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+    @staticmethod
+    def attach_local(engines: tp.Sequence["FBStepEngine"]) -> None:
+        """Several ranks inside ONE process (tests: R engines on one device): exchange the arena addresses directly, then bind."""
+        arenas = (C.c_void_p * len(engines))(*[e.lib.fb_p2p_arena(e.h) for e in engines])
+        for e in engines:
+            with torch.cuda.device(e.device):
+                L.check(e.lib.fb_p2p_attach(e.h, None, arenas), "fb_p2p_attach")
+                e._bind()
+
+    def _bind(self) -> None:
+        h, cfg = self.h, self.cfg
         with torch.cuda.device(self.device):
             n_fb, n_actor = self.lib.fb_flat_size(h, 0), self.lib.fb_flat_size(h, 1)
             z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.device)  # noqa: E731
-            self.param_fb, self.grad_fb, self.m_fb, self.v_fb, self.target_fb = z(n_fb), z(n_fb), z(n_fb), z(n_fb), z(n_fb)
-            self.param_actor, self.grad_actor, self.m_actor, self.v_actor = z(n_actor), z(n_actor), z(n_actor), z(n_actor)
+            if self._arena_bufs is not None:   # gradients and parameters live in the arena the peers can address
+                ab = self._arena_bufs
+                wrap = lambda ptr, n: torch.as_tensor(self._DeviceBlock(ptr, n), device=self.device)  # noqa: E731
+                self.param_fb, self.grad_fb = wrap(ab.d_param_fb, n_fb), wrap(ab.d_grad_fb, n_fb)
+                self.param_actor, self.grad_actor = wrap(ab.d_param_actor, n_actor), wrap(ab.d_grad_actor, n_actor)
+            else:
+                self.param_fb, self.grad_fb, self.param_actor, self.grad_actor = z(n_fb), z(n_fb), z(n_actor), z(n_actor)
+            self.m_fb, self.v_fb, self.target_fb = z(n_fb), z(n_fb), z(n_fb)
+            self.m_actor, self.v_actor = z(n_actor), z(n_actor)
             ws_bytes = self.lib.fb_workspace_bytes(h)
             self.workspace = torch.zeros(ws_bytes + 256, dtype=torch.uint8, device=self.device)
             ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
@@ -113,6 +160,8 @@ class FBStepEngine:
                                 self.target_fb.data_ptr(), self.param_actor.data_ptr(), self.grad_actor.data_ptr(),
                                 self.m_actor.data_ptr(), self.v_actor.data_ptr(), ws_ptr, ws_bytes)
             L.check(self.lib.fb_bind(h, C.byref(bufs), self._stream()), "fb_bind")
+        self._bound = True
+        cfg = self.cfg
         self.layout = {net: self._tensor_table(net) for net in (L.NET_FORWARD, L.NET_BACKWARD, L.NET_ACTOR)}
         self._scalars: tp.Optional[tp.Tuple[float, ...]] = None
         self._keepalive: tp.List[tp.Any] = []
@@ -334,6 +383,13 @@ class FBStepEngine:
             mask |= L.RUN_UNFUSED
         L.check(self.lib.fb_run(self.h, mask, int(graph), self._stream()), f"fb_run(0x{mask:x})")
 
+    @_on_device
+    def prepare_graph(self, mask: int = L.PHASE_ALL, fused: tp.Optional[bool] = None) -> None:
+        """Capture and instantiate the CUDA graph of `mask` without launching it."""
+        if not (self.cfg.fused if fused is None else fused):
+            mask |= L.RUN_UNFUSED
+        L.check(self.lib.fb_run(self.h, mask, 2, self._stream()), f"fb_run(0x{mask:x}, capture only)")
+
     def launch_count(self, mask: int = L.PHASE_ALL, fused: tp.Optional[bool] = None) -> int:
         """Kernel launches one run of `mask` issues (fused execution: one per fused segment / stand-alone kernel)."""
         if not (self.cfg.fused if fused is None else fused):
@@ -366,6 +422,41 @@ class FBStepEngine:
             what = L.FS_TYPES[t] if t >= 0 else ("staging batch" if t == -2 else "kernel:" + L.OP_KINDS[-1 - t])
             out.append({"us": us[i], "unit": unit, "stage": stage, "items": items, "first": what, "count": count})
         return out
+
+    @_on_device
+    def p2p_status(self) -> tp.Tuple[int, tp.List[int]]:
+        """(error code, epochs of the 8 exchange barriers); raises nothing: 0 = every wait of this rank was answered."""
+        code, ep = C.c_uint32(), (C.c_uint64 * 8)()
+        L.check(self.lib.fb_p2p_status(self.h, C.byref(code), ep, self._stream()), "fb_p2p_status")
+        return code.value, list(ep)
+
+    def moment_slice(self, actor: bool) -> tp.Tuple[int, int]:
+        """p2p exchange: the [first, first + count) float range of the flat segment whose Adam moments THIS rank owns
+        (every other range of m / v is dead on this rank); without p2p: the whole segment."""
+        if not self.has_p2p:
+            n = (self.m_actor if actor else self.m_fb).numel()
+            return 0, n
+        a, b = C.c_size_t(), C.c_size_t()
+        L.check(self.lib.fb_p2p_slice(self.h, int(actor), C.byref(a), C.byref(b)), "fb_p2p_slice")
+        return a.value, b.value
+
+    def full_moments(self) -> tp.Dict[str, torch.Tensor]:
+        """Adam moments of the whole segments: with the p2p exchange the slices are all-gathered from their owners (collective)."""
+        out = {"m_fb": self.m_fb, "v_fb": self.v_fb, "m_actor": self.m_actor, "v_actor": self.v_actor}
+        if not self.has_p2p:
+            return {k: v.clone() for k, v in out.items()}
+        import torch.distributed as dist
+        world = self.cfg.p2p[0]
+        res = {}
+        for k, t in out.items():
+            first, count = self.moment_slice(k.endswith("actor"))
+            per = -(-t.numel() // (4 * world)) * 4
+            mine = torch.zeros(per, dtype=torch.float32, device=self.device)
+            mine[:count] = t[first:first + count]
+            full = torch.empty(per * world, dtype=torch.float32, device=self.device)
+            dist.all_gather_into_tensor(full, mine)
+            res[k] = full[:t.numel()].clone()
+        return res
 
     def gather_block(self) -> tp.Tuple[torch.Tensor, torch.Tensor]:
         """(local, global) packed [rows, pitch] blocks for the multi-GPU all-gather between FB_FWD and FB_LOSS."""

@@ -22,7 +22,7 @@
  * parameter/optimizer/replay memory and never takes ownership.  Calls enqueue work on `stream`
  * (a cudaStream_t passed as void*) and do not synchronise unless documented.  Return value:
  * 0 = ok, negative = argument/state error (FB_E_*), positive = cudaError_t.  A handle may be used
- * from one host thread at a time.  No global state.
+ * from one host thread at a time.  No mutable global state (one lazily dlopen'ed table of NCCL entry points is shared by the handles of a process).
  */
 #ifndef FB_B200_H
 #define FB_B200_H
@@ -214,6 +214,26 @@ int fb_set_batch(fb_handle* h, const float* d_obs, const float* d_action, const 
  * (NULL: "libnccl.so.2" as already loaded by the process). */
 int fb_nccl_unique_id(const char* libnccl_path, void* id128);
 int fb_nccl_init(fb_handle* h, const char* libnccl_path, const void* id128, int world, int rank);
+/* The same exchange by the library's OWN kernels over NVLink peer memory (csrc/p2p.cuh), no NCCL on the step's path.  Every rank
+ * calls fb_p2p_create BEFORE fb_bind: it allocates this rank's arena (flags | gradients | parameters | global exchange block; the
+ * one allocation the library makes, because the peers must be able to open it), writes its CUDA IPC handle (64 bytes) to
+ * ipc_handle64 (may be NULL) and fills bufs->d_grad_fb / d_grad_actor / d_param_fb / d_param_actor with the arena's segments — the
+ * caller wraps those instead of allocating them and passes the SAME fb_buffers (moments, targets and workspace added) to fb_bind.
+ * fb_p2p_attach then maps the peers: ipc_handles = world x 64 bytes in rank order (every rank's handle, shipped by the host, e.g.
+ * torch.distributed.all_gather_object), or local_arenas = world pointers obtained from fb_p2p_arena when the engines share a
+ * process (tests: several ranks on one device).  The plan then contains, per step: rows of the [F|B|targets|discount] block stored
+ * into every arena (k_p2p_scatter_rows) between FB_FWD and FB_LOSS, and k_p2p_adam in FB_PHASE_FB_ADAM / ACTOR_ADAM: rank r sums
+ * slice r of the flat gradient over the arenas, applies Adam to slice r (the Adam moments of slice r are live on rank r only:
+ * fb_p2p_slice) and stores the new parameter slice into every arena; six epoch-flag barriers per step order the ranks. */
+int fb_p2p_create(fb_handle* h, int world, int rank, void* ipc_handle64, fb_buffers* bufs);
+int fb_p2p_attach(fb_handle* h, const void* ipc_handles, void* const* local_arenas);
+void* fb_p2p_arena(fb_handle* h);
+/* 0, or 0xDEAD0000 + (barrier id << 8) + peer rank of the first wait that gave up (~4 s without the peer's signal: a rank died
+ * or the ranks issued different phase sequences); the results of that step are invalid.  epochs8 (nullable): this rank's epoch
+ * counters of the 8 barriers.  Synchronises `stream`. */
+int fb_p2p_status(fb_handle* h, uint32_t* code, uint64_t* epochs8, void* stream);
+/* the float range [first, first + count) of the flat fb (actor = 0) / actor (actor = 1) segment whose Adam moments this rank owns */
+int fb_p2p_slice(const fb_handle* h, int actor, size_t* first, size_t* count);
 /* Host-buffer form of fb_set_batch = EpisodeBatch.to(device) (replay_buffer.py:50-63) as ONE copy: h_rows is [batch, pitch]
  * floats in HOST memory (pinned for an asynchronous copy) laid out by fb_batch_row_layout(obs, action, goal_dim or 0, 0,
  * future_ratio > 0): obs | action | reward, discount (already times the replay discount) | next_obs | goal | next_goal
@@ -233,7 +253,7 @@ int fb_set_noise(fb_handle* h, const float* d_noise_fb, const float* d_noise_act
 
 /* ---- the step -------------------------------------------------------------------------------- */
 /* enqueue the phases in `phase_mask` in step order.  use_graph != 0 replays a CUDA graph captured
- * (once per mask) from the same launch sequence. */
+ * (once per mask) from the same launch sequence; use_graph == 2 only captures and instantiates that graph (nothing runs). */
 int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream);
 /* number of kernel launches (graph nodes) fb_run(mask) issues */
 int fb_launch_count(fb_handle* h, uint32_t phase_mask);

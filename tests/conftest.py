@@ -1,5 +1,9 @@
 """pytest configuration: the `gpu` marker, repo root on sys.path, golden-fixture loader."""
 import os
+
+# several engines (emulated ranks) of one process spin on each other's flags: each of their streams needs its own hardware queue,
+# or a waiting kernel sits in front of the very kernels it waits for (set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import sys
 
 import numpy as np

@@ -458,7 +458,7 @@ def test_sharded_step_sums_to_single_gpu_step(world, contract_mode, q_coef):
     assert rel(shards[0].param_fb, full.param_fb) < 1e-6
     assert rel(sum(e.grad_actor for e in shards), full.grad_actor) < 2e-5
     assert sum(e.read_metrics()["actor_loss"] for e in shards) == pytest.approx(full.read_metrics()["actor_loss"], rel=1e-4, abs=1e-6)
-    for e in shards + [full]:
+    for e in shards:
         e.close()
 
 
@@ -506,3 +506,85 @@ def test_add_trunk_wide_tcgen05_against_simt_and_oracle():
     for a, b_ in zip(got[L.MLP_TCGEN05][1:], got[L.MLP_SIMT][1:]):
         for name in a:
             assert rel(a[name], b_[name]) < 3e-3, name
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world,graph", [(2, False), (2, True), (4, True)])
+def test_p2p_exchange_ranks_on_one_device(world, graph):
+    """The peer-memory exchange (csrc/p2p.cuh: row scatter, fused reduce-scatter + Adam + all-gather, epoch-flag barriers) with
+    `world` ranks emulated on ONE device: one engine per rank, each on its own stream, arenas attached by address.  Two full
+    gradient steps must land every rank on the parameters / targets of ONE engine stepping the whole batch, and the owned slices of
+    the Adam moments must tile the single-engine moments.  (Real multi-GPU ranks: bench.py's parity_check.)"""
+    from controllable_agent_b200.engine import EngineConfig, FBStepEngine
+    L = _L()
+    d = O.Dims(obs_dim=24, action_dim=6, z_dim=50, goal_dim=24, hidden_dim=128, feature_dim=64, backward_hidden_dim=70)
+    B = 64 * world
+    gen = torch.Generator().manual_seed(5)
+    actor = O.init_params(O.actor_spec(d), gen)
+    fwd = O.init_params(O.forward_map_spec(d), gen)
+    bwd = O.init_params(O.backward_map_spec(d), gen)
+    obs, next_obs = torch.randn(B, d.obs_dim, generator=gen), torch.randn(B, d.obs_dim, generator=gen)
+    action = torch.rand(B, d.action_dim, generator=gen) * 2 - 1
+    discount = 0.98 * (torch.rand(B, 1, generator=gen) > 0.1).float()
+    z = O.sample_z(B, d.z_dim, gen)
+    nf, na = torch.randn(B, d.action_dim, generator=gen), torch.randn(B, d.action_dim, generator=gen)
+    mask = L.PHASE_ALL & ~L.PHASE_SAMPLE
+
+    def feed(e, sl):
+        load_params(e, fwd=fwd, bwd=bwd, actor=actor, fwd_tgt=fwd, bwd_tgt=bwd)
+        e.set_scalars(0.2, 0.3, 1e-3, 1e-3, 1e-3, 0.01)
+        e.set_batch(obs[sl], action[sl], discount[sl], next_obs[sl])
+        e.set_z(z[sl])
+        e.set_noise(nf[sl], na[sl])
+        n = sl.stop - sl.start
+        e.set_indices(perm=np.arange(n, dtype=np.int32), mix_mask=np.zeros(n, np.int32))
+
+    full = make_engine(d, B)
+    feed(full, slice(0, B))
+    for _ in range(2):
+        full.run(mask, graph=False)
+    torch.cuda.synchronize()
+    ref_m = full.read_metrics()
+    ref = {k: getattr(full, k).clone() for k in ("param_fb", "param_actor", "target_fb", "m_fb", "v_fb", "m_actor", "v_actor")}
+    full.close()   # frees its lanes: every stream of the emulated ranks must map to a hardware queue of its own
+
+    rows = B // world
+    shards = [FBStepEngine(EngineConfig(batch=rows, obs_dim=d.obs_dim, action_dim=d.action_dim, z_dim=d.z_dim, goal_dim=d.goal_dim,
+                                        hidden_dim=d.hidden_dim, feature_dim=d.feature_dim, backward_hidden_dim=d.backward_hidden_dim,
+                                        global_batch=B, row_offset=r * rows, p2p=(world, r)), "cuda", p2p_attach="local")
+              for r in range(world)]
+    FBStepEngine.attach_local(shards)
+    streams = [torch.cuda.Stream() for _ in shards]
+    torch.cuda.synchronize()
+    for r, (e, st) in enumerate(zip(shards, streams)):
+        with torch.cuda.stream(st):
+            feed(e, slice(r * rows, (r + 1) * rows))
+    torch.cuda.synchronize()
+    if graph:   # ranks of ONE context: instantiate every graph before any rank starts spinning on its peers
+        for e in shards:
+            e.prepare_graph(mask)
+    for _ in range(2):
+        for e, st in zip(shards, streams):
+            with torch.cuda.stream(st):
+                e.run(mask, graph=graph)
+    torch.cuda.synchronize()
+    status = [e.p2p_status() for e in shards]
+    assert all(code == 0 for code, _ in status), [(hex(c), ep) for c, ep in status]
+    for r, e in enumerate(shards):
+        assert rel(e.param_fb, ref["param_fb"]) < 2e-6, r
+        assert rel(e.param_actor, ref["param_actor"]) < 2e-6, r
+        assert rel(e.target_fb, ref["target_fb"]) < 2e-6, r
+        assert float(e.grad_fb.abs().max()) == 0.0 and float(e.grad_actor.abs().max()) == 0.0   # cleared for the next step
+        assert e.get_adam_steps() == (2, 2)
+    for r in range(1, world):   # the ranks hold the SAME bits: one owner computes each slice
+        assert torch.equal(shards[r].param_fb, shards[0].param_fb) and torch.equal(shards[r].param_actor, shards[0].param_actor)
+    for name, actor_seg in (("m_fb", False), ("v_fb", False), ("m_actor", True), ("v_actor", True)):
+        tiled = torch.zeros_like(ref[name])
+        for e in shards:
+            first, count = e.moment_slice(actor_seg)
+            tiled[first:first + count] = getattr(e, name)[first:first + count]
+        assert rel(tiled, ref[name]) < 2e-5, name
+    for k in ("fb_loss", "actor_loss"):
+        assert sum(e.read_metrics()[k] for e in shards) == pytest.approx(ref_m[k], rel=1e-4, abs=1e-6), k
+    for e in shards:
+        e.close()
