@@ -15,89 +15,128 @@ import typing as tp
 import numpy as np
 import torch
 import torch.nn.functional as F
-from torch import distributions as pyd
 from torch import nn
 from torch.distributions.utils import _standard_normal
 
 
+_SCHEDULE_CALL = re.compile(r"^\s*(linear|step_linear)\((.*)\)\s*$")
+
+
+def _schedule_knots(spec: str) -> tp.Tuple[tp.List[float], tp.List[float]]:
+    """(steps, values) of the piecewise-linear curve a schedule string describes: `linear(a,b,n)` goes from a to b over n steps,
+    `step_linear(a,b,n,c,m)` continues from b to c over the m steps after n (the grammar of utils.schedule, utils.py:235-255)."""
+    m = _SCHEDULE_CALL.match(spec)
+    if m is None:
+        raise NotImplementedError(spec)
+    args = [float(x) for x in m.group(2).split(",")]
+    if m.group(1) == "linear" and len(args) == 3:
+        a, b, n = args
+        return [0.0, n], [a, b]
+    if m.group(1) == "step_linear" and len(args) == 5:
+        a, b, n, c, k = args
+        return [0.0, n, n + k], [a, b, c]
+    raise NotImplementedError(spec)
+
+
 def schedule(schdl: tp.Any, step: int) -> float:
-    """utils.schedule (utils.py:235-255): constant, linear(a,b,n) or step_linear(a,b,n,c,m)."""
+    """Value of a schedule spec at `step`: a number (or numeric string) is constant, otherwise piecewise-linear between the knots of
+    the spec and flat outside them."""
     try:
         return float(schdl)
-    except ValueError:
-        match = re.match(r'linear\((.+),(.+),(.+)\)', schdl)
-        if match:
-            init, final, duration = [float(g) for g in match.groups()]
-            mix = np.clip(step / duration, 0.0, 1.0)
-            return float((1.0 - mix) * init + mix * final)
-        match = re.match(r'step_linear\((.+),(.+),(.+),(.+),(.+)\)', schdl)
-        if match:
-            init, final1, duration1, final2, duration2 = [float(g) for g in match.groups()]
-            if step <= duration1:
-                mix = np.clip(step / duration1, 0.0, 1.0)
-                return float((1.0 - mix) * init + mix * final1)
-            mix = np.clip((step - duration1) / duration2, 0.0, 1.0)
-            return float((1.0 - mix) * final1 + mix * final2)
-    raise NotImplementedError(schdl)
+    except (TypeError, ValueError):
+        xs, ys = _schedule_knots(str(schdl))
+        return float(np.interp(float(step), xs, ys))
 
 
 def weight_init(m: nn.Module) -> None:
-    """utils.weight_init (utils.py:81-87) for the Linear layers of the FB networks."""
+    """Initialisation of the FB networks' Linear layers: orthogonal weight, zero bias (what utils.weight_init does for nn.Linear,
+    utils.py:81-87; one orthogonal_ draw per layer, in registration order, so seeded construction matches the reference)."""
     if isinstance(m, nn.Linear):
         nn.init.orthogonal_(m.weight.data)
         if m.bias is not None:
-            m.bias.data.fill_(0.0)
+            nn.init.zeros_(m.bias.data)
+
+
+def _param_pairs(net: nn.Module, target_net: nn.Module) -> tp.Tuple[tp.List[torch.Tensor], tp.List[torch.Tensor]]:
+    src, dst = [p.data for p in net.parameters()], [p.data for p in target_net.parameters()]
+    if len(src) != len(dst):
+        raise ValueError("networks with different parameter lists")
+    return src, dst
 
 
 def soft_update_params(net: nn.Module, target_net: nn.Module, tau: float) -> None:
-    for param, target_param in zip(net.parameters(), target_net.parameters()):
-        target_param.data.copy_(tau * param.data + (1 - tau) * target_param.data)
+    """target <- tau * net + (1 - tau) * target, parameter by parameter in registration order (host-side twin of the lerp fused into
+    k_adam; utils.py:66-69).  The agent's step does this on the device; this exists for callers that poke the modules."""
+    src, dst = _param_pairs(net, target_net)
+    with torch.no_grad():   # two rounded products and one rounded sum per element (no fused multiply-add): bit-identical to the reference
+        mixed = torch._foreach_add(torch._foreach_mul(src, tau), torch._foreach_mul(dst, 1.0 - tau))
+        torch._foreach_copy_(dst, mixed)
 
 
 def hard_update_params(net: nn.Module, target_net: nn.Module) -> None:
-    for param, target_param in zip(net.parameters(), target_net.parameters()):
-        target_param.data.copy_(param.data)
+    """target <- net (utils.py:72-74), what init_from uses to adopt another agent's networks."""
+    src, dst = _param_pairs(net, target_net)
+    with torch.no_grad():
+        torch._foreach_copy_(dst, src)
 
 
-class TruncatedNormal(pyd.Normal):
-    """utils.TruncatedNormal (utils.py:164-185): clipped noise, value clamp with straight-through gradient."""
+class TruncatedNormal:
+    """The action distribution the actor returns: N(loc, scale) whose samples are clipped noise around loc, clamped into
+    (low, high) with a straight-through gradient (the contract of utils.TruncatedNormal, utils.py:164-185, which the CUDA step
+    implements in k_actor_out).  Only what callers of `agent.actor(...)` use is provided: mean / loc / scale / stddev, sample(clip),
+    log_prob."""
 
     def __init__(self, loc: torch.Tensor, scale: torch.Tensor, low: float = -1.0, high: float = 1.0, eps: float = 1e-6) -> None:
-        super().__init__(loc, scale, validate_args=False)
-        self.low, self.high, self.eps = low, high, eps
+        self.loc, self.scale = loc, scale
+        self._lo, self._hi = low + eps, high - eps
 
-    def _clamp(self, x: torch.Tensor) -> torch.Tensor:
-        clamped_x = torch.clamp(x, self.low + self.eps, self.high - self.eps)
-        return x - x.detach() + clamped_x.detach()
+    @property
+    def mean(self) -> torch.Tensor:
+        return self.loc
 
-    def sample(self, clip: tp.Optional[float] = None, sample_shape: torch.Size = torch.Size()) -> torch.Tensor:  # type: ignore
-        shape = self._extended_shape(sample_shape)
-        eps = _standard_normal(shape, dtype=self.loc.dtype, device=self.loc.device)
-        eps *= self.scale
+    @property
+    def stddev(self) -> torch.Tensor:
+        return self.scale
+
+    def sample(self, clip: tp.Optional[float] = None, sample_shape: torch.Size = torch.Size()) -> torch.Tensor:
+        shape = torch.Size(sample_shape) + self.loc.shape
+        noise = _standard_normal(shape, dtype=self.loc.dtype, device=self.loc.device) * self.scale   # one draw per element, like the reference
         if clip is not None:
-            eps = torch.clamp(eps, -clip, clip)
-        return self._clamp(self.loc + eps)
+            noise = noise.clamp(-clip, clip)
+        x = self.loc + noise
+        inside = x.clamp(self._lo, self._hi).detach()
+        return inside + (x - x.detach())   # value: the clamped sample, exactly; gradient w.r.t. loc: identity
+
+    def log_prob(self, value: torch.Tensor) -> torch.Tensor:
+        var = self.scale ** 2
+        return -((value - self.loc) ** 2) / (2 * var) - torch.log(self.scale) - 0.5 * math.log(2 * math.pi)
+
+
+_ACTIVATIONS: tp.Dict[str, tp.Callable[[int], tp.List[nn.Module]]] = {
+    "irelu": lambda width: [nn.ReLU(inplace=True)],
+    "relu": lambda width: [nn.ReLU()],
+    "ntanh": lambda width: [nn.LayerNorm(width), nn.Tanh()],
+}
 
 
 def mlp(*layers: tp.Union[int, str]) -> nn.Sequential:
-    """fb_modules.mlp (fb_modules.py:60-78): ints are Linear widths, strings name the non-linearity."""
-    assert len(layers) >= 2 and isinstance(layers[0], int)
-    seq: tp.List[nn.Module] = []
-    prev = layers[0]
-    for layer in layers[1:]:
-        if isinstance(layer, str):
-            if layer == "irelu":
-                seq.append(nn.ReLU(inplace=True))
-            elif layer == "relu":
-                seq.append(nn.ReLU())
-            elif layer == "ntanh":
-                seq.extend([nn.LayerNorm(prev), nn.Tanh()])
-            else:
-                raise ValueError(f"Unknown non-linearity {layer}")
+    """Sequential stack from a width / activation list in the reference's notation (fb_modules.py:60-78): the first entry is the
+    input width, every further int adds a Linear to that width, every string an activation from _ACTIVATIONS ("ntanh" = LayerNorm
+    + Tanh, "irelu" = in-place ReLU).  Module indices — and therefore parameter names like `0.weight`, `1.bias`, `3.weight` — come
+    out as the reference's, which is what the flat parameter layout of the library is keyed on."""
+    if len(layers) < 2 or not isinstance(layers[0], int):
+        raise ValueError("mlp(in_width, ...) needs an input width and at least one layer")
+    width = layers[0]
+    stack: tp.List[nn.Module] = []
+    for item in layers[1:]:
+        if isinstance(item, int):
+            stack.append(nn.Linear(width, item))
+            width = item
+        elif item in _ACTIVATIONS:
+            stack.extend(_ACTIVATIONS[item](width))
         else:
-            seq.append(nn.Linear(prev, layer))
-            prev = layer
-    return nn.Sequential(*seq)
+            raise ValueError(f"Unknown non-linearity {item}")
+    return nn.Sequential(*stack)
 
 
 class Actor(nn.Module):

@@ -43,50 +43,57 @@ class EpisodeBatch(tp.Generic[T]):
     future_goal: tp.Optional[T] = None
 
     def __post_init__(self) -> None:
-        assert isinstance(self.reward, (np.ndarray, torch.Tensor))
-        assert isinstance(self.discount, (np.ndarray, torch.Tensor))
-        assert isinstance(self.meta, dict)
+        for name in ("reward", "discount"):
+            if not isinstance(getattr(self, name), (np.ndarray, torch.Tensor)):
+                raise TypeError(f"EpisodeBatch.{name} must be an array or a tensor")
+        if not isinstance(self.meta, dict):
+            raise TypeError("EpisodeBatch.meta must be a dict")
+
+    # -- array fields, in declaration order (everything but `meta`) ---------------------------------
+    @classmethod
+    def _array_fields(cls) -> tp.List[str]:
+        return [f.name for f in dataclasses.fields(cls) if f.name != "meta"]
 
     def to(self, device: tp.Union[str, torch.device]) -> "EpisodeBatch[torch.Tensor]":
-        out: tp.Dict[str, tp.Any] = {}
-        for field in dataclasses.fields(self):
-            data = getattr(self, field.name)
-            if field.name == "meta":
-                out[field.name] = {k: torch.as_tensor(v, device=device) for k, v in data.items()}
-            elif isinstance(data, (torch.Tensor, np.ndarray)):
-                out[field.name] = torch.as_tensor(data, device=device)
-            elif data is None:
-                out[field.name] = None
-            else:
-                raise RuntimeError(f"Not sure what to do with {field.name}: {data}")
-        return EpisodeBatch(**out)
+        """Every array / tensor field (and every meta entry) as a tensor on `device`; absent optional fields stay None
+        (replay_buffer.py:50-63).  Batches sampled from the HBM replay are already device tensors: nothing is copied."""
+        def move(name: str, value: tp.Any) -> tp.Any:
+            if value is None:
+                return None
+            if not isinstance(value, (torch.Tensor, np.ndarray)):
+                raise RuntimeError(f"Not sure what to do with {name}: {value}")
+            return torch.as_tensor(value, device=device)
+        moved = {name: move(name, getattr(self, name)) for name in self._array_fields()}
+        return EpisodeBatch(meta={k: torch.as_tensor(v, device=device) for k, v in self.meta.items()}, **moved)
 
     @classmethod
     def collate_fn(cls, batches: tp.List["EpisodeBatch[T]"]) -> "EpisodeBatch[torch.Tensor]":
-        out: tp.Dict[str, tp.Any] = {}
+        """Stack a list of batches field by field (replay_buffer.py:65-88): numpy batches are first moved to CPU tensors, a field must
+        be present in all batches or in none."""
         if isinstance(batches[0].obs, np.ndarray):
             batches = [b.to("cpu") for b in batches]  # type: ignore
-        for field in dataclasses.fields(cls):
-            data = [getattr(b, field.name) for b in batches]
-            if data[0] is None:
-                if any(x is not None for x in data):
-                    raise RuntimeError("Found a non-None value mixed with Nones")
-                out[field.name] = None
-            elif field.name == "meta":
-                out[field.name] = {k: torch.stack([d[k] for d in data]) for k in data[0]}
-            elif isinstance(data[0], torch.Tensor):
-                out[field.name] = torch.stack(data)
+        stacked: tp.Dict[str, tp.Any] = {}
+        for name in cls._array_fields():
+            column = [getattr(b, name) for b in batches]
+            if all(x is None for x in column):
+                stacked[name] = None
+            elif any(x is None for x in column):
+                raise RuntimeError("Found a non-None value mixed with Nones")
+            elif isinstance(column[0], torch.Tensor):
+                stacked[name] = torch.stack(column)
             else:
-                raise RuntimeError(f"Not sure what to do with {field.name}: {data}")
-        return EpisodeBatch(**out)
+                raise RuntimeError(f"Not sure what to do with {name}: {column}")
+        meta = {k: torch.stack([b.meta[k] for b in batches]) for k in batches[0].meta}
+        return EpisodeBatch(meta=meta, **stacked)
 
     def unpack(self) -> tp.Tuple[T, T, T, T, T]:
-        return (self.obs, self.action, self.reward, self.discount, self.next_obs)
+        """(obs, action, reward, discount, next_obs) — the tuple order DDPG-style agents destructure (replay_buffer.py:90-96)."""
+        return self.obs, self.action, self.reward, self.discount, self.next_obs
 
     def with_no_reward(self: B) -> B:
-        reward = self.reward
-        reward = torch.zeros_like(reward) if isinstance(reward, torch.Tensor) else 0 * reward
-        return dataclasses.replace(self, reward=reward)
+        """A copy whose reward field is all zeros (replay_buffer.py:98-103)."""
+        zero = torch.zeros_like(self.reward) if isinstance(self.reward, torch.Tensor) else np.zeros_like(self.reward)
+        return dataclasses.replace(self, reward=zero)
 
 
 def load_episode(fn: tp.Any) -> tp.Dict[str, np.ndarray]:

@@ -250,3 +250,26 @@ def test_replay_load_reads_episode_files_in_order_until_full(tmp_path):
     big = Recorder(max_episodes=8, discount=0.98, future=0.99)
     big.load(None, str(tmp_path), relabel=False)
     assert len(big.seen) == 5 and not big._full and len(big) == 5
+
+
+def test_episode_batch_collate_to_and_reward_masking():
+    """Reads like url_benchmark/test_replay_buffer.py:10-32, on this package's EpisodeBatch (same container contract)."""
+    from controllable_agent_b200 import EpisodeBatch
+    shapes = dict(obs=(4, 12), action=(5, 11), next_obs=(6, 10))
+    meta = dict(a=np.random.rand(16), b=np.random.rand(17))
+    batch = EpisodeBatch(reward=np.array([1.0]), discount=np.array([0.5]), meta=meta, **{x: np.random.rand(*y) for x, y in shapes.items()})
+    batches = EpisodeBatch.collate_fn([batch, batch])
+    assert batches.obs.shape == (2, 4, 12)
+    assert isinstance(batches.meta, dict) and len(batches.meta) == 2 and batches.meta["a"].shape == (2, 16)
+    cpu = batch.to("cpu")
+    assert cpu.reward.shape == (1,) and cpu.goal is None
+    batches = EpisodeBatch.collate_fn([cpu, cpu])
+    assert batches.reward.shape == (2, 1)
+    no_reward = batches.with_no_reward()
+    assert not no_reward.reward.abs().sum(), "reward should be masked"
+    assert batches.reward.abs().sum(), "reward should not be masked"
+    assert no_reward.obs is batches.obs, "observations must not be copied"
+    assert [x.shape for x in batches.unpack()] == [(2, 4, 12), (2, 5, 11), (2, 1), (2, 1), (2, 6, 10)]
+    mixed = EpisodeBatch(reward=np.array([1.0]), discount=np.array([0.5]), goal=np.zeros(3), **{x: np.random.rand(*y) for x, y in shapes.items()})
+    with pytest.raises(RuntimeError, match="mixed with Nones"):
+        EpisodeBatch.collate_fn([batch, mixed])
