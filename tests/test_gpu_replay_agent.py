@@ -601,3 +601,113 @@ def test_update_fb_then_update_actor_on_explicit_tensors_against_oracle():
     ma = agent.update_actor(obs, z, 1)
     ora_a = O.actor_loss_and_grads(actor, fwd1, obs, z, noise_actor, 0.2, 0.3)
     assert ma["actor_loss"] == pytest.approx(float(ora_a["actor_loss"]), rel=1e-3)
+
+
+def test_workspace_shaped_offline_loop(tmp_path):
+    """What url_benchmark's offline workspace does with an agent and a replay buffer, in its order (train_offline.py:56-134,
+    pretrain.py:147-206,374-435,437-494): ctor pokes (`agent.cfg.update_every_steps = 1`, `_future`, `_discount`, `_max_episodes`
+    from `_storage`), the train loop (update -> metrics dict -> checkpoint of {agent, global_step, ...} excluding the replay),
+    eval (zero-shot z from rewards through infer_meta_from_obs_and_rewards, act() per environment step under eval_mode, z_correl),
+    then a fresh workspace that reloads the checkpoint through agent.init_from and keeps training on the same trajectory."""
+    from controllable_agent_b200 import FBDDPGAgent, ReplayBuffer
+    O_, A_, Z, B = 24, 6, 50, 128
+    torch.manual_seed(1)
+    np.random.seed(1)
+    base = dict(obs_type="states", obs_shape=(O_,), action_shape=(A_,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,
+                use_tb=True, use_wandb=False, use_hiplog=True, batch_size=B, z_dim=Z, hidden_dim=256, feature_dim=128, backward_hidden_dim=134,
+                num_inference_steps=300)
+
+    class Workspace:
+        _CHECKPOINTED_KEYS = ("agent", "global_step", "global_episode", "replay_loader")
+
+        def __init__(self, replay=None):
+            self.agent = FBDDPGAgent(**base)
+            assert isinstance(self.agent, FBDDPGAgent)           # the isinstance gates of pretrain.py:151-155,405-408
+            self.agent.cfg.update_every_steps = 1                # train_offline.py:59
+            self.global_step, self.global_episode = 0, 0
+            self.replay_loader = replay
+            if replay is not None:
+                replay._future, replay._discount = 0.99, 0.98    # train_offline.py:92-95
+                replay._max_episodes = len(replay._storage["discount"])
+
+        def save_checkpoint(self, fp, exclude=()):
+            payload = {k: self.__dict__[k] for k in self._CHECKPOINTED_KEYS if k not in exclude}
+            with open(fp, "wb") as f:
+                torch.save(payload, f, pickle_protocol=4)
+
+        def load_checkpoint(self, fp, only=None):
+            with open(fp, "rb") as f:
+                payload = torch.load(f, weights_only=False)
+            for name, val in payload.items():
+                if only is not None and name not in only:
+                    continue
+                if name == "agent":
+                    self.agent.init_from(val)
+                elif name == "replay_loader":
+                    val._current_episode.clear()
+                    val._max_episodes = len(val._storage["discount"])
+                    self.replay_loader = val
+                else:
+                    setattr(self, name, val)
+
+    rs = np.random.RandomState(0)
+    replay = ReplayBuffer(max_episodes=6, discount=0.98, future=0.99)
+    for _ in range(6):
+        n = 41
+        replay.add_episode({"observation": rs.randn(n, O_).astype(np.float32), "action": rs.uniform(-1, 1, (n, A_)).astype(np.float32),
+                            "reward": rs.uniform(0, 1, (n, 1)).astype(np.float32), "discount": np.ones((n, 1), np.float32),
+                            "physics": rs.randn(n, 4).astype(np.float32)})
+    ws = Workspace(replay)
+    logged = []
+    ckpt = tmp_path / "latest.pt"
+    for _ in range(6):
+        metrics = ws.agent.update(ws.replay_loader, ws.global_step)
+        assert {"fb_loss", "orth_loss", "fb_opt_lr"} <= set(metrics) and all(np.isfinite(v) for v in metrics.values())
+        logged.append(metrics)
+        ws.global_step += 1
+        if ws.global_step % 3 == 0:
+            ws.save_checkpoint(ckpt, exclude=["replay_loader"])
+    assert logged[-1]["fb_loss"] != logged[0]["fb_loss"]
+
+    # eval: zero-shot inference of z from (next_obs, reward) samples, then act() per step under eval_mode semantics
+    class Reward:
+        @staticmethod
+        def from_physics(p):
+            return float(p[0])
+    obs_list, reward_list, n = [], [], 0
+    while n < ws.agent.cfg.num_inference_steps:
+        batch = ws.replay_loader.sample(B, custom_reward=Reward()).to("cuda")
+        obs_list.append(batch.next_obs)
+        reward_list.append(batch.reward)
+        n += batch.next_obs.size(0)
+    obs_t = torch.cat(obs_list, 0)[:ws.agent.cfg.num_inference_steps]
+    rew_t = torch.cat(reward_list, 0)[:ws.agent.cfg.num_inference_steps]
+    meta = ws.agent.infer_meta_from_obs_and_rewards(obs_t, rew_t)
+    assert meta["z"].shape == (Z,) and abs(np.linalg.norm(meta["z"]) - np.sqrt(Z)) < 1e-3
+    was_training = ws.agent.training
+    ws.agent.train(False)
+    action = ws.agent.act(rs.randn(O_).astype(np.float32), meta, ws.global_step, eval_mode=True)
+    ws.agent.train(was_training)
+    assert action.shape == (A_,) and np.all(np.abs(action) <= 1.0)
+
+    class TS:
+        observation = rs.randn(O_).astype(np.float32)
+    assert -1.0 <= ws.agent.compute_z_correl(TS(), meta) <= 1.0
+    meta2 = ws.agent.infer_meta(ws.replay_loader)
+    assert meta2["z"].shape == (Z,)
+
+    # a fresh workspace reloads the checkpoint (agent.init_from of the pickled agent) and continues: same parameters, same Adam
+    # state, therefore the same next update as the original agent given the same RNG streams
+    ws2 = Workspace(replay)
+    ws2.load_checkpoint(ckpt)
+    assert ws2.global_step == 6
+    for name in ("actor", "forward_net", "backward_net", "forward_target_net", "backward_target_net"):
+        for p, q in zip(getattr(ws.agent, name).parameters(), getattr(ws2.agent, name).parameters()):
+            assert torch.equal(p.data, q.data), name
+    assert ws2.agent.engine.get_adam_steps() == ws.agent.engine.get_adam_steps() == (6, 6)
+    sd, sd2 = ws.agent.fb_opt.state_dict(), ws2.agent.fb_opt.state_dict()
+    assert float(sd["state"][0]["step"]) == float(sd2["state"][0]["step"]) == 6.0
+    assert torch.equal(sd["state"][0]["exp_avg"], sd2["state"][0]["exp_avg"])
+    m1 = ws.agent.update(ws.replay_loader, 6)
+    m2 = ws2.agent.update(ws2.replay_loader, 6)
+    assert m1.keys() == m2.keys()   # (device RNG streams of the two agents differ: values are not compared)
