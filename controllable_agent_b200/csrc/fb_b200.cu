@@ -1108,11 +1108,15 @@ static int build_plan(fb_handle* h) {
         fb_launch_pdl(k_p2p_finish, dim3(FB_SM_COUNT * 8), dim3(256), 0, s, (const float4*)p, g, t, n4, (const DevScalars*)sc);
         return cudaGetLastError();
       }, FB_OPK_ADAM, 0.0, 16.0 * (double)n4 * 4.0);
-    } else
+    } else {
     b.push([=](cudaStream_t s) {
       fb_launch_pdl(k_adam, dim3(FB_SM_COUNT * 8), dim3(256), 0, s, p, g, m, v, t, n4, split4, sc, 0, b1, b2, eps);
       return cudaGetLastError();
     }, FB_OPK_ADAM, 0.0, 4.0 * 4.0 * (double)n4 * 10.0);  // r(p,g,m,v,target) + w(p,g,m,v,target)
+    // Adam step count + the next step's bias corrections: one thread on the side lane, behind k_adam (its CTAs read the scalars)
+    b.push([=](cudaStream_t s) { fb_launch_pdl(k_tick, dim3(1), dim3(32), 0, s, sc, 0, b1, b2); return cudaGetLastError(); },
+           FB_OPK_ELEMENTWISE, 0.0, 0.0, 1);
+    }
   }
 
   // =========================== FB_PHASE_ACTOR_FWD ===============================================
@@ -1221,11 +1225,14 @@ static int build_plan(fb_handle* h) {
         fb_launch_pdl(k_p2p_finish, dim3(FB_SM_COUNT * 8), dim3(256), 0, s, (const float4*)p, g, (float4*)nullptr, n4, (const DevScalars*)sc);
         return cudaGetLastError();
       }, FB_OPK_ADAM, 0.0, 16.0 * (double)n4);
-    } else
+    } else {
     b.push([=](cudaStream_t s) {
       fb_launch_pdl(k_adam, dim3(FB_SM_COUNT * 8), dim3(256), 0, s, p, g, m, v, nullptr, n4, n4, sc, 1, b1, b2, eps);
       return cudaGetLastError();
     }, FB_OPK_ADAM, 0.0, 4.0 * 4.0 * (double)n4 * 8.0);
+    b.push([=](cudaStream_t s) { fb_launch_pdl(k_tick, dim3(1), dim3(32), 0, s, sc, 1, b1, b2); return cudaGetLastError(); },
+           FB_OPK_ELEMENTWISE, 0.0, 0.0, 1);
+    }
   }
 
   // =========================== FB_PHASE_METRICS =================================================

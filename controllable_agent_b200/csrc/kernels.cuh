@@ -1179,9 +1179,9 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
   fb_pdl_trigger();
   fb_pdl_wait();
   // this launch is Adam step t = (steps so far) + 1; its bias corrections were published by the previous step (or by
-  // fb_bind / fb_set_adam_steps); the CTA that finishes last publishes t and the corrections of step t + 1 (no separate
-  // "tick" launch on the step's critical path, no fp64 pow in front of the streaming loop)
-  const long long t = (which == 0 ? sc->step_fb : sc->step_actor) + 1;
+  // fb_bind / fb_set_adam_steps).  The step count and the corrections of step t + 1 are published by k_tick, a one-thread launch
+  // on the side lane right behind this kernel: the streaming CTAs end without a ticket (a ticket at the end of every CTA cost this
+  // pass a sixth of its bandwidth: 0.68 instead of 0.81 of the copy peak, profiles/r1d) and nothing of it sits on the critical path.
   const float bc1 = which == 0 ? sc->bc1_fb : sc->bc1_actor;
   const float bc2s = which == 0 ? sc->bc2s_fb : sc->bc2s_actor;
   const float lr_a = which == 0 ? sc->lr_forward : sc->lr_actor;
@@ -1207,17 +1207,6 @@ __global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, float4* __
       tt.x = tau * pp.x + (1.f - tau) * tt.x; tt.y = tau * pp.y + (1.f - tau) * tt.y;
       tt.z = tau * pp.z + (1.f - tau) * tt.z; tt.w = tau * pp.w + (1.f - tau) * tt.w;
       target[i] = tt;
-    }
-  }
-  __syncthreads();   // every thread of this CTA has read the scalars (no fence needed: the ticket orders reads of `sc`, not the
-                     // streamed parameter stores, which become visible at kernel end as usual)
-  if (threadIdx.x == 0) {
-    if (atomicAdd(&sc->adam_ticket[which], 1u) == gridDim.x - 1) {   // every other CTA has read the scalars long ago
-      float n1, n2;
-      adam_bias_corrections(beta1, beta2, t + 1, &n1, &n2);
-      if (which == 0) { sc->step_fb = t; sc->bc1_fb = n1; sc->bc2s_fb = n2; }
-      else { sc->step_actor = t; sc->bc1_actor = n1; sc->bc2s_actor = n2; }
-      sc->adam_ticket[which] = 0u;
     }
   }
 }
