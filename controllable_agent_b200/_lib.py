@@ -19,7 +19,7 @@ CONTRACT_TCGEN05, CONTRACT_SIMT = 0, 1
 MLP_TCGEN05, MLP_SIMT = 0, 1
 HEADER = os.path.join(ROOT, "include", "fb_b200.h")
 
-FB_ABI_VERSION = 3
+FB_ABI_VERSION = 4
 FB_OK = 0
 
 NET_FORWARD, NET_BACKWARD, NET_ACTOR = 0, 1, 2
@@ -59,7 +59,8 @@ class fb_config(C.Structure):
                 ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float), ("future_ratio", C.c_float),
                 ("seed", C.c_uint64), ("q_loss", C.c_int32), ("q_loss_coef", C.c_float),
                 ("no_norm_z", C.c_int32), ("rand_weight", C.c_int32),
-                ("add_trunk", C.c_int32), ("no_preprocess", C.c_int32)]
+                ("add_trunk", C.c_int32), ("no_preprocess", C.c_int32),
+                ("boltzmann", C.c_int32), ("temp", C.c_float), ("log_std_min", C.c_float), ("log_std_max", C.c_float)]
 
 
 class fb_step_scalars(C.Structure):

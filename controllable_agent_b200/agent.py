@@ -122,7 +122,7 @@ def register_hydra() -> None:
     ConfigStore.instance().store(group="agent", name="fb_ddpg", node=FBDDPGAgentConfig)
 
 
-_UNSUPPORTED = {"boltzmann": False, "debug": False}
+_UNSUPPORTED = {"debug": False}
 
 
 class _EngineAdam(torch.optim.Adam):
@@ -199,7 +199,8 @@ class FBDDPGAgent:
             batch=local, obs_dim=self.obs_dim, action_dim=self.action_dim, z_dim=cfg.z_dim, goal_dim=goal_dim,
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
-            mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, q_loss=bool(cfg.q_loss), q_loss_coef=float(cfg.q_loss_coef), norm_z=bool(cfg.norm_z), rand_weight=bool(cfg.rand_weight), add_trunk=bool(cfg.add_trunk), preprocess=bool(cfg.preprocess), seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
+            mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, q_loss=bool(cfg.q_loss), q_loss_coef=float(cfg.q_loss_coef), norm_z=bool(cfg.norm_z), rand_weight=bool(cfg.rand_weight), add_trunk=bool(cfg.add_trunk), preprocess=bool(cfg.preprocess),
+            boltzmann=bool(cfg.boltzmann), temp=float(cfg.temp), log_std_bounds=(float(cfg.log_std_bounds[0]), float(cfg.log_std_bounds[1])), seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
             mlp_mode=L.MLP_SIMT if cfg.mlp_mode == "simt" else L.MLP_TCGEN05,
             contract_mode=L.CONTRACT_SIMT if cfg.contract_mode == "simt" else L.CONTRACT_TCGEN05), device)
 
@@ -207,7 +208,10 @@ class FBDDPGAgent:
         # ForwardMap target — fb_ddpg.py:117-139) so that the torch CPU generator is consumed identically, then moved
         # onto the flat device segments
         e = self.engine
-        self.actor = M.Actor(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk, preprocess=cfg.preprocess)
+        if cfg.boltzmann:   # fb_ddpg.py:118-120
+            self.actor: nn.Module = M.DiagGaussianActor(self.obs_dim, cfg.z_dim, self.action_dim, cfg.hidden_dim, cfg.log_std_bounds)
+        else:
+            self.actor = M.Actor(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk, preprocess=cfg.preprocess)
         self.forward_net = M.ForwardMap(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk, preprocess=cfg.preprocess)
         self.backward_net = M.BackwardMap(goal_dim, cfg.z_dim, cfg.backward_hidden_dim, norm_z=cfg.norm_z)
         self.backward_target_net = M.BackwardMap(goal_dim, cfg.z_dim, cfg.backward_hidden_dim, norm_z=cfg.norm_z)
@@ -375,6 +379,18 @@ class FBDDPGAgent:
         obs_np = np.asarray(obs, dtype=np.float32).reshape(1, -1)
         z_np = np.asarray(meta["z"], dtype=np.float32).reshape(1, -1)
         mu = self.engine.infer_actor(obs_np, z_np)
+        if self.cfg.boltzmann:
+            # the plan returns [mu | std] of the pre-tanh Normal (fb_modules.py:141-151); dist.mean = tanh(mu), dist.sample() = tanh of a
+            # torch.normal draw on the device generator (utils.py:218-233)
+            loc, std = mu[:, :self.action_dim], mu[:, self.action_dim:]
+            if eval_mode:
+                mu = np.tanh(loc)
+            else:
+                dev = self.cfg.device
+                action = torch.tanh(torch.normal(torch.as_tensor(loc, device=dev), torch.as_tensor(std, device=dev)))
+                if step < self.cfg.num_expl_steps:
+                    action.uniform_(-1.0, 1.0)
+                return action.cpu().numpy()[0]
         if eval_mode:
             action = mu
             if self.cfg.additional_metric:   # F(s, z, mu) against F(s, z, random action): diagnostic branch, parameter-view modules

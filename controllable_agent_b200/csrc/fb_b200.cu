@@ -522,13 +522,16 @@ static LnBwdDesc embed_ln_bwd(const EmbedAct& e, const PSet& p, const Mat& dy, i
 
 // activations of one BackwardMap instance: Linear -> LN -> Tanh -> Linear -> ReLU -> Linear -> sqrt(Z) normalize
 struct BAct { Mat x, pre, y, h2, raw, out; float* mean; float* rstd; float* nrm; };
-static BAct b_alloc(fb_handle* h, const Mat& x, const Mat& out, const std::string& name) {
+// width / out_dim: hidden and output widths (defaults: the BackwardMap's); the DiagGaussianActor of cfg.boltzmann has the same shape
+static BAct b_alloc(fb_handle* h, const Mat& x, const Mat& out, const std::string& name, int width = 0, int out_dim = 0) {
   const fb_config& c = h->cfg;
+  if (!width) width = c.backward_hidden_dim;
+  if (!out_dim) out_dim = c.z_dim;
   BAct b; b.x = x; b.out = out;
-  b.pre = ws_mat(h, x.rows, c.backward_hidden_dim, (name + ".pre").c_str());
-  b.y = ws_mat(h, x.rows, c.backward_hidden_dim, (name + ".y").c_str());
-  b.h2 = ws_mat(h, x.rows, c.backward_hidden_dim, (name + ".h2").c_str());
-  b.raw = ws_mat(h, x.rows, c.z_dim, (name + ".raw").c_str());
+  b.pre = ws_mat(h, x.rows, width, (name + ".pre").c_str());
+  b.y = ws_mat(h, x.rows, width, (name + ".y").c_str());
+  b.h2 = ws_mat(h, x.rows, width, (name + ".h2").c_str());
+  b.raw = ws_mat(h, x.rows, out_dim, (name + ".raw").c_str());
   b.mean = (float*)ws_alloc(h, x.rows * sizeof(float));
   b.rstd = (float*)ws_alloc(h, x.rows * sizeof(float));
   b.nrm = (float*)ws_alloc(h, x.rows * sizeof(float));
@@ -569,6 +572,10 @@ static int build_plan(fb_handle* h) {
   const int Hc = deep ? H : 2 * Fd;      // width of the (concatenated) embed output the trunk / heads read
   const int act_col = deep ? O + Z : O;  // column of the action inside the forward-net inputs
   const int nz = c.no_norm_z ? 0 : 1;   // cfg.norm_z: sqrt(Z)-sphere projection of backward_net outputs and of the mixed z
+  // cfg.boltzmann: the actor is ONE BackwardMap-shaped stack (Linear -> LN -> tanh -> Linear -> ReLU -> Linear) on [obs | z] with a
+  // [mu | raw log-std] output; every launch of the default actor (two embeds, trunk, policy head) is built with zero rows and
+  // drops out in the Builder, the stack's layers join the grouped launches of the same depth
+  const bool bz = c.boltzmann != 0;
   for (auto& v : h->ops) v.clear();
   for (auto& v : h->early_stage) v.clear();
   for (auto& v : h->early_avail) v.clear();
@@ -604,7 +611,7 @@ static int build_plan(fb_handle* h) {
   h->packed = ws_mat(h, B, L.pitch, "packed");
 
   // ---- step inputs ---------------------------------------------------------------------------
-  Mat actor_in_o = ws_mat(h, deep ? 0 : 2 * B, O, "actor_in_o");
+  Mat actor_in_o = ws_mat(h, (deep || bz) ? 0 : 2 * B, O, "actor_in_o");
   Mat actor_in_oz = ws_mat(h, 2 * B, O + Z, "actor_in_oz");
   Mat in_oa = ws_mat(h, B, act_col + A, "in_oa");      // [obs | action], or [obs | z | action]
   Mat in_noa = ws_mat(h, B, act_col + A, "in_noa");
@@ -660,14 +667,16 @@ static int build_plan(fb_handle* h) {
   const int A_O = 0, A_OZ = deep ? 0 : 6, A_TR = NE, A_POL = NE + T_N;                        // actor (deep: A_O is never launched)
 
   // ---- activations ---------------------------------------------------------------------------
-  Mat hA = ws_mat(h, 2 * B, Hc, "hA");
+  const int RA = bz ? 0 : 2 * B, RA1 = bz ? 0 : B;   // rows of the default actor's activations / gradients (none with cfg.boltzmann)
+  Mat hA = ws_mat(h, RA, Hc, "hA");
   Mat hFt = ws_mat(h, B, Hc, "hFt");
   Mat hF = ws_mat(h, B, Hc, "hF");
   Mat hF2 = ws_mat(h, B, Hc, "hF2");
   const int oz0 = deep ? 0 : Fd;   // first column of the obs_z embed inside the concatenated output
   auto oz_rows = [&](int r0) { Mat m = actor_in_oz.rs(r0, B); if (deep) m.rows = 0; return m; };   // forward_net's obs_z embeds: absent when deep
   EmbedAct eAo = embed_alloc(h, actor_in_o, hA.cs(0, Fe), H, "actor.obs_net");
-  EmbedAct eAoz = embed_alloc(h, actor_in_oz, hA.cs(oz0, Fe), H, "actor.obs_z_net");
+  Mat actor_oz_x = actor_in_oz; actor_oz_x.rows = RA;
+  EmbedAct eAoz = embed_alloc(h, actor_oz_x, hA.cs(oz0, Fe), H, "actor.obs_z_net");
   EmbedAct eFtoa = embed_alloc(h, in_noa, hFt.cs(0, Fe), H, "Ft.obs_action_net");
   EmbedAct eFtoz = embed_alloc(h, oz_rows(0), hFt.cs(oz0, Fe), H, "Ft.obs_z_net");
   EmbedAct eFoa = embed_alloc(h, in_oa, hF.cs(0, Fe), H, "F.obs_action_net");
@@ -676,10 +685,14 @@ static int build_plan(fb_handle* h) {
   EmbedAct eF2oz = embed_alloc(h, oz_rows(B), hF2.cs(oz0, Fe), H, "F2.obs_z_net");
   // add_trunk: ReLU(Linear(2 Fd -> H)) of each concatenated embed pair; the heads then read these instead of hA / hFt / hF / hF2
   Mat trA, trFt, trF, trF2;
-  if (trunk) { trA = ws_mat(h, 2 * B, H, "actor.trunk"); trFt = ws_mat(h, B, H, "Ft.trunk"); trF = ws_mat(h, B, H, "F.trunk"); trF2 = ws_mat(h, B, H, "F2.trunk"); }
+  if (trunk) { trA = ws_mat(h, RA, H, "actor.trunk"); trFt = ws_mat(h, B, H, "Ft.trunk"); trF = ws_mat(h, B, H, "F.trunk"); trF2 = ws_mat(h, B, H, "F2.trunk"); }
   const Mat& inFt = trunk ? trFt : hFt; const Mat& inF = trunk ? trF : hF; const Mat& inF2 = trunk ? trF2 : hF2;
-  Mat h1A = ws_mat(h, 2 * B, H, "actor.policy.h1");
-  Mat preA = ws_mat(h, 2 * B, A, "actor.policy.out");
+  Mat h1A = ws_mat(h, RA, H, "actor.policy.h1");
+  Mat preA = ws_mat(h, RA, A, "actor.policy.out");
+  // cfg.boltzmann: the DiagGaussianActor stack on [next_obs | z ; obs | z]; raw = [mu | raw log-std]
+  Mat pol_x = actor_in_oz; pol_x.rows = bz ? 2 * B : 0;
+  BAct pol = b_alloc(h, pol_x, Mat(), "actor.policy", H, 2 * A);
+  Mat bz_x = ws_mat(h, bz ? B : 0, A, "bz_x"), bz_sd = ws_mat(h, bz ? B : 0, A, "bz_std"), bz_t = ws_mat(h, bz ? B : 0, A, "bz_t");
   Mat h1Ft1 = ws_mat(h, B, H, "Ft.F1.h1"), h1Ft2 = ws_mat(h, B, H, "Ft.F2.h1");
   Mat h1F1 = ws_mat(h, B, H, "F.F1.h1"), h1F2 = ws_mat(h, B, H, "F.F2.h1");
   Mat h1Fa1 = ws_mat(h, B, H, "F2.F1.h1"), h1Fa2 = ws_mat(h, B, H, "F2.F2.h1");
@@ -710,12 +723,14 @@ static int build_plan(fb_handle* h) {
   Mat dFa = ws_mat(h, B, 2 * ldZ, "dFa");
   Mat dFa1 = dFa.cs(0, Z), dFa2 = dFa.cs(ldZ, Z);
   Mat dhoa = ws_mat(h, B, Fe, "dhoa");
-  Mat dpreA = ws_mat(h, B, A, "dpreA");
-  Mat dh1A = ws_mat(h, B, H, "dh1A");
-  Mat dhA = ws_mat(h, B, Hc, "dhA");
-  Mat dy_o = ws_mat(h, deep ? 0 : B, H, "dy_o"), dy_aoz = ws_mat(h, B, H, "dy_aoz");
+  Mat dpreA = ws_mat(h, RA1, A, "dpreA");
+  Mat dh1A = ws_mat(h, RA1, H, "dh1A");
+  Mat dhA = ws_mat(h, RA1, Hc, "dhA");
+  Mat dy_o = ws_mat(h, (deep || bz) ? 0 : B, H, "dy_o"), dy_aoz = ws_mat(h, RA1, H, "dy_aoz");
+  const int RB = bz ? B : 0;   // cfg.boltzmann: gradients of the DiagGaussianActor stack
+  Mat bz_da = ws_mat(h, RB, A, "bz_da"), bz_dpre = ws_mat(h, RB, 2 * A, "bz_dpre"), bz_dh2 = ws_mat(h, RB, H, "bz_dh2"), bz_dy = ws_mat(h, RB, H, "bz_dy");
   Mat dtF, dtA;   // add_trunk: gradients w.r.t. the trunk outputs
-  if (trunk) { dtF = ws_mat(h, B, H, "dtF"); dtA = ws_mat(h, B, H, "dtA"); }
+  if (trunk) { dtF = ws_mat(h, B, H, "dtF"); dtA = ws_mat(h, RA1, H, "dtA"); }
 
   Builder b{h, d_arena};
   DevScalars* sc = h->d_sc;
@@ -770,7 +785,7 @@ static int build_plan(fb_handle* h) {
   {
     StageParams sp; memset(&sp, 0, sizeof(sp));
     sp.L = L; sp.batch = B; sp.use_goal = use_goal ? 1 : 0;
-    sp.actor_in_o = deep ? nullptr : actor_in_o.p; sp.ldO = actor_in_o.ld; sp.act_col = act_col; sp.actor_in_oz = actor_in_oz.p; sp.ldOZ = actor_in_oz.ld;
+    sp.actor_in_o = (deep || bz) ? nullptr : actor_in_o.p; sp.ldO = actor_in_o.ld; sp.act_col = act_col; sp.actor_in_oz = actor_in_oz.p; sp.ldOZ = actor_in_oz.ld;
     sp.in_oa = in_oa.p; sp.in_noa = in_noa.p; sp.in_oa2 = in_oa2.p; sp.ldOA = in_oa.ld;
     sp.goal_next = goal_next.p; sp.mix_in = mix_in.p; sp.ldG = goal_next.ld;
     sp.blk = bl.p; sp.blk_pitch = bl.ld; sp.disc_col = disc_col;
@@ -827,12 +842,15 @@ static int build_plan(fb_handle* h) {
   }
   b.gemm({lin_fwd(eAoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eAoz.pre, 0), lin_fwd(eFoz.x, pF.w(E_OZ + 0), pF.v(E_OZ + 1), eFoz.pre, 0),
           lin_fwd(eFtoz.x, pFt.w(E_OZ + 0), pFt.v(E_OZ + 1), eFtoz.pre, 0),
-          lin_fwd(eFoa_late.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eFoa_late.pre, 0)});
-  b.ln_fwd({embed_ln(eAoz, pA.sub(A_OZ)), embed_ln(eFoz, pF.sub(E_OZ)), embed_ln(eFtoz, pFt.sub(E_OZ)), embed_ln(eFoa_late, pF.sub(E_OA))});
+          lin_fwd(eFoa_late.x, pF.w(E_OA + 0), pF.v(E_OA + 1), eFoa_late.pre, 0),
+          lin_fwd(pol.x, pA.w(0), pA.v(1), pol.pre, 0)});   // (cfg.boltzmann: policy.0)
+  b.ln_fwd({embed_ln(eAoz, pA.sub(A_OZ)), embed_ln(eFoz, pF.sub(E_OZ)), embed_ln(eFtoz, pFt.sub(E_OZ)), embed_ln(eFoa_late, pF.sub(E_OA)),
+            b_ln(pol, pA)});
   b.gemm({lin_fwd(eAo.y, pA.w(A_O + 4), pA.v(A_O + 5), eAo.out, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(eAoz.y, pA.w(A_OZ + 4), pA.v(A_OZ + 5), eAoz.out, GF_RELU | GF_RELU_LAZY_OK),
           lin_fwd(eFoa.y, pF.w(E_OA + 4), pF.v(E_OA + 5), eFoa.out, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(eFoz.y, pF.w(E_OZ + 4), pF.v(E_OZ + 5), eFoz.out, GF_RELU | GF_RELU_LAZY_OK),
           lin_fwd(eFtoz.y, pFt.w(E_OZ + 4), pFt.v(E_OZ + 5), eFtoz.out, GF_RELU | GF_RELU_LAZY_OK),
-          lin_fwd(bO.y, pB.w(4), pB.v(5), bO.h2, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(bT.y, pBt.w(4), pBt.v(5), bT.h2, GF_RELU | GF_RELU_LAZY_OK)});
+          lin_fwd(bO.y, pB.w(4), pB.v(5), bO.h2, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(bT.y, pBt.w(4), pBt.v(5), bT.h2, GF_RELU | GF_RELU_LAZY_OK),
+          lin_fwd(pol.y, pA.w(4), pA.v(5), pol.h2, GF_RELU | GF_RELU_LAZY_OK)});   // (cfg.boltzmann: policy.3)
   if (trunk) {
     b.gemm({lin_fwd(hA, pA.w(A_TR + 0), pA.v(A_TR + 1), trA, GF_RELU | GF_RELU_LAZY_OK), lin_fwd(hF, pF.w(F_TR + 0), pF.v(F_TR + 1), trF, GF_RELU | GF_RELU_LAZY_OK),
             lin_fwd(bO.h2, pB.w(6), pB.v(7), bO.raw, 0), lin_fwd(bT.h2, pBt.w(6), pBt.v(7), bT.raw, 0)});
@@ -841,9 +859,21 @@ static int build_plan(fb_handle* h) {
     b.gemm({lin_fwd(hA, pA.w(A_POL + 0), pA.v(A_POL + 1), h1A, GF_RELU | GF_RELU_LAZY_OK),
             lin_fwd(bO.h2, pB.w(6), pB.v(7), bO.raw, 0), lin_fwd(bT.h2, pBt.w(6), pBt.v(7), bT.raw, 0)});
   }
-  b.gemm({lin_fwd(h1A, pA.w(A_POL + 2), pA.v(A_POL + 3), preA, 0)});
+  b.gemm({lin_fwd(h1A, pA.w(A_POL + 2), pA.v(A_POL + 3), preA, 0), lin_fwd(pol.h2, pA.w(6), pA.v(7), pol.raw, 0)});   // (policy.5)
   b.l2_fwd({b_l2(bO, Z, nz), b_l2(bT, Z, nz)});
-  {
+  if (bz) {   // SquashedNormal samples of both sides + log pi of the obs side (fb_ddpg.py:304-306,391-396)
+    ActorOutBzParams ap; memset(&ap, 0, sizeof(ap));
+    ap.batch = B; ap.A = A; ap.act_col = act_col; ap.pre = pol.raw.p; ap.ldP = pol.raw.ld;
+    ap.noise_fb = h->noise_fb.p; ap.noise_actor = h->noise_actor.p; ap.ldN = h->noise_fb.ld;
+    ap.in_noa = in_noa.p; ap.in_oa2 = in_oa2.p; ap.ldOA = in_noa.ld; ap.next_action = next_action.p; ap.action_new = action_new.p;
+    ap.ldA = next_action.ld; ap.xs = bz_x.p; ap.sds = bz_sd.p; ap.ts = bz_t.p;
+    ap.log_std_min = c.log_std_min; ap.log_std_max = c.log_std_max; ap.acc = acc;
+    b.push([ap](cudaStream_t s) {
+      fb_launch_pdl(k_actor_out_bz, dim3(fb_ceil_div(2 * ap.batch * ap.A, 256)), dim3(256), 0, s, ap);
+      return cudaGetLastError();
+    });
+    h->ops[b.phase].back().wait_stage = 1;   // the zeroed accumulators
+  } else {
     ActorOutParams ap; memset(&ap, 0, sizeof(ap));
     ap.batch = B; ap.A = A; ap.O = O; ap.act_col = act_col; ap.pre = preA.p; ap.mu = mu.p; ap.ldA = preA.ld;
     ap.noise_fb = h->noise_fb.p; ap.noise_actor = h->noise_actor.p; ap.ldN = h->noise_fb.ld;
@@ -1167,7 +1197,32 @@ static int build_plan(fb_handle* h) {
   }
   b.gemm({lin_dx(dhoa, pF.w(E_OA + 4), dy_oa, 0, nullptr)});
   b.ln_bwd({embed_ln_bwd(eF2oa, pF.sub(E_OA), dy_oa, 0, false)});
-  {
+  if (bz) {
+    // d(-mean Q)/d action, then the SquashedNormal / log-std chain rule and the entropy term (k_boltz_bwd), then the
+    // DiagGaussianActor stack backwards: policy.5 -> ReLU -> policy.3 -> LayerNorm + tanh -> policy.0
+    b.gemm({lin_dx(dy_oa, pF.w(E_OA + 0).cs(act_col, A), bz_da, 0, nullptr)});
+    BoltzBwdParams bp; memset(&bp, 0, sizeof(bp));
+    bp.batch = B; bp.A = A; bp.da = bz_da.p; bp.ldda = bz_da.ld; bp.xs = bz_x.p; bp.sds = bz_sd.p; bp.ts = bz_t.p; bp.ldA = bz_x.ld;
+    bp.noise_actor = h->noise_actor.p; bp.ldN = h->noise_actor.ld; bp.dpre = bz_dpre.p; bp.ldP = bz_dpre.ld;
+    bp.temp_over_n = c.temp / (float)n; bp.half_range = 0.5f * (c.log_std_max - c.log_std_min);
+    b.push([bp](cudaStream_t s) {
+      fb_launch_pdl(k_boltz_bwd, dim3(fb_ceil_div(bp.batch * bp.A, 256)), dim3(256), 0, s, bp);
+      return cudaGetLastError();
+    });
+    Mat h2_o = pol.h2.rs(B, B), y_o = pol.y.rs(B, B), x_o = pol.x.rs(B, B);
+    b.colsum({mk_colsum(bz_dpre, pA.gv(7))});
+    b.gemm({lin_dw(bz_dpre, h2_o, pA.gw(6)), lin_dx(bz_dpre, pA.w(6), bz_dh2, GF_MASK_RELU, &h2_o)});
+    b.colsum({mk_colsum(bz_dh2, pA.gv(5))});
+    b.gemm({lin_dw(bz_dh2, y_o, pA.gw(4)), lin_dx(bz_dh2, pA.w(4), bz_dy, 0, nullptr)});
+    {
+      LnBwdDesc d; memset(&d, 0, sizeof(d));
+      d.dy = bz_dy.p; d.dx = bz_dy.p; d.y = y_o.p; d.x = pol.pre.p + (size_t)B * pol.pre.ld; d.gamma = pA.v(2); d.mean = pol.mean + B; d.rstd = pol.rstd + B;
+      d.dgamma = pA.gv(2); d.dbeta = pA.gv(3); d.rows = B; d.D = bz_dy.cols; d.ld = pol.y.ld; d.ld_dy = bz_dy.ld;
+      b.ln_bwd({d});
+    }
+    b.colsum({mk_colsum(bz_dy, pA.gv(1))});
+    b.gemm({lin_dw(bz_dy, x_o, pA.gw(0))});
+  } else {
     Mat muB = mu.rs(B, B);
     b.gemm({lin_dx(dy_oa, pF.w(E_OA + 0).cs(act_col, A), dpreA, GF_MASK_TANH, &muB)});
   }
@@ -1252,6 +1307,7 @@ static int build_plan(fb_handle* h) {
     MetricFinalParams mp; memset(&mp, 0, sizeof(mp));
     mp.acc = acc; mp.linf_bits = linf; mp.out = h->d_metrics; mp.n_local = B; mp.n_global = n; mp.Z = Z; mp.ortho_coef = c.ortho_coef;
     mp.q_loss_coef = c.q_loss ? c.q_loss_coef : 0.f;
+    mp.temp = bz ? c.temp : 0.f;
     b.push([mp](cudaStream_t s) { fb_launch_pdl(k_metric_final, dim3(1), dim3(32), 0, s, mp); return cudaGetLastError(); });
   }
 
@@ -1262,19 +1318,25 @@ static int build_plan(fb_handle* h) {
   {
     const int R = FB_INFER_ROWS;
     Mat io = ws_mat(h, R, O, "infer_obs"), iz = ws_mat(h, R, Z, "infer_z"), ioz = ws_mat(h, R, O + Z, "infer_oz");
-    Mat ihA = ws_mat(h, R, Hc, "infer_hA"), ih1 = ws_mat(h, R, H, "infer_h1"), ipre = ws_mat(h, R, A, "infer_pre");
-    Mat imu = ws_mat(h, R, A, "infer_mu");
+    const int RI = bz ? 0 : R;   // the default actor's inference activations (cfg.boltzmann: none; infer_mu then holds [mu | std])
+    Mat ihA = ws_mat(h, RI, Hc, "infer_hA"), ih1 = ws_mat(h, RI, H, "infer_h1"), ipre = ws_mat(h, RI, A, "infer_pre");
+    Mat imu = ws_mat(h, R, bz ? 2 * A : A, "infer_mu");
     Mat io_embed = io;
-    if (deep) io_embed.rows = 0;   // no obs-only embed
-    EmbedAct eo = embed_alloc(h, io_embed, ihA.cs(0, Fe), H, "infer.obs_net"), eoz = embed_alloc(h, ioz, ihA.cs(oz0, Fe), H, "infer.obs_z_net");
+    if (deep || bz) io_embed.rows = 0;   // no obs-only embed
+    Mat ioz_embed = ioz; ioz_embed.rows = RI;
+    EmbedAct eo = embed_alloc(h, io_embed, ihA.cs(0, Fe), H, "infer.obs_net"), eoz = embed_alloc(h, ioz_embed, ihA.cs(oz0, Fe), H, "infer.obs_z_net");
+    Mat ipol_x = ioz; ipol_x.rows = bz ? R : 0;
+    BAct ipol = b_alloc(h, ipol_x, Mat(), "infer.policy", H, 2 * A);
     b.set_phase(FB_PHASE_INFER_ACTOR);
     b.push([=](cudaStream_t s) {
       fb_launch_pdl(k_infer_concat, dim3(R), dim3(128), 0, s, io.p, io.ld, iz.p, iz.ld, ioz.p, ioz.ld, R, O, Z);
       return cudaGetLastError();
     });
-    b.gemm({lin_fwd(eo.x, pA.w(A_O + 0), pA.v(A_O + 1), eo.pre, 0), lin_fwd(eoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eoz.pre, 0)});
-    b.ln_fwd({embed_ln(eo, pA.sub(A_O)), embed_ln(eoz, pA.sub(A_OZ))});
-    b.gemm({lin_fwd(eo.y, pA.w(A_O + 4), pA.v(A_O + 5), eo.out, GF_RELU), lin_fwd(eoz.y, pA.w(A_OZ + 4), pA.v(A_OZ + 5), eoz.out, GF_RELU)});
+    b.gemm({lin_fwd(eo.x, pA.w(A_O + 0), pA.v(A_O + 1), eo.pre, 0), lin_fwd(eoz.x, pA.w(A_OZ + 0), pA.v(A_OZ + 1), eoz.pre, 0),
+            lin_fwd(ipol.x, pA.w(0), pA.v(1), ipol.pre, 0)});
+    b.ln_fwd({embed_ln(eo, pA.sub(A_O)), embed_ln(eoz, pA.sub(A_OZ)), b_ln(ipol, pA)});
+    b.gemm({lin_fwd(eo.y, pA.w(A_O + 4), pA.v(A_O + 5), eo.out, GF_RELU), lin_fwd(eoz.y, pA.w(A_OZ + 4), pA.v(A_OZ + 5), eoz.out, GF_RELU),
+            lin_fwd(ipol.y, pA.w(4), pA.v(5), ipol.h2, GF_RELU)});
     if (trunk) {
       Mat ihT = ws_mat(h, R, H, "infer_trunk");
       b.gemm({lin_fwd(ihA, pA.w(A_TR + 0), pA.v(A_TR + 1), ihT, GF_RELU)});
@@ -1282,7 +1344,14 @@ static int build_plan(fb_handle* h) {
     } else {
       b.gemm({lin_fwd(ihA, pA.w(A_POL + 0), pA.v(A_POL + 1), ih1, GF_RELU)});
     }
-    b.gemm({lin_fwd(ih1, pA.w(A_POL + 2), pA.v(A_POL + 3), ipre, 0)});
+    b.gemm({lin_fwd(ih1, pA.w(A_POL + 2), pA.v(A_POL + 3), ipre, 0), lin_fwd(ipol.h2, pA.w(6), pA.v(7), ipol.raw, 0)});
+    if (bz) {
+      const float lo = c.log_std_min, hi = c.log_std_max;
+      b.push([=](cudaStream_t s) {
+        fb_launch_pdl(k_infer_gauss, dim3(fb_ceil_div(R * A, 128)), dim3(128), 0, s, ipol.raw.p, imu.p, ipol.raw.ld, R, A, lo, hi);
+        return cudaGetLastError();
+      });
+    } else
     b.push([=](cudaStream_t s) {
       fb_launch_pdl(k_infer_tanh, dim3(fb_ceil_div(R * A, 128)), dim3(128), 0, s, ipre.p, imu.p, ipre.ld, R, A);
       return cudaGetLastError();
@@ -1421,6 +1490,7 @@ int fb_create(const fb_config* cfg, fb_handle** out) {
   if (!cfg->use_goal && cfg->goal_dim != cfg->obs_dim) return FB_E_ARG;
   if (!(cfg->future_ratio >= 0.f && cfg->future_ratio <= 1.f) || !(cfg->mix_ratio >= 0.f && cfg->mix_ratio <= 1.f)) return FB_E_ARG;
   if (cfg->q_loss && cfg->z_dim > FB_QLOSS_MAX_Z) return FB_E_UNSUPPORTED;
+  if (cfg->boltzmann && !(cfg->log_std_max > cfg->log_std_min)) return FB_E_ARG;
   if (cfg->rand_weight && cfg->z_dim > FB_MIXW_MAX_Z) return FB_E_UNSUPPORTED;
   fb_handle* h = new fb_handle();
   h->cfg = *cfg;

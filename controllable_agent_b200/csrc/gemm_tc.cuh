@@ -12,22 +12,28 @@
 // tiny / shared-output products.  Operands TMA cannot address directly (mn-major, or a leading dimension that is not a
 // multiple of 4 floats) are first staged into an aligned K-major copy by k_transpose_grouped.
 //
-// Where the lo parts come from (profiles/r1c_gemm_tc_breakdown.txt: building them in shared memory costs as much
-// shared-memory bandwidth as the MMAs themselves): every operand that passes through a staging launch anyway (weights,
-// transposed operands) gets its lo plane written there, ONCE per step, and TMA loads it next to the raw tile
-// (TC_A_PRE / TC_B_PRE); only operands that come straight from the producing kernel (activations, K-major) are split
-// inside this kernel by the builder warps.
+// Where the operand bytes go (profiles/r1c_gemm_tc_breakdown.txt, profiles/r2_gemm_tc_ts.txt): with both operands in shared memory
+// ("SS" form) a k-block of a 128 x 128 tile moves ~176 KB through the SM's 128 B/clk shared-memory port (TMA writes, the lo
+// builders' reads and writes, 6 operand reads of the three MMA chains) against an MMA floor of 768 clk = 98 KB, and every lo plane
+// that TMA loads next to its raw tile also costs L2 -> SM bandwidth (~42 B/clk/SM chip-wide).  The A operand therefore takes the
+// "TS" form: the builder warps read the landed raw A tile ONCE from shared memory, split it in registers (hi = the tf32 bits the
+// tensor core would read, lo = x - hi, exact) and write both halves into TENSOR MEMORY (tcgen05.st), where the MMAs read them at
+// no shared-memory cost; A needs no lo plane in shared memory or in HBM at all.  B stays in shared memory: its lo plane is
+// pre-split once per step by the staging launch for operands that pass through one anyway (weights, transposed operands:
+// TC_B_PRE) and built next to the raw tile by the builder warps otherwise.
 //
 // Persistent CTAs (one per SM), each looping over 128 x BN output tiles of the whole group, 6 warps:
-//   warp 0      TMA producer      raw fp32 tiles (BK = 32 floats = one 128-byte swizzle atom) (+ pre-split lo tiles) -> smem
+//   warp 0      TMA producer      raw fp32 tiles (BK = 32 floats = one 128-byte swizzle atom) (+ the pre-split B lo tile) -> smem
 //                                 ring; runs ahead into the next tile while the current one drains
-//   warp 1      MMA issuer        one thread: 3 chains x 4 tcgen05.mma (M128 x BN x K8, kind::tf32) per stage, accumulators in TMEM
-//                                 (the tensor core's fp32 accumulate truncates, a bias that grows with the number of sequential
-//                                 accumulations: the hi.hi chain is therefore spread round-robin over three accumulators and the
-//                                 two small correction chains go to a fourth; the epilogue adds the four in IEEE fp32)
-//   warps 2..5  lo-part builders  lo = x - trunc_tf32(x) for the landed tiles that were not pre-split,
+//   warp 1      MMA issuer        one thread: 3 chains x 4 tcgen05.mma (M128 x BN x K8, kind::tf32, A from TMEM) per stage,
+//                                 accumulators in TMEM (the tensor core's fp32 accumulate truncates, a bias that grows with the
+//                                 number of sequential accumulations: the hi.hi chain alternates between two accumulators and the
+//                                 two small correction chains go to a third; the epilogue adds the three in IEEE fp32)
+//   warps 2..5  operand builders  thread = one row of the A tile: swizzled 128-byte row -> registers -> (ReLU) -> hi / lo ->
+//                                 TMEM slot of the k-block; B lo = x - trunc_tf32(x) in shared memory when not pre-split;
 //                                 then the epilogue: tcgen05.ld, transpose through a padded smem scratch so that every global
 //                                 access (C, ReLU / tanh' mask) is a coalesced 128-bit one, bias / ReLU / masks
+// TMEM (512 columns): [0, 3 bn) accumulators hi0 | hi1 | corrections, [3 ring_bn, ...) A slots of 64 columns (hi 32 | lo 32).
 #pragma once
 #include <cuda.h>
 
@@ -47,6 +53,8 @@
                                        // (3 stages at BN = 128 and TC_BK = 32)
 #define TC_SMEM_BYTES (TC_RING_BYTES + 1024)
 #define TC_EPI_LD 36                   // padded row of the epilogue scratch (floats): conflict-free 128-bit writes and reads
+#define TC_A_SLOT_COLS 64              // TS form: TMEM columns of one k-block of A (hi: 32 columns, lo: 32 columns; lane = tile row)
+#define TC_MAX_ASLOTS 4                // A slots in flight (2 at BN = 128: 3 x 128 accumulator columns + 2 x 64 = 512)
 
 #define TC_A_PRE (1 << 8)    // mapAlo / mapA2lo address a pre-split lo plane of A
 #define TC_B_PRE (1 << 9)    // same for B
@@ -118,6 +126,28 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same with the A operand in tensor memory ("TS" form): a_tmem = TMEM address (lane 0, first column) of a 128 x 8 tf32 block,
+// row r of the tile in lane r, one 32-bit column per k
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive columns of this thread's TMEM lane (warp w of the CTA owns lanes 32 (w % 4) .. +31)
+__device__ __forceinline__ void tc_tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
 __device__ __forceinline__ void tc_mma_commit(uint64_t* bar) {
@@ -210,6 +240,7 @@ struct TcShared {
   uint64_t bar_raw[TC_MAX_STAGES];    // TMA -> lo builders
   uint64_t bar_ready[TC_MAX_STAGES];  // lo builders -> MMA issuer
   uint64_t bar_empty[TC_MAX_STAGES];  // MMA issuer (tcgen05.commit) -> TMA producer
+  uint64_t bar_afree[TC_MAX_ASLOTS];  // TS form: MMA issuer (tcgen05.commit) -> builders: the k-block's TMEM A slot may be rewritten
   uint64_t bar_accum;                 // all MMAs of a tile retired -> epilogue
   uint64_t bar_tmem_empty;            // epilogue has read the accumulators -> MMA issuer (next tile)
   uint32_t tmem_base;
@@ -224,6 +255,7 @@ __device__ __forceinline__ void tc_init_barriers(TcShared* sh, bool reinit) {
       asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_ready[s])) : "memory");
       asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_empty[s])) : "memory");
     }
+    for (int j = 0; j < TC_MAX_ASLOTS; ++j) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_afree[j])) : "memory");
     asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_accum)) : "memory");
     asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_tmem_empty)) : "memory");
   }
@@ -232,6 +264,7 @@ __device__ __forceinline__ void tc_init_barriers(TcShared* sh, bool reinit) {
     tc_mbar_init(&sh->bar_ready[s], 128);
     tc_mbar_init(&sh->bar_empty[s], 1);
   }
+  for (int j = 0; j < TC_MAX_ASLOTS; ++j) tc_mbar_init(&sh->bar_afree[j], 1);
   tc_mbar_init(&sh->bar_accum, 1);
   tc_mbar_init(&sh->bar_tmem_empty, 128);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -48,11 +48,12 @@ __global__ void k_tick(DevScalars* s, int which, float beta1, float beta2) {
   fb_pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (which == 2) { s->rng_counter += 1ull; return; }
-  long long t = (which == 0 ? s->step_fb : s->step_actor) + 1;
-  const double bc1 = 1.0 - pow((double)beta1, (double)t);
-  const double bc2 = 1.0 - pow((double)beta2, (double)t);
-  if (which == 0) { s->step_fb = t; s->bc1_fb = (float)bc1; s->bc2s_fb = (float)sqrt(bc2); }
-  else { s->step_actor = t; s->bc1_actor = (float)bc1; s->bc2s_actor = (float)sqrt(bc2); }
+  // runs BEHIND the k_adam launch of step t: publishes t and the bias corrections of step t + 1 (what the next k_adam reads)
+  const long long t = (which == 0 ? s->step_fb : s->step_actor) + 1;
+  float n1, n2;
+  adam_bias_corrections(beta1, beta2, t + 1, &n1, &n2);
+  if (which == 0) { s->step_fb = t; s->bc1_fb = n1; s->bc2s_fb = n2; }
+  else { s->step_actor = t; s->bc1_actor = n1; s->bc2s_actor = n2; }
 }
 
 // ---- replay gather ----------------------------------------------------------------------------------
@@ -866,6 +867,83 @@ __global__ void __launch_bounds__(256) k_actor_out(ActorOutParams P, const DevSc
   actor_out_body(P, sc, blockIdx.x);
 }
 
+// ---- cfg.boltzmann: DiagGaussianActor + SquashedNormal (fb_modules.py:129-151, utils.py:188-233) -----------------
+// pre [2B, ldP] = policy output [mu | raw log-std]; std = exp(lo + (hi - lo) (tanh(raw) + 1) / 2).
+// rows [0,B): next_obs side, next_action = tanh(mu + std * noise_fb) (dist.sample(), no clipping, fb_ddpg.py:304-306)
+// rows [B,2B): obs side, x = mu + std * noise_actor (rsample), action = tanh(x); log pi(a) = N(x; mu, std) - 2 (log 2 - x - softplus(-2x))
+// summed into acc[ACC_LOGPROB]; x, std and tanh(raw) are kept for the backward.
+struct ActorOutBzParams {
+  int batch, A, act_col;
+  const float* pre; int ldP;
+  const float* noise_fb; const float* noise_actor; int ldN;
+  float* in_noa; float* in_oa2; int ldOA;
+  float* next_action; float* action_new; int ldA;
+  float* xs; float* sds; float* ts;   // [B, ldA]: pre-tanh sample, std, tanh(raw log-std) of the obs side
+  float log_std_min, log_std_max;
+  double* acc;
+};
+
+__device__ __forceinline__ float fb_softplus(float v) { return v > 20.f ? v : log1pf(expf(v)); }   // F.softplus (beta 1, threshold 20)
+
+__global__ void __launch_bounds__(256) k_actor_out_bz(ActorOutBzParams P) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = 2 * P.batch * P.A;
+  double lp = 0.0;
+  if (idx < total) {
+    const int r = idx / P.A, a = idx - r * P.A;
+    const float mu = P.pre[(size_t)r * P.ldP + a];
+    const float t = tanhf(P.pre[(size_t)r * P.ldP + P.A + a]);
+    const float ls = P.log_std_min + 0.5f * (P.log_std_max - P.log_std_min) * (t + 1.f);
+    const float sd = expf(ls);
+    const bool fb_side = r < P.batch;
+    const int rb = fb_side ? r : r - P.batch;
+    const float nz = fb_side ? P.noise_fb[(size_t)rb * P.ldN + a] : P.noise_actor[(size_t)rb * P.ldN + a];
+    const float x = mu + sd * nz;
+    const float act = tanhf(x);
+    if (fb_side) {
+      P.in_noa[(size_t)rb * P.ldOA + P.act_col + a] = act;
+      P.next_action[(size_t)rb * P.ldA + a] = act;
+    } else {
+      P.in_oa2[(size_t)rb * P.ldOA + P.act_col + a] = act;
+      P.action_new[(size_t)rb * P.ldA + a] = act;
+      P.xs[(size_t)rb * P.ldA + a] = x; P.sds[(size_t)rb * P.ldA + a] = sd; P.ts[(size_t)rb * P.ldA + a] = t;
+      const float d = x - mu;
+      const float base = -(d * d) / (2.f * sd * sd) - ls - 0.91893853320467274178f;
+      lp = (double)(base - 2.f * (0.69314718055994530942f - x - fb_softplus(-2.f * x)));
+    }
+  }
+  lp = warp_sum_d(lp);
+  if ((threadIdx.x & 31) == 0 && lp != 0.0) atomicAdd(P.acc + ACC_LOGPROB, lp);
+}
+
+// gradient of mean_s(temp * log pi(a_s) - Q_s) w.r.t. the policy output [mu | raw], from da = d(-mean Q)/d action (the dX product
+// through forward_net): with x = mu + std eps, a = tanh(x):  g_x = da (1 - a^2) + (temp / n) 2 a;  d/dmu = g_x;
+// d/dstd = g_x eps - (temp / n) / std;  d/draw = d/dstd * std * (hi - lo) / 2 * (1 - tanh(raw)^2)
+struct BoltzBwdParams {
+  int batch, A;
+  const float* da; int ldda;
+  const float* xs; const float* sds; const float* ts; int ldA;
+  const float* noise_actor; int ldN;
+  float* dpre; int ldP;
+  float temp_over_n, half_range;
+};
+__global__ void __launch_bounds__(256) k_boltz_bwd(BoltzBwdParams P) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P.batch * P.A) return;
+  const int r = idx / P.A, a = idx - r * P.A;
+  const float x = P.xs[(size_t)r * P.ldA + a], sd = P.sds[(size_t)r * P.ldA + a], t = P.ts[(size_t)r * P.ldA + a];
+  const float eps = P.noise_actor[(size_t)r * P.ldN + a];
+  const float act = tanhf(x);
+  const float gx = P.da[(size_t)r * P.ldda + a] * (1.f - act * act) + P.temp_over_n * 2.f * act;
+  const float dsd = gx * eps - P.temp_over_n / sd;
+  P.dpre[(size_t)r * P.ldP + a] = gx;
+  P.dpre[(size_t)r * P.ldP + P.A + a] = dsd * sd * P.half_range * (1.f - t * t);
+}
+
 // ---- batch x batch loss, elementwise stage ----------------------------------------------------------
 // In:  M1,M2 = F_k . B^T; T1,T2 = tF_k . tB^T; Cov = B . B^T for a block of `nr` rows (global row index
 //      row0 + i) by `nc` columns (global).  Out (in place): G1,G2 = dL/dM_k, Gc = ortho_coef * dL_orth/dCov
@@ -1274,6 +1352,7 @@ struct MetricFinalParams {
   const double* acc; const unsigned int* linf_bits; float* out;
   int n_local, n_global, Z; float ortho_coef;
   float q_loss_coef;   // 0 when cfg.q_loss is off (the accumulator then stays 0)
+  float temp;          // cfg.boltzmann: actor_loss = mean(temp * log pi - Q) (fb_ddpg.py:406); 0 otherwise
 };
 // indices must match FB_M_* in fb_b200.h
 __global__ void k_metric_final(MetricFinalParams P) {
@@ -1303,7 +1382,7 @@ __global__ void k_metric_final(MetricFinalParams P) {
   o[11] = (float)orth_off;
   o[12] = __uint_as_float(*P.linf_bits);
   o[13] = (float)(sqrt(P.acc[ACC_ORTH_SQ]) / sqrt((double)P.Z));
-  o[14] = (float)(-P.acc[ACC_Q] / n);
+  o[14] = (float)(((double)P.temp * P.acc[ACC_LOGPROB] - P.acc[ACC_Q]) / n);
   o[15] = (float)(P.acc[ACC_Q] / n);
   o[16] = (float)(P.acc[ACC_LOGPROB] / n);
   o[17] = (float)q_loss;
@@ -1327,6 +1406,17 @@ __global__ void k_infer_tanh(const float* __restrict__ pre, float* __restrict__ 
   fb_pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows * A) { const int r = i / A, a = i - r * A; mu[(size_t)r * ld + a] = tanhf(pre[(size_t)r * ld + a]); }
+}
+// cfg.boltzmann: out [rows, 2A] = [mu (pre-tanh mean) | std] of the SquashedNormal (fb_modules.py:141-151)
+__global__ void k_infer_gauss(const float* __restrict__ pre, float* __restrict__ out, int ld, int rows, int A, float lo, float hi) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * A) {
+    const int r = i / A, a = i - r * A;
+    out[(size_t)r * ld + a] = pre[(size_t)r * ld + a];
+    out[(size_t)r * ld + A + a] = expf(lo + 0.5f * (hi - lo) * (tanhf(pre[(size_t)r * ld + A + a]) + 1.f));
+  }
 }
 // zsum[c] += sum_r reward[r] * b[r, c]   (fb_ddpg.py:215: z = reward^T . B): block = 32 columns, 8 warps stride the rows
 __global__ void __launch_bounds__(256) k_infer_weighted_colsum(const float* __restrict__ b, int ldb, const float* __restrict__ reward, int ldr,

@@ -29,7 +29,7 @@
 struct Mat {
   float* p = nullptr;
   int rows = 0, cols = 0, ld = 0;
-  Mat rs(int r0, int n) const { Mat m = *this; m.p = p + (size_t)r0 * ld; m.rows = n; return m; }
+  Mat rs(int r0, int n) const { Mat m = *this; m.p = p + (size_t)r0 * ld; m.rows = rows ? n : 0; return m; }   // a row block of an absent (zero-row) matrix is absent
   Mat cs(int c0, int n) const { Mat m = *this; m.p = p + c0; m.cols = n; return m; }
 };
 
@@ -181,6 +181,11 @@ static void build_layout(fb_handle* h) {
   f.add("B.0.weight", Hb, G); f.add("B.0.bias", Hb, 0); f.add("B.1.weight", Hb, 0); f.add("B.1.bias", Hb, 0);
   f.add("B.3.weight", Hb, Hb); f.add("B.3.bias", Hb, 0); f.add("B.5.weight", Z, Hb); f.add("B.5.bias", Z, 0);
   SegmentLayout& a = h->seg_actor;
+  if (c.boltzmann) {   // DiagGaussianActor: policy = mlp(obs + z, hidden, "ntanh", hidden, "relu", 2 * action)  (fb_modules.py:137)
+    a.add("policy.0.weight", H, O + Z); a.add("policy.0.bias", H, 0); a.add("policy.1.weight", H, 0); a.add("policy.1.bias", H, 0);
+    a.add("policy.3.weight", H, H); a.add("policy.3.bias", H, 0); a.add("policy.5.weight", 2 * A, H); a.add("policy.5.bias", 2 * A, 0);
+    return;
+  }
   if (deep) {
     add_embed(a, "trunk", O + Z, H, H);
     a.add("trunk.5.weight", H, H); a.add("trunk.5.bias", H, 0);
@@ -195,10 +200,12 @@ static void build_layout(fb_handle* h) {
 // a parameter set: values + (optional) gradient buffer sharing one layout
 struct PSet {
   const SegmentLayout* L; int first; float* val; float* grad;
-  Mat w(int i) const { const TensorInfo& t = L->t[first + i]; Mat m; m.p = val + t.off; m.rows = t.rows; m.cols = t.cols ? t.cols : 1; m.ld = m.cols; return m; }
-  float* v(int i) const { return val + L->t[first + i].off; }
-  Mat gw(int i) const { Mat m = w(i); m.p = grad + L->t[first + i].off; return m; }
-  float* gv(int i) const { return grad ? grad + L->t[first + i].off : nullptr; }
+  // an index past the layout (a network variant without that tensor: the plan builds its launches with zero rows) reads as empty
+  bool has(int i) const { return first + i >= 0 && first + i < (int)L->t.size(); }
+  Mat w(int i) const { Mat m; if (!has(i)) return m; const TensorInfo& t = L->t[first + i]; m.p = val + t.off; m.rows = t.rows; m.cols = t.cols ? t.cols : 1; m.ld = m.cols; return m; }
+  float* v(int i) const { return has(i) ? val + L->t[first + i].off : nullptr; }
+  Mat gw(int i) const { Mat m = w(i); if (has(i)) m.p = grad + L->t[first + i].off; return m; }
+  float* gv(int i) const { return (grad && has(i)) ? grad + L->t[first + i].off : nullptr; }
   PSet sub(int d) const { PSet p = *this; p.first += d; return p; }
 };
 

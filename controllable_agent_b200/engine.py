@@ -39,6 +39,9 @@ class EngineConfig:
     preprocess: bool = True     # False: one deep trunk instead of the two embeds (fb_modules.py:102-104,175-177)
     add_trunk: bool = False     # trunk Linear + ReLU between the embeds and the heads (fb_modules.py:96-100,169-173)
     rand_weight: bool = False   # mixed z rows = random weighted sums of B rows (fb_ddpg.py:475-482)
+    boltzmann: bool = False     # DiagGaussianActor + SquashedNormal actions, actor loss mean(temp * log pi - Q) (fb_modules.py:129-151)
+    temp: float = 1.0
+    log_std_bounds: tp.Tuple[float, float] = (-5.0, 2.0)
     norm_z: bool = True         # sqrt(z_dim)-sphere projection of B's output / of z (fb_modules.py:227-229, fb_ddpg.py:228,483)
     beta1: float = 0.9
     beta2: float = 0.999
@@ -89,7 +92,8 @@ class FBStepEngine:
                         rng_device=int(cfg.rng_device), contract_mode=int(cfg.contract_mode), mlp_mode=int(cfg.mlp_mode), ortho_coef=cfg.ortho_coef, mix_ratio=cfg.mix_ratio,
                         future_ratio=cfg.future_ratio,
                         beta1=cfg.beta1, beta2=cfg.beta2, adam_eps=cfg.adam_eps, seed=cfg.seed,
-                        q_loss=int(cfg.q_loss), q_loss_coef=cfg.q_loss_coef, no_norm_z=int(not cfg.norm_z), rand_weight=int(cfg.rand_weight), add_trunk=int(cfg.add_trunk), no_preprocess=int(not cfg.preprocess))
+                        q_loss=int(cfg.q_loss), q_loss_coef=cfg.q_loss_coef, no_norm_z=int(not cfg.norm_z), rand_weight=int(cfg.rand_weight), add_trunk=int(cfg.add_trunk), no_preprocess=int(not cfg.preprocess),
+                        boltzmann=int(cfg.boltzmann), temp=float(cfg.temp), log_std_min=float(cfg.log_std_bounds[0]), log_std_max=float(cfg.log_std_bounds[1]))
         h = C.c_void_p()
         L.check(self.lib.fb_create(C.byref(c), C.byref(h)), "fb_create")
         self.h = h
@@ -474,14 +478,15 @@ class FBStepEngine:
             views = {n: self.view(n) for n in names}
             R = L.INFER_ROWS
             pin = lambda *shape: torch.zeros(shape, dtype=torch.float32).pin_memory()  # noqa: E731
-            self._infer = {"v": views, "obs": pin(R, c.obs_dim), "z": pin(R, c.z_dim), "mu": pin(R, c.action_dim),
+            self._infer = {"v": views, "obs": pin(R, c.obs_dim), "z": pin(R, c.z_dim), "mu": pin(R, c.action_dim * (2 if c.boltzmann else 1)),
                            "goal": pin(R, c.goal_dim), "b": pin(R, c.z_dim), "zsum": pin(1, c.z_dim)}
         return self._infer
 
     @_on_device
     def infer_actor(self, obs: np.ndarray, z: np.ndarray, graph: bool = True) -> np.ndarray:
         """mu = tanh(policy(obs, z)) of the online actor for up to 8 rows (fb_modules.py:110-122): one small upload, the
-        FB_PHASE_INFER_ACTOR graph, one small read-back."""
+        FB_PHASE_INFER_ACTOR graph, one small read-back.  cfg.boltzmann: the rows are [mu (pre-tanh) | std] of the
+        DiagGaussianActor (fb_modules.py:141-151)."""
         io = self._infer_io()
         n = obs.shape[0]
         assert n <= L.INFER_ROWS and z.shape[0] == n

@@ -68,6 +68,8 @@ def soft_update_params(net: nn.Module, target_net: nn.Module, tau: float) -> Non
     """target <- tau * net + (1 - tau) * target, parameter by parameter in registration order (host-side twin of the lerp fused into
     k_adam; utils.py:66-69).  The agent's step does this on the device; this exists for callers that poke the modules."""
     src, dst = _param_pairs(net, target_net)
+    if not src:   # parameter-free modules (the states-only agent's nn.Identity encoder)
+        return
     with torch.no_grad():   # two rounded products and one rounded sum per element (no fused multiply-add): bit-identical to the reference
         mixed = torch._foreach_add(torch._foreach_mul(src, tau), torch._foreach_mul(dst, 1.0 - tau))
         torch._foreach_copy_(dst, mixed)
@@ -76,6 +78,8 @@ def soft_update_params(net: nn.Module, target_net: nn.Module, tau: float) -> Non
 def hard_update_params(net: nn.Module, target_net: nn.Module) -> None:
     """target <- net (utils.py:72-74), what init_from uses to adopt another agent's networks."""
     src, dst = _param_pairs(net, target_net)
+    if not src:
+        return
     with torch.no_grad():
         torch._foreach_copy_(dst, src)
 
@@ -110,6 +114,34 @@ class TruncatedNormal:
     def log_prob(self, value: torch.Tensor) -> torch.Tensor:
         var = self.scale ** 2
         return -((value - self.loc) ** 2) / (2 * var) - torch.log(self.scale) - 0.5 * math.log(2 * math.pi)
+
+
+class SquashedNormal:
+    """tanh of a Normal(loc, scale) draw: the action distribution of the DiagGaussianActor (cfg.boltzmann; the contract of
+    utils.SquashedNormal, utils.py:188-233).  `mean` is tanh(loc) (the transform applied to the base mean, not the true mean);
+    log_prob(y) = Normal.log_prob(x) - log|d tanh / dx|(x) with x = atanh(y) and the Jacobian in its softplus form, which is what
+    k_actor_out_bz evaluates from the pre-tanh sample it keeps."""
+
+    def __init__(self, loc: torch.Tensor, scale: torch.Tensor) -> None:
+        self.loc, self.scale = loc, scale
+
+    @property
+    def mean(self) -> torch.Tensor:
+        return torch.tanh(self.loc)
+
+    def rsample(self, sample_shape: torch.Size = torch.Size()) -> torch.Tensor:
+        shape = torch.Size(sample_shape) + self.loc.shape
+        return torch.tanh(self.loc + self.scale * _standard_normal(shape, dtype=self.loc.dtype, device=self.loc.device))
+
+    def sample(self, sample_shape: torch.Size = torch.Size()) -> torch.Tensor:
+        shape = torch.Size(sample_shape) + self.loc.shape
+        with torch.no_grad():   # Normal.sample: torch.normal on the expanded parameters
+            return torch.tanh(torch.normal(self.loc.expand(shape), self.scale.expand(shape)))
+
+    def log_prob(self, value: torch.Tensor) -> torch.Tensor:
+        x = 0.5 * (torch.log1p(value) - torch.log1p(-value))
+        base = -((x - self.loc) ** 2) / (2 * self.scale ** 2) - torch.log(self.scale) - 0.5 * math.log(2 * math.pi)
+        return base - 2.0 * (math.log(2.0) - x - F.softplus(-2.0 * x))
 
 
 _ACTIVATIONS: tp.Dict[str, tp.Callable[[int], tp.List[nn.Module]]] = {
@@ -167,6 +199,23 @@ class Actor(nn.Module):
             h = torch.cat([obs, z], dim=-1)
         mu = torch.tanh(self.policy(self.trunk(h)))
         return TruncatedNormal(mu, torch.ones_like(mu) * std)
+
+
+class DiagGaussianActor(nn.Module):
+    """fb_modules.DiagGaussianActor (cfg.boltzmann, fb_modules.py:129-151): one stack on [obs | z] whose output is
+    [mu | raw log-std]; the log-std is squashed into log_std_bounds with a tanh."""
+
+    def __init__(self, obs_dim: int, z_dim: int, action_dim: int, hidden_dim: int, log_std_bounds: tp.Tuple[float, float]) -> None:
+        super().__init__()
+        self.obs_dim, self.z_dim, self.action_dim, self.log_std_bounds = obs_dim, z_dim, action_dim, tuple(log_std_bounds)
+        self.policy = mlp(obs_dim + z_dim, hidden_dim, "ntanh", hidden_dim, "relu", 2 * action_dim)
+        self.apply(weight_init)
+
+    def forward(self, obs: torch.Tensor, z: torch.Tensor) -> SquashedNormal:
+        assert z.shape[-1] == self.z_dim
+        mu, raw = self.policy(torch.cat([obs, z], dim=-1)).chunk(2, dim=-1)
+        lo, hi = self.log_std_bounds
+        return SquashedNormal(mu, torch.exp(lo + 0.5 * (hi - lo) * (torch.tanh(raw) + 1.0)))
 
 
 class ForwardMap(nn.Module):

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 3
+#define FB_ABI_VERSION 4
 
 enum {
   FB_OK = 0,
@@ -133,6 +133,11 @@ typedef struct fb_config {
   int32_t no_preprocess;       /* cfg.preprocess == False (fb_modules.py:102-104,175-177): Actor / ForwardMap are one deep trunk
                                   mlp(obs+z[+action], hidden, "ntanh", hidden, "irelu", hidden, "irelu") in front of the heads instead
                                   of the two embeds; tensors "trunk.{0,1,3,5}.*" then the heads */
+  int32_t boltzmann;           /* cfg.boltzmann (fb_modules.py:129-151, fb_ddpg.py:118-120,304-306,391-393,406): the actor is the
+                                  DiagGaussianActor mlp(obs+z, hidden, "ntanh", hidden, "relu", 2 action) (tensors "policy.{0,1,3,5}.*"),
+                                  actions are tanh of a Normal(mu, std) sample and the actor loss is mean(temp * log pi - Q) */
+  float temp;                  /* cfg.temp */
+  float log_std_min, log_std_max; /* cfg.log_std_bounds */
 } fb_config;
 
 /* per-step scalars (host values; copied to the device by fb_set_step_scalars) */

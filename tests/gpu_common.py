@@ -19,6 +19,12 @@ def rel(a, b):
 
 
 def dims_from_params(fwd, bwd, actor):
+    if "policy.5.weight" in actor:   # cfg.boltzmann: the DiagGaussianActor has no embeds; the obs width comes from policy.0 ([obs | z] columns)
+        hidden, oa = fwd["obs_action_net.0.weight"].shape
+        z_dim = fwd["F1.2.weight"].shape[0]
+        obs_dim = actor["policy.0.weight"].shape[1] - z_dim
+        return O.Dims(obs_dim=obs_dim, action_dim=oa - obs_dim, z_dim=z_dim, goal_dim=bwd["B.0.weight"].shape[1], hidden_dim=hidden,
+                      feature_dim=fwd["obs_action_net.3.weight"].shape[0], backward_hidden_dim=bwd["B.0.weight"].shape[0])
     if "obs_action_net.0.weight" not in fwd:   # preprocess = False: the feature width does not exist; taken from make_golden.CASES["small"]
         hidden, oza = fwd["trunk.0.weight"].shape
         oz = actor["trunk.0.weight"].shape[1]
@@ -37,13 +43,14 @@ def golden_params(g, prefix):
 
 
 def make_engine(d, batch, use_goal=False, rng_device=False, mix_ratio=0.5, ortho_coef=1.0, seed=0, global_batch=None,
-                row_offset=0, contract_mode=0, mlp_mode=0, q_loss_coef=None, norm_z=True, add_trunk=False, fused=False, preprocess=True):
+                row_offset=0, contract_mode=0, mlp_mode=0, q_loss_coef=None, norm_z=True, add_trunk=False, fused=False, preprocess=True, boltzmann=False, temp=1.0):
     from controllable_agent_b200.engine import EngineConfig, FBStepEngine
     cfg = EngineConfig(batch=batch, obs_dim=d.obs_dim, action_dim=d.action_dim, z_dim=d.z_dim, goal_dim=d.goal_dim,
                        hidden_dim=d.hidden_dim, feature_dim=d.feature_dim, backward_hidden_dim=d.backward_hidden_dim,
                        use_goal=use_goal, rng_device=rng_device, ortho_coef=ortho_coef, mix_ratio=mix_ratio, seed=seed,
                        global_batch=global_batch, row_offset=row_offset, contract_mode=contract_mode, mlp_mode=mlp_mode,
-                       q_loss=q_loss_coef is not None, q_loss_coef=q_loss_coef if q_loss_coef is not None else 0.01, norm_z=norm_z, add_trunk=add_trunk, fused=fused, preprocess=preprocess)
+                       q_loss=q_loss_coef is not None, q_loss_coef=q_loss_coef if q_loss_coef is not None else 0.01, norm_z=norm_z, add_trunk=add_trunk, fused=fused, preprocess=preprocess,
+                       boltzmann=boltzmann, temp=temp)
     return FBStepEngine(cfg, "cuda")
 
 

@@ -38,7 +38,8 @@ def _create(L, lib, d, batch=64, **kw):
                     feature_dim=d.feature_dim, backward_hidden_dim=d.backward_hidden_dim, use_goal=kw.get("use_goal", 0), rng_device=0, contract_mode=kw.get("contract_mode", 0), mlp_mode=kw.get("mlp_mode", 0),
                     ortho_coef=1.0, mix_ratio=kw.get("mix_ratio", 0.5), beta1=0.9, beta2=0.999, adam_eps=1e-8, seed=0,
                     future_ratio=kw.get("future_ratio", 0.0), q_loss=kw.get("q_loss", 0), q_loss_coef=0.01, no_norm_z=kw.get("no_norm_z", 0),
-                    rand_weight=kw.get("rand_weight", 0), add_trunk=kw.get("add_trunk", 0), no_preprocess=kw.get("no_preprocess", 0))
+                    rand_weight=kw.get("rand_weight", 0), add_trunk=kw.get("add_trunk", 0), no_preprocess=kw.get("no_preprocess", 0),
+                    boltzmann=kw.get("boltzmann", 0), temp=0.7, log_std_min=kw.get("log_std_min", -5.0), log_std_max=2.0)
     h = C.c_void_p()
     return lib.fb_create(C.byref(c), C.byref(h)), h
 
@@ -94,9 +95,15 @@ def test_add_trunk_layout_and_optional_branch_plans(d):
     for net, spec in ((L.NET_FORWARD, O.forward_map_spec(d, preprocess=False)), (L.NET_ACTOR, O.actor_spec(d, preprocess=False))):
         assert [(n, s) for n, _, s in _table(lib, h, net)] == [(n, tuple(s)) for n, s in spec]
     lib.fb_destroy(h)
-    for bits in range(64):
+    rc, h = _create(L, lib, d, boltzmann=1)   # boltzmann = True: the DiagGaussianActor's one stack (fb_modules.py:129-139); forward_net unchanged
+    assert rc == 0
+    for net, spec in ((L.NET_FORWARD, O.forward_map_spec(d)), (L.NET_ACTOR, O.boltzmann_actor_spec(d))):
+        assert [(n, s) for n, _, s in _table(lib, h, net)] == [(n, tuple(s)) for n, s in spec]
+    lib.fb_destroy(h)
+    assert _create(L, lib, d, boltzmann=1, log_std_min=3.0)[0] == -1   # empty log-std interval
+    for bits in range(128):
         kw = dict(q_loss=bits & 1, no_norm_z=(bits >> 1) & 1, rand_weight=(bits >> 2) & 1, add_trunk=(bits >> 3) & 1,
-                  future_ratio=0.3 if bits & 16 else 0.0, no_preprocess=(bits >> 5) & 1)
+                  future_ratio=0.3 if bits & 16 else 0.0, no_preprocess=(bits >> 5) & 1, boltzmann=(bits >> 6) & 1)
         for mlp_mode in (0, 1):
             rc, h = _create(L, lib, d, mlp_mode=mlp_mode, contract_mode=mlp_mode, **kw)
             assert rc == 0, (kw, mlp_mode)
@@ -201,6 +208,23 @@ def test_module_mirrors_match_oracle_forward():
         o1, o2 = O.forward_map(pf, obs, z, act)
         assert torch.allclose(f1, o1, atol=1e-6) and torch.allclose(f2, o2, atol=1e-6)
         assert torch.allclose(bwd(obs), O.backward_map(pb, obs, 10), atol=1e-6)
+        # cfg.boltzmann: DiagGaussianActor + SquashedNormal (fb_modules.py:129-151, utils.py:188-233)
+        ga = M.DiagGaussianActor(11, 10, 3, 48, (-5.0, 2.0))
+        assert [n for n, _ in ga.named_parameters()] == [n for n, _ in O.boltzmann_actor_spec(d)]
+        dist = ga(obs, z)
+        mu, std = O.diag_gaussian_actor(dict(ga.named_parameters()), obs, z)
+        assert torch.allclose(dist.loc, mu, atol=1e-6) and torch.allclose(dist.scale, std, atol=1e-6) and torch.allclose(dist.mean, torch.tanh(mu))
+        x = mu + std * torch.randn(5, 3)
+        assert torch.allclose(dist.log_prob(torch.tanh(x)), O.squashed_normal_log_prob(x, mu, std), atol=2e-4)
+        torch.manual_seed(3); a1 = dist.sample()
+        torch.manual_seed(3); a2 = dist.rsample()
+        assert torch.allclose(a1, a2, atol=1e-6) and a1.abs().max() <= 1.0   # torch.normal and loc + scale * randn consume the CPU generator alike
+    M.hard_update_params(torch.nn.Identity(), torch.nn.Identity())      # the states-only agent's encoder: nothing to copy, no error
+    M.soft_update_params(torch.nn.Identity(), torch.nn.Identity(), 0.01)
+    tgt = M.BackwardMap(11, 10, 30)
+    M.soft_update_params(bwd, tgt, 0.25)
+    M.hard_update_params(bwd, tgt)
+    assert all(torch.equal(a, b) for a, b in zip(bwd.parameters(), tgt.parameters()))
     assert M.schedule("linear(1,0.2,200)", 100) == pytest.approx(0.6)
     assert M.schedule("step_linear(1,0.5,100,0.1,100)", 150) == pytest.approx(0.3)
     # same construction order + same init calls => same parameters as the reference for the same torch seed

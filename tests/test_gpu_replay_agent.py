@@ -118,7 +118,7 @@ def test_pack_episode_kernel_matches_host_packing():
     assert torch.equal(rows[3], buf._rows[3])
 
 
-SMALL_CASES = ("small", "future", "qloss", "nonorm", "randw", "randw_nonorm", "trunk", "nopre")   # fixtures generated from make_golden.CASES["small"]
+SMALL_CASES = ("small", "future", "qloss", "nonorm", "randw", "randw_nonorm", "trunk", "nopre", "boltz")   # fixtures generated from make_golden.CASES["small"]
 
 
 def _agent_for(g, case, **kw):
@@ -140,7 +140,7 @@ def _agent_for(g, case, **kw):
     return agent
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm", "trunk", "nopre"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm", "trunk", "nopre", "boltz"])
 @pytest.mark.parametrize("foreign_replay", [False, True, "fused"])   # "fused": HBM replay, the MLP stacks as fused persistent kernels
 def test_agent_update_walks_reference_trajectory(case, foreign_replay):
     fuse = foreign_replay == "fused"
@@ -159,6 +159,8 @@ def test_agent_update_walks_reference_trajectory(case, foreign_replay):
         extra = dict(add_trunk=True)
     if case == "nopre":   # preprocess = False (fb_modules.py:102-104,175-177)
         extra = dict(preprocess=False)
+    if case == "boltz":   # boltzmann = True (fb_modules.py:129-151), temp as make_golden generated it
+        extra = dict(boltzmann=True, temp=float(g["cfg/temp"]) if "cfg/temp" in g else 0.7)
     agent = _agent_for(g, case, rng_mode="reference", fuse_stacks=fuse, **extra)
     agent.draw_device = "cpu"
     eps = [subtree(g, f"ep{i}") for i in range(4)]
@@ -453,8 +455,7 @@ def test_unsupported_branches_raise():
     from controllable_agent_b200 import FBDDPGAgent
     base = dict(obs_type="states", obs_shape=(24,), action_shape=(6,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,
                 use_tb=False, use_wandb=False, use_hiplog=False)
-    for kw in (dict(boltzmann=True),
-               dict(obs_type="pixels"), dict(debug=True)):
+    for kw in (dict(obs_type="pixels"), dict(debug=True)):
         with pytest.raises(NotImplementedError):
             FBDDPGAgent(**{**base, **kw})
     with pytest.raises(RuntimeError):

@@ -101,7 +101,8 @@ def _run_update_case(g, d, use_goal, graph, mlp_mode=0, fused=False):
                       q_loss_coef=float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None,
                       norm_z=bool(g["cfg/norm_z"]) if "cfg/norm_z" in g else True,
                       add_trunk="param0/actor/trunk.0.weight" in g and "param0/actor/obs_net.0.weight" in g,
-                      preprocess="param0/actor/obs_net.0.weight" in g)
+                      preprocess="param0/actor/obs_net.0.weight" in g or ("cfg/boltzmann" in g and bool(g["cfg/boltzmann"])),
+                      boltzmann="cfg/boltzmann" in g and bool(g["cfg/boltzmann"]), temp=float(g["cfg/temp"]) if "cfg/temp" in g else 1.0)
     load_params(eng, fwd=subtree(g, "param0/forward_net"), bwd=subtree(g, "param0/backward_net"),
                 actor=subtree(g, "param0/actor"), fwd_tgt=subtree(g, "param0/forward_target_net"),
                 bwd_tgt=subtree(g, "param0/backward_target_net"))
@@ -115,7 +116,8 @@ def _run_update_case(g, d, use_goal, graph, mlp_mode=0, fused=False):
 
 
 # qloss*: cfg.q_loss (fb_ddpg.py:330-341); nonorm*: cfg.norm_z = False (fb_modules.py:227-229); trunk*: cfg.add_trunk (fb_modules.py:96-100)
-@pytest.mark.parametrize("case", ["small", "goal", "wide", "qloss", "qloss_goal", "nonorm", "nonorm_goal", "trunk", "trunk_goal", "nopre"])
+# boltz: cfg.boltzmann (DiagGaussianActor + SquashedNormal, fb_modules.py:129-151, fb_ddpg.py:304-306,391-393,406)
+@pytest.mark.parametrize("case", ["small", "goal", "wide", "qloss", "qloss_goal", "nonorm", "nonorm_goal", "trunk", "trunk_goal", "nopre", "boltz"])
 # (graph, mlp_mode, fused): eager / CUDA-graph launches of the per-layer plan, the fp32 SIMT plan, and the fused stack kernels
 # (k_fused_stack: the same plan as stages of one persistent kernel per segment), eager and under a graph
 @pytest.mark.parametrize("graph,mlp_mode,fused", [(False, 0, False), (True, 0, False), (True, 1, False), (False, 0, True), (True, 0, True)])
@@ -126,10 +128,12 @@ def test_update_matches_reference_golden(case, graph, mlp_mode, fused):
     use_goal = case.endswith("goal")
     q_coef = float(g["cfg/q_loss_coef"]) if "cfg/q_loss_coef" in g else None
     norm_z = bool(g["cfg/norm_z"]) if "cfg/norm_z" in g else True
+    boltz = "cfg/boltzmann" in g and bool(g["cfg/boltzmann"])
+    temp = float(g["cfg/temp"]) if "cfg/temp" in g else 1.0
     eng, t, L = _run_update_case(g, d, use_goal, graph, mlp_mode, fused)
     if fused:   # the segment really is one launch: MIX + FB_FWD up to the contraction, then the loss GEMMs + FB_BWD
         assert eng.launch_count(L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD) < eng.launch_count(
-            L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD, fused=False) // 4
+            L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD, fused=False) // 3
 
     # ---- update_fb up to the gradients (fb_ddpg.py:303-383) ----
     eng.run(L.PHASE_MIX | L.PHASE_FB_FWD | L.PHASE_FB_LOSS | L.PHASE_FB_BWD | L.PHASE_METRICS, graph=graph)
@@ -137,7 +141,8 @@ def test_update_matches_reference_golden(case, graph, mlp_mode, fused):
     assert rel(eng.view("z"), t["z"]) < 1e-6
     ora = O.fb_loss_and_grads(fwd, bwd, golden_params(g, "param0/forward_target_net"), golden_params(g, "param0/backward_target_net"),
                               actor, t["obs"], t["action"], t["discount"], t["next_obs"], t["next_goal"], t["z"], t["noise_fb"],
-                              float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]), float(g["cfg/ortho_coef"]), d.z_dim, q_coef, norm_z)
+                              float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]), float(g["cfg/ortho_coef"]), d.z_dim, q_coef, norm_z,
+                              boltzmann=boltz)
     for name in ("next_action", "tF1", "tF2", "tB", "F1", "F2", "B", "dF1", "dF2", "dB"):
         assert rel(eng.view(name), ora[name]) < REL_TOL, name
     m = eng.read_metrics()
@@ -176,9 +181,11 @@ def test_update_matches_reference_golden(case, graph, mlp_mode, fused):
     fwd1 = read_tensors(eng, L.NET_FORWARD, "param")
     eng.run(L.PHASE_ACTOR_FWD | L.PHASE_ACTOR_BWD | L.PHASE_METRICS, graph=graph)
     torch.cuda.synchronize()
-    ora_a = O.actor_loss_and_grads(actor, fwd1, t["obs"], t["z"], t["noise_actor"], float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]))
+    ora_a = O.actor_loss_and_grads(actor, fwd1, t["obs"], t["z"], t["noise_actor"], float(g["cfg/stddev"]), float(g["cfg/stddev_clip"]),
+                                   boltzmann=boltz, temp=temp)
     assert rel(eng.view("action_new"), ora_a["action"]) < REL_TOL
-    assert rel(eng.view("mu"), ora_a["mu"]) < REL_TOL
+    if not boltz:   # (the DiagGaussianActor has no tanh'd mean buffer: its [mu | raw log-std] output is checked through action / log pi)
+        assert rel(eng.view("mu"), ora_a["mu"]) < REL_TOL
     m = eng.read_metrics()
     assert m["actor_loss"] == pytest.approx(float(ora_a["actor_loss"]), rel=REL_TOL, abs=1e-5)
     assert m["q"] == pytest.approx(float(ora_a["q"]), rel=REL_TOL, abs=1e-5)
