@@ -241,21 +241,30 @@ def run_reference(a: argparse.Namespace) -> None:
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
 class HostReplay:
-    """A host-memory replay with the reference's sample() contract (in_memory_replay_buffer.py:139-190: numpy index draws and
-    fancy-index gathers returning numpy arrays), for the end-to-end leg: every step's batch is gathered on the host and
-    crosses PCIe inside the timed region."""
+    """A replay buffer in HOST memory with the attribute layout and the sample() contract of the reference's
+    in_memory_replay_buffer.ReplayBuffer (:66-88, :139-190: numpy index draws and fancy-index gathers returning numpy arrays), filled
+    the way ReplayBuffer.load() fills `_storage`.  For the end-to-end leg: every step's batch is gathered on the host and crosses PCIe
+    inside the timed region — by the library's own host gather when the agent recognises the layout (the default), or by this
+    object's Python sample() (agent.native_host_sampling = False)."""
 
-    def __init__(self, storage: dict, gamma: float) -> None:
-        self.s = storage
-        self._discount, self._future = gamma, 1.0
+    def __init__(self, storage: dict, gamma: float, episode_len: int) -> None:
+        import numpy as np
+        self._storage = storage
+        E = storage["observation"].shape[0]
+        self._max_episodes, self._discount, self._future = E, gamma, 1.0
+        self._episodes_length = np.full(E, episode_len, np.int32)
+        self._is_fixed_episode_length, self._episodes_selection_probability = True, None
+        self._idx, self._full = 0, True
+
+    def __len__(self) -> int:
+        return self._max_episodes
 
     def sample(self, batch_size: int):
         import numpy as np
         from controllable_agent_b200 import EpisodeBatch
-        s = self.s
-        E, R = s["observation"].shape[:2]
-        ep = np.random.randint(0, E, size=batch_size)
-        t = np.random.randint(0, R - 1, size=batch_size) + 1
+        s = self._storage
+        ep = np.random.randint(0, len(self), size=batch_size)
+        t = np.random.randint(0, self._episodes_length[ep]) + 1
         goal = s["goal"][ep, t - 1] if "goal" in s else None
         next_goal = s["goal"][ep, t] if "goal" in s else None
         return EpisodeBatch(obs=s["observation"][ep, t - 1], action=s["action"][ep, t], reward=s["reward"][ep, t],
@@ -429,11 +438,12 @@ def run_ours(a: argparse.Namespace) -> None:
     # ---- end-to-end leg: host buffers, H2D of the step's inputs and D2H of its metrics inside the timed region -------
     e2e_steps = a.e2e_steps or min(a.steps, 100)
     hstore = host_storage(a, E, seed=7 + rank, physics_dim=18 if (rank == 0 and world == 1 and not a.no_cpu_baseline) else 0)
-    host = HostReplay(hstore, 0.98)
+    host = HostReplay(hstore, 0.98, a.episode_len)
     agent.cfg.use_tb = True          # metrics on: one D2H read of the step's losses per step
 
-    def e2e_leg(prefetch: bool) -> float:
+    def e2e_leg(prefetch: bool, native: bool = True) -> float:
         agent.cfg.prefetch_host_batch = prefetch
+        agent.native_host_sampling = native
         agent._prefetched = None
         for i in range(3):
             agent.update(host, i)
@@ -453,6 +463,8 @@ def run_ours(a: argparse.Namespace) -> None:
 
     e2e_ms = e2e_leg(False)            # default flags: sample -> upload -> step -> read, strictly in sequence (the reference's own order)
     e2e_ms_prefetch = e2e_leg(True)    # opt-in cfg.prefetch_host_batch: the next batch is sampled and uploaded while the step runs
+    e2e_ms_python = e2e_leg(False, native=False)   # the replay object's own Python sample() (what any foreign replay object gets)
+    agent.native_host_sampling = True
     m = e2e_leg.metrics
     agent.cfg.prefetch_host_batch = False
     Bl = a.batch // world
@@ -545,9 +557,12 @@ def run_ours(a: argparse.Namespace) -> None:
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": {"value": e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "steps": e2e_steps, "value_with_prefetch": e2e_steps / (e2e_ms_prefetch * 1e-3),
-                        "path": "FBDDPGAgent.update(host_replay, step) at default flags: host numpy sample() -> pinned packed rows -> one H2D -> "
-                                "step graph (device RNG) -> metrics block D2H, strictly in sequence every step; value_with_prefetch: the opt-in "
-                                "agent.prefetch_host_batch=True (next step's sample + upload issued while this step runs on the GPU)"},
+                        "value_python_sample": e2e_steps / (e2e_ms_python * 1e-3),
+                        "path": "FBDDPGAgent.update(host_replay, step) at default flags, host_replay = a buffer in host memory with the reference "
+                                "ReplayBuffer's layout: numpy index draws (the reference's order) -> fb_host_gather_rows into pinned packed rows -> "
+                                "one H2D -> step graph (device RNG) -> metrics block D2H, strictly in sequence every step; value_with_prefetch: "
+                                "the opt-in agent.prefetch_host_batch=True (next step's sample + upload issued while this step runs on the GPU); "
+                                "value_python_sample: the replay object's own numpy sample() instead of the library's host gather"},
                 "gpu_launches": launches_per_step * a.steps, "launches_per_step": launches_per_step,
                 "roofline": roofline, "cpu_baseline": cpu, "reference_cuda_eager": cuda_eager, "parity_check": parity,
                 "breakdown_ms": {k: round(v["ms"], 4) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1]["ms"])},

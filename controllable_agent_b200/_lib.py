@@ -19,7 +19,7 @@ CONTRACT_TCGEN05, CONTRACT_SIMT = 0, 1
 MLP_TCGEN05, MLP_SIMT = 0, 1
 HEADER = os.path.join(ROOT, "include", "fb_b200.h")
 
-FB_ABI_VERSION = 4
+FB_ABI_VERSION = 5
 FB_OK = 0
 
 NET_FORWARD, NET_BACKWARD, NET_ACTOR = 0, 1, 2
@@ -60,7 +60,13 @@ class fb_config(C.Structure):
                 ("seed", C.c_uint64), ("q_loss", C.c_int32), ("q_loss_coef", C.c_float),
                 ("no_norm_z", C.c_int32), ("rand_weight", C.c_int32),
                 ("add_trunk", C.c_int32), ("no_preprocess", C.c_int32),
-                ("boltzmann", C.c_int32), ("temp", C.c_float), ("log_std_min", C.c_float), ("log_std_max", C.c_float)]
+                ("boltzmann", C.c_int32), ("temp", C.c_float), ("log_std_min", C.c_float), ("log_std_max", C.c_float),
+                ("fused_stacks", C.c_int32)]
+
+
+class fb_host_storage(C.Structure):
+    _fields_ = [("observation", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p), ("discount", C.c_void_p), ("goal", C.c_void_p),
+                ("rows_per_episode", C.c_int32), ("obs_dim", C.c_int32), ("action_dim", C.c_int32), ("goal_dim", C.c_int32)]
 
 
 class fb_step_scalars(C.Structure):
@@ -100,6 +106,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
     "fb_set_indices": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fb_set_batch": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fb_upload_batch": (_i, [_vp, _vp, _i, _vp]),
+    "fb_host_gather_rows": (_i, [C.POINTER(fb_host_storage), _vp, _vp, _vp, _i, _f, _vp, _i]),
     "fb_nccl_unique_id": (_i, [C.c_char_p, _vp]),
     "fb_nccl_init": (_i, [_vp, C.c_char_p, _vp, _i, _i]),
     "fb_p2p_create": (_i, [_vp, _i, _i, _vp, C.POINTER(fb_buffers)]),

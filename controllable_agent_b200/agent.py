@@ -26,7 +26,7 @@ from . import _lib as L
 from . import modules as M
 from .dist_utils import reduce_metrics, shard_layout
 from .engine import EngineConfig, FBStepEngine
-from .replay import ReplayBuffer
+from .replay import HostStorageView, ReplayBuffer, draw_sample_indices
 
 logger = logging.getLogger(__name__)
 MetaDict = tp.Mapping[str, np.ndarray]
@@ -240,6 +240,8 @@ class FBDDPGAgent:
         self.actor_success: tp.List[float] = []
         self._replay_key: tp.Any = None
         self._prefetched: tp.Any = None   # id of the host replay whose next batch is already in the packed block
+        self.native_host_sampling = True   # reference-layout host replays are sampled by the library (False: always their own sample())
+        self._host_views: tp.Dict[int, HostStorageView] = {}
         self.last_update_launches = 0
         # where rng_mode="reference" makes its torch draws (z, action noise): the agent's device, like the reference run
         # with device=cuda; tests point it at "cpu" to replay the CPU-generated golden trajectories
@@ -587,6 +589,13 @@ class FBDDPGAgent:
         return metrics
 
     def _upload_host_batch(self, replay_loader: tp.Any, B: int) -> None:
+        # a host buffer in the reference's own layout: its index draws here (same numpy stream as its sample()), its row gathers in
+        # the library, straight into the pinned block; any other object: its own sample() contract
+        view = self._host_view(replay_loader)
+        if view is not None:
+            ep_idx, step_idx, future_idx = draw_sample_indices(replay_loader, B)
+            self.engine.upload_host_rows(view, ep_idx, step_idx, future_idx, float(replay_loader._discount))
+            return
         batch = replay_loader.sample(B)
         use_goal = self.cfg.goal_space is not None
         if use_goal:
@@ -595,6 +604,16 @@ class FBDDPGAgent:
         self.engine.upload_batch(batch.obs, batch.action, batch.discount, batch.next_obs, batch.goal if use_goal else None,
                                  batch.next_goal if use_goal else None, batch.future_obs if fut else None,
                                  batch.future_goal if (fut and use_goal) else None)
+
+    def _host_view(self, replay_loader: tp.Any) -> tp.Optional[HostStorageView]:
+        if not self.native_host_sampling:
+            return None
+        cached = self._host_views.get(id(replay_loader))
+        if cached is not None and cached.replay is replay_loader and cached.still_valid():
+            return cached
+        view = HostStorageView.adopt(replay_loader)
+        self._host_views = {id(replay_loader): view} if view is not None else {}
+        return view
 
     def _reduce_metrics(self, m: tp.Dict[str, float]) -> tp.Dict[str, float]:
         """Per-rank metric blocks -> global values: loss-type entries are partial sums over the rank's rows, the

@@ -93,6 +93,52 @@ static int make_tc_launch(const std::vector<TcGemmDesc>& v, int total, int ring_
 }
 
 // ------------------------------------------------------------------------------------------------
+// the tensor-core GEMM kernels: CTA pairs (cta_group::2, clusters of two) or single CTAs, operands in shared memory unless
+// FB_TC_TS=1 asks for the A-through-tensor-memory variant (A/B measurements, profiles/r2_gemm_tc_ts.txt)
+typedef void (*TcKernel)(const TcGemmDesc*, const TcLaunch);
+static TcKernel tc_kernel(int ncta) {
+  static const bool ts = getenv("FB_TC_TS") != nullptr;
+  if (ncta == 2) return ts ? (TcKernel)k_gemm_tc<true, 2> : (TcKernel)k_gemm_tc<false, 2>;
+  return ts ? (TcKernel)k_gemm_tc<true, 1> : (TcKernel)k_gemm_tc<false, 1>;
+}
+static cudaError_t tc_set_smem_attr() {
+  for (int ncta = 1; ncta <= 2; ++ncta) {
+    cudaError_t e = cudaFuncSetAttribute(tc_kernel(ncta), cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+// CTA pairs that can be resident at once (persistent grid of a pair launch): 74 on a full B200 unless a GPC holds an odd number of SMs
+static int tc_max_pairs() {
+  static int pairs = 0;
+  if (pairs) return pairs;
+  int n = 0;
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(FB_SM_COUNT); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (tc_set_smem_attr() == cudaSuccess && cudaOccupancyMaxActiveClusters(&n, tc_kernel(2), &cfg) == cudaSuccess && n > 0) pairs = std::min(n, FB_SM_COUNT / 2);
+  else { cudaGetLastError(); return FB_SM_COUNT / 2; }   // (no device yet: the sizing pass of fb_create)
+  return pairs;
+}
+// one grouped launch: `work` items (tiles x k-ranges; pair tiles when ncta == 2) on a persistent grid
+static cudaError_t tc_launch(const TcGemmDesc* dd, const TcLaunch& hdr, int work, int ncta, cudaStream_t s, bool pdl) {
+  cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+  const int units = ncta == 2 ? tc_max_pairs() : FB_SM_COUNT;
+  cfg.gridDim = dim3((work < units ? work : units) * ncta); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {   // programmatic dependent launch: the kernel's prologue may overlap the tail of the launch before it (fb_pdl_wait inside)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na;
+  }
+  if (ncta == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, tc_kernel(ncta), dd, hdr);
+}
+
 // op recorders
 // ------------------------------------------------------------------------------------------------
 struct Builder {
@@ -234,11 +280,17 @@ struct Builder {
     // Tile width and split-K of the launch, from a cost model of the persistent kernel (profiles/r1c_gemm_tc_breakdown.txt):
     // a k-block of a 128 x bn tile costs f(bn) (shared-memory bound: 1.0 / 0.8 / 0.72 for bn = 128 / 64 / 32, in units of
     // ~0.7 us), a work item additionally its epilogue; CTA c of min(items, 148) executes items c, c + grid, ... so the
-    // launch lasts as long as its most loaded CTA.  Candidates: bn in {128, 64, 32} x split-K in {1, 2, 3, 4, 6, 8} (only
+    // launch lasts as long as its most loaded CTA (items dealt in rounds of alternating direction, see tc_snake).  Candidates: bn in {128, 64, 32} x split-K in {1, 2, 3, 4, 6, 8} (only
     // problems whose epilogue is linear may be split; their partial sums are added into a zeroed C).  Problems are ordered
     // longest k-chain first, which makes the round-robin an LPT schedule.
     std::vector<GemmDesc> gs = g;
-    int bn_group = 128, sk_group = 1;
+    int bn_group = 128, sk_group = 1, pair_group = 0;
+    // CTA pairs (cta_group::2): 256 x bn work items on 74 pairs.  Measured (profiles/r2_gemm_tc_pairs_ts.txt): correct, and a pair
+    // needs no pre-split lo planes to match the single-CTA kernel fed with them, but it is not faster (the M = 256 tf32 instruction
+    // issues at ~107 clk against 64 for M = 128, which cancels the halved operand traffic), so the plan uses pairs only on request
+    // (FB_TC_PAIRS=1).  Never for plans that run through k_fused_stack (its GEMM stages are single-CTA) nor on the side lane (two
+    // concurrent persistent launches could not both be resident).
+    const bool pairs_ok = getenv("FB_TC_PAIRS") && !h->cfg.fused_stacks && cur_lane == 0;
     {
       auto natural_bn = [](int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); };
       auto nkb_of = [](const GemmDesc& s) { return fb_ceil_div(s.K, 32) + fb_ceil_div(s.K2, 32); };   // the model counts 32-float k-steps
@@ -249,6 +301,8 @@ struct Builder {
         return (s.flags & GF_RELU_LAZY_OK) != 0 && !getenv("FB_NO_LAZY_RELU");
       };
       double best = 1e30;
+      for (int pair : {0, 1}) {
+      if (pair && !pairs_ok) continue;
       for (int bn : {128, 64, 32}) {
         for (int sk : {1, 2, 3, 4, 6, 8}) {
           if (sk > 1 && getenv("FB_NO_SPLITK")) continue;
@@ -259,26 +313,27 @@ struct Builder {
             const bool splittable = can_split(s, nkb);
             int len = nkb, parts = 1;
             if (splittable && sk > 1) { len = fb_ceil_div(nkb, std::min(sk, nkb / 4)); parts = fb_ceil_div(nkb, len); }
-            const double f = bnp == 128 ? 1.0 : (bnp == 64 ? 0.8 : 0.72);
+            const double f = (bnp == 128 ? 1.0 : (bnp == 64 ? 0.8 : 0.72)) * (pair ? 0.97 : 1.0);
             const double epi = (2.0 + bnp / 64.0) * (parts > 1 ? 2.0 : 1.0);
-            items.push_back(Item{len * f + epi, fb_ceil_div(s.M, TC_BM) * fb_ceil_div(s.N, bnp) * parts});
+            items.push_back(Item{len * f + epi, fb_ceil_div(s.M, TC_BM * (pair + 1)) * fb_ceil_div(s.N, bnp) * parts});
           }
           std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.cost > y.cost; });
           int total = 0;
           for (auto& it : items) total += it.count;
-          const int grid = std::min(total, FB_SM_COUNT);
+          const int grid = std::min(total, pair ? FB_SM_COUNT / 2 : FB_SM_COUNT);
           std::vector<double> load(grid, 0.0);
           int w = 0;
-          for (auto& it : items)
-            for (int i = 0; i < it.count; ++i, ++w) load[w % grid] += it.cost;
+          for (auto& it : items)   // the kernel's deal: rounds of `grid` items in alternating direction (tc_snake)
+            for (int i = 0; i < it.count; ++i, ++w) load[((w / grid) & 1) ? grid - 1 - w % grid : w % grid] += it.cost;
           double cost = 0.0;
           for (double l : load) cost = std::max(cost, l);
-          cost += 0.02 * sk + (bn == 128 ? 0.0 : 0.01);   // ties: fewer splits, wider tiles
-          if (cost < best) { best = cost; bn_group = bn; sk_group = sk; }
+          cost += 0.02 * sk + (bn == 128 ? 0.0 : 0.01) + (pair ? 0.005 : 0.0);   // ties: fewer splits, wider tiles, single CTAs
+          if (cost < best) { best = cost; bn_group = bn; sk_group = sk; pair_group = pair; }
         }
       }
+      }
       if (getenv("FB_DEBUG_PLAN")) {
-        fprintf(stderr, "[fb plan %s] phase %d gemm_tc group: bn=%d splitk=%d model cost %.1f :", h->ws_base ? "real" : "dry", phase, bn_group, sk_group, best);
+        fprintf(stderr, "[fb plan %s] phase %d gemm_tc group: bn=%d splitk=%d %s model cost %.1f :", h->ws_base ? "real" : "dry", phase, bn_group, sk_group, pair_group ? "pairs" : "single", best);
         for (const GemmDesc& s : gs) fprintf(stderr, " [%dx%dx%d%s%s]", s.M, s.N, s.K + s.K2, s.K2 ? "(K2)" : "", (s.flags & GF_RELU) ? " relu" : "");
         fprintf(stderr, "\n");
       }
@@ -292,6 +347,8 @@ struct Builder {
       });
     }
     int ring_bn = 32;
+    const int ncta = pair_group ? 2 : 1;
+    if (ncta == 2) h->uses_pairs = true;
     for (const GemmDesc& s : gs) {
       TcGemmDesc d; memset(&d, 0, sizeof(d));
       d.C = s.C; d.bias = s.bias; d.mask = s.mask; d.M = s.M; d.N = s.N; d.K = s.K; d.K2 = s.K2;
@@ -299,7 +356,7 @@ struct Builder {
       d.bn = s.N <= 32 ? 32 : (s.N <= 64 ? 64 : 128);
       if (d.bn > bn_group) d.bn = bn_group;
       if (d.bn > ring_bn) ring_bn = d.bn;
-      d.tiles_m = fb_ceil_div(s.M, TC_BM); d.tiles_n = fb_ceil_div(s.N, d.bn);
+      d.tiles_m = fb_ceil_div(s.M, TC_BM * ncta); d.tiles_n = fb_ceil_div(s.N, d.bn);   // (pairs: 256-row work items)
       d.splitk = 1; d.kb_per_split = fb_ceil_div(s.K, TC_BK) + fb_ceil_div(s.K2, TC_BK);
       const bool may_split = !(s.flags & GF_RELU) || ((s.flags & GF_RELU_LAZY_OK) && !getenv("FB_NO_LAZY_RELU"));
       const int nkb32 = fb_ceil_div(s.K, 32) + fb_ceil_div(s.K2, 32);
@@ -333,13 +390,14 @@ struct Builder {
       if ((B1 == s.B && is_lazy(s.B)) || (s.K2 && (is_lazy(s.A2) || is_lazy(s.B2)))) { if (rc == FB_OK) rc = FB_E_STATE; }
       if (h->ws_base && rc == FB_OK) {
         rc = encode_tiled_map(&d.mapA, A1, s.M, s.K, lda, TC_BM);
-        if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, B1, s.N, s.K, ldb, d.bn);
+        const int bbox = d.bn / ncta;   // B-tile rows one CTA loads
+        if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, B1, s.N, s.K, ldb, bbox);
         if (rc == FB_OK && s.K2) rc = encode_tiled_map(&d.mapA2, A2, s.M, s.K2, lda2, TC_BM);
-        if (rc == FB_OK && s.K2) rc = encode_tiled_map(&d.mapB2, B2, s.N, s.K2, ldb2, d.bn);
+        if (rc == FB_OK && s.K2) rc = encode_tiled_map(&d.mapB2, B2, s.N, s.K2, ldb2, bbox);
         if (rc == FB_OK && a_pre) rc = encode_tiled_map(&d.mapAlo, Alo, s.M, s.K, ldal, TC_BM);
-        if (rc == FB_OK && b_pre) rc = encode_tiled_map(&d.mapBlo, Blo, s.N, s.K, ldbl, d.bn);
+        if (rc == FB_OK && b_pre) rc = encode_tiled_map(&d.mapBlo, Blo, s.N, s.K, ldbl, bbox);
         if (rc == FB_OK && a_pre && s.K2) rc = encode_tiled_map(&d.mapA2lo, A2lo, s.M, s.K2, ldal2, TC_BM);
-        if (rc == FB_OK && b_pre && s.K2) rc = encode_tiled_map(&d.mapB2lo, B2lo, s.N, s.K2, ldbl2, d.bn);
+        if (rc == FB_OK && b_pre && s.K2) rc = encode_tiled_map(&d.mapB2lo, B2lo, s.N, s.K2, ldbl2, bbox);
       }
       const double k = (double)s.K + s.K2;
       flops += 2.0 * s.M * (double)s.N * k;
@@ -376,18 +434,10 @@ struct Builder {
     for (int i = 0; i < n; ++i)
       if (v[i].splitk == 1 && v[i].M % 4 == 0 && cur_lane == 0)
         produced.push_back(Produced{v[i].C, v[i].M, v[i].N, v[i].ldc, (size_t)((const char*)(dd + i) - d_arena)});
-    const int grid = work < FB_SM_COUNT ? work : FB_SM_COUNT;   // persistent: one CTA per SM walks the group's tiles
-    TcLaunch hdr;
+    TcLaunch hdr;   // persistent grid: one CTA per SM (or one pair per two SMs) walks the group's work items
     if (make_tc_launch(v, work, ring_bn, &hdr) != FB_OK && rc == FB_OK) rc = FB_E_UNSUPPORTED;
-    push([dd, hdr, grid](cudaStream_t s) {
-      // programmatic dependent launch: the kernel's prologue may overlap the tail of the launch before it (fb_pdl_wait inside)
-      cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = s;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = attr; cfg.numAttrs = getenv("FB_NO_PDL") ? 0 : 1;
-      return cudaLaunchKernelEx(&cfg, k_gemm_tc, dd, hdr);
+    push([dd, hdr, work, ncta](cudaStream_t s) {
+      return tc_launch(dd, hdr, work, ncta, s, getenv("FB_NO_PDL") == nullptr);
     }, FB_OPK_GEMM_TC, flops, bytes);
     { FsGemmArgs fa; memset(&fa, 0, sizeof(fa)); fa.descs = dd; fa.hdr = hdr; h->ops[phase].back().dev.set(FS_GEMM_TC, work, fa); }
     if (used_early) h->ops[phase].back().wait_stage = 1;   // operands staged on the staging lane: wait for this phase's staging event
@@ -587,7 +637,7 @@ static int build_plan(fb_handle* h) {
   char* d_arena = (char*)ws_alloc(h, FB_DESC_ARENA_BYTES);
   h->d_sc = (DevScalars*)ws_alloc(h, sizeof(DevScalars));
   h->d_acc = (double*)ws_alloc(h, ACC_COUNT * sizeof(double));
-  h->d_linf = (unsigned int*)ws_alloc(h, 16);
+  h->d_linf = (unsigned int*)ws_alloc(h, (size_t)c.z_dim * c.z_dim * sizeof(float));   // B^T B scratch of the metrics phase (k_metric_cov)
   h->d_metrics = (float*)ws_alloc(h, FB_METRIC_COUNT * sizeof(float));
   h->d_n_episodes = (int*)ws_alloc(h, 16);
   h->d_ep_idx = (int*)ws_alloc(h, B * sizeof(int));
@@ -602,6 +652,7 @@ static int build_plan(fb_handle* h) {
   h->d_fs_barrier = (unsigned long long*)ws_alloc(h, FS_NUM_BARRIERS * sizeof(unsigned long long));
   h->d_fs_err = (unsigned int*)ws_alloc(h, 16);
   h->d_fs_times = (unsigned long long*)ws_alloc(h, (FS_MAX_STAGES + 1) * sizeof(unsigned long long));
+  h->uses_pairs = false;
   h->fused_plans.clear(); h->prog_host.clear(); h->prog_uploaded = 0; h->n_fs_barriers = 0;
 
   // ---- packed batch rows ---------------------------------------------------------------------
@@ -1293,19 +1344,20 @@ static int build_plan(fb_handle* h) {
   // =========================== FB_PHASE_METRICS =================================================
   b.set_phase(FB_PHASE_METRICS);
   b.memset0(acc + ACC_F1, 6 * sizeof(double));
-  b.memset0(h->d_linf, 16);
+  b.memset0(h->d_linf, (size_t)Z * Z * sizeof(float));
   b.push([F1, Bm, z, B, Z, acc](cudaStream_t s) {
     fb_launch_pdl(k_metric_rows, dim3(fb_ceil_div(B, 8)), dim3(256), 0, s, F1.p, F1.ld, Bm.p, Bm.ld, z.p, z.ld, B, Z, acc);
     return cudaGetLastError();
   });
   {
-    unsigned int* linf = h->d_linf;
-    b.push([Bg, n, Z, acc, linf](cudaStream_t s) {
-      fb_launch_pdl(k_metric_cov, dim3(Z), dim3(256), 0, s, Bg.p, Bg.ld, n, Z, acc, linf);
+    float* cov = reinterpret_cast<float*>(h->d_linf);
+    const int chunk = std::max(1, std::min(FB_COV_ROWS, (int)(48 * 1024 / ((Z + 1) * sizeof(float)))));
+    b.push([Bg, n, Z, cov, chunk](cudaStream_t s) {
+      fb_launch_pdl(k_metric_cov, dim3(fb_ceil_div(n, chunk)), dim3(256), (size_t)chunk * (Z + 1) * sizeof(float), s, Bg.p, Bg.ld, n, Z, cov, chunk);
       return cudaGetLastError();
     });
     MetricFinalParams mp; memset(&mp, 0, sizeof(mp));
-    mp.acc = acc; mp.linf_bits = linf; mp.out = h->d_metrics; mp.n_local = B; mp.n_global = n; mp.Z = Z; mp.ortho_coef = c.ortho_coef;
+    mp.acc = acc; mp.cov = cov; mp.out = h->d_metrics; mp.n_local = B; mp.n_global = n; mp.Z = Z; mp.ortho_coef = c.ortho_coef;
     mp.q_loss_coef = c.q_loss ? c.q_loss_coef : 0.f;
     mp.temp = bz ? c.temp : 0.f;
     b.push([mp](cudaStream_t s) { fb_launch_pdl(k_metric_final, dim3(1), dim3(32), 0, s, mp); return cudaGetLastError(); });
@@ -1589,7 +1641,7 @@ int fb_bind(fb_handle* h, const fb_buffers* bufs, void* stream) {
   int rc = build_plan(h);
   if (rc != FB_OK) return rc;
   CK(cudaFuncSetAttribute(k_gemm_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  if (h->uses_gemm_tc) CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  if (h->uses_gemm_tc) CK(tc_set_smem_attr());
   if (h->uses_gemm_tc) {
     CK(cudaFuncSetAttribute(k_fused_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     int dev = 0, sms = 0, per_sm = 0;
@@ -2039,6 +2091,7 @@ int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream) {
   if ((phase_mask & FB_PHASE_SAMPLE) && !(phase_mask & FB_RUN_HOST_BATCH) && !h->replay_bound) return FB_E_STATE;
   cudaStream_t s = (cudaStream_t)stream;
   const bool fused = fused_wanted(h, phase_mask);
+  if (fused && h->uses_pairs) return FB_E_STATE;   // CTA-pair GEMM launches have no fused form: create the handle with cfg.fused_stacks
   fb_handle::FusedPlan* fplan = nullptr;
   if (fused) {   // before any capture: building the plan uploads its programs
     int rc = get_fused_plan(h, phase_mask, s, &fplan);
@@ -2072,6 +2125,7 @@ int fb_run(fb_handle* h, uint32_t phase_mask, int use_graph, void* stream) {
 
 int fb_launch_count(fb_handle* h, uint32_t phase_mask) {
   if (!h || !h->bound) return FB_E_STATE;
+  if (fused_wanted(h, phase_mask) && h->uses_pairs) return FB_E_STATE;
   if (fused_wanted(h, phase_mask)) {   // fused execution: one launch per unit (fused segment or stand-alone kernel)
     auto it = h->fused_plans.find(phase_mask);
     if (it != h->fused_plans.end()) return (int)it->second.units.size();
@@ -2142,6 +2196,7 @@ int fb_profile_ops(fb_handle* h, uint32_t phase_mask, int reps, void* stream, fl
 int fb_fused_profile(fb_handle* h, uint32_t phase_mask, int reps, void* stream, float* us_out, int32_t* info_out, int cap) {
   if (!h || !h->bound) return FB_E_STATE;
   if (reps < 1 || cap < 1 || !us_out || !info_out || !fused_wanted(h, phase_mask)) return FB_E_ARG;
+  if (h->uses_pairs) return FB_E_STATE;
   cudaStream_t s = (cudaStream_t)stream;
   fb_handle::FusedPlan* plan = nullptr;
   int rc = get_fused_plan(h, phase_mask, s, &plan);
@@ -2243,6 +2298,53 @@ int fb_batch_row_layout(int obs_dim, int action_dim, int goal_dim, int extra_dim
   return FB_OK;
 }
 
+int fb_host_gather_rows(const fb_host_storage* st, const int32_t* ep_idx, const int32_t* step_idx, const int32_t* future_idx,
+                        int batch, float replay_discount, float* rows, int pitch) {
+  if (!st || !st->observation || !st->action || !st->discount || !ep_idx || !step_idx || !rows || batch < 1) return FB_E_ARG;
+  const int O = st->obs_dim, A = st->action_dim, G = st->goal ? st->goal_dim : 0, R = st->rows_per_episode;
+  BatchLayout L;
+  make_batch_layout(L, O, A, G, 0, future_idx != nullptr);
+  if (pitch < L.pitch || O < 1 || A < 1 || R < 2) return FB_E_ARG;
+  auto row = [R](const float* base, int dim, int ep, int t) { return base + ((size_t)ep * R + t) * dim; };
+  // pass 1: touch every source line (the rows are random 100-byte reads of a buffer far larger than the caches: the misses overlap)
+  for (int i = 0; i < batch; ++i) {
+    const int ep = ep_idx[i], t = step_idx[i];
+    if (t < 1 || t >= R) return FB_E_ARG;
+    const float* o0 = row(st->observation, O, ep, t - 1);
+    for (int b = 0; b < 2 * O * 4; b += 64) __builtin_prefetch((const char*)o0 + b);   // rows t-1 and t are adjacent
+    __builtin_prefetch(row(st->action, A, ep, t));
+    __builtin_prefetch(row(st->discount, 1, ep, t));
+    if (st->reward) __builtin_prefetch(row(st->reward, 1, ep, t));
+    if (G) { const float* g0 = row(st->goal, G, ep, t - 1); for (int b = 0; b < 2 * G * 4; b += 64) __builtin_prefetch((const char*)g0 + b); }
+    if (future_idx) {
+      const int f = future_idx[i];
+      if (f < 1 || f > R) return FB_E_ARG;
+      __builtin_prefetch(row(st->observation, O, ep, f - 1));
+      if (G) __builtin_prefetch(row(st->goal, G, ep, f - 1));
+    }
+  }
+  for (int i = 0; i < batch; ++i) {
+    const int ep = ep_idx[i], t = step_idx[i];
+    float* out = rows + (size_t)i * pitch;
+    memcpy(out + L.off_obs, row(st->observation, O, ep, t - 1), O * sizeof(float));
+    memcpy(out + L.off_action, row(st->action, A, ep, t), A * sizeof(float));
+    out[L.off_rd + 0] = st->reward ? *row(st->reward, 1, ep, t) : 0.f;
+    out[L.off_rd + 1] = replay_discount * *row(st->discount, 1, ep, t);
+    out[L.off_rd + 2] = 0.f; out[L.off_rd + 3] = 0.f;
+    memcpy(out + L.off_next_obs, row(st->observation, O, ep, t), O * sizeof(float));
+    if (G) {
+      memcpy(out + L.off_goal, row(st->goal, G, ep, t - 1), G * sizeof(float));
+      memcpy(out + L.off_next_goal, row(st->goal, G, ep, t), G * sizeof(float));
+    }
+    if (future_idx) {
+      const int f = future_idx[i];
+      memcpy(out + L.off_future_obs, row(st->observation, O, ep, f - 1), O * sizeof(float));
+      if (G) memcpy(out + L.off_future_goal, row(st->goal, G, ep, f - 1), G * sizeof(float));
+    }
+  }
+  return FB_OK;
+}
+
 int fb_replay_gather(const fb_replay_view* view, int obs_dim, int action_dim, const int32_t* d_ep_idx, const int32_t* d_step_idx,
                      const int32_t* d_future_idx, int batch, float replay_discount, float* d_out, int out_ld, void* stream) {
   if (!view || !d_ep_idx || !d_step_idx || !d_out || batch < 1) return FB_E_ARG;
@@ -2278,9 +2380,10 @@ int fb_replay_pack_episode(const fb_replay_view* view, float* d_rows_mut, int sl
 int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, int M, int N, int K, int lda, int ldb, int ldc,
              int a_kmajor, int b_kmajor, int relu, int splitk, int tile_cfg, void* stream) {
   if (!dA || !dB || !dC || M < 1 || N < 1 || K < 1) return FB_E_ARG;
-  if (tile_cfg > 3) return FB_E_ARG;
+  if (tile_cfg > 4) return FB_E_ARG;
   cudaStream_t s = (cudaStream_t)stream;
-  if (tile_cfg == 3) {  // tcgen05 3xTF32 kernel
+  if (tile_cfg >= 3) {  // tcgen05 3xTF32 kernel (4: CTA pairs, cta_group::2)
+    const int ncta = tile_cfg == 4 ? 2 : 1;
     if (!a_kmajor || !aligned16(dA) || lda % 4) return FB_E_UNSUPPORTED;
     const float* Bp = dB;
     int ldbp = ldb;
@@ -2304,7 +2407,7 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
     }
     TcGemmDesc d; memset(&d, 0, sizeof(d));
     d.C = dC; d.bias = d_bias; d.M = M; d.N = N; d.K = K; d.ldc = ldc; d.flags = relu ? GF_RELU : 0; d.bn = N > 64 ? 128 : 64;
-    d.tiles_m = fb_ceil_div(M, TC_BM); d.tiles_n = fb_ceil_div(N, d.bn); d.work_begin = 0;
+    d.tiles_m = fb_ceil_div(M, TC_BM * ncta); d.tiles_n = fb_ceil_div(N, d.bn); d.work_begin = 0;
     d.splitk = 1; d.kb_per_split = fb_ceil_div(K, TC_BK);
     if (splitk > 1) {   // C must be zeroed by the caller
       if (relu) return FB_E_ARG;
@@ -2313,17 +2416,17 @@ int fb_sgemm(const float* dA, const float* dB, float* dC, const float* d_bias, i
     }
     d.work_count = d.tiles_m * d.tiles_n * d.splitk;
     int rc = encode_tiled_map(&d.mapA, dA, M, K, lda, TC_BM);
-    if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, Bp, N, K, ldbp, d.bn);
-    if (rc == FB_OK && tmp_lo) { rc = encode_tiled_map(&d.mapBlo, tmp_lo, N, K, ldbp, d.bn); d.flags |= TC_B_PRE; }
+    if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, Bp, N, K, ldbp, d.bn / ncta);
+    if (rc == FB_OK && tmp_lo) { rc = encode_tiled_map(&d.mapBlo, tmp_lo, N, K, ldbp, d.bn / ncta); d.flags |= TC_B_PRE; }
     if (rc != FB_OK) return rc;
     TcGemmDesc* dd = nullptr;
     CK(cudaMallocAsync(&dd, sizeof(d), s));
     CK(cudaMemcpyAsync(dd, &d, sizeof(d), cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));
-    CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CK(tc_set_smem_attr());
     TcLaunch hdr;
     make_tc_launch(std::vector<TcGemmDesc>(1, d), d.work_count, d.bn, &hdr);
-    k_gemm_tc<<<d.work_count < FB_SM_COUNT ? d.work_count : FB_SM_COUNT, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, hdr);
+    CK(tc_launch(dd, hdr, d.work_count, ncta, s, false));
     CK(cudaGetLastError());
     CK(cudaFreeAsync(dd, s));
     if (tmp) CK(cudaFreeAsync(tmp, s));
@@ -2368,7 +2471,8 @@ int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int splitk, int dbg
   TcGemmDesc* dd = nullptr;
   const bool pre_b = dbg & (1 << 19), pre_a = dbg & (1 << 20);   // lo planes: a second (zero) copy behind the raw one
   const bool random_fill = dbg & (1 << 21);                       // operands: pseudo-random instead of a constant
-  dbg &= ~((1 << 19) | (1 << 20) | (1 << 21));
+  const int ncta = (dbg & (1 << 22)) ? 2 : 1;                     // CTA pairs
+  dbg &= ~((1 << 19) | (1 << 20) | (1 << 21) | (1 << 22));
   CK(cudaMallocAsync(&A, (size_t)nprob * M * K * 4 * 2, s));
   CK(cudaMallocAsync(&B, (size_t)nprob * N * K * 4 * 2, s));
   CK(cudaMemsetAsync(A, 0, (size_t)nprob * M * K * 4 * 2, s));
@@ -2386,27 +2490,26 @@ int fb_gemm_tc_bench(int M, int N, int K, int bn, int nprob, int splitk, int dbg
   for (int i = 0; i < nprob && rc == FB_OK; ++i) {
     TcGemmDesc& d = v[i]; memset(&d, 0, sizeof(d));
     d.C = Cm + (size_t)i * M * N; d.M = M; d.N = N; d.K = K; d.ldc = N; d.flags = dbg; d.bn = bn;
-    d.tiles_m = fb_ceil_div(M, TC_BM); d.tiles_n = fb_ceil_div(N, bn); d.work_begin = work;
+    d.tiles_m = fb_ceil_div(M, TC_BM * ncta); d.tiles_n = fb_ceil_div(N, bn); d.work_begin = work;
     d.splitk = 1; d.kb_per_split = fb_ceil_div(K, TC_BK);
     if (splitk > 1) { d.kb_per_split = fb_ceil_div(d.kb_per_split, splitk); d.splitk = fb_ceil_div(fb_ceil_div(K, TC_BK), d.kb_per_split); }
     d.work_count = d.tiles_m * d.tiles_n * d.splitk;
     work += d.work_count;
     rc = encode_tiled_map(&d.mapA, A + (size_t)i * M * K, M, K, K, TC_BM);
-    if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, B + (size_t)i * N * K, N, K, K, bn);
+    if (rc == FB_OK) rc = encode_tiled_map(&d.mapB, B + (size_t)i * N * K, N, K, K, bn / ncta);
     if (rc == FB_OK && pre_a) { rc = encode_tiled_map(&d.mapAlo, A + (size_t)(nprob + i) * M * K, M, K, K, TC_BM); d.flags |= TC_A_PRE; }
-    if (rc == FB_OK && pre_b) { rc = encode_tiled_map(&d.mapBlo, B + (size_t)(nprob + i) * N * K, N, K, K, bn); d.flags |= TC_B_PRE; }
+    if (rc == FB_OK && pre_b) { rc = encode_tiled_map(&d.mapBlo, B + (size_t)(nprob + i) * N * K, N, K, K, bn / ncta); d.flags |= TC_B_PRE; }
   }
   if (rc == FB_OK) {
     cudaEvent_t e0, e1;
     CK(cudaMemcpyAsync(dd, v.data(), sizeof(TcGemmDesc) * nprob, cudaMemcpyHostToDevice, s));
-    CK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CK(tc_set_smem_attr());
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    const int grid = work < FB_SM_COUNT ? work : FB_SM_COUNT;
     TcLaunch hdr;
     make_tc_launch(v, work, bn, &hdr);
-    for (int r = 0; r < 3; ++r) k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, hdr);
+    for (int r = 0; r < 3; ++r) CK(tc_launch(dd, hdr, work, ncta, s, false));
     CK(cudaEventRecord(e0, s));
-    for (int r = 0; r < reps; ++r) k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(dd, hdr);
+    for (int r = 0; r < reps; ++r) CK(tc_launch(dd, hdr, work, ncta, s, false));
     CK(cudaEventRecord(e1, s));
     CK(cudaEventSynchronize(e1));
     CK(cudaGetLastError());

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_stack(const char* __res
       switch (item.type) {
         case FS_GEMM_TC: {
           const FsGemmArgs* a = reinterpret_cast<const FsGemmArgs*>(args);
-          tc_gemm_roles(a->descs, a->hdr, vcta, ng, &sh, epi_scratch, smem_base, smem_gen);
+          tc_gemm_roles<false, 1>(a->descs, a->hdr, vcta, ng, &sh, epi_scratch, smem_base, smem_gen);
           break;
         }
         case FS_LN_FWD: {

@@ -109,6 +109,64 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(tc_smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// ---- CTA pairs (cta_group::2): the two CTAs of a cluster share one 256 x BN tile; rank 0 issues the MMAs for both ----
+__device__ __forceinline__ uint32_t tc_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default (CTA-scope) semantics on purpose: a
+// .release.cluster arrive compiles to MEMBAR.ALL.GPU in front of it and the matching .acquire.cluster wait to CCTL.IVALL behind it,
+// once per k-block and warp (measured: a pair k-block at 1600 clk whatever the MMA count).  What the barrier orders here is shared /
+// tensor memory handed to the async proxy (fence.proxy.async / tcgen05 fences on the writer's side), not global memory.
+__device__ __forceinline__ void tc_mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(tc_smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// wait on a barrier whose arrivals come from both CTAs of the pair (see tc_mbar_arrive_remote for the scope)
+__device__ __forceinline__ void tc_mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(tc_smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_ts_2cta(uint32_t tmem_d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of every MMA issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_mma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void tc_tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
                "l"(reinterpret_cast<uint64_t>(map)), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1)
@@ -212,6 +270,7 @@ __device__ __forceinline__ void tc_build_lo_relu(float4* __restrict__ raw, float
 }
 
 // which problem / tile / k-range of the group is work item w (header only: no global loads)
+template <int NCTA = 1>   // NCTA = 2: a work item is a 256-row pair tile (the header's work counts are built for pairs)
 __device__ __forceinline__ int tc_locate(const TcLaunch& L, int w, int* m0, int* n0, int* kb0, int* kb1) {
   int p = 0;
   while (p + 1 < L.nprob && L.p[p + 1].work_begin <= w) ++p;
@@ -227,8 +286,16 @@ __device__ __forceinline__ int tc_locate(const TcLaunch& L, int w, int* m0, int*
     *kb0 = 0; *kb1 = nk;
   }
   const int tm = local / d.tiles_n, tn = local - tm * d.tiles_n;
-  *m0 = tm * TC_BM; *n0 = tn * d.bn;
+  *m0 = tm * (TC_BM * NCTA); *n0 = tn * d.bn;
   return p;
+}
+
+// Work item of (virtual) CTA `vcta` in the round that starts at item `base`: rounds alternate direction (0, 1, .., n-1, then n-1, ..,
+// 0), so that with the items ordered longest first the CTAs that drew the long items of one round draw the short ones of the next.
+// A plain round-robin stacks long on long: a group of 64 long + 133 short tiles on 148 CTAs ends at long + short instead of
+// 2 x short (the LPT schedule; fb_b200.cu gemm_tc() orders the problems and models exactly this deal).
+__device__ __forceinline__ int tc_snake(int base, int vcta, int ncta) {
+  return base + (((base / ncta) & 1) ? (ncta - 1 - vcta) : vcta);
 }
 
 __device__ __forceinline__ void tc_prefetch_map(const CUtensorMap* m) {
@@ -248,7 +315,7 @@ struct TcShared {
 };
 
 // one thread: (re)initialise the pipeline barriers of a launch / of a GEMM item of the fused kernel (reinit: the objects are live)
-__device__ __forceinline__ void tc_init_barriers(TcShared* sh, bool reinit) {
+__device__ __forceinline__ void tc_init_barriers(TcShared* sh, bool reinit, int group_ctas = 1) {
   if (reinit) {
     for (int s = 0; s < TC_MAX_STAGES; ++s) {
       asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_raw[s])) : "memory");
@@ -261,12 +328,12 @@ __device__ __forceinline__ void tc_init_barriers(TcShared* sh, bool reinit) {
   }
   for (int s = 0; s < TC_MAX_STAGES; ++s) {
     tc_mbar_init(&sh->bar_raw[s], 1);
-    tc_mbar_init(&sh->bar_ready[s], 128);
+    tc_mbar_init(&sh->bar_ready[s], 4 * group_ctas);   // one arrival per builder warp of every CTA of the group, on the leader's barrier
     tc_mbar_init(&sh->bar_empty[s], 1);
   }
   for (int j = 0; j < TC_MAX_ASLOTS; ++j) tc_mbar_init(&sh->bar_afree[j], 1);
   tc_mbar_init(&sh->bar_accum, 1);
-  tc_mbar_init(&sh->bar_tmem_empty, 128);
+  tc_mbar_init(&sh->bar_tmem_empty, 4 * group_ctas);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
@@ -275,30 +342,51 @@ __device__ __forceinline__ void tc_init_barriers(TcShared* sh, bool reinit) {
 // or shared memory).  smem_base / smem_gen: the 1024-byte aligned operand ring (shared-window address / generic pointer).
 // Activations and masks produced by earlier launches are read with plain (coherent) loads: inside the fused kernel they were
 // written by other SMs during the same kernel.
+// TS = true: A operand through tensor memory (FB_TC_TS=1; measured latency-bound by the number of A slots that fit next to the
+// accumulators, profiles/r2_gemm_tc_ts.txt); TS = false: both operands in shared memory.
+// NCTA = 2: CTA pairs (clusters of two, tcgen05 cta_group::2).  A work item is a 256 x bn tile; CTA `rank` of the pair loads its own
+// 128 rows of A and HALF of the B tile (rows [rank bn/2, (rank+1) bn/2)), so a k-block costs each SM 16 + 8 KB of L2 -> SM and
+// shared-memory traffic instead of 16 + 16; rank 0's MMA warp issues M = 256 instructions that read both CTAs' operands and write
+// both CTAs' tensor memory; the builders / epilogue warps of both CTAs arrive on rank 0's barriers, tcgen05.commit multicasts the
+// completions to both.  `vcta` / `ncta` then count pairs.
+template <bool TS, int NCTA>
 __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcLaunch& L, int vcta, int ncta, TcShared* sh,
-                                              float* epi_scratch, uint32_t smem_base, uint8_t* smem_gen) {
+                                              float* epi_scratch, uint32_t smem_base, uint8_t* smem_gen, uint32_t rank = 0) {
   const int total = L.total, ring_bn = L.ring_bn;
   uint64_t* bar_raw = sh->bar_raw; uint64_t* bar_ready = sh->bar_ready; uint64_t* bar_empty = sh->bar_empty;
   uint64_t& bar_accum = sh->bar_accum; uint64_t& bar_tmem_empty = sh->bar_tmem_empty;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // ring geometry: narrower B tiles leave room for more stages (3 at BN = 128, 4 at BN = 64 / 32)
+  // ring geometry: narrower B tiles leave room for more stages.  SS: a stage is [A raw | B raw | A lo | B lo] (3 stages at BN = 128);
+  // TS: [A raw | B raw | B lo] (4 stages at BN = 128, 6 at BN <= 64)
   const uint32_t b_off = TC_A_TILE_BYTES;
-  const uint32_t half_bytes = TC_A_TILE_BYTES + (uint32_t)ring_bn * TC_ROW_BYTES;   // raw (or lo) part of a stage: A tile then B tile
-  const uint32_t stage_bytes = 2u * half_bytes;
+  const uint32_t b_bytes = (uint32_t)(ring_bn / NCTA) * TC_ROW_BYTES;   // this CTA's share of the B tile
+  const uint32_t half_bytes = TC_A_TILE_BYTES + b_bytes;   // raw part of a stage: A tile then B tile
+  const uint32_t blo_off = TS ? half_bytes : half_bytes + b_off;   // the B lo tile inside a stage
+  const uint32_t stage_bytes = TS ? half_bytes + b_bytes : 2u * half_bytes;
   const int nst = min(TC_MAX_STAGES, (int)(TC_RING_BYTES / stage_bytes));
   const uint32_t tmem_base = sh->tmem_base;
+  // TS: TMEM columns [0, (n_hh + 1) ring_bn) hold the accumulators of the widest tile, A slots of 64 columns follow.  At BN = 128
+  // only ONE hi.hi accumulator fits next to four slots (two slots cannot cover the commit -> rebuild -> issue latency)
+  const int n_hh_max = TS ? (ring_bn > 64 ? 1 : 2) : 3;
+  const uint32_t slot_col0 = (uint32_t)(n_hh_max + 1) * (uint32_t)ring_bn;
+  const int nslots = min(TC_MAX_ASLOTS, (int)((512u - slot_col0) / TC_A_SLOT_COLS));
+  uint64_t* bar_afree = sh->bar_afree;
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       uint32_t kbg = 0;   // k-blocks issued by this CTA so far (ring position), across tiles
-      for (int w = vcta; w < total; w += ncta) {
+      for (int base = 0; base < total; base += ncta) {
+        const int w = tc_snake(base, vcta, ncta);
+        if (w >= total) continue;
         int m0, n0, kb0, kb1;
-        const int pi = tc_locate(L, w, &m0, &n0, &kb0, &kb1);
+        const int pi = tc_locate<NCTA>(L, w, &m0, &n0, &kb0, &kb1);
         const TcGemmDesc* __restrict__ d = &descs[pi];
         const int bn = L.p[pi].bn, flags = L.p[pi].flags;
         const int nk1 = (L.p[pi].K + TC_BK - 1) / TC_BK;
+        m0 += (int)rank * TC_BM; n0 += (int)rank * (bn / NCTA);   // this CTA's rows of A and of the B tile
         if (kb0 < nk1) { tc_prefetch_map(&d->mapA); tc_prefetch_map(&d->mapB); }
-        const uint32_t tx_bytes = (uint32_t)TC_A_TILE_BYTES * ((flags & TC_A_PRE) ? 2u : 1u) + (uint32_t)bn * TC_ROW_BYTES * ((flags & TC_B_PRE) ? 2u : 1u);
+        const bool a_pre = !TS && (flags & TC_A_PRE);   // TS: the A lo half is built in registers, a pre-split plane is never loaded
+        const uint32_t tx_bytes = (uint32_t)TC_A_TILE_BYTES * (a_pre ? 2u : 1u) + (uint32_t)(bn / NCTA) * TC_ROW_BYTES * ((flags & TC_B_PRE) ? 2u : 1u);
         for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)nst;
           if (kbg >= (uint32_t)nst) tc_mbar_wait(&bar_empty[s], ((kbg / (uint32_t)nst) - 1u) & 1u);
@@ -308,48 +396,79 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
           const int kc = (second ? kb - nk1 : kb) * TC_BK;
           tc_tma_load_2d(st, second ? &d->mapA2 : &d->mapA, &bar_raw[s], kc, m0);
           tc_tma_load_2d(st + b_off, second ? &d->mapB2 : &d->mapB, &bar_raw[s], kc, n0);
-          if (flags & TC_A_PRE) tc_tma_load_2d(st + half_bytes, second ? &d->mapA2lo : &d->mapAlo, &bar_raw[s], kc, m0);
-          if (flags & TC_B_PRE) tc_tma_load_2d(st + half_bytes + b_off, second ? &d->mapB2lo : &d->mapBlo, &bar_raw[s], kc, n0);
+          if (a_pre) tc_tma_load_2d(st + half_bytes, second ? &d->mapA2lo : &d->mapAlo, &bar_raw[s], kc, m0);
+          if (flags & TC_B_PRE) tc_tma_load_2d(st + blo_off, second ? &d->mapB2lo : &d->mapBlo, &bar_raw[s], kc, n0);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      uint32_t kbg = 0, it = 0;
-      for (int w = vcta; w < total; w += ncta, ++it) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (the pair's leader) =====
+      uint32_t kbg = 0, itc = 0;
+      for (int base = 0; base < total; base += ncta) {
+        const int w = tc_snake(base, vcta, ncta);
+        if (w >= total) continue;
+        const uint32_t it = itc++;
         int m0, n0, kb0, kb1;
-        const int pi = tc_locate(L, w, &m0, &n0, &kb0, &kb1);
+        const int pi = tc_locate<NCTA>(L, w, &m0, &n0, &kb0, &kb1);
         const int bn = L.p[pi].bn;
         const int nk = kb1 - kb0;
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((TC_BM * NCTA) >> 4) << 24);
+        auto mma_ss = [](uint32_t d_, uint64_t a_, uint64_t b_, uint32_t i_, uint32_t acc_) {
+          if constexpr (NCTA == 2) tc_mma_tf32_2cta(d_, a_, b_, i_, acc_); else tc_mma_tf32(d_, a_, b_, i_, acc_);
+        };
+        auto mma_ts = [](uint32_t d_, uint32_t a_, uint64_t b_, uint32_t i_, uint32_t acc_) {
+          if constexpr (NCTA == 2) tc_mma_tf32_ts_2cta(d_, a_, b_, i_, acc_); else tc_mma_tf32_ts(d_, a_, b_, i_, acc_);
+        };
+        auto commit = [](uint64_t* bar) { if constexpr (NCTA == 2) tc_mma_commit_2cta(bar); else tc_mma_commit(bar); };
         const int nchain = (L.p[pi].flags & TC_DBG_ONECHAIN) ? 1 : 3;
         if (it > 0) {   // the previous tile's accumulators must have been read out
+          if constexpr (NCTA == 2) tc_mbar_wait_cluster(&bar_tmem_empty, (it - 1u) & 1u); else
           tc_mbar_wait(&bar_tmem_empty, (it - 1u) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         for (int kb = 0; kb < nk; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)nst;
+          if constexpr (NCTA == 2) tc_mbar_wait_cluster(&bar_ready[s], (kbg / (uint32_t)nst) & 1u); else
           tc_mbar_wait(&bar_ready[s], (kbg / (uint32_t)nst) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_base + s * stage_bytes;
+          const int k32 = kb / TC_KB_PER_32;
+          if constexpr (TS) {
+            // accumulators: columns [j*bn, (j+1)*bn): j = (32-float k-step) % n_hh_max for hi.hi, j = n_hh_max for the two correction chains
+            const uint32_t a_hi = tmem_base + slot_col0 + (uint32_t)(kbg % (uint32_t)nslots) * TC_A_SLOT_COLS, a_lo = a_hi + 32u;
+            const uint32_t b_raw = st + b_off, b_lo = st + blo_off;
+            const uint32_t acc_hh = tmem_base + (uint32_t)(k32 % n_hh_max) * (uint32_t)bn, acc_c = tmem_base + (uint32_t)n_hh_max * (uint32_t)bn;
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 8; ++ks)
+              mma_ts(acc_hh, a_hi + ks * 8u, tc_umma_desc(b_raw + ks * 32u), idesc, (ks == 0 && k32 < n_hh_max) ? 0u : 1u);
+            if (nchain > 1) {
+#pragma unroll
+              for (int ks = 0; ks < TC_BK / 8; ++ks)
+                mma_ts(acc_c, a_lo + ks * 8u, tc_umma_desc(b_raw + ks * 32u), idesc, (ks == 0 && kb == 0) ? 0u : 1u);
+#pragma unroll
+              for (int ks = 0; ks < TC_BK / 8; ++ks)
+                mma_ts(acc_c, a_hi + ks * 8u, tc_umma_desc(b_lo + ks * 32u), idesc, 1u);
+            }
+            commit(&bar_afree[kbg % (uint32_t)nslots]);
+          } else {
 #pragma unroll
           for (int chain = 0; chain < 3; ++chain) {   // (A raw, B raw), (A lo, B raw), (A raw, B lo)
             if (chain >= nchain) break;
             const uint32_t a = st + (chain == 1 ? half_bytes : 0u);
             const uint32_t b = st + b_off + (chain == 2 ? half_bytes : 0u);
             // accumulators: columns [j*bn, (j+1)*bn): j = (32-float k-step) % 3 for hi.hi, j = 3 for the two correction chains
-            const int k32 = kb / TC_KB_PER_32;
             const uint32_t acc = tmem_base + (uint32_t)(chain == 0 ? (k32 % 3) : 3) * (uint32_t)bn;
 #pragma unroll
             for (int ks = 0; ks < TC_BK / 8; ++ks) {
               const bool first = (ks == 0) && (chain == 0 ? (k32 < 3 && kb % TC_KB_PER_32 == 0) : (kb == 0 && chain == 1));
-              tc_mma_tf32(acc, tc_umma_desc(a + ks * 32u), tc_umma_desc(b + ks * 32u), idesc, first ? 0u : 1u);
+              mma_ss(acc, tc_umma_desc(a + ks * 32u), tc_umma_desc(b + ks * 32u), idesc, first ? 0u : 1u);
             }
           }
-          tc_mma_commit(&bar_empty[s]);
+          }
+          commit(&bar_empty[s]);
         }
-        tc_mma_commit(&bar_accum);
+        commit(&bar_accum);
       }
     }
   } else if (warp < 6) {
@@ -358,13 +477,18 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
     float* scr = epi_scratch + q * (32 * TC_EPI_LD);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t kbg = 0, it = 0;
-    for (int w = vcta; w < total; w += ncta, ++it) {
+    uint32_t kbg = 0, itc = 0;
+    for (int base = 0; base < total; base += ncta) {
+      const int w = tc_snake(base, vcta, ncta);
+      if (w >= total) continue;
+      const uint32_t it = itc++;
       int m0, n0, kb0, kb1;
-      const int pi = tc_locate(L, w, &m0, &n0, &kb0, &kb1);
+      const int pi = tc_locate<NCTA>(L, w, &m0, &n0, &kb0, &kb1);
       const TcGemmDesc* __restrict__ d = &descs[pi];
       const int bn = L.p[pi].bn, flags = L.p[pi].flags;
       const int nk = kb1 - kb0;
+      const int bnl = bn / NCTA;          // rows of this CTA's share of the B tile
+      m0 += (int)rank * TC_BM;            // this CTA's 128 rows of the (pair) tile
       // epilogue pointers: loaded now, used after the mainloop (their latency hides behind it)
       const int M = L.p[pi].M, N = L.p[pi].N, ldc = d->ldc, ldmask = d->ldmask;
       const float* __restrict__ bias = d->bias;
@@ -373,25 +497,69 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
       float* __restrict__ CT = d->CT;
       float* __restrict__ CT_lo = d->CT_lo;
       const int ldct = d->ldct;
-      const bool build_a = !(flags & (TC_A_PRE | TC_DBG_NOBUILD)), build_b = !(flags & (TC_B_PRE | TC_DBG_NOBUILD));
+      const bool build_a = !TS && !(flags & (TC_A_PRE | TC_DBG_NOBUILD)), build_b = !(flags & (TC_B_PRE | TC_DBG_NOBUILD));
       for (int kb = 0; kb < nk; ++kb, ++kbg) {
         const uint32_t s = kbg % (uint32_t)nst;
         tc_mbar_wait(&bar_raw[s], (kbg / (uint32_t)nst) & 1u);
         const float4* raw = reinterpret_cast<const float4*>(smem_gen + (size_t)s * stage_bytes);
-        float4* lo = reinterpret_cast<float4*>(smem_gen + (size_t)s * stage_bytes + half_bytes);
+        float4* lo = reinterpret_cast<float4*>(smem_gen + (size_t)s * stage_bytes + half_bytes);   // SS: [A lo | B lo]
+        if constexpr (TS) {
+          // this thread's row of the A tile: eight 16-byte chunks, chunk c of row r stored at c ^ (r & 7) (SWIZZLE_128B); a
+          // quarter-warp reads eight different rows, i.e. eight different physical chunks: conflict-free
+          const int r = q * 32 + lane;
+          const uint8_t* arow = smem_gen + (size_t)s * stage_bytes + (size_t)r * TC_ROW_BYTES;
+          uint32_t hi[32], lw[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 x = *reinterpret_cast<const float4*>(arow + ((c ^ (r & 7)) << 4));
+            if (flags & TC_A_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t h = __float_as_uint(xv[j]) & 0xFFFFE000u;
+              hi[c * 4 + j] = h;
+              lw[c * 4 + j] = (flags & TC_DBG_NOBUILD) ? 0u : __float_as_uint(xv[j] - __uint_as_float(h));
+            }
+          }
+          if (build_b) {                                               // B lo tile next to the raw one: bn rows x TC_ROW_BYTES
+            const float4* braw = reinterpret_cast<const float4*>(smem_gen + (size_t)s * stage_bytes + b_off);
+            float4* blo = reinterpret_cast<float4*>(smem_gen + (size_t)s * stage_bytes + blo_off);
+            if (bnl == 128) tc_build_lo<8>(braw, blo, t);
+            else if (bnl == 64) tc_build_lo<4>(braw, blo, t);
+            else if (bnl == 32) tc_build_lo<2>(braw, blo, t);
+            else tc_build_lo<1>(braw, blo, t);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (the MMA's reads)
+          }
+          const uint32_t slot = kbg % (uint32_t)nslots;
+          if (kbg >= (uint32_t)nslots) {   // the MMAs that read this slot's previous k-block have retired
+            tc_mbar_wait(&bar_afree[slot], ((kbg / (uint32_t)nslots) - 1u) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          const uint32_t a_hi = lane_addr + slot_col0 + slot * TC_A_SLOT_COLS;
+          tc_tmem_st32(a_hi, hi);
+          tc_tmem_st32(a_hi + 32u, lw);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();   // ONE arrival per warp (128 arrivals per stage on one barrier serialise; across the pair they cost ~25 clk each)
+          if (lane == 0) { if constexpr (NCTA == 2) tc_mbar_arrive_remote(&bar_ready[s], 0); else tc_mbar_arrive(&bar_ready[s]); }
+        } else {
         if (build_a) {                                                 // A tile: 128 rows x TC_ROW_BYTES = 32 * TC_BK float4
           if (flags & TC_A_RELU) tc_build_lo_relu<TC_BK / 4>(const_cast<float4*>(raw), lo, t);
           else tc_build_lo<TC_BK / 4>(raw, lo, t);
         }
         if (build_b) {                                                 // B tile: bn rows x TC_ROW_BYTES
           constexpr int B_OFF4 = TC_A_TILE_BYTES / 16;
-          if (bn == 128) tc_build_lo<TC_BK / 4>(raw + B_OFF4, lo + B_OFF4, t);
-          else if (bn == 64) tc_build_lo<TC_BK / 8>(raw + B_OFF4, lo + B_OFF4, t);
-          else if (TC_BK == 32) tc_build_lo<2>(raw + B_OFF4, lo + B_OFF4, t);
+          if (bnl == 128) tc_build_lo<TC_BK / 4>(raw + B_OFF4, lo + B_OFF4, t);
+          else if (bnl == 64) tc_build_lo<TC_BK / 8>(raw + B_OFF4, lo + B_OFF4, t);
+          else if (bnl * TC_BK == 32 * 32) tc_build_lo<2>(raw + B_OFF4, lo + B_OFF4, t);
           else tc_build_lo<1>(raw + B_OFF4, lo + B_OFF4, t);
         }
-        if (build_a || build_b) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy
-        tc_mbar_arrive(&bar_ready[s]);
+        // generic-proxy stores -> async proxy (the MMAs' operand reads).  The .shared::cta form also for a pair: the unqualified fence
+        // compiles to MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC, and what the other SM's MMA reads is this CTA's shared memory
+        if (build_a || build_b) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) { if constexpr (NCTA == 2) tc_mbar_arrive_remote(&bar_ready[s], 0); else tc_mbar_arrive(&bar_ready[s]); }
+        }
       }
       tc_mbar_wait(&bar_accum, it & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -399,7 +567,7 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
       const bool c_vec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
       const bool m_vec = ((ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
       const bool b_vec = (reinterpret_cast<uintptr_t>(bias) & 15u) == 0;
-      const int n_hh = min(3, (nk + TC_KB_PER_32 - 1) / TC_KB_PER_32);   // hi.hi accumulators that were written
+      const int n_hh = min(n_hh_max, (nk + TC_KB_PER_32 - 1) / TC_KB_PER_32);   // hi.hi accumulators that were written (the corrections follow the n_hh_max)
       const int sub = lane >> 3, c4 = (lane & 7) * 4;
       const bool split = L.p[pi].splitk > 1;   // partial sums: added into the zeroed C; the bias rides on the first k-range
       if (split && kb0 > 0) bias = nullptr;
@@ -433,7 +601,7 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
           else { for (int j = 0; j < 4; ++j) if (col + j < N) bz[j] = __ldg(bias + col + j); }
         }
         float v[32], u[32];
-        tc_tmem_ld32(lane_addr + (uint32_t)(3 * bn + cb), v);   // correction chains first (smallest terms)
+        tc_tmem_ld32(lane_addr + (uint32_t)(n_hh_max * bn + cb), v);   // correction chains first (smallest terms)
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         for (int a = n_hh - 1; a >= 0; --a) {
           tc_tmem_ld32(lane_addr + (uint32_t)(a * bn + cb), u);
@@ -501,13 +669,16 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
         __syncwarp();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      tc_mbar_arrive(&bar_tmem_empty);
+      __syncwarp();
+      if (lane == 0) { if constexpr (NCTA == 2) tc_mbar_arrive_remote(&bar_tmem_empty, 0); else tc_mbar_arrive(&bar_tmem_empty); }
     }
   }
 }
 
 // ring_bn: B-tile rows the ring geometry is laid out for (>= every problem's bn); total: tiles of the whole group
+template <bool TS, int NCTA>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __restrict__ descs, const __grid_constant__ TcLaunch L) {
+  static_assert(!TS || TC_BK == 32, "the TS form reads SWIZZLE_128B rows");
   fb_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   __shared__ __align__(16) float epi_scratch[4 * 32 * TC_EPI_LD];
@@ -516,23 +687,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
   const int warp = threadIdx.x >> 5;
   const uint32_t smem_base = (tc_smem_u32(tc_smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = tc_smem_raw + (smem_base - tc_smem_u32(tc_smem_raw));
+  const uint32_t rank = NCTA == 2 ? tc_cluster_rank() : 0u;
 
-  if (threadIdx.x == 0) tc_init_barriers(&sh, false);
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sh.tmem_base)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (threadIdx.x == 0) tc_init_barriers(&sh, false, NCTA);
+  if (warp == 1) {   // (a pair allocates the same columns in both CTAs: the same warp of each issues the cta_group::2 form)
+    if constexpr (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sh.tmem_base)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sh.tmem_base)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (NCTA == 2) tc_cluster_sync();   // the partner's barriers are initialised before anything arrives on them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   fb_pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
-  tc_gemm_roles(descs, L, blockIdx.x, gridDim.x, &sh, epi_scratch, smem_base, smem_gen);
+  tc_gemm_roles<TS, NCTA>(descs, L, (int)(blockIdx.x / NCTA), (int)(gridDim.x / NCTA), &sh, epi_scratch, smem_base, smem_gen, rank);
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (NCTA == 2) tc_cluster_sync();   // neither CTA leaves (or frees tensor memory) while the pair's MMAs / commits can still touch it
+  else __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh.tmem_base), "r"(512) : "memory");
+    if constexpr (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(sh.tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh.tmem_base), "r"(512) : "memory");
   }
 }
 

@@ -1309,47 +1309,36 @@ __global__ void __launch_bounds__(256) k_metric_rows(const float* __restrict__ F
   }
 }
 
-// eye_diff = B^T B / n - I  (Z x Z): block a computes row a; its 8 warps each take every 8th batch row (lane = column b,
-// coalesced), partial rows are summed through shared memory; linf via atomicMax on the float bits (values >= 0)
-__global__ void __launch_bounds__(256) k_metric_cov(const float* __restrict__ Bm, int ldb, int rows, int Z, double* acc,
-                                                    unsigned int* linf_bits) {
+// cov += B_chunk^T B_chunk for a chunk of FB_COV_ROWS batch rows (B^T B of the whole batch = the sum over the chunks; Z x Z fp32,
+// zeroed by the phase's memset): the chunk is staged in shared memory, thread t forms outputs t, t + 256, ... (a, b) = (idx / Z,
+// idx % Z) and adds them with one atomic each.  (The first version gave one CTA per ROW of the covariance and walked the whole batch
+// in each: 50 CTAs, 115 us at batch 1024.)  eye_diff = cov / n - I and its norms are taken by k_metric_final.
+#define FB_COV_ROWS 64
+__global__ void __launch_bounds__(256) k_metric_cov(const float* __restrict__ Bm, int ldb, int rows, int Z, float* __restrict__ cov, int chunk) {
   fb_pdl_trigger();
   fb_pdl_wait();
-  __shared__ float part[8][128];
-  const int a = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float mx = 0.f, sq = 0.f;
-  for (int b0 = 0; b0 < Z; b0 += 128) {   // 128 columns per pass (one pass for z_dim <= 128)
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = warp; r < rows; r += 8) {
-      const float* row = Bm + (size_t)r * ldb;
-      const float va = __ldg(row + a);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int b = b0 + j * 32 + lane;
-        if (b < Z) s[j] = fmaf(va, __ldg(row + b), s[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) part[warp][j * 32 + lane] = s[j];
-    __syncthreads();
-    if (threadIdx.x < 128) {
-      const int b = b0 + threadIdx.x;
-      if (b < Z) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
-        const float e = t / (float)rows - (a == b ? 1.f : 0.f);
-        mx = fmaxf(mx, fabsf(e)); sq += e * e;
-      }
-    }
-    __syncthreads();
+  extern __shared__ float cov_tile[];   // [chunk][Z + 1], chunk <= FB_COV_ROWS (fewer for a very wide z: 48 KB of shared memory)
+  const int r0 = blockIdx.x * chunk, nr = min(chunk, rows - r0), zp = Z + 1;
+  for (int i = threadIdx.x; i < nr * Z; i += blockDim.x) {
+    const int r = i / Z, c = i - r * Z;
+    cov_tile[r * zp + c] = Bm[(size_t)(r0 + r) * ldb + c];
   }
-  mx = warp_max(mx); sq = warp_sum(sq);
-  if (lane == 0 && warp < 4) { atomicMax(linf_bits, __float_as_uint(mx)); atomicAdd(acc + ACC_ORTH_SQ, (double)sq); }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < Z * Z; idx += blockDim.x) {
+    const int a = idx / Z, b = idx - a * Z;
+    float s0 = 0.f, s1 = 0.f;
+    int r = 0;
+    for (; r + 1 < nr; r += 2) {
+      s0 = fmaf(cov_tile[r * zp + a], cov_tile[r * zp + b], s0);
+      s1 = fmaf(cov_tile[(r + 1) * zp + a], cov_tile[(r + 1) * zp + b], s1);
+    }
+    if (r < nr) s0 = fmaf(cov_tile[r * zp + a], cov_tile[r * zp + b], s0);
+    atomicAdd(cov + idx, s0 + s1);
+  }
 }
 
 struct MetricFinalParams {
-  const double* acc; const unsigned int* linf_bits; float* out;
+  const double* acc; const float* cov; float* out;   // cov: B^T B of the (global) batch, Z x Z (k_metric_cov)
   int n_local, n_global, Z; float ortho_coef;
   float q_loss_coef;   // 0 when cfg.q_loss is off (the accumulator then stays 0)
   float temp;          // cfg.boltzmann: actor_loss = mean(temp * log pi - Q) (fb_ddpg.py:406); 0 otherwise
@@ -1358,7 +1347,17 @@ struct MetricFinalParams {
 __global__ void k_metric_final(MetricFinalParams P) {
   fb_pdl_trigger();
   fb_pdl_wait();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  // eye_diff = B^T B / n - I: its max-norm and Frobenius norm (fb_ddpg.py:366-370), one warp over the Z x Z entries
+  float mx = 0.f;
+  double sq = 0.0;
+  for (int idx = threadIdx.x; idx < P.Z * P.Z; idx += 32) {
+    const int a = idx / P.Z, b = idx - a * P.Z;
+    const float e = P.cov[idx] / (float)P.n_global - (a == b ? 1.f : 0.f);
+    mx = fmaxf(mx, fabsf(e)); sq += (double)(e * e);
+  }
+  mx = warp_max(mx); sq = warp_sum_d(sq);
+  if (threadIdx.x != 0) return;
   const double n = (double)P.n_global, nl = (double)P.n_local;
   const double noff = n * (n - 1.0);
   const double fb_off = 0.5 * P.acc[ACC_OFFDIAG_SQ] / noff;
@@ -1380,8 +1379,8 @@ __global__ void k_metric_final(MetricFinalParams P) {
   o[9] = (float)orth;
   o[10] = (float)orth_diag;
   o[11] = (float)orth_off;
-  o[12] = __uint_as_float(*P.linf_bits);
-  o[13] = (float)(sqrt(P.acc[ACC_ORTH_SQ]) / sqrt((double)P.Z));
+  o[12] = mx;
+  o[13] = (float)(sqrt(sq) / sqrt((double)P.Z));
   o[14] = (float)(((double)P.temp * P.acc[ACC_LOGPROB] - P.acc[ACC_Q]) / n);
   o[15] = (float)(P.acc[ACC_Q] / n);
   o[16] = (float)(P.acc[ACC_LOGPROB] / n);

@@ -95,6 +95,7 @@ struct fb_handle {
   size_t contract_smem = 0;  // dynamic shared memory of k_contract_tc (0: SIMT contraction)
   size_t qloss_smem = 0;     // dynamic shared memory of k_qloss_inverse (0: cfg.q_loss off)
   bool uses_gemm_tc = false;
+  bool uses_pairs = false;   // some GEMM launch of the plan is a CTA-pair (cta_group::2) launch: no fused (k_fused_stack) execution
   // Operands whose source is final before the consuming phase starts (weights, activations of earlier phases) are staged
   // (aligned / transposed copies, pre-split lo planes, zero fills) on a staging lane, as early as their source allows: an
   // entry of phase P with availability a is launched at the start of the first phase >= a of the running mask, so that the

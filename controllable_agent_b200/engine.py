@@ -93,7 +93,8 @@ class FBStepEngine:
                         future_ratio=cfg.future_ratio,
                         beta1=cfg.beta1, beta2=cfg.beta2, adam_eps=cfg.adam_eps, seed=cfg.seed,
                         q_loss=int(cfg.q_loss), q_loss_coef=cfg.q_loss_coef, no_norm_z=int(not cfg.norm_z), rand_weight=int(cfg.rand_weight), add_trunk=int(cfg.add_trunk), no_preprocess=int(not cfg.preprocess),
-                        boltzmann=int(cfg.boltzmann), temp=float(cfg.temp), log_std_min=float(cfg.log_std_bounds[0]), log_std_max=float(cfg.log_std_bounds[1]))
+                        boltzmann=int(cfg.boltzmann), temp=float(cfg.temp), log_std_min=float(cfg.log_std_bounds[0]), log_std_max=float(cfg.log_std_bounds[1]),
+                        fused_stacks=int(bool(cfg.fused)))
         h = C.c_void_p()
         L.check(self.lib.fb_create(C.byref(c), C.byref(h)), "fb_create")
         self.h = h
@@ -332,6 +333,37 @@ class FBStepEngine:
             put(o[7], future_obs, c.obs_dim)
             if c.use_goal:
                 put(o[8], future_goal, c.goal_dim)
+        L.check(self.lib.fb_upload_batch(self.h, self._row_stage[slot].data_ptr(), self._row_pitch, self._stream()), "fb_upload_batch")
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._row_events[slot] = ev
+        return 4 * c.batch * self._row_pitch
+
+    @_on_device
+    def upload_host_rows(self, host: tp.Any, ep_idx: np.ndarray, step_idx: np.ndarray, future_idx: tp.Optional[np.ndarray],
+                         replay_discount: float) -> int:
+        """ReplayBuffer.sample's gathers + EpisodeBatch.to for a reference-layout HOST replay (replay.HostStorageView): the library
+        copies the sampled rows of the host storage straight into the pinned block (fb_host_gather_rows), one asynchronous
+        host-to-device copy follows.  Returns the bytes copied."""
+        c = self.cfg
+        if self._row_stage is None:
+            self._row_stage = torch.zeros((2, c.batch, self._row_pitch), dtype=torch.float32).pin_memory()
+        slot = self._row_slot
+        self._row_slot ^= 1
+        if self._row_events[slot] is not None:
+            self._row_events[slot].synchronize()   # the copy that last read this block has completed
+        want_future = c.future_ratio > 0
+        if want_future and future_idx is None:
+            raise ValueError("future_ratio > 0 needs a replay buffer created with future < 1 (it samples no future_obs / future_goal)")
+        if bool(c.use_goal) != bool(host.c.goal):
+            raise ValueError("agent.goal_space and the replay's `goal` storage disagree")
+        ep = np.ascontiguousarray(ep_idx, dtype=np.int32)
+        st = np.ascontiguousarray(step_idx, dtype=np.int32)
+        fu = np.ascontiguousarray(future_idx, dtype=np.int32) if want_future else None
+        assert ep.shape[0] == c.batch and st.shape[0] == c.batch
+        L.check(self.lib.fb_host_gather_rows(C.byref(host.c), ep.ctypes.data, st.ctypes.data, fu.ctypes.data if fu is not None else None,
+                                             c.batch, float(replay_discount), self._row_stage[slot].data_ptr(), self._row_pitch),
+                "fb_host_gather_rows")
         L.check(self.lib.fb_upload_batch(self.h, self._row_stage[slot].data_ptr(), self._row_pitch, self._stream()), "fb_upload_batch")
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))

@@ -127,6 +127,78 @@ def _round4(x: int) -> int:
     return (x + 3) // 4 * 4
 
 
+def draw_sample_indices(replay: tp.Any, batch_size: int) -> tp.Tuple[np.ndarray, np.ndarray, tp.Optional[np.ndarray]]:
+    """(episode, step, future step) indices of one sampled batch: the draws of in_memory_replay_buffer.py:141-161 on the numpy GLOBAL
+    generator, call for call, for any object with that class's attributes (this package's ReplayBuffer, the reference's own)."""
+    if not isinstance(replay._future, float):
+        assert isinstance(replay._future, bool)
+        replay._future = float(replay._future)
+    if replay._is_fixed_episode_length:
+        ep_idx = np.random.randint(0, len(replay), size=batch_size)
+    else:
+        if replay._episodes_selection_probability is None:
+            replay._episodes_selection_probability = replay._episodes_length / replay._episodes_length.sum()
+        ep_idx = np.random.choice(np.arange(len(replay._episodes_length)), size=batch_size, p=replay._episodes_selection_probability)
+    eps_lengths = replay._episodes_length[ep_idx]
+    step_idx = np.random.randint(0, eps_lengths) + 1
+    assert (step_idx <= eps_lengths).all()
+    future_idx = None
+    if replay._future < 1:
+        future_idx = step_idx + np.random.geometric(p=(1 - replay._future), size=batch_size)
+        future_idx = np.clip(future_idx, 0, eps_lengths)
+        assert (future_idx <= eps_lengths).all()
+    return ep_idx, step_idx, future_idx
+
+
+class HostStorageView:
+    """A replay buffer that lives in HOST memory in the reference's layout (url_benchmark.in_memory_replay_buffer.ReplayBuffer, or any
+    object carrying its attributes: `_storage` name -> fp32 [max_episodes, T + 1, dim], `_episodes_length`, `_discount`, `_future`, ...)
+    as the C ABI sees it (fb_host_storage).  `agent.update(replay, step)` samples such a buffer without going through its Python
+    `sample()`: the index draws are the reference's (draw_sample_indices, same numpy RNG stream), the row gathers run in the library
+    (fb_host_gather_rows) straight into the pinned block that crosses PCIe."""
+    FIELDS = ("observation", "action", "discount")
+
+    def __init__(self, replay: tp.Any) -> None:
+        st = replay._storage
+        self.replay = replay
+        self.arrays = {k: st[k] for k in ("observation", "action", "reward", "discount", "goal") if k in st}   # keeps them alive
+        E, R = self.arrays["observation"].shape[:2]
+        ptr = lambda k: self.arrays[k].ctypes.data if k in self.arrays else None  # noqa: E731
+        self.c = L.fb_host_storage(observation=ptr("observation"), action=ptr("action"), reward=ptr("reward"), discount=ptr("discount"),
+                                   goal=ptr("goal"), rows_per_episode=R, obs_dim=self.arrays["observation"].shape[2],
+                                   action_dim=self.arrays["action"].shape[2],
+                                   goal_dim=self.arrays["goal"].shape[2] if "goal" in self.arrays else 0)
+        self.key = tuple((k, v.ctypes.data, v.shape) for k, v in self.arrays.items())
+
+    @classmethod
+    def adopt(cls, replay: tp.Any) -> tp.Optional["HostStorageView"]:
+        """The view of `replay` if it is a reference-layout host buffer the library can read in place, else None (the caller then
+        falls back to the object's own sample())."""
+        st = getattr(replay, "_storage", None)
+        need = ("_episodes_length", "_discount", "_future", "_is_fixed_episode_length", "_episodes_selection_probability")
+        if not isinstance(st, dict) or not all(hasattr(replay, a) for a in need) or not hasattr(replay, "__len__"):
+            return None
+        if not all(k in st for k in cls.FIELDS):
+            return None
+        shape = None
+        for k in ("observation", "action", "reward", "discount", "goal"):
+            v = st.get(k)
+            if v is None:
+                continue
+            if not (isinstance(v, np.ndarray) and v.dtype == np.float32 and v.ndim == 3 and v.flags["C_CONTIGUOUS"]):
+                return None
+            if shape is not None and v.shape[:2] != shape:
+                return None
+            shape = v.shape[:2]
+            if k in ("reward", "discount") and v.shape[2] != 1:
+                return None
+        return cls(replay)
+
+    def still_valid(self) -> bool:
+        st = self.replay._storage
+        return all(k in st and st[k].ctypes.data == p and st[k].shape == shp for k, p, shp in self.key)
+
+
 class ReplayBuffer:
     """Drop-in for in_memory_replay_buffer.ReplayBuffer(max_episodes, discount, future, max_episode_length)."""
 
@@ -393,24 +465,7 @@ class ReplayBuffer:
     # -- sampling --------------------------------------------------------------------------------
     def draw_indices(self, batch_size: int) -> tp.Tuple[np.ndarray, np.ndarray, tp.Optional[np.ndarray]]:
         """The index draws of in_memory_replay_buffer.py:146-161 on the numpy GLOBAL RNG, in the same order."""
-        if not isinstance(self._future, float):
-            assert isinstance(self._future, bool)
-            self._future = float(self._future)
-        if self._is_fixed_episode_length:
-            ep_idx = np.random.randint(0, len(self), size=batch_size)
-        else:
-            if self._episodes_selection_probability is None:
-                self._episodes_selection_probability = self._episodes_length / self._episodes_length.sum()
-            ep_idx = np.random.choice(np.arange(len(self._episodes_length)), size=batch_size, p=self._episodes_selection_probability)
-        eps_lengths = self._episodes_length[ep_idx]
-        step_idx = np.random.randint(0, eps_lengths) + 1
-        assert (step_idx <= eps_lengths).all()
-        future_idx = None
-        if self._future < 1:
-            future_idx = step_idx + np.random.geometric(p=(1 - self._future), size=batch_size)
-            future_idx = np.clip(future_idx, 0, eps_lengths)
-            assert (future_idx <= eps_lengths).all()
-        return ep_idx, step_idx, future_idx
+        return draw_sample_indices(self, batch_size)
 
     def view(self) -> "L.fb_replay_view":
         """The C-ABI description of the device storage (fb_replay_view, include/fb_b200.h)."""

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 4
+#define FB_ABI_VERSION 5
 
 enum {
   FB_OK = 0,
@@ -138,6 +138,9 @@ typedef struct fb_config {
                                   actions are tanh of a Normal(mu, std) sample and the actor loss is mean(temp * log pi - Q) */
   float temp;                  /* cfg.temp */
   float log_std_min, log_std_max; /* cfg.log_std_bounds */
+  int32_t fused_stacks;        /* the handle will be run WITHOUT FB_RUN_UNFUSED (k_fused_stack segments): its GEMM launches are then planned
+                                  for single CTAs.  0 (default): wide GEMM groups run on CTA pairs (tcgen05 cta_group::2) and fused
+                                  execution of such a plan is refused with FB_E_STATE */
 } fb_config;
 
 /* per-step scalars (host values; copied to the device by fb_set_step_scalars) */
@@ -245,6 +248,18 @@ int fb_p2p_slice(const fb_handle* h, int actor, size_t* first, size_t* count);
  * [| future_obs | future_goal].  The copy is enqueued
  * on `stream`; the caller keeps h_rows alive until it has completed. */
 int fb_upload_batch(fb_handle* h, const float* h_rows, int pitch, void* stream);
+/* A replay buffer that lives in HOST memory in the reference's own layout (in_memory_replay_buffer.py:66-88,126: `_storage`
+ * name -> C-contiguous fp32 [max_episodes, rows_per_episode, dim]); `goal` may be NULL. */
+typedef struct fb_host_storage {
+  const float* observation; const float* action; const float* reward; const float* discount; const float* goal;
+  int32_t rows_per_episode, obs_dim, action_dim, goal_dim;
+} fb_host_storage;
+/* ReplayBuffer.sample's gathers (in_memory_replay_buffer.py:162-183) for host storage, straight into the packed rows fb_upload_batch
+ * takes (h_rows [batch, pitch], fb_batch_row_layout(obs, action, goal_dim or 0, 0, h_future_idx != NULL) order): row i reads
+ * (episode h_ep_idx[i], steps h_step_idx[i] - 1 and h_step_idx[i], future step h_future_idx[i] - 1), discount times
+ * replay_discount.  Runs on the calling thread's cores (software-prefetched row copies; no device work). */
+int fb_host_gather_rows(const fb_host_storage* st, const int32_t* h_ep_idx, const int32_t* h_step_idx, const int32_t* h_future_idx,
+                        int batch, float replay_discount, float* h_rows, int pitch);
 /* rng_device == 0, future_ratio > 0: the hindsight row mask of fb_ddpg.py:490 ([batch] int32, non-zero = hindsight z) */
 int fb_set_future_mask(fb_handle* h, const int32_t* d_future_mask, void* stream);
 /* rng_device == 0, rand_weight = 1: the U(0,1) draws of fb_ddpg.py:477,479 as a [batch, batch] block (row s = the weight row of

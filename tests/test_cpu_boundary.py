@@ -297,3 +297,66 @@ def test_episode_batch_collate_to_and_reward_masking():
     mixed = EpisodeBatch(reward=np.array([1.0]), discount=np.array([0.5]), goal=np.zeros(3), **{x: np.random.rand(*y) for x, y in shapes.items()})
     with pytest.raises(RuntimeError, match="mixed with Nones"):
         EpisodeBatch.collate_fn([batch, mixed])
+
+
+class _RefLayoutHostReplay:
+    """Attribute layout of url_benchmark.in_memory_replay_buffer.ReplayBuffer (:66-88) with a filled `_storage`."""
+
+    def __init__(self, rs, E, T, O, A, G, future, ragged=False):
+        self._max_episodes, self._discount, self._future = E, 0.98, future
+        self._storage = {"observation": rs.standard_normal((E, T + 1, O)).astype(np.float32), "action": rs.random((E, T + 1, A)).astype(np.float32),
+                         "reward": rs.random((E, T + 1, 1)).astype(np.float32), "discount": (rs.random((E, T + 1, 1)) > 0.1).astype(np.float32),
+                         "physics": np.zeros((E, T + 1, 3), np.float32)}
+        if G:
+            self._storage["goal"] = rs.standard_normal((E, T + 1, G)).astype(np.float32)
+        self._episodes_length = np.full(E, T, np.int32)
+        if ragged:
+            self._episodes_length = rs.integers(2, T + 1, size=E).astype(np.int32)
+        self._is_fixed_episode_length, self._episodes_selection_probability = not ragged, None
+        self._idx, self._full = 0, True
+
+    def __len__(self):
+        return self._max_episodes
+
+
+@pytest.mark.parametrize("G,future,ragged", [(0, 1.0, False), (3, 1.0, False), (0, 0.9, True), (2, 0.8, False)])
+def test_host_gather_rows_matches_reference_sample_gathers(G, future, ragged):
+    """fb_host_gather_rows = the fancy-index gathers of in_memory_replay_buffer.py:162-183 on host storage, written in the packed
+    batch-row layout; HostStorageView + draw_sample_indices reproduce the reference's index draws (no GPU involved)."""
+    from controllable_agent_b200.replay import HostStorageView, draw_sample_indices
+    L, lib = _lib()
+    rs = np.random.default_rng(5)
+    E, T, O, A, B = 7, 19, 11, 3, 64
+    rep = _RefLayoutHostReplay(rs, E, T, O, A, G, future, ragged)
+    view = HostStorageView.adopt(rep)
+    assert view is not None and view.still_valid()
+    np.random.seed(3)
+    ep, st, fu = draw_sample_indices(rep, B)
+    assert (fu is None) == (future >= 1.0) and st.min() >= 1 and (st <= rep._episodes_length[ep]).all()
+    offs, pitch = (C.c_int32 * 9)(), C.c_int32()
+    assert lib.fb_batch_row_layout(O, A, G, 0, int(fu is not None), offs, C.byref(pitch)) == 0
+    rows = np.full((B, pitch.value), np.nan, np.float32)
+    i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)  # noqa: E731
+    ep32, st32, fu32 = i32(ep), i32(st), (i32(fu) if fu is not None else None)
+    rc = lib.fb_host_gather_rows(C.byref(view.c), ep32.ctypes.data, st32.ctypes.data, fu32.ctypes.data if fu32 is not None else None, B,
+                                 0.98, rows.ctypes.data, pitch.value)
+    assert rc == 0
+    S = rep._storage
+    np.testing.assert_array_equal(rows[:, offs[0]:offs[0] + O], S["observation"][ep, st - 1])
+    np.testing.assert_array_equal(rows[:, offs[1]:offs[1] + A], S["action"][ep, st])
+    np.testing.assert_array_equal(rows[:, offs[2]], S["reward"][ep, st][:, 0])
+    np.testing.assert_array_equal(rows[:, offs[2] + 1], (np.float32(0.98) * S["discount"][ep, st])[:, 0])
+    np.testing.assert_array_equal(rows[:, offs[3]:offs[3] + O], S["observation"][ep, st])
+    if G:
+        np.testing.assert_array_equal(rows[:, offs[4]:offs[4] + G], S["goal"][ep, st - 1])
+        np.testing.assert_array_equal(rows[:, offs[5]:offs[5] + G], S["goal"][ep, st])
+    if fu is not None:
+        np.testing.assert_array_equal(rows[:, offs[7]:offs[7] + O], S["observation"][ep, fu - 1])
+        if G:
+            np.testing.assert_array_equal(rows[:, offs[8]:offs[8] + G], S["goal"][ep, fu - 1])
+    # out-of-range steps are refused, not read
+    bad = st32.copy(); bad[0] = 0
+    assert lib.fb_host_gather_rows(C.byref(view.c), ep32.ctypes.data, bad.ctypes.data, None, B, 0.98, rows.ctypes.data, pitch.value) == -1
+    # a storage the library cannot read in place (float64 field) is not adopted: the caller falls back to the object's sample()
+    rep._storage["action"] = rep._storage["action"].astype(np.float64)
+    assert HostStorageView.adopt(rep) is None and not view.still_valid()

@@ -342,6 +342,49 @@ def test_agent_host_replay_with_device_rng():
         assert agent.engine.launch_count(L.PHASE_ALL | L.RUN_HOST_BATCH) == agent.engine.launch_count(L.PHASE_ALL) - 1
 
 
+@pytest.mark.parametrize("goal_space,G,future", [(None, 0, 1.0), ("simplified_walker", 3, 0.9)])
+def test_agent_samples_reference_layout_host_replay_natively(goal_space, G, future):
+    """A host buffer with the reference ReplayBuffer's attribute layout (in_memory_replay_buffer.py:66-88) is sampled without its
+    Python sample(): index draws in the reference's order on the numpy generator, row gathers by fb_host_gather_rows into the pinned
+    block.  The rows that land on the device are exactly what its own sample() would have returned for the same generator state."""
+    from controllable_agent_b200 import EpisodeBatch, FBDDPGAgent, _lib as L
+    from test_cpu_boundary import _RefLayoutHostReplay
+    B, O_, A_, Z = 64, 24, 6, 50
+    rep = _RefLayoutHostReplay(np.random.default_rng(2), 9, 30, O_, A_, G, future)
+
+    def ref_sample(n):   # what in_memory_replay_buffer.py:139-190 returns for these attributes
+        from controllable_agent_b200.replay import draw_sample_indices
+        ep, st, fu = draw_sample_indices(rep, n)
+        S = rep._storage
+        return EpisodeBatch(obs=S["observation"][ep, st - 1], action=S["action"][ep, st], reward=S["reward"][ep, st],
+                            discount=rep._discount * S["discount"][ep, st], next_obs=S["observation"][ep, st],
+                            goal=S["goal"][ep, st - 1] if G else None, next_goal=S["goal"][ep, st] if G else None,
+                            future_obs=S["observation"][ep, fu - 1] if fu is not None else None,
+                            future_goal=S["goal"][ep, fu - 1] if (fu is not None and G) else None)
+    rep.sample = ref_sample
+    torch.manual_seed(5)
+    agent = FBDDPGAgent(obs_type="states", obs_shape=(O_,), action_shape=(A_,), device="cuda", num_expl_steps=0, update_encoder=True,
+                        goal_space=goal_space, use_tb=True, use_wandb=True, use_hiplog=False, batch_size=B, update_every_steps=1,
+                        hidden_dim=256, feature_dim=128, backward_hidden_dim=134, future_ratio=0.3 if future < 1 else 0.0)
+    for step in range(4):
+        agent.native_host_sampling = step % 2 == 0   # alternate: library gather / the object's own sample()
+        agent.cfg.prefetch_host_batch = False
+        state = np.random.get_state()
+        m = agent.update(rep, step)
+        after = np.random.get_state()
+        np.random.set_state(state)
+        want = ref_sample(B)                          # the batch the reference would have drawn from the same generator state
+        np.random.set_state(after)
+        e = agent.engine
+        assert torch.equal(e.view("actor_in_o")[B:].cpu(), torch.from_numpy(want.obs))
+        assert torch.equal(e.view("actor_in_o")[:B].cpu(), torch.from_numpy(want.next_obs))
+        assert torch.equal(e.view("in_oa")[:, O_:].cpu(), torch.from_numpy(want.action))
+        assert torch.equal(e.view("discount").cpu(), torch.from_numpy(want.discount.astype(np.float32)))
+        assert torch.equal(e.view("next_goal").cpu(), torch.from_numpy(want.next_goal if G else want.next_obs))
+        assert all(np.isfinite(v) for v in m.values()) and m["z_norm"] == pytest.approx(np.sqrt(Z), rel=1e-4)
+    assert agent.engine.get_adam_steps() == (4, 4)
+
+
 @pytest.mark.parametrize("goal_space,G,add_trunk", [(None, 24, False), ("simplified_walker", 3, False), (None, 24, True)])
 def test_inference_plans_match_the_module_forward(goal_space, G, add_trunk):
     """act / get_goal_meta / compute_z_correl / infer_meta_from_obs_and_rewards run through the library's inference plans

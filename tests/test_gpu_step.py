@@ -45,7 +45,8 @@ def test_sgemm_against_float64(M, N, K, ak, bk, relu, splitk, tile_cfg):
 @pytest.mark.parametrize("M,N,K,bk,relu", [
     (128, 128, 32, 1, 0), (128, 128, 64, 1, 0), (256, 128, 128, 1, 1), (1024, 512, 1024, 1, 1), (200, 150, 72, 1, 1), (96, 50, 128, 1, 0),
     (1024, 6, 1024, 1, 0), (300, 528, 528, 0, 0), (130, 8, 48, 0, 0), (257, 129, 1028, 1, 0), (64, 64, 8, 1, 0), (2048, 1024, 1024, 0, 0)])
-def test_sgemm_tcgen05_3xtf32_against_float64(M, N, K, bk, relu):
+@pytest.mark.parametrize("pairs", [False, True])   # True: CTA pairs (tcgen05 cta_group::2, 256-row work items)
+def test_sgemm_tcgen05_3xtf32_against_float64(M, N, K, bk, relu, pairs):
     """The tensor-core GEMM (gemm_tc.cuh) holds fp32-grade accuracy: rel err vs float64 at the level of the SIMT fp32 kernel."""
     L = _L()
     lib = L.load()
@@ -61,7 +62,7 @@ def test_sgemm_tcgen05_3xtf32_against_float64(M, N, K, bk, relu):
     dC = torch.zeros(M, ldc, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     L.check(lib.fb_sgemm(dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), dbias.data_ptr(), M, N, K, A.shape[1], Bm.shape[1], ldc,
-                         1, bk, relu, 1, 3, s))
+                         1, bk, relu, 1, 4 if pairs else 3, s))
     torch.cuda.synchronize()
     err = rel(dC[:, :N], ref)
     print(f"tcgen05 3xTF32 M={M} N={N} K={K}: rel err vs float64 {err:.2e}")
@@ -71,7 +72,8 @@ def test_sgemm_tcgen05_3xtf32_against_float64(M, N, K, bk, relu):
 
 @pytest.mark.parametrize("M,N,K,bk,splitk", [(1024, 50, 1024, 1, 4), (2048, 6, 1024, 0, 8), (50, 1024, 1024, 1, 3), (257, 129, 1028, 1, 5),
                                               (128, 128, 64, 1, 2), (1024, 512, 2048, 0, 2)])
-def test_sgemm_tcgen05_split_k(M, N, K, bk, splitk):
+@pytest.mark.parametrize("pairs", [False, True])
+def test_sgemm_tcgen05_split_k(M, N, K, bk, splitk, pairs):
     """split-K of the tensor-core GEMM: every k-range adds its partial tile into a zeroed C (the bias rides on the first)."""
     L = _L()
     lib = L.load()
@@ -85,12 +87,12 @@ def test_sgemm_tcgen05_split_k(M, N, K, bk, splitk):
     dC = torch.zeros(M, ldc, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     L.check(lib.fb_sgemm(dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), dbias.data_ptr(), M, N, K, A.shape[1], Bm.shape[1], ldc,
-                         1, bk, 0, splitk, 3, s))
+                         1, bk, 0, splitk, 4 if pairs else 3, s))
     torch.cuda.synchronize()
     assert rel(dC[:, :N], ref) < 1e-5
     assert float(dC[:, N:].abs().max()) == 0.0 if ldc > N else True
     assert lib.fb_sgemm(dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), dbias.data_ptr(), M, N, K, A.shape[1], Bm.shape[1], ldc,
-                        1, bk, 1, splitk, 3, s) != 0      # a ReLU epilogue cannot be split
+                        1, bk, 1, splitk, 4 if pairs else 3, s) != 0      # a ReLU epilogue cannot be split
 
 
 def _run_update_case(g, d, use_goal, graph, mlp_mode=0, fused=False):
@@ -578,9 +580,9 @@ def test_p2p_exchange_ranks_on_one_device(world, graph):
     status = [e.p2p_status() for e in shards]
     assert all(code == 0 for code, _ in status), [(hex(c), ep) for c, ep in status]
     for r, e in enumerate(shards):
-        assert rel(e.param_fb, ref["param_fb"]) < 2e-6, r
-        assert rel(e.param_actor, ref["param_actor"]) < 2e-6, r
-        assert rel(e.target_fb, ref["target_fb"]) < 2e-6, r
+        assert rel(e.param_fb, ref["param_fb"]) < 5e-6, r   # (split-K partial sums land in atomic order: ulp-level gradient noise, times Adam)
+        assert rel(e.param_actor, ref["param_actor"]) < 5e-6, r
+        assert rel(e.target_fb, ref["target_fb"]) < 5e-6, r
         assert float(e.grad_fb.abs().max()) == 0.0 and float(e.grad_actor.abs().max()) == 0.0   # cleared for the next step
         assert e.get_adam_steps() == (2, 2)
     for r in range(1, world):   # the ranks hold the SAME bits: one owner computes each slice

@@ -9,10 +9,10 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from controllable_agent_b200 import _lib as L  # noqa: E402
 
-NOBUILD, ONECHAIN, NOEPI, PRE_B, PRE_A = 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20
+NOBUILD, ONECHAIN, NOEPI, PRE_B, PRE_A, PAIR = 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20, 1 << 22
 
 
-def main() -> None:
+def main(pair: int = 0) -> None:
     lib = L.load()
     s = torch.cuda.current_stream().cuda_stream
     ms = C.c_float()
@@ -21,11 +21,11 @@ def main() -> None:
     for (M, N, K, bn, nprob) in shapes:
         row = []
         for dbg in (0, PRE_B, PRE_A | PRE_B, NOBUILD, NOBUILD | ONECHAIN, NOBUILD | ONECHAIN | NOEPI, NOEPI):
-            L.check(lib.fb_gemm_tc_bench(M, N, K, bn, nprob, 1, dbg, 20, C.byref(ms), s))
+            L.check(lib.fb_gemm_tc_bench(M, N, K, bn, nprob, 1, dbg | pair, 20, C.byref(ms), s))
             row.append(ms.value * 1e3)
         fl = 2.0 * M * N * K * nprob
         tiles = -(-M // 128) * -(-N // bn) * nprob
-        print(f"M={M} N={N} K={K} bn={bn} x{nprob} ({tiles} tiles): build A+B {row[0]:7.1f} us ({fl / row[0] / 1e6:6.1f} TF/s) | "
+        print(("pairs " if pair else "") + f"M={M} N={N} K={K} bn={bn} x{nprob} ({tiles} tiles): build A+B {row[0]:7.1f} us ({fl / row[0] / 1e6:6.1f} TF/s) | "
               f"pre-split B {row[1]:7.1f} ({fl / row[1] / 1e6:6.1f}) | pre-split A+B {row[2]:7.1f} ({fl / row[2] / 1e6:6.1f}) | nobuild {row[3]:7.1f} | "
               f"nobuild+1chain {row[4]:7.1f} | +noepi {row[5]:7.1f} | noepi {row[6]:7.1f}", flush=True)
 
@@ -58,6 +58,8 @@ def data_sweep() -> None:
 
 
 if __name__ == "__main__":
-    data_sweep()
-    splitk_sweep()
+    if "--quick" not in sys.argv:
+        data_sweep()
+        splitk_sweep()
     main()
+    main(PAIR)
