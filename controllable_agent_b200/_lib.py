@@ -136,7 +136,7 @@ SIGNATURES: tp.Dict[str, tp.Tuple[tp.Any, tp.List[tp.Any]]] = {
 }
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-ldl"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-ldl", "-lgomp"]
 
 
 def nccl_library_path() -> tp.Optional[bytes]:

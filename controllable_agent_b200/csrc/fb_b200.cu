@@ -1360,7 +1360,7 @@ static int build_plan(fb_handle* h) {
     mp.acc = acc; mp.cov = cov; mp.out = h->d_metrics; mp.n_local = B; mp.n_global = n; mp.Z = Z; mp.ortho_coef = c.ortho_coef;
     mp.q_loss_coef = c.q_loss ? c.q_loss_coef : 0.f;
     mp.temp = bz ? c.temp : 0.f;
-    b.push([mp](cudaStream_t s) { fb_launch_pdl(k_metric_final, dim3(1), dim3(32), 0, s, mp); return cudaGetLastError(); });
+    b.push([mp](cudaStream_t s) { fb_launch_pdl(k_metric_final, dim3(1), dim3(256), 0, s, mp); return cudaGetLastError(); });
   }
 
   // =========================== inference plans ==================================================
@@ -2306,40 +2306,50 @@ int fb_host_gather_rows(const fb_host_storage* st, const int32_t* ep_idx, const 
   make_batch_layout(L, O, A, G, 0, future_idx != nullptr);
   if (pitch < L.pitch || O < 1 || A < 1 || R < 2) return FB_E_ARG;
   auto row = [R](const float* base, int dim, int ep, int t) { return base + ((size_t)ep * R + t) * dim; };
-  // pass 1: touch every source line (the rows are random 100-byte reads of a buffer far larger than the caches: the misses overlap)
-  for (int i = 0; i < batch; ++i) {
-    const int ep = ep_idx[i], t = step_idx[i];
-    if (t < 1 || t >= R) return FB_E_ARG;
-    const float* o0 = row(st->observation, O, ep, t - 1);
-    for (int b = 0; b < 2 * O * 4; b += 64) __builtin_prefetch((const char*)o0 + b);   // rows t-1 and t are adjacent
-    __builtin_prefetch(row(st->action, A, ep, t));
-    __builtin_prefetch(row(st->discount, 1, ep, t));
-    if (st->reward) __builtin_prefetch(row(st->reward, 1, ep, t));
-    if (G) { const float* g0 = row(st->goal, G, ep, t - 1); for (int b = 0; b < 2 * G * 4; b += 64) __builtin_prefetch((const char*)g0 + b); }
-    if (future_idx) {
-      const int f = future_idx[i];
-      if (f < 1 || f > R) return FB_E_ARG;
-      __builtin_prefetch(row(st->observation, O, ep, f - 1));
-      if (G) __builtin_prefetch(row(st->goal, G, ep, f - 1));
-    }
+  for (int i = 0; i < batch; ++i) {   // indices first: nothing is read through a bad one
+    if (ep_idx[i] < 0 || step_idx[i] < 1 || step_idx[i] >= R) return FB_E_ARG;
+    if (future_idx && (future_idx[i] < 1 || future_idx[i] > R)) return FB_E_ARG;
   }
-  for (int i = 0; i < batch; ++i) {
-    const int ep = ep_idx[i], t = step_idx[i];
-    float* out = rows + (size_t)i * pitch;
-    memcpy(out + L.off_obs, row(st->observation, O, ep, t - 1), O * sizeof(float));
-    memcpy(out + L.off_action, row(st->action, A, ep, t), A * sizeof(float));
-    out[L.off_rd + 0] = st->reward ? *row(st->reward, 1, ep, t) : 0.f;
-    out[L.off_rd + 1] = replay_discount * *row(st->discount, 1, ep, t);
-    out[L.off_rd + 2] = 0.f; out[L.off_rd + 3] = 0.f;
-    memcpy(out + L.off_next_obs, row(st->observation, O, ep, t), O * sizeof(float));
-    if (G) {
-      memcpy(out + L.off_goal, row(st->goal, G, ep, t - 1), G * sizeof(float));
-      memcpy(out + L.off_next_goal, row(st->goal, G, ep, t), G * sizeof(float));
+  // The rows are random ~100-byte reads of a buffer far larger than the caches: the copy is bound by how many misses are in flight.
+  // Each worker first touches every source line of its share (the misses overlap), then copies; a few workers multiply the lines
+  // in flight (one core sustains ~12).
+  static const int max_workers = getenv("FB_HOST_GATHER_WORKERS") ? std::max(1, atoi(getenv("FB_HOST_GATHER_WORKERS"))) : 4;
+  const int workers = batch >= 256 ? max_workers : 1;
+#pragma omp parallel for num_threads(workers) schedule(static)
+  for (int w = 0; w < workers; ++w) {
+    const int i0 = (int)((long long)batch * w / workers), i1 = (int)((long long)batch * (w + 1) / workers);
+    for (int i = i0; i < i1; ++i) {
+      const int ep = ep_idx[i], t = step_idx[i];
+      const float* o0 = row(st->observation, O, ep, t - 1);
+      for (int b = 0; b < 2 * O * 4; b += 64) __builtin_prefetch((const char*)o0 + b);   // rows t-1 and t are adjacent
+      __builtin_prefetch(row(st->action, A, ep, t));
+      __builtin_prefetch(row(st->discount, 1, ep, t));
+      if (st->reward) __builtin_prefetch(row(st->reward, 1, ep, t));
+      if (G) { const float* g0 = row(st->goal, G, ep, t - 1); for (int b = 0; b < 2 * G * 4; b += 64) __builtin_prefetch((const char*)g0 + b); }
+      if (future_idx) {
+        const int f = future_idx[i];
+        __builtin_prefetch(row(st->observation, O, ep, f - 1));
+        if (G) __builtin_prefetch(row(st->goal, G, ep, f - 1));
+      }
     }
-    if (future_idx) {
-      const int f = future_idx[i];
-      memcpy(out + L.off_future_obs, row(st->observation, O, ep, f - 1), O * sizeof(float));
-      if (G) memcpy(out + L.off_future_goal, row(st->goal, G, ep, f - 1), G * sizeof(float));
+    for (int i = i0; i < i1; ++i) {
+      const int ep = ep_idx[i], t = step_idx[i];
+      float* out = rows + (size_t)i * pitch;
+      memcpy(out + L.off_obs, row(st->observation, O, ep, t - 1), O * sizeof(float));
+      memcpy(out + L.off_action, row(st->action, A, ep, t), A * sizeof(float));
+      out[L.off_rd + 0] = st->reward ? *row(st->reward, 1, ep, t) : 0.f;
+      out[L.off_rd + 1] = replay_discount * *row(st->discount, 1, ep, t);
+      out[L.off_rd + 2] = 0.f; out[L.off_rd + 3] = 0.f;
+      memcpy(out + L.off_next_obs, row(st->observation, O, ep, t), O * sizeof(float));
+      if (G) {
+        memcpy(out + L.off_goal, row(st->goal, G, ep, t - 1), G * sizeof(float));
+        memcpy(out + L.off_next_goal, row(st->goal, G, ep, t), G * sizeof(float));
+      }
+      if (future_idx) {
+        const int f = future_idx[i];
+        memcpy(out + L.off_future_obs, row(st->observation, O, ep, f - 1), O * sizeof(float));
+        if (G) memcpy(out + L.off_future_goal, row(st->goal, G, ep, f - 1), G * sizeof(float));
+      }
     }
   }
   return FB_OK;

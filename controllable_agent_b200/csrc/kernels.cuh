@@ -1347,17 +1347,23 @@ struct MetricFinalParams {
 __global__ void k_metric_final(MetricFinalParams P) {
   fb_pdl_trigger();
   fb_pdl_wait();
-  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
-  // eye_diff = B^T B / n - I: its max-norm and Frobenius norm (fb_ddpg.py:366-370), one warp over the Z x Z entries
+  if (blockIdx.x != 0) return;
+  // eye_diff = B^T B / n - I: its max-norm and Frobenius norm (fb_ddpg.py:366-370), 256 threads over the Z x Z entries
+  __shared__ float s_mx[8];
+  __shared__ double s_sq[8];
   float mx = 0.f;
   double sq = 0.0;
-  for (int idx = threadIdx.x; idx < P.Z * P.Z; idx += 32) {
+  for (int idx = threadIdx.x; idx < P.Z * P.Z; idx += blockDim.x) {
     const int a = idx / P.Z, b = idx - a * P.Z;
     const float e = P.cov[idx] / (float)P.n_global - (a == b ? 1.f : 0.f);
     mx = fmaxf(mx, fabsf(e)); sq += (double)(e * e);
   }
   mx = warp_max(mx); sq = warp_sum_d(sq);
+  if ((threadIdx.x & 31) == 0) { s_mx[threadIdx.x >> 5] = mx; s_sq[threadIdx.x >> 5] = sq; }
+  __syncthreads();
   if (threadIdx.x != 0) return;
+  mx = 0.f; sq = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { mx = fmaxf(mx, s_mx[w]); sq += s_sq[w]; }
   const double n = (double)P.n_global, nl = (double)P.n_local;
   const double noff = n * (n - 1.0);
   const double fb_off = 0.5 * P.acc[ACC_OFFDIAG_SQ] / noff;
