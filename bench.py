@@ -62,6 +62,7 @@ def parse() -> argparse.Namespace:
     p.add_argument("--no-cuda-eager", action="store_true", help="skip the reference-on-cuda (PyTorch eager) leg")
     p.add_argument("--no-parity-check", action="store_true")
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--timeline", default=None, help="file for rank 0's per-launch table of one step (phase, kind, us; collectives marked)")
     p.add_argument("--collectives", default="auto", choices=["auto", "p2p", "graph", "torch"],
                    help="multi-GPU exchange: p2p = the library's own kernels over NVLink peer memory, graph = NCCL calls captured in the step "
                         "graph on the library's communicator, torch = torch.distributed calls between graph segments; auto = the agent's default")
@@ -474,8 +475,31 @@ def run_ours(a: argparse.Namespace) -> None:
 
     # ---- per-kernel timings (CUDA events between launches, eager) -> roofline of the dominant kernel -----------------
     line: dict = {}
+    # (N > 1: every rank walks the same eager launch sequence in lock step — the exchange kernels / NCCL calls of the plan keep them
+    # aligned — so a collective's time is what it costs this rank including the wait for its peers)
+    ops = []
+    if world == 1 or agent.collectives_mode in ("p2p", "graph"):
+        barrier()
+        ops = eng.profile_ops(L.PHASE_ALL & ~L.PHASE_METRICS, reps=5)
+        barrier()
+    if rank == 0 and a.timeline:
+        names = ["SAMPLE", "MIX", "FB_FWD", "FB_LOSS", "FB_BWD", "FB_ADAM", "ACTOR_FWD", "ACTOR_BWD", "ACTOR_ADAM", "METRICS"]
+        bounds, acc_ = [], 0
+        for ph in range(10):
+            acc_ += eng.launch_count(1 << ph, fused=False)
+            bounds.append(acc_)
+        with open(a.timeline, "w") as f:
+            tot = sum(o["ms"] for o in ops)
+            coll = sum(o["ms"] for o in ops if o["kind"] == "collective")
+            f.write(f"# rank 0 of {world}: per-launch CUDA-event durations of one step, eager and serialised (every entry carries ~4 us of event "
+                    f"overhead); batch {a.batch} global / {a.batch // world} per rank, z {a.z_dim}, collectives = {agent.collectives_mode}\n")
+            f.write(f"# {len(ops)} launches, {tot:.3f} ms summed: collective {coll * 1e3:.1f} us, everything else {1e3 * (tot - coll):.1f} us\n")
+            ph = 0
+            for i, o in enumerate(ops):
+                while ph < 9 and i >= bounds[ph]:
+                    ph += 1
+                f.write(f"{i:3d} {names[ph]:10s} {o['kind']:11s} {o['ms'] * 1e3:8.1f} us\n")
     if rank == 0:
-        ops = eng.profile_ops(L.PHASE_ALL & ~L.PHASE_METRICS, reps=5) if world == 1 else []
         by_kind: dict = {}
         for o in ops:
             k = by_kind.setdefault(o["kind"], {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
@@ -575,10 +599,17 @@ def run_ours(a: argparse.Namespace) -> None:
 
 def main() -> None:
     a = parse()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 behind Python's back (NCCL prints
+    # "NCCL version ..." there when NCCL_DEBUG is set on the box) are pointed at stderr for the whole run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w", buffering=1)
     if a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

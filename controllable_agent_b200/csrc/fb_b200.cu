@@ -1825,6 +1825,10 @@ int fb_set_future_mask(fb_handle* h, const int32_t* d_future_mask, void* stream)
 int fb_upload_batch(fb_handle* h, const float* h_rows, int pitch, void* stream) {
   if (!h || !h->bound) return FB_E_STATE;
   if (!h_rows || pitch != h->bl.pitch) return FB_E_ARG;
+  if (h->packed.ld == pitch) {   // one contiguous block: a 1-D copy (the 2-D form hands the copy engine one descriptor per 240-byte row)
+    CK(cudaMemcpyAsync(h->packed.p, h_rows, (size_t)pitch * sizeof(float) * (size_t)h->cfg.batch, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return FB_OK;
+  }
   CK(cudaMemcpy2DAsync(h->packed.p, (size_t)h->packed.ld * sizeof(float), h_rows, (size_t)pitch * sizeof(float), (size_t)pitch * sizeof(float),
                        (size_t)h->cfg.batch, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   return FB_OK;
