@@ -61,7 +61,7 @@ class fb_config(C.Structure):
                 ("no_norm_z", C.c_int32), ("rand_weight", C.c_int32),
                 ("add_trunk", C.c_int32), ("no_preprocess", C.c_int32),
                 ("boltzmann", C.c_int32), ("temp", C.c_float), ("log_std_min", C.c_float), ("log_std_max", C.c_float),
-                ("fused_stacks", C.c_int32)]
+                ("fused_stacks", C.c_int32), ("debug_identity_b", C.c_int32)]
 
 
 class fb_host_storage(C.Structure):

@@ -122,7 +122,7 @@ def register_hydra() -> None:
     ConfigStore.instance().store(group="agent", name="fb_ddpg", node=FBDDPGAgentConfig)
 
 
-_UNSUPPORTED = {"debug": False}
+_UNSUPPORTED: tp.Dict[str, tp.Any] = {}   # every non-default branch of fb_ddpg.py runs on the device (pixels: see __init__)
 
 
 class _EngineAdam(torch.optim.Adam):
@@ -166,6 +166,8 @@ class FBDDPGAgent:
         goal_dim = self.obs_dim
         if cfg.goal_space is not None:
             goal_dim = get_goal_space_dim(cfg.goal_space)
+        if cfg.debug and cfg.z_dim != goal_dim:
+            raise ValueError(f"agent.debug=True makes backward_net an identity map: z_dim ({cfg.z_dim}) must equal the goal dimension ({goal_dim})")
         if cfg.z_dim < goal_dim:
             logger.warning(f"z_dim {cfg.z_dim} should not be smaller that goal_dim {goal_dim}")
         self.goal_dim = goal_dim
@@ -200,7 +202,8 @@ class FBDDPGAgent:
             hidden_dim=cfg.hidden_dim, feature_dim=cfg.feature_dim, backward_hidden_dim=cfg.backward_hidden_dim,
             use_goal=cfg.goal_space is not None, rng_device=cfg.rng_mode == "device", ortho_coef=cfg.ortho_coef,
             mix_ratio=cfg.mix_ratio, future_ratio=cfg.future_ratio, q_loss=bool(cfg.q_loss), q_loss_coef=float(cfg.q_loss_coef), norm_z=bool(cfg.norm_z), rand_weight=bool(cfg.rand_weight), add_trunk=bool(cfg.add_trunk), preprocess=bool(cfg.preprocess),
-            boltzmann=bool(cfg.boltzmann), temp=float(cfg.temp), log_std_bounds=(float(cfg.log_std_bounds[0]), float(cfg.log_std_bounds[1])), seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
+            boltzmann=bool(cfg.boltzmann), temp=float(cfg.temp), log_std_bounds=(float(cfg.log_std_bounds[0]), float(cfg.log_std_bounds[1])),
+            debug=bool(cfg.debug), seed=seed, global_batch=cfg.batch_size, row_offset=row_offset,
             mlp_mode=L.MLP_SIMT if cfg.mlp_mode == "simt" else L.MLP_TCGEN05,
             contract_mode=L.CONTRACT_SIMT if cfg.contract_mode == "simt" else L.CONTRACT_TCGEN05), device)
 
@@ -213,8 +216,12 @@ class FBDDPGAgent:
         else:
             self.actor = M.Actor(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk, preprocess=cfg.preprocess)
         self.forward_net = M.ForwardMap(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk, preprocess=cfg.preprocess)
-        self.backward_net = M.BackwardMap(goal_dim, cfg.z_dim, cfg.backward_hidden_dim, norm_z=cfg.norm_z)
-        self.backward_target_net = M.BackwardMap(goal_dim, cfg.z_dim, cfg.backward_hidden_dim, norm_z=cfg.norm_z)
+        if cfg.debug:   # fb_ddpg.py:128-130
+            self.backward_net: nn.Module = M.IdentityMap()
+            self.backward_target_net: nn.Module = M.IdentityMap()
+        else:
+            self.backward_net = M.BackwardMap(goal_dim, cfg.z_dim, cfg.backward_hidden_dim, norm_z=cfg.norm_z)
+            self.backward_target_net = M.BackwardMap(goal_dim, cfg.z_dim, cfg.backward_hidden_dim, norm_z=cfg.norm_z)
         self.forward_target_net = M.ForwardMap(self.obs_dim, cfg.z_dim, self.action_dim, cfg.feature_dim, cfg.hidden_dim, add_trunk=cfg.add_trunk, preprocess=cfg.preprocess)
         M.adopt_flat(self.actor, e.tensors(L.NET_ACTOR, "param"))
         M.adopt_flat(self.forward_net, e.tensors(L.NET_FORWARD, "param"))

@@ -232,6 +232,16 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
   const int diag_col = P.diag0 + row;
   float g_row = 0.f;
   if (P.mode == CT_MODE_ROW && row_ok) g_row = P.disc[(size_t)row * P.disc_stride];
+  // G tiles leave through shared memory: a thread owns one ROW of the tile (its TMEM lane), so direct stores would put the 32 lanes of
+  // every store instruction on 32 different rows (one 32-byte sector each for 4 useful bytes: 8x write amplification in L2, and the
+  // kernel's largest cost).  Each warp stages its 32 x 16 chunk of G1 / G2 / Gc in the operand ring (free once bar_done has fired)
+  // and writes it back as 128-bit stores, 4 lanes per row: full sectors.  The transposed copies Gt1 / Gt2 are coalesced as they are
+  // (for a fixed column the lanes are consecutive rows).
+  constexpr int SCR_LD = 20;   // floats per staged row: 16 + 4, conflict-free for the 128-bit row writes
+  float* scr = reinterpret_cast<float*>(smem) + warp * (3 * 32 * SCR_LD);
+  const bool g_vec = (P.ld % 4 == 0) && (((reinterpret_cast<uintptr_t>(P.G1) | reinterpret_cast<uintptr_t>(P.G2) |
+                                            reinterpret_cast<uintptr_t>(P.Gc ? P.Gc : P.G1)) & 15u) == 0);
+  const int n_arr = P.mode == CT_MODE_ROW ? 3 : 2;
 #pragma unroll 1
   for (int cb = 0; cb < CT_TILE_N; cb += 16) {
     float m1[16], m2[16], t1[16], t2[16], cv[16];
@@ -241,16 +251,15 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
     ct_tmem_ld16(lane_addr + 3 * CT_TILE_N + cb, t2);
     if (P.mode == CT_MODE_ROW) ct_tmem_ld16(lane_addr + 4 * CT_TILE_N + cb, cv);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (row_ok) {
+    float g1v[16], g2v[16], gcv[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = col0 + cb + j;
-        if (col >= P.nc) continue;
+    for (int j = 0; j < 16; ++j) {
+      const int col = col0 + cb + j;
+      float g1 = 0.f, g2 = 0.f, gc = 0.f;
+      if (row_ok && col < P.nc) {
         const float tm = fminf(t1[j], t2[j]);
-        const size_t o = (size_t)row * P.ld + col;
         if (P.mode == CT_MODE_ROW) {
           a_tm += tm; a_m1 += m1[j];
-          float g1, g2, gc;
           if (col != diag_col) {
             const float d1 = m1[j] - g_row * tm, d2 = m2[j] - g_row * tm;
             a_off += (double)d1 * d1 + (double)d2 * d2;
@@ -261,24 +270,53 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
             a_covd += cv[j];
             g1 = -inv_n; g2 = -inv_n; gc = 0.f;
           }
-          P.G1[o] = g1; P.G2[o] = g2; P.Gc[o] = gc;
           if (P.Gt1) {  // transposed copies: for a fixed column the 32 lanes of a warp write 32 consecutive floats
             const size_t ot = (size_t)col * P.ld + row;
             P.Gt1[ot] = g1; P.Gt2[ot] = g2;
           }
         } else {
           // COL mode: rows are the LOCAL columns t of the loss matrices, cols run over all global rows s
-          float g1, g2;
           if (col != diag_col) {
             const float g = __ldg(P.disc + (size_t)col * P.disc_stride);
             g1 = (m1[j] - g * tm) * inv_noff; g2 = (m2[j] - g * tm) * inv_noff;
           } else {
             g1 = -inv_n; g2 = -inv_n;
           }
-          P.G1[o] = g1; P.G2[o] = g2;
+        }
+      }
+      g1v[j] = g1; g2v[j] = g2; gcv[j] = gc;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      *reinterpret_cast<float4*>(scr + (0 * 32 + lane) * SCR_LD + j) = make_float4(g1v[j], g1v[j + 1], g1v[j + 2], g1v[j + 3]);
+      *reinterpret_cast<float4*>(scr + (1 * 32 + lane) * SCR_LD + j) = make_float4(g2v[j], g2v[j + 1], g2v[j + 2], g2v[j + 3]);
+      if (P.mode == CT_MODE_ROW)
+        *reinterpret_cast<float4*>(scr + (2 * 32 + lane) * SCR_LD + j) = make_float4(gcv[j], gcv[j + 1], gcv[j + 2], gcv[j + 3]);
+    }
+    __syncwarp();
+    {
+      const int rr = lane >> 2, c4o = (lane & 3) * 4;
+      const int col = col0 + cb + c4o;
+#pragma unroll
+      for (int r8 = 0; r8 < 4; ++r8) {
+        const int r = r8 * 8 + rr;
+        const int grow = row0 + warp * 32 + r;
+        if (grow >= P.nr || col >= P.nc) continue;
+        for (int a = 0; a < n_arr; ++a) {
+          float* G = a == 0 ? P.G1 : (a == 1 ? P.G2 : P.Gc);
+          const float4 v = *reinterpret_cast<const float4*>(scr + (a * 32 + r) * SCR_LD + c4o);
+          float* gp = G + (size_t)grow * P.ld + col;
+          if (g_vec && col + 3 < P.nc) *reinterpret_cast<float4*>(gp) = v;
+          else {
+            gp[0] = v.x;
+            if (col + 1 < P.nc) gp[1] = v.y;
+            if (col + 2 < P.nc) gp[2] = v.z;
+            if (col + 3 < P.nc) gp[3] = v.w;
+          }
         }
       }
     }
+    __syncwarp();
   }
   if (P.mode == CT_MODE_ROW) {
     double vals[6] = {a_off, a_diag, a_cov, a_covd, a_tm, a_m1};

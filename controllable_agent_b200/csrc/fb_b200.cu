@@ -573,15 +573,19 @@ static LnBwdDesc embed_ln_bwd(const EmbedAct& e, const PSet& p, const Mat& dy, i
 // activations of one BackwardMap instance: Linear -> LN -> Tanh -> Linear -> ReLU -> Linear -> sqrt(Z) normalize
 struct BAct { Mat x, pre, y, h2, raw, out; float* mean; float* rstd; float* nrm; };
 // width / out_dim: hidden and output widths (defaults: the BackwardMap's); the DiagGaussianActor of cfg.boltzmann has the same shape
-static BAct b_alloc(fb_handle* h, const Mat& x, const Mat& out, const std::string& name, int width = 0, int out_dim = 0) {
+// identity: cfg.debug (fb_ddpg.py:128-130, fb_modules.py:202-208): the backward map is nn.Identity — no layers, no activations; "raw" is
+// the input itself (goal_dim == z_dim) and the L2 launch that follows degenerates to the copy input -> output
+static BAct b_alloc(fb_handle* h, const Mat& x, const Mat& out, const std::string& name, int width = 0, int out_dim = 0, bool identity = false) {
   const fb_config& c = h->cfg;
   if (!width) width = c.backward_hidden_dim;
   if (!out_dim) out_dim = c.z_dim;
   BAct b; b.x = x; b.out = out;
-  b.pre = ws_mat(h, x.rows, width, (name + ".pre").c_str());
-  b.y = ws_mat(h, x.rows, width, (name + ".y").c_str());
-  b.h2 = ws_mat(h, x.rows, width, (name + ".h2").c_str());
-  b.raw = ws_mat(h, x.rows, out_dim, (name + ".raw").c_str());
+  const int rows = identity ? 0 : x.rows;
+  b.pre = ws_mat(h, rows, width, (name + ".pre").c_str());
+  b.y = ws_mat(h, rows, width, (name + ".y").c_str());
+  b.h2 = ws_mat(h, rows, width, (name + ".h2").c_str());
+  if (identity) { b.raw = x; b.raw.cols = out_dim; }
+  else b.raw = ws_mat(h, x.rows, out_dim, (name + ".raw").c_str());
   b.mean = (float*)ws_alloc(h, x.rows * sizeof(float));
   b.rstd = (float*)ws_alloc(h, x.rows * sizeof(float));
   b.nrm = (float*)ws_alloc(h, x.rows * sizeof(float));
@@ -626,6 +630,9 @@ static int build_plan(fb_handle* h) {
   // [mu | raw log-std] output; every launch of the default actor (two embeds, trunk, policy head) is built with zero rows and
   // drops out in the Builder, the stack's layers join the grouped launches of the same depth
   const bool bz = c.boltzmann != 0;
+  // cfg.debug: backward_net / backward_target_net are identity maps (no parameters, no sqrt(Z) projection of their output)
+  const bool dbg = c.debug_identity_b != 0;
+  const int nzB = dbg ? 0 : nz;
   for (auto& v : h->ops) v.clear();
   for (auto& v : h->early_stage) v.clear();
   for (auto& v : h->early_avail) v.clear();
@@ -751,9 +758,9 @@ static int build_plan(fb_handle* h) {
   Mat Fa1 = Fa.cs(0, Z), Fa2 = Fa.cs(ldZ, Z);
   h->views["F1a"] = Fa1; h->views["F2a"] = Fa2;
   Mat b_mix_out = ws_mat(h, with_future ? 2 * B : B, Z, "B_mix");
-  BAct bMix = b_alloc(h, mix_in, b_mix_out, "Bmix");
-  BAct bT = b_alloc(h, goal_next, tB, "Bt");
-  BAct bO = b_alloc(h, goal_next, Bm, "Bo");
+  BAct bMix = b_alloc(h, mix_in, b_mix_out, "Bmix", 0, 0, dbg);
+  BAct bT = b_alloc(h, goal_next, tB, "Bt", 0, 0, dbg);
+  BAct bO = b_alloc(h, goal_next, Bm, "Bo", 0, 0, dbg);
 
   h->ws_fwd_end = h->ws_off;  // everything allocated so far is written by MIX / FB_FWD / ACTOR_FWD (or is an input)
 
@@ -770,7 +777,7 @@ static int build_plan(fb_handle* h) {
   Mat dh1_1 = dh1.cs(0, H), dh1_2 = dh1.cs(H, H);
   Mat dhF = ws_mat(h, B, Hc, "dhF");
   Mat dy_oa = ws_mat(h, B, H, "dy_oa"), dy_oz = ws_mat(h, deep ? 0 : B, H, "dy_oz");
-  Mat dh2 = ws_mat(h, B, c.backward_hidden_dim, "dh2"), dy1 = ws_mat(h, B, c.backward_hidden_dim, "dy1");
+  Mat dh2 = ws_mat(h, dbg ? 0 : B, c.backward_hidden_dim, "dh2"), dy1 = ws_mat(h, dbg ? 0 : B, c.backward_hidden_dim, "dy1");   // (cfg.debug: no backward_net to differentiate)
   Mat dFa = ws_mat(h, B, 2 * ldZ, "dFa");
   Mat dFa1 = dFa.cs(0, Z), dFa2 = dFa.cs(ldZ, Z);
   Mat dhoa = ws_mat(h, B, Fe, "dhoa");
@@ -854,7 +861,7 @@ static int build_plan(fb_handle* h) {
     b.ln_fwd({b_ln(bMix, pB)});
     b.gemm({lin_fwd(bMix.y, pB.w(4), pB.v(5), bMix.h2, GF_RELU | GF_RELU_LAZY_OK)});
     b.gemm({lin_fwd(bMix.h2, pB.w(6), pB.v(7), bMix.raw, 0)});
-    b.l2_fwd({b_l2(bMix, Z, nz)});
+    b.l2_fwd({b_l2(bMix, Z, nzB)});
   }
   if (rand_w) {   // mixed rows = random weighted sums of all B rows of backward_net(backward_input[perm])
     MixWeightParams mp; memset(&mp, 0, sizeof(mp));
@@ -911,7 +918,7 @@ static int build_plan(fb_handle* h) {
             lin_fwd(bO.h2, pB.w(6), pB.v(7), bO.raw, 0), lin_fwd(bT.h2, pBt.w(6), pBt.v(7), bT.raw, 0)});
   }
   b.gemm({lin_fwd(h1A, pA.w(A_POL + 2), pA.v(A_POL + 3), preA, 0), lin_fwd(pol.h2, pA.w(6), pA.v(7), pol.raw, 0)});   // (policy.5)
-  b.l2_fwd({b_l2(bO, Z, nz), b_l2(bT, Z, nz)});
+  b.l2_fwd({b_l2(bO, Z, nzB), b_l2(bT, Z, nzB)});
   if (bz) {   // SquashedNormal samples of both sides + log pi of the obs side (fb_ddpg.py:304-306,391-396)
     ActorOutBzParams ap; memset(&ap, 0, sizeof(ap));
     ap.batch = B; ap.A = A; ap.act_col = act_col; ap.pre = pol.raw.p; ap.ldP = pol.raw.ld;
@@ -1108,21 +1115,23 @@ static int build_plan(fb_handle* h) {
     const int ldp = tc_inner ? dBparts.ld : dB.ld;
     float* dsum = tc_inner ? dB.p : nullptr;   // keep the "dB" view complete on both paths
     const float coef = tc_inner ? db_coef : 0.f;
-    b.push([p0, p1, p2, ldp, coef, dsum, dB, Bm, bO, draw, B, Z, nz](cudaStream_t s) {
-      fb_launch_pdl(k_l2norm_bwd, dim3(fb_ceil_div(B, 8)), dim3(256), 0, s, p0, p1, p2, ldp, coef, dsum, dB.ld, Bm.p, Bm.ld, bO.nrm, draw.p, draw.ld, B, Z, nz);
+    b.push([p0, p1, p2, ldp, coef, dsum, dB, Bm, bO, draw, B, Z, nzB](cudaStream_t s) {
+      fb_launch_pdl(k_l2norm_bwd, dim3(fb_ceil_div(B, 8)), dim3(256), 0, s, p0, p1, p2, ldp, coef, dsum, dB.ld, Bm.p, Bm.ld, bO.nrm, draw.p, draw.ld, B, Z, nzB);
       return cudaGetLastError();
     });
     {
       FsL2BwdArgs fa; memset(&fa, 0, sizeof(fa));
       fa.dy0 = p0; fa.dy1 = p1; fa.dy2 = p2; fa.dsum = dsum; fa.y = Bm.p; fa.nrm = bO.nrm; fa.dx = draw.p;
-      fa.lddy = ldp; fa.ldsum = dB.ld; fa.ldy = Bm.ld; fa.lddx = draw.ld; fa.rows = B; fa.Z = Z; fa.normalize = nz; fa.coef = coef;
+      fa.lddy = ldp; fa.ldsum = dB.ld; fa.ldy = Bm.ld; fa.lddx = draw.ld; fa.rows = B; fa.Z = Z; fa.normalize = nzB; fa.coef = coef;
       h->ops[b.phase].back().dev.set(FS_L2_BWD, fb_ceil_div(B, 8), fa);
     }
   }
-  b.colsum({mk_colsum(dF1, pF.gv(HD_1 + 3)), mk_colsum(dF2, pF.gv(HD_2 + 3)), mk_colsum(draw, pB.gv(7))});
-  b.gemm({lin_dw(dF1, h1F1, pF.gw(HD_1 + 2)), lin_dw(dF2, h1F2, pF.gw(HD_2 + 2)), lin_dw(draw, bO.h2, pB.gw(6)),
+  Mat draw_c = draw;   // the gradient w.r.t. backward_net's last Linear output, as its backward launches see it (cfg.debug: nobody)
+  if (dbg) draw_c.rows = 0;
+  b.colsum({mk_colsum(dF1, pF.gv(HD_1 + 3)), mk_colsum(dF2, pF.gv(HD_2 + 3)), mk_colsum(draw_c, pB.gv(7))});
+  b.gemm({lin_dw(dF1, h1F1, pF.gw(HD_1 + 2)), lin_dw(dF2, h1F2, pF.gw(HD_2 + 2)), lin_dw(draw_c, bO.h2, pB.gw(6)),
           lin_dx(dF1, pF.w(HD_1 + 2), dh1_1, GF_MASK_RELU, &h1F1), lin_dx(dF2, pF.w(HD_2 + 2), dh1_2, GF_MASK_RELU, &h1F2),
-          lin_dx(draw, pB.w(6), dh2, GF_MASK_RELU, &bO.h2)});
+          lin_dx(draw_c, pB.w(6), dh2, GF_MASK_RELU, &bO.h2)});
   b.colsum({mk_colsum(dh1_1, pF.gv(HD_1 + 1)), mk_colsum(dh1_2, pF.gv(HD_2 + 1)), mk_colsum(dh2, pB.gv(5))});
   {
     // both heads' dX products land in one buffer (K2 = the second head): the gradient of the heads' common input, masked by its ReLU
@@ -1142,7 +1151,7 @@ static int build_plan(fb_handle* h) {
   {
     LnBwdDesc d; memset(&d, 0, sizeof(d));
     d.dy = dy1.p; d.dx = dy1.p; d.y = bO.y.p; d.x = bO.pre.p; d.gamma = pB.v(2); d.mean = bO.mean; d.rstd = bO.rstd;
-    d.dgamma = pB.gv(2); d.dbeta = pB.gv(3); d.rows = B; d.D = dy1.cols; d.ld = bO.y.ld; d.ld_dy = dy1.ld;
+    d.dgamma = pB.gv(2); d.dbeta = pB.gv(3); d.rows = dy1.rows; d.D = dy1.cols; d.ld = bO.y.ld; d.ld_dy = dy1.ld;
     b.ln_bwd({d});
   }
   b.colsum({mk_colsum(dy1, pB.gv(1))});
@@ -1410,23 +1419,23 @@ static int build_plan(fb_handle* h) {
     });
 
     Mat ig = ws_mat(h, R, G, "infer_goal"), ib = ws_mat(h, R, Z, "infer_b");
-    BAct b1 = b_alloc(h, ig, ib, "infer.B");
+    BAct b1 = b_alloc(h, ig, ib, "infer.B", 0, 0, dbg);
     b.set_phase(FB_PHASE_INFER_B);
     b.gemm({lin_fwd(b1.x, pB.w(0), pB.v(1), b1.pre, 0)});
     b.ln_fwd({b_ln(b1, pB)});
     b.gemm({lin_fwd(b1.y, pB.w(4), pB.v(5), b1.h2, GF_RELU)});
     b.gemm({lin_fwd(b1.h2, pB.w(6), pB.v(7), b1.raw, 0)});
-    b.l2_fwd({b_l2(b1, Z, nz)});
+    b.l2_fwd({b_l2(b1, Z, nzB)});
 
     Mat igN = ws_mat(h, B, G, "infer_goal_batch"), irN = ws_mat(h, B, 1, "infer_reward"), ibN = ws_mat(h, B, Z, "infer_b_batch");
     Mat izs = ws_mat(h, 1, Z, "infer_zsum");
-    BAct bN = b_alloc(h, igN, ibN, "infer.BN");
+    BAct bN = b_alloc(h, igN, ibN, "infer.BN", 0, 0, dbg);
     b.set_phase(FB_PHASE_INFER_BN);
     b.gemm({lin_fwd(bN.x, pB.w(0), pB.v(1), bN.pre, 0)});
     b.ln_fwd({b_ln(bN, pB)});
     b.gemm({lin_fwd(bN.y, pB.w(4), pB.v(5), bN.h2, GF_RELU)});
     b.gemm({lin_fwd(bN.h2, pB.w(6), pB.v(7), bN.raw, 0)});
-    b.l2_fwd({b_l2(bN, Z, nz)});
+    b.l2_fwd({b_l2(bN, Z, nzB)});
     b.push([=](cudaStream_t s) {
       fb_launch_pdl(k_infer_weighted_colsum, dim3(fb_ceil_div(Z, 32)), dim3(256), 0, s, ibN.p, ibN.ld, irN.p, irN.ld, B, Z, izs.p);
       return cudaGetLastError();
@@ -1543,6 +1552,7 @@ int fb_create(const fb_config* cfg, fb_handle** out) {
   if (!(cfg->future_ratio >= 0.f && cfg->future_ratio <= 1.f) || !(cfg->mix_ratio >= 0.f && cfg->mix_ratio <= 1.f)) return FB_E_ARG;
   if (cfg->q_loss && cfg->z_dim > FB_QLOSS_MAX_Z) return FB_E_UNSUPPORTED;
   if (cfg->boltzmann && !(cfg->log_std_max > cfg->log_std_min)) return FB_E_ARG;
+  if (cfg->debug_identity_b && cfg->z_dim != cfg->goal_dim) return FB_E_ARG;   // an identity backward map: z lives in goal space
   if (cfg->rand_weight && cfg->z_dim > FB_MIXW_MAX_Z) return FB_E_UNSUPPORTED;
   fb_handle* h = new fb_handle();
   h->cfg = *cfg;

@@ -179,8 +179,10 @@ static void build_layout(fb_handle* h) {
   add_head(f, "F2", head_in, H, Z);
   h->bwd_first = (int)f.t.size();
   h->bwd_offset = f.size;
-  f.add("B.0.weight", Hb, G); f.add("B.0.bias", Hb, 0); f.add("B.1.weight", Hb, 0); f.add("B.1.bias", Hb, 0);
-  f.add("B.3.weight", Hb, Hb); f.add("B.3.bias", Hb, 0); f.add("B.5.weight", Z, Hb); f.add("B.5.bias", Z, 0);
+  if (!c.debug_identity_b) {   // (cfg.debug: the backward map is nn.Identity, no tensors)
+    f.add("B.0.weight", Hb, G); f.add("B.0.bias", Hb, 0); f.add("B.1.weight", Hb, 0); f.add("B.1.bias", Hb, 0);
+    f.add("B.3.weight", Hb, Hb); f.add("B.3.bias", Hb, 0); f.add("B.5.weight", Z, Hb); f.add("B.5.bias", Z, 0);
+  }
   SegmentLayout& a = h->seg_actor;
   if (c.boltzmann) {   // DiagGaussianActor: policy = mlp(obs + z, hidden, "ntanh", hidden, "relu", 2 * action)  (fb_modules.py:137)
     a.add("policy.0.weight", H, O + Z); a.add("policy.0.bias", H, 0); a.add("policy.1.weight", H, 0); a.add("policy.1.bias", H, 0);

@@ -42,6 +42,7 @@ class EngineConfig:
     boltzmann: bool = False     # DiagGaussianActor + SquashedNormal actions, actor loss mean(temp * log pi - Q) (fb_modules.py:129-151)
     temp: float = 1.0
     log_std_bounds: tp.Tuple[float, float] = (-5.0, 2.0)
+    debug: bool = False         # backward_net / backward_target_net = nn.Identity (fb_ddpg.py:128-130); needs z_dim == goal_dim
     norm_z: bool = True         # sqrt(z_dim)-sphere projection of B's output / of z (fb_modules.py:227-229, fb_ddpg.py:228,483)
     beta1: float = 0.9
     beta2: float = 0.999
@@ -94,7 +95,7 @@ class FBStepEngine:
                         beta1=cfg.beta1, beta2=cfg.beta2, adam_eps=cfg.adam_eps, seed=cfg.seed,
                         q_loss=int(cfg.q_loss), q_loss_coef=cfg.q_loss_coef, no_norm_z=int(not cfg.norm_z), rand_weight=int(cfg.rand_weight), add_trunk=int(cfg.add_trunk), no_preprocess=int(not cfg.preprocess),
                         boltzmann=int(cfg.boltzmann), temp=float(cfg.temp), log_std_min=float(cfg.log_std_bounds[0]), log_std_max=float(cfg.log_std_bounds[1]),
-                        fused_stacks=int(bool(cfg.fused)))
+                        fused_stacks=int(bool(cfg.fused)), debug_identity_b=int(bool(cfg.debug)))
         h = C.c_void_p()
         L.check(self.lib.fb_create(C.byref(c), C.byref(h)), "fb_create")
         self.h = h

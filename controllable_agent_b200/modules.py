@@ -265,6 +265,17 @@ class BackwardMap(nn.Module):
         return b
 
 
+class IdentityMap(nn.Module):
+    """fb_modules.IdentityMap (cfg.debug, fb_modules.py:202-208): the backward representation is the goal itself."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.B = nn.Identity()
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        return self.B(obs)
+
+
 def adopt_flat(module: nn.Module, views: tp.Mapping[str, torch.Tensor]) -> None:
     """Move a freshly initialised CPU module onto the flat device segment: copy each parameter into its view and
     re-point the parameter at the view, keeping nn.Module registration order == flat layout order."""

@@ -141,6 +141,8 @@ typedef struct fb_config {
   int32_t fused_stacks;        /* the handle will be run WITHOUT FB_RUN_UNFUSED (k_fused_stack segments): its GEMM launches are then planned
                                   for single CTAs.  0 (default): wide GEMM groups run on CTA pairs (tcgen05 cta_group::2) and fused
                                   execution of such a plan is refused with FB_E_STATE */
+  int32_t debug_identity_b;    /* cfg.debug (fb_ddpg.py:128-130, fb_modules.py:202-208): backward_net and its target are nn.Identity: B(goal) =
+                                  goal (needs z_dim == goal_dim), no "B.*" tensors, no projection of B's output, no backward_net gradients */
 } fb_config;
 
 /* per-step scalars (host values; copied to the device by fb_set_step_scalars) */

@@ -205,7 +205,10 @@ def l2_project(x: Tensor, z_dim: int) -> Tensor:
 
 
 def backward_map(p: Params, goal: Tensor, z_dim: int, norm_z: bool = True) -> Tensor:
-    """BackwardMap.forward (fb_modules.py:223-230)."""
+    """BackwardMap.forward (fb_modules.py:223-230).  A parameter-free map is the IdentityMap of cfg.debug (fb_modules.py:202-208,
+    fb_ddpg.py:128-130): B(goal) = goal, no projection."""
+    if len(p) == 0:
+        return goal
     h = F.linear(goal, p["B.0.weight"], p["B.0.bias"])
     h = torch.tanh(F.layer_norm(h, (h.shape[-1],), p["B.1.weight"], p["B.1.bias"], LN_EPS))
     h = torch.relu(F.linear(h, p["B.3.weight"], p["B.3.bias"]))
@@ -344,6 +347,8 @@ def fb_loss_and_grads(fwd: Params, bwd: Params, fwd_tgt: Params, bwd_tgt: Params
     f, b = _with_grad(fwd), _with_grad(bwd)
     F1, F2 = forward_map(f, obs, z, action)
     Bm = backward_map(b, next_goal, z_dim, norm_z)
+    if not Bm.requires_grad:   # the identity map of cfg.debug: B is the input itself; its gradient is still reported (dL/dB)
+        Bm = Bm.detach().clone().requires_grad_(True)
     F1.retain_grad(), F2.retain_grad(), Bm.retain_grad()
     terms = fb_loss_terms(F1, F2, Bm, tF1, tF2, tB, discount, ortho_coef, z, q_loss_coef)
     terms["fb_loss"].backward()
@@ -513,6 +518,7 @@ class OracleConfig:
     add_trunk: bool = False       # Linear(2 feature -> hidden) + ReLU between the embeds and the heads (fb_modules.py:96-100,169-173)
     rand_weight: bool = False     # mixed z = random convex-like combinations of B rows (fb_ddpg.py:475-482)
     norm_z: bool = True           # sqrt(z_dim)-sphere projection of B's output and of z (fb_modules.py:227-229, fb_ddpg.py:228,483)
+    debug: bool = False           # backward_net = IdentityMap (fb_ddpg.py:128-130); needs z_dim == goal_dim
 
 
 class OracleAgent:
@@ -526,7 +532,7 @@ class OracleAgent:
         d = cfg.dims
         self.actor = init_params(boltzmann_actor_spec(d) if cfg.boltzmann else actor_spec(d, cfg.add_trunk, cfg.preprocess), generator)
         self.forward_net = init_params(forward_map_spec(d, cfg.add_trunk, cfg.preprocess), generator)
-        self.backward_net = init_params(backward_map_spec(d), generator)
+        self.backward_net = init_params([] if cfg.debug else backward_map_spec(d), generator)
         self.forward_target_net = collections.OrderedDict((k, v.clone()) for k, v in self.forward_net.items())
         self.backward_target_net = collections.OrderedDict((k, v.clone()) for k, v in self.backward_net.items())
         self._build_optimizers()

@@ -46,7 +46,7 @@ def make_agent(R: tp.Any, case: tp.Mapping[str, tp.Any], use_tb: bool = True) ->
         q_loss_coef=case.get("q_loss_coef", 0.01), additional_metric=case.get("additional_metric", False),
         norm_z=case.get("norm_z", True), rand_weight=case.get("rand_weight", False),
         add_trunk=case.get("add_trunk", False), preprocess=case.get("preprocess", True), boltzmann=case.get("boltzmann", False),
-        temp=case.get("temp", 1))
+        temp=case.get("temp", 1), debug=case.get("debug", False))
     return R.FBDDPGAgent(**dataclasses.asdict(cfg))
 
 
@@ -325,9 +325,19 @@ def write_oracle_only_cases(R: tp.Any) -> None:
         print("wrote trajectory_%s" % name)
 
 
+def write_debug_cases(R: tp.Any) -> None:
+    """debug=True (fb_ddpg.py:128-130, fb_modules.py:202-208): backward_net / backward_target_net are IdentityMap, so z lives in goal space
+    (z_dim == goal_dim = obs_dim here) and backward_net has no parameters."""
+    case = dict(CASES["small"], debug=True, z_dim=CASES["small"]["obs_dim"])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "update_debug.npz"), **gen_update_case(R, "debug", case))
+    print("wrote update_debug")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "trajectory_debug.npz"), **gen_trajectory_case(R, case))
+    print("wrote trajectory_debug")
+
+
 # fixture families added after the first ones; `--<name>-only` regenerates one family without touching the others
 LATER_FAMILIES = {"hindsight": write_hindsight_cases, "qloss": write_qloss_cases, "nonorm": write_nonorm_cases, "randw": write_randw_cases,
-                  "trunk": write_trunk_cases, "oracle": write_oracle_only_cases}
+                  "trunk": write_trunk_cases, "oracle": write_oracle_only_cases, "debug": write_debug_cases}
 
 
 def main() -> None:

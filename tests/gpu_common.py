@@ -19,6 +19,11 @@ def rel(a, b):
 
 
 def dims_from_params(fwd, bwd, actor):
+    if len(bwd) == 0:   # cfg.debug: identity backward map, z_dim == goal_dim == obs_dim; the (unused) hidden width is make_golden's
+        hidden, oa = fwd["obs_action_net.0.weight"].shape
+        obs_dim = actor["obs_net.0.weight"].shape[1]
+        return O.Dims(obs_dim=obs_dim, action_dim=oa - obs_dim, z_dim=fwd["F1.2.weight"].shape[0], goal_dim=obs_dim, hidden_dim=hidden,
+                      feature_dim=fwd["obs_action_net.3.weight"].shape[0], backward_hidden_dim=30)
     if "policy.5.weight" in actor:   # cfg.boltzmann: the DiagGaussianActor has no embeds; the obs width comes from policy.0 ([obs | z] columns)
         hidden, oa = fwd["obs_action_net.0.weight"].shape
         z_dim = fwd["F1.2.weight"].shape[0]
@@ -43,14 +48,14 @@ def golden_params(g, prefix):
 
 
 def make_engine(d, batch, use_goal=False, rng_device=False, mix_ratio=0.5, ortho_coef=1.0, seed=0, global_batch=None,
-                row_offset=0, contract_mode=0, mlp_mode=0, q_loss_coef=None, norm_z=True, add_trunk=False, fused=False, preprocess=True, boltzmann=False, temp=1.0):
+                row_offset=0, contract_mode=0, mlp_mode=0, q_loss_coef=None, norm_z=True, add_trunk=False, fused=False, preprocess=True, boltzmann=False, temp=1.0, debug=False):
     from controllable_agent_b200.engine import EngineConfig, FBStepEngine
     cfg = EngineConfig(batch=batch, obs_dim=d.obs_dim, action_dim=d.action_dim, z_dim=d.z_dim, goal_dim=d.goal_dim,
                        hidden_dim=d.hidden_dim, feature_dim=d.feature_dim, backward_hidden_dim=d.backward_hidden_dim,
                        use_goal=use_goal, rng_device=rng_device, ortho_coef=ortho_coef, mix_ratio=mix_ratio, seed=seed,
                        global_batch=global_batch, row_offset=row_offset, contract_mode=contract_mode, mlp_mode=mlp_mode,
                        q_loss=q_loss_coef is not None, q_loss_coef=q_loss_coef if q_loss_coef is not None else 0.01, norm_z=norm_z, add_trunk=add_trunk, fused=fused, preprocess=preprocess,
-                       boltzmann=boltzmann, temp=temp)
+                       boltzmann=boltzmann, temp=temp, debug=debug)
     return FBStepEngine(cfg, "cuda")
 
 

@@ -105,9 +105,11 @@ def test_refused_configurations():
     from controllable_agent_b200 import FBDDPGAgent
     base = dict(obs_type="states", obs_shape=(24,), action_shape=(6,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,
                 use_tb=False, use_wandb=False, use_hiplog=False)
-    for kw in (dict(debug=True), dict(obs_type="pixels")):
+    for kw in (dict(obs_type="pixels"),):
         with pytest.raises(NotImplementedError):
             FBDDPGAgent(**{**base, **kw})
+    with pytest.raises(ValueError, match="identity"):      # debug=True: z must live in goal space (z_dim 50 != obs_dim 24)
+        FBDDPGAgent(**{**base, "debug": True})
     with pytest.raises(ValueError):
         FBDDPGAgent(**{**base, "future_ratio": -0.1})
     with pytest.raises(RuntimeError, match="no CPU fallback|CPU"):

@@ -39,7 +39,8 @@ def _create(L, lib, d, batch=64, **kw):
                     ortho_coef=1.0, mix_ratio=kw.get("mix_ratio", 0.5), beta1=0.9, beta2=0.999, adam_eps=1e-8, seed=0,
                     future_ratio=kw.get("future_ratio", 0.0), q_loss=kw.get("q_loss", 0), q_loss_coef=0.01, no_norm_z=kw.get("no_norm_z", 0),
                     rand_weight=kw.get("rand_weight", 0), add_trunk=kw.get("add_trunk", 0), no_preprocess=kw.get("no_preprocess", 0),
-                    boltzmann=kw.get("boltzmann", 0), temp=0.7, log_std_min=kw.get("log_std_min", -5.0), log_std_max=2.0)
+                    boltzmann=kw.get("boltzmann", 0), temp=0.7, log_std_min=kw.get("log_std_min", -5.0), log_std_max=2.0,
+                    debug_identity_b=kw.get("debug", 0))
     h = C.c_void_p()
     return lib.fb_create(C.byref(c), C.byref(h)), h
 
@@ -101,6 +102,20 @@ def test_add_trunk_layout_and_optional_branch_plans(d):
         assert [(n, s) for n, _, s in _table(lib, h, net)] == [(n, tuple(s)) for n, s in spec]
     lib.fb_destroy(h)
     assert _create(L, lib, d, boltzmann=1, log_std_min=3.0)[0] == -1   # empty log-std interval
+    dz = dataclasses.replace(d, z_dim=d.goal_dim)   # debug = True: identity backward map, z in goal space; no "B.*" tensors
+    rc, h = _create(L, lib, dz, debug=1)
+    assert rc == 0 and _table(lib, h, L.NET_BACKWARD) == []
+    assert [(n, s) for n, _, s in _table(lib, h, L.NET_FORWARD)] == [(n, tuple(s)) for n, s in O.forward_map_spec(dz)]
+    lib.fb_destroy(h)
+    if d.z_dim != d.goal_dim:
+        assert _create(L, lib, d, debug=1)[0] == -1
+    for bits in range(64):   # ... and it plans with every other branch
+        kw = dict(q_loss=bits & 1, no_norm_z=(bits >> 1) & 1, rand_weight=(bits >> 2) & 1, add_trunk=(bits >> 3) & 1,
+                  future_ratio=0.3 if bits & 16 else 0.0, boltzmann=(bits >> 5) & 1, debug=1)
+        for mlp_mode in (0, 1):
+            rc, h = _create(L, lib, dz, mlp_mode=mlp_mode, contract_mode=mlp_mode, **kw)
+            assert rc == 0, (kw, mlp_mode)
+            lib.fb_destroy(h)
     for bits in range(128):
         kw = dict(q_loss=bits & 1, no_norm_z=(bits >> 1) & 1, rand_weight=(bits >> 2) & 1, add_trunk=(bits >> 3) & 1,
                   future_ratio=0.3 if bits & 16 else 0.0, no_preprocess=(bits >> 5) & 1, boltzmann=(bits >> 6) & 1)

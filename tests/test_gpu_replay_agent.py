@@ -118,7 +118,7 @@ def test_pack_episode_kernel_matches_host_packing():
     assert torch.equal(rows[3], buf._rows[3])
 
 
-SMALL_CASES = ("small", "future", "qloss", "nonorm", "randw", "randw_nonorm", "trunk", "nopre", "boltz")   # fixtures generated from make_golden.CASES["small"]
+SMALL_CASES = ("small", "future", "qloss", "nonorm", "randw", "randw_nonorm", "trunk", "nopre", "boltz", "debug")   # fixtures generated from make_golden.CASES["small"]
 
 
 def _agent_for(g, case, **kw):
@@ -130,7 +130,7 @@ def _agent_for(g, case, **kw):
     agent = FBDDPGAgent(obs_type="states", obs_shape=(obs_dim,), action_shape=(oa - obs_dim,), device="cuda", num_expl_steps=0,
                         update_encoder=True, goal_space=None if case in SMALL_CASES else "simplified_walker", use_tb=True, use_wandb=False,
                         use_hiplog=False, hidden_dim=hidden, feature_dim=d.feature_dim,
-                        backward_hidden_dim=b["B.0.weight"].shape[0], z_dim=f["F1.2.weight"].shape[0],
+                        backward_hidden_dim=d.backward_hidden_dim, z_dim=f["F1.2.weight"].shape[0],
                         batch_size=32 if case in SMALL_CASES else 64, update_every_steps=1,
                         future_ratio=0.4 if case.startswith("future") else (0.3 if case == "nonorm" else 0.0), **kw)
     for net, src in ((agent.actor, a), (agent.forward_net, f), (agent.backward_net, b), (agent.forward_target_net, f),
@@ -140,7 +140,7 @@ def _agent_for(g, case, **kw):
     return agent
 
 
-@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm", "trunk", "nopre", "boltz"])
+@pytest.mark.parametrize("case", ["small", "goal", "future", "future_goal", "qloss", "nonorm", "randw", "randw_nonorm", "trunk", "nopre", "boltz", "debug"])
 @pytest.mark.parametrize("foreign_replay", [False, True, "fused"])   # "fused": HBM replay, the MLP stacks as fused persistent kernels
 def test_agent_update_walks_reference_trajectory(case, foreign_replay):
     fuse = foreign_replay == "fused"
@@ -161,6 +161,8 @@ def test_agent_update_walks_reference_trajectory(case, foreign_replay):
         extra = dict(preprocess=False)
     if case == "boltz":   # boltzmann = True (fb_modules.py:129-151), temp as make_golden generated it
         extra = dict(boltzmann=True, temp=float(g["cfg/temp"]) if "cfg/temp" in g else 0.7)
+    if case == "debug":   # debug = True: identity backward map (fb_ddpg.py:128-130)
+        extra = dict(debug=True)
     agent = _agent_for(g, case, rng_mode="reference", fuse_stacks=fuse, **extra)
     agent.draw_device = "cpu"
     eps = [subtree(g, f"ep{i}") for i in range(4)]
@@ -498,9 +500,11 @@ def test_unsupported_branches_raise():
     from controllable_agent_b200 import FBDDPGAgent
     base = dict(obs_type="states", obs_shape=(24,), action_shape=(6,), device="cuda", num_expl_steps=0, update_encoder=True, goal_space=None,
                 use_tb=False, use_wandb=False, use_hiplog=False)
-    for kw in (dict(obs_type="pixels"), dict(debug=True)):
+    for kw in (dict(obs_type="pixels"),):
         with pytest.raises(NotImplementedError):
             FBDDPGAgent(**{**base, **kw})
+    with pytest.raises(ValueError):   # debug=True needs z_dim == goal_dim
+        FBDDPGAgent(**{**base, "debug": True})
     with pytest.raises(RuntimeError):
         FBDDPGAgent(**{**base, "device": "cpu"})
     with pytest.raises(ValueError):

@@ -176,15 +176,22 @@ def test_schedule():
 SMALL = O.Dims(obs_dim=11, action_dim=3, z_dim=10, goal_dim=11, hidden_dim=48, feature_dim=24, backward_hidden_dim=30)   # make_golden.CASES["small"]
 
 
-@pytest.mark.parametrize("case", ["nopre", "boltz"])
+def _branch_dims(case):
+    """make_golden's "small" dims; debug=True puts z in goal space (z_dim = obs_dim = 11)."""
+    import dataclasses
+    return dataclasses.replace(SMALL, z_dim=11) if case == "debug" else SMALL
+
+
+@pytest.mark.parametrize("case", ["nopre", "boltz", "debug"])
 def test_oracle_only_branches_update(case):
-    """preprocess=False and boltzmann=True: the two fb_ddpg branches the CUDA step does not implement yet (the agent raises for
-    them).  The oracle is pinned against the reference here so that the kernels of a later round have a checker."""
+    """preprocess=False, boltzmann=True and debug=True (identity backward map): the oracle's restatement of these fb_ddpg branches is
+    pinned against the reference here (the CUDA step is checked against the same files in the -m gpu tests)."""
     g = load_golden(f"update_{case}")
     boltz = bool(g["cfg/boltzmann"])
+    SMALL = _branch_dims(case)
     fwd_spec = O.forward_map_spec(SMALL, preprocess=case != "nopre")
     act_spec = O.boltzmann_actor_spec(SMALL) if boltz else O.actor_spec(SMALL, preprocess=case != "nopre")
-    for net, spec in (("forward_net", fwd_spec), ("actor", act_spec), ("backward_net", O.backward_map_spec(SMALL))):
+    for net, spec in (("forward_net", fwd_spec), ("actor", act_spec), ("backward_net", [] if case == "debug" else O.backward_map_spec(SMALL))):
         ref = subtree(g, f"param0/{net}")
         assert [(n, tuple(s)) for n, s in spec] == [(k, v.shape) for k, v in ref.items()]
     t = {k: torch.from_numpy(v.copy()) for k, v in subtree(g, "in").items()}
@@ -208,11 +215,12 @@ def test_oracle_only_branches_update(case):
         assert rel(res["grads_actor"][name].numpy(), ref) < 1e-5, name
 
 
-@pytest.mark.parametrize("case", ["nopre", "boltz"])
+@pytest.mark.parametrize("case", ["nopre", "boltz", "debug"])
 def test_oracle_only_branches_trajectory(case):
     torch.set_num_threads(1)
     g = load_golden(f"trajectory_{case}")
-    agent = O.OracleAgent(O.OracleConfig(dims=SMALL, batch_size=32, preprocess=case != "nopre", boltzmann=case == "boltz", temp=0.7))
+    agent = O.OracleAgent(O.OracleConfig(dims=_branch_dims(case), batch_size=32, preprocess=case != "nopre", boltzmann=case == "boltz", temp=0.7,
+                                         debug=case == "debug"))
     a, f, b = subtree(g, "param0/actor"), subtree(g, "param0/forward_net"), subtree(g, "param0/backward_net")
     agent.load_params(actor=a, forward_net=f, backward_net=b, forward_target_net=f, backward_target_net=b)
     buf = O.OracleReplay(4, 0.98, 0.99)
