@@ -27,7 +27,7 @@
 #define CT_TILE_N 64
 #define CT_MAX_PRODUCTS 5
 #define CT_TMEM_COLS 512
-#define CT_THREADS 128
+#define CT_THREADS 192   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
 
 enum { CT_MODE_ROW = 0, CT_MODE_COL = 1 };
 enum { CT_F1 = 0, CT_F2, CT_TF1, CT_TF2, CT_B, CT_TB, CT_NUM_OPERANDS };
@@ -134,33 +134,45 @@ __global__ void __launch_bounds__(256) k_contract_split(const float* __restrict_
   o[KP + c] = lo;
 }
 
-// dynamic smem: [stage][A raw | A lo | B raw | B lo], each part nbox boxes of (rows x 128 B); 1024-byte aligned
+// Persistent, warp-specialised: min(tiles, SMs) CTAs walk the 128 x 64 tiles of the pair space column by column (consecutive CTAs
+// share one column block of the B-side operands in L2).
+//   warp 0      TMA producer   one K-box (32 floats) of one product per ring stage: [A raw | A lo | B raw | B lo] = 48 KB, 4 stages;
+//                              runs ahead into the next tile while the current one is in its epilogue
+//   warp 1      MMA issuer     3 chains x <= 4 tcgen05.mma (M128 x N64 x K8) per stage into the product's 64 TMEM columns
+//   warps 2..5  epilogue       tcgen05.ld of the five accumulators, loss math, G tiles out through a shared-memory transpose
+// (The first version ran one tile per CTA with ONE thread as producer and issuer and whole products as stages: at z = 100 a single
+// 192 KB stage, i.e. no overlap of loads and MMAs at all; at batch 4096 that was 15 % of the step.)
+// dynamic smem: [4 stages x 48 KB | epilogue scratch 4 warps x 3 x 32 x 20 floats], 1024-byte aligned
+#define CT_STAGES 4
+#define CT_STAGE_BYTES (2 * CT_TILE_M * 128 + 2 * CT_TILE_N * 128)
+#define CT_SCR_LD 20
+#define CT_SCRATCH_BYTES (4 * 3 * 32 * CT_SCR_LD * 4)
+#define CT_SMEM_BYTES (CT_STAGES * CT_STAGE_BYTES + CT_SCRATCH_BYTES + 1024)
+
 __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_constant__ ContractParams P) {
   fb_pdl_trigger();
-  fb_pdl_wait();
   extern __shared__ __align__(1024) uint8_t ct_smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[2];
-  __shared__ __align__(8) uint64_t bar_empty[2];
-  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ __align__(8) uint64_t bar_full[CT_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[CT_STAGES];
+  __shared__ __align__(8) uint64_t bar_accum;        // all MMAs of a tile retired -> epilogue
+  __shared__ __align__(8) uint64_t bar_tmem_empty;   // epilogue has read the accumulators -> MMA issuer (next tile)
   __shared__ uint32_t tmem_base_smem;
   __shared__ double red[6][4];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ct_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.y, tile_n = blockIdx.x;
-  const int row0 = tile_m * CT_TILE_M, col0 = tile_n * CT_TILE_N;
-  const int nbox = P.nbox;
-  const uint32_t a_part = (uint32_t)nbox * CT_TILE_M * 128u;   // bytes of one A part (raw or lo)
-  const uint32_t b_part = (uint32_t)nbox * CT_TILE_N * 128u;
-  const uint32_t stage_bytes = 2u * a_part + 2u * b_part;
-  const int nstage = (2u * stage_bytes <= 200u * 1024u) ? 2 : 1;
+  const int tiles_m = (P.nr + CT_TILE_M - 1) / CT_TILE_M, tiles_n = (P.nc + CT_TILE_N - 1) / CT_TILE_N;
+  const int ntiles = tiles_m * tiles_n;
+  const int nbox = P.nbox, np = P.n_products;
+  constexpr uint32_t A_BOX = CT_TILE_M * 128u, B_BOX = CT_TILE_N * 128u;   // bytes of one K-box of the A / B side (raw or lo)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { ct_mbar_init(&bar_full[s], 1); ct_mbar_init(&bar_empty[s], 1); }
-    ct_mbar_init(&bar_done, 1);
+    for (int s = 0; s < CT_STAGES; ++s) { ct_mbar_init(&bar_full[s], 1); ct_mbar_init(&bar_empty[s], 1); }
+    ct_mbar_init(&bar_accum, 1);
+    ct_mbar_init(&bar_tmem_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ct_smem_u32(&tmem_base_smem)), "r"(CT_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -169,161 +181,179 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  fb_pdl_wait();   // the prologue above overlapped the previous kernel's tail
 
-  if (threadIdx.x == 0) {
-    // ---- single-thread producer + MMA issuer: loads run one product ahead of the tensor core ----
-    auto issue_loads = [&](int p) {
-      const int s = p % nstage;
-      uint8_t* st = smem + (size_t)s * stage_bytes;
-      ct_mbar_expect_tx(&bar_full[s], stage_bytes);
-      const CUtensorMap* ma = &P.maps[P.prod_a[p]];
-      const CUtensorMap* mb = &P.maps[P.prod_b[p]];
-      const int KP = nbox * 32;
-      for (int part = 0; part < 2; ++part) {       // 0: raw, 1: lo
-        for (int b = 0; b < nbox; ++b) {
-          const int kcol = part * KP + b * 32;
-          uint8_t* da = st + part * a_part + (size_t)b * CT_TILE_M * 128;
-          ct_tma_load_2d(da, ma, &bar_full[s], kcol, P.a_row0 + row0);
-          ct_tma_load_2d(da + 64 * 128, ma, &bar_full[s], kcol, P.a_row0 + row0 + 64);
-          uint8_t* db = st + 2 * a_part + part * b_part + (size_t)b * CT_TILE_N * 128;
-          ct_tma_load_2d(db, mb, &bar_full[s], kcol, col0);
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t kbg = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int row0 = (t % tiles_m) * CT_TILE_M, col0 = (t / tiles_m) * CT_TILE_N;
+        const int KP = nbox * 32;
+        for (int p = 0; p < np; ++p) {
+          const CUtensorMap* ma = &P.maps[P.prod_a[p]];
+          const CUtensorMap* mb = &P.maps[P.prod_b[p]];
+          for (int b = 0; b < nbox; ++b, ++kbg) {
+            const uint32_t s = kbg % CT_STAGES;
+            if (kbg >= CT_STAGES) ct_mbar_wait(&bar_empty[s], ((kbg / CT_STAGES) - 1u) & 1u);
+            uint8_t* st = smem + (size_t)s * CT_STAGE_BYTES;
+            ct_mbar_expect_tx(&bar_full[s], CT_STAGE_BYTES);
+            for (int part = 0; part < 2; ++part) {       // 0: raw, 1: lo
+              const int kcol = part * KP + b * 32;
+              uint8_t* da = st + part * A_BOX;
+              ct_tma_load_2d(da, ma, &bar_full[s], kcol, P.a_row0 + row0);
+              ct_tma_load_2d(da + 64 * 128, ma, &bar_full[s], kcol, P.a_row0 + row0 + 64);
+              ct_tma_load_2d(st + 2 * A_BOX + part * B_BOX, mb, &bar_full[s], kcol, col0);
+            }
+          }
         }
       }
-    };
-    const uint32_t idesc = ct_idesc();
-    const int np = P.n_products;
-    for (int p = 0; p < nstage && p < np; ++p) issue_loads(p);
-    for (int p = 0; p < np; ++p) {
-      const int s = p % nstage;
-      ct_mbar_wait(&bar_full[s], (p / nstage) & 1);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = ct_idesc();
+      uint32_t kbg = 0, it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        if (it > 0) {   // the previous tile's accumulators have been read out
+          ct_mbar_wait(&bar_tmem_empty, (it - 1u) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int p = 0; p < np; ++p) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)p * CT_TILE_N;
+          for (int b = 0; b < nbox; ++b, ++kbg) {
+            const uint32_t s = kbg % CT_STAGES;
+            ct_mbar_wait(&bar_full[s], (kbg / CT_STAGES) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sbase = ct_smem_u32(smem + (size_t)s * CT_STAGE_BYTES);
+            const int nks = min(4, P.ksteps - 4 * b);   // 8-float k-steps of this box that hold columns < Z (the rest is zero padding)
+            // chains: (A raw, B raw), (A lo, B raw), (A raw, B lo)
+            for (int chain = 0; chain < 3; ++chain) {
+              const uint32_t abase = sbase + (chain == 1 ? A_BOX : 0u);
+              const uint32_t bbase = sbase + 2u * A_BOX + (chain == 2 ? B_BOX : 0u);
+              for (int ks = 0; ks < nks; ++ks)
+                ct_mma_tf32(d_tmem, ct_umma_desc(abase + (uint32_t)ks * 32u), ct_umma_desc(bbase + (uint32_t)ks * 32u), idesc,
+                            (b | chain | ks) != 0 ? 1u : 0u);
+            }
+            ct_mma_commit(&bar_empty[s]);   // arrives when the MMAs above have finished reading this stage
+          }
+        }
+        ct_mma_commit(&bar_accum);
+      }
+    }
+  } else {
+    // ===== epilogue: thread = one row of the tile (TMEM lane), 16 columns at a time =====
+    const int q = warp & 3;   // TMEM lane quadrant this warp may read
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* scr = reinterpret_cast<float*>(smem + (size_t)CT_STAGES * CT_STAGE_BYTES) + q * (3 * 32 * CT_SCR_LD);
+    double a_off = 0.0, a_diag = 0.0, a_cov = 0.0, a_covd = 0.0, a_tm = 0.0, a_m1 = 0.0;
+    const float inv_noff = P.inv_noff, inv_n = P.inv_n, c4 = P.c4;
+    const bool g_vec = (P.ld % 4 == 0) && (((reinterpret_cast<uintptr_t>(P.G1) | reinterpret_cast<uintptr_t>(P.G2) |
+                                              reinterpret_cast<uintptr_t>(P.Gc ? P.Gc : P.G1)) & 15u) == 0);
+    const int n_arr = P.mode == CT_MODE_ROW ? 3 : 2;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int row0 = (t % tiles_m) * CT_TILE_M, col0 = (t / tiles_m) * CT_TILE_N;
+      const int row = row0 + q * 32 + lane;
+      const bool row_ok = row < P.nr;
+      const int diag_col = P.diag0 + row;
+      float g_row = 0.f;
+      if (P.mode == CT_MODE_ROW && row_ok) g_row = P.disc[(size_t)row * P.disc_stride];
+      ct_mbar_wait(&bar_accum, it & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sbase = ct_smem_u32(smem + (size_t)s * stage_bytes);
-      const uint32_t d_tmem = tmem_base + (uint32_t)p * CT_TILE_N;
-      // chains: (A raw, B raw), (A lo, B raw), (A raw, B lo)
-      for (int chain = 0; chain < 3; ++chain) {
-        const uint32_t abase = sbase + (chain == 1 ? a_part : 0u);
-        const uint32_t bbase = sbase + 2u * a_part + (chain == 2 ? b_part : 0u);
-        for (int ks = 0; ks < P.ksteps; ++ks) {
-          const uint32_t box = (uint32_t)ks >> 2, kin = (uint32_t)ks & 3u;
-          const uint64_t ad = ct_umma_desc(abase + box * CT_TILE_M * 128u + kin * 32u);
-          const uint64_t bd = ct_umma_desc(bbase + box * CT_TILE_N * 128u + kin * 32u);
-          ct_mma_tf32(d_tmem, ad, bd, idesc, (chain | ks) != 0 ? 1u : 0u);
-        }
-      }
-      ct_mma_commit(&bar_empty[s]);   // arrives when the MMAs above have finished reading this stage
-      if (p + nstage < np) {
-        ct_mbar_wait(&bar_empty[s], (p / nstage) & 1);
-        issue_loads(p + nstage);
-      }
-    }
-    ct_mma_commit(&bar_done);
-  }
-  __syncwarp();
-  ct_mbar_wait(&bar_done, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-  // ---- epilogue: thread = one row of the tile (TMEM lane), 16 columns at a time ----
-  const int r_local = warp * 32 + lane;
-  const int row = row0 + r_local;
-  const bool row_ok = row < P.nr;
-  const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-  double a_off = 0.0, a_diag = 0.0, a_cov = 0.0, a_covd = 0.0, a_tm = 0.0, a_m1 = 0.0;
-  const float inv_noff = P.inv_noff, inv_n = P.inv_n, c4 = P.c4;
-  const int diag_col = P.diag0 + row;
-  float g_row = 0.f;
-  if (P.mode == CT_MODE_ROW && row_ok) g_row = P.disc[(size_t)row * P.disc_stride];
-  // G tiles leave through shared memory: a thread owns one ROW of the tile (its TMEM lane), so direct stores would put the 32 lanes of
-  // every store instruction on 32 different rows (one 32-byte sector each for 4 useful bytes: 8x write amplification in L2, and the
-  // kernel's largest cost).  Each warp stages its 32 x 16 chunk of G1 / G2 / Gc in the operand ring (free once bar_done has fired)
-  // and writes it back as 128-bit stores, 4 lanes per row: full sectors.  The transposed copies Gt1 / Gt2 are coalesced as they are
-  // (for a fixed column the lanes are consecutive rows).
-  constexpr int SCR_LD = 20;   // floats per staged row: 16 + 4, conflict-free for the 128-bit row writes
-  float* scr = reinterpret_cast<float*>(smem) + warp * (3 * 32 * SCR_LD);
-  const bool g_vec = (P.ld % 4 == 0) && (((reinterpret_cast<uintptr_t>(P.G1) | reinterpret_cast<uintptr_t>(P.G2) |
-                                            reinterpret_cast<uintptr_t>(P.Gc ? P.Gc : P.G1)) & 15u) == 0);
-  const int n_arr = P.mode == CT_MODE_ROW ? 3 : 2;
+      // G tiles leave through shared memory: a thread owns one ROW of the tile (its TMEM lane), so direct stores would put the 32 lanes
+      // of every store instruction on 32 different rows (one 32-byte sector each for 4 useful bytes).  Each warp stages its 32 x 16
+      // chunk of G1 / G2 / Gc and writes it back as 128-bit stores, 4 lanes per row: full sectors.  The transposed copies Gt1 / Gt2 are
+      // coalesced as they are (for a fixed column the lanes are consecutive rows).
 #pragma unroll 1
-  for (int cb = 0; cb < CT_TILE_N; cb += 16) {
-    float m1[16], m2[16], t1[16], t2[16], cv[16];
-    ct_tmem_ld16(lane_addr + 0 * CT_TILE_N + cb, m1);
-    ct_tmem_ld16(lane_addr + 1 * CT_TILE_N + cb, m2);
-    ct_tmem_ld16(lane_addr + 2 * CT_TILE_N + cb, t1);
-    ct_tmem_ld16(lane_addr + 3 * CT_TILE_N + cb, t2);
-    if (P.mode == CT_MODE_ROW) ct_tmem_ld16(lane_addr + 4 * CT_TILE_N + cb, cv);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    float g1v[16], g2v[16], gcv[16];
+      for (int cb = 0; cb < CT_TILE_N; cb += 16) {
+        float m1[16], m2[16], t1[16], t2[16], cv[16];
+        ct_tmem_ld16(lane_addr + 0 * CT_TILE_N + cb, m1);
+        ct_tmem_ld16(lane_addr + 1 * CT_TILE_N + cb, m2);
+        ct_tmem_ld16(lane_addr + 2 * CT_TILE_N + cb, t1);
+        ct_tmem_ld16(lane_addr + 3 * CT_TILE_N + cb, t2);
+        if (P.mode == CT_MODE_ROW) ct_tmem_ld16(lane_addr + 4 * CT_TILE_N + cb, cv);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (cb + 16 >= CT_TILE_N) {   // last chunk read: the issuer may overwrite the accumulators with the next tile
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ct_smem_u32(&bar_tmem_empty)) : "memory");
+        }
+        float g1v[16], g2v[16], gcv[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int col = col0 + cb + j;
-      float g1 = 0.f, g2 = 0.f, gc = 0.f;
-      if (row_ok && col < P.nc) {
-        const float tm = fminf(t1[j], t2[j]);
-        if (P.mode == CT_MODE_ROW) {
-          a_tm += tm; a_m1 += m1[j];
-          if (col != diag_col) {
-            const float d1 = m1[j] - g_row * tm, d2 = m2[j] - g_row * tm;
-            a_off += (double)d1 * d1 + (double)d2 * d2;
-            a_cov += (double)cv[j] * cv[j];
-            g1 = d1 * inv_noff; g2 = d2 * inv_noff; gc = c4 * cv[j];
-          } else {
-            a_diag += (double)m1[j] + (double)m2[j];
-            a_covd += cv[j];
-            g1 = -inv_n; g2 = -inv_n; gc = 0.f;
+        for (int j = 0; j < 16; ++j) {
+          const int col = col0 + cb + j;
+          float g1 = 0.f, g2 = 0.f, gc = 0.f;
+          if (row_ok && col < P.nc) {
+            const float tm = fminf(t1[j], t2[j]);
+            if (P.mode == CT_MODE_ROW) {
+              a_tm += tm; a_m1 += m1[j];
+              if (col != diag_col) {
+                const float d1 = m1[j] - g_row * tm, d2 = m2[j] - g_row * tm;
+                a_off += (double)d1 * d1 + (double)d2 * d2;
+                a_cov += (double)cv[j] * cv[j];
+                g1 = d1 * inv_noff; g2 = d2 * inv_noff; gc = c4 * cv[j];
+              } else {
+                a_diag += (double)m1[j] + (double)m2[j];
+                a_covd += cv[j];
+                g1 = -inv_n; g2 = -inv_n; gc = 0.f;
+              }
+              if (P.Gt1) {  // transposed copies: for a fixed column the 32 lanes of a warp write 32 consecutive floats
+                const size_t ot = (size_t)col * P.ld + row;
+                P.Gt1[ot] = g1; P.Gt2[ot] = g2;
+              }
+            } else {
+              // COL mode: rows are the LOCAL columns t of the loss matrices, cols run over all global rows s
+              if (col != diag_col) {
+                const float g = __ldg(P.disc + (size_t)col * P.disc_stride);
+                g1 = (m1[j] - g * tm) * inv_noff; g2 = (m2[j] - g * tm) * inv_noff;
+              } else {
+                g1 = -inv_n; g2 = -inv_n;
+              }
+            }
           }
-          if (P.Gt1) {  // transposed copies: for a fixed column the 32 lanes of a warp write 32 consecutive floats
-            const size_t ot = (size_t)col * P.ld + row;
-            P.Gt1[ot] = g1; P.Gt2[ot] = g2;
-          }
-        } else {
-          // COL mode: rows are the LOCAL columns t of the loss matrices, cols run over all global rows s
-          if (col != diag_col) {
-            const float g = __ldg(P.disc + (size_t)col * P.disc_stride);
-            g1 = (m1[j] - g * tm) * inv_noff; g2 = (m2[j] - g * tm) * inv_noff;
-          } else {
-            g1 = -inv_n; g2 = -inv_n;
+          g1v[j] = g1; g2v[j] = g2; gcv[j] = gc;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          *reinterpret_cast<float4*>(scr + (0 * 32 + lane) * CT_SCR_LD + j) = make_float4(g1v[j], g1v[j + 1], g1v[j + 2], g1v[j + 3]);
+          *reinterpret_cast<float4*>(scr + (1 * 32 + lane) * CT_SCR_LD + j) = make_float4(g2v[j], g2v[j + 1], g2v[j + 2], g2v[j + 3]);
+          if (P.mode == CT_MODE_ROW)
+            *reinterpret_cast<float4*>(scr + (2 * 32 + lane) * CT_SCR_LD + j) = make_float4(gcv[j], gcv[j + 1], gcv[j + 2], gcv[j + 3]);
+        }
+        __syncwarp();
+        {
+          const int rr = lane >> 2, c4o = (lane & 3) * 4;
+          const int col = col0 + cb + c4o;
+#pragma unroll
+          for (int r8 = 0; r8 < 4; ++r8) {
+            const int r = r8 * 8 + rr;
+            const int grow = row0 + q * 32 + r;
+            if (grow >= P.nr || col >= P.nc) continue;
+            for (int a = 0; a < n_arr; ++a) {
+              float* G = a == 0 ? P.G1 : (a == 1 ? P.G2 : P.Gc);
+              const float4 v = *reinterpret_cast<const float4*>(scr + (a * 32 + r) * CT_SCR_LD + c4o);
+              float* gp = G + (size_t)grow * P.ld + col;
+              if (g_vec && col + 3 < P.nc) *reinterpret_cast<float4*>(gp) = v;
+              else {
+                gp[0] = v.x;
+                if (col + 1 < P.nc) gp[1] = v.y;
+                if (col + 2 < P.nc) gp[2] = v.z;
+                if (col + 3 < P.nc) gp[3] = v.w;
+              }
+            }
           }
         }
-      }
-      g1v[j] = g1; g2v[j] = g2; gcv[j] = gc;
-    }
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      *reinterpret_cast<float4*>(scr + (0 * 32 + lane) * SCR_LD + j) = make_float4(g1v[j], g1v[j + 1], g1v[j + 2], g1v[j + 3]);
-      *reinterpret_cast<float4*>(scr + (1 * 32 + lane) * SCR_LD + j) = make_float4(g2v[j], g2v[j + 1], g2v[j + 2], g2v[j + 3]);
-      if (P.mode == CT_MODE_ROW)
-        *reinterpret_cast<float4*>(scr + (2 * 32 + lane) * SCR_LD + j) = make_float4(gcv[j], gcv[j + 1], gcv[j + 2], gcv[j + 3]);
-    }
-    __syncwarp();
-    {
-      const int rr = lane >> 2, c4o = (lane & 3) * 4;
-      const int col = col0 + cb + c4o;
-#pragma unroll
-      for (int r8 = 0; r8 < 4; ++r8) {
-        const int r = r8 * 8 + rr;
-        const int grow = row0 + warp * 32 + r;
-        if (grow >= P.nr || col >= P.nc) continue;
-        for (int a = 0; a < n_arr; ++a) {
-          float* G = a == 0 ? P.G1 : (a == 1 ? P.G2 : P.Gc);
-          const float4 v = *reinterpret_cast<const float4*>(scr + (a * 32 + r) * SCR_LD + c4o);
-          float* gp = G + (size_t)grow * P.ld + col;
-          if (g_vec && col + 3 < P.nc) *reinterpret_cast<float4*>(gp) = v;
-          else {
-            gp[0] = v.x;
-            if (col + 1 < P.nc) gp[1] = v.y;
-            if (col + 2 < P.nc) gp[2] = v.z;
-            if (col + 3 < P.nc) gp[3] = v.w;
-          }
-        }
+        __syncwarp();
       }
     }
-    __syncwarp();
-  }
-  if (P.mode == CT_MODE_ROW) {
-    double vals[6] = {a_off, a_diag, a_cov, a_covd, a_tm, a_m1};
+    if (P.mode == CT_MODE_ROW) {   // the loss sums of every tile this CTA walked: one reduction, six atomics per CTA
+      double vals[6] = {a_off, a_diag, a_cov, a_covd, a_tm, a_m1};
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const double v = warp_sum_d(vals[i]);
-      if (lane == 0) red[i][warp] = v;
+      for (int i = 0; i < 6; ++i) {
+        const double v = warp_sum_d(vals[i]);
+        if (lane == 0) red[i][q] = v;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -332,7 +362,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
     const int slot[6] = {ACC_OFFDIAG_SQ, ACC_DIAG, ACC_COV_OFF_SQ, ACC_COV_DIAG, ACC_TARGET_M, ACC_M1};
     atomicAdd(P.acc + slot[threadIdx.x], red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3]);
   }
-  if (warp == 0) {
+  if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(CT_TMEM_COLS) : "memory");
   }
 }

@@ -1019,9 +1019,9 @@ static int build_plan(fb_handle* h) {
     }
     cp.nbox = nbox; cp.ksteps = fb_ceil_div(Z, 8); cp.ld = M1.ld; cp.inv_noff = inv_noff; cp.inv_n = inv_n;
     cp.c4 = 4.0f * c.ortho_coef * inv_noff; cp.acc = acc; cp.diag0 = c.row_offset;
-    const size_t stage_bytes = (size_t)nbox * (2 * CT_TILE_M + 2 * CT_TILE_N) * 128;
-    const size_t smem_bytes = (2 * stage_bytes <= 200u * 1024u ? 2 : 1) * stage_bytes + 1024;
+    const size_t smem_bytes = CT_SMEM_BYTES;   // 4 ring stages of one K-box each + the epilogue scratch
     h->contract_smem = smem_bytes;
+    const int ct_sms = h->sm_count > 0 ? h->sm_count : FB_SM_COUNT;
     const double tile_flops = 2.0 * 3.0 * cp.ksteps * 8.0;  // per pair, per product (3 chains)
     {
       ContractParams r = cp;
@@ -1031,9 +1031,9 @@ static int build_plan(fb_handle* h) {
       r.G1 = M1.p; r.G2 = M2.p; r.Gc = Cov.p;
       r.Gt1 = (n == B) ? Mt1.p : nullptr; r.Gt2 = (n == B) ? Mt2.p : nullptr;
       r.disc = bl.p + disc_col; r.disc_stride = bl.ld;
-      b.push([r, smem_bytes](cudaStream_t s) {
-        dim3 grid(fb_ceil_div(r.nc, CT_TILE_N), fb_ceil_div(r.nr, CT_TILE_M));
-        fb_launch_pdl(k_contract_tc, dim3(grid), dim3(CT_THREADS), smem_bytes, s, r);
+      b.push([r, smem_bytes, ct_sms](cudaStream_t s) {
+        const int tiles = fb_ceil_div(r.nc, CT_TILE_N) * fb_ceil_div(r.nr, CT_TILE_M);   // persistent: one CTA per SM walks them
+        fb_launch_pdl(k_contract_tc, dim3(std::min(tiles, ct_sms)), dim3(CT_THREADS), smem_bytes, s, r);
         return cudaGetLastError();
       }, FB_OPK_CONTRACT, 5.0 * tile_flops * B * (double)n, 4.0 * (5.0 * B * (double)n + 6.0 * n * 2.0 * KP));
     }
@@ -1044,9 +1044,9 @@ static int build_plan(fb_handle* h) {
       r.n_products = 4; r.mode = CT_MODE_COL; r.nr = B; r.nc = n; r.a_row0 = c.row_offset;
       r.G1 = Mt1.p; r.G2 = Mt2.p;
       r.disc = bg.p + disc_col; r.disc_stride = bg.ld;
-      b.push([r, smem_bytes](cudaStream_t s) {
-        dim3 grid(fb_ceil_div(r.nc, CT_TILE_N), fb_ceil_div(r.nr, CT_TILE_M));
-        fb_launch_pdl(k_contract_tc, dim3(grid), dim3(CT_THREADS), smem_bytes, s, r);
+      b.push([r, smem_bytes, ct_sms](cudaStream_t s) {
+        const int tiles = fb_ceil_div(r.nc, CT_TILE_N) * fb_ceil_div(r.nr, CT_TILE_M);   // persistent: one CTA per SM walks them
+        fb_launch_pdl(k_contract_tc, dim3(std::min(tiles, ct_sms)), dim3(CT_THREADS), smem_bytes, s, r);
         return cudaGetLastError();
       }, FB_OPK_CONTRACT, 4.0 * tile_flops * B * (double)n, 4.0 * (2.0 * B * (double)n + 6.0 * n * 2.0 * KP));
     }
