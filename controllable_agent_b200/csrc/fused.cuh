@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_stack(const char* __res
                                                                unsigned long long* times) {
   fb_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t fs_smem_raw[];
-  __shared__ __align__(16) float epi_scratch[4 * 32 * TC_EPI_LD];
+  __shared__ __align__(16) float epi_scratch[4 * TC_EPI_SCR];
   __shared__ __align__(8) TcShared sh;
   __shared__ __align__(16) FsHeader hdr;
   __shared__ __align__(16) FsItem items[FS_MAX_ITEMS];
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_stack(const char* __res
       switch (item.type) {
         case FS_GEMM_TC: {
           const FsGemmArgs* a = reinterpret_cast<const FsGemmArgs*>(args);
-          tc_gemm_roles<false, 1>(a->descs, a->hdr, vcta, ng, &sh, epi_scratch, smem_base, smem_gen);
+          tc_gemm_roles<false, 1, 1>(a->descs, a->hdr, vcta, ng, &sh, epi_scratch, smem_base, smem_gen);
           break;
         }
         case FS_LN_FWD: {

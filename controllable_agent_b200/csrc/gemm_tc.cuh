@@ -48,11 +48,13 @@
 #define TC_A_TILE_BYTES (TC_BM * TC_ROW_BYTES)
 #define TC_KB_PER_32 (32 / TC_BK)      // k-blocks per 32 floats of K: the unit the host-side cost model and the accumulator rotation count in
 #define TC_MAX_STAGES 6
-#define TC_THREADS 192
+#define TC_THREADS 320                 // warp 0 TMA, warp 1 MMA, warps 2..5 builders + epilogue, warps 6..9 epilogue helpers
+#define TC_EPI_CW 16                   // columns of one epilogue chunk
 #define TC_RING_BYTES 196608           // shared-memory ring; a stage is [A raw | B raw (BN rows) | A lo | B lo], rows of TC_ROW_BYTES.
                                        // (3 stages at BN = 128 and TC_BK = 32)
 #define TC_SMEM_BYTES (TC_RING_BYTES + 1024)
-#define TC_EPI_LD 36                   // padded row of the epilogue scratch (floats): conflict-free 128-bit writes and reads
+#define TC_EPI_LD 20                   // padded row of the epilogue scratch (floats): 16 + 4, conflict-free 128-bit row writes
+#define TC_EPI_SCR (32 * TC_EPI_LD)    // floats of one epilogue warp's scratch (>= 16 x 33 for the transposed copy)
 #define TC_A_SLOT_COLS 64              // TS form: TMEM columns of one k-block of A (hi: 32 columns, lo: 32 columns; lane = tile row)
 #define TC_MAX_ASLOTS 4                // A slots in flight (2 at BN = 128: 3 x 128 accumulator columns + 2 x 64 = 512)
 
@@ -315,7 +317,7 @@ struct TcShared {
 };
 
 // one thread: (re)initialise the pipeline barriers of a launch / of a GEMM item of the fused kernel (reinit: the objects are live)
-__device__ __forceinline__ void tc_init_barriers(TcShared* sh, bool reinit, int group_ctas = 1) {
+__device__ __forceinline__ void tc_init_barriers(TcShared* sh, bool reinit, int group_ctas = 1, int epi_groups = 1) {
   if (reinit) {
     for (int s = 0; s < TC_MAX_STAGES; ++s) {
       asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(&sh->bar_raw[s])) : "memory");
@@ -333,7 +335,7 @@ __device__ __forceinline__ void tc_init_barriers(TcShared* sh, bool reinit, int 
   }
   for (int j = 0; j < TC_MAX_ASLOTS; ++j) tc_mbar_init(&sh->bar_afree[j], 1);
   tc_mbar_init(&sh->bar_accum, 1);
-  tc_mbar_init(&sh->bar_tmem_empty, 4 * group_ctas);
+  tc_mbar_init(&sh->bar_tmem_empty, 4 * epi_groups * group_ctas);   // one arrival per epilogue warp
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
@@ -349,7 +351,10 @@ __device__ __forceinline__ void tc_init_barriers(TcShared* sh, bool reinit, int 
 // shared-memory traffic instead of 16 + 16; rank 0's MMA warp issues M = 256 instructions that read both CTAs' operands and write
 // both CTAs' tensor memory; the builders / epilogue warps of both CTAs arrive on rank 0's barriers, tcgen05.commit multicasts the
 // completions to both.  `vcta` / `ncta` then count pairs.
-template <bool TS, int NCTA>
+// EG: epilogue warp groups.  The epilogue of a tile is instruction-latency-bound with ONE warp per scheduler (TMEM loads, transpose,
+// masks, stores: ~5 us per 128 x 128 tile, serial with the mainloop because TMEM holds one tile's accumulators), so k_gemm_tc runs a
+// second group (warps 6..9, same TMEM lane quadrants) that takes every other 16-column chunk.  The fused kernel keeps one group.
+template <bool TS, int NCTA, int EG = 1>
 __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcLaunch& L, int vcta, int ncta, TcShared* sh,
                                               float* epi_scratch, uint32_t smem_base, uint8_t* smem_gen, uint32_t rank = 0) {
   const int total = L.total, ring_bn = L.ring_bn;
@@ -471,11 +476,12 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
         commit(&bar_accum);
       }
     }
-  } else if (warp < 6) {
-    // ===== lo-part builders (128 threads), then epilogue =====
+  } else if (warp < 2 + 4 * EG) {
+    // ===== lo-part builders (group 0: 128 threads), then epilogue (every group) =====
     const int t = threadIdx.x - 64;
     const int q = warp & 3;                 // TMEM lane quadrant this warp may read
-    float* scr = epi_scratch + q * (32 * TC_EPI_LD);
+    const int grp = (warp - 2) >> 2;        // 0: builders + epilogue, 1: epilogue helpers
+    float* scr = epi_scratch + (grp * 4 + q) * TC_EPI_SCR;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t kbg = 0, itc = 0;
     for (int base = 0; base < total; base += ncta) {
@@ -498,7 +504,7 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
       float* __restrict__ CT_lo = d->CT_lo;
       const int ldct = d->ldct;
       const bool build_a = !TS && !(flags & (TC_A_PRE | TC_DBG_NOBUILD)), build_b = !(flags & (TC_B_PRE | TC_DBG_NOBUILD));
-      for (int kb = 0; kb < nk; ++kb, ++kbg) {
+      for (int kb = 0; kb < (grp == 0 ? nk : 0); ++kb, ++kbg) {   // (the helper group only takes part in the epilogue)
         const uint32_t s = kbg % (uint32_t)nst;
         tc_mbar_wait(&bar_raw[s], (kbg / (uint32_t)nst) & 1u);
         const float4* raw = reinterpret_cast<const float4*>(smem_gen + (size_t)s * stage_bytes);
@@ -568,29 +574,29 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
       const bool m_vec = ((ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0);
       const bool b_vec = (reinterpret_cast<uintptr_t>(bias) & 15u) == 0;
       const int n_hh = min(n_hh_max, (nk + TC_KB_PER_32 - 1) / TC_KB_PER_32);   // hi.hi accumulators that were written (the corrections follow the n_hh_max)
-      const int sub = lane >> 3, c4 = (lane & 7) * 4;
+      const int sub = lane >> 2, c4 = (lane & 3) * 4;   // chunk = 32 rows x 16 columns: lane = 4 consecutive columns of 4 different rows
       const bool split = L.p[pi].splitk > 1;   // partial sums: added into the zeroed C; the bias rides on the first k-range
       if (split && kb0 > 0) bias = nullptr;
-      for (int cb = 0; cb < ((flags & TC_DBG_NOEPI) ? 0 : bn); cb += 32) {
-        if (n0 + cb >= N) break;          // warp-uniform: nothing of this 32-column chunk is inside the matrix
-        // the saved activations this thread's 8 output float4s are masked with: issued first, so that their L2 latency
-        // hides behind the TMEM reads and the transpose (a load -> use -> store chain per row serialises 8 round trips)
+      for (int cb = grp * TC_EPI_CW; cb < ((flags & TC_DBG_NOEPI) ? 0 : bn); cb += TC_EPI_CW * EG) {   // the groups interleave the chunks
+        if (n0 + cb >= N) break;          // warp-uniform: nothing of this chunk is inside the matrix
+        // the saved activations this thread's 4 output float4s are masked with: issued first, so that their L2 latency
+        // hides behind the TMEM reads and the transpose (a load -> use -> store chain per row serialises the round trips)
         const int col = n0 + cb + c4;
         const bool full = col + 3 < N;
-        float4 mk4[8];
+        float4 mk4[4];
         if (flags & (GF_MASK_RELU | GF_MASK_TANH)) {
 #pragma unroll
-          for (int r8 = 0; r8 < 8; ++r8) {
-            const int row = m0 + q * 32 + r8 * 4 + sub;
-            mk4[r8] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int r4 = 0; r4 < 4; ++r4) {
+            const int row = m0 + q * 32 + r4 * 8 + sub;
+            mk4[r4] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < M && col < N) {
               const float* mp = mask + (size_t)row * ldmask + col;
-              if (m_vec && full) mk4[r8] = *reinterpret_cast<const float4*>(mp);
+              if (m_vec && full) mk4[r4] = *reinterpret_cast<const float4*>(mp);
               else {
-                mk4[r8].x = mp[0];
-                if (col + 1 < N) mk4[r8].y = mp[1];
-                if (col + 2 < N) mk4[r8].z = mp[2];
-                if (col + 3 < N) mk4[r8].w = mp[3];
+                mk4[r4].x = mp[0];
+                if (col + 1 < N) mk4[r4].y = mp[1];
+                if (col + 2 < N) mk4[r4].z = mp[2];
+                if (col + 3 < N) mk4[r4].w = mp[3];
               }
             }
           }
@@ -600,26 +606,26 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
           if (b_vec && full) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + col)); bz[0] = t4.x; bz[1] = t4.y; bz[2] = t4.z; bz[3] = t4.w; }
           else { for (int j = 0; j < 4; ++j) if (col + j < N) bz[j] = __ldg(bias + col + j); }
         }
-        float v[32], u[32];
-        tc_tmem_ld32(lane_addr + (uint32_t)(n_hh_max * bn + cb), v);   // correction chains first (smallest terms)
+        float v[16], u[16];
+        tc_tmem_ld16(lane_addr + (uint32_t)(n_hh_max * bn + cb), v);   // correction chains first (smallest terms)
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         for (int a = n_hh - 1; a >= 0; --a) {
-          tc_tmem_ld32(lane_addr + (uint32_t)(a * bn + cb), u);
+          tc_tmem_ld16(lane_addr + (uint32_t)(a * bn + cb), u);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += u[j];
+          for (int j = 0; j < 16; ++j) v[j] += u[j];
         }
-        // thread = one row of the chunk -> scratch -> thread = 4 consecutive columns of 8 different rows
+        // thread = one row of the chunk -> scratch -> thread = 4 consecutive columns of 4 different rows
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(scr + lane * TC_EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(scr + lane * TC_EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
-        float4 xf[8];   // final values (kept for the transposed copy)
+        float4 xf[4];   // final values (kept for the transposed copy)
 #pragma unroll
-        for (int r8 = 0; r8 < 8; ++r8) {
-          const int r = r8 * 4 + sub;
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const int r = r4 * 8 + sub;
           const int row = m0 + q * 32 + r;
           const float4 x4 = *reinterpret_cast<const float4*>(scr + r * TC_EPI_LD + c4);
-          xf[r8] = make_float4(0.f, 0.f, 0.f, 0.f);
+          xf[r4] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row >= M || col >= N) continue;
           float x[4] = {x4.x + bz[0], x4.y + bz[1], x4.z + bz[2], x4.w + bz[3]};
           if (flags & GF_RELU) {
@@ -627,7 +633,7 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
             for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
           }
           if (flags & (GF_MASK_RELU | GF_MASK_TANH)) {
-            const float mk[4] = {mk4[r8].x, mk4[r8].y, mk4[r8].z, mk4[r8].w};
+            const float mk[4] = {mk4[r4].x, mk4[r4].y, mk4[r4].z, mk4[r4].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (flags & GF_MASK_RELU) x[j] = (mk[j] > 0.f) ? x[j] : 0.f;
@@ -640,7 +646,7 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
             else { for (int j = 0; j < 4; ++j) if (col + j < N) atomicAdd(cp + j, x[j]); }
           } else if (c_vec && full) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
           else { for (int j = 0; j < 4; ++j) if (col + j < N) cp[j] = x[j]; }
-          xf[r8] = make_float4(x[0], x[1], x[2], x[3]);
+          xf[r4] = make_float4(x[0], x[1], x[2], x[3]);
         }
         if (CT) {
           // transposed copy: final values back into the scratch, column-major with an odd pitch (conflict-free both ways), then
@@ -648,17 +654,17 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
           // 8 lanes = one 128-byte run
           __syncwarp();
 #pragma unroll
-          for (int r8 = 0; r8 < 8; ++r8) {
-            const int r = r8 * 4 + sub;
-            scr[(c4 + 0) * 33 + r] = xf[r8].x; scr[(c4 + 1) * 33 + r] = xf[r8].y;
-            scr[(c4 + 2) * 33 + r] = xf[r8].z; scr[(c4 + 3) * 33 + r] = xf[r8].w;
+          for (int r4 = 0; r4 < 4; ++r4) {
+            const int r = r4 * 8 + sub;
+            scr[(c4 + 0) * 33 + r] = xf[r4].x; scr[(c4 + 1) * 33 + r] = xf[r4].y;
+            scr[(c4 + 2) * 33 + r] = xf[r4].z; scr[(c4 + 3) * 33 + r] = xf[r4].w;
           }
           __syncwarp();
           const int g = lane & 7, jj = lane >> 3;
           const int rowT = m0 + q * 32 + 4 * g;
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            const int cl = c8 * 4 + jj, colT = n0 + cb + cl;
+          for (int c4i = 0; c4i < 4; ++c4i) {
+            const int cl = c4i * 4 + jj, colT = n0 + cb + cl;
             if (colT < N && rowT < M) {
               const float4 t4 = make_float4(scr[cl * 33 + 4 * g], scr[cl * 33 + 4 * g + 1], scr[cl * 33 + 4 * g + 2], scr[cl * 33 + 4 * g + 3]);
               *reinterpret_cast<float4*>(CT + (size_t)colT * ldct + rowT) = t4;
@@ -681,7 +687,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
   static_assert(!TS || TC_BK == 32, "the TS form reads SWIZZLE_128B rows");
   fb_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
-  __shared__ __align__(16) float epi_scratch[4 * 32 * TC_EPI_LD];
+  __shared__ __align__(16) float epi_scratch[8 * TC_EPI_SCR];   // two epilogue groups of four warps
   __shared__ __align__(8) TcShared sh;
 
   const int warp = threadIdx.x >> 5;
@@ -689,7 +695,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
   uint8_t* smem_gen = tc_smem_raw + (smem_base - tc_smem_u32(tc_smem_raw));
   const uint32_t rank = NCTA == 2 ? tc_cluster_rank() : 0u;
 
-  if (threadIdx.x == 0) tc_init_barriers(&sh, false, NCTA);
+  if (threadIdx.x == 0) tc_init_barriers(&sh, false, NCTA, 2);
   if (warp == 1) {   // (a pair allocates the same columns in both CTAs: the same warp of each issues the cta_group::2 form)
     if constexpr (NCTA == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sh.tmem_base)), "r"(512) : "memory");
@@ -705,7 +711,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   fb_pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
-  tc_gemm_roles<TS, NCTA>(descs, L, (int)(blockIdx.x / NCTA), (int)(gridDim.x / NCTA), &sh, epi_scratch, smem_base, smem_gen, rank);
+  tc_gemm_roles<TS, NCTA, 2>(descs, L, (int)(blockIdx.x / NCTA), (int)(gridDim.x / NCTA), &sh, epi_scratch, smem_base, smem_gen, rank);
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if constexpr (NCTA == 2) tc_cluster_sync();   // neither CTA leaves (or frees tensor memory) while the pair's MMAs / commits can still touch it

@@ -368,15 +368,11 @@ __global__ void __launch_bounds__(256) k_ln_tanh_fwd(const __grid_constant__ Des
 
 // Vectorised forward for D <= 1024 and 16-byte aligned rows: the row lives in registers (one global read), two-pass
 // mean / variance on the register copy like nn.LayerNorm, float4 stores.
-__device__ __forceinline__ void ln_tanh_fwd_v4_body(const LnDesc* descs, const int nprob, int total_rows, const int bid) {
-
+// FULL: D == 1024 exactly: no column-bound tests (see ln_tanh_bwd_v4_rows)
+template <bool FULL>
+__device__ __forceinline__ void ln_tanh_fwd_v4_row(const LnDesc& d, const int r, const int lane) {
   constexpr int NV = 8;
-  const int gw = (bid * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (gw >= total_rows) return;
-  int p = 0;
-  while (p + 1 < nprob && descs[p + 1].row_begin <= gw) ++p;
-  const LnDesc d = descs[p];
-  const int r = gw - d.row_begin, D = d.D;
+  const int D = d.D;
   const float4* x = reinterpret_cast<const float4*>(d.x + (size_t)r * d.ld);
   float4 v[NV];
   float s = 0.f;
@@ -384,11 +380,13 @@ __device__ __forceinline__ void ln_tanh_fwd_v4_body(const LnDesc* descs, const i
   for (int i = 0; i < NV; ++i) {
     const int q = lane + 32 * i, c = q * 4;
     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < D) {
+    if (FULL || c < D) {
       v[i] = x[q];
-      if (c + 1 >= D) v[i].y = 0.f;
-      if (c + 2 >= D) v[i].z = 0.f;
-      if (c + 3 >= D) v[i].w = 0.f;
+      if (!FULL) {
+        if (c + 1 >= D) v[i].y = 0.f;
+        if (c + 2 >= D) v[i].z = 0.f;
+        if (c + 3 >= D) v[i].w = 0.f;
+      }
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
   }
@@ -397,12 +395,12 @@ __device__ __forceinline__ void ln_tanh_fwd_v4_body(const LnDesc* descs, const i
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + 32 * i) * 4;
-    if (c < D) {
+    if (FULL || c < D) {
       const float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
       var += a * a;
-      if (c + 1 < D) var += b * b;
-      if (c + 2 < D) var += e * e;
-      if (c + 3 < D) var += f * f;
+      if (FULL || c + 1 < D) var += b * b;
+      if (FULL || c + 2 < D) var += e * e;
+      if (FULL || c + 3 < D) var += f * f;
     }
   }
   const float rstd = 1.0f / sqrtf(warp_sum(var) / (float)D + FB_LN_EPS);
@@ -410,15 +408,15 @@ __device__ __forceinline__ void ln_tanh_fwd_v4_body(const LnDesc* descs, const i
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int q = lane + 32 * i, c = q * 4;
-    if (c < D) {
+    if (FULL || c < D) {
       float o[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
       // gamma / beta: 128-bit loads (every parameter tensor starts on a 128-byte boundary and is padded to 32 floats)
       const float4 g4 = __ldg(reinterpret_cast<const float4*>(d.gamma + c)), b4 = __ldg(reinterpret_cast<const float4*>(d.beta + c));
       const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (c + e < D) o[e] = tanhf((o[e] - mean) * rstd * gg[e] + bb[e]);
-      if (c + 3 < D) {
+        if (FULL || c + e < D) o[e] = tanhf((o[e] - mean) * rstd * gg[e] + bb[e]);
+      if (FULL || c + 3 < D) {
         y[q] = make_float4(o[0], o[1], o[2], o[3]);
       } else {
         float* ys = reinterpret_cast<float*>(y + q);
@@ -428,6 +426,15 @@ __device__ __forceinline__ void ln_tanh_fwd_v4_body(const LnDesc* descs, const i
     }
   }
   if (lane == 0) { d.mean[r] = mean; d.rstd[r] = rstd; }
+}
+__device__ __forceinline__ void ln_tanh_fwd_v4_body(const LnDesc* descs, const int nprob, int total_rows, const int bid) {
+  const int gw = (bid * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= total_rows) return;
+  int p = 0;
+  while (p + 1 < nprob && descs[p + 1].row_begin <= gw) ++p;
+  const LnDesc d = descs[p];
+  if (d.D == 1024) ln_tanh_fwd_v4_row<true>(d, gw - d.row_begin, lane);
+  else ln_tanh_fwd_v4_row<false>(d, gw - d.row_begin, lane);
 }
 __global__ void __launch_bounds__(256) k_ln_tanh_fwd_v4(const __grid_constant__ DescTable<LnDesc, 8> T, int total_rows) {
   fb_pdl_trigger();
@@ -504,13 +511,13 @@ __global__ void __launch_bounds__(256) k_ln_tanh_bwd(const __grid_constant__ Des
 // (one pass over dy / y / x), and its share of dgamma / dbeta in registers across the rows of the CTA (no per-element
 // shared-memory atomics); per CTA one shared-memory combine across the 8 warps, then one global atomic per column.
 // s_dg, s_db: 1024 floats of shared memory each
-__device__ __forceinline__ void ln_tanh_bwd_v4_body(const LnBwdDesc* descs, const int nprob, float* s_dg, float* s_db, const int bid) {
+// FULL: D == 1024 exactly (the hidden width of the F / actor embeds: the large launches): every lane owns 8 complete float4s, so the
+// column-bound tests of the general path (two thirds of its instructions; the kernel is instruction-latency-bound at one CTA of 8 warps
+// per SM) compile away
+template <bool FULL>
+__device__ __forceinline__ void ln_tanh_bwd_v4_rows(const LnBwdDesc& d, float* s_dg, float* s_db, const int cta) {
 
   constexpr int NV = 8;  // float4s per lane: D <= 32 * 4 * 8 = 1024
-  int p = 0;
-  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)bid) ++p;
-  const LnBwdDesc d = descs[p];
-  const int cta = bid - d.cta_begin;
   const bool affine = d.dgamma != nullptr;
   const int D = d.D;
   if (affine) {
@@ -525,11 +532,13 @@ __device__ __forceinline__ void ln_tanh_bwd_v4_body(const LnBwdDesc* descs, cons
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + 32 * i) * 4;
     gam[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < D) {   // 128-bit load: parameter tensors are 128-byte aligned and padded to 32 floats; columns >= D are masked below
+    if (FULL || c < D) {   // 128-bit load: parameter tensors are 128-byte aligned and padded to 32 floats; columns >= D are masked below
       gam[i] = __ldg(reinterpret_cast<const float4*>(d.gamma + c));
-      if (c + 1 >= D) gam[i].y = 0.f;
-      if (c + 2 >= D) gam[i].z = 0.f;
-      if (c + 3 >= D) gam[i].w = 0.f;
+      if (!FULL) {
+        if (c + 1 >= D) gam[i].y = 0.f;
+        if (c + 2 >= D) gam[i].z = 0.f;
+        if (c + 3 >= D) gam[i].w = 0.f;
+      }
     }
   }
   float4 adg[NV], adb[NV];
@@ -548,12 +557,12 @@ __device__ __forceinline__ void ln_tanh_bwd_v4_body(const LnBwdDesc* descs, cons
     for (int i = 0; i < NV; ++i) {
       const int q = lane + 32 * i, c = q * 4;
       g[i] = make_float4(0.f, 0.f, 0.f, 0.f); xh[i] = g[i];
-      if (c < D) {
+      if (FULL || c < D) {
         const float4 dv = dy[q], yv = y[q], xv = x[q];
         g[i].x = dv.x * (1.f - yv.x * yv.x); xh[i].x = (xv.x - mean) * rstd;
-        if (c + 1 < D) { g[i].y = dv.y * (1.f - yv.y * yv.y); xh[i].y = (xv.y - mean) * rstd; }
-        if (c + 2 < D) { g[i].z = dv.z * (1.f - yv.z * yv.z); xh[i].z = (xv.z - mean) * rstd; }
-        if (c + 3 < D) { g[i].w = dv.w * (1.f - yv.w * yv.w); xh[i].w = (xv.w - mean) * rstd; }
+        if (FULL || c + 1 < D) { g[i].y = dv.y * (1.f - yv.y * yv.y); xh[i].y = (xv.y - mean) * rstd; }
+        if (FULL || c + 2 < D) { g[i].z = dv.z * (1.f - yv.z * yv.z); xh[i].z = (xv.z - mean) * rstd; }
+        if (FULL || c + 3 < D) { g[i].w = dv.w * (1.f - yv.w * yv.w); xh[i].w = (xv.w - mean) * rstd; }
         const float4 gg = make_float4(g[i].x * gam[i].x, g[i].y * gam[i].y, g[i].z * gam[i].z, g[i].w * gam[i].w);
         a += gg.x + gg.y + gg.z + gg.w;
         b += gg.x * xh[i].x + gg.y * xh[i].y + gg.z * xh[i].z + gg.w * xh[i].w;
@@ -564,13 +573,13 @@ __device__ __forceinline__ void ln_tanh_bwd_v4_body(const LnBwdDesc* descs, cons
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int q = lane + 32 * i, c = q * 4;
-      if (c < D) {
+      if (FULL || c < D) {
         float4 o;
         o.x = rstd * (g[i].x * gam[i].x - a - xh[i].x * b);
         o.y = rstd * (g[i].y * gam[i].y - a - xh[i].y * b);
         o.z = rstd * (g[i].z * gam[i].z - a - xh[i].z * b);
         o.w = rstd * (g[i].w * gam[i].w - a - xh[i].w * b);
-        if (c + 3 < D) {
+        if (FULL || c + 3 < D) {
           dx[q] = o;
         } else {  // ragged tail (D not a multiple of 4): the row pitch still holds a full float4, only valid lanes are stored
           float* ds = reinterpret_cast<float*>(dx + q);
@@ -587,16 +596,23 @@ __device__ __forceinline__ void ln_tanh_bwd_v4_body(const LnBwdDesc* descs, cons
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + 32 * i) * 4;
-      if (c < D) {
+      if (FULL || c < D) {
         atomicAdd(&s_dg[c], adg[i].x); atomicAdd(&s_db[c], adb[i].x);
-        if (c + 1 < D) { atomicAdd(&s_dg[c + 1], adg[i].y); atomicAdd(&s_db[c + 1], adb[i].y); }
-        if (c + 2 < D) { atomicAdd(&s_dg[c + 2], adg[i].z); atomicAdd(&s_db[c + 2], adb[i].z); }
-        if (c + 3 < D) { atomicAdd(&s_dg[c + 3], adg[i].w); atomicAdd(&s_db[c + 3], adb[i].w); }
+        if (FULL || c + 1 < D) { atomicAdd(&s_dg[c + 1], adg[i].y); atomicAdd(&s_db[c + 1], adb[i].y); }
+        if (FULL || c + 2 < D) { atomicAdd(&s_dg[c + 2], adg[i].z); atomicAdd(&s_db[c + 2], adb[i].z); }
+        if (FULL || c + 3 < D) { atomicAdd(&s_dg[c + 3], adg[i].w); atomicAdd(&s_db[c + 3], adb[i].w); }
       }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < D; c += blockDim.x) { atomicAdd(d.dgamma + c, s_dg[c]); atomicAdd(d.dbeta + c, s_db[c]); }
   }
+}
+__device__ __forceinline__ void ln_tanh_bwd_v4_body(const LnBwdDesc* descs, const int nprob, float* s_dg, float* s_db, const int bid) {
+  int p = 0;
+  while (p + 1 < nprob && descs[p + 1].cta_begin <= (int)bid) ++p;
+  const LnBwdDesc d = descs[p];
+  if (d.D == 1024) ln_tanh_bwd_v4_rows<true>(d, s_dg, s_db, bid - d.cta_begin);
+  else ln_tanh_bwd_v4_rows<false>(d, s_dg, s_db, bid - d.cta_begin);
 }
 __global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const __grid_constant__ DescTable<LnBwdDesc, 4> T) {
   fb_pdl_trigger();
