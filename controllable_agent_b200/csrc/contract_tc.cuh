@@ -27,7 +27,8 @@
 #define CT_TILE_N 64
 #define CT_MAX_PRODUCTS 5
 #define CT_TMEM_COLS 512
-#define CT_THREADS 192   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue
+#define CT_EPI_GROUPS 2
+#define CT_THREADS (64 + 128 * CT_EPI_GROUPS)   // warp 0: TMA producer, warp 1: MMA issuer, then CT_EPI_GROUPS x 4 epilogue warps
 
 enum { CT_MODE_ROW = 0, CT_MODE_COL = 1 };
 enum { CT_F1 = 0, CT_F2, CT_TF1, CT_TF2, CT_B, CT_TB, CT_NUM_OPERANDS };
@@ -139,14 +140,16 @@ __global__ void __launch_bounds__(256) k_contract_split(const float* __restrict_
 //   warp 0      TMA producer   one K-box (32 floats) of one product per ring stage: [A raw | A lo | B raw | B lo] = 48 KB, 4 stages;
 //                              runs ahead into the next tile while the current one is in its epilogue
 //   warp 1      MMA issuer     3 chains x <= 4 tcgen05.mma (M128 x N64 x K8) per stage into the product's 64 TMEM columns
-//   warps 2..5  epilogue       tcgen05.ld of the five accumulators, loss math, G tiles out through a shared-memory transpose
+//   warps 2..9  epilogue       two groups of four warps (one per TMEM lane quadrant) that take alternate 16-column chunks (one warp per
+//                              scheduler is instruction-latency-bound): tcgen05.ld of the five accumulators, loss math, G tiles out
+//                              through a shared-memory transpose
 // (The first version ran one tile per CTA with ONE thread as producer and issuer and whole products as stages: at z = 100 a single
 // 192 KB stage, i.e. no overlap of loads and MMAs at all; at batch 4096 that was 15 % of the step.)
-// dynamic smem: [4 stages x 48 KB | epilogue scratch 4 warps x 3 x 32 x 20 floats], 1024-byte aligned
+// dynamic smem: [4 stages x 48 KB | epilogue scratch, 32 x 20 floats per epilogue warp], 1024-byte aligned
 #define CT_STAGES 4
 #define CT_STAGE_BYTES (2 * CT_TILE_M * 128 + 2 * CT_TILE_N * 128)
 #define CT_SCR_LD 20
-#define CT_SCRATCH_BYTES (4 * 3 * 32 * CT_SCR_LD * 4)
+#define CT_SCRATCH_BYTES (4 * CT_EPI_GROUPS * 32 * CT_SCR_LD * 4)   // one 32 x 16 chunk per epilogue warp (G1, G2, Gc pass through it in turn)
 #define CT_SMEM_BYTES (CT_STAGES * CT_STAGE_BYTES + CT_SCRATCH_BYTES + 1024)
 
 __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_constant__ ContractParams P) {
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
   __shared__ __align__(8) uint64_t bar_accum;        // all MMAs of a tile retired -> epilogue
   __shared__ __align__(8) uint64_t bar_tmem_empty;   // epilogue has read the accumulators -> MMA issuer (next tile)
   __shared__ uint32_t tmem_base_smem;
-  __shared__ double red[6][4];
+  __shared__ double red[6][4 * CT_EPI_GROUPS];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ct_smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < CT_STAGES; ++s) { ct_mbar_init(&bar_full[s], 1); ct_mbar_init(&bar_empty[s], 1); }
     ct_mbar_init(&bar_accum, 1);
-    ct_mbar_init(&bar_tmem_empty, 4);
+    ct_mbar_init(&bar_tmem_empty, 4 * CT_EPI_GROUPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -244,8 +247,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
   } else {
     // ===== epilogue: thread = one row of the tile (TMEM lane), 16 columns at a time =====
     const int q = warp & 3;   // TMEM lane quadrant this warp may read
+    const int grp = (warp - 2) >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* scr = reinterpret_cast<float*>(smem + (size_t)CT_STAGES * CT_STAGE_BYTES) + q * (3 * 32 * CT_SCR_LD);
+    float* scr = reinterpret_cast<float*>(smem + (size_t)CT_STAGES * CT_STAGE_BYTES) + (grp * 4 + q) * (32 * CT_SCR_LD);
     double a_off = 0.0, a_diag = 0.0, a_cov = 0.0, a_covd = 0.0, a_tm = 0.0, a_m1 = 0.0;
     const float inv_noff = P.inv_noff, inv_n = P.inv_n, c4 = P.c4;
     const bool g_vec = (P.ld % 4 == 0) && (((reinterpret_cast<uintptr_t>(P.G1) | reinterpret_cast<uintptr_t>(P.G2) |
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
       // chunk of G1 / G2 / Gc and writes it back as 128-bit stores, 4 lanes per row: full sectors.  The transposed copies Gt1 / Gt2 are
       // coalesced as they are (for a fixed column the lanes are consecutive rows).
 #pragma unroll 1
-      for (int cb = 0; cb < CT_TILE_N; cb += 16) {
+      for (int cb = grp * 16; cb < CT_TILE_N; cb += 16 * CT_EPI_GROUPS) {
         float m1[16], m2[16], t1[16], t2[16], cv[16];
         ct_tmem_ld16(lane_addr + 0 * CT_TILE_N + cb, m1);
         ct_tmem_ld16(lane_addr + 1 * CT_TILE_N + cb, m2);
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
         ct_tmem_ld16(lane_addr + 3 * CT_TILE_N + cb, t2);
         if (P.mode == CT_MODE_ROW) ct_tmem_ld16(lane_addr + 4 * CT_TILE_N + cb, cv);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (cb + 16 >= CT_TILE_N) {   // last chunk read: the issuer may overwrite the accumulators with the next tile
+        if (cb + 16 * CT_EPI_GROUPS >= CT_TILE_N) {   // this warp's last chunk is read: the issuer may overwrite the accumulators with the next tile
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ct_smem_u32(&bar_tmem_empty)) : "memory");
@@ -314,37 +318,32 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
           }
           g1v[j] = g1; g2v[j] = g2; gcv[j] = gc;
         }
+        const int rr = lane >> 2, c4o = (lane & 3) * 4;
+        const int colo = col0 + cb + c4o;
+        auto flush = [&](const float (&gv)[16], float* G) {   // one G array through the warp's 32 x 16 scratch
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          *reinterpret_cast<float4*>(scr + (0 * 32 + lane) * CT_SCR_LD + j) = make_float4(g1v[j], g1v[j + 1], g1v[j + 2], g1v[j + 3]);
-          *reinterpret_cast<float4*>(scr + (1 * 32 + lane) * CT_SCR_LD + j) = make_float4(g2v[j], g2v[j + 1], g2v[j + 2], g2v[j + 3]);
-          if (P.mode == CT_MODE_ROW)
-            *reinterpret_cast<float4*>(scr + (2 * 32 + lane) * CT_SCR_LD + j) = make_float4(gcv[j], gcv[j + 1], gcv[j + 2], gcv[j + 3]);
-        }
-        __syncwarp();
-        {
-          const int rr = lane >> 2, c4o = (lane & 3) * 4;
-          const int col = col0 + cb + c4o;
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(scr + lane * CT_SCR_LD + j) = make_float4(gv[j], gv[j + 1], gv[j + 2], gv[j + 3]);
+          __syncwarp();
 #pragma unroll
           for (int r8 = 0; r8 < 4; ++r8) {
             const int r = r8 * 8 + rr;
             const int grow = row0 + q * 32 + r;
-            if (grow >= P.nr || col >= P.nc) continue;
-            for (int a = 0; a < n_arr; ++a) {
-              float* G = a == 0 ? P.G1 : (a == 1 ? P.G2 : P.Gc);
-              const float4 v = *reinterpret_cast<const float4*>(scr + (a * 32 + r) * CT_SCR_LD + c4o);
-              float* gp = G + (size_t)grow * P.ld + col;
-              if (g_vec && col + 3 < P.nc) *reinterpret_cast<float4*>(gp) = v;
-              else {
-                gp[0] = v.x;
-                if (col + 1 < P.nc) gp[1] = v.y;
-                if (col + 2 < P.nc) gp[2] = v.z;
-                if (col + 3 < P.nc) gp[3] = v.w;
-              }
+            if (grow >= P.nr || colo >= P.nc) continue;
+            const float4 v = *reinterpret_cast<const float4*>(scr + r * CT_SCR_LD + c4o);
+            float* gp = G + (size_t)grow * P.ld + colo;
+            if (g_vec && colo + 3 < P.nc) *reinterpret_cast<float4*>(gp) = v;
+            else {
+              gp[0] = v.x;
+              if (colo + 1 < P.nc) gp[1] = v.y;
+              if (colo + 2 < P.nc) gp[2] = v.z;
+              if (colo + 3 < P.nc) gp[3] = v.w;
             }
           }
-        }
-        __syncwarp();
+          __syncwarp();
+        };
+        flush(g1v, P.G1);
+        flush(g2v, P.G2);
+        if (n_arr == 3) flush(gcv, P.Gc);
       }
     }
     if (P.mode == CT_MODE_ROW) {   // the loss sums of every tile this CTA walked: one reduction, six atomics per CTA
@@ -352,7 +351,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         const double v = warp_sum_d(vals[i]);
-        if (lane == 0) red[i][q] = v;
+        if (lane == 0) red[i][grp * 4 + q] = v;
       }
     }
   }
@@ -360,7 +359,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_contract_tc(const __grid_cons
   __syncthreads();
   if (P.mode == CT_MODE_ROW && threadIdx.x < 6) {
     const int slot[6] = {ACC_OFFDIAG_SQ, ACC_DIAG, ACC_COV_OFF_SQ, ACC_COV_DIAG, ACC_TARGET_M, ACC_M1};
-    atomicAdd(P.acc + slot[threadIdx.x], red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3]);
+    double tot = 0.0;
+    for (int w = 0; w < 4 * CT_EPI_GROUPS; ++w) tot += red[threadIdx.x][w];
+    atomicAdd(P.acc + slot[threadIdx.x], tot);
   }
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(CT_TMEM_COLS) : "memory");

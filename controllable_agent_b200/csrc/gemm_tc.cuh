@@ -48,7 +48,11 @@
 #define TC_A_TILE_BYTES (TC_BM * TC_ROW_BYTES)
 #define TC_KB_PER_32 (32 / TC_BK)      // k-blocks per 32 floats of K: the unit the host-side cost model and the accumulator rotation count in
 #define TC_MAX_STAGES 6
-#define TC_THREADS 320                 // warp 0 TMA, warp 1 MMA, warps 2..5 builders + epilogue, warps 6..9 epilogue helpers
+#ifndef TC_EPI_GROUPS
+#define TC_EPI_GROUPS 3                // epilogue warp groups of k_gemm_tc (4 warps each; group 0 also builds the lo parts): 1 -> 2 -> 3 groups
+                                       // measured 975 -> 1022 -> 1038 steps/s; a fourth does not fit next to the 192 KB ring
+#endif
+#define TC_THREADS (64 + 128 * TC_EPI_GROUPS)   // warp 0 TMA, warp 1 MMA, warps 2..5 builders + epilogue, further warps epilogue helpers
 #define TC_EPI_CW 16                   // columns of one epilogue chunk
 #define TC_RING_BYTES 196608           // shared-memory ring; a stage is [A raw | B raw (BN rows) | A lo | B lo], rows of TC_ROW_BYTES.
                                        // (3 stages at BN = 128 and TC_BK = 32)
@@ -687,7 +691,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
   static_assert(!TS || TC_BK == 32, "the TS form reads SWIZZLE_128B rows");
   fb_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
-  __shared__ __align__(16) float epi_scratch[8 * TC_EPI_SCR];   // two epilogue groups of four warps
+  __shared__ __align__(16) float epi_scratch[4 * TC_EPI_GROUPS * TC_EPI_SCR];   // one region per epilogue warp
   __shared__ __align__(8) TcShared sh;
 
   const int warp = threadIdx.x >> 5;
@@ -695,7 +699,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
   uint8_t* smem_gen = tc_smem_raw + (smem_base - tc_smem_u32(tc_smem_raw));
   const uint32_t rank = NCTA == 2 ? tc_cluster_rank() : 0u;
 
-  if (threadIdx.x == 0) tc_init_barriers(&sh, false, NCTA, 2);
+  if (threadIdx.x == 0) tc_init_barriers(&sh, false, NCTA, TC_EPI_GROUPS);
   if (warp == 1) {   // (a pair allocates the same columns in both CTAs: the same warp of each issues the cta_group::2 form)
     if constexpr (NCTA == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&sh.tmem_base)), "r"(512) : "memory");
@@ -711,7 +715,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   fb_pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
-  tc_gemm_roles<TS, NCTA, 2>(descs, L, (int)(blockIdx.x / NCTA), (int)(gridDim.x / NCTA), &sh, epi_scratch, smem_base, smem_gen, rank);
+  tc_gemm_roles<TS, NCTA, TC_EPI_GROUPS>(descs, L, (int)(blockIdx.x / NCTA), (int)(gridDim.x / NCTA), &sh, epi_scratch, smem_base, smem_gen, rank);
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if constexpr (NCTA == 2) tc_cluster_sync();   // neither CTA leaves (or frees tensor memory) while the pair's MMAs / commits can still touch it
