@@ -139,6 +139,16 @@ static cudaError_t tc_launch(const TcGemmDesc* dd, const TcLaunch& hdr, int work
   return cudaLaunchKernelEx(&cfg, tc_kernel(ncta), dd, hdr);
 }
 
+// CTAs of the fused reduce-scatter + Adam + all-gather pass (one per SM; FB_P2P_ADAM_CTAS overrides).  Measured at 8 ranks
+// (tools/gpu_p2p_adam_sweep.sh): 61.4 / 59.4 / 59.6 us for the fb segment with 296 / 148 / 74 CTAs, i.e. 12.9 MB in + 12.9 MB out per
+// rank at ~220 GB/s each: the pass is bound by the rate of its peer LOADS (ld.volatile over NVLink), not by how the inbound and outbound
+// transfers overlap.  What would change that is a push design (every rank stores its gradient slices into the owners' arenas as the
+// backward produces them) or the switch's multimem.ld_reduce.
+static int p2p_adam_ctas() {
+  static const int n = getenv("FB_P2P_ADAM_CTAS") ? std::max(1, atoi(getenv("FB_P2P_ADAM_CTAS"))) : FB_SM_COUNT;
+  return n;
+}
+
 // op recorders
 // ------------------------------------------------------------------------------------------------
 struct Builder {
@@ -1189,7 +1199,7 @@ static int build_plan(fb_handle* h) {
       ap.off_grad = h->p2p_off_grad_fb; ap.off_param = h->p2p_off_param_fb; ap.m = m; ap.v = v; ap.n4 = n4; ap.split4 = split4;
       ap.slice4 = (n4 + pp.world - 1) / pp.world; ap.sc = sc; ap.which = 0; ap.bar_param = P2P_BAR_PARAM_FB; ap.beta1 = b1; ap.beta2 = b2; ap.eps = eps;
       b.push([pp, ap](cudaStream_t s) {
-        fb_launch_pdl(k_p2p_adam, dim3(FB_SM_COUNT * 2), dim3(256), 0, s, pp, ap);
+        fb_launch_pdl(k_p2p_adam, dim3(p2p_adam_ctas()), dim3(256), 0, s, pp, ap);
         return cudaGetLastError();
       }, FB_OPK_ADAM, 0.0, 16.0 * (double)ap.slice4 * (pp.world + 5.0 + pp.world));   // r(g x R, p, m, v) + w(m, v, p x R) of one slice
       b.push([pp](cudaStream_t s) { fb_launch_pdl(k_p2p_barrier, dim3(1), dim3(32), 0, s, pp, (int)P2P_BAR_PARAM_FB, 0, 1); return cudaGetLastError(); },
@@ -1331,7 +1341,7 @@ static int build_plan(fb_handle* h) {
       ap.off_grad = h->p2p_off_grad_actor; ap.off_param = h->p2p_off_param_actor; ap.m = m; ap.v = v; ap.n4 = n4; ap.split4 = n4;
       ap.slice4 = (n4 + pp.world - 1) / pp.world; ap.sc = sc; ap.which = 1; ap.bar_param = P2P_BAR_PARAM_ACTOR; ap.beta1 = b1; ap.beta2 = b2; ap.eps = eps;
       b.push([pp, ap](cudaStream_t s) {
-        fb_launch_pdl(k_p2p_adam, dim3(FB_SM_COUNT * 2), dim3(256), 0, s, pp, ap);
+        fb_launch_pdl(k_p2p_adam, dim3(p2p_adam_ctas()), dim3(256), 0, s, pp, ap);
         return cudaGetLastError();
       }, FB_OPK_ADAM, 0.0, 16.0 * (double)ap.slice4 * (pp.world + 5.0 + pp.world));
       b.push([pp](cudaStream_t s) { fb_launch_pdl(k_p2p_barrier, dim3(1), dim3(32), 0, s, pp, (int)P2P_BAR_PARAM_ACTOR, 0, 1); return cudaGetLastError(); },
