@@ -507,8 +507,11 @@ struct Builder {
     if (v.size() > 4) { if (rc == FB_OK) rc = FB_E_UNSUPPORTED; return; }
     tab.n = (int)v.size();
     for (size_t i = 0; i < v.size(); ++i) tab.d[i] = v[i];
-    push([tab, ctas, vec](cudaStream_t s) {
-      if (vec) fb_launch_pdl(k_ln_tanh_bwd_v4, dim3(ctas), dim3(256), 0, s, tab);
+    bool full = vec;   // every problem exactly 1024 wide: the kernel without column-bound tests (128 registers: two CTAs per SM)
+    for (auto& d : v) full = full && d.D == 1024;
+    push([tab, ctas, vec, full](cudaStream_t s) {
+      if (full) fb_launch_pdl(k_ln_tanh_bwd_v4_full, dim3(ctas), dim3(256), 0, s, tab);
+      else if (vec) fb_launch_pdl(k_ln_tanh_bwd_v4, dim3(ctas), dim3(256), 0, s, tab);
       else fb_launch_pdl(k_ln_tanh_bwd, dim3(ctas), dim3(256), 0, s, tab);
       return cudaGetLastError();
     }, FB_OPK_LAYERNORM, 0.0, bytes);

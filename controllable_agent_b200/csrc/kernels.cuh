@@ -621,6 +621,17 @@ __global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4(const __grid_constant__ 
   __shared__ float s_db[1024];
   ln_tanh_bwd_v4_body(T.d, T.n, s_dg, s_db, blockIdx.x);
 }
+// every problem of the launch has D == 1024: the full-width path alone (a kernel of its own so that its register count, not the general
+// path's, decides how many CTAs an SM holds)
+__global__ void __launch_bounds__(256) k_ln_tanh_bwd_v4_full(const __grid_constant__ DescTable<LnBwdDesc, 4> T) {
+  fb_pdl_trigger();
+  fb_pdl_wait();
+  __shared__ float s_dg[1024];
+  __shared__ float s_db[1024];
+  int p = 0;
+  while (p + 1 < T.n && T.d[p + 1].cta_begin <= (int)blockIdx.x) ++p;
+  ln_tanh_bwd_v4_rows<true>(T.d[p], s_dg, s_db, blockIdx.x - T.d[p].cta_begin);
+}
 
 // ---- sqrt(Z) * F.normalize (fb_modules.py:33-40, 227-229) ------------------------------------------
 struct L2Desc { const float* x; float* y; float* nrm; int rows, Z, ldx, ldy, row_begin; int normalize; };   // normalize = 0: y = x (norm_z off)
