@@ -709,6 +709,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const TcGemmDesc* __r
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
+  if (warp == 0 && (threadIdx.x & 31) == 0 && (int)(blockIdx.x / NCTA) < L.total) {
+    // the tensor maps of this CTA's first work item: written at bind time, not by the previous kernel, so their fetch (~1 us on the
+    // first TMA of a launch) may overlap that kernel's tail
+    int m0, n0, kb0, kb1;
+    const int pi = tc_locate<NCTA>(L, tc_snake(0, (int)(blockIdx.x / NCTA), (int)(gridDim.x / NCTA)), &m0, &n0, &kb0, &kb1);
+    tc_prefetch_map(&descs[pi].mapA); tc_prefetch_map(&descs[pi].mapB);
+    if (L.p[pi].flags & TC_B_PRE) tc_prefetch_map(&descs[pi].mapBlo);
+    if (!TS && (L.p[pi].flags & TC_A_PRE)) tc_prefetch_map(&descs[pi].mapAlo);
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if constexpr (NCTA == 2) tc_cluster_sync();   // the partner's barriers are initialised before anything arrives on them
   else __syncthreads();
