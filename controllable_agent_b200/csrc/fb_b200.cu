@@ -324,7 +324,8 @@ struct Builder {
             int len = nkb, parts = 1;
             if (splittable && sk > 1) { len = fb_ceil_div(nkb, std::min(sk, nkb / 4)); parts = fb_ceil_div(nkb, len); }
             const double f = (bnp == 128 ? 1.0 : (bnp == 64 ? 0.8 : 0.72)) * (pair ? 0.97 : 1.0);
-            const double epi = (2.0 + bnp / 64.0) * (parts > 1 ? 2.0 : 1.0);
+            static const double epi_scale = getenv("FB_TC_EPI_COST") ? atof(getenv("FB_TC_EPI_COST")) : 1.0;
+            const double epi = epi_scale * (2.0 + bnp / 64.0) * (parts > 1 ? 2.0 : 1.0);
             items.push_back(Item{len * f + epi, fb_ceil_div(s.M, TC_BM * (pair + 1)) * fb_ceil_div(s.N, bnp) * parts});
           }
           std::sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.cost > y.cost; });
