@@ -600,7 +600,7 @@ class FBDDPGAgent:
         # the library, straight into the pinned block; any other object: its own sample() contract
         view = self._host_view(replay_loader)
         if view is not None:
-            ep_idx, step_idx, future_idx = draw_sample_indices(replay_loader, B)
+            ep_idx, step_idx, future_idx = draw_sample_indices(replay_loader, B, exact_stream=self.cfg.rng_mode != "device")
             self.engine.upload_host_rows(view, ep_idx, step_idx, future_idx, float(replay_loader._discount))
             return
         batch = replay_loader.sample(B)

@@ -127,9 +127,12 @@ def _round4(x: int) -> int:
     return (x + 3) // 4 * 4
 
 
-def draw_sample_indices(replay: tp.Any, batch_size: int) -> tp.Tuple[np.ndarray, np.ndarray, tp.Optional[np.ndarray]]:
+def draw_sample_indices(replay: tp.Any, batch_size: int, exact_stream: bool = True) -> tp.Tuple[np.ndarray, np.ndarray, tp.Optional[np.ndarray]]:
     """(episode, step, future step) indices of one sampled batch: the draws of in_memory_replay_buffer.py:141-161 on the numpy GLOBAL
-    generator, call for call, for any object with that class's attributes (this package's ReplayBuffer, the reference's own)."""
+    generator, call for call, for any object with that class's attributes (this package's ReplayBuffer, the reference's own).
+    exact_stream=False (the agent's rng_mode="device", where nothing else follows the reference's generator stream either): the same
+    distributions through cheaper calls — a scalar bound instead of a per-row bound array when every episode has the same length (the
+    array form costs 4x as much per draw), no consistency asserts."""
     if not isinstance(replay._future, float):
         assert isinstance(replay._future, bool)
         replay._future = float(replay._future)
@@ -139,6 +142,20 @@ def draw_sample_indices(replay: tp.Any, batch_size: int) -> tp.Tuple[np.ndarray,
         if replay._episodes_selection_probability is None:
             replay._episodes_selection_probability = replay._episodes_length / replay._episodes_length.sum()
         ep_idx = np.random.choice(np.arange(len(replay._episodes_length)), size=batch_size, p=replay._episodes_selection_probability)
+    if not exact_stream and replay._is_fixed_episode_length:
+        lengths = replay._episodes_length
+        first = int(lengths[0])
+        cache = getattr(replay, "_fb_uniform_length", None)     # (array identity, length) of the last check: episodes are appended rarely
+        if cache is None or cache[0] is not lengths or cache[1] != first or cache[2] != len(replay):
+            n = len(replay)
+            uniform = bool(n > 0 and (lengths[:n] == first).all())
+            replay._fb_uniform_length = cache = (lengths, first if uniform else -1, n)
+        if cache[1] > 0:
+            step_idx = np.random.randint(0, cache[1], size=batch_size) + 1
+            future_idx = None
+            if replay._future < 1:
+                future_idx = np.minimum(step_idx + np.random.geometric(p=(1 - replay._future), size=batch_size), cache[1])
+            return ep_idx, step_idx, future_idx
     eps_lengths = replay._episodes_length[ep_idx]
     step_idx = np.random.randint(0, eps_lengths) + 1
     assert (step_idx <= eps_lengths).all()
@@ -196,6 +213,8 @@ class HostStorageView:
 
     def still_valid(self) -> bool:
         st = self.replay._storage
+        if all(st.get(k) is v for k, v in self.arrays.items()):   # the very same array objects (the per-step check)
+            return True
         return all(k in st and st[k].ctypes.data == p and st[k].shape == shp for k, p, shp in self.key)
 
 

@@ -344,8 +344,9 @@ def test_agent_host_replay_with_device_rng():
         assert agent.engine.launch_count(L.PHASE_ALL | L.RUN_HOST_BATCH) == agent.engine.launch_count(L.PHASE_ALL) - 1
 
 
+@pytest.mark.parametrize("rng_mode", ["device", "reference"])
 @pytest.mark.parametrize("goal_space,G,future", [(None, 0, 1.0), ("simplified_walker", 3, 0.9)])
-def test_agent_samples_reference_layout_host_replay_natively(goal_space, G, future):
+def test_agent_samples_reference_layout_host_replay_natively(goal_space, G, future, rng_mode):
     """A host buffer with the reference ReplayBuffer's attribute layout (in_memory_replay_buffer.py:66-88) is sampled without its
     Python sample(): index draws in the reference's order on the numpy generator, row gathers by fb_host_gather_rows into the pinned
     block.  The rows that land on the device are exactly what its own sample() would have returned for the same generator state."""
@@ -356,7 +357,8 @@ def test_agent_samples_reference_layout_host_replay_natively(goal_space, G, futu
 
     def ref_sample(n):   # what in_memory_replay_buffer.py:139-190 returns for these attributes
         from controllable_agent_b200.replay import draw_sample_indices
-        ep, st, fu = draw_sample_indices(rep, n)
+        # rng_mode="reference": the reference's own numpy calls (its generator stream); "device": the cheaper equivalent draws
+        ep, st, fu = draw_sample_indices(rep, n, exact_stream=rng_mode == "reference")
         S = rep._storage
         return EpisodeBatch(obs=S["observation"][ep, st - 1], action=S["action"][ep, st], reward=S["reward"][ep, st],
                             discount=rep._discount * S["discount"][ep, st], next_obs=S["observation"][ep, st],
@@ -367,7 +369,8 @@ def test_agent_samples_reference_layout_host_replay_natively(goal_space, G, futu
     torch.manual_seed(5)
     agent = FBDDPGAgent(obs_type="states", obs_shape=(O_,), action_shape=(A_,), device="cuda", num_expl_steps=0, update_encoder=True,
                         goal_space=goal_space, use_tb=True, use_wandb=True, use_hiplog=False, batch_size=B, update_every_steps=1,
-                        hidden_dim=256, feature_dim=128, backward_hidden_dim=134, future_ratio=0.3 if future < 1 else 0.0)
+                        hidden_dim=256, feature_dim=128, backward_hidden_dim=134, future_ratio=0.3 if future < 1 else 0.0, rng_mode=rng_mode)
+    agent.draw_device = "cpu"
     for step in range(4):
         agent.native_host_sampling = step % 2 == 0   # alternate: library gather / the object's own sample()
         agent.cfg.prefetch_host_batch = False
