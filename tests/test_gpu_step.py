@@ -252,6 +252,7 @@ FULL_WIDTH_CASES = [
     ("cheetah_z100_b4096", 4096, 17, 6, 100, None, 15, 0),
     ("walker_b1024_fused", 1024, 24, 6, 50, None, 12, 2),               # mlp_mode 2 here: tcgen05 plan through the fused stack kernels
     ("quadruped_goal2_b1024_fused", 1024, 78, 12, 50, 2, 13, 2),
+    ("walker_b1024_boltzmann", 1024, 24, 6, 50, None, 16, 0, "boltz"),   # cfg.boltzmann: DiagGaussianActor stack at full width (temp 0.7)
 ]
 
 
@@ -268,14 +269,16 @@ def test_full_width_step_against_oracle(monkeypatch, case):
     differ from the oracle's own choice only on units whose pre-activation is ~0 (|x| < 1e-4 of the layer's mean |x|,
     and only a handful of them); on that common branch every gradient tensor must match to 2e-4 (observed ~3e-6), the
     losses / metrics to 1e-3 against the unforced fp32 oracle."""
-    _, B, obs_dim, act_dim, z_dim, goal_dim, seed, mlp_mode = case
+    _, B, obs_dim, act_dim, z_dim, goal_dim, seed, mlp_mode = case[:8]
+    boltz = len(case) > 8 and case[8] == "boltz"
+    temp = 0.7 if boltz else 1.0
     use_goal = goal_dim is not None
     L = _L()
     d = O.Dims(obs_dim=obs_dim, action_dim=act_dim, z_dim=z_dim, goal_dim=goal_dim if use_goal else obs_dim)
     Fd = d.feature_dim
     max_flips = 64 * max(1, B // 256)
     gen = torch.Generator().manual_seed(seed)
-    actor = O.init_params(O.actor_spec(d), gen)
+    actor = O.init_params(O.boltzmann_actor_spec(d) if boltz else O.actor_spec(d), gen)
     fwd = O.init_params(O.forward_map_spec(d), gen)
     bwd = O.init_params(O.backward_map_spec(d), gen)
     fwd_t = {k: v + 0.02 * torch.randn(v.shape, generator=gen) for k, v in fwd.items()}
@@ -295,7 +298,7 @@ def test_full_width_step_against_oracle(monkeypatch, case):
     with torch.no_grad():
         z[idx] = O.l2_project(O.backward_map(bwd, goal[perm][idx], d.z_dim), d.z_dim)
 
-    eng = make_engine(d, B, use_goal=use_goal, mlp_mode=mlp_mode % 2, fused=mlp_mode == 2)
+    eng = make_engine(d, B, use_goal=use_goal, mlp_mode=mlp_mode % 2, fused=mlp_mode == 2, boltzmann=boltz, temp=temp)
     load_params(eng, fwd=fwd, bwd=bwd, actor=actor, fwd_tgt=fwd_t, bwd_tgt=bwd_t)
     eng.set_scalars(0.2, 0.3, 1e-4, 1e-4, 1e-4, 0.01)
     eng.set_indices(perm=perm, mix_mask=mix_mask.int())
@@ -314,19 +317,22 @@ def test_full_width_step_against_oracle(monkeypatch, case):
 
     def run_fb(dt):
         return O.fb_loss_and_grads(_to(fwd, dt), _to(bwd, dt), _to(fwd_t, dt), _to(bwd_t, dt), _to(actor, dt), obs.to(dt), action.to(dt),
-                                   discount.to(dt), next_obs.to(dt), next_goal.to(dt), zz.to(dt), noise_fb.to(dt), 0.2, 0.3, 1.0, d.z_dim)
+                                   discount.to(dt), next_obs.to(dt), next_goal.to(dt), zz.to(dt), noise_fb.to(dt), 0.2, 0.3, 1.0, d.z_dim,
+                                   boltzmann=boltz)
 
     ora32 = run_fb(f32)
     # ReLU call order of fb_loss_and_grads: actor(next_obs) [obs_z_net, obs_net, policy], target F [oa, oz, F1, F2], target B,
     # online F [oa, oz, F1, F2], online B
-    forced = _ForcedRelu([act("hA", 0, Fd), act("hA", 0, 0), act("actor.policy.h1"), act("hFt", 0, 0), act("hFt", 0, Fd),
+    # (cfg.boltzmann: the DiagGaussianActor is ONE stack with one ReLU: policy.3 -> "actor.policy.h2", rows [0, B) = next_obs)
+    actor_fb = [act("actor.policy.h2")] if boltz else [act("hA", 0, Fd), act("hA", 0, 0), act("actor.policy.h1")]
+    forced = _ForcedRelu(actor_fb + [act("hFt", 0, 0), act("hFt", 0, Fd),
                           act("Ft.F1.h1"), act("Ft.F2.h1"), act("Bt.h2"), act("hF", 0, 0), act("hF", 0, Fd), act("F.F1.h1"),
                           act("F.F2.h1"), act("Bo.h2")])
     with monkeypatch.context() as mp:
         mp.setattr(torch, "relu", forced)
         ora = run_fb(f64)
     assert forced.i == len(forced.masks)
-    print(f"fb step: {forced.flips} of ~{13 * B * 1024} ReLU units on the other branch than the fp64 oracle, largest |x|/mean|x| {forced.worst:.1e}")
+    print(f"fb step: {forced.flips} of ~{len(forced.masks) * B * 1024} ReLU units on the other branch than the fp64 oracle, largest |x|/mean|x| {forced.worst:.1e}")
     assert forced.flips <= max_flips and forced.worst < 1e-4
     m = eng.read_metrics()
     for k, v in ora32["metrics"].items():
@@ -349,12 +355,13 @@ def test_full_width_step_against_oracle(monkeypatch, case):
     torch.cuda.synchronize()
 
     def run_actor(dt):
-        return O.actor_loss_and_grads(_to(actor, dt), _to(fwd1, dt), obs.to(dt), zz.to(dt), noise_actor.to(dt), 0.2, 0.3)
+        return O.actor_loss_and_grads(_to(actor, dt), _to(fwd1, dt), obs.to(dt), zz.to(dt), noise_actor.to(dt), 0.2, 0.3,
+                                      boltzmann=boltz, temp=temp)
 
     ora32 = run_actor(f32)
     # actor(obs) [obs_z_net, obs_net, policy] = rows B..2B of the batched actor forward, then F(obs, z, action) [oa, oz, F1, F2]
-    forced = _ForcedRelu([act("hA", B, Fd), act("hA", B, 0), act("actor.policy.h1", B), act("hF2", 0, 0), act("hF2", 0, Fd),
-                          act("F2.F1.h1"), act("F2.F2.h1")])
+    actor_a = [act("actor.policy.h2", B)] if boltz else [act("hA", B, Fd), act("hA", B, 0), act("actor.policy.h1", B)]
+    forced = _ForcedRelu(actor_a + [act("hF2", 0, 0), act("hF2", 0, Fd), act("F2.F1.h1"), act("F2.F2.h1")])
     with monkeypatch.context() as mp:
         mp.setattr(torch, "relu", forced)
         ora_a = run_actor(f64)
