@@ -396,17 +396,26 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
         if (kb0 < nk1) { tc_prefetch_map(&d->mapA); tc_prefetch_map(&d->mapB); }
         const bool a_pre = !TS && (flags & TC_A_PRE);   // TS: the A lo half is built in registers, a pre-split plane is never loaded
         const uint32_t tx_bytes = (uint32_t)TC_A_TILE_BYTES * (a_pre ? 2u : 1u) + (uint32_t)(bn / NCTA) * TC_ROW_BYTES * ((flags & TC_B_PRE) ? 2u : 1u);
+        // nothing to build (both lo planes pre-split): the landed bytes complete the MMA issuer's barrier directly, the builder warps
+        // sit this tile out (a stage's wake -> arrive hop through them is latency on every k-block); both barriers still see one phase
+        // per use so that the parities of a mixed group stay in step
+        const bool direct = !TS && NCTA == 1 && a_pre && (flags & TC_B_PRE) && !(flags & TC_A_RELU);
         for (int kb = kb0; kb < kb1; ++kb, ++kbg) {
           const uint32_t s = kbg % (uint32_t)nst;
           if (kbg >= (uint32_t)nst) tc_mbar_wait(&bar_empty[s], ((kbg / (uint32_t)nst) - 1u) & 1u);
-          tc_mbar_expect_tx(&bar_raw[s], tx_bytes);
+          uint64_t* land = direct ? &bar_ready[s] : &bar_raw[s];
+          tc_mbar_expect_tx(land, tx_bytes);
+          if (direct) {
+            for (int e = 1; e < 4; ++e) tc_mbar_arrive(&bar_ready[s]);   // the builder warps' arrivals
+            tc_mbar_arrive(&bar_raw[s]);
+          }
           const uint32_t st = smem_base + s * stage_bytes;
           const bool second = kb >= nk1;
           const int kc = (second ? kb - nk1 : kb) * TC_BK;
-          tc_tma_load_2d(st, second ? &d->mapA2 : &d->mapA, &bar_raw[s], kc, m0);
-          tc_tma_load_2d(st + b_off, second ? &d->mapB2 : &d->mapB, &bar_raw[s], kc, n0);
-          if (a_pre) tc_tma_load_2d(st + half_bytes, second ? &d->mapA2lo : &d->mapAlo, &bar_raw[s], kc, m0);
-          if (flags & TC_B_PRE) tc_tma_load_2d(st + blo_off, second ? &d->mapB2lo : &d->mapBlo, &bar_raw[s], kc, n0);
+          tc_tma_load_2d(st, second ? &d->mapA2 : &d->mapA, land, kc, m0);
+          tc_tma_load_2d(st + b_off, second ? &d->mapB2 : &d->mapB, land, kc, n0);
+          if (a_pre) tc_tma_load_2d(st + half_bytes, second ? &d->mapA2lo : &d->mapAlo, land, kc, m0);
+          if (flags & TC_B_PRE) tc_tma_load_2d(st + blo_off, second ? &d->mapB2lo : &d->mapBlo, land, kc, n0);
         }
       }
     }
@@ -508,7 +517,9 @@ __device__ __forceinline__ void tc_gemm_roles(const TcGemmDesc* descs, const TcL
       float* __restrict__ CT_lo = d->CT_lo;
       const int ldct = d->ldct;
       const bool build_a = !TS && !(flags & (TC_A_PRE | TC_DBG_NOBUILD)), build_b = !(flags & (TC_B_PRE | TC_DBG_NOBUILD));
-      for (int kb = 0; kb < (grp == 0 ? nk : 0); ++kb, ++kbg) {   // (the helper group only takes part in the epilogue)
+      const bool direct = !TS && NCTA == 1 && (flags & TC_A_PRE) && (flags & TC_B_PRE) && !(flags & TC_A_RELU);   // see the producer
+      if (direct) kbg += (uint32_t)nk;
+      for (int kb = 0; kb < ((grp == 0 && !direct) ? nk : 0); ++kb, ++kbg) {   // (the helper groups only take part in the epilogue)
         const uint32_t s = kbg % (uint32_t)nst;
         tc_mbar_wait(&bar_raw[s], (kbg / (uint32_t)nst) & 1u);
         const float4* raw = reinterpret_cast<const float4*>(smem_gen + (size_t)s * stage_bytes);
