@@ -189,7 +189,7 @@ struct Builder {
   bool force_simt = false;   // inference plans: a handful of rows, the fp32 CUDA-core kernel
   bool tc_ok(const GemmDesc& g) const {
     if (force_simt) return false;
-    if (h->cfg.mlp_mode != FB_MLP_TCGEN05 || (g.flags & GF_SHARED_C) || g.K < 8) return false;
+    if (h->cfg.mlp_mode != FB_MLP_TCGEN05 || (g.flags & GF_SHARED_C) || g.K < 4) return false;
     // a first-layer product (K = obs + action / z, tens of columns): its weight is staged anyway (pre-split lo plane, early on
     // the side lane); only an activation operand that would need a late staging launch keeps it on the SIMT kernel
     const bool a_direct = g.a_kmajor && aligned16(g.A) && g.lda % 4 == 0;
