@@ -834,7 +834,7 @@ static int build_plan(fb_handle* h) {
     }
     unsigned int* keys = h->d_perm_keys; int* perm = h->d_perm;
     b.push([keys, perm, B, sc](cudaStream_t s) {
-      fb_launch_pdl(k_randperm, dim3(fb_ceil_div(B, 256)), dim3(256), (size_t)B * sizeof(unsigned int), s, keys, B, perm, sc);
+      fb_launch_pdl(k_randperm, dim3(fb_ceil_div(8 * B, 256)), dim3(256), (size_t)B * sizeof(unsigned int), s, keys, B, perm, sc);
       return cudaGetLastError();
     });
   }

@@ -305,33 +305,45 @@ __global__ void __launch_bounds__(256) k_rng_draw(RngParams P, const DevScalars*
   }
 }
 
-// random permutation of [0, n) = argsort of n random keys (torch.randperm, fb_ddpg.py:467): every thread ranks one
-// (key, index) pair against all others held in shared memory (no dependent sort network: one pass, any number of CTAs).
-// The thread that owns pair 0 also bumps the RNG counter (the draws of this step are done: k_rng_draw ran before).
+// random permutation of [0, n) = argsort of n random keys (torch.randperm, fb_ddpg.py:467): every (key, index) pair is ranked against
+// all others held in shared memory (no dependent sort network: one pass, any number of CTAs).  EIGHT lanes share a pair, each scanning
+// every eighth 16-byte group of the key table (one thread per pair was a 2 500-instruction serial loop at batch 1024: 13 us at the very
+// start of every step, in front of the replay gather).  The lane group that owns pair 0 also bumps the RNG counter (the draws of this
+// step are done: k_rng_draw ran before).  Launch with ceil(8 n / 256) CTAs.
 __global__ void __launch_bounds__(256) k_randperm(const unsigned int* __restrict__ keys, int n, int* __restrict__ perm, DevScalars* sc) {
   fb_pdl_trigger();
   fb_pdl_wait();
   extern __shared__ __align__(16) unsigned int sk[];
   for (int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = keys[i];
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned int mine = sk[i];
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = gt >> 3, sub = gt & 7;
+  const bool live = i < n;
+  const unsigned int mine = live ? sk[i] : 0u;
   int rank = 0;
   const int n4 = n & ~3;
-  for (int j = 0; j < n4; j += 4) {   // 128-bit broadcast reads of the key table
-    const uint4 k = *reinterpret_cast<const uint4*>(sk + j);
-    rank += (k.x < mine || (k.x == mine && j < i)) ? 1 : 0;
-    rank += (k.y < mine || (k.y == mine && j + 1 < i)) ? 1 : 0;
-    rank += (k.z < mine || (k.z == mine && j + 2 < i)) ? 1 : 0;
-    rank += (k.w < mine || (k.w == mine && j + 3 < i)) ? 1 : 0;
+  if (live) {
+    for (int j = sub * 4; j < n4; j += 32) {   // the 8 lanes of a pair read 128 contiguous bytes: conflict-free, broadcast across pairs
+      const uint4 k = *reinterpret_cast<const uint4*>(sk + j);
+      rank += (k.x < mine || (k.x == mine && j < i)) ? 1 : 0;
+      rank += (k.y < mine || (k.y == mine && j + 1 < i)) ? 1 : 0;
+      rank += (k.z < mine || (k.z == mine && j + 2 < i)) ? 1 : 0;
+      rank += (k.w < mine || (k.w == mine && j + 3 < i)) ? 1 : 0;
+    }
+    if (sub == 0) {
+      for (int j = n4; j < n; ++j) {
+        const unsigned int k = sk[j];
+        rank += (k < mine || (k == mine && j < i)) ? 1 : 0;
+      }
+    }
   }
-  for (int j = n4; j < n; ++j) {
-    const unsigned int k = sk[j];
-    rank += (k < mine || (k == mine && j < i)) ? 1 : 0;
+  rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+  if (live && sub == 0) {
+    perm[rank] = i;
+    if (i == 0) sc->rng_counter += 1ull;
   }
-  perm[rank] = i;
-  if (i == 0) sc->rng_counter += 1ull;
 }
 
 // ---- LayerNorm + tanh ("ntanh", fb_modules.py:49-50) ------------------------------------------------
