@@ -375,3 +375,28 @@ def test_host_gather_rows_matches_reference_sample_gathers(G, future, ragged):
     # a storage the library cannot read in place (float64 field) is not adopted: the caller falls back to the object's sample()
     rep._storage["action"] = rep._storage["action"].astype(np.float64)
     assert HostStorageView.adopt(rep) is None and not view.still_valid()
+
+
+def test_draw_sample_indices_cheap_stream_has_the_same_support():
+    """rng_mode="device" draws the replay indices of a host buffer through cheaper numpy calls (exact_stream=False): same ranges and the
+    same handling of `future` as the reference's calls; ragged buffers fall back to the reference's calls themselves."""
+    from controllable_agent_b200.replay import draw_sample_indices
+    rs = np.random.default_rng(0)
+    rep = _RefLayoutHostReplay(rs, 6, 25, 4, 2, 0, 0.8)
+    np.random.seed(1)
+    ep, st, fu = draw_sample_indices(rep, 4096, exact_stream=False)
+    assert ep.min() == 0 and ep.max() == 5 and st.min() == 1 and st.max() == 25
+    assert fu is not None and (fu >= st).all() and fu.max() == 25 and (fu > st).any()
+    rep._future = 1.0
+    assert draw_sample_indices(rep, 64, exact_stream=False)[2] is None
+    # an appended episode (the length vector changes) is seen on the next draw
+    rep._episodes_length = np.concatenate([rep._episodes_length, [25]]).astype(np.int32)
+    rep._max_episodes = 7
+    ep, st, _ = draw_sample_indices(rep, 4096, exact_stream=False)
+    assert ep.max() == 6
+    ragged = _RefLayoutHostReplay(rs, 6, 25, 4, 2, 0, 1.0, ragged=True)
+    np.random.seed(2)
+    a = draw_sample_indices(ragged, 256, exact_stream=False)
+    np.random.seed(2)
+    b = draw_sample_indices(ragged, 256, exact_stream=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and (a[1] <= ragged._episodes_length[a[0]]).all()
