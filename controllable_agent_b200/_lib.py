@@ -19,7 +19,7 @@ CONTRACT_TCGEN05, CONTRACT_SIMT = 0, 1
 MLP_TCGEN05, MLP_SIMT = 0, 1
 HEADER = os.path.join(ROOT, "include", "fb_b200.h")
 
-FB_ABI_VERSION = 5
+FB_ABI_VERSION = 6
 FB_OK = 0
 
 NET_FORWARD, NET_BACKWARD, NET_ACTOR = 0, 1, 2
@@ -66,7 +66,8 @@ class fb_config(C.Structure):
 
 class fb_host_storage(C.Structure):
     _fields_ = [("observation", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p), ("discount", C.c_void_p), ("goal", C.c_void_p),
-                ("rows_per_episode", C.c_int32), ("obs_dim", C.c_int32), ("action_dim", C.c_int32), ("goal_dim", C.c_int32)]
+                ("rows_per_episode", C.c_int32), ("obs_dim", C.c_int32), ("action_dim", C.c_int32), ("goal_dim", C.c_int32),
+                ("max_episodes", C.c_int32)]
 
 
 class fb_step_scalars(C.Structure):

@@ -2332,10 +2332,10 @@ int fb_host_gather_rows(const fb_host_storage* st, const int32_t* ep_idx, const 
   const int O = st->obs_dim, A = st->action_dim, G = st->goal ? st->goal_dim : 0, R = st->rows_per_episode;
   BatchLayout L;
   make_batch_layout(L, O, A, G, 0, future_idx != nullptr);
-  if (pitch < L.pitch || O < 1 || A < 1 || R < 2) return FB_E_ARG;
+  if (pitch < L.pitch || O < 1 || A < 1 || R < 2 || st->max_episodes < 1) return FB_E_ARG;
   auto row = [R](const float* base, int dim, int ep, int t) { return base + ((size_t)ep * R + t) * dim; };
   for (int i = 0; i < batch; ++i) {   // indices first: nothing is read through a bad one
-    if (ep_idx[i] < 0 || step_idx[i] < 1 || step_idx[i] >= R) return FB_E_ARG;
+    if (ep_idx[i] < 0 || ep_idx[i] >= st->max_episodes || step_idx[i] < 1 || step_idx[i] >= R) return FB_E_ARG;
     if (future_idx && (future_idx[i] < 1 || future_idx[i] > R)) return FB_E_ARG;
   }
   // The rows are random ~100-byte reads of a buffer far larger than the caches: the copy is bound by how many misses are in flight.

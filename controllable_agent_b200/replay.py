@@ -184,7 +184,7 @@ class HostStorageView:
         self.c = L.fb_host_storage(observation=ptr("observation"), action=ptr("action"), reward=ptr("reward"), discount=ptr("discount"),
                                    goal=ptr("goal"), rows_per_episode=R, obs_dim=self.arrays["observation"].shape[2],
                                    action_dim=self.arrays["action"].shape[2],
-                                   goal_dim=self.arrays["goal"].shape[2] if "goal" in self.arrays else 0)
+                                   goal_dim=self.arrays["goal"].shape[2] if "goal" in self.arrays else 0, max_episodes=E)
         self.key = tuple((k, v.ctypes.data, v.shape) for k, v in self.arrays.items())
 
     @classmethod

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 5
+#define FB_ABI_VERSION 6
 
 enum {
   FB_OK = 0,
@@ -255,6 +255,7 @@ int fb_upload_batch(fb_handle* h, const float* h_rows, int pitch, void* stream);
 typedef struct fb_host_storage {
   const float* observation; const float* action; const float* reward; const float* discount; const float* goal;
   int32_t rows_per_episode, obs_dim, action_dim, goal_dim;
+  int32_t max_episodes;   /* first dimension of every array: episode indices are checked against it */
 } fb_host_storage;
 /* ReplayBuffer.sample's gathers (in_memory_replay_buffer.py:162-183) for host storage, straight into the packed rows fb_upload_batch
  * takes (h_rows [batch, pitch], fb_batch_row_layout(obs, action, goal_dim or 0, 0, h_future_idx != NULL) order): row i reads

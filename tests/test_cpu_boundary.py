@@ -372,6 +372,10 @@ def test_host_gather_rows_matches_reference_sample_gathers(G, future, ragged):
     # out-of-range steps are refused, not read
     bad = st32.copy(); bad[0] = 0
     assert lib.fb_host_gather_rows(C.byref(view.c), ep32.ctypes.data, bad.ctypes.data, None, B, 0.98, rows.ctypes.data, pitch.value) == -1
+    for bad_ep in (-1, view.c.max_episodes):   # and so are episode indices outside the storage
+        bad = ep32.copy(); bad[-1] = bad_ep
+        assert lib.fb_host_gather_rows(C.byref(view.c), bad.ctypes.data, st32.ctypes.data, None, B, 0.98, rows.ctypes.data, pitch.value) == -1
+    assert view.c.max_episodes == S["observation"].shape[0]
     # a storage the library cannot read in place (float64 field) is not adopted: the caller falls back to the object's sample()
     rep._storage["action"] = rep._storage["action"].astype(np.float64)
     assert HostStorageView.adopt(rep) is None and not view.still_valid()
