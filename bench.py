@@ -357,6 +357,28 @@ def parity_check(agent, a: argparse.Namespace, world: int, rank: int, dev) -> di
     return res
 
 
+def profile_traffic(kernel: str, csv_path: str = "profiles/r2_ncu_key_metrics.csv") -> dict | None:
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of one step (dram__bytes_read.sum +
+    dram__bytes_write.sum averaged over its launches); bench.py itself cannot read DRAM counters.  None when the file is absent."""
+    import csv
+    path = os.path.join(ROOT, csv_path)
+    try:
+        with open(path, newline="") as f:
+            rows = list(csv.reader(f))
+        col = {name: i for i, name in enumerate(rows[0])}
+        rd, wr = col["dram__bytes_read.sum"], col["dram__bytes_write.sum"]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        picked = [r for r in rows[2:] if kernel in r[0]]
+        if not picked:
+            return None
+        total = sum(float(r[rd]) * scale[rows[1][rd]] + float(r[wr]) * scale[rows[1][wr]] for r in picked)
+        return {"bytes_per_launch": total / len(picked), "launches": len(picked),
+                "source": f"{csv_path} (ncu --set full of one step at an earlier commit of this round, not this run: dram__bytes_read.sum + "
+                          f"dram__bytes_write.sum averaged over the step's {len(picked)} {kernel} launches)"}
+    except (OSError, KeyError, ValueError, IndexError):
+        return None
+
+
 def run_ours(a: argparse.Namespace) -> None:
     import numpy as np
     import torch
@@ -521,13 +543,12 @@ def run_ours(a: argparse.Namespace) -> None:
             gk = by_kind["gemm_tc"]
             achieved = gk["flops"] / (gk["ms"] * 1e-3) / 1e12
             peak = burst / 6.0
+            tp_ = profile_traffic("k_gemm_tc")
             roofline = {"kernel": "k_gemm_tc (tcgen05 kind::tf32, 3xTF32 split, TMA + TMEM): all wide nn.Linear forward / dX / dW products",
                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                         "peak_sustained": sustained / 6.0, "frac_of_sustained": achieved / (sustained / 6.0),
-                        # not measured in this run: bench.py cannot read DRAM counters; the committed ncu --set full capture holds them
-                        "traffic": None,
-                        "traffic_from_profile": {"bytes_per_launch": 19.66e6, "source": "profiles/r1d_ncu_key_metrics.csv (dram__bytes_read.sum + "
-                                                 "dram__bytes_write.sum averaged over a step's k_gemm_tc launches; an earlier capture, not this run)"},
+                        # not measured in this run: bench.py cannot read DRAM counters; read from the committed ncu --set full capture
+                        "traffic": tp_["bytes_per_launch"] if tp_ else None, "traffic_from_profile": tp_,
                         "algorithmic_bytes_per_launch": gk["bytes"] / gk["launches"],
                         "peak_source": f"{src} = {burst:.1f} TFLOP/s dense bf16; /2 for tf32, /3 for the three chains of an fp32-grade product "
                                        "(achieved counts each algorithmic fp32 FLOP once); timing = CUDA events around each eager launch "
